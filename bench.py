@@ -1,0 +1,468 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the batched Clifford-algebra hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+Default workload = BASELINE.json configs[1]: PGA Cl(3,0,1) motor sandwich applied to 2^28 points,
+f32, dense 16-blade rows (128 algorithmic bytes per point: 64 read + 64 written).  A "step" is one
+pass of the sandwich kernel over the whole device-resident batch.  For N > 1 (torchrun, one process
+per GPU) every rank owns its own 2^28-point shard (weak scaling, no data-path collective); timing is
+bracketed by a barrier + synchronize and the MAX over ranks is reported.
+
+One JSON line on stdout (rank 0):
+  value       points/s with inputs already resident in HBM (CUDA events on the launching stream)
+  e2e         the same metric through the C-ABI host-buffer entry point lcc_host_sandwich: pinned HOST
+              buffers in the reference's (N, 16) layout, H2D and D2H copies inside the timed region
+  roofline    algorithmic bytes / kernel time against the measured HBM peak (MEASURED_PEAKS.json)
+  cpu_baseline  the oracle port of the reference's Rust loop timed on this box's host cores
+`--impl reference` times only that CPU implementation (bounded sample per step) and prints the same
+line shape with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (signature, dtype, log2 rows, algorithmic bytes per unit, unit)
+    "pga_sandwich": ((3, 0, 1), "f32", 28, 128, "points/s"),
+    "cga_gp": ((4, 1, 0), "f64", 26, 768, "products/s"),
+    "cga_gp_outer": ((4, 1, 0), "f64", 26, 1024, "products/s"),
+    "r3_gp": ((3, 0, 0), "f64", 20, 192, "products/s"),
+    "sta_grade_inner_sum": ((1, 3, 0), "f64", 27, 256 + 384 + 128, "multivectors/s"),
+}
+HEADLINE = "pga_sandwich"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+# --------------------------------------------------------------------------------------------- motor (BASELINE cfg2)
+def headline_motor():
+    """M = T(4,5,6) * R(axis (1,2,3) through (0.5,-0.25,1), theta 0.7), built in f64 from the
+    formulas of src/pga.rs:287-345,386-389 (the product T*R expanded by hand for a translator)."""
+    axis = np.array([1.0, 2.0, 3.0])
+    axis /= np.linalg.norm(axis)
+    p = np.array([0.5, -0.25, 1.0])
+    c, s = np.cos(0.35), np.sin(0.35)
+    R = np.zeros(16)
+    R[0], R[6], R[5], R[3] = c, -s * axis[0], s * axis[1], -s * axis[2]
+    mom = np.cross(p, axis)
+    R[9], R[10], R[12] = s * mom[0], s * mom[1], s * mom[2]
+    T = np.zeros(16)
+    T[0], T[9], T[10], T[12] = 1.0, 2.0, 2.5, 3.0
+    import oracle  # used here only to compose two constants; not on any timed path
+
+    return oracle.OracleAlgebra(3, 0, 1).geometric_product(T[None, :], R[None, :])[0]
+
+
+# --------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs (NVML)."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self._stop = index, [], set(), threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self.nv:
+            self.t.join(timeout=1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_rate(workload, sample_rows, threads, repeats=1):
+    """Oracle port of the reference loop on `sample_rows` rows of the same synthetic workload."""
+    import oracle
+
+    sig, dt, _, _, _ = WORKLOADS[workload]
+    o = oracle.OracleAlgebra(*sig)
+    ndt = np.float32 if dt == "f32" else np.float64
+    rng = np.random.default_rng(42)
+    nb = o.num_blades
+    if workload == "pga_sandwich":
+        pts = rng.standard_normal((sample_rows, 3)).astype(ndt)
+        x = np.zeros((sample_rows, 16), ndt)
+        x[:, 7], x[:, 14], x[:, 13], x[:, 11] = 1.0, -pts[:, 0], pts[:, 1], -pts[:, 2]
+        motor = headline_motor()
+        fn = lambda: o.sandwich(motor, x, threads=threads)  # noqa: E731
+    else:
+        a = rng.standard_normal((sample_rows, nb)).astype(ndt)
+        b = rng.standard_normal((sample_rows, nb)).astype(ndt)
+        if workload == "cga_gp_outer":
+            fn = lambda: (o.geometric_product(a, b, threads=threads), o.outer_product(a, b, threads=threads))  # noqa: E731
+        elif workload == "sta_grade_inner_sum":
+            fn = lambda: o.sum(o.left_contraction(o.grade(a, 1), b, threads=threads))  # noqa: E731
+        else:
+            fn = lambda: o.geometric_product(a, b, threads=threads)  # noqa: E731
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        fn()
+        dtm = time.perf_counter() - t0
+        best = dtm if best is None else min(best, dtm)
+    return sample_rows / best, best
+
+
+def cpu_sample_rows(workload):
+    return {"pga_sandwich": 1 << 25, "cga_gp": 1 << 22, "cga_gp_outer": 1 << 22, "r3_gp": 1 << 20, "sta_grade_inner_sum": 1 << 23}[workload]
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the reference's own CPU implementation of the path (oracle port of the Rust
+    loops -- the crate itself cannot be built here) on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle
+
+    wl = args.workload
+    sig, dt, log2n, bytes_per, unit = WORKLOADS[wl]
+    threads = args.cpu_threads or 1
+    rows = max(1 << 16, cpu_sample_rows(wl) // 4)  # per-step sample, bounded so K steps end within minutes
+    for _ in range(min(args.warmup, 1)):
+        cpu_rate(wl, 1 << 16, threads)
+    times = []
+    for _ in range(args.steps):
+        _, t = cpu_rate(wl, rows, threads)
+        times.append(t)
+    ms = 1e3 * float(np.mean(times))
+    value = rows / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": f"{wl} throughput", "value": value, "unit": unit, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": dt, "data": "synthetic",
+        "config": {"workload": workload_name(wl), "sample_rows_per_step": rows},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port",
+                         "sample": f"{rows} rows per step of the same synthetic workload; the reference is single-threaded (GIL held, no threads)",
+                         "host_threads_available": oracle.max_threads()},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_name(wl):
+    sig, dt, log2n, _, _ = WORKLOADS[wl]
+    desc = {
+        "pga_sandwich": "PGA Cl(3,0,1) motor sandwich", "cga_gp": "CGA Cl(4,1,0) batched geometric product",
+        "cga_gp_outer": "CGA Cl(4,1,0) fused geometric + outer product", "r3_gp": "Cl(3,0,0) batched geometric product",
+        "sta_grade_inner_sum": "STA Cl(1,3,0) grade projection + inner product + batch sum",
+    }[wl]
+    return f"{desc}, 2^{log2n} rows per GPU, {dt}, {1 << sum(sig)} blades"
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from largecrimsoncanine_b200 import cabi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the batched path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = cabi.lib()
+    cabi.check(lib.lcc_set_device(local))
+
+    wl = args.workload
+    sig, dt, log2n, bytes_per, unit = WORKLOADS[wl]
+    if args.log2_rows:
+        log2n = args.log2_rows
+    n = 1 << log2n
+    tdt = torch.float32 if dt == "f32" else torch.float64
+    code = cabi.LCC_F32 if dt == "f32" else cabi.LCC_F64
+    alg = cabi.Algebra(*sig)
+    nb = alg.num_blades
+    flags = cabi.LCC_FLAG_STRICT_FP if args.strict else 0
+    # a dedicated non-default stream: its handle is non-zero (NULL would mean "the library's own stream"),
+    # kernels are launched on it and the CUDA events below are recorded on it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    sptr = C.c_void_p(stream.cuda_stream)
+    assert stream.cuda_stream != 0
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(42 + rank)
+
+    def soa(t):  # torch (nb, n) tensor == engine-native SoA view with ld = n
+        return cabi.view(t.data_ptr(), t.shape[1], t.stride(0), code, cabi.LCC_SOA)
+
+    motor = None
+    if wl == "pga_sandwich":
+        x = torch.zeros((nb, n), device=dev, dtype=tdt)
+        pts = torch.randn((3, n), device=dev, dtype=tdt, generator=gen)
+        x[7].fill_(1.0)
+        x[14].copy_(-pts[0]); x[13].copy_(pts[1]); x[11].copy_(-pts[2])
+        del pts
+        out = torch.empty_like(x)
+        motor = headline_motor()
+        mptr = motor.ctypes.data_as(C.POINTER(C.c_double))
+        vx, vo = soa(x), soa(out)
+
+        def step():
+            cabi.check(lib.lcc_batch_sandwich(alg.h, mptr, C.byref(vx), C.byref(vo), flags, sptr))
+    elif wl in ("cga_gp", "r3_gp", "cga_gp_outer"):
+        a = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
+        b = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
+        out = torch.empty_like(a)
+        va, vb, vo = soa(a), soa(b), soa(out)
+        if wl == "cga_gp_outer":
+            out2 = torch.empty_like(a)
+            vo2 = soa(out2)
+
+            def step():
+                cabi.check(lib.lcc_batch_gp_outer(alg.h, C.byref(va), C.byref(vb), C.byref(vo), C.byref(vo2), flags, sptr))
+        else:
+            def step():
+                cabi.check(lib.lcc_batch_product(alg.h, cabi.LCC_OP_GP, C.byref(va), C.byref(vb), C.byref(vo), flags, sptr))
+    elif wl == "sta_grade_inner_sum":
+        a = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
+        b = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
+        g1 = torch.empty_like(a)
+        out = torch.empty_like(a)
+        sums = torch.zeros(nb, device=dev, dtype=tdt)
+        va, vb, vg, vo = soa(a), soa(b), soa(g1), soa(out)
+
+        def step():
+            cabi.check(lib.lcc_batch_unary(alg.h, cabi.LCC_UN_GRADE, 1, C.byref(va), C.byref(vg), sptr))
+            cabi.check(lib.lcc_batch_product(alg.h, cabi.LCC_OP_LC, C.byref(vg), C.byref(vb), C.byref(vo), flags, sptr))
+            cabi.check(lib.lcc_batch_sum(alg.h, C.byref(vo), C.c_void_p(sums.data_ptr()), sptr))
+            if world > 1:
+                dist.all_reduce(sums)  # the one collective of the path: 16 elements over NCCL
+    else:
+        raise SystemExit(f"unknown workload {wl}")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    lib.lcc_kernel_launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        barrier()
+    launches = int(lib.lcc_kernel_launch_count())
+    elapsed_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * n / (ms_per_step / 1e3)
+
+    # ---- parity spot check against the oracle on sampled rows (outside every timed region)
+    parity = None
+    if rank == 0 and not args.no_parity:
+        import oracle
+
+        o = oracle.OracleAlgebra(*sig)
+        idx = torch.cat([torch.arange(0, 4096), torch.arange(n // 2, n // 2 + 4096), torch.arange(n - 4096, n)]).to(dev)
+        tol = 1e-5 if dt == "f32" else 1e-12
+        if wl == "pga_sandwich":
+            xs = x[:, idx].T.contiguous().cpu().numpy()
+            got = out[:, idx].T.contiguous().cpu().numpy()
+            want = o.sandwich(motor, xs)
+        elif wl == "sta_grade_inner_sum":
+            xs, ys = a[:, idx].T.contiguous().cpu().numpy(), b[:, idx].T.contiguous().cpu().numpy()
+            got = out[:, idx].T.contiguous().cpu().numpy()
+            want = o.left_contraction(o.grade(xs, 1), ys)
+        else:
+            xs, ys = a[:, idx].T.contiguous().cpu().numpy(), b[:, idx].T.contiguous().cpu().numpy()
+            got = out[:, idx].T.contiguous().cpu().numpy()
+            want = o.geometric_product(xs, ys)
+        err = float(np.abs(got.astype(np.float64) - want.astype(np.float64)).max() / np.abs(want).max())
+        parity = {"rows_checked": int(idx.numel()), "max_rel_err": err, "tolerance": tol, "ok": bool(err <= tol)}
+
+    # ---- end to end through the C-ABI host-buffer entry point (headline workload only)
+    e2e = None
+    if wl == "pga_sandwich" and not args.no_e2e:
+        e2e = measure_e2e(args, lib, alg, code, motor, n, nb, world, rank, dev, dist if world > 1 else None, flags)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks, peak_kind = load_peaks()
+    peak = float(peaks["hbm_gbs"])
+    kernel_ms = ms_per_step  # one kernel per step for the headline; the step IS the kernel
+    achieved = bytes_per * n / (kernel_ms / 1e3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(wl)
+    except Exception:
+        pass
+    cpu = None
+    if not args.no_cpu:
+        rows = cpu_sample_rows(wl)
+        rate1, t1 = cpu_rate(wl, rows, 1)
+        import oracle
+
+        cores = oracle.max_threads()
+        rate_all, _ = cpu_rate(wl, rows, cores) if cores > 1 else (rate1, t1)
+        cpu = {"value": rate1, "unit": unit, "cores": 1, "kind": "port",
+               "sample": f"{rows} rows of the same synthetic workload ({t1:.1f} s); the reference is single-threaded",
+               "all_cores_value": rate_all, "all_cores": cores}
+    line = {
+        "metric": f"{wl} throughput", "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": dt, "data": "synthetic",
+        "config": {"workload": workload_name(wl), "rows_per_gpu": n, "layout": "SoA (blade-major) in HBM",
+                   "l2_policy": "inputs larger than L2 (>= 17 GB per pass vs 126 MB L2)", "strict_fp": bool(args.strict)},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
+                     "algorithmic_bytes_per_unit": bytes_per, "frac_of_nominal_8TBs": achieved / 8000.0},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(), "parity": parity,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def measure_e2e(args, lib, alg, code, motor, n, nb, world, rank, dev, dist, flags):
+    """lcc_host_sandwich on pinned host buffers in the reference's (N, 16) row-major layout."""
+    import psutil
+    import torch
+
+    from largecrimsoncanine_b200 import cabi
+
+    es = 4 if code == cabi.LCC_F32 else 8
+    n_e2e = n
+    need = 2 * n_e2e * nb * es * max(world, 1)
+    avail = psutil.virtual_memory().available
+    while need > 0.5 * avail and n_e2e > (1 << 20):
+        n_e2e //= 2
+        need //= 2
+    tdt = torch.float32 if es == 4 else torch.float64
+    xh = torch.empty((n_e2e, nb), dtype=tdt, pin_memory=True)
+    oh = torch.empty((n_e2e, nb), dtype=tdt, pin_memory=True)
+    xh.zero_()
+    g = torch.Generator().manual_seed(7 + rank)
+    blk = 1 << 22
+    for s in range(0, n_e2e, blk):  # fill in blocks: (N,3) normals embedded as PGA points
+        e = min(n_e2e, s + blk)
+        p = torch.randn((e - s, 3), dtype=tdt, generator=g)
+        xh[s:e, 7] = 1.0
+        xh[s:e, 14], xh[s:e, 13], xh[s:e, 11] = -p[:, 0], p[:, 1], -p[:, 2]
+    mptr = motor.ctypes.data_as(C.POINTER(C.c_double))
+
+    def call():
+        cabi.check(lib.lcc_host_sandwich(alg.h, code, mptr, C.c_void_p(xh.data_ptr()), C.c_void_p(oh.data_ptr()), n_e2e, flags))
+
+    steps = max(1, min(args.steps, args.e2e_steps))
+    call()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        call()
+    torch.cuda.synchronize()
+    dt_s = time.perf_counter() - t0
+    if dist:
+        t = torch.tensor([dt_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_s = float(t.item())
+    import oracle
+
+    o = oracle.OracleAlgebra(3, 0, 1)
+    ok = bool(np.abs(oh[:2048].numpy() - o.sandwich(motor, xh[:2048].numpy())).max() <= 1e-4)
+    return {"value": world * n_e2e * steps / dt_s, "unit": "points/s", "h2d_bytes_per_step": n_e2e * nb * es,
+            "d2h_bytes_per_step": n_e2e * nb * es, "points_per_gpu": n_e2e, "steps": steps,
+            "api": "lcc_host_sandwich (C ABI, pinned host buffers, chunked H2D/kernel/D2H pipeline)",
+            "timer": "host wall clock around the blocking call, max over ranks", "checked_against_oracle": ok}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS))
+    ap.add_argument("--log2-rows", type=int, default=0, help="override rows per GPU (power of two exponent)")
+    ap.add_argument("--strict", action="store_true", help="LCC_FLAG_STRICT_FP (bit-exact, no FMA)")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="reference arm: OpenMP threads (default 1 = the reference's behaviour)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,229 @@
+/*
+ * lcc_b200.h -- C ABI of the B200-native batched Clifford-algebra engine.
+ *
+ * This is the drop-in boundary for ONE path of LargeCrimsonCanine/largecrimsoncanine: the batched
+ * products of src/batch.rs (+ the table machinery of src/algebra/ they read and the single-pair
+ * kernel of src/simd.rs).  The reference has no FFI of its own -- its boundary is the PyO3 module
+ * `largecrimsoncanine` (src/lib.rs:37-45) -- so every entry point below names the reference
+ * method it replaces (file:line relative to the reference root).  INTEGRATION.md shows the
+ * binding a maintainer would add on the Rust side (`extern "C"` block + safe wrappers).
+ *
+ * Conventions
+ *   - Plain C: pointers, sizes, enums.  No torch / numpy / C++ types cross this boundary.
+ *   - Every function returns an lcc_status; lcc_last_error() gives the thread-local message.
+ *     LCC_ERR_VALUE / LCC_ERR_INDEX / LCC_ERR_ZERODIV map to the reference's ValueError /
+ *     IndexError / ZeroDivisionError (src/batch.rs:83-88,289-295,981-985); everything CUDA is
+ *     LCC_ERR_CUDA.  There is NO CPU fallback: without a usable CUDA device every compute entry
+ *     point fails with LCC_ERR_NO_DEVICE.
+ *   - `stream` is a cudaStream_t passed as void*.  NULL means the library's own non-blocking
+ *     stream of the current device (lcc_stream()); pass cudaStreamLegacy / cudaStreamPerThread
+ *     explicitly if the default stream is wanted.  All compute calls are stream-ordered and
+ *     never synchronise the host unless the name says `_sync` or the data lands in host memory.
+ *   - Device data is described by lcc_view.  Two layouts:
+ *       LCC_SOA  structure-of-arrays, element (row r, blade k) at data[k*ld + r]   (engine native)
+ *       LCC_AOS  array-of-structures, element (row r, blade k) at data[r*ld + k]   (the reference's
+ *                `Array2<f64>` (N, num_blades) row-major layout, src/batch.rs:41-47; ld >= num_blades)
+ *     SoA buffers allocated by lcc_batch_alloc have ld rounded up so every blade row starts
+ *     16-byte aligned; rows n..ld-1 are padding and are never read by reductions.
+ *   - A view with n == 1 used as a binary operand broadcasts (src/batch.rs:361-376).
+ */
+#ifndef LCC_B200_H
+#define LCC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define LCC_API
+#else
+#define LCC_API __attribute__((visibility("default")))
+#endif
+
+typedef enum {
+    LCC_OK = 0,
+    LCC_ERR_VALUE = 1,       /* ValueError in the reference */
+    LCC_ERR_INDEX = 2,       /* IndexError */
+    LCC_ERR_ZERODIV = 3,     /* ZeroDivisionError */
+    LCC_ERR_CUDA = 4,        /* a CUDA runtime call failed */
+    LCC_ERR_NO_DEVICE = 5,   /* no CUDA device / driver: compute is refused, never emulated */
+    LCC_ERR_UNSUPPORTED = 6, /* valid request this build has no kernel for */
+    LCC_ERR_ALLOC = 7
+} lcc_status;
+
+typedef enum { LCC_F32 = 0, LCC_F64 = 1 } lcc_dtype;
+typedef enum { LCC_SOA = 0, LCC_AOS = 1 } lcc_layout;
+
+/* Binary products, src/batch.rs:353-410 (geometric), 514-574 (outer), 585-655 (left contraction). */
+typedef enum { LCC_OP_GP = 0, LCC_OP_OUTER = 1, LCC_OP_LC = 2 } lcc_product_op;
+
+/* Row-wise unary maps.  REVERSE / INVOLUTE: src/batch.rs:823-860.  GRADE: batch.rs:1027-1052 (arg = k).
+ * CONJUGATE: src/algebra/blades.rs:182-188.  DUAL / UNDUAL / RIGHT_DUAL: src/multivector.rs:4249-4290
+ * (batched form is new surface; LCC_ERR_VALUE when the pseudoscalar is null, as the reference raises).
+ * PGA_DUAL: src/pga.rs:521-556.  EVEN / ODD: lcc/torch/multivector.py:766-780.  COPY: identity. */
+typedef enum {
+    LCC_UN_REVERSE = 0, LCC_UN_INVOLUTE = 1, LCC_UN_CONJUGATE = 2, LCC_UN_GRADE = 3,
+    LCC_UN_DUAL = 4, LCC_UN_UNDUAL = 5, LCC_UN_RIGHT_DUAL = 6, LCC_UN_PGA_DUAL = 7,
+    LCC_UN_EVEN = 8, LCC_UN_ODD = 9, LCC_UN_COPY = 10
+} lcc_unary_op;
+
+/* src/batch.rs:863-954 */
+typedef enum { LCC_EW_ADD = 0, LCC_EW_SUB = 1 } lcc_elementwise_op;
+
+/* src/batch.rs:677-817 */
+typedef enum { LCC_NORM_SQUARED = 0, LCC_NORM = 1 } lcc_norm_kind;
+
+/* Flags for compute calls. */
+enum {
+    /* Reproduce the reference's rounding sequence exactly: separate multiply and add, left blade
+     * ascending (Rust never contracts to FMA).  Default (0) uses FMA in the same term order. */
+    LCC_FLAG_STRICT_FP = 1
+};
+
+typedef struct lcc_algebra lcc_algebra; /* opaque; replaces Arc<Algebra>, src/algebra/registry.rs:36-49 */
+
+typedef struct {
+    void *data;     /* device pointer */
+    int64_t n;      /* rows (multivectors) */
+    int64_t ld;     /* SoA: elements between consecutive blades; AoS: elements between consecutive rows */
+    int32_t dtype;  /* lcc_dtype */
+    int32_t layout; /* lcc_layout */
+} lcc_view;
+
+/* ---------------------------------------------------------------- library / device */
+
+LCC_API const char *lcc_version(void);            /* src/lib.rs:40 (__version__) */
+LCC_API const char *lcc_last_error(void);         /* thread-local message of the last failing call */
+LCC_API lcc_status lcc_device_count(int *count);  /* LCC_ERR_NO_DEVICE when there is none */
+LCC_API lcc_status lcc_set_device(int device);
+LCC_API lcc_status lcc_get_device(int *device);
+LCC_API lcc_status lcc_stream(void **stream);     /* the library's stream on the current device */
+LCC_API lcc_status lcc_stream_sync(void *stream);
+
+/* ---------------------------------------------------------------- algebra (host side, no GPU needed) */
+
+/* Algebra::new, src/algebra/registry.rs:70-81; PyAlgebra::new, src/pyalgebra.rs:53-60.  n = p+q+r <= 8. */
+LCC_API lcc_status lcc_algebra_create(int p, int q, int r, lcc_algebra **out);
+LCC_API void lcc_algebra_destroy(lcc_algebra *alg);
+LCC_API int lcc_algebra_p(const lcc_algebra *alg);          /* src/pyalgebra.rs:141-157 */
+LCC_API int lcc_algebra_q(const lcc_algebra *alg);
+LCC_API int lcc_algebra_r(const lcc_algebra *alg);
+LCC_API int lcc_algebra_dimension(const lcc_algebra *alg);  /* src/pyalgebra.rs:129-133 */
+LCC_API int lcc_algebra_num_blades(const lcc_algebra *alg); /* src/pyalgebra.rs:135-139 */
+/* Flat Cayley tables [a*nb+b]: registry.rs:192-202 (signs as int8 in {-1,0,+1}; blades as uint16). */
+LCC_API const int8_t *lcc_algebra_cayley_signs(const lcc_algebra *alg);
+LCC_API const uint16_t *lcc_algebra_cayley_blades(const lcc_algebra *alg);
+/* Grade masks, blades.rs:211-229 / registry.rs:224-232: one bit per blade, ceil(nb/64) words per
+ * grade (the reference's single usize is words==1, i.e. dimension <= 6).  Returns words per grade. */
+LCC_API int lcc_algebra_grade_mask(const lcc_algebra *alg, int grade, uint64_t *words, int capacity);
+/* blade_name, blades.rs:48-61; writes a NUL-terminated name, returns its length (or -1). */
+LCC_API int lcc_algebra_blade_name(const lcc_algebra *alg, int index, char *buf, int capacity);
+/* 1 when this build carries kernels specialised at build time for the signature (generated Cayley
+ * term lists); 0 when it will run the generic run-time-metric kernels. */
+LCC_API int lcc_algebra_is_specialised(const lcc_algebra *alg);
+/* blades.rs:128-188 -- +1 / -1 for a blade index */
+LCC_API int lcc_reverse_sign(int blade_index);
+LCC_API int lcc_grade_involution_sign(int blade_index);
+LCC_API int lcc_clifford_conjugate_sign(int blade_index);
+
+/* ---------------------------------------------------------------- device memory (stream-ordered pool) */
+
+LCC_API lcc_status lcc_device_alloc(void **ptr, size_t bytes, void *stream);
+LCC_API lcc_status lcc_device_free(void *ptr, void *stream);
+LCC_API lcc_status lcc_host_alloc_pinned(void **ptr, size_t bytes);
+LCC_API lcc_status lcc_host_free_pinned(void *ptr);
+LCC_API lcc_status lcc_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
+LCC_API lcc_status lcc_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+LCC_API lcc_status lcc_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream);
+LCC_API lcc_status lcc_memset_zero(void *dst, size_t bytes, void *stream);
+/* Allocate an engine-native SoA batch of n rows for `alg`; fills view (ld is padded). */
+LCC_API lcc_status lcc_batch_alloc(const lcc_algebra *alg, int dtype, int64_t n, lcc_view *view, void *stream);
+LCC_API lcc_status lcc_batch_free(lcc_view *view, void *stream);
+
+/* ---------------------------------------------------------------- layout conversion (K7) */
+
+/* Copy between any two views of equal n and dtype (AoS<->SoA transposes, SoA->SoA, AoS->AoS).
+ * Replaces the host copies of from_numpy / to_numpy, src/batch.rs:79-94,233-235. */
+LCC_API lcc_status lcc_batch_convert(const lcc_algebra *alg, const lcc_view *src, const lcc_view *dst, void *stream);
+/* Scatter `ncols` dense columns (AoS (n, ncols) device array, row stride = ncols) to the listed
+ * blades of a zero-filled batch: from_vectors / from_scalars / from_bivectors, batch.rs:112-221. */
+LCC_API lcc_status lcc_batch_scatter_columns(const lcc_algebra *alg, const void *cols, int ncols,
+                                             const int32_t *blade_of_col, const lcc_view *dst, void *stream);
+/* Inverse gather: to_vector_coords / scalar, batch.rs:248-261,1017-1024. */
+LCC_API lcc_status lcc_batch_gather_columns(const lcc_algebra *alg, const lcc_view *src, int ncols,
+                                            const int32_t *blade_of_col, void *cols, void *stream);
+/* Rows [start, end) of src into dst rows [dst_start, ...): slice / concat / get / set,
+ * batch.rs:288-335,1055-1097. */
+LCC_API lcc_status lcc_batch_copy_rows(const lcc_algebra *alg, const lcc_view *src, int64_t start, int64_t end,
+                                       const lcc_view *dst, int64_t dst_start, void *stream);
+
+/* ---------------------------------------------------------------- the hot path */
+
+/* out = a (op) b row by row; a.n == b.n or either == 1 (broadcast).  batch.rs:353-410,514-574,585-655.
+ * All three views share dtype and layout.  out.n must equal max(a.n, b.n). */
+LCC_API lcc_status lcc_batch_product(const lcc_algebra *alg, int op, const lcc_view *a, const lcc_view *b,
+                                     const lcc_view *out, unsigned flags, void *stream);
+/* Fused dual-output: gp_out = a*b and outer_out = a^b reading a and b once (BASELINE config 3). */
+LCC_API lcc_status lcc_batch_gp_outer(const lcc_algebra *alg, const lcc_view *a, const lcc_view *b,
+                                      const lcc_view *gp_out, const lcc_view *outer_out, unsigned flags, void *stream);
+/* out[row] = R * x[row] * ~R with one rotor/motor (host array of num_blades doubles) for the whole
+ * batch, two rounded stages as in batch.rs:434-503. */
+LCC_API lcc_status lcc_batch_sandwich(const lcc_algebra *alg, const double *rotor, const lcc_view *x,
+                                      const lcc_view *out, unsigned flags, void *stream);
+/* Per-row rotors (rotors.n == x.n): lcc/torch/multivector.py:988-1019. */
+LCC_API lcc_status lcc_batch_sandwich_rows(const lcc_algebra *alg, const lcc_view *rotors, const lcc_view *x,
+                                           const lcc_view *out, unsigned flags, void *stream);
+/* Signed permutations / masks, see lcc_unary_op.  `arg` is the grade for LCC_UN_GRADE. */
+LCC_API lcc_status lcc_batch_unary(const lcc_algebra *alg, int op, int arg, const lcc_view *x,
+                                   const lcc_view *out, void *stream);
+/* out = x * factor (batch.rs:957-962); division is the caller's scale(1.0/s) (batch.rs:980-987). */
+LCC_API lcc_status lcc_batch_scale(const lcc_algebra *alg, const lcc_view *x, double factor,
+                                   const lcc_view *out, void *stream);
+/* out = a +/- b with the size-1 broadcast, batch.rs:863-954. */
+LCC_API lcc_status lcc_batch_elementwise(const lcc_algebra *alg, int op, const lcc_view *a, const lcc_view *b,
+                                         const lcc_view *out, void *stream);
+/* norms[row] (device array of n elements of x's dtype): batch.rs:677-762. */
+LCC_API lcc_status lcc_batch_norm(const lcc_algebra *alg, int kind, const lcc_view *x, void *norms,
+                                  unsigned flags, void *stream);
+/* Rows with norm > 1e-14 divided by their norm, others copied: batch.rs:770-817. */
+LCC_API lcc_status lcc_batch_normalized(const lcc_algebra *alg, const lcc_view *x, const lcc_view *out,
+                                        unsigned flags, void *stream);
+/* Column sums over the batch: sums_dev[k] = sum_r x[r][k] (num_blades elements of x's dtype on the
+ * device; NEW surface -- the per-GPU partial that precedes the NCCL all-reduce).  Fixed reduction
+ * tree: the result does not depend on timing. */
+LCC_API lcc_status lcc_batch_sum(const lcc_algebra *alg, const lcc_view *x, void *sums_dev, void *stream);
+
+/* ---------------------------------------------------------------- PGA / CGA / STA specialisations */
+
+/* Batched embeddings of src/pga.rs:131-134 (pga_point), src/cga.rs:189-206 (cga_point),
+ * src/sta.rs:105-109 (sta_vector) and the matching extractors pga.rs:579-599, cga.rs:492-508.
+ * xyz / txyz are dense AoS device arrays (n,3) or (n,4) of dst's dtype. */
+LCC_API lcc_status lcc_pga_points_embed(const lcc_algebra *alg, const void *xyz, const lcc_view *dst, void *stream);
+LCC_API lcc_status lcc_pga_points_extract(const lcc_algebra *alg, const lcc_view *src, void *xyz, void *stream);
+LCC_API lcc_status lcc_cga_points_embed(const lcc_algebra *alg, const void *xyz, const lcc_view *dst, void *stream);
+LCC_API lcc_status lcc_cga_points_extract(const lcc_algebra *alg, const lcc_view *src, void *xyz, void *stream);
+/* ---------------------------------------------------------------- host-buffer (end-to-end) entry points */
+
+/* Same operations with HOST buffers in the reference's (n, num_blades) row-major layout: the
+ * library chunks the batch, overlaps H2D copy / kernel / D2H copy on three streams and returns
+ * when `out` is complete.  Pinned buffers (lcc_host_alloc_pinned) run at PCIe speed; pageable
+ * ones work but are staged by the driver.  These are what from_numpy -> op -> to_numpy costs. */
+LCC_API lcc_status lcc_host_sandwich(const lcc_algebra *alg, int dtype, const double *rotor, const void *x_host,
+                                     void *out_host, int64_t n, unsigned flags);
+LCC_API lcc_status lcc_host_product(const lcc_algebra *alg, int dtype, int op, const void *a_host, int64_t na,
+                                    const void *b_host, int64_t nb_rows, void *out_host, unsigned flags);
+
+/* ---------------------------------------------------------------- instrumentation */
+
+/* Number of kernels this library has launched on this thread's behalf since the last reset
+ * (bench.py reports it as gpu_launches). */
+LCC_API uint64_t lcc_kernel_launch_count(void);
+LCC_API void lcc_kernel_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LCC_B200_H */

@@ -1,0 +1,49 @@
+// launch_args.h -- plain argument blocks handed from the C-ABI dispatcher (lcc_abi.cu) to the
+// per-signature kernel translation units.  Internal; nothing here crosses the C ABI.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace lcc {
+
+enum : int { kSoA = 0, kAoS = 1 };
+enum : int { kF32 = 0, kF64 = 1 };
+// product selector inside kernels: the three reference products + the fused dual-output form
+enum : int { kOpGP = 0, kOpOuter = 1, kOpLC = 2, kOpGPOuter = 3 };
+
+struct ProductArgs {
+    int op = kOpGP;
+    int dtype = kF64;
+    int layout = kSoA;
+    bool strict = false;
+    int64_t n = 0;  // rows of the result
+    const void *a = nullptr; int64_t lda = 0; bool a_bcast = false;
+    const void *b = nullptr; int64_t ldb = 0; bool b_bcast = false;
+    void *out = nullptr; int64_t ldo = 0;
+    void *out2 = nullptr; int64_t ldo2 = 0;  // outer-product output of the fused form
+    const double *mu = nullptr;              // run-time metric factors mu[i & j] (generic kernels only)
+    cudaStream_t stream = nullptr;
+};
+
+struct SandwichArgs {
+    int dtype = kF64;
+    int layout = kSoA;
+    bool strict = false;
+    bool even = false;  // rotor has no odd-grade part: odd blades are pruned at compile time
+    int64_t n = 0;
+    const double *rotor = nullptr;  // host, num_blades
+    const void *x = nullptr; int64_t ldx = 0;
+    void *out = nullptr; int64_t ldo = 0;
+    const double *mu = nullptr;
+    cudaStream_t stream = nullptr;
+};
+
+// Each generated translation unit exports one pair of launchers with this shape; they return
+// cudaSuccess, a launch error, or cudaErrorNotSupported when the (dtype, layout) is not built.
+using ProductLauncher = cudaError_t (*)(const ProductArgs &);
+using SandwichLauncher = cudaError_t (*)(const SandwichArgs &);
+
+// counted by every launcher (bench.py reports it as gpu_launches)
+void note_kernel_launch();
+
+}  // namespace lcc

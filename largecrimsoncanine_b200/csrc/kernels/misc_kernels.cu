@@ -1,0 +1,518 @@
+// misc_kernels.cu -- run-time-nb kernels: K3 signed permutations / masks / scale / add / sub,
+// K4 norms, K5 batch sums, K7 layout conversion, column movers, the looped product for algebras
+// above 32 blades, and the PGA/CGA point embeddings.  All are streaming, HBM-bound kernels: one
+// read and one write per element (norms: one read, 1/nb write), coalesced along rows for SoA.
+#include "common.cuh"
+#include "launch_args.h"
+#include "misc_kernels.cuh"
+
+namespace lcc {
+
+namespace {
+
+template <class T> struct VecW { static constexpr int value = 16 / (int)sizeof(T); };
+
+// AoS element index -> (row, blade); nb is a power of two
+__device__ __forceinline__ void split_index(int64_t e, int log2nb, int64_t &r, int &k) {
+    r = e >> log2nb;
+    k = (int)(e & ((1 << log2nb) - 1));
+}
+inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+inline unsigned blocks_for(int64_t items, int per_block = kThreads) { return (unsigned)((items + per_block - 1) / per_block); }
+
+// ------------------------------------------------------------------------------------------ K3
+// out[k][r] = factor[k] == 0 ? +0 : x[source[k]][r] * (factor[k] * scale)
+// reverse / grade_involution multiply by +-1.0 exactly like /root/reference/src/batch.rs:823-860;
+// grade(k) writes literal zeros like batch.rs:1038-1046; scale is batch.rs:957-962.
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+blade_map_soa(const T *__restrict__ x, int64_t ldx, T *__restrict__ out, int64_t ldo, int64_t n, const BladeMap map, T scale) {
+    constexpr int W = VecW<T>::value;
+    const int k = blockIdx.y;
+    const int64_t r0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * W;
+    if (r0 >= n) return;
+    const int f = map.factor[k];
+    T v[W];
+    if (f == 0) {
+#pragma unroll
+        for (int l = 0; l < W; ++l) v[l] = T(0);
+    } else {
+        ldg_stream(x + (int64_t)map.source[k] * ldx + r0, v);
+        const T m = (f > 0 ? scale : -scale);
+#pragma unroll
+        for (int l = 0; l < W; ++l) v[l] = mul_rn(v[l], m);
+    }
+    stg_stream(out + (int64_t)k * ldo + r0, v);
+}
+
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+blade_map_aos(const T *__restrict__ x, int64_t ldx, T *__restrict__ out, int64_t ldo, int64_t n, int log2nb,
+              const BladeMap map, T scale) {
+    const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    int64_t r; int k;
+    split_index(e, log2nb, r, k);
+    if (r >= n) return;
+    const int f = map.factor[k];
+    T v = T(0);
+    if (f != 0) v = mul_rn(__ldg(x + r * ldx + map.source[k]), f > 0 ? scale : -scale);
+    out[r * ldo + k] = v;
+}
+
+// out = a +- b with the one-row broadcast of batch.rs:863-954
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+addsub_soa(const T *__restrict__ a, int64_t lda, int a_bc, const T *__restrict__ b, int64_t ldb, int b_bc,
+           T *__restrict__ out, int64_t ldo, int64_t n, int sub) {
+    constexpr int W = VecW<T>::value;
+    const int k = blockIdx.y;
+    const int64_t r0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * W;
+    if (r0 >= n) return;
+    T va[W], vb[W];
+    if (a_bc) { T s = __ldg(a + (int64_t)k * lda);
+#pragma unroll
+        for (int l = 0; l < W; ++l) va[l] = s;
+    } else ldg_stream(a + (int64_t)k * lda + r0, va);
+    if (b_bc) { T s = __ldg(b + (int64_t)k * ldb);
+#pragma unroll
+        for (int l = 0; l < W; ++l) vb[l] = s;
+    } else ldg_stream(b + (int64_t)k * ldb + r0, vb);
+#pragma unroll
+    for (int l = 0; l < W; ++l) va[l] = sub ? va[l] - vb[l] : va[l] + vb[l];
+    stg_stream(out + (int64_t)k * ldo + r0, va);
+}
+
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+addsub_aos(const T *__restrict__ a, int64_t lda, int a_bc, const T *__restrict__ b, int64_t ldb, int b_bc,
+           T *__restrict__ out, int64_t ldo, int64_t n, int log2nb, int sub) {
+    const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    int64_t r; int k;
+    split_index(e, log2nb, r, k);
+    if (r >= n) return;
+    T va = __ldg(a + (a_bc ? 0 : r * lda) + k), vb = __ldg(b + (b_bc ? 0 : r * ldb) + k);
+    out[r * ldo + k] = sub ? va - vb : va + vb;
+}
+
+// ------------------------------------------------------------------------------------------ K4
+// norm^2[r] = sum_k w[k] * x[r][k]^2, k ascending, w[k] = sign[k][k]*reverse_sign(k): the scalar part
+// of x*~x that batch.rs:685-711 reaches through its double loop (only j == i lands on blade 0).
+struct Weights { int8_t w[256]; };
+
+template <class T, bool STRICT, int LAYOUT>
+__global__ void __launch_bounds__(kThreads)
+norm_kernel(const T *__restrict__ x, int64_t ldx, int64_t n, int nb, const Weights wt, int mode,
+            T *__restrict__ norms, T *__restrict__ out, int64_t ldo) {
+    const int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (r >= n) return;
+    T acc = T(0);
+    for (int k = 0; k < nb; ++k) {
+        const int w = wt.w[k];
+        if (w == 0) continue;
+        const T v = LAYOUT == kSoA ? __ldg(x + (int64_t)k * ldx + r) : __ldg(x + r * ldx + k);
+        acc = Arith<STRICT>::madd(w > 0 ? v : -v, v, acc);
+    }
+    if (mode == 0) { norms[r] = acc; return; }
+    const T nrm = sqrt_rn(acc < T(0) ? -acc : acc);
+    if (mode == 1) { norms[r] = nrm; return; }
+    const bool divide = nrm > (T)1e-14;  // batch.rs:805-811
+    for (int k = 0; k < nb; ++k) {
+        const T v = LAYOUT == kSoA ? __ldg(x + (int64_t)k * ldx + r) : __ldg(x + r * ldx + k);
+        const T o = divide ? div_rn(v, nrm) : v;
+        if (LAYOUT == kSoA) out[(int64_t)k * ldo + r] = o; else out[r * ldo + k] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K5
+// Column sums with a fixed tree: thread-sequential over a strided chunk, warp shuffle, shared
+// memory across warps, then a second pass over the per-block partials in block order.  f32 data
+// is accumulated in f64 and rounded once at the end.
+constexpr int kSumBlocksMax = 1024;
+
+__device__ __forceinline__ double block_reduce_sum(double v) {
+    __shared__ double warp_part[kThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double total = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < kThreads / 32; ++w) total += warp_part[w];
+    __syncthreads();
+    return total;  // valid on thread 0
+}
+
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+sum_partial_soa(const T *__restrict__ x, int64_t ldx, int64_t n, int64_t rows_per_block, double *__restrict__ partial) {
+    const int k = blockIdx.y;
+    const int64_t begin = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t end = begin + rows_per_block < n ? begin + rows_per_block : n;
+    double acc = 0.0;
+    for (int64_t r = begin + threadIdx.x; r < end; r += kThreads) acc += (double)__ldg(x + (int64_t)k * ldx + r);
+    const double total = block_reduce_sum(acc);
+    if (threadIdx.x == 0) partial[(int64_t)k * gridDim.x + blockIdx.x] = total;
+}
+
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+sum_partial_aos(const T *__restrict__ x, int64_t ldx, int64_t n, int nb, int64_t rows_per_block,
+                double *__restrict__ partial) {
+    __shared__ double lane_part[kThreads];
+    const int lanes = kThreads / nb;       // row lanes per blade (nb <= 256)
+    const int k = threadIdx.x % nb, lane = threadIdx.x / nb;
+    const int64_t begin = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t end = begin + rows_per_block < n ? begin + rows_per_block : n;
+    double acc = 0.0;
+    if (lane < lanes)
+        for (int64_t r = begin + lane; r < end; r += lanes) acc += (double)__ldg(x + r * ldx + k);
+    lane_part[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < nb) {
+        double total = 0.0;
+        for (int l = 0; l < lanes; ++l) total += lane_part[l * nb + threadIdx.x];
+        partial[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = total;
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+sum_final(const double *__restrict__ partial, int nblocks, T *__restrict__ sums) {
+    const int k = blockIdx.x;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += kThreads) acc += partial[(int64_t)k * nblocks + i];
+    const double total = block_reduce_sum(acc);
+    if (threadIdx.x == 0) sums[k] = (T)total;
+}
+
+// ------------------------------------------------------------------------------------------ K7
+// AoS (n, nb) <-> SoA (nb, ld) through a padded shared-memory tile of kTileRows rows x C blades:
+// both the global read and the global write are contiguous runs.
+constexpr int kTileRows = 128;
+
+template <class T, bool TO_SOA>
+__global__ void __launch_bounds__(kThreads)
+transpose_kernel(const T *__restrict__ src, int64_t lds, T *__restrict__ dst, int64_t ldd, int64_t n, int C) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *tile = reinterpret_cast<T *>(smem_raw);  // [kTileRows][C+1]
+    const int64_t r0 = (int64_t)blockIdx.x * kTileRows;
+    const int c0 = blockIdx.y * C;
+    const int rows = (int)((n - r0) < kTileRows ? (n - r0) : kTileRows);
+    const int pitch = C + 1;
+    if (TO_SOA) {
+        for (int e = threadIdx.x; e < rows * C; e += kThreads) {
+            const int r = e / C, c = e % C;
+            tile[r * pitch + c] = __ldg(src + (r0 + r) * lds + c0 + c);
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < kTileRows * C; e += kThreads) {
+            const int c = e / kTileRows, r = e % kTileRows;
+            if (r < rows) dst[(int64_t)(c0 + c) * ldd + r0 + r] = tile[r * pitch + c];
+        }
+    } else {
+        for (int e = threadIdx.x; e < kTileRows * C; e += kThreads) {
+            const int c = e / kTileRows, r = e % kTileRows;
+            if (r < rows) tile[r * pitch + c] = __ldg(src + (int64_t)(c0 + c) * lds + r0 + r);
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < rows * C; e += kThreads) {
+            const int r = e / C, c = e % C;
+            dst[(r0 + r) * ldd + c0 + c] = tile[r * pitch + c];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ column movers
+struct ColumnMap { int16_t col_of_blade[256]; };  // -1: blade stays zero
+
+template <class T, int LAYOUT>
+__global__ void __launch_bounds__(kThreads)
+scatter_columns_kernel(const T *__restrict__ cols, int ncols, T *__restrict__ dst, int64_t ldd, int64_t n, int log2nb,
+                       const ColumnMap map) {
+    int64_t r; int k;
+    if (LAYOUT == kSoA) { r = (int64_t)blockIdx.x * kThreads + threadIdx.x; k = blockIdx.y; }
+    else split_index((int64_t)blockIdx.x * kThreads + threadIdx.x, log2nb, r, k);
+    if (r >= n) return;
+    const int c = map.col_of_blade[k];
+    const T v = c >= 0 ? __ldg(cols + r * ncols + c) : T(0);
+    if (LAYOUT == kSoA) dst[(int64_t)k * ldd + r] = v; else dst[r * ldd + k] = v;
+}
+
+struct BladeList { int32_t blade_of_col[256]; };
+
+template <class T, int LAYOUT>
+__global__ void __launch_bounds__(kThreads)
+gather_columns_kernel(const T *__restrict__ src, int64_t lds, int64_t n, int ncols, const BladeList list,
+                      T *__restrict__ cols) {
+    const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t r = e / ncols;
+    const int c = (int)(e % ncols);
+    if (r >= n) return;
+    const int k = list.blade_of_col[c];
+    cols[e] = LAYOUT == kSoA ? __ldg(src + (int64_t)k * lds + r) : __ldg(src + r * lds + k);
+}
+
+// ------------------------------------------------------------------------------------------ looped product (64..256 blades)
+// One block owns 32 rows; both operand tiles sit in shared memory as [blade][row]; warp w produces
+// output blades w, w+8, ...  gather_signs[k*nb+i] = sign(i, i^k) keeps the reference's ascending-i
+// order per output blade (batch.rs:384-404).  Not a bandwidth-bound kernel: 2*nb^2 shared loads per row.
+template <class T, bool STRICT>
+__global__ void __launch_bounds__(kThreads)
+big_product_kernel(const T *__restrict__ a, int64_t lda, int a_bc, const T *__restrict__ b, int64_t ldb, int b_bc,
+                   T *__restrict__ out, int64_t ldo, int64_t n, int nb, int op, const int8_t *__restrict__ gsign) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sa = reinterpret_cast<T *>(smem_raw);
+    T *sb = sa + (size_t)nb * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r = (int64_t)blockIdx.x * 32 + lane;
+    const bool live = r < n;
+    for (int i = warp; i < nb; i += kThreads / 32) {
+        sa[i * 32 + lane] = live ? __ldg(a + (int64_t)i * lda + (a_bc ? 0 : r)) : T(0);
+        sb[i * 32 + lane] = live ? __ldg(b + (int64_t)i * ldb + (b_bc ? 0 : r)) : T(0);
+    }
+    __syncthreads();
+    for (int k = warp; k < nb; k += kThreads / 32) {
+        T acc = T(0);
+        const int8_t *g = gsign + (size_t)k * nb;
+        for (int i = 0; i < nb; ++i) {
+            const int s = g[i];
+            const int j = i ^ k;
+            if (s == 0) continue;
+            if (op == kOpOuter && (i & j) != 0) continue;
+            if (op == kOpLC && (i & j) != i) continue;
+            const T av = sa[i * 32 + lane];
+            acc = Arith<STRICT>::madd(s > 0 ? av : -av, sb[j * 32 + lane], acc);
+        }
+        if (live) out[(int64_t)k * ldo + r] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ PGA / CGA points
+// which 0: PGA3D point  c[7]=1, c[14]=-x, c[13]=y, c[11]=-z        (src/pga.rs:131-134)
+// which 1: CGA3D point  c[1,2,4]=x,y,z, c[8]=0.5|x|^2-0.5, c[16]=0.5|x|^2+0.5   (src/cga.rs:189-206)
+template <class T, int LAYOUT>
+__global__ void __launch_bounds__(kThreads)
+points_embed_kernel(int which, const T *__restrict__ xyz, T *__restrict__ dst, int64_t ldd, int64_t n) {
+    const int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (r >= n) return;
+    const T x = __ldg(xyz + r * 3), y = __ldg(xyz + r * 3 + 1), z = __ldg(xyz + r * 3 + 2);
+    const int nb = which == 0 ? 16 : 32;
+    T nsq = T(0);
+    if (which == 1) {  // x*x + y*y + z*z, each operation rounded on its own (no FMA in the reference)
+        const T xx = mul_rn(x, x), yy = mul_rn(y, y), zz = mul_rn(z, z);
+        nsq = Arith<true>::madd(T(1), zz, Arith<true>::madd(T(1), yy, xx));
+    }
+    for (int k = 0; k < nb; ++k) {
+        T v = T(0);
+        if (which == 0) {
+            if (k == 7) v = T(1); else if (k == 14) v = -x; else if (k == 13) v = y; else if (k == 11) v = -z;
+        } else {
+            if (k == 1) v = x; else if (k == 2) v = y; else if (k == 4) v = z;
+            else if (k == 8) v = mul_rn(T(0.5), nsq) - T(0.5);
+            else if (k == 16) v = mul_rn(T(0.5), nsq) + T(0.5);
+        }
+        if (LAYOUT == kSoA) dst[(int64_t)k * ldd + r] = v; else dst[r * ldd + k] = v;
+    }
+}
+
+// which 0: x=-c[14]/w, y=c[13]/w, z=-c[11]/w, w=c[7]   (src/pga.rs:579-599)
+// which 1: (c[1],c[2],c[4]) / (c[16]-c[8])             (src/cga.rs:492-508)
+// Rows whose weight is below the reference's threshold (1e-10 / 1e-12) have no finite point: the
+// scalar API raises ValueError there; the batched form writes NaN for that row.
+template <class T, int LAYOUT>
+__global__ void __launch_bounds__(kThreads)
+points_extract_kernel(int which, const T *__restrict__ src, int64_t lds, int64_t n, T *__restrict__ xyz) {
+    const int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (r >= n) return;
+    auto at = [&](int k) { return LAYOUT == kSoA ? __ldg(src + (int64_t)k * lds + r) : __ldg(src + r * lds + k); };
+    T w, x, y, z, thr;
+    if (which == 0) { w = at(7); x = -at(14); y = at(13); z = -at(11); thr = (T)1e-10; }
+    else { w = at(16) - at(8); x = at(1); y = at(2); z = at(4); thr = (T)1e-12; }
+    const bool ok = (w < T(0) ? -w : w) >= thr;
+    const T nanv = (T)__int_as_float(0x7fc00000);
+    xyz[r * 3 + 0] = ok ? div_rn(x, w) : nanv;
+    xyz[r * 3 + 1] = ok ? div_rn(y, w) : nanv;
+    xyz[r * 3 + 2] = ok ? div_rn(z, w) : nanv;
+}
+
+template <class F32, class F64> cudaError_t by_dtype(int dtype, F32 f32, F64 f64) {
+    if (dtype == kF32) f32(); else if (dtype == kF64) f64(); else return cudaErrorInvalidValue;
+    note_kernel_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+// ============================================================================================ launchers
+
+cudaError_t launch_blade_map(int nb, const ViewArg &x, const ViewArg &out, const BladeMap &map, double scale, cudaStream_t s) {
+    const int64_t n = out.n;
+    if (n <= 0) return cudaSuccess;
+    auto run = [&](auto tag) {
+        using T = decltype(tag);
+        if (x.layout == kSoA) {
+            constexpr int W = VecW<T>::value;
+            dim3 grid(blocks_for((n + W - 1) / W), nb);
+            blade_map_soa<T><<<grid, kThreads, 0, s>>>((const T *)x.data, x.ld, (T *)out.data, out.ld, n, map, (T)scale);
+        } else {
+            blade_map_aos<T><<<blocks_for(n * nb), kThreads, 0, s>>>((const T *)x.data, x.ld, (T *)out.data, out.ld, n, ilog2(nb), map, (T)scale);
+        }
+    };
+    return by_dtype(x.dtype, [&] { run(float()); }, [&] { run(double()); });
+}
+
+cudaError_t launch_addsub(int nb, int op, const ViewArg &a, bool a_bc, const ViewArg &b, bool b_bc, const ViewArg &out, cudaStream_t s) {
+    const int64_t n = out.n;
+    if (n <= 0) return cudaSuccess;
+    auto run = [&](auto tag) {
+        using T = decltype(tag);
+        if (out.layout == kSoA) {
+            constexpr int W = VecW<T>::value;
+            dim3 grid(blocks_for((n + W - 1) / W), nb);
+            addsub_soa<T><<<grid, kThreads, 0, s>>>((const T *)a.data, a.ld, a_bc, (const T *)b.data, b.ld, b_bc, (T *)out.data, out.ld, n, op);
+        } else {
+            addsub_aos<T><<<blocks_for(n * nb), kThreads, 0, s>>>((const T *)a.data, a.ld, a_bc, (const T *)b.data, b.ld, b_bc, (T *)out.data, out.ld, n, ilog2(nb), op);
+        }
+    };
+    return by_dtype(out.dtype, [&] { run(float()); }, [&] { run(double()); });
+}
+
+cudaError_t launch_norm(int nb, int mode, bool strict, const ViewArg &x, const int8_t *weights, void *norms, const ViewArg &out, cudaStream_t s) {
+    const int64_t n = x.n;
+    if (n <= 0) return cudaSuccess;
+    Weights wt;
+    for (int k = 0; k < 256; ++k) wt.w[k] = k < nb ? weights[k] : 0;
+    auto run = [&](auto tag) {
+        using T = decltype(tag);
+        const unsigned g = blocks_for(n);
+#define LCC_NORM_LAUNCH(STRICT, LAYOUT) \
+    norm_kernel<T, STRICT, LAYOUT><<<g, kThreads, 0, s>>>((const T *)x.data, x.ld, n, nb, wt, mode, (T *)norms, (T *)out.data, out.ld)
+        if (x.layout == kSoA) { if (strict) LCC_NORM_LAUNCH(true, kSoA); else LCC_NORM_LAUNCH(false, kSoA); }
+        else { if (strict) LCC_NORM_LAUNCH(true, kAoS); else LCC_NORM_LAUNCH(false, kAoS); }
+#undef LCC_NORM_LAUNCH
+    };
+    return by_dtype(x.dtype, [&] { run(float()); }, [&] { run(double()); });
+}
+
+static int sum_blocks(int64_t n) {
+    int64_t b = (n + (int64_t)kThreads * 16 - 1) / ((int64_t)kThreads * 16);
+    if (b < 1) b = 1;
+    if (b > kSumBlocksMax) b = kSumBlocksMax;
+    return (int)b;
+}
+int64_t sum_scratch_elems(int nb, int64_t n) { return (int64_t)nb * sum_blocks(n); }
+
+cudaError_t launch_sum(int nb, const ViewArg &x, void *sums_dev, void *scratch_dev, int64_t scratch_elems, cudaStream_t s) {
+    const int64_t n = x.n;
+    const int nblocks = sum_blocks(n);
+    if (scratch_elems < (int64_t)nb * nblocks) return cudaErrorInvalidValue;
+    const int64_t rows_per_block = (n + nblocks - 1) / nblocks;
+    auto run = [&](auto tag) {
+        using T = decltype(tag);
+        if (x.layout == kSoA) {
+            sum_partial_soa<T><<<dim3(nblocks, nb), kThreads, 0, s>>>((const T *)x.data, x.ld, n, rows_per_block, (double *)scratch_dev);
+        } else {
+            sum_partial_aos<T><<<nblocks, kThreads, 0, s>>>((const T *)x.data, x.ld, n, nb, rows_per_block, (double *)scratch_dev);
+        }
+        note_kernel_launch();
+        sum_final<T><<<nb, kThreads, 0, s>>>((const double *)scratch_dev, nblocks, (T *)sums_dev);
+    };
+    return by_dtype(x.dtype, [&] { run(float()); }, [&] { run(double()); });
+}
+
+cudaError_t launch_convert(int nb, const ViewArg &src, const ViewArg &dst, cudaStream_t s) {
+    const int64_t n = src.n;
+    if (n <= 0) return cudaSuccess;
+    const size_t es = src.dtype == kF32 ? 4 : 8;
+    if (src.layout == dst.layout) {  // same layout, possibly different leading dimensions: strided copy
+        if (src.layout == kSoA)
+            return cudaMemcpy2DAsync(dst.data, dst.ld * es, src.data, src.ld * es, n * es, nb, cudaMemcpyDeviceToDevice, s);
+        return cudaMemcpy2DAsync(dst.data, dst.ld * es, src.data, src.ld * es, nb * es, n, cudaMemcpyDeviceToDevice, s);
+    }
+    const int C = nb < 32 ? nb : 32;
+    dim3 grid(blocks_for(n, kTileRows), nb / C);
+    const size_t smem = (size_t)kTileRows * (C + 1) * es;
+    auto run = [&](auto tag) {
+        using T = decltype(tag);
+        if (dst.layout == kSoA) transpose_kernel<T, true><<<grid, kThreads, smem, s>>>((const T *)src.data, src.ld, (T *)dst.data, dst.ld, n, C);
+        else transpose_kernel<T, false><<<grid, kThreads, smem, s>>>((const T *)src.data, src.ld, (T *)dst.data, dst.ld, n, C);
+    };
+    return by_dtype(src.dtype, [&] { run(float()); }, [&] { run(double()); });
+}
+
+cudaError_t launch_scatter_columns(int nb, const void *cols, int ncols, const int32_t *blade_of_col, const ViewArg &dst, cudaStream_t s) {
+    const int64_t n = dst.n;
+    if (n <= 0) return cudaSuccess;
+    ColumnMap map;
+    for (int k = 0; k < 256; ++k) map.col_of_blade[k] = -1;
+    for (int c = 0; c < ncols; ++c) map.col_of_blade[blade_of_col[c]] = (int16_t)c;
+    auto run = [&](auto tag) {
+        using T = decltype(tag);
+        if (dst.layout == kSoA) scatter_columns_kernel<T, kSoA><<<dim3(blocks_for(n), nb), kThreads, 0, s>>>((const T *)cols, ncols, (T *)dst.data, dst.ld, n, 0, map);
+        else scatter_columns_kernel<T, kAoS><<<blocks_for(n * nb), kThreads, 0, s>>>((const T *)cols, ncols, (T *)dst.data, dst.ld, n, ilog2(nb), map);
+    };
+    return by_dtype(dst.dtype, [&] { run(float()); }, [&] { run(double()); });
+}
+
+cudaError_t launch_gather_columns(int nb, const ViewArg &src, int ncols, const int32_t *blade_of_col, void *cols, cudaStream_t s) {
+    (void)nb;
+    const int64_t n = src.n;
+    if (n <= 0 || ncols <= 0) return cudaSuccess;
+    BladeList list;
+    for (int c = 0; c < 256; ++c) list.blade_of_col[c] = c < ncols ? blade_of_col[c] : 0;
+    auto run = [&](auto tag) {
+        using T = decltype(tag);
+        if (src.layout == kSoA) gather_columns_kernel<T, kSoA><<<blocks_for(n * ncols), kThreads, 0, s>>>((const T *)src.data, src.ld, n, ncols, list, (T *)cols);
+        else gather_columns_kernel<T, kAoS><<<blocks_for(n * ncols), kThreads, 0, s>>>((const T *)src.data, src.ld, n, ncols, list, (T *)cols);
+    };
+    return by_dtype(src.dtype, [&] { run(float()); }, [&] { run(double()); });
+}
+
+cudaError_t launch_copy_rows(int nb, const ViewArg &src, int64_t start, int64_t end, const ViewArg &dst, int64_t dst_start, cudaStream_t s) {
+    const size_t es = src.dtype == kF32 ? 4 : 8;
+    ViewArg a = src, b = dst;
+    a.n = b.n = end - start;
+    a.data = (char *)src.data + (src.layout == kSoA ? start : start * src.ld) * es;
+    b.data = (char *)dst.data + (dst.layout == kSoA ? dst_start : dst_start * dst.ld) * es;
+    return launch_convert(nb, a, b, s);
+}
+
+cudaError_t launch_big_product(int nb, int op, bool strict, const ViewArg &a, bool a_bc, const ViewArg &b, bool b_bc, const ViewArg &out, const int8_t *gsign, cudaStream_t s) {
+    const int64_t n = out.n;
+    if (n <= 0) return cudaSuccess;
+    const size_t es = out.dtype == kF32 ? 4 : 8;
+    const size_t smem = (size_t)2 * nb * 32 * es;
+    auto run = [&](auto tag) {
+        using T = decltype(tag);
+        auto go = [&](auto kernel) {
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            kernel<<<blocks_for(n, 32), kThreads, smem, s>>>((const T *)a.data, a.ld, a_bc, (const T *)b.data, b.ld, b_bc, (T *)out.data, out.ld, n, nb, op, gsign);
+        };
+        if (strict) go(big_product_kernel<T, true>); else go(big_product_kernel<T, false>);
+    };
+    return by_dtype(out.dtype, [&] { run(float()); }, [&] { run(double()); });
+}
+
+cudaError_t launch_points_embed(int which, const void *xyz, const ViewArg &dst, cudaStream_t s) {
+    const int64_t n = dst.n;
+    if (n <= 0) return cudaSuccess;
+    auto run = [&](auto tag) {
+        using T = decltype(tag);
+        if (dst.layout == kSoA) points_embed_kernel<T, kSoA><<<blocks_for(n), kThreads, 0, s>>>(which, (const T *)xyz, (T *)dst.data, dst.ld, n);
+        else points_embed_kernel<T, kAoS><<<blocks_for(n), kThreads, 0, s>>>(which, (const T *)xyz, (T *)dst.data, dst.ld, n);
+    };
+    return by_dtype(dst.dtype, [&] { run(float()); }, [&] { run(double()); });
+}
+
+cudaError_t launch_points_extract(int which, const ViewArg &src, void *xyz, cudaStream_t s) {
+    const int64_t n = src.n;
+    if (n <= 0) return cudaSuccess;
+    auto run = [&](auto tag) {
+        using T = decltype(tag);
+        if (src.layout == kSoA) points_extract_kernel<T, kSoA><<<blocks_for(n), kThreads, 0, s>>>(which, (const T *)src.data, src.ld, n, (T *)xyz);
+        else points_extract_kernel<T, kAoS><<<blocks_for(n), kThreads, 0, s>>>(which, (const T *)src.data, src.ld, n, (T *)xyz);
+    };
+    return by_dtype(src.dtype, [&] { run(float()); }, [&] { run(double()); });
+}
+
+}  // namespace lcc

@@ -1,0 +1,43 @@
+// misc_kernels.cuh -- declarations of the run-time-nb kernels' host launchers (misc_kernels.cu):
+// K3 signed permutations / masks, K4 norms, K5 batch sums, K7 layout conversion, the row/column
+// movers behind the container API, and the looped product used for algebras above 32 blades.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace lcc {
+
+struct ViewArg {  // one device batch; mirrors lcc_view with typed fields
+    void *data; int64_t n; int64_t ld; int dtype; int layout;
+};
+
+struct BladeMap {  // out[k] = factor[k] * in[source[k]], factor in {-1, 0, +1}
+    int8_t factor[256];
+    uint16_t source[256];
+};
+
+cudaError_t launch_blade_map(int nb, const ViewArg &x, const ViewArg &out, const BladeMap &map, double scale,
+                             cudaStream_t s);
+cudaError_t launch_addsub(int nb, int op, const ViewArg &a, bool a_bcast, const ViewArg &b, bool b_bcast,
+                          const ViewArg &out, cudaStream_t s);
+// weights[k] = sign[k][k] * reverse_sign(k) in {-1,0,+1}; mode 0 norm^2, 1 norm, 2 normalized
+cudaError_t launch_norm(int nb, int mode, bool strict, const ViewArg &x, const int8_t *weights, void *norms,
+                        const ViewArg &out, cudaStream_t s);
+cudaError_t launch_sum(int nb, const ViewArg &x, void *sums_dev, void *scratch_dev, int64_t scratch_elems,
+                       cudaStream_t s);
+int64_t sum_scratch_elems(int nb, int64_t n);
+cudaError_t launch_convert(int nb, const ViewArg &src, const ViewArg &dst, cudaStream_t s);
+cudaError_t launch_scatter_columns(int nb, const void *cols, int ncols, const int32_t *blade_of_col,
+                                   const ViewArg &dst, cudaStream_t s);
+cudaError_t launch_gather_columns(int nb, const ViewArg &src, int ncols, const int32_t *blade_of_col, void *cols,
+                                  cudaStream_t s);
+cudaError_t launch_copy_rows(int nb, const ViewArg &src, int64_t start, int64_t end, const ViewArg &dst,
+                             int64_t dst_start, cudaStream_t s);
+// Looped product for 64..256 blades (SoA only): gather_signs[k*nb+i] = sign(i, i^k) on the device.
+cudaError_t launch_big_product(int nb, int op, bool strict, const ViewArg &a, bool a_bcast, const ViewArg &b,
+                               bool b_bcast, const ViewArg &out, const int8_t *gather_signs_dev, cudaStream_t s);
+// PGA3D / CGA3D point embeddings and extractors (src/pga.rs:131-134,579-599; src/cga.rs:189-206,492-508)
+cudaError_t launch_points_embed(int which, const void *xyz, const ViewArg &dst, cudaStream_t s);
+cudaError_t launch_points_extract(int which, const ViewArg &src, void *xyz, cudaStream_t s);
+
+}  // namespace lcc

@@ -1,0 +1,235 @@
+// product_impl.cuh -- K1 (binary product family) and K2 (fixed-versor sandwich) for ONE signature
+// and ONE precision.  The including translation unit defines
+//
+//   LCC_TERMS_FILE      the generated term list (csrc/generated/cayley_*.inc)
+//   LCC_NB              number of blades (2, 4, 8, 16 or 32)
+//   LCC_RUNTIME_METRIC  0: signs are the signature's own, folded into FMA operand negation
+//                       1: the list holds the metric-free reorder signs; the metric factor
+//                          mu[i & j] in {+1,-1,0} arrives as a kernel argument (any Cl(p,q,r))
+//   LCC_REAL            float or double
+//   LCC_TU              token used to name the two exported launchers
+//
+// Reference semantics (file:line in /root/reference): out[i^j] += sign[i][j]*a[i]*b[j], i outer,
+// j inner, src/batch.rs:384-404 (geometric), :544-568 (outer, (i&j)==0), :615-649 (left
+// contraction, (i&j)==i); sandwich = two such stages with one rotor, :452-497.  In gather form
+// every output blade k receives its terms in ascending i, which is the order of the generated
+// list, so STRICT kernels reproduce the reference bit for bit and FAST kernels differ only by
+// the single rounding an FMA saves per term.
+//
+// Roofline: these kernels are HBM-bound streaming kernels.  Algorithmic bytes per row are
+// 3*NB*sizeof(T) for a product (2 reads + 1 write), 4*NB*sizeof(T) for the fused gp+outer form
+// and 2*NB*sizeof(T) for the sandwich; each byte is touched exactly once by a full-width
+// coalesced access (common.cuh).
+#pragma once
+#include "common.cuh"
+#include "launch_args.h"
+
+#ifndef LCC_TERMS_FILE
+#error "define LCC_TERMS_FILE, LCC_NB, LCC_RUNTIME_METRIC, LCC_REAL and LCC_TU before including product_impl.cuh"
+#endif
+
+namespace lcc {
+namespace LCC_TU {
+
+constexpr int NB = LCC_NB;
+constexpr bool kRuntimeMetric = LCC_RUNTIME_METRIC != 0;
+using real = LCC_REAL;
+constexpr int kRowsSoA = RowsPerThread<real, NB, kRuntimeMetric ? 256 : 512>::value;  // rows per thread, SoA
+
+struct Coeffs { real v[NB]; };  // a uniform multivector (rotor, metric factors) in the constant bank
+
+__host__ __device__ constexpr bool even_grade(int blade) {
+    int c = 0;
+    for (int b = blade; b; b >>= 1) c += b & 1;
+    return (c & 1) == 0;
+}
+__host__ __device__ constexpr bool term_in_op(int op, int flags) {
+    return op == kOpGP || op == kOpGPOuter || (op == kOpOuter && (flags & 1)) || (op == kOpLC && (flags & 2));
+}
+
+// Output sink: SoA stores V rows of one blade per call; AoS collects 16 bytes of consecutive
+// blades of the thread's row before storing.
+template <int LAYOUT, int V> struct Sink {
+    static constexpr int W = 16 / (int)sizeof(real);
+    real *base; int64_t ld; int64_t r0; bool vec_ok;
+    real buf[W];
+    template <int K> __device__ __forceinline__ void put(const real (&acc)[V]) {
+        if constexpr (LAYOUT == kSoA) {
+            stg_stream(base + (int64_t)K * ld + r0, acc);
+        } else {
+            if constexpr (NB < W) {
+                base[r0 * ld + K] = acc[0];
+            } else {
+                buf[K % W] = acc[0];
+                if constexpr ((K % W) == W - 1) {
+                    real *p = base + r0 * ld + (K - (W - 1));
+                    if (vec_ok) {
+                        stg_stream(p, buf);
+                    } else {
+#pragma unroll
+                        for (int l = 0; l < W; ++l) p[l] = buf[l];
+                    }
+                }
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------ K1
+template <int LAYOUT, int OP, bool STRICT>
+__global__ void __launch_bounds__(kThreads)
+product_kernel(const real *__restrict__ a, int64_t lda, int a_bcast, const real *__restrict__ b, int64_t ldb,
+               int b_bcast, real *__restrict__ out, int64_t ldo, real *__restrict__ out2, int64_t ldo2,
+               int64_t n, int vec_ok, const Coeffs mu) {
+    constexpr int V = LAYOUT == kSoA ? kRowsSoA : 1;
+    const int64_t r0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * V;
+    if (r0 >= n) return;
+
+    Tile<real, NB, V> A, B;
+    if constexpr (LAYOUT == kSoA) {
+        load_soa(A, a, lda, r0, a_bcast != 0);
+        load_soa(B, b, ldb, r0, b_bcast != 0);
+    } else {
+        load_aos(A, a, lda, r0, a_bcast != 0, vec_ok != 0);
+        load_aos(B, b, ldb, r0, b_bcast != 0, vec_ok != 0);
+    }
+    Sink<LAYOUT, V> sink{out, ldo, r0, vec_ok != 0, {}};
+    Sink<LAYOUT, V> sink2{out2, ldo2, r0, vec_ok != 0, {}};
+    (void)sink2;
+    (void)mu;
+
+#define LCC_OUT_BEGIN(k) { real acc[V]; real acc2[V]; _Pragma("unroll") for (int l = 0; l < V; ++l) { acc[l] = real(0); acc2[l] = real(0); }
+#define LCC_TERM(k, i, j, neg, flags)                                                                   \
+    if constexpr (term_in_op(OP, flags)) {                                                             \
+        _Pragma("unroll") for (int l = 0; l < V; ++l) {                                                \
+            real av = (neg) ? -A.v[i][l] : A.v[i][l];                                                  \
+            if constexpr (kRuntimeMetric) av = mul_rn(av, mu.v[(i) & (j)]);                            \
+            acc[l] = Arith<STRICT>::madd(av, B.v[j][l], acc[l]);                                       \
+            if constexpr (OP == kOpGPOuter && ((flags) & 1)) acc2[l] = Arith<STRICT>::madd(av, B.v[j][l], acc2[l]); \
+        }                                                                                              \
+    }
+#define LCC_OUT_END(k) sink.template put<k>(acc); if constexpr (OP == kOpGPOuter) sink2.template put<k>(acc2); }
+#include LCC_TERMS_FILE
+#undef LCC_OUT_BEGIN
+#undef LCC_TERM
+#undef LCC_OUT_END
+}
+
+// ------------------------------------------------------------------------------------------ K2
+// out = R * x * ~R, two stages, the intermediate R*x rounded to storage precision exactly as the
+// reference's `rx` vector (batch.rs:462-478).  EVEN prunes the odd-grade blades of R at compile
+// time (rotors and motors are even); pruned terms would only have added +-0.
+template <int LAYOUT, bool STRICT, bool EVEN>
+__global__ void __launch_bounds__(kThreads)
+sandwich_kernel(const real *__restrict__ x, int64_t ldx, real *__restrict__ out, int64_t ldo, int64_t n,
+                int vec_ok, const Coeffs R, const Coeffs Rrev, const Coeffs mu) {
+    constexpr int V = LAYOUT == kSoA ? kRowsSoA : 1;
+    const int64_t r0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * V;
+    if (r0 >= n) return;
+
+    Tile<real, NB, V> X, RX;
+    if constexpr (LAYOUT == kSoA) load_soa(X, x, ldx, r0, false);
+    else load_aos(X, x, ldx, r0, false, vec_ok != 0);
+    (void)mu;
+
+    // stage 1: rx[k] = sum_i sign(i, i^k) * R[i] * x[i^k]
+#define LCC_OUT_BEGIN(k) { real acc[V]; _Pragma("unroll") for (int l = 0; l < V; ++l) acc[l] = real(0);
+#define LCC_TERM(k, i, j, neg, flags)                                                                   \
+    if constexpr (!EVEN || even_grade(i)) {                                                            \
+        real rv = (neg) ? -R.v[i] : R.v[i];                                                            \
+        if constexpr (kRuntimeMetric) rv = mul_rn(rv, mu.v[(i) & (j)]);                                \
+        _Pragma("unroll") for (int l = 0; l < V; ++l) acc[l] = Arith<STRICT>::madd(rv, X.v[j][l], acc[l]); \
+    }
+#define LCC_OUT_END(k) _Pragma("unroll") for (int l = 0; l < V; ++l) RX.v[k][l] = acc[l]; }
+#include LCC_TERMS_FILE
+#undef LCC_TERM
+#undef LCC_OUT_END
+
+    // stage 2: out[k] = sum_i sign(i, i^k) * rx[i] * ~R[i^k]
+    Sink<LAYOUT, V> sink{out, ldo, r0, vec_ok != 0, {}};
+#define LCC_TERM(k, i, j, neg, flags)                                                                   \
+    if constexpr (!EVEN || even_grade(j)) {                                                            \
+        real rv = (neg) ? -Rrev.v[j] : Rrev.v[j];                                                      \
+        if constexpr (kRuntimeMetric) rv = mul_rn(rv, mu.v[(i) & (j)]);                                \
+        _Pragma("unroll") for (int l = 0; l < V; ++l) acc[l] = Arith<STRICT>::madd(RX.v[i][l], rv, acc[l]); \
+    }
+#define LCC_OUT_END(k) sink.template put<k>(acc); }
+#include LCC_TERMS_FILE
+#undef LCC_OUT_BEGIN
+#undef LCC_TERM
+#undef LCC_OUT_END
+}
+
+// ------------------------------------------------------------------------------------------ host
+static inline Coeffs to_coeffs(const double *src, double fill) {
+    Coeffs c;
+    for (int i = 0; i < NB; ++i) c.v[i] = src ? (real)src[i] : (real)fill;
+    return c;
+}
+
+template <int LAYOUT> static inline unsigned grid_for(int64_t n) {
+    constexpr int V = LAYOUT == kSoA ? kRowsSoA : 1;
+    int64_t threads = (n + V - 1) / V;
+    return (unsigned)((threads + kThreads - 1) / kThreads);
+}
+
+template <int LAYOUT, int OP, bool STRICT> static cudaError_t launch_product_t(const ProductArgs &g) {
+    if (g.n <= 0) return cudaSuccess;
+    constexpr int W = 16 / (int)sizeof(real);
+    int vec_ok = 1;
+    if (LAYOUT == kAoS) {
+        auto ok = [&](const void *p, int64_t ld) { return ((uintptr_t)p % 16 == 0) && (ld % W == 0); };
+        vec_ok = ok(g.a, g.lda) && ok(g.b, g.ldb) && ok(g.out, g.ldo) && (OP != kOpGPOuter || ok(g.out2, g.ldo2));
+    }
+    product_kernel<LAYOUT, OP, STRICT><<<grid_for<LAYOUT>(g.n), kThreads, 0, g.stream>>>(
+        (const real *)g.a, g.lda, g.a_bcast, (const real *)g.b, g.ldb, g.b_bcast, (real *)g.out, g.ldo,
+        (real *)g.out2, g.ldo2, g.n, vec_ok, to_coeffs(g.mu, 1.0));
+    note_kernel_launch();
+    return cudaGetLastError();
+}
+
+template <int LAYOUT, bool STRICT> static cudaError_t launch_product_op(const ProductArgs &g) {
+    switch (g.op) {
+        case kOpGP: return launch_product_t<LAYOUT, kOpGP, STRICT>(g);
+        case kOpOuter: return launch_product_t<LAYOUT, kOpOuter, STRICT>(g);
+        case kOpLC: return launch_product_t<LAYOUT, kOpLC, STRICT>(g);
+        case kOpGPOuter: return launch_product_t<LAYOUT, kOpGPOuter, STRICT>(g);
+    }
+    return cudaErrorInvalidValue;
+}
+
+static cudaError_t launch_product(const ProductArgs &g) {
+    if (g.layout == kSoA) return g.strict ? launch_product_op<kSoA, true>(g) : launch_product_op<kSoA, false>(g);
+    return g.strict ? launch_product_op<kAoS, true>(g) : launch_product_op<kAoS, false>(g);
+}
+
+template <int LAYOUT, bool STRICT, bool EVEN> static cudaError_t launch_sandwich_t(const SandwichArgs &g) {
+    if (g.n <= 0) return cudaSuccess;
+    constexpr int W = 16 / (int)sizeof(real);
+    int vec_ok = 1;
+    if (LAYOUT == kAoS)
+        vec_ok = ((uintptr_t)g.x % 16 == 0) && (g.ldx % W == 0) && ((uintptr_t)g.out % 16 == 0) && (g.ldo % W == 0);
+    Coeffs R = to_coeffs(g.rotor, 0.0), Rrev;
+    for (int i = 0; i < NB; ++i) {
+        int grade = 0;
+        for (int b = i; b; b >>= 1) grade += b & 1;
+        // ~R[i] = R[i] * reverse_sign(grade): src/batch.rs:452-457, src/algebra/blades.rs:128-135
+        Rrev.v[i] = R.v[i] * ((grade % 4 < 2) ? real(1) : real(-1));
+    }
+    sandwich_kernel<LAYOUT, STRICT, EVEN><<<grid_for<LAYOUT>(g.n), kThreads, 0, g.stream>>>(
+        (const real *)g.x, g.ldx, (real *)g.out, g.ldo, g.n, vec_ok, R, Rrev, to_coeffs(g.mu, 1.0));
+    note_kernel_launch();
+    return cudaGetLastError();
+}
+
+template <int LAYOUT> static cudaError_t launch_sandwich_l(const SandwichArgs &g) {
+    if (g.strict) return g.even ? launch_sandwich_t<LAYOUT, true, true>(g) : launch_sandwich_t<LAYOUT, true, false>(g);
+    return g.even ? launch_sandwich_t<LAYOUT, false, true>(g) : launch_sandwich_t<LAYOUT, false, false>(g);
+}
+
+static cudaError_t launch_sandwich(const SandwichArgs &g) {
+    return g.layout == kSoA ? launch_sandwich_l<kSoA>(g) : launch_sandwich_l<kAoS>(g);
+}
+
+}  // namespace LCC_TU
+}  // namespace lcc

@@ -1,0 +1,839 @@
+// lcc_abi.cu -- the C ABI of include/lcc_b200.h: argument validation with the reference's error
+// behaviour, the algebra registry, the stream-ordered device memory pool, and dispatch to the
+// sm_100a kernels (per-signature generated translation units + misc_kernels.cu).
+//
+// There is deliberately no host implementation of any batched operation in this file: without a
+// usable CUDA device every compute entry point returns LCC_ERR_NO_DEVICE.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/lcc_b200.h"
+#include "algebra_host.hpp"
+#include "generated/cayley_tables.h"
+#include "kernels/launch_args.h"
+#include "kernels/misc_kernels.cuh"
+
+// ------------------------------------------------------------------ generated kernel registry
+namespace lcc {
+#define LCC_SPEC_ENTRY(p, q, r, tu32, tu64)                         \
+    cudaError_t launch_product_##tu32(const ProductArgs &);         \
+    cudaError_t launch_sandwich_##tu32(const SandwichArgs &);       \
+    cudaError_t launch_product_##tu64(const ProductArgs &);         \
+    cudaError_t launch_sandwich_##tu64(const SandwichArgs &);
+#define LCC_GENERIC_ENTRY(dim, tu32, tu64) LCC_SPEC_ENTRY(dim, 0, 0, tu32, tu64)
+#include "generated/dispatch_table.inc"
+#undef LCC_SPEC_ENTRY
+#undef LCC_GENERIC_ENTRY
+
+struct SpecEntry { int p, q, r; ProductLauncher prod[2]; SandwichLauncher sand[2]; };
+struct GenericEntry { int dim; ProductLauncher prod[2]; SandwichLauncher sand[2]; };
+static const SpecEntry kSpecEntries[] = {
+#define LCC_SPEC_ENTRY(p, q, r, tu32, tu64) \
+    {p, q, r, {launch_product_##tu32, launch_product_##tu64}, {launch_sandwich_##tu32, launch_sandwich_##tu64}},
+#define LCC_GENERIC_ENTRY(dim, tu32, tu64)
+#include "generated/dispatch_table.inc"
+#undef LCC_SPEC_ENTRY
+#undef LCC_GENERIC_ENTRY
+    {-1, -1, -1, {nullptr, nullptr}, {nullptr, nullptr}}};
+static const GenericEntry kGenericEntries[] = {
+#define LCC_SPEC_ENTRY(p, q, r, tu32, tu64)
+#define LCC_GENERIC_ENTRY(dim, tu32, tu64) \
+    {dim, {launch_product_##tu32, launch_product_##tu64}, {launch_sandwich_##tu32, launch_sandwich_##tu64}},
+#include "generated/dispatch_table.inc"
+#undef LCC_SPEC_ENTRY
+#undef LCC_GENERIC_ENTRY
+    {-1, {nullptr, nullptr}, {nullptr, nullptr}}};
+
+static thread_local uint64_t t_launches = 0;
+void note_kernel_launch() { ++t_launches; }
+
+// ------------------------------------------------------------------ algebra builder
+void build_algebra(lcc_algebra &alg, int p, int q, int r) {
+    alg.p = p; alg.q = q; alg.r = r; alg.dim = p + q + r; alg.nb = 1 << alg.dim;
+    const int nb = alg.nb;
+    alg.signs.resize((size_t)nb * nb);
+    alg.blades.resize((size_t)nb * nb);
+    for (int a = 0; a < nb; ++a)
+        for (int b = 0; b < nb; ++b) {
+            alg.signs[(size_t)a * nb + b] = (int8_t)blade_sign((unsigned)a, (unsigned)b, p, q, r);
+            alg.blades[(size_t)a * nb + b] = (uint16_t)(a ^ b);
+        }
+    alg.names.resize(nb);
+    for (int i = 0; i < nb; ++i) {  // blades.rs:48-61: "1", then "e" + 1-based vector indices
+        if (i == 0) { alg.names[i] = "1"; continue; }
+        std::string s = "e";
+        for (int b = 0; b < alg.dim; ++b)
+            if ((i >> b) & 1) s += std::to_string(b + 1);
+        alg.names[i] = s;
+    }
+    const int words = (nb + 63) / 64;
+    alg.grade_masks.assign(alg.dim + 1, std::vector<uint64_t>(words, 0));
+    for (int i = 0; i < nb; ++i) alg.grade_masks[popcount32(i)][i / 64] |= 1ull << (i % 64);
+    alg.mu.resize(nb);
+    for (int c = 0; c < nb; ++c) {
+        int m = 1;
+        for (int b = 0; b < alg.dim; ++b)
+            if ((c >> b) & 1) m *= basis_square(p, q, r, b);
+        alg.mu[c] = (double)m;
+    }
+    alg.norm_weights.resize(nb);
+    for (int k = 0; k < nb; ++k)
+        alg.norm_weights[k] = (int8_t)(alg.signs[(size_t)k * nb + k] * reverse_sign_of_grade(popcount32(k)));
+    alg.pseudoscalar_invertible = alg.signs[(size_t)(nb - 1) * nb + (nb - 1)] != 0;
+    for (const SpecEntry *e = kSpecEntries; e->p >= 0; ++e)
+        if (e->p == p && e->q == q && e->r == r) {
+            alg.specialised = true;
+            for (int d = 0; d < 2; ++d) { alg.product[d] = e->prod[d]; alg.sandwich[d] = e->sand[d]; }
+        }
+    if (!alg.specialised)
+        for (const GenericEntry *e = kGenericEntries; e->dim >= 0; ++e)
+            if (e->dim == alg.dim)
+                for (int d = 0; d < 2; ++d) { alg.product[d] = e->prod[d]; alg.sandwich[d] = e->sand[d]; }
+}
+}  // namespace lcc
+
+using namespace lcc;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string t_error;
+
+static lcc_status fail(lcc_status code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_error = buf;
+    return code;
+}
+static lcc_status cuda_fail(cudaError_t e, const char *what) {
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver)
+        return fail(LCC_ERR_NO_DEVICE, "%s: no usable CUDA device (%s); batched operations have no CPU fallback",
+                    what, cudaGetErrorString(e));
+    return fail(LCC_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+#define LCC_CUDA(call)                                          \
+    do {                                                        \
+        cudaError_t e__ = (call);                               \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);   \
+    } while (0)
+#define LCC_TRY(expr)                               \
+    do {                                            \
+        lcc_status s__ = (expr);                    \
+        if (s__ != LCC_OK) return s__;              \
+    } while (0)
+
+static std::string sig_str(const lcc_algebra *a) {
+    char b[64];
+    snprintf(b, sizeof b, "Cl(%d,%d,%d)", a->p, a->q, a->r);
+    return b;
+}
+
+// ------------------------------------------------------------------ device state
+namespace {
+struct DeviceState {
+    cudaStream_t stream = nullptr;  // compute
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    bool ready = false;
+};
+std::mutex g_dev_mutex;
+DeviceState g_devices[64];
+
+lcc_status device_state(DeviceState **out) {
+    int dev = 0;
+    LCC_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(LCC_ERR_CUDA, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    DeviceState &st = g_devices[dev];
+    if (!st.ready) {
+        LCC_CUDA(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+        LCC_CUDA(cudaStreamCreateWithFlags(&st.copy_in, cudaStreamNonBlocking));
+        LCC_CUDA(cudaStreamCreateWithFlags(&st.copy_out, cudaStreamNonBlocking));
+        cudaMemPool_t pool;
+        LCC_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t keep = UINT64_MAX;  // keep freed blocks in the pool: steady-state calls never hit cudaMalloc
+        LCC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        st.ready = true;
+    }
+    *out = &st;
+    return LCC_OK;
+}
+
+lcc_status resolve_stream(void *stream, cudaStream_t *out) {
+    if (stream) { *out = (cudaStream_t)stream; return LCC_OK; }
+    DeviceState *st = nullptr;
+    LCC_TRY(device_state(&st));
+    *out = st->stream;
+    return LCC_OK;
+}
+
+inline size_t elem_size(int dtype) { return dtype == LCC_F32 ? 4 : 8; }
+
+lcc_status check_view(const lcc_algebra *alg, const lcc_view *v, const char *name, bool allow_null_data = false) {
+    if (!alg) return fail(LCC_ERR_VALUE, "algebra handle is NULL");
+    if (!v) return fail(LCC_ERR_VALUE, "%s: view is NULL", name);
+    if (v->dtype != LCC_F32 && v->dtype != LCC_F64) return fail(LCC_ERR_VALUE, "%s: dtype must be LCC_F32 or LCC_F64", name);
+    if (v->layout != LCC_SOA && v->layout != LCC_AOS) return fail(LCC_ERR_VALUE, "%s: layout must be LCC_SOA or LCC_AOS", name);
+    if (v->n < 0) return fail(LCC_ERR_VALUE, "%s: negative batch size", name);
+    if (v->n > 0 && !v->data && !allow_null_data) return fail(LCC_ERR_VALUE, "%s: data pointer is NULL", name);
+    const int64_t w = 16 / (int64_t)elem_size(v->dtype);
+    if (v->layout == LCC_SOA) {
+        if (v->ld < v->n || v->ld % w != 0 || ((uintptr_t)v->data % 16) != 0)
+            return fail(LCC_ERR_VALUE, "%s: SoA views need ld >= n, ld a multiple of %lld and 16-byte aligned data "
+                        "(use lcc_batch_alloc)", name, (long long)w);
+    } else if (v->ld < alg->nb) {
+        return fail(LCC_ERR_VALUE, "coeffs must have %d columns for %s but got %lld", alg->nb, sig_str(alg).c_str(), (long long)v->ld);
+    }
+    return LCC_OK;
+}
+
+ViewArg arg_of(const lcc_view *v) { return ViewArg{v->data, v->n, v->ld, v->dtype, v->layout}; }
+
+// batch.rs:361-376
+lcc_status broadcast_rows(int64_t na, int64_t nbr, int64_t *n) {
+    if (na == nbr || nbr == 1) { *n = na; return LCC_OK; }
+    if (na == 1) { *n = nbr; return LCC_OK; }
+    return fail(LCC_ERR_VALUE, "batch sizes must match or be 1 for broadcasting: %lld vs %lld", (long long)na, (long long)nbr);
+}
+
+lcc_status same_kind(const lcc_view *a, const lcc_view *b, const char *what) {
+    if (a->dtype != b->dtype) return fail(LCC_ERR_VALUE, "%s: operands must share one dtype", what);
+    if (a->layout != b->layout) return fail(LCC_ERR_VALUE, "%s: operands must share one layout", what);
+    return LCC_OK;
+}
+
+// device copy of gather_signs for the looped (> 32 blades) product
+lcc_status gather_signs_on_device(const lcc_algebra *calg, const int8_t **out) {
+    lcc_algebra *alg = const_cast<lcc_algebra *>(calg);
+    int dev = 0;
+    LCC_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(alg->mu_dev);
+    auto it = alg->gather_signs_dev.find(dev);
+    if (it != alg->gather_signs_dev.end()) { *out = it->second; return LCC_OK; }
+    const int nb = alg->nb;
+    std::vector<int8_t> g((size_t)nb * nb);
+    for (int k = 0; k < nb; ++k)
+        for (int i = 0; i < nb; ++i) g[(size_t)k * nb + i] = alg->signs[(size_t)i * nb + (i ^ k)];
+    int8_t *d = nullptr;
+    LCC_CUDA(cudaMalloc(&d, g.size()));
+    LCC_CUDA(cudaMemcpy(d, g.data(), g.size(), cudaMemcpyHostToDevice));
+    alg->gather_signs_dev[dev] = d;
+    *out = d;
+    return LCC_OK;
+}
+
+// RAII for stream-ordered temporaries
+struct PoolBuffer {
+    void *ptr = nullptr; cudaStream_t stream = nullptr;
+    ~PoolBuffer() { if (ptr) cudaFreeAsync(ptr, stream); }
+    lcc_status alloc(size_t bytes, cudaStream_t s) {
+        stream = s;
+        cudaError_t e = cudaMallocAsync(&ptr, bytes ? bytes : 16, s);
+        if (e != cudaSuccess) { ptr = nullptr; return cuda_fail(e, "cudaMallocAsync"); }
+        return LCC_OK;
+    }
+};
+
+int64_t padded_ld(int64_t n) { return n <= 0 ? 64 : ((n + 63) / 64) * 64; }
+
+lcc_status make_soa_temp(const lcc_algebra *alg, int dtype, int64_t n, PoolBuffer &buf, lcc_view *v, cudaStream_t s) {
+    v->n = n; v->ld = padded_ld(n); v->dtype = dtype; v->layout = LCC_SOA;
+    LCC_TRY(buf.alloc((size_t)alg->nb * v->ld * elem_size(dtype), s));
+    v->data = buf.ptr;
+    return LCC_OK;
+}
+}  // namespace
+
+// ================================================================== library / device
+extern "C" {
+
+const char *lcc_version(void) { return "0.3.0+b200.1"; }
+const char *lcc_last_error(void) { return t_error.c_str(); }
+
+lcc_status lcc_device_count(int *count) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess || c == 0) {
+        if (count) *count = 0;
+        return cuda_fail(e == cudaSuccess ? cudaErrorNoDevice : e, "cudaGetDeviceCount");
+    }
+    if (count) *count = c;
+    return LCC_OK;
+}
+lcc_status lcc_set_device(int device) { LCC_CUDA(cudaSetDevice(device)); return LCC_OK; }
+lcc_status lcc_get_device(int *device) { LCC_CUDA(cudaGetDevice(device)); return LCC_OK; }
+lcc_status lcc_stream(void **stream) {
+    DeviceState *st = nullptr;
+    LCC_TRY(device_state(&st));
+    *stream = (void *)st->stream;
+    return LCC_OK;
+}
+lcc_status lcc_stream_sync(void *stream) {
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    LCC_CUDA(cudaStreamSynchronize(s));
+    return LCC_OK;
+}
+
+// ================================================================== algebra
+lcc_status lcc_algebra_create(int p, int q, int r, lcc_algebra **out) {
+    if (!out) return fail(LCC_ERR_VALUE, "out is NULL");
+    if (p < 0 || q < 0 || r < 0) return fail(LCC_ERR_VALUE, "signature entries must be non-negative");
+    if (p + q + r > 8) return fail(LCC_ERR_UNSUPPORTED, "Cl(%d,%d,%d): at most 8 basis vectors (256 blades) are supported", p, q, r);
+    lcc_algebra *alg = new lcc_algebra();
+    build_algebra(*alg, p, q, r);
+    *out = alg;
+    return LCC_OK;
+}
+void lcc_algebra_destroy(lcc_algebra *alg) {
+    if (!alg) return;
+    for (auto &kv : alg->gather_signs_dev) cudaFree(kv.second);
+    delete alg;
+}
+int lcc_algebra_p(const lcc_algebra *a) { return a->p; }
+int lcc_algebra_q(const lcc_algebra *a) { return a->q; }
+int lcc_algebra_r(const lcc_algebra *a) { return a->r; }
+int lcc_algebra_dimension(const lcc_algebra *a) { return a->dim; }
+int lcc_algebra_num_blades(const lcc_algebra *a) { return a->nb; }
+const int8_t *lcc_algebra_cayley_signs(const lcc_algebra *a) { return a->signs.data(); }
+const uint16_t *lcc_algebra_cayley_blades(const lcc_algebra *a) { return a->blades.data(); }
+int lcc_algebra_grade_mask(const lcc_algebra *a, int grade, uint64_t *words, int capacity) {
+    const int nwords = (a->nb + 63) / 64;
+    if (words)
+        for (int w = 0; w < nwords && w < capacity; ++w)
+            words[w] = (grade >= 0 && grade <= a->dim) ? a->grade_masks[grade][w] : 0;  // registry.rs:224-232
+    return nwords;
+}
+int lcc_algebra_blade_name(const lcc_algebra *a, int index, char *buf, int capacity) {
+    if (index < 0 || index >= a->nb || !buf || capacity <= 0) return -1;
+    const std::string &s = a->names[index];
+    snprintf(buf, capacity, "%s", s.c_str());
+    return (int)s.size();
+}
+int lcc_algebra_is_specialised(const lcc_algebra *a) { return a->specialised ? 1 : 0; }
+int lcc_reverse_sign(int blade) { return reverse_sign_of_grade(popcount32((unsigned)blade)); }
+int lcc_grade_involution_sign(int blade) { return involution_sign_of_grade(popcount32((unsigned)blade)); }
+int lcc_clifford_conjugate_sign(int blade) { return conjugate_sign_of_grade(popcount32((unsigned)blade)); }
+
+// ================================================================== memory
+lcc_status lcc_device_alloc(void **ptr, size_t bytes, void *stream) {
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    cudaError_t e = cudaMallocAsync(ptr, bytes ? bytes : 16, s);
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return fail(LCC_ERR_ALLOC, "out of device memory allocating %zu bytes", bytes); }
+    LCC_CUDA(e);
+    return LCC_OK;
+}
+lcc_status lcc_device_free(void *ptr, void *stream) {
+    if (!ptr) return LCC_OK;
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    LCC_CUDA(cudaFreeAsync(ptr, s));
+    return LCC_OK;
+}
+lcc_status lcc_host_alloc_pinned(void **ptr, size_t bytes) { LCC_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 16, cudaHostAllocDefault)); return LCC_OK; }
+lcc_status lcc_host_free_pinned(void *ptr) { if (ptr) LCC_CUDA(cudaFreeHost(ptr)); return LCC_OK; }
+static lcc_status copy_async(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, void *stream) {
+    if (bytes == 0) return LCC_OK;
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    LCC_CUDA(cudaMemcpyAsync(dst, src, bytes, kind, s));
+    return LCC_OK;
+}
+lcc_status lcc_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream) { return copy_async(dst, src, bytes, cudaMemcpyHostToDevice, stream); }
+lcc_status lcc_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream) { return copy_async(dst, src, bytes, cudaMemcpyDeviceToHost, stream); }
+lcc_status lcc_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream) { return copy_async(dst, src, bytes, cudaMemcpyDeviceToDevice, stream); }
+lcc_status lcc_memset_zero(void *dst, size_t bytes, void *stream) {
+    if (bytes == 0) return LCC_OK;
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    LCC_CUDA(cudaMemsetAsync(dst, 0, bytes, s));
+    return LCC_OK;
+}
+lcc_status lcc_batch_alloc(const lcc_algebra *alg, int dtype, int64_t n, lcc_view *view, void *stream) {
+    if (!alg || !view) return fail(LCC_ERR_VALUE, "algebra / view is NULL");
+    if (dtype != LCC_F32 && dtype != LCC_F64) return fail(LCC_ERR_VALUE, "dtype must be LCC_F32 or LCC_F64");
+    if (n < 0) return fail(LCC_ERR_VALUE, "negative batch size");
+    view->n = n; view->ld = padded_ld(n); view->dtype = dtype; view->layout = LCC_SOA; view->data = nullptr;
+    return lcc_device_alloc(&view->data, (size_t)alg->nb * view->ld * elem_size(dtype), stream);
+}
+lcc_status lcc_batch_free(lcc_view *view, void *stream) {
+    if (!view || !view->data) return LCC_OK;
+    lcc_status s = lcc_device_free(view->data, stream);
+    view->data = nullptr;
+    return s;
+}
+
+// ================================================================== layout conversion / movers
+lcc_status lcc_batch_convert(const lcc_algebra *alg, const lcc_view *src, const lcc_view *dst, void *stream) {
+    LCC_TRY(check_view(alg, src, "src"));
+    LCC_TRY(check_view(alg, dst, "dst"));
+    if (src->dtype != dst->dtype) return fail(LCC_ERR_VALUE, "convert: dtype mismatch");
+    if (src->n != dst->n) return fail(LCC_ERR_VALUE, "convert: batch sizes differ: %lld vs %lld", (long long)src->n, (long long)dst->n);
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    LCC_CUDA(launch_convert(alg->nb, arg_of(src), arg_of(dst), s));
+    return LCC_OK;
+}
+
+lcc_status lcc_batch_scatter_columns(const lcc_algebra *alg, const void *cols, int ncols, const int32_t *blade_of_col,
+                                     const lcc_view *dst, void *stream) {
+    LCC_TRY(check_view(alg, dst, "dst"));
+    if (ncols < 0 || ncols > alg->nb) return fail(LCC_ERR_VALUE, "scatter: bad column count %d", ncols);
+    for (int c = 0; c < ncols; ++c)
+        if (blade_of_col[c] < 0 || blade_of_col[c] >= alg->nb) return fail(LCC_ERR_INDEX, "scatter: blade index %d out of range", blade_of_col[c]);
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    LCC_CUDA(launch_scatter_columns(alg->nb, cols, ncols, blade_of_col, arg_of(dst), s));
+    return LCC_OK;
+}
+
+lcc_status lcc_batch_gather_columns(const lcc_algebra *alg, const lcc_view *src, int ncols, const int32_t *blade_of_col,
+                                    void *cols, void *stream) {
+    LCC_TRY(check_view(alg, src, "src"));
+    if (ncols < 0 || ncols > alg->nb) return fail(LCC_ERR_VALUE, "gather: bad column count %d", ncols);
+    for (int c = 0; c < ncols; ++c)
+        if (blade_of_col[c] < 0 || blade_of_col[c] >= alg->nb) return fail(LCC_ERR_INDEX, "gather: blade index %d out of range", blade_of_col[c]);
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    LCC_CUDA(launch_gather_columns(alg->nb, arg_of(src), ncols, blade_of_col, cols, s));
+    return LCC_OK;
+}
+
+lcc_status lcc_batch_copy_rows(const lcc_algebra *alg, const lcc_view *src, int64_t start, int64_t end,
+                               const lcc_view *dst, int64_t dst_start, void *stream) {
+    LCC_TRY(check_view(alg, src, "src"));
+    LCC_TRY(check_view(alg, dst, "dst"));
+    if (src->dtype != dst->dtype) return fail(LCC_ERR_VALUE, "copy_rows: dtype mismatch");
+    if (start > src->n || end > src->n || start > end)  // batch.rs:1085-1090
+        return fail(LCC_ERR_INDEX, "invalid slice [%lld:%lld] for batch of size %lld", (long long)start, (long long)end, (long long)src->n);
+    if (dst_start < 0 || dst_start + (end - start) > dst->n)
+        return fail(LCC_ERR_INDEX, "index %lld out of bounds for batch of size %lld", (long long)dst_start, (long long)dst->n);
+    if (end == start) return LCC_OK;
+    // sub-views of SoA batches start mid-row: only the strided-copy / transpose paths touch them, no alignment needed
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    LCC_CUDA(launch_copy_rows(alg->nb, arg_of(src), start, end, arg_of(dst), dst_start, s));
+    return LCC_OK;
+}
+
+// ================================================================== the hot path
+static lcc_status run_product(const lcc_algebra *alg, int op, const lcc_view *a, const lcc_view *b, const lcc_view *out,
+                              const lcc_view *out2, unsigned flags, void *stream) {
+    LCC_TRY(check_view(alg, a, "a"));
+    LCC_TRY(check_view(alg, b, "b"));
+    LCC_TRY(check_view(alg, out, "out"));
+    LCC_TRY(same_kind(a, b, "product"));
+    LCC_TRY(same_kind(a, out, "product"));
+    if (out2) { LCC_TRY(check_view(alg, out2, "outer_out")); LCC_TRY(same_kind(a, out2, "product")); }
+    int64_t n = 0;
+    LCC_TRY(broadcast_rows(a->n, b->n, &n));
+    if (out->n != n || (out2 && out2->n != n)) return fail(LCC_ERR_VALUE, "product: output has %lld rows, expected %lld", (long long)out->n, (long long)n);
+    if (n == 0) return LCC_OK;
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    const bool strict = (flags & LCC_FLAG_STRICT_FP) != 0;
+    const bool a_bc = a->n == 1 && n > 1, b_bc = b->n == 1 && n > 1;
+    if (alg->nb <= 32) {
+        ProductLauncher launch = alg->product[a->dtype];
+        if (!launch) return fail(LCC_ERR_UNSUPPORTED, "no product kernel built for %s", sig_str(alg).c_str());
+        ProductArgs g;
+        g.op = op; g.dtype = a->dtype; g.layout = a->layout; g.strict = strict; g.n = n;
+        g.a = a->data; g.lda = a->ld; g.a_bcast = a_bc;
+        g.b = b->data; g.ldb = b->ld; g.b_bcast = b_bc;
+        g.out = out->data; g.ldo = out->ld;
+        if (out2) { g.out2 = out2->data; g.ldo2 = out2->ld; }
+        g.mu = alg->specialised ? nullptr : alg->mu.data();
+        g.stream = s;
+        LCC_CUDA(launch(g));
+        return LCC_OK;
+    }
+    // 64..256 blades: looped shared-memory kernel on SoA data (AoS operands are transposed through pool temporaries)
+    const int8_t *gs = nullptr;
+    LCC_TRY(gather_signs_on_device(alg, &gs));
+    auto one = [&](int single_op, const lcc_view *dst) -> lcc_status {
+        if (a->layout == LCC_SOA) {
+            LCC_CUDA(launch_big_product(alg->nb, single_op, strict, arg_of(a), a_bc, arg_of(b), b_bc, arg_of(dst), gs, s));
+            return LCC_OK;
+        }
+        PoolBuffer ba, bb, bo;
+        lcc_view ta, tb, to;
+        LCC_TRY(make_soa_temp(alg, a->dtype, a->n, ba, &ta, s));
+        LCC_TRY(make_soa_temp(alg, a->dtype, b->n, bb, &tb, s));
+        LCC_TRY(make_soa_temp(alg, a->dtype, n, bo, &to, s));
+        LCC_CUDA(launch_convert(alg->nb, arg_of(a), arg_of(&ta), s));
+        LCC_CUDA(launch_convert(alg->nb, arg_of(b), arg_of(&tb), s));
+        LCC_CUDA(launch_big_product(alg->nb, single_op, strict, arg_of(&ta), a_bc, arg_of(&tb), b_bc, arg_of(&to), gs, s));
+        LCC_CUDA(launch_convert(alg->nb, arg_of(&to), arg_of(dst), s));
+        return LCC_OK;
+    };
+    if (op == kOpGPOuter) { LCC_TRY(one(kOpGP, out)); return one(kOpOuter, out2); }
+    return one(op, out);
+}
+
+lcc_status lcc_batch_product(const lcc_algebra *alg, int op, const lcc_view *a, const lcc_view *b, const lcc_view *out,
+                             unsigned flags, void *stream) {
+    if (op != LCC_OP_GP && op != LCC_OP_OUTER && op != LCC_OP_LC) return fail(LCC_ERR_VALUE, "unknown product op %d", op);
+    return run_product(alg, op, a, b, out, nullptr, flags, stream);
+}
+
+lcc_status lcc_batch_gp_outer(const lcc_algebra *alg, const lcc_view *a, const lcc_view *b, const lcc_view *gp_out,
+                              const lcc_view *outer_out, unsigned flags, void *stream) {
+    if (!outer_out) return fail(LCC_ERR_VALUE, "outer_out is NULL");
+    return run_product(alg, kOpGPOuter, a, b, gp_out, outer_out, flags, stream);
+}
+
+lcc_status lcc_batch_sandwich(const lcc_algebra *alg, const double *rotor, const lcc_view *x, const lcc_view *out,
+                              unsigned flags, void *stream) {
+    LCC_TRY(check_view(alg, x, "x"));
+    LCC_TRY(check_view(alg, out, "out"));
+    LCC_TRY(same_kind(x, out, "sandwich"));
+    if (!rotor) return fail(LCC_ERR_VALUE, "rotor is NULL");
+    if (x->n != out->n) return fail(LCC_ERR_VALUE, "sandwich: output has %lld rows, expected %lld", (long long)out->n, (long long)x->n);
+    if (x->n == 0) return LCC_OK;
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    const bool strict = (flags & LCC_FLAG_STRICT_FP) != 0;
+    const int nb = alg->nb;
+    if (nb <= 32) {
+        SandwichLauncher launch = alg->sandwich[x->dtype];
+        if (!launch) return fail(LCC_ERR_UNSUPPORTED, "no sandwich kernel built for %s", sig_str(alg).c_str());
+        SandwichArgs g;
+        g.dtype = x->dtype; g.layout = x->layout; g.strict = strict; g.n = x->n;
+        g.even = true;
+        for (int i = 0; i < nb; ++i)
+            if ((popcount32((unsigned)i) & 1) && rotor[i] != 0.0) g.even = false;
+        g.rotor = rotor; g.x = x->data; g.ldx = x->ld; g.out = out->data; g.ldo = out->ld;
+        g.mu = alg->specialised ? nullptr : alg->mu.data();
+        g.stream = s;
+        LCC_CUDA(launch(g));
+        return LCC_OK;
+    }
+    // > 32 blades: two looped products with the rotor as a one-row batch (batch.rs:462-496)
+    const size_t es = elem_size(x->dtype);
+    std::vector<unsigned char> host((size_t)2 * nb * es);
+    for (int i = 0; i < nb; ++i) {
+        const double rev = rotor[i] * reverse_sign_of_grade(popcount32((unsigned)i));
+        if (x->dtype == LCC_F32) { ((float *)host.data())[i] = (float)rotor[i]; ((float *)host.data())[nb + i] = (float)rotor[i] * (float)reverse_sign_of_grade(popcount32((unsigned)i)); }
+        else { ((double *)host.data())[i] = rotor[i]; ((double *)host.data())[nb + i] = rev; }
+    }
+    PoolBuffer br, brx;
+    LCC_TRY(br.alloc(host.size(), s));
+    LCC_CUDA(cudaMemcpyAsync(br.ptr, host.data(), host.size(), cudaMemcpyHostToDevice, s));
+    LCC_CUDA(cudaStreamSynchronize(s));  // host staging vector goes out of scope
+    // one-row SoA views with ld = 1: blade k of the rotor at data[k] (the looped kernel uses scalar loads)
+    lcc_view r1{br.ptr, 1, 1, x->dtype, LCC_SOA};
+    lcc_view r2{(char *)br.ptr + nb * es, 1, 1, x->dtype, LCC_SOA};
+    lcc_view rx;
+    LCC_TRY(make_soa_temp(alg, x->dtype, x->n, brx, &rx, s));
+    const int8_t *gs = nullptr;
+    LCC_TRY(gather_signs_on_device(alg, &gs));
+    auto big = [&](const lcc_view *a, bool a_bc, const lcc_view *b, bool b_bc, const lcc_view *dst) -> lcc_status {
+        LCC_CUDA(launch_big_product(nb, kOpGP, strict, arg_of(a), a_bc, arg_of(b), b_bc, arg_of(dst), gs, s));
+        return LCC_OK;
+    };
+    if (x->layout == LCC_SOA) {
+        LCC_TRY(big(&r1, true, x, false, &rx));
+        LCC_TRY(big(&rx, false, &r2, true, out));
+        return LCC_OK;
+    }
+    PoolBuffer bx, bo;
+    lcc_view tx, to;
+    LCC_TRY(make_soa_temp(alg, x->dtype, x->n, bx, &tx, s));
+    LCC_TRY(make_soa_temp(alg, x->dtype, x->n, bo, &to, s));
+    LCC_CUDA(launch_convert(nb, arg_of(x), arg_of(&tx), s));
+    LCC_TRY(big(&r1, true, &tx, false, &rx));
+    LCC_TRY(big(&rx, false, &r2, true, &to));
+    LCC_CUDA(launch_convert(nb, arg_of(&to), arg_of(out), s));
+    return LCC_OK;
+}
+
+lcc_status lcc_batch_sandwich_rows(const lcc_algebra *alg, const lcc_view *rotors, const lcc_view *x, const lcc_view *out,
+                                   unsigned flags, void *stream) {
+    LCC_TRY(check_view(alg, rotors, "rotors"));
+    LCC_TRY(check_view(alg, x, "x"));
+    LCC_TRY(check_view(alg, out, "out"));
+    if (rotors->n != x->n && rotors->n != 1) return fail(LCC_ERR_VALUE, "batch sizes must match or be 1 for broadcasting: %lld vs %lld", (long long)rotors->n, (long long)x->n);
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    // rx = R * x ; out = rx * ~R   (lcc/torch/multivector.py:1006-1017), composed from K1 and K3
+    PoolBuffer brev, brx;
+    lcc_view rev = *rotors, rx = *x;
+    const size_t es = elem_size(x->dtype);
+    const int64_t rows_r = rotors->layout == LCC_SOA ? rotors->ld : rotors->n;
+    const int64_t rows_x = x->layout == LCC_SOA ? x->ld : x->n;
+    LCC_TRY(brev.alloc((size_t)(rotors->layout == LCC_SOA ? alg->nb * rows_r : rows_r * rotors->ld) * es, s));
+    LCC_TRY(brx.alloc((size_t)(x->layout == LCC_SOA ? alg->nb * rows_x : rows_x * x->ld) * es, s));
+    rev.data = brev.ptr; rx.data = brx.ptr;
+    LCC_TRY(lcc_batch_unary(alg, LCC_UN_REVERSE, 0, rotors, &rev, (void *)s));
+    LCC_TRY(run_product(alg, kOpGP, rotors, x, &rx, nullptr, flags, (void *)s));
+    return run_product(alg, kOpGP, &rx, &rev, out, nullptr, flags, (void *)s);
+}
+
+lcc_status lcc_batch_unary(const lcc_algebra *alg, int op, int arg, const lcc_view *x, const lcc_view *out, void *stream) {
+    LCC_TRY(check_view(alg, x, "x"));
+    LCC_TRY(check_view(alg, out, "out"));
+    LCC_TRY(same_kind(x, out, "unary"));
+    if (x->n != out->n) return fail(LCC_ERR_VALUE, "unary: output has %lld rows, expected %lld", (long long)out->n, (long long)x->n);
+    const int nb = alg->nb, ps = nb - 1;
+    auto S = [&](int a, int b) { return (int)alg->signs[(size_t)a * nb + b]; };
+    BladeMap map;
+    for (int k = 0; k < 256; ++k) { map.factor[k] = 0; map.source[k] = (uint16_t)(k < nb ? k : 0); }
+    for (int k = 0; k < nb; ++k) {
+        const int g = popcount32((unsigned)k);
+        switch (op) {
+            case LCC_UN_REVERSE: map.factor[k] = (int8_t)reverse_sign_of_grade(g); break;
+            case LCC_UN_INVOLUTE: map.factor[k] = (int8_t)involution_sign_of_grade(g); break;
+            case LCC_UN_CONJUGATE: map.factor[k] = (int8_t)conjugate_sign_of_grade(g); break;
+            case LCC_UN_GRADE: map.factor[k] = g == arg ? 1 : 0; break;
+            case LCC_UN_EVEN: map.factor[k] = (g % 2 == 0) ? 1 : 0; break;
+            case LCC_UN_ODD: map.factor[k] = (g % 2 == 1) ? 1 : 0; break;
+            case LCC_UN_COPY: map.factor[k] = 1; break;
+            // out[i^ps] = S[i][ps]*S[ps][ps]*a[i]  (A * I^-1, I^-1 = S[ps][ps]*e_ps; multivector.rs:4249-4255,2989-2999)
+            case LCC_UN_DUAL: map.source[k] = (uint16_t)(k ^ ps); map.factor[k] = (int8_t)(S(k ^ ps, ps) * S(ps, ps)); break;
+            case LCC_UN_UNDUAL: map.source[k] = (uint16_t)(k ^ ps); map.factor[k] = (int8_t)S(k ^ ps, ps); break;  // A * I, :4270-4274
+            case LCC_UN_RIGHT_DUAL: map.source[k] = (uint16_t)(k ^ ps); map.factor[k] = (int8_t)(S(ps, k ^ ps) * S(ps, ps)); break;  // I^-1 * A, :4285-4290
+            // out[15^i] = reverse_sign(grade i) * a[i]  (src/pga.rs:534-549)
+            case LCC_UN_PGA_DUAL: map.source[k] = (uint16_t)(k ^ ps); map.factor[k] = (int8_t)reverse_sign_of_grade(popcount32((unsigned)(k ^ ps))); break;
+            default: return fail(LCC_ERR_VALUE, "unknown unary op %d", op);
+        }
+    }
+    if (op == LCC_UN_GRADE && (arg < 0 || arg > alg->dim))  // batch.rs:1029-1033
+        return fail(LCC_ERR_VALUE, "grade %d exceeds dimension %d of algebra", arg, alg->dim);
+    if ((op == LCC_UN_DUAL || op == LCC_UN_RIGHT_DUAL) && !alg->pseudoscalar_invertible)  // multivector.rs:2991-2996
+        return fail(LCC_ERR_VALUE, "cannot invert multivector with zero norm; the pseudoscalar of %s squares to 0 "
+                    "(use pga_dual for PGA)", sig_str(alg).c_str());
+    if (op == LCC_UN_PGA_DUAL && !(alg->p == 3 && alg->q == 0 && alg->r == 1))
+        return fail(LCC_ERR_VALUE, "pga_dual requires a PGA3D element");
+    if (x->n == 0) return LCC_OK;
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    LCC_CUDA(launch_blade_map(nb, arg_of(x), arg_of(out), map, 1.0, s));
+    return LCC_OK;
+}
+
+lcc_status lcc_batch_scale(const lcc_algebra *alg, const lcc_view *x, double factor, const lcc_view *out, void *stream) {
+    LCC_TRY(check_view(alg, x, "x"));
+    LCC_TRY(check_view(alg, out, "out"));
+    LCC_TRY(same_kind(x, out, "scale"));
+    if (x->n != out->n) return fail(LCC_ERR_VALUE, "scale: output has %lld rows, expected %lld", (long long)out->n, (long long)x->n);
+    if (x->n == 0) return LCC_OK;
+    BladeMap map;
+    for (int k = 0; k < 256; ++k) { map.factor[k] = k < alg->nb ? 1 : 0; map.source[k] = (uint16_t)(k < alg->nb ? k : 0); }
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    LCC_CUDA(launch_blade_map(alg->nb, arg_of(x), arg_of(out), map, factor, s));
+    return LCC_OK;
+}
+
+lcc_status lcc_batch_elementwise(const lcc_algebra *alg, int op, const lcc_view *a, const lcc_view *b, const lcc_view *out, void *stream) {
+    LCC_TRY(check_view(alg, a, "a"));
+    LCC_TRY(check_view(alg, b, "b"));
+    LCC_TRY(check_view(alg, out, "out"));
+    LCC_TRY(same_kind(a, b, "elementwise"));
+    LCC_TRY(same_kind(a, out, "elementwise"));
+    if (op != LCC_EW_ADD && op != LCC_EW_SUB) return fail(LCC_ERR_VALUE, "unknown elementwise op %d", op);
+    int64_t n = 0;
+    LCC_TRY(broadcast_rows(a->n, b->n, &n));
+    if (out->n != n) return fail(LCC_ERR_VALUE, "elementwise: output has %lld rows, expected %lld", (long long)out->n, (long long)n);
+    if (n == 0) return LCC_OK;
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    LCC_CUDA(launch_addsub(alg->nb, op, arg_of(a), a->n == 1 && n > 1, arg_of(b), b->n == 1 && n > 1, arg_of(out), s));
+    return LCC_OK;
+}
+
+lcc_status lcc_batch_norm(const lcc_algebra *alg, int kind, const lcc_view *x, void *norms, unsigned flags, void *stream) {
+    LCC_TRY(check_view(alg, x, "x"));
+    if (kind != LCC_NORM_SQUARED && kind != LCC_NORM) return fail(LCC_ERR_VALUE, "unknown norm kind %d", kind);
+    if (x->n == 0) return LCC_OK;
+    if (!norms) return fail(LCC_ERR_VALUE, "norms is NULL");
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    ViewArg none{nullptr, 0, 0, x->dtype, x->layout};
+    LCC_CUDA(launch_norm(alg->nb, kind == LCC_NORM_SQUARED ? 0 : 1, (flags & LCC_FLAG_STRICT_FP) != 0, arg_of(x),
+                         alg->norm_weights.data(), norms, none, s));
+    return LCC_OK;
+}
+
+lcc_status lcc_batch_normalized(const lcc_algebra *alg, const lcc_view *x, const lcc_view *out, unsigned flags, void *stream) {
+    LCC_TRY(check_view(alg, x, "x"));
+    LCC_TRY(check_view(alg, out, "out"));
+    LCC_TRY(same_kind(x, out, "normalized"));
+    if (x->n != out->n) return fail(LCC_ERR_VALUE, "normalized: output has %lld rows, expected %lld", (long long)out->n, (long long)x->n);
+    if (x->n == 0) return LCC_OK;
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    LCC_CUDA(launch_norm(alg->nb, 2, (flags & LCC_FLAG_STRICT_FP) != 0, arg_of(x), alg->norm_weights.data(), nullptr, arg_of(out), s));
+    return LCC_OK;
+}
+
+lcc_status lcc_batch_sum(const lcc_algebra *alg, const lcc_view *x, void *sums_dev, void *stream) {
+    LCC_TRY(check_view(alg, x, "x"));
+    if (!sums_dev) return fail(LCC_ERR_VALUE, "sums_dev is NULL");
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    PoolBuffer scratch;
+    const int64_t elems = sum_scratch_elems(alg->nb, x->n);
+    LCC_TRY(scratch.alloc((size_t)elems * sizeof(double), s));
+    LCC_CUDA(launch_sum(alg->nb, arg_of(x), sums_dev, scratch.ptr, elems, s));
+    return LCC_OK;
+}
+
+// ================================================================== PGA / CGA points
+static lcc_status points_check(const lcc_algebra *alg, int which) {
+    if (which == 0 && !(alg->p == 3 && alg->q == 0 && alg->r == 1))
+        return fail(LCC_ERR_VALUE, "pga_point requires a PGA3D algebra Cl(3,0,1)");  // src/pga.rs:110-114
+    if (which == 1 && !(alg->q == 1 && alg->r == 0 && alg->dim == 5))
+        return fail(LCC_ERR_VALUE, "cga_point(x,y,z) requires CGA3D (dimension 5); use Algebra.cga(3)");  // src/cga.rs:172-184
+    return LCC_OK;
+}
+static lcc_status points_embed(const lcc_algebra *alg, int which, const void *xyz, const lcc_view *dst, void *stream) {
+    LCC_TRY(check_view(alg, dst, "dst"));
+    LCC_TRY(points_check(alg, which));
+    if (dst->n == 0) return LCC_OK;
+    if (!xyz) return fail(LCC_ERR_VALUE, "xyz is NULL");
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    LCC_CUDA(launch_points_embed(which, xyz, arg_of(dst), s));
+    return LCC_OK;
+}
+static lcc_status points_extract(const lcc_algebra *alg, int which, const lcc_view *src, void *xyz, void *stream) {
+    LCC_TRY(check_view(alg, src, "src"));
+    LCC_TRY(points_check(alg, which));
+    if (src->n == 0) return LCC_OK;
+    if (!xyz) return fail(LCC_ERR_VALUE, "xyz is NULL");
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    LCC_CUDA(launch_points_extract(which, arg_of(src), xyz, s));
+    return LCC_OK;
+}
+lcc_status lcc_pga_points_embed(const lcc_algebra *alg, const void *xyz, const lcc_view *dst, void *stream) { return points_embed(alg, 0, xyz, dst, stream); }
+lcc_status lcc_pga_points_extract(const lcc_algebra *alg, const lcc_view *src, void *xyz, void *stream) { return points_extract(alg, 0, src, xyz, stream); }
+lcc_status lcc_cga_points_embed(const lcc_algebra *alg, const void *xyz, const lcc_view *dst, void *stream) { return points_embed(alg, 1, xyz, dst, stream); }
+lcc_status lcc_cga_points_extract(const lcc_algebra *alg, const lcc_view *src, void *xyz, void *stream) { return points_extract(alg, 1, src, xyz, stream); }
+
+// ================================================================== host-buffer (end-to-end) entry points
+// Chunked three-stream pipeline: H2D copy of chunk c+1, kernel of chunk c and D2H copy of chunk
+// c-1 overlap.  Kernels run directly on the reference's AoS layout, so each chunk crosses HBM once
+// in each direction and PCIe is the only bound.
+namespace {
+constexpr int64_t kChunkBytes = 64ll << 20;
+
+struct Pipeline {
+    DeviceState *st = nullptr;
+    cudaEvent_t h2d[2]{}, kern[2]{}, d2h[2]{};
+    bool made = false;
+    lcc_status init() {
+        LCC_TRY(device_state(&st));
+        for (int i = 0; i < 2; ++i) {
+            LCC_CUDA(cudaEventCreateWithFlags(&h2d[i], cudaEventDisableTiming));
+            LCC_CUDA(cudaEventCreateWithFlags(&kern[i], cudaEventDisableTiming));
+            LCC_CUDA(cudaEventCreateWithFlags(&d2h[i], cudaEventDisableTiming));
+        }
+        made = true;
+        return LCC_OK;
+    }
+    ~Pipeline() {
+        if (!made) return;
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(h2d[i]); cudaEventDestroy(kern[i]); cudaEventDestroy(d2h[i]); }
+    }
+};
+}  // namespace
+
+lcc_status lcc_host_sandwich(const lcc_algebra *alg, int dtype, const double *rotor, const void *x_host, void *out_host,
+                             int64_t n, unsigned flags) {
+    if (!alg) return fail(LCC_ERR_VALUE, "algebra handle is NULL");
+    if (dtype != LCC_F32 && dtype != LCC_F64) return fail(LCC_ERR_VALUE, "dtype must be LCC_F32 or LCC_F64");
+    if (n < 0) return fail(LCC_ERR_VALUE, "negative batch size");
+    if (n == 0) return LCC_OK;
+    if (!rotor || !x_host || !out_host) return fail(LCC_ERR_VALUE, "NULL buffer");
+    Pipeline pl;
+    LCC_TRY(pl.init());
+    const size_t row_bytes = (size_t)alg->nb * elem_size(dtype);
+    int64_t chunk = kChunkBytes / (int64_t)row_bytes;
+    if (chunk > n) chunk = n;
+    PoolBuffer in[2], out[2];
+    for (int i = 0; i < 2; ++i) { LCC_TRY(in[i].alloc(chunk * row_bytes, pl.st->stream)); LCC_TRY(out[i].alloc(chunk * row_bytes, pl.st->stream)); }
+    LCC_CUDA(cudaStreamSynchronize(pl.st->stream));  // buffers exist before the copy streams touch them
+    int64_t done = 0;
+    for (int64_t c = 0; done < n; ++c, done += chunk) {
+        const int buf = (int)(c & 1);
+        const int64_t rows = (n - done) < chunk ? (n - done) : chunk;
+        if (c >= 2) LCC_CUDA(cudaStreamWaitEvent(pl.st->copy_in, pl.kern[buf], 0));
+        LCC_CUDA(cudaMemcpyAsync(in[buf].ptr, (const char *)x_host + done * row_bytes, rows * row_bytes, cudaMemcpyHostToDevice, pl.st->copy_in));
+        LCC_CUDA(cudaEventRecord(pl.h2d[buf], pl.st->copy_in));
+        LCC_CUDA(cudaStreamWaitEvent(pl.st->stream, pl.h2d[buf], 0));
+        if (c >= 2) LCC_CUDA(cudaStreamWaitEvent(pl.st->stream, pl.d2h[buf], 0));
+        lcc_view vx{in[buf].ptr, rows, alg->nb, dtype, LCC_AOS}, vo{out[buf].ptr, rows, alg->nb, dtype, LCC_AOS};
+        LCC_TRY(lcc_batch_sandwich(alg, rotor, &vx, &vo, flags, (void *)pl.st->stream));
+        LCC_CUDA(cudaEventRecord(pl.kern[buf], pl.st->stream));
+        LCC_CUDA(cudaStreamWaitEvent(pl.st->copy_out, pl.kern[buf], 0));
+        LCC_CUDA(cudaMemcpyAsync((char *)out_host + done * row_bytes, out[buf].ptr, rows * row_bytes, cudaMemcpyDeviceToHost, pl.st->copy_out));
+        LCC_CUDA(cudaEventRecord(pl.d2h[buf], pl.st->copy_out));
+    }
+    LCC_CUDA(cudaStreamSynchronize(pl.st->copy_out));
+    LCC_CUDA(cudaStreamSynchronize(pl.st->stream));
+    return LCC_OK;
+}
+
+lcc_status lcc_host_product(const lcc_algebra *alg, int dtype, int op, const void *a_host, int64_t na, const void *b_host,
+                            int64_t nb_rows, void *out_host, unsigned flags) {
+    if (!alg) return fail(LCC_ERR_VALUE, "algebra handle is NULL");
+    if (dtype != LCC_F32 && dtype != LCC_F64) return fail(LCC_ERR_VALUE, "dtype must be LCC_F32 or LCC_F64");
+    if (op != LCC_OP_GP && op != LCC_OP_OUTER && op != LCC_OP_LC) return fail(LCC_ERR_VALUE, "unknown product op %d", op);
+    int64_t n = 0;
+    LCC_TRY(broadcast_rows(na, nb_rows, &n));
+    if (n == 0) return LCC_OK;
+    if (!a_host || !b_host || !out_host) return fail(LCC_ERR_VALUE, "NULL buffer");
+    Pipeline pl;
+    LCC_TRY(pl.init());
+    const size_t row_bytes = (size_t)alg->nb * elem_size(dtype);
+    int64_t chunk = kChunkBytes / (int64_t)row_bytes;
+    if (chunk > n) chunk = n;
+    const bool a_bc = na == 1 && n > 1, b_bc = nb_rows == 1 && n > 1;
+    PoolBuffer ia[2], ib[2], out[2];
+    for (int i = 0; i < 2; ++i) {
+        LCC_TRY(ia[i].alloc((a_bc ? 1 : chunk) * row_bytes, pl.st->stream));
+        LCC_TRY(ib[i].alloc((b_bc ? 1 : chunk) * row_bytes, pl.st->stream));
+        LCC_TRY(out[i].alloc(chunk * row_bytes, pl.st->stream));
+    }
+    if (a_bc) LCC_CUDA(cudaMemcpyAsync(ia[0].ptr, a_host, row_bytes, cudaMemcpyHostToDevice, pl.st->stream));
+    if (b_bc) LCC_CUDA(cudaMemcpyAsync(ib[0].ptr, b_host, row_bytes, cudaMemcpyHostToDevice, pl.st->stream));
+    LCC_CUDA(cudaStreamSynchronize(pl.st->stream));
+    int64_t done = 0;
+    for (int64_t c = 0; done < n; ++c, done += chunk) {
+        const int buf = (int)(c & 1);
+        const int64_t rows = (n - done) < chunk ? (n - done) : chunk;
+        if (c >= 2) LCC_CUDA(cudaStreamWaitEvent(pl.st->copy_in, pl.kern[buf], 0));
+        if (!a_bc) LCC_CUDA(cudaMemcpyAsync(ia[buf].ptr, (const char *)a_host + done * row_bytes, rows * row_bytes, cudaMemcpyHostToDevice, pl.st->copy_in));
+        if (!b_bc) LCC_CUDA(cudaMemcpyAsync(ib[buf].ptr, (const char *)b_host + done * row_bytes, rows * row_bytes, cudaMemcpyHostToDevice, pl.st->copy_in));
+        LCC_CUDA(cudaEventRecord(pl.h2d[buf], pl.st->copy_in));
+        LCC_CUDA(cudaStreamWaitEvent(pl.st->stream, pl.h2d[buf], 0));
+        if (c >= 2) LCC_CUDA(cudaStreamWaitEvent(pl.st->stream, pl.d2h[buf], 0));
+        lcc_view va{a_bc ? ia[0].ptr : ia[buf].ptr, a_bc ? 1 : rows, alg->nb, dtype, LCC_AOS};
+        lcc_view vb{b_bc ? ib[0].ptr : ib[buf].ptr, b_bc ? 1 : rows, alg->nb, dtype, LCC_AOS};
+        lcc_view vo{out[buf].ptr, rows, alg->nb, dtype, LCC_AOS};
+        LCC_TRY(lcc_batch_product(alg, op, &va, &vb, &vo, flags, (void *)pl.st->stream));
+        LCC_CUDA(cudaEventRecord(pl.kern[buf], pl.st->stream));
+        LCC_CUDA(cudaStreamWaitEvent(pl.st->copy_out, pl.kern[buf], 0));
+        LCC_CUDA(cudaMemcpyAsync((char *)out_host + done * row_bytes, out[buf].ptr, rows * row_bytes, cudaMemcpyDeviceToHost, pl.st->copy_out));
+        LCC_CUDA(cudaEventRecord(pl.d2h[buf], pl.st->copy_out));
+    }
+    LCC_CUDA(cudaStreamSynchronize(pl.st->copy_out));
+    LCC_CUDA(cudaStreamSynchronize(pl.st->stream));
+    return LCC_OK;
+}
+
+// ================================================================== instrumentation
+uint64_t lcc_kernel_launch_count(void) { return t_launches; }
+void lcc_kernel_launch_count_reset(void) { t_launches = 0; }
+
+}  // extern "C"

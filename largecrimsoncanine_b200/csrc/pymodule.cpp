@@ -1,0 +1,910 @@
+// pymodule.cpp -- CPython extension `largecrimsoncanine`: the host-side mirror of the reference's
+// PyO3 boundary (/root/reference/src/lib.rs:37-45) over the C ABI of include/lcc_b200.h.
+//
+//   Algebra          <- src/pyalgebra.rs:30-200
+//   Multivector      <- the host value type of src/multivector.rs (the subset SURVEY.md Appendix B
+//                       lists).  It only carries coefficients; every PRODUCT it offers is executed by
+//                       the same CUDA kernels as a one-row batch -- there is no CPU product loop here.
+//   MultivectorBatch <- src/batch.rs:39-1098, device resident (structure-of-arrays in HBM)
+//
+// Same names, argument meaning, exception types and message substrings as the reference so its own
+// tests run unmodified (tests/test_reference_suites.py).  Written in C++ because the reference's
+// host layer is compiled Rust and this image has no Rust toolchain.
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <cmath>
+#include <cstdlib>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "lcc_b200.h"
+
+namespace py = pybind11;
+
+namespace {
+
+// ------------------------------------------------------------------ error translation
+[[noreturn]] void raise_status(lcc_status st) {
+    const std::string msg = lcc_last_error();
+    switch (st) {
+        case LCC_ERR_VALUE: throw py::value_error(msg);
+        case LCC_ERR_INDEX: throw py::index_error(msg);
+        case LCC_ERR_ZERODIV: { py::gil_scoped_acquire gil; PyErr_SetString(PyExc_ZeroDivisionError, msg.c_str()); throw py::error_already_set(); }
+        case LCC_ERR_ALLOC: throw std::bad_alloc();  // pybind11 maps this to MemoryError
+        default: throw std::runtime_error(msg);
+    }
+}
+inline void check(lcc_status st) { if (st != LCC_OK) raise_status(st); }
+
+bool g_strict_fp = [] { const char *e = std::getenv("LCC_STRICT_FP"); return e && e[0] && e[0] != '0'; }();
+inline unsigned fp_flags() { return g_strict_fp ? LCC_FLAG_STRICT_FP : 0u; }
+
+inline int popcount(unsigned v) { return __builtin_popcount(v); }
+inline double reverse_sign(int grade) { return (grade % 4 < 2) ? 1.0 : -1.0; }
+
+// ------------------------------------------------------------------ Algebra
+struct AlgebraHandle {
+    lcc_algebra *h = nullptr;
+    int p, q, r;
+    AlgebraHandle(int p_, int q_, int r_) : p(p_), q(q_), r(r_) { check(lcc_algebra_create(p_, q_, r_, &h)); }
+    ~AlgebraHandle() { lcc_algebra_destroy(h); }
+    AlgebraHandle(const AlgebraHandle &) = delete;
+    int dim() const { return p + q + r; }
+    int nb() const { return 1 << dim(); }
+    bool same_signature(const AlgebraHandle &o) const { return p == o.p && q == o.q && r == o.r; }
+    bool is_euclidean() const { return q == 0 && r == 0; }
+    bool is_pga() const { return q == 0 && r == 1; }
+    std::string str() const { std::ostringstream s; s << "Cl(" << p << "," << q << "," << r << ")"; return s.str(); }
+};
+using AlgebraPtr = std::shared_ptr<AlgebraHandle>;
+
+struct PyAlgebra { AlgebraPtr inner; };
+
+PyAlgebra make_algebra(long p, long q, long r) {
+    if (p < 0 || q < 0 || r < 0) throw py::type_error("signature entries must be non-negative integers");
+    return PyAlgebra{std::make_shared<AlgebraHandle>((int)p, (int)q, (int)r)};
+}
+
+// get_euclidean, src/algebra/registry.rs:275-303
+AlgebraPtr cached_euclidean(int n) {
+    static std::mutex m;
+    static std::map<int, AlgebraPtr> cache;
+    std::lock_guard<std::mutex> lock(m);
+    auto it = cache.find(n);
+    if (it != cache.end()) return it->second;
+    auto a = std::make_shared<AlgebraHandle>(n, 0, 0);
+    cache[n] = a;
+    return a;
+}
+
+// ------------------------------------------------------------------ one-row device products (Multivector)
+// Runs op(a, b) for ONE pair through lcc_batch_product on the GPU (array-of-structures views, n = 1).
+std::vector<double> device_pair_product(const AlgebraPtr &alg, int op, const std::vector<double> &a, const std::vector<double> &b) {
+    const int nb = alg->nb();
+    const size_t bytes = (size_t)nb * sizeof(double);
+    void *buf = nullptr;
+    check(lcc_device_alloc(&buf, 3 * bytes, nullptr));
+    std::vector<double> out(nb);
+    char *base = (char *)buf;
+    lcc_status st = lcc_memcpy_h2d(base, a.data(), bytes, nullptr);
+    if (st == LCC_OK) st = lcc_memcpy_h2d(base + bytes, b.data(), bytes, nullptr);
+    lcc_view va{base, 1, nb, LCC_F64, LCC_AOS}, vb{base + bytes, 1, nb, LCC_F64, LCC_AOS}, vo{base + 2 * bytes, 1, nb, LCC_F64, LCC_AOS};
+    if (st == LCC_OK) st = lcc_batch_product(alg->h, op, &va, &vb, &vo, fp_flags(), nullptr);
+    if (st == LCC_OK) st = lcc_memcpy_d2h(out.data(), base + 2 * bytes, bytes, nullptr);
+    if (st == LCC_OK) st = lcc_stream_sync(nullptr);
+    lcc_device_free(buf, nullptr);
+    check(st);
+    return out;
+}
+
+// ------------------------------------------------------------------ Multivector (host value type)
+struct Multivector {
+    std::vector<double> coeffs;
+    int dims = 0;
+    AlgebraPtr algebra_opt;  // may be null: "legacy" Euclidean multivector (src/multivector.rs:24-45)
+
+    AlgebraPtr get_algebra() const { return algebra_opt ? algebra_opt : cached_euclidean(dims); }
+
+    // src/multivector.rs:48-55
+    bool same_algebra(const Multivector &o) const {
+        if (algebra_opt && o.algebra_opt) return algebra_opt.get() == o.algebra_opt.get() || algebra_opt->same_signature(*o.algebra_opt);
+        if (!algebra_opt && !o.algebra_opt) return dims == o.dims;
+        const AlgebraPtr &a = algebra_opt ? algebra_opt : o.algebra_opt;
+        const int other_dims = algebra_opt ? o.dims : dims;
+        return a->is_euclidean() && a->dim() == other_dims;
+    }
+    Multivector like(std::vector<double> c, bool keep_algebra = true) const { return Multivector{std::move(c), dims, keep_algebra ? algebra_opt : nullptr}; }
+
+    static Multivector from_coeffs(std::vector<double> c) {  // src/multivector.rs:123-142
+        const size_t len = c.size();
+        if (len == 0) throw py::value_error("coeffs must not be empty; provide a list of coefficients (e.g., [1.0] for a scalar, [0.0, 1.0, 0.0, 0.0] for e1 in 2D)");
+        if (len & (len - 1)) {
+            size_t lower = 1; while (lower * 2 < len) lower *= 2;
+            std::ostringstream s; s << "coeffs length must be a power of 2 (got " << len << ", expected " << lower << " or " << lower * 2 << ")";
+            throw py::value_error(s.str());
+        }
+        int dims = 0; while ((size_t(1) << dims) < len) ++dims;
+        return Multivector{std::move(c), dims, nullptr};
+    }
+    Multivector product(int op, const Multivector &o) const {  // src/multivector.rs:1438-1593
+        if (!same_algebra(o)) {
+            std::ostringstream s;
+            s << "algebra mismatch: left operand is Cl(" << dims << ") but right operand is Cl(" << o.dims << "); both multivectors must be in the same algebra";
+            throw py::value_error(s.str());
+        }
+        return like(device_pair_product(get_algebra(), op, coeffs, o.coeffs));
+    }
+    Multivector reverse() const {  // src/multivector.rs:2711-2726
+        std::vector<double> c(coeffs.size());
+        for (size_t i = 0; i < c.size(); ++i) c[i] = coeffs[i] * reverse_sign(popcount((unsigned)i));
+        return like(std::move(c));
+    }
+    Multivector scale(double s) const {  // src/multivector.rs:2153-2160
+        std::vector<double> c(coeffs.size());
+        for (size_t i = 0; i < c.size(); ++i) c[i] = coeffs[i] * s;
+        return like(std::move(c));
+    }
+    // scalar part of A*~A, i ascending (src/multivector.rs:2890-2913); only j == i reaches blade 0
+    double norm_squared() const {
+        AlgebraPtr alg = get_algebra();
+        const int8_t *signs = lcc_algebra_cayley_signs(alg->h);
+        const int nb = alg->nb();
+        double acc = 0.0;
+        for (int i = 0; i < nb; ++i) {
+            const double a = coeffs[i];
+            if (a == 0.0) continue;
+            const double b = a * reverse_sign(popcount((unsigned)i));
+            const double t = (double)signs[(size_t)i * nb + i] * a;  // exact; (sign*a)*b then one add, no FMA (-ffp-contract=off)
+            acc += t * b;
+        }
+        return acc;
+    }
+    double norm() const { return std::sqrt(std::fabs(norm_squared())); }
+    Multivector grade(int k) const {  // src/multivector.rs:1269-1287 (drops the explicit algebra)
+        if (k < 0 || k > dims) {
+            std::ostringstream s; s << "grade " << k << " exceeds algebra dimension " << dims << " (max grade is " << dims << ")";
+            throw py::value_error(s.str());
+        }
+        std::vector<double> c(coeffs.size(), 0.0);
+        for (size_t i = 0; i < c.size(); ++i) if (popcount((unsigned)i) == k) c[i] = coeffs[i];
+        return like(std::move(c), false);
+    }
+    std::vector<int> grades() const {  // src/multivector.rs:3153-3171
+        std::vector<int> g;
+        for (int k = 0; k <= dims; ++k)
+            for (size_t i = 0; i < coeffs.size(); ++i)
+                if (coeffs[i] != 0.0 && popcount((unsigned)i) == k) { g.push_back(k); break; }
+        return g;
+    }
+    Multivector sandwich(const Multivector &x) const {  // src/multivector.rs:3040-3052
+        if (dims != x.dims) {
+            std::ostringstream s; s << "dimension mismatch: rotor is Cl(" << dims << ") but operand is Cl(" << x.dims << "); both must have the same dimension";
+            throw py::value_error(s.str());
+        }
+        return product(LCC_OP_GP, x).product(LCC_OP_GP, reverse());
+    }
+    Multivector inverse() const {  // src/multivector.rs:2989-2999
+        const double n2 = norm_squared();
+        if (n2 == 0.0) throw py::value_error("cannot invert multivector with zero norm; only non-null blades and versors are invertible");
+        return reverse().scale(1.0 / n2);
+    }
+    Multivector pseudoscalar_like() const { std::vector<double> c(coeffs.size(), 0.0); c.back() = 1.0; return like(std::move(c)); }
+};
+
+Multivector mv_in(const PyAlgebra &alg, std::vector<double> c) { return Multivector{std::move(c), alg.inner->dim(), alg.inner}; }
+
+void require_pga3d(const PyAlgebra &a, const char *who) {
+    if (!a.inner->is_pga() || a.inner->dim() != 4) throw py::value_error(std::string(who) + " requires a PGA3D algebra Cl(3,0,1)");
+}
+void require_pga3d_element(const Multivector &m, const char *who) {
+    AlgebraPtr alg = m.get_algebra();
+    if (!alg->is_pga() || m.dims != 4) throw py::value_error(std::string(who) + " requires a PGA3D element");
+}
+
+// ------------------------------------------------------------------ MultivectorBatch (device resident)
+struct Batch {
+    AlgebraPtr algebra;
+    lcc_view view{nullptr, 0, 0, LCC_F64, LCC_SOA};
+    int device = 0;
+
+    Batch(AlgebraPtr alg, int dtype, int64_t n) : algebra(std::move(alg)) {
+        check(lcc_get_device(&device));
+        check(lcc_batch_alloc(algebra->h, dtype, n, &view, nullptr));
+    }
+    ~Batch() { lcc_batch_free(&view, nullptr); }
+    Batch(const Batch &) = delete;
+    int nb() const { return algebra->nb(); }
+    int64_t n() const { return view.n; }
+    size_t es() const { return view.dtype == LCC_F32 ? 4 : 8; }
+    std::shared_ptr<Batch> empty_like(int64_t rows) const { return std::make_shared<Batch>(algebra, view.dtype, rows); }
+};
+using BatchPtr = std::shared_ptr<Batch>;
+
+struct DeviceTemp {  // stream-ordered scratch
+    void *ptr = nullptr;
+    explicit DeviceTemp(size_t bytes) { check(lcc_device_alloc(&ptr, bytes, nullptr)); }
+    ~DeviceTemp() { lcc_device_free(ptr, nullptr); }
+};
+
+int dtype_of(const py::array &arr) {
+    if (arr.dtype().is(py::dtype::of<double>())) return LCC_F64;
+    if (arr.dtype().is(py::dtype::of<float>())) return LCC_F32;
+    throw py::type_error("expected a float64 (or float32) NumPy array, got dtype " + std::string(py::str(arr.dtype())));
+}
+py::array contiguous(const py::array &arr) {
+    return py::array::ensure(arr, py::array::c_style);
+}
+py::dtype np_dtype(int dtype) { return dtype == LCC_F32 ? py::dtype::of<float>() : py::dtype::of<double>(); }
+
+// upload an (n, cols) host array as a dense device AoS block; caller frees
+void upload(const py::array &arr, void *dst) {
+    check(lcc_memcpy_h2d(dst, arr.data(), (size_t)arr.nbytes(), nullptr));
+    check(lcc_stream_sync(nullptr));  // the NumPy buffer may be pageable and may change after we return
+}
+
+BatchPtr batch_from_numpy(const PyAlgebra &alg, const py::array &coeffs_in) {  // src/batch.rs:79-94
+    py::array coeffs = contiguous(coeffs_in);
+    const int dtype = dtype_of(coeffs);
+    if (coeffs.ndim() != 2) throw py::type_error("coeffs must be a 2-D array of shape (N, num_blades)");
+    const int nb = alg.inner->nb();
+    if (coeffs.shape(1) != nb) {
+        std::ostringstream s; s << "coeffs must have " << nb << " columns for " << alg.inner->str() << " but got " << coeffs.shape(1);
+        throw py::value_error(s.str());
+    }
+    const int64_t n = coeffs.shape(0);
+    auto b = std::make_shared<Batch>(alg.inner, dtype, n);
+    if (n == 0) return b;
+    py::gil_scoped_release nogil;
+    DeviceTemp stage((size_t)coeffs.nbytes());
+    upload(coeffs, stage.ptr);
+    lcc_view src{stage.ptr, n, nb, dtype, LCC_AOS};
+    check(lcc_batch_convert(alg.inner->h, &src, &b->view, nullptr));
+    return b;
+}
+
+BatchPtr batch_from_columns(const PyAlgebra &alg, const py::array &cols_in, const std::vector<int32_t> &blades, const char *what) {
+    py::array cols = contiguous(cols_in);
+    const int dtype = dtype_of(cols);
+    const int64_t n = cols.shape(0);
+    const int ncols = (int)blades.size();
+    auto b = std::make_shared<Batch>(alg.inner, dtype, n);
+    if (n == 0) return b;
+    (void)what;
+    py::gil_scoped_release nogil;
+    DeviceTemp stage((size_t)std::max<int64_t>(cols.nbytes(), 16));
+    if (cols.nbytes()) upload(cols, stage.ptr);
+    check(lcc_batch_scatter_columns(alg.inner->h, stage.ptr, ncols, blades.data(), &b->view, nullptr));
+    return b;
+}
+
+py::array batch_gather(const Batch &b, const std::vector<int32_t> &blades, bool flat) {
+    const int ncols = (int)blades.size();
+    std::vector<py::ssize_t> shape;
+    if (flat) shape = {(py::ssize_t)b.n()}; else shape = {(py::ssize_t)b.n(), (py::ssize_t)ncols};
+    py::array out(np_dtype(b.view.dtype), shape);
+    if (b.n() == 0 || ncols == 0) return out;
+    py::gil_scoped_release nogil;
+    DeviceTemp stage((size_t)b.n() * ncols * b.es());
+    check(lcc_batch_gather_columns(b.algebra->h, &b.view, ncols, blades.data(), stage.ptr, nullptr));
+    check(lcc_memcpy_d2h(out.mutable_data(), stage.ptr, (size_t)b.n() * ncols * b.es(), nullptr));
+    check(lcc_stream_sync(nullptr));
+    return out;
+}
+
+py::array batch_to_numpy(const Batch &b) {  // src/batch.rs:233-235
+    py::array out(np_dtype(b.view.dtype), std::vector<py::ssize_t>{(py::ssize_t)b.n(), (py::ssize_t)b.nb()});
+    if (b.n() == 0) return out;
+    py::gil_scoped_release nogil;
+    const size_t bytes = (size_t)b.n() * b.nb() * b.es();
+    DeviceTemp stage(bytes);
+    lcc_view dst{stage.ptr, b.n(), b.nb(), b.view.dtype, LCC_AOS};
+    check(lcc_batch_convert(b.algebra->h, &b.view, &dst, nullptr));
+    check(lcc_memcpy_d2h(out.mutable_data(), stage.ptr, bytes, nullptr));
+    check(lcc_stream_sync(nullptr));
+    return out;
+}
+
+void require_same_algebra(const Batch &a, const Batch &b) {  // src/batch.rs:354-359
+    if (!a.algebra->same_signature(*b.algebra))
+        throw py::value_error("algebra mismatch: left is " + a.algebra->str() + " but right is " + b.algebra->str());
+    if (a.view.dtype != b.view.dtype) throw py::type_error("batches must share one dtype (float64 or float32)");
+}
+int64_t broadcast_n(const Batch &a, const Batch &b) {  // src/batch.rs:361-376
+    if (a.n() == b.n() || b.n() == 1) return a.n();
+    if (a.n() == 1) return b.n();
+    std::ostringstream s; s << "batch sizes must match or be 1 for broadcasting: " << a.n() << " vs " << b.n();
+    throw py::value_error(s.str());
+}
+
+BatchPtr batch_product(const Batch &a, const Batch &b, int op) {
+    require_same_algebra(a, b);
+    auto out = a.empty_like(broadcast_n(a, b));
+    py::gil_scoped_release nogil;
+    check(lcc_batch_product(a.algebra->h, op, &a.view, &b.view, &out->view, fp_flags(), nullptr));
+    return out;
+}
+BatchPtr batch_unary(const Batch &a, int op, int arg = 0) {
+    auto out = a.empty_like(a.n());
+    py::gil_scoped_release nogil;
+    check(lcc_batch_unary(a.algebra->h, op, arg, &a.view, &out->view, nullptr));
+    return out;
+}
+BatchPtr batch_scale(const Batch &a, double f) {  // src/batch.rs:957-962
+    auto out = a.empty_like(a.n());
+    py::gil_scoped_release nogil;
+    check(lcc_batch_scale(a.algebra->h, &a.view, f, &out->view, nullptr));
+    return out;
+}
+BatchPtr batch_addsub(const Batch &a, const Batch &b, int op) {
+    require_same_algebra(a, b);
+    auto out = a.empty_like(broadcast_n(a, b));
+    py::gil_scoped_release nogil;
+    check(lcc_batch_elementwise(a.algebra->h, op, &a.view, &b.view, &out->view, nullptr));
+    return out;
+}
+py::array batch_norm(const Batch &a, int kind) {
+    py::array out(np_dtype(a.view.dtype), std::vector<py::ssize_t>{(py::ssize_t)a.n()});
+    if (a.n() == 0) return out;
+    py::gil_scoped_release nogil;
+    DeviceTemp stage((size_t)a.n() * a.es());
+    check(lcc_batch_norm(a.algebra->h, kind, &a.view, stage.ptr, fp_flags(), nullptr));
+    check(lcc_memcpy_d2h(out.mutable_data(), stage.ptr, (size_t)a.n() * a.es(), nullptr));
+    check(lcc_stream_sync(nullptr));
+    return out;
+}
+BatchPtr batch_sandwich(const Batch &a, const Multivector &rotor) {  // src/batch.rs:434-503
+    AlgebraPtr ralg = rotor.get_algebra();
+    if (!a.algebra->same_signature(*ralg))
+        throw py::value_error("algebra mismatch: batch is " + a.algebra->str() + " but rotor is " + ralg->str());
+    auto out = a.empty_like(a.n());
+    py::gil_scoped_release nogil;
+    check(lcc_batch_sandwich(a.algebra->h, rotor.coeffs.data(), &a.view, &out->view, fp_flags(), nullptr));
+    return out;
+}
+Multivector batch_get(const Batch &b, int64_t index) {  // src/batch.rs:288-303
+    if (index < 0 || index >= b.n()) {
+        std::ostringstream s; s << "index " << index << " out of bounds for batch of size " << b.n();
+        throw py::index_error(s.str());
+    }
+    const int nb = b.nb();
+    std::vector<double> c(nb);
+    {
+        py::gil_scoped_release nogil;
+        DeviceTemp stage((size_t)nb * b.es());
+        lcc_view row{stage.ptr, 1, nb, b.view.dtype, LCC_AOS};
+        check(lcc_batch_copy_rows(b.algebra->h, &b.view, index, index + 1, &row, 0, nullptr));
+        if (b.view.dtype == LCC_F64) {
+            check(lcc_memcpy_d2h(c.data(), stage.ptr, (size_t)nb * 8, nullptr));
+            check(lcc_stream_sync(nullptr));
+        } else {
+            std::vector<float> f(nb);
+            check(lcc_memcpy_d2h(f.data(), stage.ptr, (size_t)nb * 4, nullptr));
+            check(lcc_stream_sync(nullptr));
+            for (int i = 0; i < nb; ++i) c[i] = f[i];
+        }
+    }
+    return Multivector{std::move(c), b.algebra->dim(), b.algebra};
+}
+void batch_set(Batch &b, int64_t index, const Multivector &mv) {  // src/batch.rs:314-335
+    if (index < 0 || index >= b.n()) {
+        std::ostringstream s; s << "index " << index << " out of bounds for batch of size " << b.n();
+        throw py::index_error(s.str());
+    }
+    const int nb = b.nb();
+    if ((int)mv.coeffs.size() != nb) {
+        std::ostringstream s; s << "multivector has " << mv.coeffs.size() << " blades but batch expects " << nb;
+        throw py::value_error(s.str());
+    }
+    py::gil_scoped_release nogil;
+    DeviceTemp stage((size_t)nb * b.es());
+    std::vector<float> f;
+    const void *src = mv.coeffs.data();
+    if (b.view.dtype == LCC_F32) { f.assign(mv.coeffs.begin(), mv.coeffs.end()); src = f.data(); }
+    check(lcc_memcpy_h2d(stage.ptr, src, (size_t)nb * b.es(), nullptr));
+    lcc_view row{stage.ptr, 1, nb, b.view.dtype, LCC_AOS};
+    check(lcc_batch_copy_rows(b.algebra->h, &row, 0, 1, &b.view, index, nullptr));
+    check(lcc_stream_sync(nullptr));
+}
+BatchPtr batch_slice(const Batch &b, int64_t start, int64_t end) {  // src/batch.rs:1083-1097
+    if (start < 0 || end < 0 || start > b.n() || end > b.n() || start > end) {
+        std::ostringstream s; s << "invalid slice [" << start << ":" << end << "] for batch of size " << b.n();
+        throw py::index_error(s.str());
+    }
+    auto out = b.empty_like(end - start);
+    py::gil_scoped_release nogil;
+    check(lcc_batch_copy_rows(b.algebra->h, &b.view, start, end, &out->view, 0, nullptr));
+    return out;
+}
+BatchPtr batch_concat(const Batch &a, const Batch &b) {  // src/batch.rs:1055-1073
+    require_same_algebra(a, b);
+    auto out = a.empty_like(a.n() + b.n());
+    py::gil_scoped_release nogil;
+    check(lcc_batch_copy_rows(a.algebra->h, &a.view, 0, a.n(), &out->view, 0, nullptr));
+    check(lcc_batch_copy_rows(a.algebra->h, &b.view, 0, b.n(), &out->view, a.n(), nullptr));
+    return out;
+}
+py::array batch_sum(const Batch &a, bool mean) {
+    const int nb = a.nb();
+    py::array out(np_dtype(a.view.dtype), std::vector<py::ssize_t>{(py::ssize_t)nb});
+    {
+        py::gil_scoped_release nogil;
+        DeviceTemp stage((size_t)nb * a.es());
+        check(lcc_batch_sum(a.algebra->h, &a.view, stage.ptr, nullptr));
+        check(lcc_memcpy_d2h(out.mutable_data(), stage.ptr, (size_t)nb * a.es(), nullptr));
+        check(lcc_stream_sync(nullptr));
+    }
+    if (mean && a.n() > 0) {
+        if (a.view.dtype == LCC_F64) { double *p = (double *)out.mutable_data(); for (int k = 0; k < nb; ++k) p[k] /= (double)a.n(); }
+        else { float *p = (float *)out.mutable_data(); for (int k = 0; k < nb; ++k) p[k] = (float)((double)p[k] / (double)a.n()); }
+    }
+    return out;
+}
+
+std::vector<int32_t> vector_blades(int dim) { std::vector<int32_t> b; for (int i = 0; i < dim; ++i) b.push_back(1 << i); return b; }
+std::vector<int32_t> blades_of_grade(int nb, int g) { std::vector<int32_t> b; for (int i = 0; i < nb; ++i) if (popcount((unsigned)i) == g) b.push_back(i); return b; }
+
+std::string repr_float(double v) { return py::cast<std::string>(py::repr(py::float_(v))); }
+
+}  // namespace
+
+PYBIND11_MODULE(largecrimsoncanine, m) {
+    m.doc() = "B200-native drop-in for the batched path of LargeCrimsonCanine (Algebra, Multivector, MultivectorBatch)";
+    m.attr("__version__") = lcc_version();
+    m.def("set_strict_fp", [](bool on) { g_strict_fp = on; },
+          "Reproduce the reference's rounding sequence bit for bit (separate multiply and add) instead of FMA.");
+    m.def("get_strict_fp", [] { return g_strict_fp; });
+    m.def("kernel_launch_count", [] { return lcc_kernel_launch_count(); });
+    m.def("device_count", [] { int c = 0; check(lcc_device_count(&c)); return c; });
+    m.def("set_device", [](int d) { check(lcc_set_device(d)); });
+    m.def("synchronize", [] { check(lcc_stream_sync(nullptr)); });
+
+    // ------------------------------------------------------------------ Algebra (src/pyalgebra.rs:30-200)
+    py::class_<PyAlgebra>(m, "Algebra")
+        .def(py::init([](long p, long q, long r) { return make_algebra(p, q, r); }), py::arg("p"), py::arg("q") = 0, py::arg("r") = 0)
+        .def_static("euclidean", [](long n) { return make_algebra(n, 0, 0); })
+        .def_static("pga", [](long n) { return make_algebra(n, 0, 1); })
+        .def_static("cga", [](long n) { return make_algebra(n + 1, 1, 0); })
+        .def_static("sta", [] { return make_algebra(1, 3, 0); })
+        .def_property_readonly("dimension", [](const PyAlgebra &a) { return a.inner->dim(); })
+        .def_property_readonly("num_blades", [](const PyAlgebra &a) { return a.inner->nb(); })
+        .def_property_readonly("p", [](const PyAlgebra &a) { return a.inner->p; })
+        .def_property_readonly("q", [](const PyAlgebra &a) { return a.inner->q; })
+        .def_property_readonly("r", [](const PyAlgebra &a) { return a.inner->r; })
+        .def("is_euclidean", [](const PyAlgebra &a) { return a.inner->is_euclidean(); })
+        .def("is_pga", [](const PyAlgebra &a) { return a.inner->is_pga(); })
+        .def("blade_name", [](const PyAlgebra &a, long index) {
+            if (index < 0 || index >= a.inner->nb()) throw py::index_error("blade index out of range");
+            char buf[32];
+            lcc_algebra_blade_name(a.inner->h, (int)index, buf, sizeof buf);
+            return std::string(buf);
+        })
+        .def("__repr__", [](const PyAlgebra &a) { return a.inner->str(); })
+        .def("__str__", [](const PyAlgebra &a) { return a.inner->str(); })
+        .def("__eq__", [](const PyAlgebra &a, const PyAlgebra &b) { return a.inner->same_signature(*b.inner); })
+        .def("__hash__", [](const PyAlgebra &a) { return py::hash(py::make_tuple(a.inner->p, a.inner->q, a.inner->r)); })
+        // additive surface: lets table parity be tested from Python and makes lcc.torch interop work
+        .def_property_readonly("signature", [](const PyAlgebra &a) { return py::make_tuple(a.inner->p, a.inner->q, a.inner->r); })
+        .def("cayley_signs", [](const PyAlgebra &a) {
+            const int nb = a.inner->nb();
+            py::array_t<int8_t> out({nb, nb});
+            std::memcpy(out.mutable_data(), lcc_algebra_cayley_signs(a.inner->h), (size_t)nb * nb);
+            return out;
+        })
+        .def("cayley_blades", [](const PyAlgebra &a) {
+            const int nb = a.inner->nb();
+            py::array_t<uint16_t> out({nb, nb});
+            std::memcpy(out.mutable_data(), lcc_algebra_cayley_blades(a.inner->h), (size_t)nb * nb * 2);
+            return out;
+        })
+        .def_property_readonly("grade_masks", [](const PyAlgebra &a) {
+            py::list out;
+            const int words = (a.inner->nb() + 63) / 64;
+            std::vector<uint64_t> w(words);
+            for (int g = 0; g <= a.inner->dim(); ++g) {
+                lcc_algebra_grade_mask(a.inner->h, g, w.data(), words);
+                py::object v = py::int_(0);
+                for (int i = words - 1; i >= 0; --i) {
+                    py::object shifted = py::reinterpret_steal<py::object>(PyNumber_Lshift(v.ptr(), py::int_(64).ptr()));
+                    py::object word = py::reinterpret_steal<py::object>(PyLong_FromUnsignedLongLong(w[i]));
+                    v = py::reinterpret_steal<py::object>(PyNumber_Or(shifted.ptr(), word.ptr()));
+                }
+                out.append(v);
+            }
+            return out;
+        })
+        .def_property_readonly("is_specialised", [](const PyAlgebra &a) { return lcc_algebra_is_specialised(a.inner->h) != 0; });
+
+    // ------------------------------------------------------------------ Multivector
+    py::class_<Multivector> mv(m, "Multivector");
+    mv.def(py::init([](std::vector<double> c) { return Multivector::from_coeffs(std::move(c)); }))
+        .def_static("from_list", [](std::vector<double> c) { return Multivector::from_coeffs(std::move(c)); })
+        .def_static("zero", [](int dims) {
+            if (dims <= 0) throw py::value_error("dimension must be at least 1");
+            return Multivector{std::vector<double>(size_t(1) << dims, 0.0), dims, nullptr};
+        })
+        .def_static("from_scalar", [](double value, int dims) {  // src/multivector.rs:318-329
+            if (dims <= 0) throw py::value_error("dimension must be at least 1");
+            std::vector<double> c(size_t(1) << dims, 0.0);
+            c[0] = value;
+            return Multivector{std::move(c), dims, nullptr};
+        }, py::arg("value"), py::arg("dims"))
+        .def_static("from_vector", [](std::vector<double> coords) {  // src/multivector.rs:380-395
+            const int dims = (int)coords.size();
+            if (dims == 0) throw py::value_error("coords must not be empty; provide at least one coordinate");
+            std::vector<double> c(size_t(1) << dims, 0.0);
+            for (int i = 0; i < dims; ++i) c[size_t(1) << i] = coords[i];
+            return Multivector{std::move(c), dims, nullptr};
+        })
+        .def_static("basis", [](int index, int dims) {
+            if (dims <= 0) throw py::value_error("dimension must be at least 1");
+            if (index <= 0 || index > dims) throw py::value_error("basis index out of range");
+            std::vector<double> c(size_t(1) << dims, 0.0);
+            c[size_t(1) << (index - 1)] = 1.0;
+            return Multivector{std::move(c), dims, nullptr};
+        }, py::arg("index"), py::arg("dims"))
+        .def_static("from_bivector", [](std::vector<double> comps, int dims) {
+            auto bl = blades_of_grade(1 << dims, 2);
+            if (comps.size() != bl.size()) throw py::value_error("wrong number of bivector components");
+            std::vector<double> c(size_t(1) << dims, 0.0);
+            for (size_t i = 0; i < bl.size(); ++i) c[bl[i]] = comps[i];
+            return Multivector{std::move(c), dims, nullptr};
+        }, py::arg("components"), py::arg("dims"))
+        .def_static("from_list_in", [](std::vector<double> c, const PyAlgebra &a) {  // additive: coefficients + explicit algebra
+            if ((int)c.size() != a.inner->nb()) {
+                std::ostringstream s; s << "coefficient list has " << c.size() << " entries but " << a.inner->str() << " has " << a.inner->nb() << " blades";
+                throw py::value_error(s.str());
+            }
+            return mv_in(a, std::move(c));
+        }, py::arg("coeffs"), py::arg("algebra"))
+        .def_static("zero_in", [](const PyAlgebra &a) { return mv_in(a, std::vector<double>(a.inner->nb(), 0.0)); })
+        .def_static("scalar_in", [](double v, const PyAlgebra &a) { std::vector<double> c(a.inner->nb(), 0.0); c[0] = v; return mv_in(a, std::move(c)); })
+        .def_static("vector_in", [](std::vector<double> coords, const PyAlgebra &a) {  // src/multivector.rs:498-517
+            if ((int)coords.size() != a.inner->dim()) {
+                std::ostringstream s; s << "coords length " << coords.size() << " doesn't match algebra dimension " << a.inner->dim();
+                throw py::value_error(s.str());
+            }
+            std::vector<double> c(a.inner->nb(), 0.0);
+            for (size_t i = 0; i < coords.size(); ++i) c[size_t(1) << i] = coords[i];
+            return mv_in(a, std::move(c));
+        })
+        .def_static("basis_in", [](int index, const PyAlgebra &a) {  // src/multivector.rs:530-547
+            const int dim = a.inner->dim();
+            if (index <= 0 || index > dim) {
+                std::ostringstream s; s << "basis index " << index << " out of range for " << dim << "-dimensional algebra (use 1 to " << dim << ")";
+                throw py::value_error(s.str());
+            }
+            std::vector<double> c(a.inner->nb(), 0.0);
+            c[size_t(1) << (index - 1)] = 1.0;
+            return mv_in(a, std::move(c));
+        })
+        .def_static("pseudoscalar_in", [](const PyAlgebra &a) { std::vector<double> c(a.inner->nb(), 0.0); c.back() = 1.0; return mv_in(a, std::move(c)); })
+        .def_static("from_axis_angle", [](const Multivector &axis, double angle) {  // src/multivector.rs:955-999
+            if (axis.dims != 3) { std::ostringstream s; s << "from_axis_angle requires 3D vectors, got Cl(" << axis.dims << ")"; throw py::value_error(s.str()); }
+            auto g = axis.grades();
+            if (g.size() != 1 || g[0] != 1) throw py::value_error("axis must be a vector (grade 1)");
+            const double n = axis.norm();
+            if (n == 0.0) throw py::value_error("axis has zero norm; cannot create rotor");
+            const double inv = 1.0 / n;
+            const double ax = axis.coeffs[1] * inv, ay = axis.coeffs[2] * inv, az = axis.coeffs[4] * inv;
+            const double half = angle / 2.0, c = std::cos(half), s = std::sin(half);
+            std::vector<double> r(8, 0.0);
+            r[0] = c; r[3] = -s * az; r[5] = s * ay; r[6] = -s * ax;
+            return Multivector{std::move(r), 3, nullptr};
+        })
+        .def("algebra", [](const Multivector &a) -> py::object { if (!a.algebra_opt) return py::none(); return py::cast(PyAlgebra{a.algebra_opt}); })
+        .def_property_readonly("dims", [](const Multivector &a) { return a.dims; })
+        .def("dimension", [](const Multivector &a) { return a.dims; })
+        .def("scalar", [](const Multivector &a) { return a.coeffs[0]; })
+        .def("coefficients", [](const Multivector &a) { return a.coeffs; })
+        .def("to_list", [](const Multivector &a) { return a.coeffs; })
+        .def("to_vector_coords", [](const Multivector &a) { std::vector<double> v; for (int i = 0; i < a.dims; ++i) v.push_back(a.coeffs[size_t(1) << i]); return v; })
+        .def("to_bivector_coords", [](const Multivector &a) { std::vector<double> v; for (size_t i = 0; i < a.coeffs.size(); ++i) if (popcount((unsigned)i) == 2) v.push_back(a.coeffs[i]); return v; })
+        .def("blades", [](const Multivector &a) {
+            std::vector<std::tuple<size_t, double, int>> out;
+            for (size_t i = 0; i < a.coeffs.size(); ++i) if (a.coeffs[i] != 0.0) out.emplace_back(i, a.coeffs[i], popcount((unsigned)i));
+            return out;
+        })
+        .def("grade", &Multivector::grade)
+        .def("vector_part", [](const Multivector &a) { return a.grade(1); })
+        .def("bivector_part", [](const Multivector &a) { return a.dims >= 2 ? a.grade(2) : a; })
+        .def("grades", &Multivector::grades)
+        .def("max_grade", [](const Multivector &a) -> py::object { auto g = a.grades(); if (g.empty()) return py::none(); return py::int_(g.back()); })
+        .def("pure_grade", [](const Multivector &a) -> py::object { auto g = a.grades(); if (g.size() != 1) return py::none(); return py::int_(g[0]); })
+        .def("is_vector", [](const Multivector &a) { auto g = a.grades(); return g.size() == 1 && g[0] == 1; })
+        .def("is_scalar", [](const Multivector &a) { auto g = a.grades(); return g.size() == 1 && g[0] == 0; })
+        .def("geometric_product", [](const Multivector &a, const Multivector &b) { return a.product(LCC_OP_GP, b); })
+        .def("gp", [](const Multivector &a, const Multivector &b) { return a.product(LCC_OP_GP, b); })
+        .def("outer_product", [](const Multivector &a, const Multivector &b) { return a.product(LCC_OP_OUTER, b); })
+        .def("wedge", [](const Multivector &a, const Multivector &b) { return a.product(LCC_OP_OUTER, b); })
+        .def("left_contraction", [](const Multivector &a, const Multivector &b) { return a.product(LCC_OP_LC, b); })
+        .def("inner", [](const Multivector &a, const Multivector &b) { return a.product(LCC_OP_LC, b); })
+        .def("lc", [](const Multivector &a, const Multivector &b) { return a.product(LCC_OP_LC, b); })
+        .def("reverse", &Multivector::reverse)
+        .def("tilde", &Multivector::reverse)
+        .def("__invert__", &Multivector::reverse)
+        .def("norm_squared", &Multivector::norm_squared)
+        .def("norm", &Multivector::norm)
+        .def("magnitude", &Multivector::norm)
+        .def("scale", &Multivector::scale)
+        .def("normalized", [](const Multivector &a) {  // src/multivector.rs:2957-2967
+            const double n = a.norm();
+            if (n == 0.0) throw py::value_error("cannot normalize zero multivector; normalization requires non-zero norm (check that your multivector has at least one non-zero coefficient)");
+            return a.scale(1.0 / n);
+        })
+        .def("normalize", [](const Multivector &a) -> py::object { const double n = a.norm(); if (n == 0.0) return py::none(); return py::cast(a.scale(1.0 / n)); })
+        .def("inverse", &Multivector::inverse)
+        .def("sandwich", &Multivector::sandwich)
+        .def("apply", &Multivector::sandwich)
+        .def("dual", [](const Multivector &a) { return a.product(LCC_OP_GP, a.pseudoscalar_like().inverse()); })      // src/multivector.rs:4249-4255
+        .def("undual", [](const Multivector &a) { return a.product(LCC_OP_GP, a.pseudoscalar_like()); })               // :4270-4274
+        .def("right_dual", [](const Multivector &a) { return a.pseudoscalar_like().inverse().product(LCC_OP_GP, a); })  // :4285-4290
+        .def("approx_eq", [](const Multivector &a, const Multivector &b, double tol) {
+            if (a.coeffs.size() != b.coeffs.size()) return false;
+            for (size_t i = 0; i < a.coeffs.size(); ++i) if (std::fabs(a.coeffs[i] - b.coeffs[i]) > tol) return false;
+            return true;
+        }, py::arg("other"), py::arg("tol") = 1e-10)
+        .def("__mul__", [](const Multivector &a, const py::object &o) -> Multivector {  // src/multivector.rs:2030-2041
+            if (py::isinstance<Multivector>(o)) return a.product(LCC_OP_GP, o.cast<const Multivector &>());
+            if (py::isinstance<py::float_>(o) || py::isinstance<py::int_>(o)) return a.scale(o.cast<double>());
+            throw py::type_error("unsupported operand type for *: expected Multivector or float");
+        })
+        .def("__rmul__", [](const Multivector &a, const py::object &o) -> Multivector {
+            if (py::isinstance<py::float_>(o) || py::isinstance<py::int_>(o)) return a.scale(o.cast<double>());
+            throw py::type_error("unsupported operand type for *: expected float");
+        })
+        .def("__truediv__", [](const Multivector &a, const py::object &o) -> Multivector {  // src/multivector.rs:2054-2070
+            if (py::isinstance<Multivector>(o)) return a.product(LCC_OP_GP, o.cast<const Multivector &>().inverse());
+            if (py::isinstance<py::float_>(o) || py::isinstance<py::int_>(o)) {
+                const double s = o.cast<double>();
+                if (s == 0.0) { PyErr_SetString(PyExc_ZeroDivisionError, "cannot divide multivector by zero"); throw py::error_already_set(); }
+                return a.scale(1.0 / s);
+            }
+            throw py::type_error("unsupported operand type for /: expected Multivector or float");
+        })
+        .def("__xor__", [](const Multivector &a, const Multivector &b) { return a.product(LCC_OP_OUTER, b); })
+        .def("__or__", [](const Multivector &a, const Multivector &b) { return a.product(LCC_OP_LC, b); })
+        .def("__add__", [](const Multivector &a, const Multivector &b) {  // src/multivector.rs:2084-2103 (drops the algebra)
+            if (a.dims != b.dims) { std::ostringstream s; s << "dimension mismatch: left operand is Cl(" << a.dims << ") but right operand is Cl(" << b.dims << "); both multivectors must have the same dimension"; throw py::value_error(s.str()); }
+            std::vector<double> c(a.coeffs.size());
+            for (size_t i = 0; i < c.size(); ++i) c[i] = a.coeffs[i] + b.coeffs[i];
+            return Multivector{std::move(c), a.dims, nullptr};
+        })
+        .def("__sub__", [](const Multivector &a, const Multivector &b) {
+            if (a.dims != b.dims) { std::ostringstream s; s << "dimension mismatch: left operand is Cl(" << a.dims << ") but right operand is Cl(" << b.dims << "); both multivectors must have the same dimension"; throw py::value_error(s.str()); }
+            std::vector<double> c(a.coeffs.size());
+            for (size_t i = 0; i < c.size(); ++i) c[i] = a.coeffs[i] - b.coeffs[i];
+            return Multivector{std::move(c), a.dims, nullptr};
+        })
+        .def("__neg__", [](const Multivector &a) { std::vector<double> c(a.coeffs); for (auto &v : c) v = -v; return a.like(std::move(c)); })
+        .def("__pos__", [](const Multivector &a) { return a; })
+        .def("__eq__", [](const Multivector &a, const py::object &o) {
+            if (!py::isinstance<Multivector>(o)) return false;
+            const Multivector &b = o.cast<const Multivector &>();
+            return a.dims == b.dims && a.coeffs == b.coeffs;
+        })
+        .def("__hash__", [](const Multivector &a) { return py::hash(py::make_tuple(a.dims, py::tuple(py::cast(a.coeffs)))); })
+        .def("__len__", [](const Multivector &a) { return a.coeffs.size(); })
+        .def("__getitem__", [](const Multivector &a, long i) {
+            const long n = (long)a.coeffs.size();
+            const long idx = i < 0 ? n + i : i;
+            if (idx < 0 || idx >= n) throw py::index_error("coefficient index out of range");
+            return a.coeffs[idx];
+        })
+        .def("__repr__", [](const Multivector &a) {  // src/multivector.rs:1819-1821
+            std::ostringstream s;
+            s << "Multivector([";
+            for (size_t i = 0; i < a.coeffs.size(); ++i) s << (i ? ", " : "") << repr_float(a.coeffs[i]);
+            s << "], dims=" << a.dims << ")";
+            return s.str();
+        });
+
+    // ---- PGA3D (src/pga.rs)
+    mv.def_static("pga_point", [](const PyAlgebra &a, double x, double y, double z) {  // :109-141
+          require_pga3d(a, "pga_point");
+          std::vector<double> c(16, 0.0);
+          c[7] = 1.0; c[14] = -x; c[13] = y; c[11] = -z;
+          return mv_in(a, std::move(c));
+      })
+        .def_static("pga_plane", [](const PyAlgebra &a, double pa, double pb, double pc, double pd) {  // :165-186
+            require_pga3d(a, "pga_plane");
+            std::vector<double> c(16, 0.0);
+            c[1] = pa; c[2] = pb; c[4] = pc; c[8] = pd;
+            return mv_in(a, std::move(c));
+        })
+        .def_static("pga_translator", [](const PyAlgebra &a, double dx, double dy, double dz) {  // :371-396
+            require_pga3d(a, "pga_translator");
+            std::vector<double> c(16, 0.0);
+            c[0] = 1.0; c[9] = dx / 2.0; c[10] = dy / 2.0; c[12] = dz / 2.0;
+            return mv_in(a, std::move(c));
+        })
+        .def_static("pga_motor_from_axis_angle", [](const PyAlgebra &a, std::vector<double> axis, std::vector<double> point, double angle) {  // :263-345
+            require_pga3d(a, "pga_motor_from_axis_angle");
+            if (axis.size() != 3) throw py::value_error("axis must have 3 components");
+            if (point.size() != 3) throw py::value_error("point must have 3 components");
+            const double len = std::sqrt(axis[0] * axis[0] + axis[1] * axis[1] + axis[2] * axis[2]);
+            if (len < 1e-10) throw py::value_error("axis has zero length");
+            const double ax = axis[0] / len, ay = axis[1] / len, az = axis[2] / len;
+            const double px = point[0], py_ = point[1], pz = point[2];
+            const double half = angle / 2.0, c = std::cos(half), s = std::sin(half);
+            std::vector<double> m(16, 0.0);
+            m[0] = c; m[6] = -s * ax; m[5] = s * ay; m[3] = -s * az;
+            const double mx = py_ * az - pz * ay, my = pz * ax - px * az, mz = px * ay - py_ * ax;
+            m[9] = s * mx; m[10] = s * my; m[12] = s * mz;
+            return mv_in(a, std::move(m));
+        })
+        .def("pga_point_coords", [](const Multivector &p) {  // :571-599
+            require_pga3d_element(p, "pga_point_coords");
+            const double w = p.coeffs[7];
+            if (std::fabs(w) < 1e-10) throw py::value_error("cannot extract coordinates from ideal point (e123 = 0)");
+            return py::make_tuple(-p.coeffs[14] / w, p.coeffs[13] / w, -p.coeffs[11] / w);
+        })
+        .def("pga_normalize", [](const Multivector &p) {  // :413-439
+            require_pga3d_element(p, "pga_normalize");
+            const double w = p.coeffs[7];
+            if (std::fabs(w) < 1e-10) throw py::value_error("cannot normalize ideal point (e123 coefficient is zero)");
+            std::vector<double> c(p.coeffs);
+            for (auto &v : c) v = v / w;
+            return p.like(std::move(c));
+        })
+        .def("pga_dual", [](const Multivector &p) {  // :521-556
+            require_pga3d_element(p, "pga_dual");
+            std::vector<double> c(16, 0.0);
+            for (int i = 0; i < 16; ++i)
+                if (p.coeffs[i] != 0.0) c[15 ^ i] += reverse_sign(popcount((unsigned)i)) * p.coeffs[i];
+            return p.like(std::move(c));
+        });
+
+    // ------------------------------------------------------------------ MultivectorBatch (src/batch.rs)
+    py::class_<Batch, BatchPtr>(m, "MultivectorBatch")
+        .def_static("from_numpy", &batch_from_numpy, py::arg("algebra"), py::arg("coeffs"))
+        .def_static("from_vectors", [](const PyAlgebra &a, const py::array &coords) {  // :112-138
+            if (coords.ndim() != 2) throw py::type_error("coords must be a 2-D array of shape (N, dim)");
+            if (coords.shape(1) != a.inner->dim()) {
+                std::ostringstream s; s << "coords must have " << a.inner->dim() << " columns for " << a.inner->str() << " but got " << coords.shape(1);
+                throw py::value_error(s.str());
+            }
+            return batch_from_columns(a, coords, vector_blades(a.inner->dim()), "coords");
+        }, py::arg("algebra"), py::arg("coords"))
+        .def_static("from_scalars", [](const PyAlgebra &a, const py::array &values) {  // :156-171
+            if (values.ndim() != 1) throw py::type_error("values must be a 1-D array of shape (N,)");
+            return batch_from_columns(a, values, std::vector<int32_t>{0}, "values");
+        }, py::arg("algebra"), py::arg("values"))
+        .def_static("from_bivectors", [](const PyAlgebra &a, const py::array &biv) {  // :191-221
+            if (biv.ndim() != 2) throw py::type_error("bivector_coeffs must be a 2-D array");
+            const int dim = a.inner->dim(), nbiv = dim * (dim - 1) / 2;
+            if (biv.shape(1) != nbiv) {
+                std::ostringstream s; s << "bivector_coeffs must have " << nbiv << " columns for " << a.inner->str() << " but got " << biv.shape(1);
+                throw py::value_error(s.str());
+            }
+            return batch_from_columns(a, biv, blades_of_grade(a.inner->nb(), 2), "bivector_coeffs");
+        }, py::arg("algebra"), py::arg("bivector_coeffs"))
+        .def("to_numpy", [](const Batch &b) { return batch_to_numpy(b); })
+        .def("to_vector_coords", [](const Batch &b) { return batch_gather(b, vector_blades(b.algebra->dim()), false); })
+        .def("scalar", [](const Batch &b) { return batch_gather(b, std::vector<int32_t>{0}, true); })
+        .def("len", &Batch::n)
+        .def("__len__", &Batch::n)
+        .def("is_empty", [](const Batch &b) { return b.n() == 0; })
+        .def("num_blades", &Batch::nb)
+        .def("get", [](const Batch &b, int64_t i) { return batch_get(b, i); })
+        .def("set", [](Batch &b, int64_t i, const Multivector &mv) { batch_set(b, i, mv); })
+        .def("__getitem__", [](const Batch &b, int64_t index) {  // :1004-1014
+            const int64_t idx = index < 0 ? b.n() + index : index;
+            if (idx < 0 || idx >= b.n()) {
+                std::ostringstream s; s << "index " << index << " out of bounds for batch of size " << b.n();
+                throw py::index_error(s.str());
+            }
+            return batch_get(b, idx);
+        })
+        .def("geometric_product", [](const Batch &a, const Batch &b) { return batch_product(a, b, LCC_OP_GP); })
+        .def("gp", [](const Batch &a, const Batch &b) { return batch_product(a, b, LCC_OP_GP); })
+        .def("outer_product", [](const Batch &a, const Batch &b) { return batch_product(a, b, LCC_OP_OUTER); })
+        .def("wedge", [](const Batch &a, const Batch &b) { return batch_product(a, b, LCC_OP_OUTER); })
+        .def("left_contraction", [](const Batch &a, const Batch &b) { return batch_product(a, b, LCC_OP_LC); })
+        .def("inner", [](const Batch &a, const Batch &b) { return batch_product(a, b, LCC_OP_LC); })
+        .def("lc", [](const Batch &a, const Batch &b) { return batch_product(a, b, LCC_OP_LC); })
+        .def("sandwich", &batch_sandwich)
+        .def("apply", &batch_sandwich)
+        .def("norm", [](const Batch &a) { return batch_norm(a, LCC_NORM); })
+        .def("norm_squared", [](const Batch &a) { return batch_norm(a, LCC_NORM_SQUARED); })
+        .def("normalized", [](const Batch &a) {
+            auto out = a.empty_like(a.n());
+            py::gil_scoped_release nogil;
+            check(lcc_batch_normalized(a.algebra->h, &a.view, &out->view, fp_flags(), nullptr));
+            return out;
+        })
+        .def("reverse", [](const Batch &a) { return batch_unary(a, LCC_UN_REVERSE); })
+        .def("grade_involution", [](const Batch &a) { return batch_unary(a, LCC_UN_INVOLUTE); })
+        .def("grade", [](const Batch &a, long k) {
+            if (k < 0) throw py::type_error("grade must be a non-negative integer");
+            return batch_unary(a, LCC_UN_GRADE, (int)std::min<long>(k, 1 << 20));
+        })
+        .def("__add__", [](const Batch &a, const Batch &b) { return batch_addsub(a, b, LCC_EW_ADD); })
+        .def("__sub__", [](const Batch &a, const Batch &b) { return batch_addsub(a, b, LCC_EW_SUB); })
+        .def("scale", [](const Batch &a, double f) { return batch_scale(a, f); })
+        .def("__neg__", [](const Batch &a) { return batch_scale(a, -1.0); })
+        .def("__mul__", [](const Batch &a, double f) { return batch_scale(a, f); })
+        .def("__rmul__", [](const Batch &a, double f) { return batch_scale(a, f); })
+        .def("__truediv__", [](const Batch &a, double s) {  // :980-987
+            if (s == 0.0) { PyErr_SetString(PyExc_ZeroDivisionError, "division by zero"); throw py::error_already_set(); }
+            return batch_scale(a, 1.0 / s);
+        })
+        .def("__repr__", [](const Batch &b) {
+            std::ostringstream s; s << "MultivectorBatch(size=" << b.n() << ", algebra=" << b.algebra->str() << ")";
+            return s.str();
+        })
+        .def("concat", [](const Batch &a, const Batch &b) { return batch_concat(a, b); })
+        .def("slice", [](const Batch &b, int64_t s, int64_t e) { return batch_slice(b, s, e); })
+        // ---- additive surface
+        .def("clifford_conjugate", [](const Batch &a) { return batch_unary(a, LCC_UN_CONJUGATE); })
+        .def("even", [](const Batch &a) { return batch_unary(a, LCC_UN_EVEN); })
+        .def("odd", [](const Batch &a) { return batch_unary(a, LCC_UN_ODD); })
+        .def("dual", [](const Batch &a) { return batch_unary(a, LCC_UN_DUAL); })
+        .def("undual", [](const Batch &a) { return batch_unary(a, LCC_UN_UNDUAL); })
+        .def("right_dual", [](const Batch &a) { return batch_unary(a, LCC_UN_RIGHT_DUAL); })
+        .def("pga_dual", [](const Batch &a) { return batch_unary(a, LCC_UN_PGA_DUAL); })
+        .def("gp_and_outer", [](const Batch &a, const Batch &b) {
+            require_same_algebra(a, b);
+            const int64_t n = broadcast_n(a, b);
+            auto g = a.empty_like(n), w = a.empty_like(n);
+            py::gil_scoped_release nogil;
+            check(lcc_batch_gp_outer(a.algebra->h, &a.view, &b.view, &g->view, &w->view, fp_flags(), nullptr));
+            return std::make_pair(g, w);
+        })
+        .def("sum", [](const Batch &a) { return batch_sum(a, false); })
+        .def("mean", [](const Batch &a) { return batch_sum(a, true); })
+        .def("algebra", [](const Batch &b) { return PyAlgebra{b.algebra}; })
+        .def_property_readonly("dtype", [](const Batch &b) { return np_dtype(b.view.dtype); })
+        .def_property_readonly("device", [](const Batch &b) { return b.device; })
+        .def_property_readonly("data_ptr", [](const Batch &b) { return (uintptr_t)b.view.data; })
+        .def_property_readonly("ld", [](const Batch &b) { return b.view.ld; })
+        .def_static("from_points_pga", [](const PyAlgebra &a, const py::array &xyz_in) {
+            py::array xyz = contiguous(xyz_in);
+            const int dtype = dtype_of(xyz);
+            if (xyz.ndim() != 2 || xyz.shape(1) != 3) throw py::value_error("points must have 3 columns");
+            auto b = std::make_shared<Batch>(a.inner, dtype, xyz.shape(0));
+            if (xyz.shape(0) == 0) { require_pga3d(a, "pga_point"); return b; }
+            py::gil_scoped_release nogil;
+            DeviceTemp stage((size_t)xyz.nbytes());
+            upload(xyz, stage.ptr);
+            check(lcc_pga_points_embed(a.inner->h, stage.ptr, &b->view, nullptr));
+            return b;
+        })
+        .def_static("from_points_cga", [](const PyAlgebra &a, const py::array &xyz_in) {
+            py::array xyz = contiguous(xyz_in);
+            const int dtype = dtype_of(xyz);
+            if (xyz.ndim() != 2 || xyz.shape(1) != 3) throw py::value_error("points must have 3 columns");
+            auto b = std::make_shared<Batch>(a.inner, dtype, xyz.shape(0));
+            if (xyz.shape(0) == 0) return b;
+            py::gil_scoped_release nogil;
+            DeviceTemp stage((size_t)xyz.nbytes());
+            upload(xyz, stage.ptr);
+            check(lcc_cga_points_embed(a.inner->h, stage.ptr, &b->view, nullptr));
+            return b;
+        })
+        .def("pga_point_coords", [](const Batch &b) {
+            py::array out(np_dtype(b.view.dtype), std::vector<py::ssize_t>{(py::ssize_t)b.n(), 3});
+            if (b.n() == 0) return out;
+            py::gil_scoped_release nogil;
+            DeviceTemp stage((size_t)b.n() * 3 * b.es());
+            check(lcc_pga_points_extract(b.algebra->h, &b.view, stage.ptr, nullptr));
+            check(lcc_memcpy_d2h(out.mutable_data(), stage.ptr, (size_t)b.n() * 3 * b.es(), nullptr));
+            check(lcc_stream_sync(nullptr));
+            return out;
+        })
+        .def("cga_extract_center", [](const Batch &b) {
+            py::array out(np_dtype(b.view.dtype), std::vector<py::ssize_t>{(py::ssize_t)b.n(), 3});
+            if (b.n() == 0) return out;
+            py::gil_scoped_release nogil;
+            DeviceTemp stage((size_t)b.n() * 3 * b.es());
+            check(lcc_cga_points_extract(b.algebra->h, &b.view, stage.ptr, nullptr));
+            check(lcc_memcpy_d2h(out.mutable_data(), stage.ptr, (size_t)b.n() * 3 * b.es(), nullptr));
+            check(lcc_stream_sync(nullptr));
+            return out;
+        });
+}

@@ -1,0 +1,135 @@
+"""CPU-side checks of the C ABI and the host logic (no compute call is made without a GPU):
+the library loads and exports every symbol include/lcc_b200.h declares; the host algebra tables
+are bit-exact against the oracle, the SURVEY.md digests and the build-time generator; error
+behaviour of the host-only entry points."""
+import ctypes as C
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+from largecrimsoncanine_b200 import cabi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIGS = [(1, 0, 0), (2, 0, 0), (3, 0, 0), (3, 0, 1), (4, 1, 0), (1, 3, 0), (2, 1, 1), (0, 2, 0), (2, 0, 2), (6, 0, 0), (4, 2, 1), (8, 0, 0)]
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "lcc_b200.h")).read()
+    return re.findall(r"LCC_API[^;]*?\b(lcc_[a-z0-9_]+)\s*\(", text)
+
+
+def test_library_exports_every_declared_symbol():
+    L = cabi.lib()
+    names = declared_symbols()
+    assert len(names) >= 50
+    for name in names:
+        assert hasattr(L, name), f"{name} declared in include/lcc_b200.h but not exported"
+    assert set(names) == set(L._lcc_signatures), "cabi.py and the header disagree"
+    assert L.lcc_version().decode().startswith("0.3.0")
+
+
+@pytest.mark.parametrize("sig", SIGS)
+def test_host_tables_bit_exact(sig):
+    a, o = cabi.Algebra(*sig), oracle.OracleAlgebra(*sig)
+    assert a.num_blades == o.num_blades
+    assert np.array_equal(a.cayley_signs(), o.signs_int8())
+    assert np.array_equal(a.cayley_blades(), o.blades_u16().astype(np.uint16))
+    if a.dimension <= 6:  # the reference's one-word masks (blades.rs:211-220)
+        assert [a.grade_mask(g) for g in range(a.dimension + 1)] == o.grade_masks()
+    else:  # multi-word extension: same rule, popcount(i) == g
+        for g in range(a.dimension + 1):
+            m = a.grade_mask(g)
+            assert all(((m >> i) & 1) == (bin(i).count("1") == g) for i in range(a.num_blades))
+    assert a.grade_mask(a.dimension + 1) == 0  # registry.rs:224-232
+
+
+def test_digests_and_names():
+    want = {
+        (3, 0, 0): "40bc89779d69516cb07eb06fbac3ad3977c2993fa25d30549b8567d059478f9a",
+        (3, 0, 1): "28398685f6263fa53dd7fe21123656b681ccac926c017907649b14a9b0de7390",
+        (4, 1, 0): "9c0bc8a9265f229dec3ad5743e29060b3c6034f1049545a51b9bad13a9e881e4",
+        (1, 3, 0): "365efcddbaab4cb448d229369d7e213ee566ac8583e6c8382844b0a76e248c26",
+        (8, 0, 0): "b9593cd2fdc94cdee10612bc8911e0d7bf4045a354132ddf10b82bcd6474a660",
+    }
+    for sig, digest in want.items():
+        assert hashlib.sha256(cabi.Algebra(*sig).cayley_signs().tobytes()).hexdigest() == digest
+    r3 = cabi.Algebra(3)
+    assert [r3.blade_name(i) for i in range(8)] == ["1", "e1", "e2", "e12", "e3", "e13", "e23", "e123"]  # registry.rs:436-448
+    assert cabi.Algebra(2, 0, 1).blade_name(4) == "e3"  # registry.rs:450-458
+    L = cabi.lib()
+    assert [L.lcc_reverse_sign(i) for i in (0, 1, 3, 7, 15)] == [1, 1, -1, -1, 1]
+    assert [L.lcc_grade_involution_sign(i) for i in (0, 1, 3, 7)] == [1, -1, 1, -1]
+    assert [L.lcc_clifford_conjugate_sign(i) for i in (0, 1, 3, 7, 15)] == [1, -1, -1, 1, 1]
+
+
+def test_generated_term_lists_match_oracle():
+    """The build-time generator's gather-form lists reproduce the oracle's tables and term order."""
+    gen = os.path.join(ROOT, "largecrimsoncanine_b200", "csrc", "generated")
+    for sig in [(3, 0, 0), (3, 0, 1), (4, 1, 0), (1, 3, 0)]:
+        o = oracle.OracleAlgebra(*sig)
+        nb = o.num_blades
+        signs = o.signs_int8().reshape(nb, nb)
+        seen = np.zeros((nb, nb), np.int8)
+        last_i = {}
+        for line in open(os.path.join(gen, "cayley_%d_%d_%d.inc" % sig)):
+            m = re.match(r"LCC_TERM\((\d+), (\d+), (\d+), (\d), (\d)\)", line)
+            if not m:
+                continue
+            k, i, j, neg, flags = map(int, m.groups())
+            assert j == i ^ k and signs[i, j] == (-1 if neg else 1)
+            assert last_i.get(k, -1) < i  # ascending left blade inside each output group
+            last_i[k] = i
+            assert bool(flags & 1) == ((i & j) == 0) and bool(flags & 2) == ((i & j) == i)
+            seen[i, j] = signs[i, j]
+        assert np.array_equal(seen, signs)  # every non-zero term emitted exactly where it belongs
+    assert cabi.lib().lcc_algebra_is_specialised(cabi.Algebra(3, 0, 1).h) == 1
+    assert cabi.lib().lcc_algebra_is_specialised(cabi.Algebra(2, 1, 1).h) == 0
+
+
+def test_host_side_errors():
+    L = cabi.lib()
+    h = C.c_void_p()
+    assert L.lcc_algebra_create(5, 3, 1, C.byref(h)) == cabi.LCC_ERR_UNSUPPORTED
+    assert b"at most 8" in L.lcc_last_error()
+    assert L.lcc_algebra_create(-1, 0, 0, C.byref(h)) == cabi.LCC_ERR_VALUE
+    with pytest.raises(ValueError):
+        cabi.check(cabi.LCC_ERR_VALUE)
+
+
+def test_extension_host_logic():
+    """Algebra / Multivector host behaviour of the `largecrimsoncanine` extension (src/pyalgebra.rs)."""
+    import largecrimsoncanine as L
+
+    a = L.Algebra(3, 0, 1)
+    assert (a.p, a.q, a.r, a.dimension, a.num_blades) == (3, 0, 1, 4, 16)
+    assert str(a) == repr(a) == "Cl(3,0,1)" and a == L.Algebra.pga(3) and hash(a) == hash(L.Algebra.pga(3))
+    assert a.is_pga() and not a.is_euclidean() and L.Algebra.euclidean(3).is_euclidean()
+    assert str(L.Algebra.cga(3)) == "Cl(4,1,0)" and str(L.Algebra.sta()) == "Cl(1,3,0)" and str(L.Algebra(2)) == "Cl(2,0,0)"
+    assert a.grade_masks == [0x1, 0x116, 0x1668, 0x6880, 0x8000]
+    assert np.array_equal(a.cayley_signs().ravel(), oracle.OracleAlgebra(3, 0, 1).signs_int8())
+    v = L.Multivector.from_vector([3.0, 4.0, 0.0])
+    assert v.norm() == 5.0 and v.to_vector_coords() == [3.0, 4.0, 0.0] and v.dims == 3 and v.algebra() is None
+    assert L.Multivector.from_scalar(2.5, 3).coefficients() == [2.5, 0, 0, 0, 0, 0, 0, 0]
+    with pytest.raises(ValueError, match="power of 2"):
+        L.Multivector([1.0, 2.0, 3.0])
+    r = L.Multivector.from_axis_angle(L.Multivector.from_vector([0.0, 0.0, 2.0]), np.pi / 2)
+    np.testing.assert_allclose(r.coefficients(), [np.cos(np.pi / 4), 0, 0, -np.sin(np.pi / 4), 0, 0, 0, 0], atol=1e-15)
+    p = L.Multivector.pga_point(a, 1.0, 2.0, 3.0)
+    assert p.pga_point_coords() == (1.0, 2.0, 3.0) and p.algebra() == a
+    with pytest.raises(ValueError, match="PGA3D"):
+        L.Multivector.pga_point(L.Algebra.euclidean(3), 1.0, 2.0, 3.0)
+
+
+def test_batched_calls_refuse_to_run_without_a_gpu():
+    if os.path.exists("/dev/nvidiactl"):
+        pytest.skip("a GPU is present")
+    import largecrimsoncanine as L
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        L.MultivectorBatch.from_numpy(L.Algebra.euclidean(3), np.zeros((4, 8)))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        L.Multivector.from_vector([1.0, 0.0, 0.0]).geometric_product(L.Multivector.from_vector([0.0, 1.0, 0.0]))

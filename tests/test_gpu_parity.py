@@ -1,0 +1,356 @@
+"""GPU parity tests proper: the CUDA path (through the `largecrimsoncanine` extension and through the
+raw C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): bit-exact for tables / masks / indexing (tests/test_cabi_host.py);
+products within 1e-12 (f64) / 1e-5 (f32) of the reference arithmetic.  On top of that the STRICT
+mode (separate multiply and add in the reference's term order) must be BIT-EXACT.
+
+Tolerance definition for the FMA mode (hard part 3): element-wise relative error
+is ill-posed where cancellation drives an output towards zero, so each element is compared with
+    |gpu - ref| <= tol * max(|ref|, sum_terms |a_i||b_j|)
+and each row with  max|gpu - ref| <= tol * max|ref|.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+SIGS = [(3, 0, 0), (3, 0, 1), (4, 1, 0), (1, 3, 0), (2, 0, 0), (2, 1, 1), (1, 0, 0), (4, 0, 0), (0, 0, 2), (3, 1, 1)]
+TOL = {np.float64: 1e-12, np.float32: 1e-5}
+SIZES = [1, 3, 64, 257, 1000]
+
+
+@pytest.fixture(scope="module")
+def L():
+    import largecrimsoncanine as ext
+
+    assert ext.device_count() >= 1
+    return ext
+
+
+@pytest.fixture()
+def strict(L):
+    L.set_strict_fp(True)
+    yield
+    L.set_strict_fp(False)
+
+
+def rand(rng, n, nb, dt):
+    return rng.standard_normal((n, nb)).astype(dt)
+
+
+def assert_close(got, ref, bound, dt):
+    tol = TOL[dt]
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    scale = np.maximum(np.abs(ref), np.asarray(bound, np.float64))
+    bad = np.abs(got - ref) > tol * scale + np.finfo(np.float64).tiny
+    assert not bad.any(), f"{bad.sum()} elements off; worst {np.abs(got - ref).max():.3e}"
+    if got.ndim == 2 and got.size:
+        row_err = np.abs(got - ref).max(axis=1)
+        row_ref = np.abs(ref).max(axis=1)
+        assert np.all(row_err <= tol * np.maximum(row_ref, np.asarray(bound, np.float64).max(axis=1)))
+
+
+def algebras(L, sig):
+    return L.Algebra(*sig), oracle.OracleAlgebra(*sig)
+
+
+# ----------------------------------------------------------------------------------------------- products
+@pytest.mark.parametrize("sig", SIGS)
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_products_strict_mode_is_bit_exact(L, strict, sig, dt):
+    alg, o = algebras(L, sig)
+    rng = np.random.default_rng(hash(sig) % 1000)
+    for n in SIZES:
+        a, b = rand(rng, n, o.num_blades, dt), rand(rng, n, o.num_blades, dt)
+        A, B = L.MultivectorBatch.from_numpy(alg, a), L.MultivectorBatch.from_numpy(alg, b)
+        assert np.array_equal(A.to_numpy(), a)
+        assert np.array_equal(A.geometric_product(B).to_numpy(), o.geometric_product(a, b))
+        assert np.array_equal(A.outer_product(B).to_numpy(), o.outer_product(a, b))
+        assert np.array_equal(A.left_contraction(B).to_numpy(), o.left_contraction(a, b))
+        g, w = A.gp_and_outer(B)
+        assert np.array_equal(g.to_numpy(), o.geometric_product(a, b)) and np.array_equal(w.to_numpy(), o.outer_product(a, b))
+        assert np.array_equal(A.norm_squared(), o.norm_squared(a))
+        assert np.array_equal(A.norm(), o.norm(a))
+        assert np.array_equal(A.normalized().to_numpy(), o.normalized(a))
+    # broadcast in both positions (batch.rs:361-376)
+    a, b = rand(rng, 130, o.num_blades, dt), rand(rng, 1, o.num_blades, dt)
+    A, B = L.MultivectorBatch.from_numpy(alg, a), L.MultivectorBatch.from_numpy(alg, b)
+    assert np.array_equal(A.geometric_product(B).to_numpy(), o.geometric_product(a, b))
+    assert np.array_equal(B.geometric_product(A).to_numpy(), o.geometric_product(b, a))
+    assert np.array_equal(B.left_contraction(A).to_numpy(), o.left_contraction(b, a))
+
+
+@pytest.mark.parametrize("sig", SIGS)
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_products_fma_mode_within_tolerance(L, sig, dt):
+    alg, o = algebras(L, sig)
+    rng = np.random.default_rng(7)
+    n = 2051
+    a, b = rand(rng, n, o.num_blades, dt), rand(rng, n, o.num_blades, dt)
+    A, B = L.MultivectorBatch.from_numpy(alg, a), L.MultivectorBatch.from_numpy(alg, b)
+    for name, op, ref in (("gp", A.geometric_product, o.geometric_product), ("outer", A.outer_product, o.outer_product),
+                          ("lc", A.left_contraction, o.left_contraction)):
+        assert_close(op(B).to_numpy(), ref(a, b), o.product_abs_bound(name, a, b), dt)
+    g, w = A.gp_and_outer(B)
+    assert_close(g.to_numpy(), o.geometric_product(a, b), o.product_abs_bound("gp", a, b), dt)
+    assert_close(w.to_numpy(), o.outer_product(a, b), o.product_abs_bound("outer", a, b), dt)
+
+
+@pytest.mark.parametrize("sig", SIGS)
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_sandwich(L, sig, dt):
+    """batch.rs:434-503: one rotor for the whole batch, two rounded stages.  Dense rotors take the
+    general kernel, even ones (rotors / motors) the kernel with odd blades pruned at compile time."""
+    alg, o = algebras(L, sig)
+    rng = np.random.default_rng(11)
+    nb = o.num_blades
+    dense = rng.standard_normal(nb)
+    even = dense * np.array([1.0 if bin(i).count("1") % 2 == 0 else 0.0 for i in range(nb)])
+    for rotor in (dense, even):
+        R = rotor_mv(L, alg, rotor)
+        for n in (1, 5, 258, 1027):
+            x = rand(rng, n, nb, dt)
+            X = L.MultivectorBatch.from_numpy(alg, x)
+            ref = o.sandwich(rotor, x)
+            L.set_strict_fp(True)
+            try:
+                assert np.array_equal(X.sandwich(R).to_numpy(), ref)
+            finally:
+                L.set_strict_fp(False)
+            assert_close(X.sandwich(R).to_numpy(), ref, sandwich_bound(o, rotor, x), dt)
+    with pytest.raises(ValueError, match="algebra mismatch"):  # batch.rs:437-442
+        X.sandwich(L.Multivector.from_scalar(1.0, o.dimension + 1))
+
+
+def rotor_mv(L, alg, coeffs):
+    """An algebra-carrying Multivector with arbitrary coefficients (additive constructor)."""
+    return L.Multivector.from_list_in([float(c) for c in coeffs], alg)
+
+
+def sandwich_bound(o, rotor, x):
+    ar = np.abs(np.asarray(rotor, np.float64))[None, :].astype(x.dtype)
+    rx = o.product_abs_bound("gp", ar, np.abs(x))
+    return o.product_abs_bound("gp", rx, ar)
+
+
+# ----------------------------------------------------------------------------------------------- unary family
+@pytest.mark.parametrize("sig", SIGS)
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_unary_family_exact(L, sig, dt):
+    alg, o = algebras(L, sig)
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 255, 1030):
+        x = rand(rng, n, o.num_blades, dt)
+        X = L.MultivectorBatch.from_numpy(alg, x)
+        assert np.array_equal(X.reverse().to_numpy(), o.reverse(x))
+        assert np.array_equal(X.grade_involution().to_numpy(), o.grade_involution(x))
+        assert np.array_equal(X.clifford_conjugate().to_numpy(), o.clifford_conjugate(x))
+        for k in range(o.dimension + 1):
+            assert np.array_equal(X.grade(k).to_numpy(), o.grade(x, k))
+        assert np.array_equal(X.scale(2.5).to_numpy(), o.scale(x, 2.5))
+        assert np.array_equal((X / 3.0).to_numpy(), o.div(x, 3.0))
+        assert np.array_equal((-X).to_numpy(), o.scale(x, -1.0))
+        y = rand(rng, n, o.num_blades, dt)
+        Y = L.MultivectorBatch.from_numpy(alg, y)
+        assert np.array_equal((X + Y).to_numpy(), o.add(x, y)) and np.array_equal((X - Y).to_numpy(), o.sub(x, y))
+        one = L.MultivectorBatch.from_numpy(alg, y[:1])
+        assert np.array_equal((X + one).to_numpy(), o.add(x, y[:1])) and np.array_equal((one - X).to_numpy(), o.sub(y[:1], x))
+    with pytest.raises(ValueError, match="exceeds dimension"):
+        X.grade(o.dimension + 1)
+
+
+def test_duals(L):
+    rng = np.random.default_rng(5)
+    for sig in [(3, 0, 0), (4, 1, 0), (1, 3, 0), (4, 0, 0)]:
+        alg, o = algebras(L, sig)
+        x = rng.standard_normal((77, o.num_blades))
+        X = L.MultivectorBatch.from_numpy(alg, x)
+        assert np.array_equal(X.dual().to_numpy(), o.dual(x))
+        assert np.array_equal(X.undual().to_numpy(), o.undual(x))
+        assert np.array_equal(X.right_dual().to_numpy(), o.right_dual(x))
+        assert np.array_equal(X.dual().undual().to_numpy(), x)
+    alg, o = algebras(L, (3, 0, 1))
+    x = rng.standard_normal((33, 16))
+    X = L.MultivectorBatch.from_numpy(alg, x)
+    assert np.array_equal(X.pga_dual().to_numpy(), o.pga_dual(x))
+    with pytest.raises(ValueError):  # I*I = 0 in PGA: Multivector::dual raises (multivector.rs:2991-2996)
+        X.dual()
+
+
+# ----------------------------------------------------------------------------------------------- golden fixtures
+@pytest.mark.parametrize("sig", [(2, 0, 0), (3, 0, 0), (3, 0, 1), (4, 1, 0), (1, 3, 0), (2, 1, 1)])
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+def test_cuda_path_reproduces_reference_golden_vectors(L, strict, golden, sig, dt):
+    """tests/golden/ref_torch_golden.npz comes from the reference's own lcc/torch implementation."""
+    alg = L.Algebra(*sig)
+    k = "cl%d%d%d.%s" % (*sig, dt)
+    a, b, rotor = golden[k + ".a"], golden[k + ".b"], golden[k + ".rotor"]
+    A, B = L.MultivectorBatch.from_numpy(alg, a), L.MultivectorBatch.from_numpy(alg, b)
+    assert np.array_equal(A.geometric_product(B).to_numpy(), golden[k + ".gp"])
+    assert np.array_equal(A.geometric_product(L.MultivectorBatch.from_numpy(alg, b[:1])).to_numpy(), golden[k + ".gp_bcast"])
+    assert np.array_equal(A.outer_product(B).to_numpy(), golden[k + ".outer"])
+    assert np.array_equal(A.left_contraction(B).to_numpy(), golden[k + ".inner"])
+    R = rotor_mv(L, alg, rotor[0].astype(a.dtype).astype(np.float64))
+    assert np.array_equal(A.sandwich(R).to_numpy(), golden[k + ".sandwich"])
+    assert np.array_equal(A.reverse().to_numpy(), golden[k + ".reverse"])
+    assert np.array_equal(A.grade_involution().to_numpy(), golden[k + ".involution"])
+    assert np.array_equal(A.clifford_conjugate().to_numpy(), golden[k + ".conjugate"])
+    assert np.array_equal(A.norm_squared(), golden[k + ".norm_squared"])
+    for g in range(alg.dimension + 1):
+        assert np.array_equal(A.grade(g).to_numpy(), golden[f"{k}.grade{g}"])
+
+
+# ----------------------------------------------------------------------------------------------- big algebras
+@pytest.mark.parametrize("sig", [(6, 0, 0), (4, 2, 1), (8, 0, 0)])
+def test_algebras_above_32_blades(L, strict, sig):
+    alg, o = algebras(L, sig)
+    rng = np.random.default_rng(9)
+    n = 37
+    a, b = rng.standard_normal((n, o.num_blades)), rng.standard_normal((n, o.num_blades))
+    A, B = L.MultivectorBatch.from_numpy(alg, a), L.MultivectorBatch.from_numpy(alg, b)
+    assert np.array_equal(A.geometric_product(B).to_numpy(), o.geometric_product(a, b))
+    assert np.array_equal(A.outer_product(B).to_numpy(), o.outer_product(a, b))
+    assert np.array_equal(A.left_contraction(B).to_numpy(), o.left_contraction(a, b))
+    # fixed-operand left product = the broadcast branch (BASELINE config 5 shape, small N)
+    M = L.MultivectorBatch.from_numpy(alg, a[:1])
+    assert np.array_equal(M.geometric_product(B).to_numpy(), o.geometric_product(a[:1], b))
+    rotor = rng.standard_normal(o.num_blades)
+    R = rotor_mv(L, alg, rotor)
+    assert np.array_equal(A.sandwich(R).to_numpy(), o.sandwich(rotor, a))
+    assert np.array_equal(A.reverse().to_numpy(), o.reverse(a))
+    assert np.array_equal(A.norm_squared(), o.norm_squared(a))
+
+
+# ----------------------------------------------------------------------------------------------- sums
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_batch_sum_and_mean(L, dt):
+    alg, o = algebras(L, (1, 3, 0))
+    rng = np.random.default_rng(13)
+    for n in (1, 1000, 100_003):
+        x = rand(rng, n, 16, dt)
+        X = L.MultivectorBatch.from_numpy(alg, x)
+        want, mag = o.sum(x)
+        tol = 1e-13 if dt == np.float64 else 1e-6
+        assert np.all(np.abs(X.sum().astype(np.float64) - want) <= tol * mag)
+        assert np.all(np.abs(X.mean().astype(np.float64) - want / n) <= tol * mag / n)
+        assert np.array_equal(X.sum(), X.sum())  # fixed reduction tree: run-to-run identical
+
+
+# ----------------------------------------------------------------------------------------------- PGA / CGA
+def test_pga_kats_through_the_batched_path(L):
+    """/root/reference/tests/test_pga.py:245-255 and :287-300 replayed with N = 1 and N = large."""
+    pga = L.Algebra.pga(3)
+    T = L.Multivector.pga_translator(pga, 4.0, 5.0, 6.0)
+    pts = np.array([[1.0, 2.0, 3.0]] + np.random.default_rng(1).standard_normal((4096, 3)).tolist())
+    P = L.MultivectorBatch.from_points_pga(pga, pts)
+    moved = P.sandwich(T).pga_point_coords()
+    np.testing.assert_allclose(moved[0], (5.0, 7.0, 9.0), atol=1e-12)
+    np.testing.assert_allclose(moved, pts + np.array([4.0, 5.0, 6.0]), atol=1e-12)
+    M = L.Multivector.pga_motor_from_axis_angle(pga, [0.0, 0.0, 1.0], [0.0, 0.0, 0.0], math.pi / 2)
+    rot = L.MultivectorBatch.from_points_pga(pga, np.array([[1.0, 0.0, 0.0]])).sandwich(M).pga_point_coords()
+    np.testing.assert_allclose(rot, [[0.0, 1.0, 0.0]], atol=1e-12)
+    # embedding equals the scalar constructor (src/pga.rs:131-134), bit for bit
+    emb = P.to_numpy()
+    one = L.Multivector.pga_point(pga, *pts[5])
+    assert np.array_equal(emb[5], np.array(one.coefficients()))
+    # scalar Multivector.sandwich (device, one row) agrees with the batch
+    assert np.allclose(T.sandwich(one).pga_point_coords(), moved[5], atol=1e-12)
+
+
+def test_cga_points(L):
+    cga = L.Algebra.cga(3)
+    pts = np.random.default_rng(2).standard_normal((513, 3))
+    P = L.MultivectorBatch.from_points_cga(cga, pts)
+    emb = P.to_numpy()
+    nsq = pts[:, 0] * pts[:, 0] + pts[:, 1] * pts[:, 1] + pts[:, 2] * pts[:, 2]  # src/cga.rs:196
+    want = np.zeros((513, 32))
+    want[:, 1], want[:, 2], want[:, 4] = pts[:, 0], pts[:, 1], pts[:, 2]
+    want[:, 8], want[:, 16] = 0.5 * nsq - 0.5, 0.5 * nsq + 0.5
+    assert np.array_equal(emb, want)
+    np.testing.assert_allclose(P.cga_extract_center(), pts, rtol=1e-14)
+    # null vectors: P.P = 0 and distance formula sqrt(-2 P.Q) (src/cga.rs:701-720), 3-4-5 KAT (tests/test_cga.py:284-291)
+    a = L.MultivectorBatch.from_points_cga(cga, np.array([[0.0, 0.0, 0.0]]))
+    b = L.MultivectorBatch.from_points_cga(cga, np.array([[3.0, 4.0, 0.0]]))
+    assert abs(math.sqrt(-2.0 * a.left_contraction(b).scalar()[0]) - 5.0) < 1e-12
+    assert np.all(np.abs(P.left_contraction(P).scalar()) < 1e-12)
+
+
+# ----------------------------------------------------------------------------------------------- raw C ABI
+def test_c_abi_with_raw_views_aos_and_soa(L):
+    """Same products through include/lcc_b200.h with caller-owned device memory in both layouts."""
+    from largecrimsoncanine_b200 import cabi
+
+    lib = cabi.lib()
+    o = oracle.OracleAlgebra(3, 0, 1)
+    alg = cabi.Algebra(3, 0, 1)
+    rng = np.random.default_rng(17)
+    n, nb = 777, 16
+    for dt, code in ((np.float64, cabi.LCC_F64), (np.float32, cabi.LCC_F32)):
+        a, b = rand(rng, n, nb, dt), rand(rng, n, nb, dt)
+        es = a.itemsize
+        for layout in (cabi.LCC_AOS, cabi.LCC_SOA):
+            ld = nb if layout == cabi.LCC_AOS else ((n + 63) // 64) * 64
+            elems = n * nb if layout == cabi.LCC_AOS else nb * ld
+            ptrs = []
+            for _ in range(3):
+                p = C.c_void_p()
+                cabi.check(lib.lcc_device_alloc(C.byref(p), elems * es, None))
+                ptrs.append(p)
+            def host_image(x):
+                if layout == cabi.LCC_AOS:
+                    return np.ascontiguousarray(x)
+                img = np.zeros((nb, ld), dt)
+                img[:, :n] = x.T
+                return img
+            ia, ib = host_image(a), host_image(b)
+            cabi.check(lib.lcc_memcpy_h2d(ptrs[0], ia.ctypes.data, ia.nbytes, None))
+            cabi.check(lib.lcc_memcpy_h2d(ptrs[1], ib.ctypes.data, ib.nbytes, None))
+            va, vb, vo = (cabi.view(p.value, n, ld, code, layout) for p in ptrs)
+            for op, ref in ((cabi.LCC_OP_GP, o.geometric_product), (cabi.LCC_OP_OUTER, o.outer_product), (cabi.LCC_OP_LC, o.left_contraction)):
+                cabi.check(lib.lcc_batch_product(alg.h, op, C.byref(va), C.byref(vb), C.byref(vo), cabi.LCC_FLAG_STRICT_FP, None))
+                out = np.empty_like(ia)
+                cabi.check(lib.lcc_memcpy_d2h(out.ctypes.data, ptrs[2], out.nbytes, None))
+                cabi.check(lib.lcc_stream_sync(None))
+                got = out if layout == cabi.LCC_AOS else out[:, :n].T
+                assert np.array_equal(got, ref(a, b))
+            rotor = rng.standard_normal(nb)
+            cabi.check(lib.lcc_batch_sandwich(alg.h, rotor.ctypes.data_as(C.POINTER(C.c_double)), C.byref(va), C.byref(vo), cabi.LCC_FLAG_STRICT_FP, None))
+            out = np.empty_like(ia)
+            cabi.check(lib.lcc_memcpy_d2h(out.ctypes.data, ptrs[2], out.nbytes, None))
+            cabi.check(lib.lcc_stream_sync(None))
+            got = out if layout == cabi.LCC_AOS else out[:, :n].T
+            assert np.array_equal(got, o.sandwich(rotor, a))
+            for p in ptrs:
+                cabi.check(lib.lcc_device_free(p, None))
+    # argument validation: wrong column count, mismatched rows (batch.rs:83-88,372-375)
+    bad = cabi.view(1 << 20, 4, 8, cabi.LCC_F64, cabi.LCC_AOS)
+    assert lib.lcc_batch_product(alg.h, 0, C.byref(bad), C.byref(bad), C.byref(bad), 0, None) == cabi.LCC_ERR_VALUE
+    assert b"must have 16 columns" in lib.lcc_last_error()
+
+
+def test_host_buffer_entry_points(L):
+    """lcc_host_sandwich / lcc_host_product: chunked H2D -> kernel -> D2H pipeline over several chunks."""
+    from largecrimsoncanine_b200 import cabi
+
+    lib = cabi.lib()
+    alg, o = cabi.Algebra(3, 0, 1), oracle.OracleAlgebra(3, 0, 1)
+    rng = np.random.default_rng(19)
+    n = 2_300_000  # > 2 chunks of 64 MiB at 64 B/row
+    x = rng.standard_normal((n, 16), dtype=np.float32)
+    motor = np.zeros(16)
+    motor[[0, 3, 5, 6, 9, 10, 12]] = rng.standard_normal(7)
+    out = np.empty_like(x)
+    cabi.check(lib.lcc_host_sandwich(alg.h, cabi.LCC_F32, motor.ctypes.data_as(C.POINTER(C.c_double)), x.ctypes.data, out.ctypes.data, n, cabi.LCC_FLAG_STRICT_FP))
+    sample = np.r_[0:4096, n // 2:n // 2 + 4096, n - 4096:n]
+    assert np.array_equal(out[sample], o.sandwich(motor, x[sample]))
+    a = rng.standard_normal((300_001, 16))
+    b = rng.standard_normal((1, 16))
+    res = np.empty_like(a)
+    cabi.check(lib.lcc_host_product(alg.h, cabi.LCC_F64, cabi.LCC_OP_GP, a.ctypes.data, a.shape[0], b.ctypes.data, 1, res.ctypes.data, cabi.LCC_FLAG_STRICT_FP))
+    assert np.array_equal(res[:5000], o.geometric_product(a[:5000], b))
