@@ -243,8 +243,9 @@ py::array contiguous(const py::array &arr) {
 py::dtype np_dtype(int dtype) { return dtype == LCC_F32 ? py::dtype::of<float>() : py::dtype::of<double>(); }
 
 // upload an (n, cols) host array as a dense device AoS block; caller frees
-void upload(const py::array &arr, void *dst) {
-    check(lcc_memcpy_h2d(dst, arr.data(), (size_t)arr.nbytes(), nullptr));
+// (pointer and size are taken while the GIL is held; the copy itself runs without it)
+void upload(const void *host, size_t bytes, void *dst) {
+    check(lcc_memcpy_h2d(dst, host, bytes, nullptr));
     check(lcc_stream_sync(nullptr));  // the NumPy buffer may be pageable and may change after we return
 }
 
@@ -260,9 +261,11 @@ BatchPtr batch_from_numpy(const PyAlgebra &alg, const py::array &coeffs_in) {  /
     const int64_t n = coeffs.shape(0);
     auto b = std::make_shared<Batch>(alg.inner, dtype, n);
     if (n == 0) return b;
+    const void *host = coeffs.data();
+    const size_t bytes = (size_t)coeffs.nbytes();
     py::gil_scoped_release nogil;
-    DeviceTemp stage((size_t)coeffs.nbytes());
-    upload(coeffs, stage.ptr);
+    DeviceTemp stage(bytes);
+    upload(host, bytes, stage.ptr);
     lcc_view src{stage.ptr, n, nb, dtype, LCC_AOS};
     check(lcc_batch_convert(alg.inner->h, &src, &b->view, nullptr));
     return b;
@@ -276,9 +279,11 @@ BatchPtr batch_from_columns(const PyAlgebra &alg, const py::array &cols_in, cons
     auto b = std::make_shared<Batch>(alg.inner, dtype, n);
     if (n == 0) return b;
     (void)what;
+    const void *host = cols.data();
+    const size_t bytes = (size_t)cols.nbytes();
     py::gil_scoped_release nogil;
-    DeviceTemp stage((size_t)std::max<int64_t>(cols.nbytes(), 16));
-    if (cols.nbytes()) upload(cols, stage.ptr);
+    DeviceTemp stage(std::max<size_t>(bytes, 16));
+    if (bytes) upload(host, bytes, stage.ptr);
     check(lcc_batch_scatter_columns(alg.inner->h, stage.ptr, ncols, blades.data(), &b->view, nullptr));
     return b;
 }
@@ -288,24 +293,26 @@ py::array batch_gather(const Batch &b, const std::vector<int32_t> &blades, bool 
     std::vector<py::ssize_t> shape;
     if (flat) shape = {(py::ssize_t)b.n()}; else shape = {(py::ssize_t)b.n(), (py::ssize_t)ncols};
     py::array out(np_dtype(b.view.dtype), shape);
+    void *out_ptr = out.mutable_data();
     if (b.n() == 0 || ncols == 0) return out;
     py::gil_scoped_release nogil;
     DeviceTemp stage((size_t)b.n() * ncols * b.es());
     check(lcc_batch_gather_columns(b.algebra->h, &b.view, ncols, blades.data(), stage.ptr, nullptr));
-    check(lcc_memcpy_d2h(out.mutable_data(), stage.ptr, (size_t)b.n() * ncols * b.es(), nullptr));
+    check(lcc_memcpy_d2h(out_ptr, stage.ptr, (size_t)b.n() * ncols * b.es(), nullptr));
     check(lcc_stream_sync(nullptr));
     return out;
 }
 
 py::array batch_to_numpy(const Batch &b) {  // src/batch.rs:233-235
     py::array out(np_dtype(b.view.dtype), std::vector<py::ssize_t>{(py::ssize_t)b.n(), (py::ssize_t)b.nb()});
+    void *out_ptr = out.mutable_data();
     if (b.n() == 0) return out;
     py::gil_scoped_release nogil;
     const size_t bytes = (size_t)b.n() * b.nb() * b.es();
     DeviceTemp stage(bytes);
     lcc_view dst{stage.ptr, b.n(), b.nb(), b.view.dtype, LCC_AOS};
     check(lcc_batch_convert(b.algebra->h, &b.view, &dst, nullptr));
-    check(lcc_memcpy_d2h(out.mutable_data(), stage.ptr, bytes, nullptr));
+    check(lcc_memcpy_d2h(out_ptr, stage.ptr, bytes, nullptr));
     check(lcc_stream_sync(nullptr));
     return out;
 }
@@ -350,11 +357,12 @@ BatchPtr batch_addsub(const Batch &a, const Batch &b, int op) {
 }
 py::array batch_norm(const Batch &a, int kind) {
     py::array out(np_dtype(a.view.dtype), std::vector<py::ssize_t>{(py::ssize_t)a.n()});
+    void *out_ptr = out.mutable_data();
     if (a.n() == 0) return out;
     py::gil_scoped_release nogil;
     DeviceTemp stage((size_t)a.n() * a.es());
     check(lcc_batch_norm(a.algebra->h, kind, &a.view, stage.ptr, fp_flags(), nullptr));
-    check(lcc_memcpy_d2h(out.mutable_data(), stage.ptr, (size_t)a.n() * a.es(), nullptr));
+    check(lcc_memcpy_d2h(out_ptr, stage.ptr, (size_t)a.n() * a.es(), nullptr));
     check(lcc_stream_sync(nullptr));
     return out;
 }
@@ -432,11 +440,12 @@ BatchPtr batch_concat(const Batch &a, const Batch &b) {  // src/batch.rs:1055-10
 py::array batch_sum(const Batch &a, bool mean) {
     const int nb = a.nb();
     py::array out(np_dtype(a.view.dtype), std::vector<py::ssize_t>{(py::ssize_t)nb});
+    void *out_ptr = out.mutable_data();
     {
         py::gil_scoped_release nogil;
         DeviceTemp stage((size_t)nb * a.es());
         check(lcc_batch_sum(a.algebra->h, &a.view, stage.ptr, nullptr));
-        check(lcc_memcpy_d2h(out.mutable_data(), stage.ptr, (size_t)nb * a.es(), nullptr));
+        check(lcc_memcpy_d2h(out_ptr, stage.ptr, (size_t)nb * a.es(), nullptr));
         check(lcc_stream_sync(nullptr));
     }
     if (mean && a.n() > 0) {
@@ -869,9 +878,11 @@ PYBIND11_MODULE(largecrimsoncanine, m) {
             if (xyz.ndim() != 2 || xyz.shape(1) != 3) throw py::value_error("points must have 3 columns");
             auto b = std::make_shared<Batch>(a.inner, dtype, xyz.shape(0));
             if (xyz.shape(0) == 0) { require_pga3d(a, "pga_point"); return b; }
+            const void *host = xyz.data();
+            const size_t bytes = (size_t)xyz.nbytes();
             py::gil_scoped_release nogil;
-            DeviceTemp stage((size_t)xyz.nbytes());
-            upload(xyz, stage.ptr);
+            DeviceTemp stage(bytes);
+            upload(host, bytes, stage.ptr);
             check(lcc_pga_points_embed(a.inner->h, stage.ptr, &b->view, nullptr));
             return b;
         })
@@ -881,29 +892,33 @@ PYBIND11_MODULE(largecrimsoncanine, m) {
             if (xyz.ndim() != 2 || xyz.shape(1) != 3) throw py::value_error("points must have 3 columns");
             auto b = std::make_shared<Batch>(a.inner, dtype, xyz.shape(0));
             if (xyz.shape(0) == 0) return b;
+            const void *host = xyz.data();
+            const size_t bytes = (size_t)xyz.nbytes();
             py::gil_scoped_release nogil;
-            DeviceTemp stage((size_t)xyz.nbytes());
-            upload(xyz, stage.ptr);
+            DeviceTemp stage(bytes);
+            upload(host, bytes, stage.ptr);
             check(lcc_cga_points_embed(a.inner->h, stage.ptr, &b->view, nullptr));
             return b;
         })
         .def("pga_point_coords", [](const Batch &b) {
             py::array out(np_dtype(b.view.dtype), std::vector<py::ssize_t>{(py::ssize_t)b.n(), 3});
+    void *out_ptr = out.mutable_data();
             if (b.n() == 0) return out;
             py::gil_scoped_release nogil;
             DeviceTemp stage((size_t)b.n() * 3 * b.es());
             check(lcc_pga_points_extract(b.algebra->h, &b.view, stage.ptr, nullptr));
-            check(lcc_memcpy_d2h(out.mutable_data(), stage.ptr, (size_t)b.n() * 3 * b.es(), nullptr));
+            check(lcc_memcpy_d2h(out_ptr, stage.ptr, (size_t)b.n() * 3 * b.es(), nullptr));
             check(lcc_stream_sync(nullptr));
             return out;
         })
         .def("cga_extract_center", [](const Batch &b) {
             py::array out(np_dtype(b.view.dtype), std::vector<py::ssize_t>{(py::ssize_t)b.n(), 3});
+    void *out_ptr = out.mutable_data();
             if (b.n() == 0) return out;
             py::gil_scoped_release nogil;
             DeviceTemp stage((size_t)b.n() * 3 * b.es());
             check(lcc_cga_points_extract(b.algebra->h, &b.view, stage.ptr, nullptr));
-            check(lcc_memcpy_d2h(out.mutable_data(), stage.ptr, (size_t)b.n() * 3 * b.es(), nullptr));
+            check(lcc_memcpy_d2h(out_ptr, stage.ptr, (size_t)b.n() * 3 * b.es(), nullptr));
             check(lcc_stream_sync(nullptr));
             return out;
         });
