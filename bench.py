@@ -40,7 +40,8 @@ WORKLOADS = {
     "cga_gp": ((4, 1, 0), "f64", 26, 768, "products/s"),
     "cga_gp_outer": ((4, 1, 0), "f64", 26, 1024, "products/s"),
     "r3_gp": ((3, 0, 0), "f64", 20, 192, "products/s"),
-    "sta_grade_inner_sum": ((1, 3, 0), "f64", 27, 256 + 384 + 128, "multivectors/s"),
+    # grade(1) reads 4 blade rows and writes 16 (160 B), lc reads 2x16 and writes 16 (384 B), sum reads 16 (128 B)
+    "sta_grade_inner_sum": ((1, 3, 0), "f64", 27, 160 + 384 + 128, "multivectors/s"),
 }
 HEADLINE = "pga_sandwich"
 
@@ -363,7 +364,7 @@ def run_gpu_arm(args):
     except Exception:
         pass
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:  # CPU baseline on rank 0 at N = 1 only
         rows = cpu_sample_rows(wl)
         rate1, t1 = cpu_rate(wl, rows, 1)
         import oracle

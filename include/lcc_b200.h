@@ -169,6 +169,13 @@ LCC_API lcc_status lcc_batch_product(const lcc_algebra *alg, int op, const lcc_v
 /* Fused dual-output: gp_out = a*b and outer_out = a^b reading a and b once (BASELINE config 3). */
 LCC_API lcc_status lcc_batch_gp_outer(const lcc_algebra *alg, const lcc_view *a, const lcc_view *b,
                                       const lcc_view *gp_out, const lcc_view *outer_out, unsigned flags, void *stream);
+/* Vector-Jacobian products of the three bilinear products (autograd of lcc.torch; new surface):
+ *   wrt = 0  grad_in[i] = sum_j sign[i][j] * grad_out[i^j] * other[j]   (other = the right operand b)
+ *   wrt = 1  grad_in[j] = sum_i sign[i][j] * other[i] * grad_out[i^j]   (other = the left operand a)
+ * restricted to the op's term set.  `other` may be a one-row batch (broadcast); the caller sums
+ * grad_in over rows (lcc_batch_sum) when the differentiated operand itself was broadcast. */
+LCC_API lcc_status lcc_batch_product_vjp(const lcc_algebra *alg, int op, int wrt, const lcc_view *grad_out,
+                                         const lcc_view *other, const lcc_view *grad_in, unsigned flags, void *stream);
 /* out[row] = R * x[row] * ~R with one rotor/motor (host array of num_blades doubles) for the whole
  * batch, two rounded stages as in batch.rs:434-503. */
 LCC_API lcc_status lcc_batch_sandwich(const lcc_algebra *alg, const double *rotor, const lcc_view *x,

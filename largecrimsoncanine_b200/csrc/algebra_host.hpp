@@ -24,9 +24,10 @@ struct lcc_algebra {
     bool specialised = false;      // build-time generated kernels exist for this signature
     lcc::ProductLauncher product[2] = {nullptr, nullptr};   // [dtype]
     lcc::SandwichLauncher sandwich[2] = {nullptr, nullptr};
-    // gather_signs[k*nb+i] = sign(i, i^k), uploaded lazily per device for the looped product (nb > 32)
+    // gather-form sign tables G[k*nb+i] for the table-driven kernel, uploaded lazily per (device, kind):
+    // kinds 0..2 forward gp / outer / lc, 3..5 their VJP wrt the left operand, 6..8 wrt the right one
     std::mutex mu_dev;
-    std::map<int, int8_t *> gather_signs_dev;
+    std::map<std::pair<int, int>, int8_t *> gather_signs_dev;
 };
 
 namespace lcc {

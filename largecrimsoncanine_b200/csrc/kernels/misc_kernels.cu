@@ -252,23 +252,30 @@ gather_columns_kernel(const T *__restrict__ src, int64_t lds, int64_t n, int nco
     cols[e] = LAYOUT == kSoA ? __ldg(src + (int64_t)k * lds + r) : __ldg(src + r * lds + k);
 }
 
-// ------------------------------------------------------------------------------------------ looped product (64..256 blades)
+// ------------------------------------------------------------------------------------------ table-driven product
+// out[k] = sum_i G[k][i] * x[i] * y[i^k], i ascending, with an arbitrary sign table G (int8, on the
+// device).  Serves (1) the products of algebras above 32 blades, where G[k][i] = sign(i, i^k) keeps
+// the reference's ascending-left-blade order per output blade (batch.rs:384-404), and (2) the
+// vector-Jacobian products behind lcc.torch autograd for every algebra (tables in lcc_abi.cu).
 // One block owns 32 rows; both operand tiles sit in shared memory as [blade][row]; warp w produces
-// output blades w, w+8, ...  gather_signs[k*nb+i] = sign(i, i^k) keeps the reference's ascending-i
-// order per output blade (batch.rs:384-404).  Not a bandwidth-bound kernel: 2*nb^2 shared loads per row.
+// output blades w, w+8, ...  Not a bandwidth-bound kernel: 2*nb^2 shared loads per row.
+template <class T> __device__ __forceinline__ T view_load(const T *p, int64_t ld, int layout, int64_t r, int k) {
+    return layout == kSoA ? __ldg(p + (int64_t)k * ld + r) : __ldg(p + r * ld + k);
+}
+
 template <class T, bool STRICT>
 __global__ void __launch_bounds__(kThreads)
-big_product_kernel(const T *__restrict__ a, int64_t lda, int a_bc, const T *__restrict__ b, int64_t ldb, int b_bc,
-                   T *__restrict__ out, int64_t ldo, int64_t n, int nb, int op, const int8_t *__restrict__ gsign) {
+table_product_kernel(const T *__restrict__ x, int64_t ldx, int x_bc, const T *__restrict__ y, int64_t ldy, int y_bc,
+                     T *__restrict__ out, int64_t ldo, int64_t n, int nb, int layout, const int8_t *__restrict__ gsign) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *sa = reinterpret_cast<T *>(smem_raw);
-    T *sb = sa + (size_t)nb * 32;
+    T *sx = reinterpret_cast<T *>(smem_raw);
+    T *sy = sx + (size_t)nb * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t r = (int64_t)blockIdx.x * 32 + lane;
     const bool live = r < n;
     for (int i = warp; i < nb; i += kThreads / 32) {
-        sa[i * 32 + lane] = live ? __ldg(a + (int64_t)i * lda + (a_bc ? 0 : r)) : T(0);
-        sb[i * 32 + lane] = live ? __ldg(b + (int64_t)i * ldb + (b_bc ? 0 : r)) : T(0);
+        sx[i * 32 + lane] = live ? view_load(x, ldx, layout, x_bc ? 0 : r, i) : T(0);
+        sy[i * 32 + lane] = live ? view_load(y, ldy, layout, y_bc ? 0 : r, i) : T(0);
     }
     __syncthreads();
     for (int k = warp; k < nb; k += kThreads / 32) {
@@ -276,14 +283,13 @@ big_product_kernel(const T *__restrict__ a, int64_t lda, int a_bc, const T *__re
         const int8_t *g = gsign + (size_t)k * nb;
         for (int i = 0; i < nb; ++i) {
             const int s = g[i];
-            const int j = i ^ k;
             if (s == 0) continue;
-            if (op == kOpOuter && (i & j) != 0) continue;
-            if (op == kOpLC && (i & j) != i) continue;
-            const T av = sa[i * 32 + lane];
-            acc = Arith<STRICT>::madd(s > 0 ? av : -av, sb[j * 32 + lane], acc);
+            const T xv = sx[i * 32 + lane];
+            acc = Arith<STRICT>::madd(s > 0 ? xv : -xv, sy[(i ^ k) * 32 + lane], acc);
         }
-        if (live) out[(int64_t)k * ldo + r] = acc;
+        if (live) {
+            if (layout == kSoA) out[(int64_t)k * ldo + r] = acc; else out[r * ldo + k] = acc;
+        }
     }
 }
 
@@ -477,7 +483,7 @@ cudaError_t launch_copy_rows(int nb, const ViewArg &src, int64_t start, int64_t 
     return launch_convert(nb, a, b, s);
 }
 
-cudaError_t launch_big_product(int nb, int op, bool strict, const ViewArg &a, bool a_bc, const ViewArg &b, bool b_bc, const ViewArg &out, const int8_t *gsign, cudaStream_t s) {
+cudaError_t launch_table_product(int nb, bool strict, const ViewArg &x, bool x_bc, const ViewArg &y, bool y_bc, const ViewArg &out, const int8_t *gsign, cudaStream_t s) {
     const int64_t n = out.n;
     if (n <= 0) return cudaSuccess;
     const size_t es = out.dtype == kF32 ? 4 : 8;
@@ -486,9 +492,9 @@ cudaError_t launch_big_product(int nb, int op, bool strict, const ViewArg &a, bo
         using T = decltype(tag);
         auto go = [&](auto kernel) {
             cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            kernel<<<blocks_for(n, 32), kThreads, smem, s>>>((const T *)a.data, a.ld, a_bc, (const T *)b.data, b.ld, b_bc, (T *)out.data, out.ld, n, nb, op, gsign);
+            kernel<<<blocks_for(n, 32), kThreads, smem, s>>>((const T *)x.data, x.ld, x_bc, (const T *)y.data, y.ld, y_bc, (T *)out.data, out.ld, n, nb, out.layout, gsign);
         };
-        if (strict) go(big_product_kernel<T, true>); else go(big_product_kernel<T, false>);
+        if (strict) go(table_product_kernel<T, true>); else go(table_product_kernel<T, false>);
     };
     return by_dtype(out.dtype, [&] { run(float()); }, [&] { run(double()); });
 }

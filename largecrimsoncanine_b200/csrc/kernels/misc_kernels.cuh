@@ -33,9 +33,10 @@ cudaError_t launch_gather_columns(int nb, const ViewArg &src, int ncols, const i
                                   cudaStream_t s);
 cudaError_t launch_copy_rows(int nb, const ViewArg &src, int64_t start, int64_t end, const ViewArg &dst,
                              int64_t dst_start, cudaStream_t s);
-// Looped product for 64..256 blades (SoA only): gather_signs[k*nb+i] = sign(i, i^k) on the device.
-cudaError_t launch_big_product(int nb, int op, bool strict, const ViewArg &a, bool a_bcast, const ViewArg &b,
-                               bool b_bcast, const ViewArg &out, const int8_t *gather_signs_dev, cudaStream_t s);
+// Table-driven product out[k] = sum_i G[k][i]*x[i]*y[i^k] (any layout, up to 256 blades): products of
+// algebras above 32 blades and the vector-Jacobian products of lcc.torch.  gsign is on the device.
+cudaError_t launch_table_product(int nb, bool strict, const ViewArg &x, bool x_bcast, const ViewArg &y, bool y_bcast,
+                                 const ViewArg &out, const int8_t *gsign_dev, cudaStream_t s);
 // PGA3D / CGA3D point embeddings and extractors (src/pga.rs:131-134,579-599; src/cga.rs:189-206,492-508)
 cudaError_t launch_points_embed(int which, const void *xyz, const ViewArg &dst, cudaStream_t s);
 cudaError_t launch_points_extract(int which, const ViewArg &src, void *xyz, cudaStream_t s);

@@ -21,6 +21,8 @@
 // and 2*NB*sizeof(T) for the sandwich; each byte is touched exactly once by a full-width
 // coalesced access (common.cuh).
 #pragma once
+#include <cstdlib>
+
 #include "common.cuh"
 #include "launch_args.h"
 
@@ -82,7 +84,7 @@ product_kernel(const real *__restrict__ a, int64_t lda, int a_bcast, const real 
                int b_bcast, real *__restrict__ out, int64_t ldo, real *__restrict__ out2, int64_t ldo2,
                int64_t n, int vec_ok, const Coeffs mu) {
     constexpr int V = LAYOUT == kSoA ? kRowsSoA : 1;
-    const int64_t r0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * V;
+    const int64_t r0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
     if (r0 >= n) return;
 
     Tile<real, NB, V> A, B;
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(kThreads)
 sandwich_kernel(const real *__restrict__ x, int64_t ldx, real *__restrict__ out, int64_t ldo, int64_t n,
                 int vec_ok, const Coeffs R, const Coeffs Rrev, const Coeffs mu) {
     constexpr int V = LAYOUT == kSoA ? kRowsSoA : 1;
-    const int64_t r0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * V;
+    const int64_t r0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
     if (r0 >= n) return;
 
     Tile<real, NB, V> X, RX;
@@ -167,10 +169,25 @@ static inline Coeffs to_coeffs(const double *src, double fill) {
     return c;
 }
 
+// Threads per block.  These kernels hold 100-170 registers per thread, so a 256-thread block fits
+// once or twice per SM and all its warps move through load / compute / store in lock step; small
+// blocks (128 threads at 32 blades, 64 below) fit 3-8 times and their phases interleave, which is
+// what keeps HBM busy: CGA gp f64 5263 -> 6804 GB/s, PGA sandwich f32 6370 -> 6766 GB/s
+// (gpurun_out/blocksize.log, profiles/r01_blocksize_sweep.txt).
+// LCC_BLOCK_THREADS (32, 64, 128 or 256) overrides the choice for experiments.
+static inline int block_threads() {
+    static const int chosen = [] {
+        const char *e = std::getenv("LCC_BLOCK_THREADS");
+        if (e) { int v = std::atoi(e); if (v == 32 || v == 64 || v == 128 || v == 256) return v; }
+        return NB >= 32 ? 128 : 64;
+    }();
+    return chosen;
+}
+
 template <int LAYOUT> static inline unsigned grid_for(int64_t n) {
     constexpr int V = LAYOUT == kSoA ? kRowsSoA : 1;
-    int64_t threads = (n + V - 1) / V;
-    return (unsigned)((threads + kThreads - 1) / kThreads);
+    const int64_t threads = (n + V - 1) / V, block = block_threads();
+    return (unsigned)((threads + block - 1) / block);
 }
 
 template <int LAYOUT, int OP, bool STRICT> static cudaError_t launch_product_t(const ProductArgs &g) {
@@ -181,7 +198,7 @@ template <int LAYOUT, int OP, bool STRICT> static cudaError_t launch_product_t(c
         auto ok = [&](const void *p, int64_t ld) { return ((uintptr_t)p % 16 == 0) && (ld % W == 0); };
         vec_ok = ok(g.a, g.lda) && ok(g.b, g.ldb) && ok(g.out, g.ldo) && (OP != kOpGPOuter || ok(g.out2, g.ldo2));
     }
-    product_kernel<LAYOUT, OP, STRICT><<<grid_for<LAYOUT>(g.n), kThreads, 0, g.stream>>>(
+    product_kernel<LAYOUT, OP, STRICT><<<grid_for<LAYOUT>(g.n), block_threads(), 0, g.stream>>>(
         (const real *)g.a, g.lda, g.a_bcast, (const real *)g.b, g.ldb, g.b_bcast, (real *)g.out, g.ldo,
         (real *)g.out2, g.ldo2, g.n, vec_ok, to_coeffs(g.mu, 1.0));
     note_kernel_launch();
@@ -216,7 +233,7 @@ template <int LAYOUT, bool STRICT, bool EVEN> static cudaError_t launch_sandwich
         // ~R[i] = R[i] * reverse_sign(grade): src/batch.rs:452-457, src/algebra/blades.rs:128-135
         Rrev.v[i] = R.v[i] * ((grade % 4 < 2) ? real(1) : real(-1));
     }
-    sandwich_kernel<LAYOUT, STRICT, EVEN><<<grid_for<LAYOUT>(g.n), kThreads, 0, g.stream>>>(
+    sandwich_kernel<LAYOUT, STRICT, EVEN><<<grid_for<LAYOUT>(g.n), block_threads(), 0, g.stream>>>(
         (const real *)g.x, g.ldx, (real *)g.out, g.ldo, g.n, vec_ok, R, Rrev, to_coeffs(g.mu, 1.0));
     note_kernel_launch();
     return cudaGetLastError();

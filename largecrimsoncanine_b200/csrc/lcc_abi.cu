@@ -209,22 +209,35 @@ lcc_status same_kind(const lcc_view *a, const lcc_view *b, const char *what) {
     return LCC_OK;
 }
 
-// device copy of gather_signs for the looped (> 32 blades) product
-lcc_status gather_signs_on_device(const lcc_algebra *calg, const int8_t **out) {
+// Device copy of a gather-form sign table for the table-driven kernel.
+//   forward  (kind = op):        out[k] = sum_i S[i][i^k] a[i] b[i^k]              G[k][i] = S[i][i^k]
+//   VJP wrt a (kind = 3 + op):   ga[i]  = sum_k' S[i][i^k'] g[k'] b[k'^i]           G[i][k'] = S[i][i^k']  (x = g, y = b)
+//   VJP wrt b (kind = 6 + op):   gb[j]  = sum_i  S[i][j]    a[i]  g[i^j]            G[j][i]  = S[i][j]     (x = a, y = g)
+// each restricted to the op's term set ((i&j)==0 outer, (i&j)==i left contraction; batch.rs:555,636).
+lcc_status gather_signs_on_device(const lcc_algebra *calg, int kind, const int8_t **out) {
     lcc_algebra *alg = const_cast<lcc_algebra *>(calg);
     int dev = 0;
     LCC_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(alg->mu_dev);
-    auto it = alg->gather_signs_dev.find(dev);
+    auto key = std::make_pair(dev, kind);
+    auto it = alg->gather_signs_dev.find(key);
     if (it != alg->gather_signs_dev.end()) { *out = it->second; return LCC_OK; }
-    const int nb = alg->nb;
+    const int nb = alg->nb, op = kind % 3, which = kind / 3;
+    auto in_op = [&](int i, int j) { return op == kOpGP || (op == kOpOuter && (i & j) == 0) || (op == kOpLC && (i & j) == i); };
+    auto S = [&](int i, int j) -> int8_t { return in_op(i, j) ? alg->signs[(size_t)i * nb + j] : (int8_t)0; };
     std::vector<int8_t> g((size_t)nb * nb);
-    for (int k = 0; k < nb; ++k)
-        for (int i = 0; i < nb; ++i) g[(size_t)k * nb + i] = alg->signs[(size_t)i * nb + (i ^ k)];
+    for (int o = 0; o < nb; ++o)
+        for (int x = 0; x < nb; ++x) {
+            int8_t v;
+            if (which == 0) v = S(x, x ^ o);        // o = output blade k, x = left blade i, right blade i^k
+            else if (which == 1) v = S(o, o ^ x);   // o = left blade i, x = grad blade k', right blade i^k'
+            else v = S(x, o);                       // o = right blade j, x = left blade i, grad blade i^j
+            g[(size_t)o * nb + x] = v;
+        }
     int8_t *d = nullptr;
     LCC_CUDA(cudaMalloc(&d, g.size()));
     LCC_CUDA(cudaMemcpy(d, g.data(), g.size(), cudaMemcpyHostToDevice));
-    alg->gather_signs_dev[dev] = d;
+    alg->gather_signs_dev[key] = d;
     *out = d;
     return LCC_OK;
 }
@@ -455,23 +468,11 @@ static lcc_status run_product(const lcc_algebra *alg, int op, const lcc_view *a,
         LCC_CUDA(launch(g));
         return LCC_OK;
     }
-    // 64..256 blades: looped shared-memory kernel on SoA data (AoS operands are transposed through pool temporaries)
-    const int8_t *gs = nullptr;
-    LCC_TRY(gather_signs_on_device(alg, &gs));
+    // 64..256 blades: table-driven shared-memory kernel (any layout)
     auto one = [&](int single_op, const lcc_view *dst) -> lcc_status {
-        if (a->layout == LCC_SOA) {
-            LCC_CUDA(launch_big_product(alg->nb, single_op, strict, arg_of(a), a_bc, arg_of(b), b_bc, arg_of(dst), gs, s));
-            return LCC_OK;
-        }
-        PoolBuffer ba, bb, bo;
-        lcc_view ta, tb, to;
-        LCC_TRY(make_soa_temp(alg, a->dtype, a->n, ba, &ta, s));
-        LCC_TRY(make_soa_temp(alg, a->dtype, b->n, bb, &tb, s));
-        LCC_TRY(make_soa_temp(alg, a->dtype, n, bo, &to, s));
-        LCC_CUDA(launch_convert(alg->nb, arg_of(a), arg_of(&ta), s));
-        LCC_CUDA(launch_convert(alg->nb, arg_of(b), arg_of(&tb), s));
-        LCC_CUDA(launch_big_product(alg->nb, single_op, strict, arg_of(&ta), a_bc, arg_of(&tb), b_bc, arg_of(&to), gs, s));
-        LCC_CUDA(launch_convert(alg->nb, arg_of(&to), arg_of(dst), s));
+        const int8_t *gs = nullptr;
+        LCC_TRY(gather_signs_on_device(alg, single_op, &gs));
+        LCC_CUDA(launch_table_product(alg->nb, strict, arg_of(a), a_bc, arg_of(b), b_bc, arg_of(dst), gs, s));
         return LCC_OK;
     };
     if (op == kOpGPOuter) { LCC_TRY(one(kOpGP, out)); return one(kOpOuter, out2); }
@@ -488,6 +489,29 @@ lcc_status lcc_batch_gp_outer(const lcc_algebra *alg, const lcc_view *a, const l
                               const lcc_view *outer_out, unsigned flags, void *stream) {
     if (!outer_out) return fail(LCC_ERR_VALUE, "outer_out is NULL");
     return run_product(alg, kOpGPOuter, a, b, gp_out, outer_out, flags, stream);
+}
+
+lcc_status lcc_batch_product_vjp(const lcc_algebra *alg, int op, int wrt, const lcc_view *grad_out, const lcc_view *other,
+                                 const lcc_view *grad_in, unsigned flags, void *stream) {
+    if (op != LCC_OP_GP && op != LCC_OP_OUTER && op != LCC_OP_LC) return fail(LCC_ERR_VALUE, "unknown product op %d", op);
+    if (wrt != 0 && wrt != 1) return fail(LCC_ERR_VALUE, "wrt must be 0 (left operand) or 1 (right operand)");
+    LCC_TRY(check_view(alg, grad_out, "grad_out"));
+    LCC_TRY(check_view(alg, other, "other"));
+    LCC_TRY(check_view(alg, grad_in, "grad_in"));
+    LCC_TRY(same_kind(grad_out, other, "product_vjp"));
+    LCC_TRY(same_kind(grad_out, grad_in, "product_vjp"));
+    if (other->n != grad_out->n && other->n != 1)
+        return fail(LCC_ERR_VALUE, "batch sizes must match or be 1 for broadcasting: %lld vs %lld", (long long)grad_out->n, (long long)other->n);
+    if (grad_in->n != grad_out->n) return fail(LCC_ERR_VALUE, "product_vjp: grad_in has %lld rows, expected %lld", (long long)grad_in->n, (long long)grad_out->n);
+    if (grad_out->n == 0) return LCC_OK;
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    const int8_t *gs = nullptr;
+    LCC_TRY(gather_signs_on_device(alg, 3 + 3 * wrt + op, &gs));
+    const bool strict = (flags & LCC_FLAG_STRICT_FP) != 0, other_bc = other->n == 1 && grad_out->n > 1;
+    if (wrt == 0) LCC_CUDA(launch_table_product(alg->nb, strict, arg_of(grad_out), false, arg_of(other), other_bc, arg_of(grad_in), gs, s));
+    else LCC_CUDA(launch_table_product(alg->nb, strict, arg_of(other), other_bc, arg_of(grad_out), false, arg_of(grad_in), gs, s));
+    return LCC_OK;
 }
 
 lcc_status lcc_batch_sandwich(const lcc_algebra *alg, const double *rotor, const lcc_view *x, const lcc_view *out,
@@ -516,42 +540,28 @@ lcc_status lcc_batch_sandwich(const lcc_algebra *alg, const double *rotor, const
         LCC_CUDA(launch(g));
         return LCC_OK;
     }
-    // > 32 blades: two looped products with the rotor as a one-row batch (batch.rs:462-496)
+    // > 32 blades: two table-driven products with the rotor as a one-row batch (batch.rs:462-496)
     const size_t es = elem_size(x->dtype);
     std::vector<unsigned char> host((size_t)2 * nb * es);
     for (int i = 0; i < nb; ++i) {
-        const double rev = rotor[i] * reverse_sign_of_grade(popcount32((unsigned)i));
-        if (x->dtype == LCC_F32) { ((float *)host.data())[i] = (float)rotor[i]; ((float *)host.data())[nb + i] = (float)rotor[i] * (float)reverse_sign_of_grade(popcount32((unsigned)i)); }
-        else { ((double *)host.data())[i] = rotor[i]; ((double *)host.data())[nb + i] = rev; }
+        const int rs = reverse_sign_of_grade(popcount32((unsigned)i));
+        if (x->dtype == LCC_F32) { ((float *)host.data())[i] = (float)rotor[i]; ((float *)host.data())[nb + i] = (float)rotor[i] * (float)rs; }
+        else { ((double *)host.data())[i] = rotor[i]; ((double *)host.data())[nb + i] = rotor[i] * rs; }
     }
     PoolBuffer br, brx;
     LCC_TRY(br.alloc(host.size(), s));
     LCC_CUDA(cudaMemcpyAsync(br.ptr, host.data(), host.size(), cudaMemcpyHostToDevice, s));
-    LCC_CUDA(cudaStreamSynchronize(s));  // host staging vector goes out of scope
-    // one-row SoA views with ld = 1: blade k of the rotor at data[k] (the looped kernel uses scalar loads)
-    lcc_view r1{br.ptr, 1, 1, x->dtype, LCC_SOA};
-    lcc_view r2{(char *)br.ptr + nb * es, 1, 1, x->dtype, LCC_SOA};
-    lcc_view rx;
-    LCC_TRY(make_soa_temp(alg, x->dtype, x->n, brx, &rx, s));
+    LCC_CUDA(cudaStreamSynchronize(s));  // the host staging vector goes out of scope
+    // one-row views of the rotor in x's layout: SoA with ld = 1 or AoS with ld = nb both put blade k at data[k]
+    lcc_view r1{br.ptr, 1, x->layout == LCC_SOA ? 1 : nb, x->dtype, x->layout};
+    lcc_view r2{(char *)br.ptr + nb * es, 1, r1.ld, x->dtype, x->layout};
+    lcc_view rx = *x;  // intermediate R*x with x's shape
+    LCC_TRY(brx.alloc((size_t)(x->layout == LCC_SOA ? nb * x->ld : x->n * x->ld) * es, s));
+    rx.data = brx.ptr;
     const int8_t *gs = nullptr;
-    LCC_TRY(gather_signs_on_device(alg, &gs));
-    auto big = [&](const lcc_view *a, bool a_bc, const lcc_view *b, bool b_bc, const lcc_view *dst) -> lcc_status {
-        LCC_CUDA(launch_big_product(nb, kOpGP, strict, arg_of(a), a_bc, arg_of(b), b_bc, arg_of(dst), gs, s));
-        return LCC_OK;
-    };
-    if (x->layout == LCC_SOA) {
-        LCC_TRY(big(&r1, true, x, false, &rx));
-        LCC_TRY(big(&rx, false, &r2, true, out));
-        return LCC_OK;
-    }
-    PoolBuffer bx, bo;
-    lcc_view tx, to;
-    LCC_TRY(make_soa_temp(alg, x->dtype, x->n, bx, &tx, s));
-    LCC_TRY(make_soa_temp(alg, x->dtype, x->n, bo, &to, s));
-    LCC_CUDA(launch_convert(nb, arg_of(x), arg_of(&tx), s));
-    LCC_TRY(big(&r1, true, &tx, false, &rx));
-    LCC_TRY(big(&rx, false, &r2, true, &to));
-    LCC_CUDA(launch_convert(nb, arg_of(&to), arg_of(out), s));
+    LCC_TRY(gather_signs_on_device(alg, kOpGP, &gs));
+    LCC_CUDA(launch_table_product(nb, strict, arg_of(&r1), true, arg_of(x), false, arg_of(&rx), gs, s));
+    LCC_CUDA(launch_table_product(nb, strict, arg_of(&rx), false, arg_of(&r2), true, arg_of(out), gs, s));
     return LCC_OK;
 }
 

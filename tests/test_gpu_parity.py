@@ -354,3 +354,21 @@ def test_host_buffer_entry_points(L):
     res = np.empty_like(a)
     cabi.check(lib.lcc_host_product(alg.h, cabi.LCC_F64, cabi.LCC_OP_GP, a.ctypes.data, a.shape[0], b.ctypes.data, 1, res.ctypes.data, cabi.LCC_FLAG_STRICT_FP))
     assert np.array_equal(res[:5000], o.geometric_product(a[:5000], b))
+
+
+def test_sharded_batch_single_rank(L):
+    """ShardedBatch with a world of one (the N > 1 path is covered by tests/test_sharding_gloo.py on CPU
+    and scripts/multi_gpu_check.py under torchrun on GPUs)."""
+    from largecrimsoncanine_b200 import sharded
+
+    rng = np.random.default_rng(23)
+    x, w = rng.standard_normal((5001, 16)), rng.standard_normal((5001, 16))
+    o = oracle.OracleAlgebra(1, 3, 0)
+    X = sharded.ShardedBatch.from_numpy(L.Algebra.sta(), x, 0, 1)
+    W = sharded.ShardedBatch.from_numpy(L.Algebra.sta(), w, 0, 1)
+    prod = X.grade(1).left_contraction(W)
+    ref = o.left_contraction(o.grade(x, 1), w)
+    want, mag = o.sum(ref)
+    assert np.all(np.abs(prod.sum() - want) <= 1e-12 * mag)
+    assert np.all(np.abs(prod.mean() - want / 5001) <= 1e-12 * mag / 5001)
+    assert len(prod) == 5001 and prod.info.rows == 5001

@@ -1,0 +1,112 @@
+"""lcc.torch on the GPU: forward parity against the oracle, gradients against plain PyTorch autograd
+of the same bilinear map (a dense sign-tensor einsum in float64 on the CPU)."""
+import numpy as np
+import pytest
+
+import oracle
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+SIGS = [(3, 0, 0), (3, 0, 1), (4, 1, 0), (1, 3, 0), (2, 1, 1)]
+MASK = {"gp": lambda i, j: True, "outer": lambda i, j: (i & j) == 0, "inner": lambda i, j: (i & j) == i}
+
+
+def sign_tensor(o, name):
+    """T[i, j, k] = sign(i, j) if k == i^j and the term belongs to the product, else 0."""
+    nb = o.num_blades
+    T = np.zeros((nb, nb, nb))
+    s = o.cayley_signs.reshape(nb, nb)
+    for i in range(nb):
+        for j in range(nb):
+            if MASK[name](i, j):
+                T[i, j, i ^ j] = s[i, j]
+    return torch.tensor(T)
+
+
+@pytest.fixture(scope="module")
+def lt():
+    import lcc.torch as m
+
+    return m
+
+
+@pytest.mark.parametrize("sig", SIGS)
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_forward_matches_oracle_bit_for_bit_in_strict_mode(lt, sig, dt):
+    o = oracle.OracleAlgebra(*sig)
+    alg = lt.TorchAlgebra._from_signature(*sig, device="cuda")
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(301, o.num_blades, generator=g, dtype=dt)
+    b = torch.randn(301, o.num_blades, generator=g, dtype=dt)
+    A, B = lt.TorchMultivector(alg, a.cuda()), lt.TorchMultivector(alg, b.cuda())
+    lt.set_strict_fp(True)
+    try:
+        assert np.array_equal(A.geometric_product(B).to_numpy(), o.geometric_product(a.numpy(), b.numpy()))
+        assert np.array_equal(A.outer_product(B).to_numpy(), o.outer_product(a.numpy(), b.numpy()))
+        assert np.array_equal(A.inner_product(B).to_numpy(), o.left_contraction(a.numpy(), b.numpy()))
+        assert np.array_equal(A.gp(B[0]).to_numpy(), o.geometric_product(a.numpy(), b.numpy()[:1]))
+        rotor = B[5]
+        assert np.array_equal(A.sandwich(rotor).to_numpy(), o.sandwich(b.numpy()[5].astype(np.float64), a.numpy()))
+        assert np.array_equal(A.norm_squared().cpu().numpy(), o.norm_squared(a.numpy()))
+    finally:
+        lt.set_strict_fp(False)
+    assert np.array_equal(A.reverse().to_numpy(), o.reverse(a.numpy()))
+    assert np.array_equal(A.grade_involution().to_numpy(), o.grade_involution(a.numpy()))
+    assert np.array_equal(A.conjugate().to_numpy(), o.clifford_conjugate(a.numpy()))
+    assert np.array_equal(A.grade(1).to_numpy(), o.grade(a.numpy(), 1))
+    want, mag = o.sum(a.numpy())
+    assert np.all(np.abs(A.sum().cpu().numpy().astype(np.float64) - want) <= (1e-13 if dt == torch.float64 else 1e-6) * mag)
+
+
+@pytest.mark.parametrize("sig", SIGS)
+@pytest.mark.parametrize("name", ["gp", "outer", "inner"])
+def test_gradients_match_pytorch_autograd_of_the_same_bilinear_map(lt, sig, name):
+    o = oracle.OracleAlgebra(*sig)
+    T = sign_tensor(o, name)
+    alg = lt.TorchAlgebra._from_signature(*sig, device="cuda")
+    g = torch.Generator().manual_seed(11)
+    for nb_rows in (64, 1):  # full batch and broadcast right operand
+        a = torch.randn(64, o.num_blades, generator=g, dtype=torch.float64)
+        b = torch.randn(nb_rows, o.num_blades, generator=g, dtype=torch.float64)
+        w = torch.randn(64, o.num_blades, generator=g, dtype=torch.float64)
+        ar, br = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        ref = torch.einsum("ni,nj,ijk->nk", ar, br.expand(64, -1), T)
+        (ref * w).sum().backward()
+        ac, bc = a.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+        A, B = lt.TorchMultivector(alg, ac), lt.TorchMultivector(alg, bc)
+        out = {"gp": A.geometric_product, "outer": A.outer_product, "inner": A.inner_product}[name](B)
+        (out.coeffs * w.cuda()).sum().backward()
+        assert torch.allclose(out.coeffs.detach().cpu(), ref.detach(), rtol=1e-12, atol=1e-12)
+        assert torch.allclose(ac.grad.cpu(), ar.grad, rtol=1e-11, atol=1e-11)
+        assert torch.allclose(bc.grad.cpu(), br.grad, rtol=1e-11, atol=1e-11)
+
+
+def test_sandwich_with_gradients_and_error_behaviour(lt):
+    alg = lt.TorchAlgebra.pga(3, device="cuda")
+    o = oracle.OracleAlgebra(3, 0, 1)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(33, 16, generator=g, dtype=torch.float64)
+    r = torch.randn(1, 16, generator=g, dtype=torch.float64)
+    xc = x.cuda().requires_grad_(True)
+    out = lt.TorchMultivector(alg, xc).sandwich(lt.TorchMultivector(alg, r.cuda()))
+    assert torch.allclose(out.coeffs.detach().cpu(), torch.tensor(o.sandwich(r.numpy()[0], x.numpy())), rtol=1e-12, atol=1e-12)
+    out.coeffs.sum().backward()
+    # sandwich is linear in x: grad = M^T 1, check by finite structure: apply to basis
+    basis = torch.eye(16, dtype=torch.float64)
+    M = torch.tensor(o.sandwich(r.numpy()[0], basis.numpy()))  # rows: image of each basis blade
+    assert torch.allclose(xc.grad.cpu(), M.sum(dim=1).expand(33, -1), rtol=1e-11, atol=1e-11)
+    with pytest.raises(ValueError, match="must have 16 columns"):
+        lt.TorchMultivector(alg, torch.zeros(4, 8))
+    cpu_alg = lt.TorchAlgebra.pga(3)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        lt.TorchMultivector(cpu_alg, torch.zeros(4, 16)).geometric_product(lt.TorchMultivector(cpu_alg, torch.zeros(4, 16)))
+    with pytest.raises(ValueError, match="batch sizes must match"):
+        lt.TorchMultivector(alg, torch.zeros(4, 16)).gp(lt.TorchMultivector(alg, torch.zeros(3, 16)))
+    # from_rust_algebra works with the extension's Algebra (the reference's version is broken)
+    import largecrimsoncanine as L
+
+    ta = lt.TorchAlgebra.from_rust_algebra(L.Algebra.cga(3), device="cuda")
+    assert ta.signature == (4, 1, 0) and ta.num_blades == 32 and ta.cayley_signs.shape == (32, 32)
+    vecs = lt.TorchMultivector.from_vectors(ta, torch.randn(7, 5, dtype=torch.float64))
+    assert vecs.to_vector_coords().shape == (7, 5) and len(vecs) == 7
