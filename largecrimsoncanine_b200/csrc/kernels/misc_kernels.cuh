@@ -37,6 +37,10 @@ cudaError_t launch_copy_rows(int nb, const ViewArg &src, int64_t start, int64_t 
 // algebras above 32 blades and the vector-Jacobian products of lcc.torch.  gsign is on the device.
 cudaError_t launch_table_product(int nb, bool strict, const ViewArg &x, bool x_bcast, const ViewArg &y, bool y_bcast,
                                  const ViewArg &out, const int8_t *gsign_dev, cudaStream_t s);
+// K6 (fixed_operand_gemm.cu): out = fixed * x (side 0) or x * fixed (side 1) for 64/128/256 blades, f32 SoA,
+// on the tcgen05 tensor cores with the 3xTF32 split.  signs_dev = sign[a*nb+b]; scratch_w = 2*nb*nb floats.
+cudaError_t launch_fixed_product_tf32x3(int nb, int side, const int8_t *signs_dev, const float *fixed_dev, int64_t fixed_stride,
+                                        const ViewArg &x, const ViewArg &out, float *scratch_w, cudaStream_t s);
 // PGA3D / CGA3D point embeddings and extractors (src/pga.rs:131-134,579-599; src/cga.rs:189-206,492-508)
 cudaError_t launch_points_embed(int which, const void *xyz, const ViewArg &dst, cudaStream_t s);
 cudaError_t launch_points_extract(int which, const ViewArg &src, void *xyz, cudaStream_t s);

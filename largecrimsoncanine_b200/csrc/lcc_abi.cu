@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -222,7 +223,7 @@ lcc_status gather_signs_on_device(const lcc_algebra *calg, int kind, const int8_
     auto key = std::make_pair(dev, kind);
     auto it = alg->gather_signs_dev.find(key);
     if (it != alg->gather_signs_dev.end()) { *out = it->second; return LCC_OK; }
-    const int nb = alg->nb, op = kind % 3, which = kind / 3;
+    const int nb = alg->nb, op = kind % 3, which = kind / 3;  // which == 3: the plain sign table sign[a*nb+b]
     auto in_op = [&](int i, int j) { return op == kOpGP || (op == kOpOuter && (i & j) == 0) || (op == kOpLC && (i & j) == i); };
     auto S = [&](int i, int j) -> int8_t { return in_op(i, j) ? alg->signs[(size_t)i * nb + j] : (int8_t)0; };
     std::vector<int8_t> g((size_t)nb * nb);
@@ -231,7 +232,8 @@ lcc_status gather_signs_on_device(const lcc_algebra *calg, int kind, const int8_
             int8_t v;
             if (which == 0) v = S(x, x ^ o);        // o = output blade k, x = left blade i, right blade i^k
             else if (which == 1) v = S(o, o ^ x);   // o = left blade i, x = grad blade k', right blade i^k'
-            else v = S(x, o);                       // o = right blade j, x = left blade i, grad blade i^j
+            else if (which == 2) v = S(x, o);       // o = right blade j, x = left blade i, grad blade i^j
+            else v = alg->signs[(size_t)o * nb + x]; // plain table (tensor-core path builds W from it)
             g[(size_t)o * nb + x] = v;
         }
     int8_t *d = nullptr;
@@ -466,6 +468,20 @@ static lcc_status run_product(const lcc_algebra *alg, int op, const lcc_view *a,
         g.mu = alg->specialised ? nullptr : alg->mu.data();
         g.stream = s;
         LCC_CUDA(launch(g));
+        return LCC_OK;
+    }
+    // 64..256 blades with ONE fixed operand (the broadcast branch, batch.rs:365-376), f32 SoA, FMA mode:
+    // a GEMM against the operand's multiplication matrix on the tcgen05 tensor cores (K6, 3xTF32)
+    static const bool tensor_path_off = [] { const char *e = getenv("LCC_DISABLE_TENSOR_PATH"); return e && e[0] == '1'; }();
+    if (!tensor_path_off && op == kOpGP && !strict && a->dtype == LCC_F32 && a->layout == LCC_SOA && (a_bc != b_bc) &&
+        (alg->nb == 64 || alg->nb == 128 || alg->nb == 256)) {
+        const int8_t *signs_dev = nullptr;
+        LCC_TRY(gather_signs_on_device(alg, 9, &signs_dev));
+        PoolBuffer w;
+        LCC_TRY(w.alloc((size_t)2 * alg->nb * alg->nb * sizeof(float), s));
+        const lcc_view *fixed = a_bc ? a : b, *batch = a_bc ? b : a;
+        LCC_CUDA(launch_fixed_product_tf32x3(alg->nb, a_bc ? 0 : 1, signs_dev, (const float *)fixed->data, fixed->ld,
+                                             arg_of(batch), arg_of(out), (float *)w.ptr, s));
         return LCC_OK;
     }
     // 64..256 blades: table-driven shared-memory kernel (any layout)
