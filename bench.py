@@ -43,6 +43,9 @@ WORKLOADS = {
     # grade(1) reads 4 blade rows and writes 16 (160 B), lc reads 2x16 and writes 16 (384 B), sum reads 16 (128 B)
     "sta_grade_inner_sum": ((1, 3, 0), "f64", 27, 160 + 384 + 128, "multivectors/s"),
 }
+# BASELINE config 5: fixed operand x batch in Cl(8,0,0) on the tensor cores (tf32 x3): bound = tensor
+WORKLOADS["cl8_fixed_gp"] = ((8, 0, 0), "f32", 24, 2048, "products/s")
+TENSOR_FLOPS_PER_UNIT = {"cl8_fixed_gp": 3 * 2 * 256 * 256}  # three tf32 MMAs per term
 HEADLINE = "pga_sandwich"
 
 
@@ -145,7 +148,9 @@ def cpu_rate(workload, sample_rows, threads, repeats=1):
     else:
         a = rng.standard_normal((sample_rows, nb)).astype(ndt)
         b = rng.standard_normal((sample_rows, nb)).astype(ndt)
-        if workload == "cga_gp_outer":
+        if workload == "cl8_fixed_gp":
+            fn = lambda: o.geometric_product(a[:1], b, threads=threads)  # noqa: E731
+        elif workload == "cga_gp_outer":
             fn = lambda: (o.geometric_product(a, b, threads=threads), o.outer_product(a, b, threads=threads))  # noqa: E731
         elif workload == "sta_grade_inner_sum":
             fn = lambda: o.sum(o.left_contraction(o.grade(a, 1), b, threads=threads))  # noqa: E731
@@ -161,7 +166,8 @@ def cpu_rate(workload, sample_rows, threads, repeats=1):
 
 
 def cpu_sample_rows(workload):
-    return {"pga_sandwich": 1 << 25, "cga_gp": 1 << 22, "cga_gp_outer": 1 << 22, "r3_gp": 1 << 20, "sta_grade_inner_sum": 1 << 23}[workload]
+    return {"pga_sandwich": 1 << 25, "cga_gp": 1 << 22, "cga_gp_outer": 1 << 22, "r3_gp": 1 << 20, "sta_grade_inner_sum": 1 << 23,
+            "cl8_fixed_gp": 1 << 14}[workload]
 
 
 def run_reference_arm(args):
@@ -204,6 +210,7 @@ def workload_name(wl):
         "pga_sandwich": "PGA Cl(3,0,1) motor sandwich", "cga_gp": "CGA Cl(4,1,0) batched geometric product",
         "cga_gp_outer": "CGA Cl(4,1,0) fused geometric + outer product", "r3_gp": "Cl(3,0,0) batched geometric product",
         "sta_grade_inner_sum": "STA Cl(1,3,0) grade projection + inner product + batch sum",
+        "cl8_fixed_gp": "Cl(8,0,0) fixed-operand left geometric product (tcgen05, 3xTF32)",
     }[wl]
     return f"{desc}, 2^{log2n} rows per GPU, {dt}, {1 << sum(sig)} blades"
 
@@ -277,6 +284,14 @@ def run_gpu_arm(args):
         else:
             def step():
                 cabi.check(lib.lcc_batch_product(alg.h, cabi.LCC_OP_GP, C.byref(va), C.byref(vb), C.byref(vo), flags, sptr))
+    elif wl == "cl8_fixed_gp":
+        b = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
+        a = torch.randn((nb, 4), device=dev, dtype=tdt, generator=gen)  # the fixed operand: one-row SoA view, ld = 4
+        out = torch.empty_like(b)
+        va, vb, vo = cabi.view(a.data_ptr(), 1, 4, code, cabi.LCC_SOA), soa(b), soa(out)
+
+        def step():
+            cabi.check(lib.lcc_batch_product(alg.h, cabi.LCC_OP_GP, C.byref(va), C.byref(vb), C.byref(vo), flags, sptr))
     elif wl == "sta_grade_inner_sum":
         a = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
         b = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
@@ -336,6 +351,11 @@ def run_gpu_arm(args):
             xs, ys = a[:, idx].T.contiguous().cpu().numpy(), b[:, idx].T.contiguous().cpu().numpy()
             got = out[:, idx].T.contiguous().cpu().numpy()
             want = o.left_contraction(o.grade(xs, 1), ys)
+        elif wl == "cl8_fixed_gp":
+            idx = idx[::64]
+            ys = b[:, idx].T.contiguous().cpu().numpy().astype(np.float64)
+            got = out[:, idx].T.contiguous().cpu().numpy()
+            want = o.geometric_product(a[:, 0].cpu().numpy().astype(np.float64)[None, :], ys)
         else:
             xs, ys = a[:, idx].T.contiguous().cpu().numpy(), b[:, idx].T.contiguous().cpu().numpy()
             got = out[:, idx].T.contiguous().cpu().numpy()
@@ -354,9 +374,7 @@ def run_gpu_arm(args):
         return 0
 
     peaks, peak_kind = load_peaks()
-    peak = float(peaks["hbm_gbs"])
     kernel_ms = ms_per_step  # one kernel per step for the headline; the step IS the kernel
-    achieved = bytes_per * n / (kernel_ms / 1e3) / 1e9
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -380,15 +398,28 @@ def run_gpu_arm(args):
         "vs_baseline": None, "dtype": dt, "data": "synthetic",
         "config": {"workload": workload_name(wl), "rows_per_gpu": n, "layout": "SoA (blade-major) in HBM",
                    "l2_policy": "inputs larger than L2 (>= 17 GB per pass vs 126 MB L2)", "strict_fp": bool(args.strict)},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
-                     "algorithmic_bytes_per_unit": bytes_per, "frac_of_nominal_8TBs": achieved / 8000.0},
+        "roofline": roofline_block(wl, n, kernel_ms, bytes_per, peaks, peak_kind, traffic),
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(), "parity": parity,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def roofline_block(wl, n, kernel_ms, bytes_per, peaks, peak_kind, traffic):
+    hbm = bytes_per * n / (kernel_ms / 1e3) / 1e9
+    if wl in TENSOR_FLOPS_PER_UNIT:  # dense contraction: tensor-pipe bound; nominal dense tf32 peak is half the bf16 one
+        tf = TENSOR_FLOPS_PER_UNIT[wl] * n / (kernel_ms / 1e3) / 1e12
+        peak_tf32 = float(peaks.get("bf16_tflops", 1590.0)) / 2.0
+        return {"bound": "tensor", "achieved": tf, "peak": peak_tf32, "unit": "TFLOP/s", "frac": tf / peak_tf32, "traffic": traffic,
+                "peak_source": f"{peak_kind} bf16_tflops / 2 (tf32 runs at half the bf16 rate; no direct tf32 measurement)",
+                "tensor_flops_per_unit": TENSOR_FLOPS_PER_UNIT[wl], "useful_tflops": tf / 3.0,
+                "hbm_gbs": hbm, "hbm_frac": hbm / float(peaks["hbm_gbs"]), "algorithmic_bytes_per_unit": bytes_per}
+    peak = float(peaks["hbm_gbs"])
+    return {"bound": "hbm", "achieved": hbm, "peak": peak, "unit": "GB/s", "frac": hbm / peak, "traffic": traffic,
+            "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)", "algorithmic_bytes_per_unit": bytes_per,
+            "frac_of_nominal_8TBs": hbm / 8000.0}
 
 
 def measure_e2e(args, lib, alg, code, motor, n, nb, world, rank, dev, dist, flags):

@@ -37,14 +37,15 @@ namespace lcc {
 namespace {
 
 constexpr int kBlockM = 128;   // rows per tile = TMEM lanes
-constexpr int kChunkK = 32;    // blades per pipeline stage (one 128-byte swizzle row of tf32)
 constexpr int kThreadsGemm = 384;
-constexpr uint32_t kXChunkBytes = kBlockM * kChunkK * 4;  // 16 KB
 
-template <int NB> struct Cfg {
-    static constexpr uint32_t kWChunkBytes = NB * kChunkK * 4;
+// CK = blades per pipeline stage: 32 (W rows are one 128-byte swizzle span) or 16 (64-byte span, twice the stages)
+template <int NB, int CK> struct Cfg {
+    static constexpr uint32_t kXChunkBytes = kBlockM * CK * 4;
+    static constexpr uint32_t kWChunkBytes = NB * CK * 4;
     static constexpr uint32_t kStageBytes = 2 * kXChunkBytes + 2 * kWChunkBytes;
-    static constexpr int kStages = NB == 256 ? 2 : (NB == 128 ? 3 : 4);
+    static constexpr int kStagesFit = (int)((227u * 1024 - 2048) / kStageBytes);
+    static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
     static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int kTmemCols = 2 * NB < 32 ? 32 : 2 * NB;  // two accumulators; power of two >= 32
 };
@@ -148,11 +149,13 @@ __global__ void build_w_kernel(const int8_t *__restrict__ signs, const float *__
 }
 
 // ------------------------------------------------------------------ the GEMM kernel
-template <int NB>
+template <int NB, int CK>
 __global__ void __launch_bounds__(kThreadsGemm, 1)
 fixed_product_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
                             const __grid_constant__ CUtensorMap map_wlo, float *__restrict__ out, int64_t ldo, int64_t n) {
-    using C = Cfg<NB>;
+    using C = Cfg<NB, CK>;
+    constexpr int kChunkK = CK;
+    constexpr uint32_t kXChunkBytes = C::kXChunkBytes;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // 128B swizzle atoms need 1024-byte alignment
     auto stage_ptr = [&](int s) { return smem + (size_t)s * C::kStageBytes; };
@@ -214,9 +217,11 @@ fixed_product_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __g
                     for (int kk = 0; kk < kChunkK / 8; ++kk) {
                         // A (MN-major, SW128 with 32-byte units): 4-blade K-atoms of 512 bytes (SBO), 8 blades = 1024 bytes
                         // per k-step; the four 32-row strips of the tile are 4096 bytes apart (LBO)
-                        const uint64_t a_hi = umma_desc(xhi + kk * 1024, 4096, 512, 1), a_lo = umma_desc(xlo + kk * 1024, 4096, 512, 1);
+                        constexpr uint32_t kStrip = CK * 128;  // one 32-row strip of the chunk
+                        const uint64_t a_hi = umma_desc(xhi + kk * 1024, kStrip, 512, 1), a_lo = umma_desc(xlo + kk * 1024, kStrip, 512, 1);
                         // B (K-major, SW128): 8 tf32 = 32 bytes per k-step inside the 128-byte row; 8-row groups 1024 bytes apart (SBO)
-                        const uint64_t b_hi = umma_desc(whi + kk * 32, 16, 1024), b_lo = umma_desc(wlo + kk * 32, 16, 1024);
+                        constexpr uint32_t kBLayout = CK == 32 ? 2 : 4, kBGroup = CK * 4 * 8;  // 128B / 64B swizzle; 8-row group pitch
+                        const uint64_t b_hi = umma_desc(whi + kk * 32, 16, kBGroup, kBLayout), b_lo = umma_desc(wlo + kk * 32, 16, kBGroup, kBLayout);
                         tcgen05_mma_tf32(d_tmem, a_hi, b_hi, idesc, (c | kk) != 0);
                         tcgen05_mma_tf32(d_tmem, a_lo, b_hi, idesc, 1);
                         tcgen05_mma_tf32(d_tmem, a_hi, b_lo, idesc, 1);
@@ -298,7 +303,7 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-template <int NB>
+template <int NB, int CK>
 cudaError_t launch_t(const float *x, int64_t ldx, float *out, int64_t ldo, int64_t n, const float *w_hi, const float *w_lo, cudaStream_t s) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return cudaErrorNotSupported;
@@ -306,7 +311,7 @@ cudaError_t launch_t(const float *x, int64_t ldx, float *out, int64_t ldo, int64
     {   // X (SoA): element (row r = 32*strip + i, blade k) at x[k*ldx + r]
         cuuint64_t dims[3] = {32, (cuuint64_t)NB, (cuuint64_t)(ldx / 32)};
         cuuint64_t strides[2] = {(cuuint64_t)ldx * 4, 128};
-        cuuint32_t box[3] = {32, (cuuint32_t)kChunkK, (cuuint32_t)(kBlockM / 32)};
+        cuuint32_t box[3] = {32, (cuuint32_t)CK, (cuuint32_t)(kBlockM / 32)};
         cuuint32_t estr[3] = {1, 1, 1};
         if (enc(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -315,20 +320,21 @@ cudaError_t launch_t(const float *x, int64_t ldx, float *out, int64_t ldo, int64
     for (int h = 0; h < 2; ++h) {  // Wt[n][k], k contiguous
         cuuint64_t dims[2] = {(cuuint64_t)NB, (cuuint64_t)NB};
         cuuint64_t strides[1] = {(cuuint64_t)NB * 4};
-        cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)NB};
+        cuuint32_t box[2] = {(cuuint32_t)CK, (cuuint32_t)NB};
         cuuint32_t estr[2] = {1, 1};
         if (enc(h ? &mlo : &mhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)(h ? w_lo : w_hi), dims, strides, box, estr,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return cudaErrorInvalidValue;
     }
     static int sm_count = [] { int d = 0, c = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, d); return c > 0 ? c : 148; }();
     const int64_t tiles = (n + kBlockM - 1) / kBlockM;
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
-    auto kernel = fixed_product_tf32x3_kernel<NB>;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<NB>::kSmemBytes);
+    auto kernel = fixed_product_tf32x3_kernel<NB, CK>;
+    using C = Cfg<NB, CK>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes);
     if (e != cudaSuccess) return e;
-    kernel<<<grid, kThreadsGemm, Cfg<NB>::kSmemBytes, s>>>(mx, mhi, mlo, out, ldo, n);
+    kernel<<<grid, kThreadsGemm, C::kSmemBytes, s>>>(mx, mhi, mlo, out, ldo, n);
     note_kernel_launch();
     return cudaGetLastError();
 }
@@ -345,11 +351,17 @@ cudaError_t launch_fixed_product_tf32x3(int nb, int side, const int8_t *signs_de
     note_kernel_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    static const int chunk = [] { const char *e = getenv("LCC_GEMM_CHUNK"); return e && atoi(e) == 32 ? 32 : 16; }();
+#define LCC_GEMM_CASE(NBV)                                                                                                   \
+    case NBV:                                                                                                                \
+        return chunk == 32 ? launch_t<NBV, 32>((const float *)x.data, x.ld, (float *)out.data, out.ld, x.n, w_hi, w_lo, s)   \
+                           : launch_t<NBV, 16>((const float *)x.data, x.ld, (float *)out.data, out.ld, x.n, w_hi, w_lo, s);
     switch (nb) {
-        case 64: return launch_t<64>((const float *)x.data, x.ld, (float *)out.data, out.ld, x.n, w_hi, w_lo, s);
-        case 128: return launch_t<128>((const float *)x.data, x.ld, (float *)out.data, out.ld, x.n, w_hi, w_lo, s);
-        case 256: return launch_t<256>((const float *)x.data, x.ld, (float *)out.data, out.ld, x.n, w_hi, w_lo, s);
+        LCC_GEMM_CASE(64)
+        LCC_GEMM_CASE(128)
+        LCC_GEMM_CASE(256)
     }
+#undef LCC_GEMM_CASE
     return cudaErrorNotSupported;
 }
 

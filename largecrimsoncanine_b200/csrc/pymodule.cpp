@@ -769,6 +769,259 @@ PYBIND11_MODULE(largecrimsoncanine, m) {
             return p.like(std::move(c));
         });
 
+    mv.def_static("pga_line_from_points", [](const Multivector &p1, const Multivector &p2) {  // src/pga.rs:204-216: join = dual(dual(p1) ^ dual(p2))
+          auto pga_dual = [](const Multivector &p) {
+              require_pga3d_element(p, "pga_dual");
+              std::vector<double> c(16, 0.0);
+              for (int i = 0; i < 16; ++i)
+                  if (p.coeffs[i] != 0.0) c[15 ^ i] += reverse_sign(popcount((unsigned)i)) * p.coeffs[i];
+              return p.like(std::move(c));
+          };
+          return pga_dual(pga_dual(p1).product(LCC_OP_OUTER, pga_dual(p2)));
+      })
+        .def_static("pga_line_from_planes", [](const Multivector &a, const Multivector &b) { return a.product(LCC_OP_OUTER, b); })  // :234-240
+        .def("pga_ideal_part", [](const Multivector &p) {  // :452-476: blades containing e0 (bit 3)
+            require_pga3d_element(p, "pga_ideal_part");
+            std::vector<double> c(16, 0.0);
+            for (int i = 0; i < 16; ++i) if (i & 8) c[i] = p.coeffs[i];
+            return p.like(std::move(c));
+        })
+        .def("pga_euclidean_part", [](const Multivector &p) {  // :489-512
+            require_pga3d_element(p, "pga_euclidean_part");
+            std::vector<double> c(16, 0.0);
+            for (int i = 0; i < 16; ++i) if (!(i & 8)) c[i] = p.coeffs[i];
+            return p.like(std::move(c));
+        })
+        .def("pga_point_plane_distance", [](const Multivector &p, const Multivector &plane) {  // :621-658
+            AlgebraPtr alg = p.get_algebra();
+            if (!alg->is_pga() || p.dims != 4) throw py::value_error("pga_point_plane_distance requires PGA3D elements");
+            const double w = p.coeffs[7];
+            if (std::fabs(w) < 1e-10) throw py::value_error("cannot compute distance from ideal point");
+            const double a = plane.coeffs[1], b = plane.coeffs[2], c = plane.coeffs[4], d = plane.coeffs[8];
+            const double len = std::sqrt(a * a + b * b + c * c);
+            if (len < 1e-10) throw py::value_error("plane has zero normal");
+            const double x = -p.coeffs[14] / w, y = p.coeffs[13] / w, z = -p.coeffs[11] / w;
+            return (a * x + b * y + c * z + d) / len;
+        })
+        .def("is_pga_motor", [](const Multivector &m, double tol) {  // :670-703: even and M*~M = 1
+            AlgebraPtr alg = m.get_algebra();
+            if (!alg->is_pga() || m.dims != 4) return false;
+            for (int i = 0; i < 16; ++i) if ((popcount((unsigned)i) & 1) && std::fabs(m.coeffs[i]) > tol) return false;
+            Multivector prod = m.product(LCC_OP_GP, m.reverse());
+            if (std::fabs(prod.coeffs[0] - 1.0) > tol) return false;
+            for (int i = 1; i < 16; ++i) if (std::fabs(prod.coeffs[i]) > tol) return false;
+            return true;
+        }, py::arg("tol") = 1e-10);
+
+    // ---- CGA (src/cga.rs): e+ = blade 2^n, e- = blade 2^(n+1) (:45-53)
+    auto require_cga = [](const PyAlgebra &a, const char *msg) { if (a.inner->q != 1 || a.inner->r != 0) throw py::value_error(msg); };
+    auto cga_algebra_of = [](const Multivector &m, const char *who) -> AlgebraPtr {
+        if (!m.algebra_opt) throw py::value_error(std::string(who) + " requires a CGA multivector with explicit algebra");
+        if (m.algebra_opt->q != 1 || m.algebra_opt->r != 0) throw py::value_error(std::string(who) + " requires a CGA multivector");
+        return m.algebra_opt;
+    };
+    auto squared_norm_inner = [](const Multivector &m) { return m.product(LCC_OP_GP, m.reverse()).coeffs[0]; };  // :650-654
+    mv.def_static("cga_eo", [require_cga](const PyAlgebra &a) {  // :79-104: (e- - e+)/2
+          require_cga(a, "cga_eo requires a CGA algebra (q=1, r=0); use Algebra.cga(n)");
+          const int n = a.inner->dim() - 2;
+          std::vector<double> c(a.inner->nb(), 0.0);
+          c[size_t(1) << n] = -0.5; c[size_t(1) << (n + 1)] = 0.5;
+          return mv_in(a, std::move(c));
+      })
+        .def_static("cga_einf", [require_cga](const PyAlgebra &a) {  // :122-147: e- + e+
+            require_cga(a, "cga_einf requires a CGA algebra (q=1, r=0); use Algebra.cga(n)");
+            const int n = a.inner->dim() - 2;
+            std::vector<double> c(a.inner->nb(), 0.0);
+            c[size_t(1) << n] = 1.0; c[size_t(1) << (n + 1)] = 1.0;
+            return mv_in(a, std::move(c));
+        })
+        .def_static("cga_point", [require_cga](const PyAlgebra &a, double x, double y, double z) {  // :171-212
+            require_cga(a, "cga_point requires a CGA algebra; use Algebra.cga(3)");
+            if (a.inner->dim() != 5) throw py::value_error("cga_point(x,y,z) requires CGA3D (dimension 5); use Algebra.cga(3)");
+            std::vector<double> c(32, 0.0);
+            c[1] = x; c[2] = y; c[4] = z;
+            const double nsq = x * x + y * y + z * z;
+            c[8] = 0.5 * nsq - 0.5; c[16] = 0.5 * nsq + 0.5;
+            return mv_in(a, std::move(c));
+        })
+        .def_static("cga_point_from_coords", [require_cga](const PyAlgebra &a, std::vector<double> coords) {  // :230-272
+            require_cga(a, "cga_point_from_coords requires a CGA algebra; use Algebra.cga(n)");
+            const int n = a.inner->dim() - 2;
+            if ((int)coords.size() != n) {
+                std::ostringstream s; s << "coords length " << coords.size() << " doesn't match Euclidean dimension " << n << "; for CGA" << n << " use " << n << " coordinates";
+                throw py::value_error(s.str());
+            }
+            std::vector<double> c(a.inner->nb(), 0.0);
+            double nsq = 0.0;
+            for (int i = 0; i < n; ++i) { c[size_t(1) << i] = coords[i]; nsq += coords[i] * coords[i]; }
+            c[size_t(1) << n] = 0.5 * nsq - 0.5; c[size_t(1) << (n + 1)] = 0.5 * nsq + 0.5;
+            return mv_in(a, std::move(c));
+        })
+        .def_static("cga_sphere", [require_cga](const PyAlgebra &a, double cx, double cy, double cz, double r) {  // :294-309
+            require_cga(a, "cga_point requires a CGA algebra; use Algebra.cga(3)");
+            if (a.inner->dim() != 5) throw py::value_error("cga_point(x,y,z) requires CGA3D (dimension 5); use Algebra.cga(3)");
+            std::vector<double> c(32, 0.0);
+            c[1] = cx; c[2] = cy; c[4] = cz;
+            const double nsq = cx * cx + cy * cy + cz * cz;
+            c[8] = 0.5 * nsq - 0.5; c[16] = 0.5 * nsq + 0.5;
+            const double half = 0.5 * r * r;
+            c[8] -= half; c[16] -= half;
+            return mv_in(a, std::move(c));
+        })
+        .def_static("cga_plane", [require_cga](const PyAlgebra &a, double pa, double pb, double pc, double pd) {  // :332-366: n + d*einf
+            require_cga(a, "cga_plane requires a CGA algebra; use Algebra.cga(3)");
+            if (a.inner->dim() != 5) throw py::value_error("cga_plane requires CGA3D (dimension 5); use Algebra.cga(3)");
+            std::vector<double> c(32, 0.0);
+            c[1] = pa; c[2] = pb; c[4] = pc; c[8] = pd; c[16] = pd;
+            return mv_in(a, std::move(c));
+        })
+        .def_static("cga_circle", [](const Multivector &s1, const Multivector &s2) { return s1.product(LCC_OP_OUTER, s2); })       // :387-389
+        .def_static("cga_point_pair", [](const Multivector &p1, const Multivector &p2) { return p1.product(LCC_OP_OUTER, p2); })  // :408-410
+        .def_static("cga_line", [](const Multivector &a, const Multivector &b) { return a.product(LCC_OP_OUTER, b); })            // :428-430
+        .def("cga_extract_center", [cga_algebra_of](const Multivector &m) {  // :451-511
+            AlgebraPtr alg = cga_algebra_of(m, "cga_extract_center");
+            if (alg->dim() != 5) throw py::value_error("cga_extract_center currently only supports CGA3D (dimension 5)");
+            const double w = m.coeffs[16] - m.coeffs[8];
+            if (std::fabs(w) < 1e-12) throw py::value_error("cannot extract center from a flat object (plane/line); use cga_is_flat() to check first");
+            return py::make_tuple(m.coeffs[1] / w, m.coeffs[2] / w, m.coeffs[4] / w);
+        })
+        .def("cga_extract_radius", [cga_algebra_of, squared_norm_inner](const Multivector &m) {  // :527-574
+            AlgebraPtr alg = cga_algebra_of(m, "cga_extract_radius");
+            if (alg->dim() != 5) throw py::value_error("cga_extract_radius currently only supports CGA3D (dimension 5)");
+            const double nsq = squared_norm_inner(m);
+            const double w = m.coeffs[16] - m.coeffs[8], w2 = w * w;
+            if (std::fabs(w2) < 1e-24) throw py::value_error("cannot extract radius from a flat object (plane/line)");
+            const double r2 = nsq / w2;
+            return r2 >= 0.0 ? std::sqrt(r2) : -std::sqrt(-r2);
+        })
+        .def("cga_is_round", [squared_norm_inner](const Multivector &m) { return squared_norm_inner(m) > 1e-10; })  // :591-594
+        .def("cga_is_flat", [cga_algebra_of, squared_norm_inner](const Multivector &m) {  // :611-648
+            AlgebraPtr alg = cga_algebra_of(m, "cga_is_flat");
+            const int n = alg->dim() - 2;
+            const double w = std::fabs(m.coeffs[size_t(1) << (n + 1)] - m.coeffs[size_t(1) << n]);
+            return w < 1e-10 || squared_norm_inner(m) < -1e-10;
+        })
+        .def("cga_point_on_sphere", [](const Multivector &p, const Multivector &sphere) {  // :674-680
+            Multivector in = p.product(LCC_OP_LC, sphere);
+            for (double c : in.coeffs) if (std::fabs(c) >= 1e-10) return false;
+            return true;
+        })
+        .def("cga_distance", [](const Multivector &p, const Multivector &q) {  // :701-720: sqrt(-2 (P . Q))
+            const double d2 = -2.0 * p.product(LCC_OP_LC, q).coeffs[0];
+            if (d2 < 0.0) {
+                if (d2 > -1e-10) return 0.0;
+                std::ostringstream s; s << "invalid distance calculation: d² = " << d2 << " (should be >= 0)";
+                throw py::value_error(s.str());
+            }
+            return std::sqrt(d2);
+        });
+
+    // ---- STA Cl(1,3,0) (src/sta.rs): gamma_mu = blade 1<<mu (:34-51)
+    auto require_sta = [](const AlgebraPtr &a) {
+        if (!(a->p == 1 && a->q == 3 && a->r == 0)) {
+            std::ostringstream s; s << "STA methods require Cl(1,3,0) algebra, got Cl(" << a->p << "," << a->q << "," << a->r << ")";
+            throw py::value_error(s.str());
+        }
+    };
+    mv.def_static("sta_vector", [require_sta](const PyAlgebra &a, double t, double x, double y, double z) {  // :102-114
+          require_sta(a.inner);
+          std::vector<double> c(16, 0.0);
+          c[1] = t; c[2] = x; c[4] = y; c[8] = z;
+          return mv_in(a, std::move(c));
+      })
+        .def_static("sta_gamma", [require_sta](const PyAlgebra &a, long i) {  // :139-156
+            require_sta(a.inner);
+            if (i < 0) throw py::type_error("gamma index must be a non-negative integer");
+            if (i > 3) { std::ostringstream s; s << "gamma index must be 0-3, got " << i; throw py::value_error(s.str()); }
+            std::vector<double> c(16, 0.0);
+            c[size_t(1) << i] = 1.0;
+            return mv_in(a, std::move(c));
+        })
+        .def_static("sta_bivector", [require_sta](const PyAlgebra &a, std::vector<double> e, std::vector<double> b) {  // :183-216
+            require_sta(a.inner);
+            if (e.size() != 3) { std::ostringstream s; s << "E field must have 3 components, got " << e.size(); throw py::value_error(s.str()); }
+            if (b.size() != 3) { std::ostringstream s; s << "B field must have 3 components, got " << b.size(); throw py::value_error(s.str()); }
+            std::vector<double> c(16, 0.0);
+            c[3] = e[0]; c[5] = e[1]; c[9] = e[2];
+            c[12] = b[0]; c[10] = -b[1]; c[6] = b[2];
+            return mv_in(a, std::move(c));
+        })
+        .def_static("sta_boost", [require_sta](const PyAlgebra &a, std::vector<double> v) {  // :243-300
+            require_sta(a.inner);
+            if (v.size() != 3) { std::ostringstream s; s << "velocity must have 3 components, got " << v.size(); throw py::value_error(s.str()); }
+            const double mag = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+            std::vector<double> c(16, 0.0);
+            if (mag < 1e-14) { c[0] = 1.0; return mv_in(a, std::move(c)); }
+            if (mag >= 1.0) { std::ostringstream s; s << "velocity magnitude " << mag << " >= c (speed of light = 1 in natural units)"; throw py::value_error(s.str()); }
+            const double phi = std::atanh(mag), nx = v[0] / mag, ny = v[1] / mag, nz = v[2] / mag;
+            const double ch = std::cosh(phi / 2.0), sh = std::sinh(phi / 2.0);
+            c[0] = ch; c[3] = -sh * nx; c[5] = -sh * ny; c[9] = -sh * nz;
+            return mv_in(a, std::move(c));
+        })
+        .def_static("sta_rotation", [require_sta](const PyAlgebra &a, std::vector<double> axis, double angle) {  // :329-373
+            require_sta(a.inner);
+            if (axis.size() != 3) { std::ostringstream s; s << "axis must have 3 components, got " << axis.size(); throw py::value_error(s.str()); }
+            const double mag = std::sqrt(axis[0] * axis[0] + axis[1] * axis[1] + axis[2] * axis[2]);
+            if (mag < 1e-14) throw py::value_error("axis has zero magnitude");
+            const double nx = axis[0] / mag, ny = axis[1] / mag, nz = axis[2] / mag;
+            const double ch = std::cos(angle / 2.0), sh = std::sin(angle / 2.0);
+            std::vector<double> c(16, 0.0);
+            c[0] = ch; c[12] = sh * nx; c[10] = -sh * ny; c[6] = sh * nz;
+            return mv_in(a, std::move(c));
+        })
+        .def_static("sta_I", [require_sta](const PyAlgebra &a) {  // :393-404
+            require_sta(a.inner);
+            std::vector<double> c(16, 0.0);
+            c[15] = 1.0;
+            return mv_in(a, std::move(c));
+        })
+        .def("sta_spacetime_split", [require_sta](const Multivector &m) {  // :428-437
+            require_sta(m.get_algebra());
+            return py::make_tuple(m.coeffs[1], std::vector<double>{m.coeffs[2], m.coeffs[4], m.coeffs[8]});
+        })
+        .def("sta_interval_squared", [require_sta](const Multivector &m) {  // :500-510
+            require_sta(m.get_algebra());
+            const double t = m.coeffs[1], x = m.coeffs[2], y = m.coeffs[4], z = m.coeffs[8];
+            return t * t - x * x - y * y - z * z;
+        })
+        .def("sta_proper_time", [require_sta](const Multivector &m) {  // :458-474
+            require_sta(m.get_algebra());
+            const double t = m.coeffs[1], x = m.coeffs[2], y = m.coeffs[4], z = m.coeffs[8];
+            const double i2 = t * t - x * x - y * y - z * z;
+            return i2 >= 0.0 ? std::sqrt(i2) : -std::sqrt(-i2);
+        })
+        .def("sta_is_timelike", [require_sta](const Multivector &m, py::object tol) {  // :523-528
+            require_sta(m.get_algebra());
+            const double t = m.coeffs[1], x = m.coeffs[2], y = m.coeffs[4], z = m.coeffs[8];
+            return (t * t - x * x - y * y - z * z) > (tol.is_none() ? 1e-10 : tol.cast<double>());
+        }, py::arg("tol") = py::none())
+        .def("sta_is_spacelike", [require_sta](const Multivector &m, py::object tol) {  // :541-546
+            require_sta(m.get_algebra());
+            const double t = m.coeffs[1], x = m.coeffs[2], y = m.coeffs[4], z = m.coeffs[8];
+            return (t * t - x * x - y * y - z * z) < -(tol.is_none() ? 1e-10 : tol.cast<double>());
+        }, py::arg("tol") = py::none())
+        .def("sta_is_lightlike", [require_sta](const Multivector &m, py::object tol) {  // :563-568
+            require_sta(m.get_algebra());
+            const double t = m.coeffs[1], x = m.coeffs[2], y = m.coeffs[4], z = m.coeffs[8];
+            return std::fabs(t * t - x * x - y * y - z * z) <= (tol.is_none() ? 1e-10 : tol.cast<double>());
+        }, py::arg("tol") = py::none())
+        .def("sta_field_decompose", [require_sta](const Multivector &m) {  // :584-596
+            require_sta(m.get_algebra());
+            return py::make_tuple(std::vector<double>{m.coeffs[3], m.coeffs[5], m.coeffs[9]},
+                                  std::vector<double>{m.coeffs[12], -m.coeffs[10], m.coeffs[6]});
+        })
+        .def("sta_em_dual", [require_sta](const Multivector &m) {  // :613-623: I * F
+            AlgebraPtr alg = m.get_algebra();
+            require_sta(alg);
+            std::vector<double> c(16, 0.0);
+            c[15] = 1.0;
+            return Multivector{std::move(c), 4, alg}.product(LCC_OP_GP, m);
+        })
+        .def("sta_lorentz_gamma", [require_sta](const Multivector &m) {  // :641-647
+            require_sta(m.get_algebra());
+            return 2.0 * m.coeffs[0] * m.coeffs[0] - 1.0;
+        });
+
     // ------------------------------------------------------------------ MultivectorBatch (src/batch.rs)
     py::class_<Batch, BatchPtr>(m, "MultivectorBatch")
         .def_static("from_numpy", &batch_from_numpy, py::arg("algebra"), py::arg("coeffs"))

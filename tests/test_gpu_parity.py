@@ -372,3 +372,27 @@ def test_sharded_batch_single_rank(L):
     assert np.all(np.abs(prod.sum() - want) <= 1e-12 * mag)
     assert np.all(np.abs(prod.mean() - want / 5001) <= 1e-12 * mag / 5001)
     assert len(prod) == 5001 and prod.info.rows == 5001
+
+
+@pytest.mark.parametrize("sig", [(6, 0, 0), (4, 2, 1), (8, 0, 0)])
+def test_fixed_operand_product_on_tensor_cores(L, sig):
+    """K6: one-row operand x batch in a 64..256-blade algebra, f32, FMA mode -> tcgen05 GEMM with the
+    3xTF32 split (BASELINE config 5 shape at small N).  Must stay within the f32 bar of 1e-5 against
+    the f64 reference arithmetic; strict mode takes the exact table-driven kernel instead."""
+    alg, o = algebras(L, sig)
+    nb = o.num_blades
+    rng = np.random.default_rng(31)
+    for n in (1, 127, 128, 129, 5000):
+        m = rng.standard_normal((1, nb)).astype(np.float32)
+        x = rng.standard_normal((n, nb)).astype(np.float32)
+        M, X = L.MultivectorBatch.from_numpy(alg, m), L.MultivectorBatch.from_numpy(alg, x)
+        for got, a, b in ((M.geometric_product(X).to_numpy(), m, x), (X.geometric_product(M).to_numpy(), x, m)):
+            ref = o.geometric_product(a.astype(np.float64), b.astype(np.float64))
+            bound = o.product_abs_bound("gp", np.abs(a.astype(np.float64)), np.abs(b.astype(np.float64)))
+            assert np.all(np.abs(got - ref) <= 1e-5 * np.maximum(np.abs(ref), bound))
+            assert np.all(np.abs(got - ref).max(axis=1) <= 1e-5 * np.abs(ref).max(axis=1))
+    L.set_strict_fp(True)
+    try:
+        assert np.array_equal(M.geometric_product(X).to_numpy(), o.geometric_product(m, x))
+    finally:
+        L.set_strict_fp(False)
