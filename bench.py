@@ -43,6 +43,8 @@ WORKLOADS = {
     # grade(1) reads 4 blade rows and writes 16 (160 B), lc reads 2x16 and writes 16 (384 B), sum reads 16 (128 B)
     "sta_grade_inner_sum": ((1, 3, 0), "f64", 27, 160 + 384 + 128, "multivectors/s"),
 }
+# BASELINE config 4 fused: <x>_1 . w summed over the batch in ONE kernel: 4 + 16 blade rows read per multivector
+WORKLOADS["sta_fused_grade_inner_sum"] = ((1, 3, 0), "f64", 27, (4 + 16) * 8, "multivectors/s")
 # BASELINE config 5: fixed operand x batch in Cl(8,0,0) on the tensor cores (tf32 x3): bound = tensor
 WORKLOADS["cl8_fixed_gp"] = ((8, 0, 0), "f32", 24, 2048, "products/s")
 TENSOR_FLOPS_PER_UNIT = {"cl8_fixed_gp": 3 * 2 * 256 * 256}  # three tf32 MMAs per term
@@ -152,7 +154,7 @@ def cpu_rate(workload, sample_rows, threads, repeats=1):
             fn = lambda: o.geometric_product(a[:1], b, threads=threads)  # noqa: E731
         elif workload == "cga_gp_outer":
             fn = lambda: (o.geometric_product(a, b, threads=threads), o.outer_product(a, b, threads=threads))  # noqa: E731
-        elif workload == "sta_grade_inner_sum":
+        elif workload in ("sta_grade_inner_sum", "sta_fused_grade_inner_sum"):
             fn = lambda: o.sum(o.left_contraction(o.grade(a, 1), b, threads=threads))  # noqa: E731
         else:
             fn = lambda: o.geometric_product(a, b, threads=threads)  # noqa: E731
@@ -167,6 +169,7 @@ def cpu_rate(workload, sample_rows, threads, repeats=1):
 
 def cpu_sample_rows(workload):
     return {"pga_sandwich": 1 << 25, "cga_gp": 1 << 22, "cga_gp_outer": 1 << 22, "r3_gp": 1 << 20, "sta_grade_inner_sum": 1 << 23,
+            "sta_fused_grade_inner_sum": 1 << 23,
             "cl8_fixed_gp": 1 << 14}[workload]
 
 
@@ -211,6 +214,7 @@ def workload_name(wl):
         "cga_gp_outer": "CGA Cl(4,1,0) fused geometric + outer product", "r3_gp": "Cl(3,0,0) batched geometric product",
         "sta_grade_inner_sum": "STA Cl(1,3,0) grade projection + inner product + batch sum",
         "cl8_fixed_gp": "Cl(8,0,0) fixed-operand left geometric product (tcgen05, 3xTF32)",
+        "sta_fused_grade_inner_sum": "STA Cl(1,3,0) fused grade projection + inner product + batch sum (one kernel)",
     }[wl]
     return f"{desc}, 2^{log2n} rows per GPU, {dt}, {1 << sum(sig)} blades"
 
@@ -284,6 +288,17 @@ def run_gpu_arm(args):
         else:
             def step():
                 cabi.check(lib.lcc_batch_product(alg.h, cabi.LCC_OP_GP, C.byref(va), C.byref(vb), C.byref(vo), flags, sptr))
+    elif wl == "sta_fused_grade_inner_sum":
+        a = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
+        b = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
+        sums = torch.zeros(nb, device=dev, dtype=tdt)
+        out = None
+        va, vb = soa(a), soa(b)
+
+        def step():
+            cabi.check(lib.lcc_batch_product_sum(alg.h, cabi.LCC_OP_LC, C.byref(va), 1, C.byref(vb), C.c_void_p(sums.data_ptr()), flags, sptr))
+            if world > 1:
+                dist.all_reduce(sums)
     elif wl == "cl8_fixed_gp":
         b = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
         a = torch.randn((nb, 4), device=dev, dtype=tdt, generator=gen)  # the fixed operand: one-row SoA view, ld = 4
@@ -347,6 +362,18 @@ def run_gpu_arm(args):
             xs = x[:, idx].T.contiguous().cpu().numpy()
             got = out[:, idx].T.contiguous().cpu().numpy()
             want = o.sandwich(motor, xs)
+        elif wl == "sta_fused_grade_inner_sum":
+            m = 1 << 20  # the fused kernel only returns the sums: re-run it on the first 2^20 rows and compare with the oracle
+            sa, sb = cabi.view(a.data_ptr(), m, a.stride(0), code, cabi.LCC_SOA), cabi.view(b.data_ptr(), m, b.stride(0), code, cabi.LCC_SOA)
+            chk = torch.zeros(nb, device=dev, dtype=tdt)
+            cabi.check(lib.lcc_batch_product_sum(alg.h, cabi.LCC_OP_LC, C.byref(sa), 1, C.byref(sb), C.c_void_p(chk.data_ptr()), flags, sptr))
+            torch.cuda.synchronize()
+            xs, ys = a[:, :m].T.contiguous().cpu().numpy(), b[:, :m].T.contiguous().cpu().numpy()
+            prod = o.left_contraction(o.grade(xs, 1), ys)
+            want, mag = o.sum(prod)
+            got = chk.cpu().numpy()
+            want = want / np.maximum(mag, 1e-300) * np.abs(mag).max()  # compare on the scale of the summed magnitudes
+            got = got / np.maximum(mag, 1e-300) * np.abs(mag).max()
         elif wl == "sta_grade_inner_sum":
             xs, ys = a[:, idx].T.contiguous().cpu().numpy(), b[:, idx].T.contiguous().cpu().numpy()
             got = out[:, idx].T.contiguous().cpu().numpy()

@@ -169,6 +169,12 @@ LCC_API lcc_status lcc_batch_product(const lcc_algebra *alg, int op, const lcc_v
 /* Fused dual-output: gp_out = a*b and outer_out = a^b reading a and b once (BASELINE config 3). */
 LCC_API lcc_status lcc_batch_gp_outer(const lcc_algebra *alg, const lcc_view *a, const lcc_view *b,
                                       const lcc_view *gp_out, const lcc_view *outer_out, unsigned flags, void *stream);
+/* Fused pipeline  sums[k] = sum over rows of ( <a>_g (op) b )[k]  -- grade projection of the left operand
+ * (a_grade < 0: none; batch.rs:1027-1052), product (batch.rs:353-655) and batch sum in ONE pass that reads
+ * only the needed blade rows and writes num_blades values (BASELINE config 4; the per-GPU partial that
+ * precedes the NCCL all-reduce).  sums_dev: num_blades elements of the operands' dtype on the device. */
+LCC_API lcc_status lcc_batch_product_sum(const lcc_algebra *alg, int op, const lcc_view *a, int a_grade, const lcc_view *b,
+                                         void *sums_dev, unsigned flags, void *stream);
 /* Vector-Jacobian products of the three bilinear products (autograd of lcc.torch; new surface):
  *   wrt = 0  grad_in[i] = sum_j sign[i][j] * grad_out[i^j] * other[j]   (other = the right operand b)
  *   wrt = 1  grad_in[j] = sum_i sign[i][j] * other[i] * grad_out[i^j]   (other = the left operand a)

@@ -89,6 +89,7 @@ def lib():
         "lcc_batch_copy_rows": (i32, [vp, V, i64, i64, V, i64, vp]),
         "lcc_batch_product": (i32, [vp, i32, V, V, V, u32, vp]),
         "lcc_batch_gp_outer": (i32, [vp, V, V, V, V, u32, vp]),
+        "lcc_batch_product_sum": (i32, [vp, i32, V, i32, V, vp, u32, vp]),
         "lcc_batch_product_vjp": (i32, [vp, i32, i32, V, V, V, u32, vp]),
         "lcc_batch_sandwich": (i32, [vp, C.POINTER(dbl), V, V, u32, vp]),
         "lcc_batch_sandwich_rows": (i32, [vp, V, V, V, u32, vp]),

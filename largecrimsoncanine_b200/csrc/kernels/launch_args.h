@@ -22,8 +22,16 @@ struct ProductArgs {
     void *out = nullptr; int64_t ldo = 0;
     void *out2 = nullptr; int64_t ldo2 = 0;  // outer-product output of the fused form
     const double *mu = nullptr;              // run-time metric factors mu[i & j] (generic kernels only)
+    // fused reduction epilogue (K5 as the epilogue of K1): when sum_partial is set nothing is stored; each block
+    // writes its column sums to sum_partial[blade * sum_blocks + block] (f64).  a_grade >= 0 additionally applies
+    // the grade projection <a>_k to the left operand on load (masked blade rows are never read).
+    double *sum_partial = nullptr;
+    int sum_blocks = 0;
+    int a_grade = -1;
     cudaStream_t stream = nullptr;
 };
+
+constexpr int kFusedSumBlocks = 148 * 4;  // fixed grid of the fused reduction: results do not depend on n or timing
 
 struct SandwichArgs {
     int dtype = kF64;

@@ -426,6 +426,11 @@ cudaError_t launch_sum(int nb, const ViewArg &x, void *sums_dev, void *scratch_d
     return by_dtype(x.dtype, [&] { run(float()); }, [&] { run(double()); });
 }
 
+cudaError_t launch_sum_final(int nb, int nblocks, const double *partial, void *sums_dev, int dtype, cudaStream_t s) {
+    return by_dtype(dtype, [&] { sum_final<float><<<nb, kThreads, 0, s>>>(partial, nblocks, (float *)sums_dev); },
+                    [&] { sum_final<double><<<nb, kThreads, 0, s>>>(partial, nblocks, (double *)sums_dev); });
+}
+
 cudaError_t launch_convert(int nb, const ViewArg &src, const ViewArg &dst, cudaStream_t s) {
     const int64_t n = src.n;
     if (n <= 0) return cudaSuccess;

@@ -26,6 +26,8 @@ cudaError_t launch_norm(int nb, int mode, bool strict, const ViewArg &x, const i
 cudaError_t launch_sum(int nb, const ViewArg &x, void *sums_dev, void *scratch_dev, int64_t scratch_elems,
                        cudaStream_t s);
 int64_t sum_scratch_elems(int nb, int64_t n);
+// second pass of every batch sum: sums[k] = sum over blocks of partial[k*nblocks + block] (fixed order)
+cudaError_t launch_sum_final(int nb, int nblocks, const double *partial, void *sums_dev, int dtype, cudaStream_t s);
 cudaError_t launch_convert(int nb, const ViewArg &src, const ViewArg &dst, cudaStream_t s);
 cudaError_t launch_scatter_columns(int nb, const void *cols, int ncols, const int32_t *blade_of_col,
                                    const ViewArg &dst, cudaStream_t s);

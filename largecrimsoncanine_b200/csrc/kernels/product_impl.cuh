@@ -117,6 +117,79 @@ product_kernel(const real *__restrict__ a, int64_t lda, int a_bcast, const real 
 #undef LCC_OUT_END
 }
 
+// ------------------------------------------------------------------------------------------ K1 + K5
+// sums[k] = sum over rows of (<a>_g (op) b)[k] without ever writing the product: the grade projection is a
+// load-time mask (masked blade rows of `a` are not read at all), the product terms run in the reference order,
+// and every thread adds its rows' results into its own f64 column of a shared-memory tile; one partial per
+// blade and block goes to global memory and sum_final (misc_kernels.cu) finishes the fixed tree.
+// Traffic for STA <x>_1 . w: 4 + 16 blade rows read per multivector (160 B in f64) instead of the 672 B of
+// the three separate kernels.
+__host__ __device__ constexpr int blade_grade_of(int blade) {
+    int c = 0;
+    for (int b = blade; b; b >>= 1) c += b & 1;
+    return c;
+}
+
+template <int LAYOUT, int OP, bool STRICT>
+__global__ void __launch_bounds__(kThreads)
+product_sum_kernel(const real *__restrict__ a, int64_t lda, int a_bcast, int a_grade, const real *__restrict__ b, int64_t ldb,
+                   int b_bcast, int64_t n, int vec_ok, const Coeffs mu, double *__restrict__ partial) {
+    constexpr int V = LAYOUT == kSoA ? kRowsSoA : 1;
+    extern __shared__ double ssum[];  // [NB][blockDim.x]
+    const int bd = blockDim.x, tid = threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) ssum[k * bd + tid] = 0.0;
+    (void)mu;
+    for (int64_t r0 = ((int64_t)blockIdx.x * bd + tid) * V; r0 < n; r0 += (int64_t)gridDim.x * bd * V) {
+        Tile<real, NB, V> A, B;
+        if constexpr (LAYOUT == kSoA) {
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+                if (a_grade >= 0 && blade_grade_of(k) != a_grade) {  // warp-uniform: this blade row is never read
+#pragma unroll
+                    for (int l = 0; l < V; ++l) A.v[k][l] = real(0);
+                } else if (a_bcast) {
+                    const real sv = __ldg(a + (int64_t)k * lda);
+#pragma unroll
+                    for (int l = 0; l < V; ++l) A.v[k][l] = sv;
+                } else {
+                    ldg_stream(a + (int64_t)k * lda + r0, A.v[k]);
+                }
+            }
+            load_soa(B, b, ldb, r0, b_bcast != 0);
+        } else {
+            load_aos(A, a, lda, r0, a_bcast != 0, vec_ok != 0);
+            load_aos(B, b, ldb, r0, b_bcast != 0, vec_ok != 0);
+            if (a_grade >= 0) {
+#pragma unroll
+                for (int k = 0; k < NB; ++k)
+                    if (blade_grade_of(k) != a_grade) A.v[k][0] = real(0);
+            }
+        }
+#define LCC_OUT_BEGIN(k) { real acc[V]; _Pragma("unroll") for (int l = 0; l < V; ++l) acc[l] = real(0);
+#define LCC_TERM(k, i, j, neg, flags)                                                                   \
+    if constexpr (term_in_op(OP, flags)) {                                                             \
+        _Pragma("unroll") for (int l = 0; l < V; ++l) {                                                \
+            real av = (neg) ? -A.v[i][l] : A.v[i][l];                                                  \
+            if constexpr (kRuntimeMetric) av = mul_rn(av, mu.v[(i) & (j)]);                            \
+            acc[l] = Arith<STRICT>::madd(av, B.v[j][l], acc[l]);                                       \
+        }                                                                                              \
+    }
+#define LCC_OUT_END(k) { double rowsum = 0.0; _Pragma("unroll") for (int l = 0; l < V; ++l) if (r0 + l < n) rowsum += (double)acc[l]; \
+                         ssum[(k) * bd + tid] += rowsum; } }
+#include LCC_TERMS_FILE
+#undef LCC_OUT_BEGIN
+#undef LCC_TERM
+#undef LCC_OUT_END
+    }
+    __syncthreads();
+    if (tid < NB) {  // fixed order over the block's threads
+        double total = 0.0;
+        for (int t = 0; t < bd; ++t) total += ssum[tid * bd + t];
+        partial[(int64_t)tid * gridDim.x + blockIdx.x] = total;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ K2
 // out = R * x * ~R, two stages, the intermediate R*x rounded to storage precision exactly as the
 // reference's `rx` vector (batch.rs:462-478).  EVEN prunes the odd-grade blades of R at compile
@@ -190,7 +263,24 @@ template <int LAYOUT> static inline unsigned grid_for(int64_t n) {
     return (unsigned)((threads + block - 1) / block);
 }
 
+template <int LAYOUT, int OP, bool STRICT> static cudaError_t launch_product_sum_t(const ProductArgs &g) {
+    constexpr int W = 16 / (int)sizeof(real);
+    int vec_ok = 1;
+    if (LAYOUT == kAoS) vec_ok = ((uintptr_t)g.a % 16 == 0) && (g.lda % W == 0) && ((uintptr_t)g.b % 16 == 0) && (g.ldb % W == 0);
+    const int bd = block_threads() < NB ? NB : block_threads();
+    const size_t smem = (size_t)NB * bd * sizeof(double);
+    auto kernel = product_sum_kernel<LAYOUT, OP, STRICT>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kernel<<<g.sum_blocks, bd, smem, g.stream>>>((const real *)g.a, g.lda, g.a_bcast, g.a_grade, (const real *)g.b, g.ldb,
+                                               g.b_bcast, g.n, vec_ok, to_coeffs(g.mu, 1.0), g.sum_partial);
+    note_kernel_launch();
+    return cudaGetLastError();
+}
+
 template <int LAYOUT, int OP, bool STRICT> static cudaError_t launch_product_t(const ProductArgs &g) {
+    if constexpr (OP != kOpGPOuter) {
+        if (g.sum_partial) return launch_product_sum_t<LAYOUT, OP, STRICT>(g);
+    }
     if (g.n <= 0) return cudaSuccess;
     constexpr int W = 16 / (int)sizeof(real);
     int vec_ok = 1;

@@ -507,6 +507,50 @@ lcc_status lcc_batch_gp_outer(const lcc_algebra *alg, const lcc_view *a, const l
     return run_product(alg, kOpGPOuter, a, b, gp_out, outer_out, flags, stream);
 }
 
+lcc_status lcc_batch_product_sum(const lcc_algebra *alg, int op, const lcc_view *a, int a_grade, const lcc_view *b, void *sums_dev,
+                                 unsigned flags, void *stream) {
+    if (op != LCC_OP_GP && op != LCC_OP_OUTER && op != LCC_OP_LC) return fail(LCC_ERR_VALUE, "unknown product op %d", op);
+    LCC_TRY(check_view(alg, a, "a"));
+    LCC_TRY(check_view(alg, b, "b"));
+    LCC_TRY(same_kind(a, b, "product_sum"));
+    if (!sums_dev) return fail(LCC_ERR_VALUE, "sums_dev is NULL");
+    if (a_grade > alg->dim) return fail(LCC_ERR_VALUE, "grade %d exceeds dimension %d of algebra", a_grade, alg->dim);  // batch.rs:1029-1033
+    int64_t n = 0;
+    LCC_TRY(broadcast_rows(a->n, b->n, &n));
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    const bool strict = (flags & LCC_FLAG_STRICT_FP) != 0;
+    const bool a_bc = a->n == 1 && n > 1, b_bc = b->n == 1 && n > 1;
+    if (alg->nb <= 32 && alg->product[a->dtype]) {
+        PoolBuffer partial;
+        LCC_TRY(partial.alloc((size_t)alg->nb * kFusedSumBlocks * sizeof(double), s));
+        ProductArgs g;
+        g.op = op; g.dtype = a->dtype; g.layout = a->layout; g.strict = strict; g.n = n;
+        g.a = a->data; g.lda = a->ld; g.a_bcast = a_bc;
+        g.b = b->data; g.ldb = b->ld; g.b_bcast = b_bc;
+        g.mu = alg->specialised ? nullptr : alg->mu.data();
+        g.sum_partial = (double *)partial.ptr; g.sum_blocks = kFusedSumBlocks; g.a_grade = a_grade < 0 ? -1 : a_grade;
+        g.stream = s;
+        LCC_CUDA(alg->product[a->dtype](g));
+        LCC_CUDA(launch_sum_final(alg->nb, kFusedSumBlocks, (const double *)partial.ptr, sums_dev, a->dtype, s));
+        return LCC_OK;
+    }
+    // large algebras: unfused composition through pool temporaries (grade -> product -> sum)
+    PoolBuffer bg, bp;
+    const size_t es = elem_size(a->dtype);
+    lcc_view ga = *a, prod = (a->n >= b->n) ? *a : *b;
+    prod.n = n;
+    if (a_grade >= 0) {
+        LCC_TRY(bg.alloc((size_t)(a->layout == LCC_SOA ? alg->nb * a->ld : a->n * a->ld) * es, s));
+        ga.data = bg.ptr;
+        LCC_TRY(lcc_batch_unary(alg, LCC_UN_GRADE, a_grade, a, &ga, (void *)s));
+    }
+    LCC_TRY(bp.alloc((size_t)(prod.layout == LCC_SOA ? alg->nb * prod.ld : prod.n * prod.ld) * es, s));
+    prod.data = bp.ptr;
+    LCC_TRY(run_product(alg, op, &ga, b, &prod, nullptr, flags, (void *)s));
+    return lcc_batch_sum(alg, &prod, sums_dev, (void *)s);
+}
+
 lcc_status lcc_batch_product_vjp(const lcc_algebra *alg, int op, int wrt, const lcc_view *grad_out, const lcc_view *other,
                                  const lcc_view *grad_in, unsigned flags, void *stream) {
     if (op != LCC_OP_GP && op != LCC_OP_OUTER && op != LCC_OP_LC) return fail(LCC_ERR_VALUE, "unknown product op %d", op);

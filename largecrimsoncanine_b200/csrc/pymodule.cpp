@@ -1118,6 +1118,28 @@ PYBIND11_MODULE(largecrimsoncanine, m) {
             check(lcc_batch_gp_outer(a.algebra->h, &a.view, &b.view, &g->view, &w->view, fp_flags(), nullptr));
             return std::make_pair(g, w);
         })
+        .def("product_sum", [](const Batch &a, const Batch &b, const std::string &op, py::object grade) {
+            // sums over the batch of <a>_grade (op) b in one fused pass (lcc_batch_product_sum)
+            require_same_algebra(a, b);
+            const int64_t n = broadcast_n(a, b);
+            (void)n;
+            int opc;
+            if (op == "gp" || op == "geometric_product") opc = LCC_OP_GP;
+            else if (op == "outer" || op == "wedge" || op == "outer_product") opc = LCC_OP_OUTER;
+            else if (op == "lc" || op == "inner" || op == "left_contraction") opc = LCC_OP_LC;
+            else throw py::value_error("op must be one of 'gp', 'outer', 'lc'");
+            const int g = grade.is_none() ? -1 : grade.cast<int>();
+            if (g < -1) throw py::value_error("grade must be non-negative");
+            const int nb = a.nb();
+            py::array out(np_dtype(a.view.dtype), std::vector<py::ssize_t>{(py::ssize_t)nb});
+            void *out_ptr = out.mutable_data();
+            py::gil_scoped_release nogil;
+            DeviceTemp stage((size_t)nb * a.es());
+            check(lcc_batch_product_sum(a.algebra->h, opc, &a.view, g, &b.view, stage.ptr, fp_flags(), nullptr));
+            check(lcc_memcpy_d2h(out_ptr, stage.ptr, (size_t)nb * a.es(), nullptr));
+            check(lcc_stream_sync(nullptr));
+            return out;
+        }, py::arg("other"), py::arg("op") = "gp", py::arg("grade") = py::none())
         .def("sum", [](const Batch &a) { return batch_sum(a, false); })
         .def("mean", [](const Batch &a) { return batch_sum(a, true); })
         .def("algebra", [](const Batch &b) { return PyAlgebra{b.algebra}; })

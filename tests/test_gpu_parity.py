@@ -396,3 +396,29 @@ def test_fixed_operand_product_on_tensor_cores(L, sig):
         assert np.array_equal(M.geometric_product(X).to_numpy(), o.geometric_product(m, x))
     finally:
         L.set_strict_fp(False)
+
+
+@pytest.mark.parametrize("sig", [(1, 3, 0), (3, 0, 1), (4, 1, 0), (2, 1, 1)])
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_fused_grade_product_sum(L, sig, dt):
+    """lcc_batch_product_sum: sum_rows(<a>_g (op) b) in one pass equals the three separate operations
+    (batch.rs:1027-1052 + 353-655 + column sums) within summation tolerance; BASELINE config 4 pipeline."""
+    alg, o = algebras(L, sig)
+    rng = np.random.default_rng(41)
+    for n in (1, 257, 50_001):
+        a, b = rand(rng, n, o.num_blades, dt), rand(rng, n, o.num_blades, dt)
+        A, B = L.MultivectorBatch.from_numpy(alg, a), L.MultivectorBatch.from_numpy(alg, b)
+        tol = 1e-12 if dt == np.float64 else 2e-5
+        for op, ref_fn in (("lc", o.left_contraction), ("gp", o.geometric_product), ("outer", o.outer_product)):
+            for g in (None, 1, 2):
+                ag = a if g is None else o.grade(a, g)
+                want, _ = o.sum(ref_fn(ag, b))
+                _, mag = o.sum(o.product_abs_bound(op, np.abs(ag), np.abs(b)))
+                got = A.product_sum(B, op=op, grade=g).astype(np.float64)
+                assert np.all(np.abs(got - want) <= tol * np.maximum(mag, 1e-300)), (op, g, n)
+        one = L.MultivectorBatch.from_numpy(alg, b[:1])
+        want, _ = o.sum(o.left_contraction(o.grade(a, 1), b[:1]))
+        _, mag = o.sum(o.product_abs_bound("lc", np.abs(o.grade(a, 1)), np.abs(b[:1])))
+        assert np.all(np.abs(A.product_sum(one, op="lc", grade=1).astype(np.float64) - want) <= tol * np.maximum(mag, 1e-300))
+    with pytest.raises(ValueError, match="exceeds dimension"):
+        A.product_sum(B, op="lc", grade=o.dimension + 1)
