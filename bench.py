@@ -449,10 +449,25 @@ def roofline_block(wl, n, kernel_ms, bytes_per, peaks, peak_kind, traffic):
             "frac_of_nominal_8TBs": hbm / 8000.0}
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this process to the CPUs NVML reports as local to its GPU, so the pinned host buffers are
+    first-touched on the NUMA node the GPU's PCIe root hangs off (matters when 8 ranks share one host)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        return True
+    except Exception:
+        return False
+
+
 def measure_e2e(args, lib, alg, code, motor, n, nb, world, rank, dev, dist, flags):
     """lcc_host_sandwich on pinned host buffers in the reference's (N, 16) row-major layout."""
     import psutil
     import torch
+
+    numa_bound = bind_to_gpu_numa_node(dev.index or 0) if world > 1 else False
 
     from largecrimsoncanine_b200 import cabi
 
@@ -500,7 +515,8 @@ def measure_e2e(args, lib, alg, code, motor, n, nb, world, rank, dev, dist, flag
     return {"value": world * n_e2e * steps / dt_s, "unit": "points/s", "h2d_bytes_per_step": n_e2e * nb * es,
             "d2h_bytes_per_step": n_e2e * nb * es, "points_per_gpu": n_e2e, "steps": steps,
             "api": "lcc_host_sandwich (C ABI, pinned host buffers, chunked H2D/kernel/D2H pipeline)",
-            "timer": "host wall clock around the blocking call, max over ranks", "checked_against_oracle": ok}
+            "timer": "host wall clock around the blocking call, max over ranks", "checked_against_oracle": ok,
+            "numa_bound": numa_bound}
 
 
 def main():
