@@ -257,8 +257,21 @@ def run_gpu_arm(args):
     gen = torch.Generator(device=dev)
     gen.manual_seed(42 + rank)
 
+    aos_layout = args.layout == "aos"
+    if aos_layout and wl not in ("pga_sandwich", "cga_gp", "r3_gp", "cga_gp_outer"):
+        raise SystemExit("--layout aos is available for pga_sandwich, cga_gp, cga_gp_outer and r3_gp")
+
     def soa(t):  # torch (nb, n) tensor == engine-native SoA view with ld = n
+        if aos_layout:  # torch (n, nb) tensor == the reference's row-major layout (src/batch.rs:41-47)
+            return cabi.view(t.data_ptr(), t.shape[0], t.stride(0), code, cabi.LCC_AOS)
         return cabi.view(t.data_ptr(), t.shape[1], t.stride(0), code, cabi.LCC_SOA)
+
+    def randn_batch():
+        t = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
+        return t.T.contiguous() if aos_layout else t
+
+    def rows_of(t, idx):  # (len(idx), nb) host array of the selected rows
+        return (t[idx] if aos_layout else t[:, idx].T).contiguous().cpu().numpy()
 
     motor = None
     if wl == "pga_sandwich":
@@ -267,6 +280,8 @@ def run_gpu_arm(args):
         x[7].fill_(1.0)
         x[14].copy_(-pts[0]); x[13].copy_(pts[1]); x[11].copy_(-pts[2])
         del pts
+        if aos_layout:
+            x = x.T.contiguous()
         out = torch.empty_like(x)
         motor = headline_motor()
         mptr = motor.ctypes.data_as(C.POINTER(C.c_double))
@@ -275,8 +290,8 @@ def run_gpu_arm(args):
         def step():
             cabi.check(lib.lcc_batch_sandwich(alg.h, mptr, C.byref(vx), C.byref(vo), flags, sptr))
     elif wl in ("cga_gp", "r3_gp", "cga_gp_outer"):
-        a = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
-        b = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
+        a = randn_batch()
+        b = randn_batch()
         out = torch.empty_like(a)
         va, vb, vo = soa(a), soa(b), soa(out)
         if wl == "cga_gp_outer":
@@ -359,8 +374,8 @@ def run_gpu_arm(args):
         idx = torch.cat([torch.arange(0, 4096), torch.arange(n // 2, n // 2 + 4096), torch.arange(n - 4096, n)]).to(dev)
         tol = 1e-5 if dt == "f32" else 1e-12
         if wl == "pga_sandwich":
-            xs = x[:, idx].T.contiguous().cpu().numpy()
-            got = out[:, idx].T.contiguous().cpu().numpy()
+            xs = rows_of(x, idx)
+            got = rows_of(out, idx)
             want = o.sandwich(motor, xs)
         elif wl == "sta_fused_grade_inner_sum":
             m = 1 << 20  # the fused kernel only returns the sums: re-run it on the first 2^20 rows and compare with the oracle
@@ -384,8 +399,8 @@ def run_gpu_arm(args):
             got = out[:, idx].T.contiguous().cpu().numpy()
             want = o.geometric_product(a[:, 0].cpu().numpy().astype(np.float64)[None, :], ys)
         else:
-            xs, ys = a[:, idx].T.contiguous().cpu().numpy(), b[:, idx].T.contiguous().cpu().numpy()
-            got = out[:, idx].T.contiguous().cpu().numpy()
+            xs, ys = rows_of(a, idx), rows_of(b, idx)
+            got = rows_of(out, idx)
             want = o.geometric_product(xs, ys)
         err = float(np.abs(got.astype(np.float64) - want.astype(np.float64)).max() / np.abs(want).max())
         parity = {"rows_checked": int(idx.numel()), "max_rel_err": err, "tolerance": tol, "ok": bool(err <= tol)}
@@ -423,7 +438,7 @@ def run_gpu_arm(args):
         "metric": f"{wl} throughput", "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": dt, "data": "synthetic",
-        "config": {"workload": workload_name(wl), "rows_per_gpu": n, "layout": "SoA (blade-major) in HBM",
+        "config": {"workload": workload_name(wl), "rows_per_gpu": n, "layout": "AoS (N, num_blades) row-major in HBM, TMA-staged tiles" if aos_layout else "SoA (blade-major) in HBM",
                    "l2_policy": "inputs larger than L2 (>= 17 GB per pass vs 126 MB L2)", "strict_fp": bool(args.strict)},
         "roofline": roofline_block(wl, n, kernel_ms, bytes_per, peaks, peak_kind, traffic),
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(), "parity": parity,
@@ -527,6 +542,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS))
     ap.add_argument("--log2-rows", type=int, default=0, help="override rows per GPU (power of two exponent)")
+    ap.add_argument("--layout", default="soa", choices=["soa", "aos"], help="HBM layout of the batches (aos = the reference's (N, num_blades) rows)")
     ap.add_argument("--strict", action="store_true", help="LCC_FLAG_STRICT_FP (bit-exact, no FMA)")
     ap.add_argument("--cpu-threads", type=int, default=0, help="reference arm: OpenMP threads (default 1 = the reference's behaviour)")
     ap.add_argument("--e2e-steps", type=int, default=5)

@@ -25,6 +25,7 @@
 
 #include "common.cuh"
 #include "launch_args.h"
+#include "tma_tile.cuh"
 
 #ifndef LCC_TERMS_FILE
 #error "define LCC_TERMS_FILE, LCC_NB, LCC_RUNTIME_METRIC, LCC_REAL and LCC_TU before including product_impl.cuh"
@@ -235,6 +236,155 @@ sandwich_kernel(const real *__restrict__ x, int64_t ldx, real *__restrict__ out,
 #undef LCC_OUT_END
 }
 
+// ------------------------------------------------------------------------------------------ K1 / K2 on TMA-staged AoS tiles
+// Same arithmetic as product_kernel<kAoS> / sandwich_kernel<kAoS>, different data movement: the block's
+// kRows consecutive rows arrive in shared memory through cp.async.bulk.tensor (one elected thread, mbarrier
+// completion), each thread reads its own row from the swizzled tile, writes its result row over it, and the
+// tile leaves through a TMA store.  A thread only ever touches the shared-memory bytes of its own row, so the
+// in-place overwrite needs no barrier; the only block-wide sync is the one that precedes the store.
+constexpr int kRowBytes = NB * (int)sizeof(real);
+constexpr bool kHasTmaPath = kRowBytes >= 32;
+using TmaTile = AosTmaTile<(kRowBytes >= 32 ? kRowBytes : 32)>;
+constexpr int kChunkElems = 16 / (int)sizeof(real);
+
+struct alignas(16) Chunk { real v[kChunkElems]; };
+
+static __device__ __forceinline__ void load_tile_row(Tile<real, NB, 1> &t, const uint8_t *tile, int row) {
+#pragma unroll
+    for (int j = 0; j < NB / kChunkElems; ++j) {
+        const Chunk c = *reinterpret_cast<const Chunk *>(tile + TmaTile::chunk_offset(row, j));
+#pragma unroll
+        for (int l = 0; l < kChunkElems; ++l) t.v[j * kChunkElems + l][0] = c.v[l];
+    }
+}
+static __device__ __forceinline__ void load_bcast_row(Tile<real, NB, 1> &t, const real *__restrict__ row) {
+#pragma unroll
+    for (int k = 0; k < NB; ++k) t.v[k][0] = __ldg(row + k);
+}
+
+struct TileSink {  // collects 16 bytes of consecutive blades, then writes them to the thread's row of the tile
+    uint8_t *tile; int row;
+    Chunk buf;
+    template <int K> __device__ __forceinline__ void put(const real (&acc)[1]) {
+        buf.v[K % kChunkElems] = acc[0];
+        if constexpr ((K % kChunkElems) == kChunkElems - 1)
+            *reinterpret_cast<Chunk *>(tile + TmaTile::chunk_offset(row, K / kChunkElems)) = buf;
+    }
+};
+
+static __device__ __forceinline__ uint8_t *tma_smem_base(uint8_t *raw) {
+    return (uint8_t *)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);  // swizzle patterns are functions of the address bits
+}
+static __device__ __forceinline__ void tma_load_tile(uint8_t *dst, const CUtensorMap *map, uint64_t *bar, int row0) {
+#pragma unroll
+    for (int sub = 0; sub < TmaTile::kSub; ++sub)
+        tma::load_2d(dst + sub * TmaTile::kRows * TmaTile::kSpan, map, bar, sub * (TmaTile::kSpan / (int)sizeof(real)), row0);
+}
+static __device__ __forceinline__ void tma_store_tile(const CUtensorMap *map, const uint8_t *src, int row0) {
+#pragma unroll
+    for (int sub = 0; sub < TmaTile::kSub; ++sub)
+        tma::store_2d(map, src + sub * TmaTile::kRows * TmaTile::kSpan, sub * (TmaTile::kSpan / (int)sizeof(real)), row0);
+}
+
+template <int OP, bool STRICT>
+__global__ void __launch_bounds__(TmaTile::kRows)
+product_kernel_aos_tma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                       const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out2,
+                       const real *__restrict__ a_row, const real *__restrict__ b_row, const Coeffs mu) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *tile_a = tma_smem_base(smem_raw), *tile_b = tile_a + TmaTile::kBytes;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(tile_b + TmaTile::kBytes);
+    const int t = threadIdx.x, row0 = blockIdx.x * TmaTile::kRows;
+    if (t == 0) {
+        tma::mbar_init(bar, 1);
+        tma::mbar_expect_tx(bar, (a_row ? 0u : (uint32_t)TmaTile::kBytes) + (b_row ? 0u : (uint32_t)TmaTile::kBytes));
+        if (!a_row) tma_load_tile(tile_a, &map_a, bar, row0);
+        if (!b_row) tma_load_tile(tile_b, &map_b, bar, row0);
+    }
+    __syncthreads();  // the barrier word is initialised before anyone polls it
+    Tile<real, NB, 1> A, B;
+    if (a_row) load_bcast_row(A, a_row);  // one-row operand (reference broadcast rule, batch.rs:361-376): no tile
+    if (b_row) load_bcast_row(B, b_row);
+    tma::mbar_wait(bar, 0);
+    if (!a_row) load_tile_row(A, tile_a, t);
+    if (!b_row) load_tile_row(B, tile_b, t);
+    TileSink sink{tile_a, t, {}};
+    TileSink sink2{tile_b, t, {}};
+    (void)sink2;
+    (void)mu;
+    constexpr int V = 1;
+#define LCC_OUT_BEGIN(k) { real acc[V]; real acc2[V]; acc[0] = real(0); acc2[0] = real(0);
+#define LCC_TERM(k, i, j, neg, flags)                                                                   \
+    if constexpr (term_in_op(OP, flags)) {                                                             \
+        real av = (neg) ? -A.v[i][0] : A.v[i][0];                                                      \
+        if constexpr (kRuntimeMetric) av = mul_rn(av, mu.v[(i) & (j)]);                                \
+        acc[0] = Arith<STRICT>::madd(av, B.v[j][0], acc[0]);                                           \
+        if constexpr (OP == kOpGPOuter && ((flags) & 1)) acc2[0] = Arith<STRICT>::madd(av, B.v[j][0], acc2[0]); \
+    }
+#define LCC_OUT_END(k) sink.template put<k>(acc); if constexpr (OP == kOpGPOuter) sink2.template put<k>(acc2); }
+#include LCC_TERMS_FILE
+#undef LCC_OUT_BEGIN
+#undef LCC_TERM
+#undef LCC_OUT_END
+    tma::fence_proxy_async();
+    __syncthreads();
+    if (t == 0) {
+        tma_store_tile(&map_out, tile_a, row0);
+        if constexpr (OP == kOpGPOuter) tma_store_tile(&map_out2, tile_b, row0);
+        tma::store_commit_and_wait_read();  // the tile must outlive the engine's read of it
+    }
+}
+
+template <bool STRICT, bool EVEN>
+__global__ void __launch_bounds__(TmaTile::kRows)
+sandwich_kernel_aos_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_out,
+                        const Coeffs R, const Coeffs Rrev, const Coeffs mu) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *tile = tma_smem_base(smem_raw);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(tile + TmaTile::kBytes);
+    const int t = threadIdx.x, row0 = blockIdx.x * TmaTile::kRows;
+    if (t == 0) {
+        tma::mbar_init(bar, 1);
+        tma::mbar_expect_tx(bar, (uint32_t)TmaTile::kBytes);
+        tma_load_tile(tile, &map_x, bar, row0);
+    }
+    __syncthreads();
+    tma::mbar_wait(bar, 0);
+    constexpr int V = 1;
+    Tile<real, NB, 1> X, RX;
+    load_tile_row(X, tile, t);
+    (void)mu;
+#define LCC_OUT_BEGIN(k) { real acc[V]; acc[0] = real(0);
+#define LCC_TERM(k, i, j, neg, flags)                                                                   \
+    if constexpr (!EVEN || even_grade(i)) {                                                            \
+        real rv = (neg) ? -R.v[i] : R.v[i];                                                            \
+        if constexpr (kRuntimeMetric) rv = mul_rn(rv, mu.v[(i) & (j)]);                                \
+        acc[0] = Arith<STRICT>::madd(rv, X.v[j][0], acc[0]);                                           \
+    }
+#define LCC_OUT_END(k) RX.v[k][0] = acc[0]; }
+#include LCC_TERMS_FILE
+#undef LCC_TERM
+#undef LCC_OUT_END
+    TileSink sink{tile, t, {}};
+#define LCC_TERM(k, i, j, neg, flags)                                                                   \
+    if constexpr (!EVEN || even_grade(j)) {                                                            \
+        real rv = (neg) ? -Rrev.v[j] : Rrev.v[j];                                                      \
+        if constexpr (kRuntimeMetric) rv = mul_rn(rv, mu.v[(i) & (j)]);                                \
+        acc[0] = Arith<STRICT>::madd(RX.v[i][0], rv, acc[0]);                                          \
+    }
+#define LCC_OUT_END(k) sink.template put<k>(acc); }
+#include LCC_TERMS_FILE
+#undef LCC_OUT_BEGIN
+#undef LCC_TERM
+#undef LCC_OUT_END
+    tma::fence_proxy_async();
+    __syncthreads();
+    if (t == 0) {
+        tma_store_tile(&map_out, tile, row0);
+        tma::store_commit_and_wait_read();
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host
 static inline Coeffs to_coeffs(const double *src, double fill) {
     Coeffs c;
@@ -277,11 +427,66 @@ template <int LAYOUT, int OP, bool STRICT> static cudaError_t launch_product_sum
     return cudaGetLastError();
 }
 
+// AoS batches of at least this many rows go through the TMA-staged kernels (below it the tensor-map
+// encode on the host costs more than the wider accesses save).  LCC_AOS_TMA=0 forces the direct-load kernels.
+constexpr int64_t kTmaMinRows = 4096;
+static inline bool tma_path_enabled() {
+    static const bool on = [] { const char *e = std::getenv("LCC_AOS_TMA"); return !(e && e[0] == '0'); }();
+    return on;
+}
+static inline bool aos_map(CUtensorMap *m, const void *base, int64_t ld, int64_t n) {
+    return make_aos_tensor_map(m, base, (int)sizeof(real), NB, ld, n, TmaTile::kSpan, TmaTile::kRows);
+}
+
+// returns cudaErrorNotSupported when the operands do not qualify (caller falls back to the direct kernel)
+template <int OP, bool STRICT> static cudaError_t launch_product_tma(const ProductArgs &g) {
+    if constexpr (!kHasTmaPath) {
+        return cudaErrorNotSupported;
+    } else {
+        if (!tma_path_enabled() || g.n < kTmaMinRows) return cudaErrorNotSupported;
+        CUtensorMap ma, mb, mo, mo2;
+        if (!aos_map(&mo, g.out, g.ldo, g.n)) return cudaErrorNotSupported;
+        ma = mb = mo2 = mo;  // placeholders for operands that do not use a tile
+        if (!g.a_bcast && !aos_map(&ma, g.a, g.lda, g.n)) return cudaErrorNotSupported;
+        if (!g.b_bcast && !aos_map(&mb, g.b, g.ldb, g.n)) return cudaErrorNotSupported;
+        if (OP == kOpGPOuter && !aos_map(&mo2, g.out2, g.ldo2, g.n)) return cudaErrorNotSupported;
+        auto kernel = product_kernel_aos_tma<OP, STRICT>;
+        constexpr int smem = 2 * TmaTile::kBytes + 1024 + 16;
+        static const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (attr != cudaSuccess) return attr;
+        const unsigned grid = (unsigned)((g.n + TmaTile::kRows - 1) / TmaTile::kRows);
+        kernel<<<grid, TmaTile::kRows, smem, g.stream>>>(ma, mb, mo, mo2, g.a_bcast ? (const real *)g.a : nullptr,
+                                                        g.b_bcast ? (const real *)g.b : nullptr, to_coeffs(g.mu, 1.0));
+        note_kernel_launch();
+        return cudaGetLastError();
+    }
+}
+
+template <bool STRICT, bool EVEN> static cudaError_t launch_sandwich_tma(const SandwichArgs &g, const Coeffs &R, const Coeffs &Rrev) {
+    if constexpr (!kHasTmaPath) {
+        return cudaErrorNotSupported;
+    } else {
+        if (!tma_path_enabled() || g.n < kTmaMinRows) return cudaErrorNotSupported;
+        CUtensorMap mx, mo;
+        if (!aos_map(&mx, g.x, g.ldx, g.n) || !aos_map(&mo, g.out, g.ldo, g.n)) return cudaErrorNotSupported;
+        auto kernel = sandwich_kernel_aos_tma<STRICT, EVEN>;
+        constexpr int smem = TmaTile::kBytes + 1024 + 16;
+        const unsigned grid = (unsigned)((g.n + TmaTile::kRows - 1) / TmaTile::kRows);
+        kernel<<<grid, TmaTile::kRows, smem, g.stream>>>(mx, mo, R, Rrev, to_coeffs(g.mu, 1.0));
+        note_kernel_launch();
+        return cudaGetLastError();
+    }
+}
+
 template <int LAYOUT, int OP, bool STRICT> static cudaError_t launch_product_t(const ProductArgs &g) {
     if constexpr (OP != kOpGPOuter) {
         if (g.sum_partial) return launch_product_sum_t<LAYOUT, OP, STRICT>(g);
     }
     if (g.n <= 0) return cudaSuccess;
+    if constexpr (LAYOUT == kAoS) {
+        const cudaError_t e = launch_product_tma<OP, STRICT>(g);
+        if (e != cudaErrorNotSupported) return e;
+    }
     constexpr int W = 16 / (int)sizeof(real);
     int vec_ok = 1;
     if (LAYOUT == kAoS) {
@@ -322,6 +527,10 @@ template <int LAYOUT, bool STRICT, bool EVEN> static cudaError_t launch_sandwich
         for (int b = i; b; b >>= 1) grade += b & 1;
         // ~R[i] = R[i] * reverse_sign(grade): src/batch.rs:452-457, src/algebra/blades.rs:128-135
         Rrev.v[i] = R.v[i] * ((grade % 4 < 2) ? real(1) : real(-1));
+    }
+    if constexpr (LAYOUT == kAoS) {
+        const cudaError_t e = launch_sandwich_tma<STRICT, EVEN>(g, R, Rrev);
+        if (e != cudaErrorNotSupported) return e;
     }
     sandwich_kernel<LAYOUT, STRICT, EVEN><<<grid_for<LAYOUT>(g.n), block_threads(), 0, g.stream>>>(
         (const real *)g.x, g.ldx, (real *)g.out, g.ldo, g.n, vec_ok, R, Rrev, to_coeffs(g.mu, 1.0));

@@ -422,3 +422,93 @@ def test_fused_grade_product_sum(L, sig, dt):
         assert np.all(np.abs(A.product_sum(one, op="lc", grade=1).astype(np.float64) - want) <= tol * np.maximum(mag, 1e-300))
     with pytest.raises(ValueError, match="exceeds dimension"):
         A.product_sum(B, op="lc", grade=o.dimension + 1)
+
+
+# ----------------------------------------------------------------------------------------------- AoS tiles through TMA
+class _Dev:
+    """Caller-owned device arrays for raw C-ABI calls."""
+
+    def __init__(self, lib):
+        self.lib, self.ptrs = lib, []
+
+    def put(self, host):
+        from largecrimsoncanine_b200 import cabi
+
+        p = C.c_void_p()
+        cabi.check(self.lib.lcc_device_alloc(C.byref(p), max(host.nbytes, 16), None))
+        cabi.check(self.lib.lcc_memcpy_h2d(p, host.ctypes.data, host.nbytes, None))
+        self.ptrs.append(p)
+        return p
+
+    def get(self, p, like):
+        from largecrimsoncanine_b200 import cabi
+
+        out = np.empty_like(like)
+        cabi.check(self.lib.lcc_memcpy_d2h(out.ctypes.data, p, out.nbytes, None))
+        cabi.check(self.lib.lcc_stream_sync(None))
+        return out
+
+    def free(self):
+        from largecrimsoncanine_b200 import cabi
+
+        for p in self.ptrs:
+            cabi.check(self.lib.lcc_device_free(p, None))
+        self.ptrs = []
+
+
+@pytest.mark.parametrize("sig", [(3, 0, 0), (3, 0, 1), (4, 1, 0), (1, 3, 0), (2, 1, 1), (2, 0, 0), (5, 0, 0)])
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_aos_batches_through_tma_tiles(L, sig, dt):
+    """Reference-layout (N, num_blades) batches of >= 4096 rows take the TMA-staged kernels
+    (kernels/tma_tile.cuh): ragged last tile, padded row pitch, broadcast operands, the fused dual-output
+    form and the sandwich, all bit-exact in strict mode; a pitch TMA cannot describe (not a multiple of
+    16 bytes) must silently take the direct-load kernels and give the same bits."""
+    from largecrimsoncanine_b200 import cabi
+
+    lib = cabi.lib()
+    o, alg = oracle.OracleAlgebra(*sig), cabi.Algebra(*sig)
+    nb = o.num_blades
+    code = cabi.LCC_F64 if dt == np.float64 else cabi.LCC_F32
+    rng = np.random.default_rng(23)
+    S = cabi.LCC_FLAG_STRICT_FP
+    dev = _Dev(lib)
+    for n, pad in ((4096, 0), (4096 + 37, 0), (10007, 0), (5000, 16 // np.dtype(dt).itemsize), (4500, 1)):
+        ld = nb + pad
+        a, b = rand(rng, n, nb, dt), rand(rng, n, nb, dt)
+
+        def image(x):
+            img = np.full((x.shape[0], ld), 7.0, dt)  # pitch padding must be neither read as data nor written
+            img[:, :nb] = x
+            return img
+
+        ia, ib = image(a), image(b)
+        pa, pb, po, po2 = dev.put(ia), dev.put(ib), dev.put(image(np.zeros_like(a))), dev.put(image(np.zeros_like(a)))
+        va, vb, vo, vo2 = (cabi.view(p.value, n, ld, code, cabi.LCC_AOS) for p in (pa, pb, po, po2))
+        for op, ref in ((cabi.LCC_OP_GP, o.geometric_product), (cabi.LCC_OP_OUTER, o.outer_product), (cabi.LCC_OP_LC, o.left_contraction)):
+            cabi.check(lib.lcc_batch_product(alg.h, op, C.byref(va), C.byref(vb), C.byref(vo), S, None))
+            got = dev.get(po, ia)
+            assert np.array_equal(got[:, :nb], ref(a, b)), (n, pad, op)
+            assert np.all(got[:, nb:] == 7.0)
+        cabi.check(lib.lcc_batch_gp_outer(alg.h, C.byref(va), C.byref(vb), C.byref(vo), C.byref(vo2), S, None))
+        assert np.array_equal(dev.get(po, ia)[:, :nb], o.geometric_product(a, b))
+        assert np.array_equal(dev.get(po2, ia)[:, :nb], o.outer_product(a, b))
+        # FMA mode stays within the stated tolerance
+        cabi.check(lib.lcc_batch_product(alg.h, cabi.LCC_OP_GP, C.byref(va), C.byref(vb), C.byref(vo), 0, None))
+        assert_close(dev.get(po, ia)[:, :nb], o.geometric_product(a, b), o.product_abs_bound("gp", a, b), dt)
+        # broadcast on either side (batch.rs:361-376)
+        one = rand(rng, 1, nb, dt)
+        p1 = dev.put(np.ascontiguousarray(one))
+        v1 = cabi.view(p1.value, 1, nb, code, cabi.LCC_AOS)
+        cabi.check(lib.lcc_batch_product(alg.h, cabi.LCC_OP_GP, C.byref(v1), C.byref(vb), C.byref(vo), S, None))
+        assert np.array_equal(dev.get(po, ia)[:, :nb], o.geometric_product(one, b))
+        cabi.check(lib.lcc_batch_product(alg.h, cabi.LCC_OP_LC, C.byref(va), C.byref(v1), C.byref(vo), S, None))
+        assert np.array_equal(dev.get(po, ia)[:, :nb], o.left_contraction(a, one))
+        # sandwich: dense rotor and even rotor (the pruned kernel)
+        dense = rng.standard_normal(nb)
+        even = dense * np.array([1.0 if bin(i).count("1") % 2 == 0 else 0.0 for i in range(nb)])
+        for rotor in (dense, even):
+            cabi.check(lib.lcc_batch_sandwich(alg.h, rotor.ctypes.data_as(C.POINTER(C.c_double)), C.byref(va), C.byref(vo), S, None))
+            got = dev.get(po, ia)
+            assert np.array_equal(got[:, :nb], o.sandwich(rotor, a)), (n, pad)
+            assert np.all(got[:, nb:] == 7.0)
+        dev.free()
