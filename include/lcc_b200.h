@@ -57,8 +57,15 @@ typedef enum {
 typedef enum { LCC_F32 = 0, LCC_F64 = 1 } lcc_dtype;
 typedef enum { LCC_SOA = 0, LCC_AOS = 1 } lcc_layout;
 
-/* Binary products, src/batch.rs:353-410 (geometric), 514-574 (outer), 585-655 (left contraction). */
-typedef enum { LCC_OP_GP = 0, LCC_OP_OUTER = 1, LCC_OP_LC = 2 } lcc_product_op;
+/* Binary products, src/batch.rs:353-410 (geometric), 514-574 (outer), 585-655 (left contraction).
+ * The rest of the row-wise product family has no batched form in the reference; these are the batched
+ * forms of Multivector::right_contraction (src/multivector.rs:1616-1661), scalar_product (:1673-1715),
+ * commutator (:1732-1745), anticommutator (:1755-1768) and regressive (:1781-1794, LCC_ERR_VALUE when the
+ * pseudoscalar is null).  Code 3 is reserved. */
+typedef enum {
+    LCC_OP_GP = 0, LCC_OP_OUTER = 1, LCC_OP_LC = 2, LCC_OP_RC = 4, LCC_OP_SCALAR = 5,
+    LCC_OP_COMMUTATOR = 6, LCC_OP_ANTICOMMUTATOR = 7, LCC_OP_REGRESSIVE = 8
+} lcc_product_op;
 
 /* Row-wise unary maps.  REVERSE / INVOLUTE: src/batch.rs:823-860.  GRADE: batch.rs:1027-1052 (arg = k).
  * CONJUGATE: src/algebra/blades.rs:182-188.  DUAL / UNDUAL / RIGHT_DUAL: src/multivector.rs:4249-4290

@@ -17,6 +17,7 @@ LCC_OK, LCC_ERR_VALUE, LCC_ERR_INDEX, LCC_ERR_ZERODIV, LCC_ERR_CUDA, LCC_ERR_NO_
 LCC_F32, LCC_F64 = 0, 1
 LCC_SOA, LCC_AOS = 0, 1
 LCC_OP_GP, LCC_OP_OUTER, LCC_OP_LC = 0, 1, 2
+LCC_OP_RC, LCC_OP_SCALAR, LCC_OP_COMMUTATOR, LCC_OP_ANTICOMMUTATOR, LCC_OP_REGRESSIVE = 4, 5, 6, 7, 8
 (LCC_UN_REVERSE, LCC_UN_INVOLUTE, LCC_UN_CONJUGATE, LCC_UN_GRADE, LCC_UN_DUAL, LCC_UN_UNDUAL,
  LCC_UN_RIGHT_DUAL, LCC_UN_PGA_DUAL, LCC_UN_EVEN, LCC_UN_ODD, LCC_UN_COPY) = range(11)
 LCC_EW_ADD, LCC_EW_SUB = 0, 1

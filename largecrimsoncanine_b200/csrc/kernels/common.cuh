@@ -32,6 +32,8 @@ template <> struct Arith<true> {
 };
 static __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
 static __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+static __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+static __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 static __device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
 static __device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
 static __device__ __forceinline__ float sqrt_rn(float a) { return __fsqrt_rn(a); }

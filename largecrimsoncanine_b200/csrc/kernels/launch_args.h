@@ -9,7 +9,8 @@ namespace lcc {
 enum : int { kSoA = 0, kAoS = 1 };
 enum : int { kF32 = 0, kF64 = 1 };
 // product selector inside kernels: the three reference products + the fused dual-output form
-enum : int { kOpGP = 0, kOpOuter = 1, kOpLC = 2, kOpGPOuter = 3 };
+// (values 0-2 and 4-7 are the public lcc_product_op codes; 3 is internal)
+enum : int { kOpGP = 0, kOpOuter = 1, kOpLC = 2, kOpGPOuter = 3, kOpRC = 4, kOpScalar = 5, kOpCommutator = 6, kOpAnticommutator = 7 };
 
 struct ProductArgs {
     int op = kOpGP;

@@ -530,17 +530,37 @@ cudaError_t launch_points_extract(int which, const ViewArg &src, void *xyz, cuda
 // ------------------------------------------------------------------------------------------ TMA tensor maps
 // cuTensorMapEncodeTiled is reached through the runtime's driver entry point query, so the library
 // does not link libcuda directly.
-bool make_aos_tensor_map(CUtensorMap *map, const void *base, int elem_bytes, int nb, int64_t ld, int64_t n,
-                         int span_bytes, int rows) {
-    using EncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+namespace {
+using EncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                              const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn tensor_map_encoder() {
     static EncodeFn enc = [] {
         void *p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
         return (EncodeFn)p;
     }();
+    return enc;
+}
+}  // namespace
+
+bool make_soa_tensor_map(CUtensorMap *map, const void *base, int elem_bytes, int nb, int64_t ld, int64_t n, int rows) {
+    EncodeFn enc = tensor_map_encoder();
+    if (!enc || n <= 0 || n >= (int64_t)1 << 31) return false;
+    if (((uintptr_t)base & 15) != 0 || ((ld * elem_bytes) & 15) != 0 || ld < n) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)nb};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * (cuuint64_t)elem_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)rows, (cuuint32_t)nb};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = elem_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    return enc(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool make_aos_tensor_map(CUtensorMap *map, const void *base, int elem_bytes, int nb, int64_t ld, int64_t n,
+                         int span_bytes, int rows) {
+    EncodeFn enc = tensor_map_encoder();
     if (!enc || n <= 0 || n >= (int64_t)1 << 31) return false;
     if (((uintptr_t)base & 15) != 0 || ((ld * elem_bytes) & 15) != 0 || ld < nb) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)nb, (cuuint64_t)n};

@@ -46,8 +46,22 @@ __host__ __device__ constexpr bool even_grade(int blade) {
     for (int b = blade; b; b >>= 1) c += b & 1;
     return (c & 1) == 0;
 }
-__host__ __device__ constexpr bool term_in_op(int op, int flags) {
-    return op == kOpGP || op == kOpGPOuter || (op == kOpOuter && (flags & 1)) || (op == kOpLC && (flags & 2));
+// flags of a generated term: 1 = (i & j) == 0 (outer), 2 = (i & j) == i (left contraction),
+// 4 = (i & j) == j (right contraction); k = output blade (the scalar product keeps k == 0 only)
+__host__ __device__ constexpr bool term_in_op(int op, int flags, int k) {
+    return op == kOpGP || op == kOpGPOuter || op == kOpCommutator || op == kOpAnticommutator ||
+           (op == kOpOuter && (flags & 1)) || (op == kOpLC && (flags & 2)) || (op == kOpRC && (flags & 4)) ||
+           (op == kOpScalar && k == 0);
+}
+__host__ __device__ constexpr bool two_sided(int op) { return op == kOpCommutator || op == kOpAnticommutator; }
+
+// (a*b -/+ b*a) * 0.5 with every step rounded, as Multivector::commutator / anticommutator compose them
+// (/root/reference/src/multivector.rs:1732-1768: geometric_product twice, __sub__ / __add__, scale(0.5)).
+template <int OP, class T, int V> static __device__ __forceinline__ void finish_two_sided(T (&acc)[V], const T (&acc2)[V]) {
+    if constexpr (two_sided(OP)) {
+#pragma unroll
+        for (int l = 0; l < V; ++l) acc[l] = mul_rn(add_rn(acc[l], OP == kOpCommutator ? -acc2[l] : acc2[l]), T(0.5));
+    }
 }
 
 // Output sink: SoA stores V rows of one blade per call; AoS collects 16 bytes of consecutive
@@ -103,15 +117,20 @@ product_kernel(const real *__restrict__ a, int64_t lda, int a_bcast, const real 
 
 #define LCC_OUT_BEGIN(k) { real acc[V]; real acc2[V]; _Pragma("unroll") for (int l = 0; l < V; ++l) { acc[l] = real(0); acc2[l] = real(0); }
 #define LCC_TERM(k, i, j, neg, flags)                                                                   \
-    if constexpr (term_in_op(OP, flags)) {                                                             \
+    if constexpr (term_in_op(OP, flags, k)) {                                                             \
         _Pragma("unroll") for (int l = 0; l < V; ++l) {                                                \
             real av = (neg) ? -A.v[i][l] : A.v[i][l];                                                  \
             if constexpr (kRuntimeMetric) av = mul_rn(av, mu.v[(i) & (j)]);                            \
             acc[l] = Arith<STRICT>::madd(av, B.v[j][l], acc[l]);                                       \
             if constexpr (OP == kOpGPOuter && ((flags) & 1)) acc2[l] = Arith<STRICT>::madd(av, B.v[j][l], acc2[l]); \
+            if constexpr (two_sided(OP)) {                                                             \
+                real bv = (neg) ? -B.v[i][l] : B.v[i][l];                                              \
+                if constexpr (kRuntimeMetric) bv = mul_rn(bv, mu.v[(i) & (j)]);                        \
+                acc2[l] = Arith<STRICT>::madd(bv, A.v[j][l], acc2[l]);                                 \
+            }                                                                                          \
         }                                                                                              \
     }
-#define LCC_OUT_END(k) sink.template put<k>(acc); if constexpr (OP == kOpGPOuter) sink2.template put<k>(acc2); }
+#define LCC_OUT_END(k) finish_two_sided<OP>(acc, acc2); sink.template put<k>(acc); if constexpr (OP == kOpGPOuter) sink2.template put<k>(acc2); }
 #include LCC_TERMS_FILE
 #undef LCC_OUT_BEGIN
 #undef LCC_TERM
@@ -169,7 +188,7 @@ product_sum_kernel(const real *__restrict__ a, int64_t lda, int a_bcast, int a_g
         }
 #define LCC_OUT_BEGIN(k) { real acc[V]; _Pragma("unroll") for (int l = 0; l < V; ++l) acc[l] = real(0);
 #define LCC_TERM(k, i, j, neg, flags)                                                                   \
-    if constexpr (term_in_op(OP, flags)) {                                                             \
+    if constexpr (term_in_op(OP, flags, k)) {                                                             \
         _Pragma("unroll") for (int l = 0; l < V; ++l) {                                                \
             real av = (neg) ? -A.v[i][l] : A.v[i][l];                                                  \
             if constexpr (kRuntimeMetric) av = mul_rn(av, mu.v[(i) & (j)]);                            \
@@ -315,13 +334,18 @@ product_kernel_aos_tma(const __grid_constant__ CUtensorMap map_a, const __grid_c
     constexpr int V = 1;
 #define LCC_OUT_BEGIN(k) { real acc[V]; real acc2[V]; acc[0] = real(0); acc2[0] = real(0);
 #define LCC_TERM(k, i, j, neg, flags)                                                                   \
-    if constexpr (term_in_op(OP, flags)) {                                                             \
+    if constexpr (term_in_op(OP, flags, k)) {                                                             \
         real av = (neg) ? -A.v[i][0] : A.v[i][0];                                                      \
         if constexpr (kRuntimeMetric) av = mul_rn(av, mu.v[(i) & (j)]);                                \
         acc[0] = Arith<STRICT>::madd(av, B.v[j][0], acc[0]);                                           \
         if constexpr (OP == kOpGPOuter && ((flags) & 1)) acc2[0] = Arith<STRICT>::madd(av, B.v[j][0], acc2[0]); \
+        if constexpr (two_sided(OP)) {                                                                 \
+            real bv = (neg) ? -B.v[i][0] : B.v[i][0];                                                  \
+            if constexpr (kRuntimeMetric) bv = mul_rn(bv, mu.v[(i) & (j)]);                            \
+            acc2[0] = Arith<STRICT>::madd(bv, A.v[j][0], acc2[0]);                                     \
+        }                                                                                              \
     }
-#define LCC_OUT_END(k) sink.template put<k>(acc); if constexpr (OP == kOpGPOuter) sink2.template put<k>(acc2); }
+#define LCC_OUT_END(k) finish_two_sided<OP>(acc, acc2); sink.template put<k>(acc); if constexpr (OP == kOpGPOuter) sink2.template put<k>(acc2); }
 #include LCC_TERMS_FILE
 #undef LCC_OUT_BEGIN
 #undef LCC_TERM
@@ -427,6 +451,172 @@ template <int LAYOUT, int OP, bool STRICT> static cudaError_t launch_product_sum
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------ K1 / K2 on TMA-staged SoA tiles
+// Engine-native blade-major batches: the tile is NB blade rows x kSoaTileRows batch rows (NB segments of
+// contiguous HBM), a thread owns V consecutive batch rows exactly as in the direct-load kernels and reads
+// them from shared memory with one 16-byte (or 8-byte) access per blade.
+#ifndef LCC_SOA_TILE_BYTES
+#define LCC_SOA_TILE_BYTES 16384
+#endif
+constexpr int kSoaTileRows = []() constexpr {
+    int r = LCC_SOA_TILE_BYTES / (NB * (int)sizeof(real));  // bytes per operand tile
+    r = r > 1024 ? 1024 : r;
+    return r < 32 * kRowsSoA ? 32 * kRowsSoA : r;  // at least one warp
+}();
+constexpr int kSoaBoxRows = kSoaTileRows > 256 ? 256 : kSoaTileRows;  // TMA boxes are at most 256 elements wide
+constexpr int kSoaBoxes = kSoaTileRows / kSoaBoxRows;
+constexpr int kSoaBoxBytes = kSoaBoxRows * NB * (int)sizeof(real);
+constexpr int kSoaTileThreads = kSoaTileRows / kRowsSoA;
+constexpr int kSoaTileBytes = kSoaTileRows * NB * (int)sizeof(real);
+
+template <int V> struct alignas(V * sizeof(real)) RowVec { real v[V]; };
+
+// byte offset of (blade k, tile row r): boxes one after the other, each [NB][kSoaBoxRows]
+static __device__ __forceinline__ size_t soa_tile_offset(int k, int r) {
+    return ((size_t)(r / kSoaBoxRows) * NB * kSoaBoxRows + (size_t)k * kSoaBoxRows + (r % kSoaBoxRows)) * sizeof(real);
+}
+template <int V>
+static __device__ __forceinline__ void load_soa_tile(Tile<real, NB, V> &t, const uint8_t *tile, int first_row) {
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        const RowVec<V> c = *reinterpret_cast<const RowVec<V> *>(tile + soa_tile_offset(k, first_row));
+#pragma unroll
+        for (int l = 0; l < V; ++l) t.v[k][l] = c.v[l];
+    }
+}
+template <int V> struct SoaTileSink {
+    uint8_t *tile; int first_row;
+    template <int K> __device__ __forceinline__ void put(const real (&acc)[V]) {
+        RowVec<V> c;
+#pragma unroll
+        for (int l = 0; l < V; ++l) c.v[l] = acc[l];
+        *reinterpret_cast<RowVec<V> *>(tile + soa_tile_offset(K, first_row)) = c;
+    }
+};
+static __device__ __forceinline__ void tma_load_soa_tile(uint8_t *dst, const CUtensorMap *map, uint64_t *bar, int row0) {
+#pragma unroll
+    for (int box = 0; box < kSoaBoxes; ++box) tma::load_2d(dst + box * kSoaBoxBytes, map, bar, row0 + box * kSoaBoxRows, 0);
+}
+static __device__ __forceinline__ void tma_store_soa_tile(const CUtensorMap *map, const uint8_t *src, int row0) {
+#pragma unroll
+    for (int box = 0; box < kSoaBoxes; ++box) tma::store_2d(map, src + box * kSoaBoxBytes, row0 + box * kSoaBoxRows, 0);
+}
+template <int V>
+static __device__ __forceinline__ void load_bcast_soa(Tile<real, NB, V> &t, const real *__restrict__ base, int64_t ld) {
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        const real sv = __ldg(base + (int64_t)k * ld);
+#pragma unroll
+        for (int l = 0; l < V; ++l) t.v[k][l] = sv;
+    }
+}
+
+template <int OP, bool STRICT>
+__global__ void __launch_bounds__(kSoaTileThreads)
+product_kernel_soa_tma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                       const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out2,
+                       const real *__restrict__ a_row, int64_t lda, const real *__restrict__ b_row, int64_t ldb, const Coeffs mu) {
+    constexpr int V = kRowsSoA;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *tile_a = tma_smem_base(smem_raw), *tile_b = tile_a + kSoaTileBytes;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(tile_b + kSoaTileBytes);
+    const int t = threadIdx.x, row0 = blockIdx.x * kSoaTileRows;
+    if (t == 0) {
+        tma::mbar_init(bar, 1);
+        tma::mbar_expect_tx(bar, (a_row ? 0u : (uint32_t)kSoaTileBytes) + (b_row ? 0u : (uint32_t)kSoaTileBytes));
+        if (!a_row) tma_load_soa_tile(tile_a, &map_a, bar, row0);
+        if (!b_row) tma_load_soa_tile(tile_b, &map_b, bar, row0);
+    }
+    __syncthreads();
+    Tile<real, NB, V> A, B;
+    if (a_row) load_bcast_soa(A, a_row, lda);
+    if (b_row) load_bcast_soa(B, b_row, ldb);
+    tma::mbar_wait(bar, 0);
+    if (!a_row) load_soa_tile(A, tile_a, t * V);
+    if (!b_row) load_soa_tile(B, tile_b, t * V);
+    SoaTileSink<V> sink{tile_a, t * V};
+    SoaTileSink<V> sink2{tile_b, t * V};
+    (void)sink2;
+    (void)mu;
+#define LCC_OUT_BEGIN(k) { real acc[V]; real acc2[V]; _Pragma("unroll") for (int l = 0; l < V; ++l) { acc[l] = real(0); acc2[l] = real(0); }
+#define LCC_TERM(k, i, j, neg, flags)                                                                   \
+    if constexpr (term_in_op(OP, flags, k)) {                                                             \
+        _Pragma("unroll") for (int l = 0; l < V; ++l) {                                                \
+            real av = (neg) ? -A.v[i][l] : A.v[i][l];                                                  \
+            if constexpr (kRuntimeMetric) av = mul_rn(av, mu.v[(i) & (j)]);                            \
+            acc[l] = Arith<STRICT>::madd(av, B.v[j][l], acc[l]);                                       \
+            if constexpr (OP == kOpGPOuter && ((flags) & 1)) acc2[l] = Arith<STRICT>::madd(av, B.v[j][l], acc2[l]); \
+            if constexpr (two_sided(OP)) {                                                             \
+                real bv = (neg) ? -B.v[i][l] : B.v[i][l];                                              \
+                if constexpr (kRuntimeMetric) bv = mul_rn(bv, mu.v[(i) & (j)]);                        \
+                acc2[l] = Arith<STRICT>::madd(bv, A.v[j][l], acc2[l]);                                 \
+            }                                                                                          \
+        }                                                                                              \
+    }
+#define LCC_OUT_END(k) finish_two_sided<OP>(acc, acc2); sink.template put<k>(acc); if constexpr (OP == kOpGPOuter) sink2.template put<k>(acc2); }
+#include LCC_TERMS_FILE
+#undef LCC_OUT_BEGIN
+#undef LCC_TERM
+#undef LCC_OUT_END
+    tma::fence_proxy_async();
+    __syncthreads();
+    if (t == 0) {
+        tma_store_soa_tile(&map_out, tile_a, row0);
+        if constexpr (OP == kOpGPOuter) tma_store_soa_tile(&map_out2, tile_b, row0);
+        tma::store_commit_and_wait_read();
+    }
+}
+
+template <bool STRICT, bool EVEN>
+__global__ void __launch_bounds__(kSoaTileThreads)
+sandwich_kernel_soa_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_out,
+                        const Coeffs R, const Coeffs Rrev, const Coeffs mu) {
+    constexpr int V = kRowsSoA;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *tile = tma_smem_base(smem_raw);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(tile + kSoaTileBytes);
+    const int t = threadIdx.x, row0 = blockIdx.x * kSoaTileRows;
+    if (t == 0) {
+        tma::mbar_init(bar, 1);
+        tma::mbar_expect_tx(bar, (uint32_t)kSoaTileBytes);
+        tma_load_soa_tile(tile, &map_x, bar, row0);
+    }
+    __syncthreads();
+    tma::mbar_wait(bar, 0);
+    Tile<real, NB, V> X, RX;
+    load_soa_tile(X, tile, t * V);
+    (void)mu;
+#define LCC_OUT_BEGIN(k) { real acc[V]; _Pragma("unroll") for (int l = 0; l < V; ++l) acc[l] = real(0);
+#define LCC_TERM(k, i, j, neg, flags)                                                                   \
+    if constexpr (!EVEN || even_grade(i)) {                                                            \
+        real rv = (neg) ? -R.v[i] : R.v[i];                                                            \
+        if constexpr (kRuntimeMetric) rv = mul_rn(rv, mu.v[(i) & (j)]);                                \
+        _Pragma("unroll") for (int l = 0; l < V; ++l) acc[l] = Arith<STRICT>::madd(rv, X.v[j][l], acc[l]); \
+    }
+#define LCC_OUT_END(k) _Pragma("unroll") for (int l = 0; l < V; ++l) RX.v[k][l] = acc[l]; }
+#include LCC_TERMS_FILE
+#undef LCC_TERM
+#undef LCC_OUT_END
+    SoaTileSink<V> sink{tile, t * V};
+#define LCC_TERM(k, i, j, neg, flags)                                                                   \
+    if constexpr (!EVEN || even_grade(j)) {                                                            \
+        real rv = (neg) ? -Rrev.v[j] : Rrev.v[j];                                                      \
+        if constexpr (kRuntimeMetric) rv = mul_rn(rv, mu.v[(i) & (j)]);                                \
+        _Pragma("unroll") for (int l = 0; l < V; ++l) acc[l] = Arith<STRICT>::madd(RX.v[i][l], rv, acc[l]); \
+    }
+#define LCC_OUT_END(k) sink.template put<k>(acc); }
+#include LCC_TERMS_FILE
+#undef LCC_OUT_BEGIN
+#undef LCC_TERM
+#undef LCC_OUT_END
+    tma::fence_proxy_async();
+    __syncthreads();
+    if (t == 0) {
+        tma_store_soa_tile(&map_out, tile, row0);
+        tma::store_commit_and_wait_read();
+    }
+}
+
 // AoS batches of at least this many rows go through the TMA-staged kernels (below it the tensor-map
 // encode on the host costs more than the wider accesses save).  LCC_AOS_TMA=0 forces the direct-load kernels.
 constexpr int64_t kTmaMinRows = 4096;
@@ -478,44 +668,110 @@ template <bool STRICT, bool EVEN> static cudaError_t launch_sandwich_tma(const S
     }
 }
 
-template <int LAYOUT, int OP, bool STRICT> static cudaError_t launch_product_t(const ProductArgs &g) {
-    if constexpr (OP != kOpGPOuter) {
-        if (g.sum_partial) return launch_product_sum_t<LAYOUT, OP, STRICT>(g);
-    }
-    if (g.n <= 0) return cudaSuccess;
-    if constexpr (LAYOUT == kAoS) {
-        const cudaError_t e = launch_product_tma<OP, STRICT>(g);
-        if (e != cudaErrorNotSupported) return e;
-    }
+static inline bool soa_tma_enabled() {  // LCC_SOA_TMA=0 forces the direct-load SoA kernels
+    static const bool on = [] { const char *e = std::getenv("LCC_SOA_TMA"); return !(e && e[0] == '0'); }();
+    return on;
+}
+static inline bool soa_map(CUtensorMap *m, const void *base, int64_t ld, int64_t n) {
+    return make_soa_tensor_map(m, base, (int)sizeof(real), NB, ld, n, kSoaBoxRows);
+}
+
+template <int OP, bool STRICT> static cudaError_t launch_product_soa_tma(const ProductArgs &g) {
+    if (!soa_tma_enabled() || g.n < kTmaMinRows) return cudaErrorNotSupported;
+    CUtensorMap ma, mb, mo, mo2;
+    if (!soa_map(&mo, g.out, g.ldo, g.n)) return cudaErrorNotSupported;
+    ma = mb = mo2 = mo;
+    if (!g.a_bcast && !soa_map(&ma, g.a, g.lda, g.n)) return cudaErrorNotSupported;
+    if (!g.b_bcast && !soa_map(&mb, g.b, g.ldb, g.n)) return cudaErrorNotSupported;
+    if (OP == kOpGPOuter && !soa_map(&mo2, g.out2, g.ldo2, g.n)) return cudaErrorNotSupported;
+    auto kernel = product_kernel_soa_tma<OP, STRICT>;
+    constexpr int smem = 2 * kSoaTileBytes + 1024 + 16;
+    static const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (attr != cudaSuccess) return attr;
+    const unsigned grid = (unsigned)((g.n + kSoaTileRows - 1) / kSoaTileRows);
+    kernel<<<grid, kSoaTileThreads, smem, g.stream>>>(ma, mb, mo, mo2, g.a_bcast ? (const real *)g.a : nullptr, g.lda,
+                                                     g.b_bcast ? (const real *)g.b : nullptr, g.ldb, to_coeffs(g.mu, 1.0));
+    note_kernel_launch();
+    return cudaGetLastError();
+}
+
+template <bool STRICT, bool EVEN> static cudaError_t launch_sandwich_soa_tma(const SandwichArgs &g, const Coeffs &R, const Coeffs &Rrev) {
+    if (!soa_tma_enabled() || g.n < kTmaMinRows) return cudaErrorNotSupported;
+    CUtensorMap mx, mo;
+    if (!soa_map(&mx, g.x, g.ldx, g.n) || !soa_map(&mo, g.out, g.ldo, g.n)) return cudaErrorNotSupported;
+    constexpr int smem = kSoaTileBytes + 1024 + 16;
+    const unsigned grid = (unsigned)((g.n + kSoaTileRows - 1) / kSoaTileRows);
+    sandwich_kernel_soa_tma<STRICT, EVEN><<<grid, kSoaTileThreads, smem, g.stream>>>(mx, mo, R, Rrev, to_coeffs(g.mu, 1.0));
+    note_kernel_launch();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------ entry points, by part
+// One (signature, precision) is compiled as several object files so that ptxas runs in parallel
+// (_build.py writes one stub per part):
+//   LCC_PART 1  product kernels with direct loads            (LCC_PART_STRICT = 0 / 1)
+//   LCC_PART 2  product kernels on TMA tiles, AoS and SoA    (LCC_PART_STRICT = 0 / 1)
+//   LCC_PART 3  sandwich kernels, direct and TMA             (LCC_PART_STRICT = 0 / 1)
+//   LCC_PART 4  fused product + batch-sum kernels and the two routers the dispatcher calls
+cudaError_t product_direct_s0(const ProductArgs &g);
+cudaError_t product_direct_s1(const ProductArgs &g);
+cudaError_t product_tma_s0(const ProductArgs &g);  // cudaErrorNotSupported: operands do not qualify, use the direct kernels
+cudaError_t product_tma_s1(const ProductArgs &g);
+cudaError_t sandwich_s0(const SandwichArgs &g);
+cudaError_t sandwich_s1(const SandwichArgs &g);
+cudaError_t launch_product(const ProductArgs &g);
+cudaError_t launch_sandwich(const SandwichArgs &g);
+
+#ifndef LCC_PART
+#error "define LCC_PART (1-4) before including product_impl.cuh"
+#endif
+#ifndef LCC_PART_STRICT
+#define LCC_PART_STRICT 0
+#endif
+#define LCC_CAT_(a, b) a##b
+#define LCC_CAT(a, b) LCC_CAT_(a, b)
+constexpr bool kPartStrict = LCC_PART_STRICT != 0;
+
+#define LCC_FOR_EACH_PRODUCT_OP(X) \
+    X(kOpGP) X(kOpOuter) X(kOpLC) X(kOpGPOuter) X(kOpRC) X(kOpScalar) X(kOpCommutator) X(kOpAnticommutator)
+
+#if LCC_PART == 1
+template <int LAYOUT, int OP> static cudaError_t launch_product_direct_t(const ProductArgs &g) {
     constexpr int W = 16 / (int)sizeof(real);
     int vec_ok = 1;
     if (LAYOUT == kAoS) {
         auto ok = [&](const void *p, int64_t ld) { return ((uintptr_t)p % 16 == 0) && (ld % W == 0); };
         vec_ok = ok(g.a, g.lda) && ok(g.b, g.ldb) && ok(g.out, g.ldo) && (OP != kOpGPOuter || ok(g.out2, g.ldo2));
     }
-    product_kernel<LAYOUT, OP, STRICT><<<grid_for<LAYOUT>(g.n), block_threads(), 0, g.stream>>>(
+    product_kernel<LAYOUT, OP, kPartStrict><<<grid_for<LAYOUT>(g.n), block_threads(), 0, g.stream>>>(
         (const real *)g.a, g.lda, g.a_bcast, (const real *)g.b, g.ldb, g.b_bcast, (real *)g.out, g.ldo,
         (real *)g.out2, g.ldo2, g.n, vec_ok, to_coeffs(g.mu, 1.0));
     note_kernel_launch();
     return cudaGetLastError();
 }
-
-template <int LAYOUT, bool STRICT> static cudaError_t launch_product_op(const ProductArgs &g) {
+cudaError_t LCC_CAT(product_direct_s, LCC_PART_STRICT)(const ProductArgs &g) {
     switch (g.op) {
-        case kOpGP: return launch_product_t<LAYOUT, kOpGP, STRICT>(g);
-        case kOpOuter: return launch_product_t<LAYOUT, kOpOuter, STRICT>(g);
-        case kOpLC: return launch_product_t<LAYOUT, kOpLC, STRICT>(g);
-        case kOpGPOuter: return launch_product_t<LAYOUT, kOpGPOuter, STRICT>(g);
+#define LCC_X(OPV) case OPV: return g.layout == kSoA ? launch_product_direct_t<kSoA, OPV>(g) : launch_product_direct_t<kAoS, OPV>(g);
+        LCC_FOR_EACH_PRODUCT_OP(LCC_X)
+#undef LCC_X
     }
     return cudaErrorInvalidValue;
 }
+#endif  // LCC_PART == 1
 
-static cudaError_t launch_product(const ProductArgs &g) {
-    if (g.layout == kSoA) return g.strict ? launch_product_op<kSoA, true>(g) : launch_product_op<kSoA, false>(g);
-    return g.strict ? launch_product_op<kAoS, true>(g) : launch_product_op<kAoS, false>(g);
+#if LCC_PART == 2
+cudaError_t LCC_CAT(product_tma_s, LCC_PART_STRICT)(const ProductArgs &g) {
+    switch (g.op) {
+#define LCC_X(OPV) case OPV: return g.layout == kSoA ? launch_product_soa_tma<OPV, kPartStrict>(g) : launch_product_tma<OPV, kPartStrict>(g);
+        LCC_FOR_EACH_PRODUCT_OP(LCC_X)
+#undef LCC_X
+    }
+    return cudaErrorInvalidValue;
 }
+#endif  // LCC_PART == 2
 
-template <int LAYOUT, bool STRICT, bool EVEN> static cudaError_t launch_sandwich_t(const SandwichArgs &g) {
+#if LCC_PART == 3
+template <int LAYOUT, bool EVEN> static cudaError_t launch_sandwich_t(const SandwichArgs &g) {
     if (g.n <= 0) return cudaSuccess;
     constexpr int W = 16 / (int)sizeof(real);
     int vec_ok = 1;
@@ -529,23 +785,44 @@ template <int LAYOUT, bool STRICT, bool EVEN> static cudaError_t launch_sandwich
         Rrev.v[i] = R.v[i] * ((grade % 4 < 2) ? real(1) : real(-1));
     }
     if constexpr (LAYOUT == kAoS) {
-        const cudaError_t e = launch_sandwich_tma<STRICT, EVEN>(g, R, Rrev);
+        const cudaError_t e = launch_sandwich_tma<kPartStrict, EVEN>(g, R, Rrev);
+        if (e != cudaErrorNotSupported) return e;
+    } else {
+        const cudaError_t e = launch_sandwich_soa_tma<kPartStrict, EVEN>(g, R, Rrev);
         if (e != cudaErrorNotSupported) return e;
     }
-    sandwich_kernel<LAYOUT, STRICT, EVEN><<<grid_for<LAYOUT>(g.n), block_threads(), 0, g.stream>>>(
+    sandwich_kernel<LAYOUT, kPartStrict, EVEN><<<grid_for<LAYOUT>(g.n), block_threads(), 0, g.stream>>>(
         (const real *)g.x, g.ldx, (real *)g.out, g.ldo, g.n, vec_ok, R, Rrev, to_coeffs(g.mu, 1.0));
     note_kernel_launch();
     return cudaGetLastError();
 }
-
-template <int LAYOUT> static cudaError_t launch_sandwich_l(const SandwichArgs &g) {
-    if (g.strict) return g.even ? launch_sandwich_t<LAYOUT, true, true>(g) : launch_sandwich_t<LAYOUT, true, false>(g);
-    return g.even ? launch_sandwich_t<LAYOUT, false, true>(g) : launch_sandwich_t<LAYOUT, false, false>(g);
+cudaError_t LCC_CAT(sandwich_s, LCC_PART_STRICT)(const SandwichArgs &g) {
+    if (g.layout == kSoA) return g.even ? launch_sandwich_t<kSoA, true>(g) : launch_sandwich_t<kSoA, false>(g);
+    return g.even ? launch_sandwich_t<kAoS, true>(g) : launch_sandwich_t<kAoS, false>(g);
 }
+#endif  // LCC_PART == 3
 
-static cudaError_t launch_sandwich(const SandwichArgs &g) {
-    return g.layout == kSoA ? launch_sandwich_l<kSoA>(g) : launch_sandwich_l<kAoS>(g);
+#if LCC_PART == 4
+template <int LAYOUT, bool STRICT> static cudaError_t launch_product_sum_op(const ProductArgs &g) {
+    switch (g.op) {
+        case kOpGP: return launch_product_sum_t<LAYOUT, kOpGP, STRICT>(g);
+        case kOpOuter: return launch_product_sum_t<LAYOUT, kOpOuter, STRICT>(g);
+        case kOpLC: return launch_product_sum_t<LAYOUT, kOpLC, STRICT>(g);
+    }
+    return cudaErrorInvalidValue;
 }
+cudaError_t launch_product(const ProductArgs &g) {
+    if (g.sum_partial) {
+        if (g.layout == kSoA) return g.strict ? launch_product_sum_op<kSoA, true>(g) : launch_product_sum_op<kSoA, false>(g);
+        return g.strict ? launch_product_sum_op<kAoS, true>(g) : launch_product_sum_op<kAoS, false>(g);
+    }
+    if (g.n <= 0) return cudaSuccess;
+    const cudaError_t e = g.strict ? product_tma_s1(g) : product_tma_s0(g);
+    if (e != cudaErrorNotSupported) return e;
+    return g.strict ? product_direct_s1(g) : product_direct_s0(g);
+}
+cudaError_t launch_sandwich(const SandwichArgs &g) { return g.strict ? sandwich_s1(g) : sandwich_s0(g); }
+#endif  // LCC_PART == 4
 
 }  // namespace LCC_TU
 }  // namespace lcc

@@ -83,4 +83,9 @@ __device__ __forceinline__ void prefetch_map(const CUtensorMap *map) {
 bool make_aos_tensor_map(CUtensorMap *map, const void *base, int elem_bytes, int nb, int64_t ld, int64_t n,
                          int span_bytes, int rows);
 
+// Blade-major (SoA) batch: element (row r, blade k) at base[k*ld + r].  Tensor = (n rows, nb blades) with
+// the rows contiguous; box = (rows, nb), no swizzle (a thread reads consecutive rows of one blade, so
+// neighbouring threads already hit neighbouring banks).  Rows beyond n are zero-filled / clipped.
+bool make_soa_tensor_map(CUtensorMap *map, const void *base, int elem_bytes, int nb, int64_t ld, int64_t n, int rows);
+
 }  // namespace lcc

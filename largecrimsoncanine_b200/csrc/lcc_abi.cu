@@ -212,9 +212,11 @@ lcc_status same_kind(const lcc_view *a, const lcc_view *b, const char *what) {
 
 // Device copy of a gather-form sign table for the table-driven kernel.
 //   forward  (kind = op):        out[k] = sum_i S[i][i^k] a[i] b[i^k]              G[k][i] = S[i][i^k]
-//   VJP wrt a (kind = 3 + op):   ga[i]  = sum_k' S[i][i^k'] g[k'] b[k'^i]           G[i][k'] = S[i][i^k']  (x = g, y = b)
-//   VJP wrt b (kind = 6 + op):   gb[j]  = sum_i  S[i][j]    a[i]  g[i^j]            G[j][i]  = S[i][j]     (x = a, y = g)
-// each restricted to the op's term set ((i&j)==0 outer, (i&j)==i left contraction; batch.rs:555,636).
+//   VJP wrt a (kind = 16 + op):  ga[i]  = sum_k' S[i][i^k'] g[k'] b[k'^i]           G[i][k'] = S[i][i^k']  (x = g, y = b)
+//   VJP wrt b (kind = 32 + op):  gb[j]  = sum_i  S[i][j]    a[i]  g[i^j]            G[j][i]  = S[i][j]     (x = a, y = g)
+//   kind = 48: the plain sign table sign[a*nb+b]
+// each restricted to the op's term set ((i&j)==0 outer, (i&j)==i left contraction, (i&j)==j right contraction,
+// i==j scalar product; batch.rs:555,636, multivector.rs:1647,1697).
 lcc_status gather_signs_on_device(const lcc_algebra *calg, int kind, const int8_t **out) {
     lcc_algebra *alg = const_cast<lcc_algebra *>(calg);
     int dev = 0;
@@ -223,8 +225,11 @@ lcc_status gather_signs_on_device(const lcc_algebra *calg, int kind, const int8_
     auto key = std::make_pair(dev, kind);
     auto it = alg->gather_signs_dev.find(key);
     if (it != alg->gather_signs_dev.end()) { *out = it->second; return LCC_OK; }
-    const int nb = alg->nb, op = kind % 3, which = kind / 3;  // which == 3: the plain sign table sign[a*nb+b]
-    auto in_op = [&](int i, int j) { return op == kOpGP || (op == kOpOuter && (i & j) == 0) || (op == kOpLC && (i & j) == i); };
+    const int nb = alg->nb, op = kind % 16, which = kind / 16;  // which == 3: the plain sign table sign[a*nb+b]
+    auto in_op = [&](int i, int j) {
+        return op == kOpGP || (op == kOpOuter && (i & j) == 0) || (op == kOpLC && (i & j) == i) || (op == kOpRC && (i & j) == j) ||
+               (op == kOpScalar && i == j);
+    };
     auto S = [&](int i, int j) -> int8_t { return in_op(i, j) ? alg->signs[(size_t)i * nb + j] : (int8_t)0; };
     std::vector<int8_t> g((size_t)nb * nb);
     for (int o = 0; o < nb; ++o)
@@ -476,7 +481,7 @@ static lcc_status run_product(const lcc_algebra *alg, int op, const lcc_view *a,
     if (!tensor_path_off && op == kOpGP && !strict && a->dtype == LCC_F32 && a->layout == LCC_SOA && (a_bc != b_bc) &&
         (alg->nb == 64 || alg->nb == 128 || alg->nb == 256)) {
         const int8_t *signs_dev = nullptr;
-        LCC_TRY(gather_signs_on_device(alg, 9, &signs_dev));
+        LCC_TRY(gather_signs_on_device(alg, 48, &signs_dev));
         PoolBuffer w;
         LCC_TRY(w.alloc((size_t)2 * alg->nb * alg->nb * sizeof(float), s));
         const lcc_view *fixed = a_bc ? a : b, *batch = a_bc ? b : a;
@@ -492,13 +497,54 @@ static lcc_status run_product(const lcc_algebra *alg, int op, const lcc_view *a,
         return LCC_OK;
     };
     if (op == kOpGPOuter) { LCC_TRY(one(kOpGP, out)); return one(kOpOuter, out2); }
+    if (op == kOpCommutator || op == kOpAnticommutator) {
+        // composed exactly as the reference does (multivector.rs:1732-1768): a*b, b*a, -/+, scale(0.5)
+        PoolBuffer tmp;
+        lcc_view ba = *out;
+        LCC_TRY(tmp.alloc((size_t)(out->layout == LCC_SOA ? alg->nb * out->ld : out->n * out->ld) * elem_size(out->dtype), s));
+        ba.data = tmp.ptr;
+        const int8_t *gs = nullptr;
+        LCC_TRY(gather_signs_on_device(alg, kOpGP, &gs));
+        LCC_CUDA(launch_table_product(alg->nb, strict, arg_of(a), a_bc, arg_of(b), b_bc, arg_of(out), gs, s));
+        LCC_CUDA(launch_table_product(alg->nb, strict, arg_of(b), b_bc, arg_of(a), a_bc, arg_of(&ba), gs, s));
+        LCC_CUDA(launch_addsub(alg->nb, op == kOpCommutator ? LCC_EW_SUB : LCC_EW_ADD, arg_of(out), false, arg_of(&ba), false, arg_of(out), s));
+        return lcc_batch_scale(alg, out, 0.5, out, (void *)s);
+    }
     return one(op, out);
+}
+
+// A v B = undual(dual(A) ^ dual(B)), multivector.rs:1781-1794; LCC_ERR_VALUE when the pseudoscalar is null
+// (every PGA), which is what Multivector::dual raises.
+static lcc_status run_regressive(const lcc_algebra *alg, const lcc_view *a, const lcc_view *b, const lcc_view *out,
+                                 unsigned flags, void *stream) {
+    LCC_TRY(check_view(alg, a, "a"));
+    LCC_TRY(check_view(alg, b, "b"));
+    LCC_TRY(check_view(alg, out, "out"));
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    auto bytes_of = [&](const lcc_view *v) { return (size_t)(v->layout == LCC_SOA ? alg->nb * v->ld : v->n * v->ld) * elem_size(v->dtype); };
+    PoolBuffer ta, tb, tw;
+    lcc_view da = *a, db = *b, w = *out;
+    LCC_TRY(ta.alloc(bytes_of(a), s));
+    LCC_TRY(tb.alloc(bytes_of(b), s));
+    LCC_TRY(tw.alloc(bytes_of(out), s));
+    da.data = ta.ptr; db.data = tb.ptr; w.data = tw.ptr;
+    LCC_TRY(lcc_batch_unary(alg, LCC_UN_DUAL, 0, a, &da, (void *)s));
+    LCC_TRY(lcc_batch_unary(alg, LCC_UN_DUAL, 0, b, &db, (void *)s));
+    LCC_TRY(run_product(alg, kOpOuter, &da, &db, &w, nullptr, flags, (void *)s));
+    return lcc_batch_unary(alg, LCC_UN_UNDUAL, 0, &w, out, (void *)s);
 }
 
 lcc_status lcc_batch_product(const lcc_algebra *alg, int op, const lcc_view *a, const lcc_view *b, const lcc_view *out,
                              unsigned flags, void *stream) {
-    if (op != LCC_OP_GP && op != LCC_OP_OUTER && op != LCC_OP_LC) return fail(LCC_ERR_VALUE, "unknown product op %d", op);
-    return run_product(alg, op, a, b, out, nullptr, flags, stream);
+    switch (op) {
+        case LCC_OP_GP: case LCC_OP_OUTER: case LCC_OP_LC: case LCC_OP_RC: case LCC_OP_SCALAR:
+        case LCC_OP_COMMUTATOR: case LCC_OP_ANTICOMMUTATOR:
+            return run_product(alg, op, a, b, out, nullptr, flags, stream);
+        case LCC_OP_REGRESSIVE:
+            return run_regressive(alg, a, b, out, flags, stream);
+    }
+    return fail(LCC_ERR_VALUE, "unknown product op %d", op);
 }
 
 lcc_status lcc_batch_gp_outer(const lcc_algebra *alg, const lcc_view *a, const lcc_view *b, const lcc_view *gp_out,
@@ -567,7 +613,7 @@ lcc_status lcc_batch_product_vjp(const lcc_algebra *alg, int op, int wrt, const 
     cudaStream_t s;
     LCC_TRY(resolve_stream(stream, &s));
     const int8_t *gs = nullptr;
-    LCC_TRY(gather_signs_on_device(alg, 3 + 3 * wrt + op, &gs));
+    LCC_TRY(gather_signs_on_device(alg, 16 + 16 * wrt + op, &gs));
     const bool strict = (flags & LCC_FLAG_STRICT_FP) != 0, other_bc = other->n == 1 && grad_out->n > 1;
     if (wrt == 0) LCC_CUDA(launch_table_product(alg->nb, strict, arg_of(grad_out), false, arg_of(other), other_bc, arg_of(grad_in), gs, s));
     else LCC_CUDA(launch_table_product(alg->nb, strict, arg_of(other), other_bc, arg_of(grad_out), false, arg_of(grad_in), gs, s));

@@ -140,6 +140,15 @@ struct Multivector {
         }
         return like(device_pair_product(get_algebra(), op, coeffs, o.coeffs));
     }
+    // commutator / anticommutator / regressive test the dimension only (src/multivector.rs:1733-1739,1782-1788)
+    Multivector product_same_dims(int op, const Multivector &o) const {
+        if (dims != o.dims) {
+            std::ostringstream s;
+            s << "dimension mismatch: left operand is Cl(" << dims << ") but right operand is Cl(" << o.dims << "); both multivectors must have the same dimension";
+            throw py::value_error(s.str());
+        }
+        return product(op, o);
+    }
     Multivector reverse() const {  // src/multivector.rs:2711-2726
         std::vector<double> c(coeffs.size());
         for (size_t i = 0; i < c.size(); ++i) c[i] = coeffs[i] * reverse_sign(popcount((unsigned)i));
@@ -634,6 +643,17 @@ PYBIND11_MODULE(largecrimsoncanine, m) {
         .def("left_contraction", [](const Multivector &a, const Multivector &b) { return a.product(LCC_OP_LC, b); })
         .def("inner", [](const Multivector &a, const Multivector &b) { return a.product(LCC_OP_LC, b); })
         .def("lc", [](const Multivector &a, const Multivector &b) { return a.product(LCC_OP_LC, b); })
+        // the rest of the product family, src/multivector.rs:1616-1797
+        .def("right_contraction", [](const Multivector &a, const Multivector &b) { return a.product(LCC_OP_RC, b); })
+        .def("rc", [](const Multivector &a, const Multivector &b) { return a.product(LCC_OP_RC, b); })
+        .def("scalar_product", [](const Multivector &a, const Multivector &b) { return a.product(LCC_OP_SCALAR, b); })
+        .def("dot", [](const Multivector &a, const Multivector &b) { return a.product(LCC_OP_SCALAR, b); })
+        .def("commutator", [](const Multivector &a, const Multivector &b) { return a.product_same_dims(LCC_OP_COMMUTATOR, b); })
+        .def("x", [](const Multivector &a, const Multivector &b) { return a.product_same_dims(LCC_OP_COMMUTATOR, b); })
+        .def("anticommutator", [](const Multivector &a, const Multivector &b) { return a.product_same_dims(LCC_OP_ANTICOMMUTATOR, b); })
+        .def("regressive", [](const Multivector &a, const Multivector &b) { return a.product_same_dims(LCC_OP_REGRESSIVE, b); })
+        .def("meet", [](const Multivector &a, const Multivector &b) { return a.product_same_dims(LCC_OP_REGRESSIVE, b); })
+        .def("vee", [](const Multivector &a, const Multivector &b) { return a.product_same_dims(LCC_OP_REGRESSIVE, b); })
         .def("reverse", &Multivector::reverse)
         .def("tilde", &Multivector::reverse)
         .def("__invert__", &Multivector::reverse)
@@ -1070,6 +1090,15 @@ PYBIND11_MODULE(largecrimsoncanine, m) {
         .def("left_contraction", [](const Batch &a, const Batch &b) { return batch_product(a, b, LCC_OP_LC); })
         .def("inner", [](const Batch &a, const Batch &b) { return batch_product(a, b, LCC_OP_LC); })
         .def("lc", [](const Batch &a, const Batch &b) { return batch_product(a, b, LCC_OP_LC); })
+        // batched forms of the rest of the scalar product family (src/multivector.rs:1616-1797); new surface
+        .def("right_contraction", [](const Batch &a, const Batch &b) { return batch_product(a, b, LCC_OP_RC); })
+        .def("rc", [](const Batch &a, const Batch &b) { return batch_product(a, b, LCC_OP_RC); })
+        .def("scalar_product", [](const Batch &a, const Batch &b) { return batch_product(a, b, LCC_OP_SCALAR); })
+        .def("dot", [](const Batch &a, const Batch &b) { return batch_product(a, b, LCC_OP_SCALAR); })
+        .def("commutator", [](const Batch &a, const Batch &b) { return batch_product(a, b, LCC_OP_COMMUTATOR); })
+        .def("anticommutator", [](const Batch &a, const Batch &b) { return batch_product(a, b, LCC_OP_ANTICOMMUTATOR); })
+        .def("regressive", [](const Batch &a, const Batch &b) { return batch_product(a, b, LCC_OP_REGRESSIVE); })
+        .def("meet", [](const Batch &a, const Batch &b) { return batch_product(a, b, LCC_OP_REGRESSIVE); })
         .def("sandwich", &batch_sandwich)
         .def("apply", &batch_sandwich)
         .def("norm", [](const Batch &a) { return batch_norm(a, LCC_NORM); })

@@ -223,9 +223,32 @@ class OracleAlgebra:
     def left_contraction(self, a, b, **kw):
         return self._product(2, a, b, **kw)
 
+    def right_contraction(self, a, b, **kw):
+        """Row-wise Multivector::right_contraction, src/multivector.rs:1616-1661."""
+        return self._product(3, a, b, **kw)
+
+    def scalar_product(self, a, b, **kw):
+        """Row-wise Multivector::scalar_product, src/multivector.rs:1673-1715 (blade 0 only, others 0)."""
+        return self._product(4, a, b, **kw)
+
+    def commutator(self, a, b):
+        """(a*b - b*a).scale(0.5), src/multivector.rs:1732-1745 (each step rounded separately)."""
+        return self.scale(self.sub(self.geometric_product(a, b), self.geometric_product(b, a)), 0.5)
+
+    def anticommutator(self, a, b):
+        """(a*b + b*a).scale(0.5), src/multivector.rs:1755-1768."""
+        return self.scale(self.add(self.geometric_product(a, b), self.geometric_product(b, a)), 0.5)
+
+    def regressive(self, a, b):
+        """undual(dual(a) ^ dual(b)), src/multivector.rs:1781-1794; ValueError when the pseudoscalar is null."""
+        a, b = _arr(a), _arr(b)
+        dt = a.dtype
+        w = self.outer_product(self.dual(a).astype(dt), self.dual(b).astype(dt))
+        return self.undual(w).astype(dt)
+
     def product_abs_bound(self, op, a, b):
         """sum_i |a_i||b_j| over the op's term set: the scale tolerance tests divide errors by."""
-        return self._product({"gp": 0, "outer": 1, "lc": 2}[op], a, b, absmode=True)
+        return self._product({"gp": 0, "outer": 1, "lc": 2, "rc": 3, "scalar": 4}[op], a, b, absmode=True)
 
     def sandwich(self, rotor, x, threads=1):
         x = _arr(x)

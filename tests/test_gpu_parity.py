@@ -512,3 +512,95 @@ def test_aos_batches_through_tma_tiles(L, sig, dt):
             assert np.array_equal(got[:, :nb], o.sandwich(rotor, a)), (n, pad)
             assert np.all(got[:, nb:] == 7.0)
         dev.free()
+
+
+@pytest.mark.parametrize("sig", [(3, 0, 0), (3, 0, 1), (4, 1, 0), (1, 3, 0), (2, 1, 1), (1, 0, 0), (5, 0, 0)])
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_soa_batches_through_tma_tiles(L, strict, sig, dt):
+    """Device-resident (blade-major) batches of >= 4096 rows take the TMA-staged SoA kernels: ragged last
+    tile, broadcast operands, fused dual output and sandwich, bit-exact in strict mode."""
+    alg, o = algebras(L, sig)
+    nb = o.num_blades
+    rng = np.random.default_rng(29)
+    for n in (4096, 4099, 9001):
+        a, b = rand(rng, n, nb, dt), rand(rng, n, nb, dt)
+        A, B = L.MultivectorBatch.from_numpy(alg, a), L.MultivectorBatch.from_numpy(alg, b)
+        assert np.array_equal(A.geometric_product(B).to_numpy(), o.geometric_product(a, b))
+        assert np.array_equal(A.outer_product(B).to_numpy(), o.outer_product(a, b))
+        assert np.array_equal(A.left_contraction(B).to_numpy(), o.left_contraction(a, b))
+        g, w = A.gp_and_outer(B)
+        assert np.array_equal(g.to_numpy(), o.geometric_product(a, b)) and np.array_equal(w.to_numpy(), o.outer_product(a, b))
+        one = rand(rng, 1, nb, dt)
+        One = L.MultivectorBatch.from_numpy(alg, one)
+        assert np.array_equal(One.geometric_product(B).to_numpy(), o.geometric_product(one, b))
+        assert np.array_equal(A.outer_product(One).to_numpy(), o.outer_product(a, one))
+        dense = rng.standard_normal(nb)
+        even = dense * np.array([1.0 if bin(i).count("1") % 2 == 0 else 0.0 for i in range(nb)])
+        for rotor in (dense, even):
+            assert np.array_equal(A.sandwich(rotor_mv(L, alg, rotor)).to_numpy(), o.sandwich(rotor, a))
+        # inputs must be left untouched by the in-place tile reuse
+        assert np.array_equal(A.to_numpy(), a) and np.array_equal(B.to_numpy(), b)
+
+
+# ----------------------------------------------------------------------------------------------- rest of the product family
+@pytest.mark.parametrize("sig", [(3, 0, 0), (3, 0, 1), (4, 1, 0), (1, 3, 0), (2, 1, 1), (2, 0, 0), (6, 0, 0)])
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_product_family_batched(L, sig, dt):
+    """Batched forms of Multivector::{right_contraction, scalar_product, commutator, anticommutator,
+    regressive} (src/multivector.rs:1616-1797): bit-exact in strict mode (direct and TMA-tile kernels),
+    within tolerance in FMA mode, broadcast rule, and the reference's error for a null pseudoscalar."""
+    alg, o = algebras(L, sig)
+    nb = o.num_blades
+    rng = np.random.default_rng(37)
+    degenerate = sig[2] > 0
+    for n in ((3, 300) if nb > 32 else (1, 77, 1030, 4100)):
+        a, b = rand(rng, n, nb, dt), rand(rng, n, nb, dt)
+        A, B = L.MultivectorBatch.from_numpy(alg, a), L.MultivectorBatch.from_numpy(alg, b)
+        L.set_strict_fp(True)
+        try:
+            assert np.array_equal(A.right_contraction(B).to_numpy(), o.right_contraction(a, b))
+            assert np.array_equal(A.rc(B).to_numpy(), o.right_contraction(a, b))
+            assert np.array_equal(A.scalar_product(B).to_numpy(), o.scalar_product(a, b))
+            assert np.array_equal(A.commutator(B).to_numpy(), o.commutator(a, b))
+            assert np.array_equal(A.anticommutator(B).to_numpy(), o.anticommutator(a, b))
+            if degenerate:
+                with pytest.raises(ValueError):
+                    A.regressive(B)
+            else:
+                assert np.array_equal(A.regressive(B).to_numpy(), o.regressive(a, b))
+                assert np.array_equal(A.meet(B).to_numpy(), o.regressive(a, b))
+        finally:
+            L.set_strict_fp(False)
+        assert_close(A.right_contraction(B).to_numpy(), o.right_contraction(a, b), o.product_abs_bound("rc", a, b), dt)
+        assert_close(A.scalar_product(B).to_numpy(), o.scalar_product(a, b), o.product_abs_bound("scalar", a, b), dt)
+        gpb = o.product_abs_bound("gp", a, b)
+        assert_close(A.commutator(B).to_numpy(), o.commutator(a, b), gpb, dt)
+        assert_close(A.anticommutator(B).to_numpy(), o.anticommutator(a, b), gpb, dt)
+    one = rand(rng, 1, nb, dt)
+    One = L.MultivectorBatch.from_numpy(alg, one)
+    L.set_strict_fp(True)
+    try:
+        assert np.array_equal(One.commutator(B).to_numpy(), o.commutator(one, b))
+        assert np.array_equal(A.right_contraction(One).to_numpy(), o.right_contraction(a, one))
+    finally:
+        L.set_strict_fp(False)
+
+
+def test_product_family_scalar_multivectors(L):
+    """The per-object methods go through the same kernels with n = 1 (known answers of
+    /root/reference/tests/test_basic.py:2275-2316,2369-2378,2407-2418,2528-2557)."""
+    M = L.Multivector
+    a, b = M.from_vector([1.0, 2.0, 3.0]), M.from_vector([4.0, 5.0, 6.0])
+    assert a.right_contraction(b).scalar() == 32.0
+    e12, e13, e1 = M.from_bivector([1.0, 0.0, 0.0], dims=3), M.from_bivector([0.0, 1.0, 0.0], dims=3), M.from_vector([1.0, 0.0, 0.0])
+    assert e12.rc(e1).approx_eq(M.from_vector([0.0, -1.0, 0.0]))
+    assert e12.scalar_product(e12).scalar() == -1.0 and e12.dot(e12).scalar() == -1.0
+    f1, f2 = M.from_vector([1.0, 0.0]), M.from_vector([0.0, 1.0])
+    assert f1.commutator(f2).approx_eq(M.from_bivector([1.0], dims=2)) and f1.x(f2).approx_eq(f1.commutator(f2))
+    assert f1.anticommutator(f1).scalar() == 1.0
+    meet = e12.regressive(e13)
+    assert meet.grade(1).norm() > 0.1 and meet.approx_eq(meet.grade(1)) and e12.meet(e13).approx_eq(meet) and e12.vee(e13).approx_eq(meet)
+    with pytest.raises(ValueError, match="dimension mismatch"):
+        a.commutator(f1)
+    with pytest.raises(ValueError, match="algebra mismatch"):
+        a.right_contraction(f1)

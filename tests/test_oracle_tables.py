@@ -151,3 +151,50 @@ def test_tables_match_reference_python_builders(golden):
         if tag + ".codegen_signs" in golden:
             assert np.array_equal(golden[tag + ".codegen_signs"].ravel(), alg.signs_int8())
             assert np.array_equal(golden[tag + ".codegen_blades"].ravel(), alg.blades_u16())
+
+
+# ----------------------------------------------------------------------------- rest of the product family
+def _vec3(x, y, z):
+    v = np.zeros((1, 8))
+    v[0, [1, 2, 4]] = (x, y, z)
+    return v
+
+
+def _blade(nb, index, value=1.0):
+    v = np.zeros((1, nb))
+    v[0, index] = value
+    return v
+
+
+def test_product_family_known_answers_of_the_reference_tests():
+    """Pins oracle ops 3/4 and the composed commutator / anticommutator / regressive to the known answers
+    of the reference's own scalar tests (tests/test_basic.py:2275-2316 right contraction, :2345-2402 scalar
+    product, :2407-2520 commutator / anticommutator, :2528-2557 regressive)."""
+    o = oracle.OracleAlgebra(3, 0, 0)
+    a, b = _vec3(1, 2, 3), _vec3(4, 5, 6)
+    rc = o.right_contraction(a, b)
+    assert rc[0, 0] == 32.0 and not rc[0, 1:].any()
+    e12, e13, e1, e2 = _blade(8, 3), _blade(8, 5), _blade(8, 1), _blade(8, 2)
+    assert np.array_equal(o.right_contraction(e12, e1), -e2)              # e12 |_ e1 = -e2
+    assert not o.right_contraction(e1, e12).any()                         # grade(A) < grade(B) => 0
+    assert np.array_equal(o.left_contraction(e1, e12), e2)
+    sp = o.scalar_product(e12, e12)
+    assert sp[0, 0] == -1.0 and not sp[0, 1:].any()
+    assert o.scalar_product(a, b)[0, 0] == 32.0
+    assert not o.scalar_product(e1, e12).any()
+    o2 = oracle.OracleAlgebra(2, 0, 0)
+    f1, f2 = _blade(4, 1), _blade(4, 2)
+    assert np.array_equal(o2.commutator(f1, f2), _blade(4, 3))            # [e1, e2] = e12
+    assert not o2.commutator(f1, f1).any()
+    assert not o2.anticommutator(f1, f2).any()
+    assert np.array_equal(o2.anticommutator(f1, f1), _blade(4, 0))
+    rng = np.random.default_rng(5)
+    x, y = rng.standard_normal((7, 8)), rng.standard_normal((7, 8))
+    assert np.allclose(o.commutator(x, y), -o.commutator(y, x), atol=1e-15)
+    assert np.allclose(o.commutator(x, y) + o.anticommutator(x, y), o.geometric_product(x, y), atol=1e-14)
+    ps = _blade(8, 7)
+    assert np.allclose(o.regressive(ps, a), a, atol=1e-15)                # I v A = A
+    meet = o.regressive(e12, e13)                                         # two planes meet in the e1 axis
+    assert abs(meet[0, 1]) == 1.0 and not np.delete(meet[0], 1).any()
+    with pytest.raises(ValueError):                                       # null pseudoscalar: dual() raises
+        oracle.OracleAlgebra(3, 0, 1).regressive(np.ones((1, 16)), np.ones((1, 16)))
