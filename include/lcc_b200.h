@@ -225,6 +225,12 @@ LCC_API lcc_status lcc_pga_points_embed(const lcc_algebra *alg, const void *xyz,
 LCC_API lcc_status lcc_pga_points_extract(const lcc_algebra *alg, const lcc_view *src, void *xyz, void *stream);
 LCC_API lcc_status lcc_cga_points_embed(const lcc_algebra *alg, const void *xyz, const lcc_view *dst, void *stream);
 LCC_API lcc_status lcc_cga_points_extract(const lcc_algebra *alg, const lcc_view *src, void *xyz, void *stream);
+/* STA: sta_vector(t,x,y,z) is lcc_batch_scatter_columns onto blades 1,2,4,8 (src/sta.rs:105-109).
+ * sta_bivector (src/sta.rs:202-212): eb = dense (n,6) rows (Ex,Ey,Ez,Bx,By,Bz).
+ * sta_boost (src/sta.rs:253-296): velocity = dense (n,3); rows with |v| >= 1 (no rotor; ValueError in the
+ * scalar API) come back as NaN. */
+LCC_API lcc_status lcc_sta_bivectors_embed(const lcc_algebra *alg, const void *eb, const lcc_view *dst, void *stream);
+LCC_API lcc_status lcc_sta_boosts_embed(const lcc_algebra *alg, const void *velocity, const lcc_view *dst, void *stream);
 /* ---------------------------------------------------------------- host-buffer (end-to-end) entry points */
 
 /* Same operations with HOST buffers in the reference's (n, num_blades) row-major layout: the
@@ -235,6 +241,15 @@ LCC_API lcc_status lcc_host_sandwich(const lcc_algebra *alg, int dtype, const do
                                      void *out_host, int64_t n, unsigned flags);
 LCC_API lcc_status lcc_host_product(const lcc_algebra *alg, int dtype, int op, const void *a_host, int64_t na,
                                     const void *b_host, int64_t nb_rows, void *out_host, unsigned flags);
+
+/* ---------------------------------------------------------------- tuning */
+
+/* Process-wide integer options (no reference counterpart):
+ *   "aos_tma_min_rows"   AoS batches with at least this many rows use the TMA-staged kernels (default 4096)
+ *   "soa_tma_min_bytes"  SoA batches with at least this many bytes per operand do (default 128 MiB)
+ * Results do not depend on either: the staged and the direct-load kernels run the same arithmetic. */
+LCC_API lcc_status lcc_set_option(const char *name, int64_t value);
+LCC_API lcc_status lcc_get_option(const char *name, int64_t *value);
 
 /* ---------------------------------------------------------------- instrumentation */
 

@@ -52,6 +52,10 @@ struct SandwichArgs {
 using ProductLauncher = cudaError_t (*)(const ProductArgs &);
 using SandwichLauncher = cudaError_t (*)(const SandwichArgs &);
 
+// tuning options (lcc_set_option): thresholds of the TMA-staged kernels
+int64_t option_aos_tma_min_rows();
+int64_t option_soa_tma_min_bytes();
+
 // counted by every launcher (bench.py reports it as gpu_launches)
 void note_kernel_launch();
 

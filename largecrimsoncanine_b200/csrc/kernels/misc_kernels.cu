@@ -297,26 +297,50 @@ table_product_kernel(const T *__restrict__ x, int64_t ldx, int x_bc, const T *__
 // ------------------------------------------------------------------------------------------ PGA / CGA points
 // which 0: PGA3D point  c[7]=1, c[14]=-x, c[13]=y, c[11]=-z        (src/pga.rs:131-134)
 // which 1: CGA3D point  c[1,2,4]=x,y,z, c[8]=0.5|x|^2-0.5, c[16]=0.5|x|^2+0.5   (src/cga.rs:189-206)
+// which 2: STA bivector from (E, B), 6 columns: c[3,5,9]=E, c[12]=Bx, c[10]=-By, c[6]=Bz   (src/sta.rs:202-212)
+// which 3: STA boost rotor from a velocity, 3 columns: c[0]=cosh(phi/2), c[3,5,9]=-sinh(phi/2)*v/|v|,
+//          phi=atanh|v|; |v|<1e-14 gives the identity; |v|>=1 has no rotor (the scalar API raises ValueError,
+//          the batched form writes NaN for that row)   (src/sta.rs:253-296)
 template <class T, int LAYOUT>
 __global__ void __launch_bounds__(kThreads)
-points_embed_kernel(int which, const T *__restrict__ xyz, T *__restrict__ dst, int64_t ldd, int64_t n) {
+points_embed_kernel(int which, const T *__restrict__ cols, T *__restrict__ dst, int64_t ldd, int64_t n) {
     const int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (r >= n) return;
-    const T x = __ldg(xyz + r * 3), y = __ldg(xyz + r * 3 + 1), z = __ldg(xyz + r * 3 + 2);
-    const int nb = which == 0 ? 16 : 32;
+    const int ncols = which == 2 ? 6 : 3;
+    T c[6];
+    for (int i = 0; i < ncols; ++i) c[i] = __ldg(cols + r * ncols + i);
+    const T x = c[0], y = c[1], z = c[2];
+    const int nb = which == 1 ? 32 : 16;
     T nsq = T(0);
-    if (which == 1) {  // x*x + y*y + z*z, each operation rounded on its own (no FMA in the reference)
+    if (which == 1 || which == 3) {  // x*x + y*y + z*z, each operation rounded on its own (no FMA in the reference)
         const T xx = mul_rn(x, x), yy = mul_rn(y, y), zz = mul_rn(z, z);
         nsq = Arith<true>::madd(T(1), zz, Arith<true>::madd(T(1), yy, xx));
+    }
+    T b0 = T(1), bx = T(0), by = T(0), bz = T(0);
+    if (which == 3) {
+        const T vmag = sqrt_rn(nsq);
+        if (vmag >= T(1)) {
+            b0 = bx = by = bz = (T)__int_as_float(0x7fc00000);
+        } else if (!(vmag < (T)1e-14)) {
+            const T half_phi = div_rn(atanh(vmag), T(2));
+            const T ch = cosh(half_phi), sh = sinh(half_phi);
+            b0 = ch;
+            bx = mul_rn(-sh, div_rn(x, vmag)); by = mul_rn(-sh, div_rn(y, vmag)); bz = mul_rn(-sh, div_rn(z, vmag));
+        }
     }
     for (int k = 0; k < nb; ++k) {
         T v = T(0);
         if (which == 0) {
             if (k == 7) v = T(1); else if (k == 14) v = -x; else if (k == 13) v = y; else if (k == 11) v = -z;
-        } else {
+        } else if (which == 1) {
             if (k == 1) v = x; else if (k == 2) v = y; else if (k == 4) v = z;
             else if (k == 8) v = mul_rn(T(0.5), nsq) - T(0.5);
             else if (k == 16) v = mul_rn(T(0.5), nsq) + T(0.5);
+        } else if (which == 2) {
+            if (k == 3) v = c[0]; else if (k == 5) v = c[1]; else if (k == 9) v = c[2];
+            else if (k == 12) v = c[3]; else if (k == 10) v = -c[4]; else if (k == 6) v = c[5];
+        } else {
+            if (k == 0) v = b0; else if (k == 3) v = bx; else if (k == 5) v = by; else if (k == 9) v = bz;
         }
         if (LAYOUT == kSoA) dst[(int64_t)k * ldd + r] = v; else dst[r * ldd + k] = v;
     }

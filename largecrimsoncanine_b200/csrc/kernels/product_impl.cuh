@@ -452,55 +452,66 @@ template <int LAYOUT, int OP, bool STRICT> static cudaError_t launch_product_sum
 }
 
 // ------------------------------------------------------------------------------------------ K1 / K2 on TMA-staged SoA tiles
-// Engine-native blade-major batches: the tile is NB blade rows x kSoaTileRows batch rows (NB segments of
+// Engine-native blade-major batches: the tile is NB blade rows x SoaTileCfg::kRows batch rows (NB segments of
 // contiguous HBM), a thread owns V consecutive batch rows exactly as in the direct-load kernels and reads
 // them from shared memory with one 16-byte (or 8-byte) access per blade.
+// Tile size per operand: two-operand products keep 2 x 32 KB per block (3 blocks per SM), the sandwich one
+// tile of LCC_SOA_SANDWICH_TILE_BYTES.  Longer row segments per blade mean longer HBM bursts: CGA gp f64 at
+// 2^26 rows runs at 6837 GB/s with 16 KB tiles, 7012 GB/s with 32 KB and 4657 GB/s with 64 KB (one block per SM);
+// PGA sandwich f32 at 2^28 rows: 6836 / 6855 / 6889 GB/s (profiles/r01_soa_tile_sweep.json).
 #ifndef LCC_SOA_TILE_BYTES
-#define LCC_SOA_TILE_BYTES 16384
+#define LCC_SOA_TILE_BYTES 32768
 #endif
-constexpr int kSoaTileRows = []() constexpr {
-    int r = LCC_SOA_TILE_BYTES / (NB * (int)sizeof(real));  // bytes per operand tile
-    r = r > 1024 ? 1024 : r;
-    return r < 32 * kRowsSoA ? 32 * kRowsSoA : r;  // at least one warp
-}();
-constexpr int kSoaBoxRows = kSoaTileRows > 256 ? 256 : kSoaTileRows;  // TMA boxes are at most 256 elements wide
-constexpr int kSoaBoxes = kSoaTileRows / kSoaBoxRows;
-constexpr int kSoaBoxBytes = kSoaBoxRows * NB * (int)sizeof(real);
-constexpr int kSoaTileThreads = kSoaTileRows / kRowsSoA;
-constexpr int kSoaTileBytes = kSoaTileRows * NB * (int)sizeof(real);
+#ifndef LCC_SOA_SANDWICH_TILE_BYTES
+#define LCC_SOA_SANDWICH_TILE_BYTES 65536
+#endif
+template <int TILE_BYTES> struct SoaTileCfg {
+    static constexpr int kRows = []() constexpr {
+        int r = TILE_BYTES / (NB * (int)sizeof(real));
+        r = r > 1024 ? 1024 : r;
+        return r < 32 * kRowsSoA ? 32 * kRowsSoA : r;  // at least one warp
+    }();
+    static constexpr int kBoxRows = kRows > 256 ? 256 : kRows;  // TMA boxes are at most 256 elements wide
+    static constexpr int kBoxes = kRows / kBoxRows;
+    static constexpr int kBoxBytes = kBoxRows * NB * (int)sizeof(real);
+    static constexpr int kThreads = kRows / kRowsSoA;
+    static constexpr int kBytes = kRows * NB * (int)sizeof(real);
+    // byte offset of (blade k, tile row r): boxes one after the other, each [NB][kBoxRows]
+    static __device__ __forceinline__ size_t offset(int k, int r) {
+        return ((size_t)(r / kBoxRows) * NB * kBoxRows + (size_t)k * kBoxRows + (r % kBoxRows)) * sizeof(real);
+    }
+    static __device__ __forceinline__ void tma_load(uint8_t *dst, const CUtensorMap *map, uint64_t *bar, int row0) {
+#pragma unroll
+        for (int box = 0; box < kBoxes; ++box) tma::load_2d(dst + box * kBoxBytes, map, bar, row0 + box * kBoxRows, 0);
+    }
+    static __device__ __forceinline__ void tma_store(const CUtensorMap *map, const uint8_t *src, int row0) {
+#pragma unroll
+        for (int box = 0; box < kBoxes; ++box) tma::store_2d(map, src + box * kBoxBytes, row0 + box * kBoxRows, 0);
+    }
+};
+using SoaProductTile = SoaTileCfg<LCC_SOA_TILE_BYTES>;
+using SoaSandwichTile = SoaTileCfg<LCC_SOA_SANDWICH_TILE_BYTES>;
 
 template <int V> struct alignas(V * sizeof(real)) RowVec { real v[V]; };
 
-// byte offset of (blade k, tile row r): boxes one after the other, each [NB][kSoaBoxRows]
-static __device__ __forceinline__ size_t soa_tile_offset(int k, int r) {
-    return ((size_t)(r / kSoaBoxRows) * NB * kSoaBoxRows + (size_t)k * kSoaBoxRows + (r % kSoaBoxRows)) * sizeof(real);
-}
-template <int V>
+template <class CFG, int V>
 static __device__ __forceinline__ void load_soa_tile(Tile<real, NB, V> &t, const uint8_t *tile, int first_row) {
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
-        const RowVec<V> c = *reinterpret_cast<const RowVec<V> *>(tile + soa_tile_offset(k, first_row));
+        const RowVec<V> c = *reinterpret_cast<const RowVec<V> *>(tile + CFG::offset(k, first_row));
 #pragma unroll
         for (int l = 0; l < V; ++l) t.v[k][l] = c.v[l];
     }
 }
-template <int V> struct SoaTileSink {
+template <class CFG, int V> struct SoaTileSink {
     uint8_t *tile; int first_row;
     template <int K> __device__ __forceinline__ void put(const real (&acc)[V]) {
         RowVec<V> c;
 #pragma unroll
         for (int l = 0; l < V; ++l) c.v[l] = acc[l];
-        *reinterpret_cast<RowVec<V> *>(tile + soa_tile_offset(K, first_row)) = c;
+        *reinterpret_cast<RowVec<V> *>(tile + CFG::offset(K, first_row)) = c;
     }
 };
-static __device__ __forceinline__ void tma_load_soa_tile(uint8_t *dst, const CUtensorMap *map, uint64_t *bar, int row0) {
-#pragma unroll
-    for (int box = 0; box < kSoaBoxes; ++box) tma::load_2d(dst + box * kSoaBoxBytes, map, bar, row0 + box * kSoaBoxRows, 0);
-}
-static __device__ __forceinline__ void tma_store_soa_tile(const CUtensorMap *map, const uint8_t *src, int row0) {
-#pragma unroll
-    for (int box = 0; box < kSoaBoxes; ++box) tma::store_2d(map, src + box * kSoaBoxBytes, row0 + box * kSoaBoxRows, 0);
-}
 template <int V>
 static __device__ __forceinline__ void load_bcast_soa(Tile<real, NB, V> &t, const real *__restrict__ base, int64_t ld) {
 #pragma unroll
@@ -512,30 +523,31 @@ static __device__ __forceinline__ void load_bcast_soa(Tile<real, NB, V> &t, cons
 }
 
 template <int OP, bool STRICT>
-__global__ void __launch_bounds__(kSoaTileThreads)
+__global__ void __launch_bounds__(SoaProductTile::kThreads)
 product_kernel_soa_tma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                        const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out2,
                        const real *__restrict__ a_row, int64_t lda, const real *__restrict__ b_row, int64_t ldb, const Coeffs mu) {
     constexpr int V = kRowsSoA;
+    using T_ = SoaProductTile;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *tile_a = tma_smem_base(smem_raw), *tile_b = tile_a + kSoaTileBytes;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(tile_b + kSoaTileBytes);
-    const int t = threadIdx.x, row0 = blockIdx.x * kSoaTileRows;
+    uint8_t *tile_a = tma_smem_base(smem_raw), *tile_b = tile_a + T_::kBytes;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(tile_b + T_::kBytes);
+    const int t = threadIdx.x, row0 = blockIdx.x * T_::kRows;
     if (t == 0) {
         tma::mbar_init(bar, 1);
-        tma::mbar_expect_tx(bar, (a_row ? 0u : (uint32_t)kSoaTileBytes) + (b_row ? 0u : (uint32_t)kSoaTileBytes));
-        if (!a_row) tma_load_soa_tile(tile_a, &map_a, bar, row0);
-        if (!b_row) tma_load_soa_tile(tile_b, &map_b, bar, row0);
+        tma::mbar_expect_tx(bar, (a_row ? 0u : (uint32_t)T_::kBytes) + (b_row ? 0u : (uint32_t)T_::kBytes));
+        if (!a_row) T_::tma_load(tile_a, &map_a, bar, row0);
+        if (!b_row) T_::tma_load(tile_b, &map_b, bar, row0);
     }
     __syncthreads();
     Tile<real, NB, V> A, B;
     if (a_row) load_bcast_soa(A, a_row, lda);
     if (b_row) load_bcast_soa(B, b_row, ldb);
     tma::mbar_wait(bar, 0);
-    if (!a_row) load_soa_tile(A, tile_a, t * V);
-    if (!b_row) load_soa_tile(B, tile_b, t * V);
-    SoaTileSink<V> sink{tile_a, t * V};
-    SoaTileSink<V> sink2{tile_b, t * V};
+    if (!a_row) load_soa_tile<T_>(A, tile_a, t * V);
+    if (!b_row) load_soa_tile<T_>(B, tile_b, t * V);
+    SoaTileSink<T_, V> sink{tile_a, t * V};
+    SoaTileSink<T_, V> sink2{tile_b, t * V};
     (void)sink2;
     (void)mu;
 #define LCC_OUT_BEGIN(k) { real acc[V]; real acc2[V]; _Pragma("unroll") for (int l = 0; l < V; ++l) { acc[l] = real(0); acc2[l] = real(0); }
@@ -561,30 +573,31 @@ product_kernel_soa_tma(const __grid_constant__ CUtensorMap map_a, const __grid_c
     tma::fence_proxy_async();
     __syncthreads();
     if (t == 0) {
-        tma_store_soa_tile(&map_out, tile_a, row0);
-        if constexpr (OP == kOpGPOuter) tma_store_soa_tile(&map_out2, tile_b, row0);
+        T_::tma_store(&map_out, tile_a, row0);
+        if constexpr (OP == kOpGPOuter) T_::tma_store(&map_out2, tile_b, row0);
         tma::store_commit_and_wait_read();
     }
 }
 
 template <bool STRICT, bool EVEN>
-__global__ void __launch_bounds__(kSoaTileThreads)
+__global__ void __launch_bounds__(SoaSandwichTile::kThreads)
 sandwich_kernel_soa_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_out,
                         const Coeffs R, const Coeffs Rrev, const Coeffs mu) {
     constexpr int V = kRowsSoA;
+    using T_ = SoaSandwichTile;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *tile = tma_smem_base(smem_raw);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(tile + kSoaTileBytes);
-    const int t = threadIdx.x, row0 = blockIdx.x * kSoaTileRows;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(tile + T_::kBytes);
+    const int t = threadIdx.x, row0 = blockIdx.x * T_::kRows;
     if (t == 0) {
         tma::mbar_init(bar, 1);
-        tma::mbar_expect_tx(bar, (uint32_t)kSoaTileBytes);
-        tma_load_soa_tile(tile, &map_x, bar, row0);
+        tma::mbar_expect_tx(bar, (uint32_t)T_::kBytes);
+        T_::tma_load(tile, &map_x, bar, row0);
     }
     __syncthreads();
     tma::mbar_wait(bar, 0);
     Tile<real, NB, V> X, RX;
-    load_soa_tile(X, tile, t * V);
+    load_soa_tile<T_>(X, tile, t * V);
     (void)mu;
 #define LCC_OUT_BEGIN(k) { real acc[V]; _Pragma("unroll") for (int l = 0; l < V; ++l) acc[l] = real(0);
 #define LCC_TERM(k, i, j, neg, flags)                                                                   \
@@ -597,7 +610,7 @@ sandwich_kernel_soa_tma(const __grid_constant__ CUtensorMap map_x, const __grid_
 #include LCC_TERMS_FILE
 #undef LCC_TERM
 #undef LCC_OUT_END
-    SoaTileSink<V> sink{tile, t * V};
+    SoaTileSink<T_, V> sink{tile, t * V};
 #define LCC_TERM(k, i, j, neg, flags)                                                                   \
     if constexpr (!EVEN || even_grade(j)) {                                                            \
         real rv = (neg) ? -Rrev.v[j] : Rrev.v[j];                                                      \
@@ -612,14 +625,17 @@ sandwich_kernel_soa_tma(const __grid_constant__ CUtensorMap map_x, const __grid_
     tma::fence_proxy_async();
     __syncthreads();
     if (t == 0) {
-        tma_store_soa_tile(&map_out, tile, row0);
+        T_::tma_store(&map_out, tile, row0);
         tma::store_commit_and_wait_read();
     }
 }
 
-// AoS batches of at least this many rows go through the TMA-staged kernels (below it the tensor-map
-// encode on the host costs more than the wider accesses save).  LCC_AOS_TMA=0 forces the direct-load kernels.
-constexpr int64_t kTmaMinRows = 4096;
+// Which batches go through the TMA-staged kernels (lcc_set_option, include/lcc_b200.h):
+//   AoS  at least aos_tma_min_rows rows (default 4096): below it the tensor-map encode on the host costs more
+//        than the wider accesses save.  LCC_AOS_TMA=0 forces the direct-load kernels.
+//   SoA  at least soa_tma_min_bytes per operand (default 128 MiB): the direct-load SoA kernels are already
+//        coalesced, the tiles only win once the launch is long enough to hide their fill latency
+//        (Cl(3,0,0) gp at 2^20 rows: 33.1 us direct vs 35.1 us tiled; CGA gp at 2^26 rows: 6773 vs 7012 GB/s).
 static inline bool tma_path_enabled() {
     static const bool on = [] { const char *e = std::getenv("LCC_AOS_TMA"); return !(e && e[0] == '0'); }();
     return on;
@@ -633,7 +649,7 @@ template <int OP, bool STRICT> static cudaError_t launch_product_tma(const Produ
     if constexpr (!kHasTmaPath) {
         return cudaErrorNotSupported;
     } else {
-        if (!tma_path_enabled() || g.n < kTmaMinRows) return cudaErrorNotSupported;
+        if (!tma_path_enabled() || g.n < option_aos_tma_min_rows()) return cudaErrorNotSupported;
         CUtensorMap ma, mb, mo, mo2;
         if (!aos_map(&mo, g.out, g.ldo, g.n)) return cudaErrorNotSupported;
         ma = mb = mo2 = mo;  // placeholders for operands that do not use a tile
@@ -656,7 +672,7 @@ template <bool STRICT, bool EVEN> static cudaError_t launch_sandwich_tma(const S
     if constexpr (!kHasTmaPath) {
         return cudaErrorNotSupported;
     } else {
-        if (!tma_path_enabled() || g.n < kTmaMinRows) return cudaErrorNotSupported;
+        if (!tma_path_enabled() || g.n < option_aos_tma_min_rows()) return cudaErrorNotSupported;
         CUtensorMap mx, mo;
         if (!aos_map(&mx, g.x, g.ldx, g.n) || !aos_map(&mo, g.out, g.ldo, g.n)) return cudaErrorNotSupported;
         auto kernel = sandwich_kernel_aos_tma<STRICT, EVEN>;
@@ -672,36 +688,41 @@ static inline bool soa_tma_enabled() {  // LCC_SOA_TMA=0 forces the direct-load 
     static const bool on = [] { const char *e = std::getenv("LCC_SOA_TMA"); return !(e && e[0] == '0'); }();
     return on;
 }
-static inline bool soa_map(CUtensorMap *m, const void *base, int64_t ld, int64_t n) {
-    return make_soa_tensor_map(m, base, (int)sizeof(real), NB, ld, n, kSoaBoxRows);
+template <class CFG> static inline bool soa_map(CUtensorMap *m, const void *base, int64_t ld, int64_t n) {
+    return make_soa_tensor_map(m, base, (int)sizeof(real), NB, ld, n, CFG::kBoxRows);
 }
 
 template <int OP, bool STRICT> static cudaError_t launch_product_soa_tma(const ProductArgs &g) {
-    if (!soa_tma_enabled() || g.n < kTmaMinRows) return cudaErrorNotSupported;
+    using T_ = SoaProductTile;
+    if (!soa_tma_enabled() || g.n * (int64_t)kRowBytes < option_soa_tma_min_bytes()) return cudaErrorNotSupported;
     CUtensorMap ma, mb, mo, mo2;
-    if (!soa_map(&mo, g.out, g.ldo, g.n)) return cudaErrorNotSupported;
+    if (!soa_map<T_>(&mo, g.out, g.ldo, g.n)) return cudaErrorNotSupported;
     ma = mb = mo2 = mo;
-    if (!g.a_bcast && !soa_map(&ma, g.a, g.lda, g.n)) return cudaErrorNotSupported;
-    if (!g.b_bcast && !soa_map(&mb, g.b, g.ldb, g.n)) return cudaErrorNotSupported;
-    if (OP == kOpGPOuter && !soa_map(&mo2, g.out2, g.ldo2, g.n)) return cudaErrorNotSupported;
+    if (!g.a_bcast && !soa_map<T_>(&ma, g.a, g.lda, g.n)) return cudaErrorNotSupported;
+    if (!g.b_bcast && !soa_map<T_>(&mb, g.b, g.ldb, g.n)) return cudaErrorNotSupported;
+    if (OP == kOpGPOuter && !soa_map<T_>(&mo2, g.out2, g.ldo2, g.n)) return cudaErrorNotSupported;
     auto kernel = product_kernel_soa_tma<OP, STRICT>;
-    constexpr int smem = 2 * kSoaTileBytes + 1024 + 16;
+    constexpr int smem = 2 * T_::kBytes + 1024 + 16;
     static const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (attr != cudaSuccess) return attr;
-    const unsigned grid = (unsigned)((g.n + kSoaTileRows - 1) / kSoaTileRows);
-    kernel<<<grid, kSoaTileThreads, smem, g.stream>>>(ma, mb, mo, mo2, g.a_bcast ? (const real *)g.a : nullptr, g.lda,
-                                                     g.b_bcast ? (const real *)g.b : nullptr, g.ldb, to_coeffs(g.mu, 1.0));
+    const unsigned grid = (unsigned)((g.n + T_::kRows - 1) / T_::kRows);
+    kernel<<<grid, T_::kThreads, smem, g.stream>>>(ma, mb, mo, mo2, g.a_bcast ? (const real *)g.a : nullptr, g.lda,
+                                                  g.b_bcast ? (const real *)g.b : nullptr, g.ldb, to_coeffs(g.mu, 1.0));
     note_kernel_launch();
     return cudaGetLastError();
 }
 
 template <bool STRICT, bool EVEN> static cudaError_t launch_sandwich_soa_tma(const SandwichArgs &g, const Coeffs &R, const Coeffs &Rrev) {
-    if (!soa_tma_enabled() || g.n < kTmaMinRows) return cudaErrorNotSupported;
+    using T_ = SoaSandwichTile;
+    if (!soa_tma_enabled() || g.n * (int64_t)kRowBytes < option_soa_tma_min_bytes()) return cudaErrorNotSupported;
     CUtensorMap mx, mo;
-    if (!soa_map(&mx, g.x, g.ldx, g.n) || !soa_map(&mo, g.out, g.ldo, g.n)) return cudaErrorNotSupported;
-    constexpr int smem = kSoaTileBytes + 1024 + 16;
-    const unsigned grid = (unsigned)((g.n + kSoaTileRows - 1) / kSoaTileRows);
-    sandwich_kernel_soa_tma<STRICT, EVEN><<<grid, kSoaTileThreads, smem, g.stream>>>(mx, mo, R, Rrev, to_coeffs(g.mu, 1.0));
+    if (!soa_map<T_>(&mx, g.x, g.ldx, g.n) || !soa_map<T_>(&mo, g.out, g.ldo, g.n)) return cudaErrorNotSupported;
+    auto kernel = sandwich_kernel_soa_tma<STRICT, EVEN>;
+    constexpr int smem = T_::kBytes + 1024 + 16;
+    static const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (attr != cudaSuccess) return attr;
+    const unsigned grid = (unsigned)((g.n + T_::kRows - 1) / T_::kRows);
+    kernel<<<grid, T_::kThreads, smem, g.stream>>>(mx, mo, R, Rrev, to_coeffs(g.mu, 1.0));
     note_kernel_launch();
     return cudaGetLastError();
 }

@@ -55,6 +55,15 @@ static const GenericEntry kGenericEntries[] = {
 static thread_local uint64_t t_launches = 0;
 void note_kernel_launch() { ++t_launches; }
 
+static int64_t env_or(const char *name, int64_t fallback) {
+    const char *e = getenv(name);
+    return e && *e ? atoll(e) : fallback;
+}
+static std::atomic<int64_t> g_aos_tma_min_rows{env_or("LCC_AOS_TMA_MIN_ROWS", 4096)};
+static std::atomic<int64_t> g_soa_tma_min_bytes{env_or("LCC_SOA_TMA_MIN_BYTES", 128ll << 20)};
+int64_t option_aos_tma_min_rows() { return g_aos_tma_min_rows.load(std::memory_order_relaxed); }
+int64_t option_soa_tma_min_bytes() { return g_soa_tma_min_bytes.load(std::memory_order_relaxed); }
+
 // ------------------------------------------------------------------ algebra builder
 void build_algebra(lcc_algebra &alg, int p, int q, int r) {
     alg.p = p; alg.q = q; alg.r = r; alg.dim = p + q + r; alg.nb = 1 << alg.dim;
@@ -809,6 +818,8 @@ static lcc_status points_check(const lcc_algebra *alg, int which) {
         return fail(LCC_ERR_VALUE, "pga_point requires a PGA3D algebra Cl(3,0,1)");  // src/pga.rs:110-114
     if (which == 1 && !(alg->q == 1 && alg->r == 0 && alg->dim == 5))
         return fail(LCC_ERR_VALUE, "cga_point(x,y,z) requires CGA3D (dimension 5); use Algebra.cga(3)");  // src/cga.rs:172-184
+    if ((which == 2 || which == 3) && !(alg->p == 1 && alg->q == 3 && alg->r == 0))
+        return fail(LCC_ERR_VALUE, "requires an STA algebra Cl(1,3,0); use Algebra.sta()");  // src/sta.rs:60-70
     return LCC_OK;
 }
 static lcc_status points_embed(const lcc_algebra *alg, int which, const void *xyz, const lcc_view *dst, void *stream) {
@@ -835,6 +846,8 @@ lcc_status lcc_pga_points_embed(const lcc_algebra *alg, const void *xyz, const l
 lcc_status lcc_pga_points_extract(const lcc_algebra *alg, const lcc_view *src, void *xyz, void *stream) { return points_extract(alg, 0, src, xyz, stream); }
 lcc_status lcc_cga_points_embed(const lcc_algebra *alg, const void *xyz, const lcc_view *dst, void *stream) { return points_embed(alg, 1, xyz, dst, stream); }
 lcc_status lcc_cga_points_extract(const lcc_algebra *alg, const lcc_view *src, void *xyz, void *stream) { return points_extract(alg, 1, src, xyz, stream); }
+lcc_status lcc_sta_bivectors_embed(const lcc_algebra *alg, const void *eb, const lcc_view *dst, void *stream) { return points_embed(alg, 2, eb, dst, stream); }
+lcc_status lcc_sta_boosts_embed(const lcc_algebra *alg, const void *velocity, const lcc_view *dst, void *stream) { return points_embed(alg, 3, velocity, dst, stream); }
 
 // ================================================================== host-buffer (end-to-end) entry points
 // Chunked three-stream pipeline: H2D copy of chunk c+1, kernel of chunk c and D2H copy of chunk
@@ -946,6 +959,21 @@ lcc_status lcc_host_product(const lcc_algebra *alg, int dtype, int op, const voi
     LCC_CUDA(cudaStreamSynchronize(pl.st->copy_out));
     LCC_CUDA(cudaStreamSynchronize(pl.st->stream));
     return LCC_OK;
+}
+
+// ================================================================== tuning
+lcc_status lcc_set_option(const char *name, int64_t value) {
+    if (!name) return fail(LCC_ERR_VALUE, "option name is NULL");
+    if (value < 0) return fail(LCC_ERR_VALUE, "option %s: value must be >= 0", name);
+    if (!strcmp(name, "aos_tma_min_rows")) { g_aos_tma_min_rows = value; return LCC_OK; }
+    if (!strcmp(name, "soa_tma_min_bytes")) { g_soa_tma_min_bytes = value; return LCC_OK; }
+    return fail(LCC_ERR_VALUE, "unknown option %s", name);
+}
+lcc_status lcc_get_option(const char *name, int64_t *value) {
+    if (!name || !value) return fail(LCC_ERR_VALUE, "option name / value is NULL");
+    if (!strcmp(name, "aos_tma_min_rows")) { *value = g_aos_tma_min_rows; return LCC_OK; }
+    if (!strcmp(name, "soa_tma_min_bytes")) { *value = g_soa_tma_min_bytes; return LCC_OK; }
+    return fail(LCC_ERR_VALUE, "unknown option %s", name);
 }
 
 // ================================================================== instrumentation

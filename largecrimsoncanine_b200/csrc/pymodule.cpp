@@ -19,6 +19,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <cstring>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -478,6 +479,9 @@ PYBIND11_MODULE(largecrimsoncanine, m) {
           "Reproduce the reference's rounding sequence bit for bit (separate multiply and add) instead of FMA.");
     m.def("get_strict_fp", [] { return g_strict_fp; });
     m.def("kernel_launch_count", [] { return lcc_kernel_launch_count(); });
+    m.def("set_option", [](const std::string &name, int64_t value) { check(lcc_set_option(name.c_str(), value)); },
+          "Tuning knobs of the engine (include/lcc_b200.h, lcc_set_option); results never depend on them.");
+    m.def("get_option", [](const std::string &name) { int64_t v = 0; check(lcc_get_option(name.c_str(), &v)); return v; });
     m.def("device_count", [] { int c = 0; check(lcc_device_count(&c)); return c; });
     m.def("set_device", [](int d) { check(lcc_set_device(d)); });
     m.def("synchronize", [] { check(lcc_stream_sync(nullptr)); });
@@ -1202,6 +1206,56 @@ PYBIND11_MODULE(largecrimsoncanine, m) {
             DeviceTemp stage(bytes);
             upload(host, bytes, stage.ptr);
             check(lcc_cga_points_embed(a.inner->h, stage.ptr, &b->view, nullptr));
+            return b;
+        })
+        // batched sta_vector / sta_bivector / sta_boost (src/sta.rs:105-109,202-212,253-296)
+        .def_static("from_events_sta", [](const PyAlgebra &a, const py::array &txyz_in) {
+            py::array txyz = contiguous(txyz_in);
+            const int dtype = dtype_of(txyz);
+            if (!(a.inner->p == 1 && a.inner->q == 3 && a.inner->r == 0)) throw py::value_error("requires an STA algebra Cl(1,3,0); use Algebra.sta()");
+            if (txyz.ndim() != 2 || txyz.shape(1) != 4) throw py::value_error("events must have 4 columns (t, x, y, z)");
+            auto b = std::make_shared<Batch>(a.inner, dtype, txyz.shape(0));
+            if (txyz.shape(0) == 0) return b;
+            const void *host = txyz.data();
+            const size_t bytes = (size_t)txyz.nbytes();
+            static const int32_t blades[4] = {1, 2, 4, 8};
+            py::gil_scoped_release nogil;
+            DeviceTemp stage(bytes);
+            upload(host, bytes, stage.ptr);
+            check(lcc_batch_scatter_columns(a.inner->h, stage.ptr, 4, blades, &b->view, nullptr));
+            return b;
+        })
+        .def_static("from_fields_sta", [](const PyAlgebra &a, const py::array &e_in, const py::array &b_in) {
+            py::array e = contiguous(e_in), bf = contiguous(b_in);
+            const int dtype = dtype_of(e);
+            if (dtype_of(bf) != dtype) throw py::type_error("E and B must share one dtype");
+            if (e.ndim() != 2 || e.shape(1) != 3 || bf.ndim() != 2 || bf.shape(1) != 3 || bf.shape(0) != e.shape(0))
+                throw py::value_error("E and B must both be (n, 3) arrays");
+            const py::ssize_t n = e.shape(0);
+            const size_t es = dtype == LCC_F32 ? 4 : 8;
+            std::vector<char> packed((size_t)n * 6 * es);  // (Ex,Ey,Ez,Bx,By,Bz) rows
+            for (py::ssize_t r = 0; r < n; ++r) {
+                std::memcpy(packed.data() + (size_t)r * 6 * es, (const char *)e.data() + (size_t)r * 3 * es, 3 * es);
+                std::memcpy(packed.data() + ((size_t)r * 6 + 3) * es, (const char *)bf.data() + (size_t)r * 3 * es, 3 * es);
+            }
+            auto b = std::make_shared<Batch>(a.inner, dtype, n);
+            py::gil_scoped_release nogil;
+            DeviceTemp stage(packed.size() ? packed.size() : 16);
+            if (n) upload(packed.data(), packed.size(), stage.ptr);
+            check(lcc_sta_bivectors_embed(a.inner->h, stage.ptr, &b->view, nullptr));
+            return b;
+        })
+        .def_static("from_boosts_sta", [](const PyAlgebra &a, const py::array &v_in) {
+            py::array v = contiguous(v_in);
+            const int dtype = dtype_of(v);
+            if (v.ndim() != 2 || v.shape(1) != 3) throw py::value_error("velocity must have 3 components");
+            auto b = std::make_shared<Batch>(a.inner, dtype, v.shape(0));
+            const void *host = v.data();
+            const size_t bytes = (size_t)v.nbytes();
+            py::gil_scoped_release nogil;
+            DeviceTemp stage(bytes ? bytes : 16);
+            if (bytes) upload(host, bytes, stage.ptr);
+            check(lcc_sta_boosts_embed(a.inner->h, stage.ptr, &b->view, nullptr));
             return b;
         })
         .def("pga_point_coords", [](const Batch &b) {

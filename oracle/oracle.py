@@ -16,6 +16,7 @@ from . import build as _build
 __all__ = [
     "OracleAlgebra", "basis_square", "reorder_sign", "blade_product", "blade_grade", "reverse_sign",
     "grade_involution_sign", "clifford_conjugate_sign", "grade_mask", "max_threads", "lib_path",
+    "sta_bivectors", "sta_boosts",
 ]
 
 _LIB = None
@@ -392,3 +393,33 @@ class OracleAlgebra:
         mag = np.empty(self.num_blades)
         getattr(_lib(), f"oracle_sum_rows_{_sfx(x.dtype)}")(x.ctypes.data, x.shape[0], self.num_blades, out.ctypes.data, mag.ctypes.data)
         return out, mag
+
+
+# ----------------------------------------------------------------------------- STA batched constructors
+def sta_bivectors(e, b):
+    """Row-wise Multivector::sta_bivector, src/sta.rs:202-212: c[3,5,9] = E, c[12] = Bx, c[10] = -By, c[6] = Bz."""
+    e, b = _arr(e), _arr(b)
+    out = np.zeros((e.shape[0], 16), dtype=e.dtype)
+    out[:, 3], out[:, 5], out[:, 9] = e[:, 0], e[:, 1], e[:, 2]
+    out[:, 12], out[:, 10], out[:, 6] = b[:, 0], -b[:, 1], b[:, 2]
+    return out
+
+
+def sta_boosts(v):
+    """Row-wise Multivector::sta_boost, src/sta.rs:253-296 (float64): identity below 1e-14, NaN row where the
+    reference raises (|v| >= 1)."""
+    v = _arr(v, dtype=np.float64)
+    out = np.zeros((v.shape[0], 16))
+    for r in range(v.shape[0]):  # small test batches only
+        vx, vy, vz = (float(t) for t in v[r])
+        vmag = np.sqrt(vx * vx + vy * vy + vz * vz)
+        if vmag < 1e-14:
+            out[r, 0] = 1.0
+        elif vmag >= 1.0:
+            out[r, [0, 3, 5, 9]] = np.nan
+        else:
+            half = np.arctanh(vmag) / 2.0
+            ch, sh = np.cosh(half), np.sinh(half)
+            out[r, 0] = ch
+            out[r, 3], out[r, 5], out[r, 9] = -sh * (vx / vmag), -sh * (vy / vmag), -sh * (vz / vmag)
+    return out

@@ -522,6 +522,15 @@ def test_soa_batches_through_tma_tiles(L, strict, sig, dt):
     alg, o = algebras(L, sig)
     nb = o.num_blades
     rng = np.random.default_rng(29)
+    before = L.get_option("soa_tma_min_bytes")
+    L.set_option("soa_tma_min_bytes", 0)  # the default (128 MiB per operand) would send these sizes to the direct kernels
+    try:
+        _soa_tma_cases(L, alg, o, nb, rng, dt)
+    finally:
+        L.set_option("soa_tma_min_bytes", before)
+
+
+def _soa_tma_cases(L, alg, o, nb, rng, dt):
     for n in (4096, 4099, 9001):
         a, b = rand(rng, n, nb, dt), rand(rng, n, nb, dt)
         A, B = L.MultivectorBatch.from_numpy(alg, a), L.MultivectorBatch.from_numpy(alg, b)

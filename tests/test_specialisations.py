@@ -202,3 +202,37 @@ def test_algebra_metric_squares(api):  # tests/test_algebras.py:171-246
     legacy, explicit = M.from_vector([0.0, 1.0, 0.0]), M.vector_in([1.0, 0.0, 0.0], A.euclidean(3))
     assert (explicit * legacy).coefficients()[3] == 1.0  # explicit Euclidean mixes with dims-only (multivector.rs:48-55)
     assert M.scalar_in(2.5, A.cga(3)).scalar() == 2.5
+
+
+@pytest.mark.gpu
+def test_sta_batched_constructors(api):
+    """Batched sta_vector / sta_bivector / sta_boost (src/sta.rs:105-109,202-212,253-296): the rows equal what
+    the per-object constructors (pinned by the reference's tests/test_sta.py) give, and a batch of events
+    boosted row by row keeps its interval t^2 - x^2 - y^2 - z^2 (tests/test_sta.py:237-290)."""
+    A, M, B = api.Algebra, api.Multivector, api.MultivectorBatch
+    sta = A.sta()
+    rng = np.random.default_rng(3)
+    n = 257
+    for dt in (np.float64, np.float32):
+        txyz = rng.standard_normal((n, 4)).astype(dt)
+        ev = B.from_events_sta(sta, txyz).to_numpy()
+        assert ev.dtype == dt and np.array_equal(ev[:, [1, 2, 4, 8]], txyz) and np.count_nonzero(ev) == np.count_nonzero(txyz)
+        e, b = rng.standard_normal((n, 3)).astype(dt), rng.standard_normal((n, 3)).astype(dt)
+        f = B.from_fields_sta(sta, e, b).to_numpy()
+        assert np.array_equal(f, oracle.sta_bivectors(e, b))
+    for r in (0, 100, 256):  # against the per-object constructor
+        want = M.sta_bivector(sta, [float(v) for v in e[r]], [float(v) for v in b[r]]).coefficients()
+        assert np.array_equal(f[r].astype(np.float64), np.asarray(want, np.float64).astype(np.float32))
+    v = rng.uniform(-0.55, 0.55, (n, 3))
+    v[0] = 0.0            # identity rotor
+    v[1] = (0.9, 0.9, 0.0)  # |v| >= 1: no rotor
+    boosts = B.from_boosts_sta(sta, v)
+    got = boosts.to_numpy()
+    want = oracle.sta_boosts(v)
+    assert np.all(np.isnan(got[1, [0, 3, 5, 9]])) and got[0, 0] == 1.0 and not got[0, 1:].any()
+    ok = np.ones(n, bool); ok[1] = False
+    np.testing.assert_allclose(got[ok], want[ok], rtol=1e-14, atol=1e-16)  # libm vs CUDA math: a few ulp
+    for r in (2, 77):
+        np.testing.assert_allclose(got[r], M.sta_boost(sta, [float(t) for t in v[r]]).coefficients(), rtol=1e-14, atol=1e-16)
+    with pytest.raises(ValueError, match="STA"):
+        B.from_boosts_sta(A.pga(3), v)
