@@ -288,6 +288,218 @@ fixed_product_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __g
     }
 }
 
+// ------------------------------------------------------------------ the GEMM kernel on CTA pairs (cta_group::2)
+// With one CTA per tile every M128 x N256 x K8 tf32 MMA pulls 4 KB of A and 8 KB of B out of shared memory in
+// 128 cycles; together with the TMA fills and the hi/lo split that is 177 B/clk against a 128 B/clk port, and
+// the tensor pipe idles 30 % of the time (profiles/r01_prof_cl8_fixed.summary.json).  Here two CTAs of one
+// cluster (the two SMs of a TPC) share each MMA: the tile is 256 rows, every CTA stages ITS 128 rows of X and
+// only HALF of the W chunk (its 128 output blades), the leader CTA's elected thread issues
+// tcgen05.mma.cta_group::2 (M256 x N=nb x K8) which reads A from both CTAs and one half of B from each, and
+// every CTA's TMEM receives the accumulator of its own 128 rows.  Per SM: 125 B/clk of shared-memory traffic
+// and half the W traffic from L2.
+//
+// Barriers (all in each CTA's own shared memory at identical offsets):
+//   full[s]      local   TMA bytes of the stage have landed                       (count 1 + tx)
+//   ready[s]     LEADER  both CTAs' splitter warps have rewritten their X chunk   (count 8, remote arrives)
+//   empty[s]     local   the MMAs that read the stage have completed              (multicast tcgen05.commit)
+//   acc_full[a]  local   accumulator a is complete                                (multicast tcgen05.commit)
+//   acc_empty[a] LEADER  both CTAs' epilogue warps have drained accumulator a     (count 8, remote arrives)
+constexpr int kCK2 = 16;  // blades per stage (64-byte swizzle span)
+
+template <int NB> struct Cfg2 {
+    static constexpr uint32_t kXChunkBytes = kBlockM * kCK2 * 4;        // this CTA's 128 rows
+    static constexpr uint32_t kWHalfBytes = (NB / 2) * kCK2 * 4;        // this CTA's half of the output blades
+    static constexpr uint32_t kStageBytes = 2 * kXChunkBytes + 2 * kWHalfBytes;
+    static constexpr int kStagesFit = (int)((227u * 1024 - 2048) / kStageBytes);
+    static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256;
+    static constexpr int kTmemCols = 2 * NB < 32 ? 32 : 2 * NB;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+    // default (CTA-scope release) semantics: a cluster-scope release compiles to MEMBAR.ALL.GPU + ERRBAR per
+    // arrival, which cost the first version of this kernel half of its time (profiles/r01_prof_cl8_pair_v1).
+    // What the arrivals publish is already ordered without it: the splitters' shared-memory writes are made
+    // visible to the tensor core by fence.proxy.async before the arrive, the epilogue's TMEM reads are retired
+    // by tcgen05.wait::ld + tcgen05.fence::before_thread_sync.
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP_C:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_C;\n\t"
+        "bra WAIT_LOOP_C;\n\t"
+        "DONE_C:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint64_t *bar) {  // one arrival on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_tf32_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// kind::tf32, D f32, A MN-major, B K-major, N = n, M = 256 (two CTAs x 128 lanes)
+__host__ __device__ constexpr uint32_t instr_desc_tf32_pair(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int NB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsGemm, 1)
+fixed_product_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
+                                 const __grid_constant__ CUtensorMap map_wlo, float *__restrict__ out, int64_t ldo, int64_t n) {
+    using C = Cfg2<NB>;
+    constexpr uint32_t kXChunkBytes = C::kXChunkBytes;
+    extern __shared__ uint8_t smem_raw[];
+    // identical offsets in both CTAs: the dynamic shared window starts at the same address in every CTA of a kernel
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    auto stage_ptr = [&](int s) { return smem + (size_t)s * C::kStageBytes; };
+    uint64_t *bars = (uint64_t *)(smem + (size_t)C::kStages * C::kStageBytes);
+    uint64_t *full = bars, *ready = bars + C::kStages, *empty = bars + 2 * C::kStages;
+    uint64_t *acc_full = bars + 3 * C::kStages, *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int64_t num_tiles = (n + 2 * kBlockM - 1) / (2 * kBlockM);  // 256-row tiles, one per cluster pass
+    const int64_t cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    constexpr int kChunks = NB / kCK2;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 8); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // both CTAs of the pair allocate, same warp, same slot address
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();  // barriers of BOTH CTAs are initialised before anyone arrives remotely
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (every CTA: its own rows of X, its own half of W) =====
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                const int strip0 = (int)((tile * 2 + rank) * (kBlockM / 32));
+                for (int c = 0; c < kChunks; ++c) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t *st = stage_ptr(s);
+                    mbar_expect_tx(&full[s], kXChunkBytes + 2 * C::kWHalfBytes);
+                    tma_load_3d(st, &map_x, &full[s], 0, c * kCK2, strip0);
+                    tma_load_2d(st + 2 * kXChunkBytes, &map_whi, &full[s], c * kCK2, (int)rank * (NB / 2));
+                    tma_load_2d(st + 2 * kXChunkBytes + C::kWHalfBytes, &map_wlo, &full[s], c * kCK2, (int)rank * (NB / 2));
+                    if (++s == C::kStages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of the LEADER CTA drives the tensor cores of both SMs =====
+        if (rank == 0 && lane == 0) {
+            constexpr uint32_t idesc = instr_desc_tf32_pair(NB);
+            int s = 0; uint32_t ph = 0; int a = 0; uint32_t pa = 0;
+            for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                mbar_wait_cluster(&acc_empty[a], pa ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(a * NB);
+                for (int c = 0; c < kChunks; ++c) {
+                    mbar_wait_cluster(&ready[s], ph);
+                    tcgen05_fence_after();
+                    const uint32_t xhi = smem_u32(stage_ptr(s)), xlo = xhi + kXChunkBytes;
+                    const uint32_t whi = xhi + 2 * kXChunkBytes, wlo = whi + C::kWHalfBytes;
+#pragma unroll
+                    for (int kk = 0; kk < kCK2 / 8; ++kk) {
+                        constexpr uint32_t kStrip = kCK2 * 128;           // one 32-row strip of the chunk
+                        constexpr uint32_t kBGroup = kCK2 * 4 * 8;        // 8-row group pitch of the K-major W chunk
+                        const uint64_t a_hi = umma_desc(xhi + kk * 1024, kStrip, 512, 1), a_lo = umma_desc(xlo + kk * 1024, kStrip, 512, 1);
+                        const uint64_t b_hi = umma_desc(whi + kk * 32, 16, kBGroup, 4), b_lo = umma_desc(wlo + kk * 32, 16, kBGroup, 4);
+                        tcgen05_mma_tf32_pair(d_tmem, a_hi, b_hi, idesc, (c | kk) != 0);
+                        tcgen05_mma_tf32_pair(d_tmem, a_lo, b_hi, idesc, 1);
+                        tcgen05_mma_tf32_pair(d_tmem, a_hi, b_lo, idesc, 1);
+                    }
+                    tcgen05_commit_pair(&empty[s]);
+                    if (++s == C::kStages) { s = 0; ph ^= 1; }
+                }
+                tcgen05_commit_pair(&acc_full[a]);
+                if (++a == 2) { a = 0; pa ^= 1; }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===== epilogue: this CTA's 128 rows, TMEM -> registers -> SoA global =====
+        const int q = warp & 3;
+        int a = 0; uint32_t pa = 0;
+        for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            mbar_wait(&acc_full[a], pa);
+            tcgen05_fence_after();
+            const int64_t row = (tile * 2 + rank) * kBlockM + q * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * NB);
+#pragma unroll 1
+            for (int col0 = 0; col0 < NB; col0 += 32) {
+                uint32_t v[32];
+                tmem_load_32x32(taddr + col0, v);
+                if (row < n) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) __stcs(out + (int64_t)(col0 + j) * ldo + row, __uint_as_float(v[j]));
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(&acc_empty[a], 0);
+            if (++a == 2) { a = 0; pa ^= 1; }
+        }
+    } else if (warp >= 8) {
+        // ===== splitters: this CTA's X chunk -> (x_hi in place, x_lo beside it) =====
+        const int t = threadIdx.x - 256;
+        int s = 0; uint32_t ph = 0;
+        for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            for (int c = 0; c < kChunks; ++c) {
+                mbar_wait(&full[s], ph);
+                float4 *hi = (float4 *)stage_ptr(s);
+                float4 *lo = (float4 *)(stage_ptr(s) + kXChunkBytes);
+#pragma unroll
+                for (int j = 0; j < (int)(kXChunkBytes / 16 / 128); ++j) {
+                    const int idx = t + 128 * j;
+                    float4 v = hi[idx], h;
+                    h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+                    hi[idx] = h;
+                    lo[idx] = make_float4(tf32_rn(v.x - h.x), tf32_rn(v.y - h.y), tf32_rn(v.z - h.z), tf32_rn(v.w - h.w));
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(&ready[s], 0);
+                if (++s == C::kStages) { s = 0; ph ^= 1; }
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    cluster_sync_all();  // the leader's last MMAs (which write the peer's TMEM) are committed before anyone frees
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kTmemCols) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------ host side
 using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -339,6 +551,55 @@ cudaError_t launch_t(const float *x, int64_t ldx, float *out, int64_t ldo, int64
     return cudaGetLastError();
 }
 
+template <int NB>
+cudaError_t launch_pair_t(const float *x, int64_t ldx, float *out, int64_t ldo, int64_t n, const float *w_hi, const float *w_lo, cudaStream_t s) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return cudaErrorNotSupported;
+    CUtensorMap mx, mhi, mlo;
+    {
+        cuuint64_t dims[3] = {32, (cuuint64_t)NB, (cuuint64_t)(ldx / 32)};
+        cuuint64_t strides[2] = {(cuuint64_t)ldx * 4, 128};
+        cuuint32_t box[3] = {32, (cuuint32_t)kCK2, (cuuint32_t)(kBlockM / 32)};
+        cuuint32_t estr[3] = {1, 1, 1};
+        if (enc(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return cudaErrorInvalidValue;
+    }
+    for (int h = 0; h < 2; ++h) {  // Wt[n][k], k contiguous; each CTA of a pair takes NB/2 rows
+        cuuint64_t dims[2] = {(cuuint64_t)NB, (cuuint64_t)NB};
+        cuuint64_t strides[1] = {(cuuint64_t)NB * 4};
+        cuuint32_t box[2] = {(cuuint32_t)kCK2, (cuuint32_t)(NB / 2)};
+        cuuint32_t estr[2] = {1, 1};
+        if (enc(h ? &mlo : &mhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)(h ? w_lo : w_hi), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return cudaErrorInvalidValue;
+    }
+    auto kernel = fixed_product_tf32x3_pair_kernel<NB>;
+    using C = Cfg2<NB>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    // The kernel is persistent with a static round-robin over tiles, so the grid must be ONE wave: ask the
+    // runtime how many CTA pairs can be resident at once (GPCs with an odd number of free SMs strand one).
+    static const int resident_pairs = [&] {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * 74); cfg.blockDim = dim3(kThreadsGemm); cfg.dynamicSmemBytes = C::kSmemBytes;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int pairs = 0;
+        if (cudaOccupancyMaxActiveClusters(&pairs, kernel, &cfg) != cudaSuccess || pairs <= 0) { cudaGetLastError(); pairs = 64; }
+        if (const char *env = getenv("LCC_GEMM_PAIRS")) { const int v = atoi(env); if (v > 0) pairs = v; }
+        return pairs;
+    }();
+    const int64_t tiles = (n + 2 * kBlockM - 1) / (2 * kBlockM);
+    const int clusters = (int)(tiles < resident_pairs ? tiles : resident_pairs);
+    kernel<<<2 * clusters, kThreadsGemm, C::kSmemBytes, s>>>(mx, mhi, mlo, out, ldo, n);
+    note_kernel_launch();
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 // out (n x nb, SoA f32) = fixed (op) x  or  x (op) fixed, geometric product, through the tensor cores.
@@ -351,6 +612,16 @@ cudaError_t launch_fixed_product_tf32x3(int nb, int side, const int8_t *signs_de
     note_kernel_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    // CTA pairs (cta_group::2) by default; LCC_GEMM_PAIR=0 selects the one-CTA-per-tile kernel
+    static const bool pair = [] { const char *e = getenv("LCC_GEMM_PAIR"); return !(e && e[0] == '0'); }();
+    if (pair) {
+        switch (nb) {
+            case 64: return launch_pair_t<64>((const float *)x.data, x.ld, (float *)out.data, out.ld, x.n, w_hi, w_lo, s);
+            case 128: return launch_pair_t<128>((const float *)x.data, x.ld, (float *)out.data, out.ld, x.n, w_hi, w_lo, s);
+            case 256: return launch_pair_t<256>((const float *)x.data, x.ld, (float *)out.data, out.ld, x.n, w_hi, w_lo, s);
+        }
+        return cudaErrorNotSupported;
+    }
     static const int chunk = [] { const char *e = getenv("LCC_GEMM_CHUNK"); return e && atoi(e) == 32 ? 32 : 16; }();
 #define LCC_GEMM_CASE(NBV)                                                                                                   \
     case NBV:                                                                                                                \

@@ -382,7 +382,7 @@ def test_fixed_operand_product_on_tensor_cores(L, sig):
     alg, o = algebras(L, sig)
     nb = o.num_blades
     rng = np.random.default_rng(31)
-    for n in (1, 127, 128, 129, 5000):
+    for n in (1, 127, 128, 129, 257, 5000, 40001):  # 40001 rows: several 256-row tiles per CTA pair, ragged tail
         m = rng.standard_normal((1, nb)).astype(np.float32)
         x = rng.standard_normal((n, nb)).astype(np.float32)
         M, X = L.MultivectorBatch.from_numpy(alg, m), L.MultivectorBatch.from_numpy(alg, x)
