@@ -95,6 +95,72 @@ addsub_aos(const T *__restrict__ a, int64_t lda, int a_bc, const T *__restrict__
     out[r * ldo + k] = sub ? va - vb : va + vb;
 }
 
+// ------------------------------------------------------------------------------------------ K3 on AoS rows, 128-bit
+// One thread per 16-byte chunk (W consecutive blades of one row); consecutive threads take consecutive chunks,
+// so every warp instruction moves 512 contiguous bytes.  The per-blade tables sit in shared memory (indexing the
+// by-value BladeMap with a lane-dependent blade serialises on the constant bank: the scalar kernel above runs at
+// 0.95 TB/s, this one at copy speed).  DIAG: source[k] == k for every blade (reverse, involutions, grade, scale,
+// even/odd), so the input chunk is one vector load too -- skipped when all its factors are zero (grade projection
+// then reads only the blades it keeps).  Otherwise (duals) the W inputs are gathered from the same row.
+template <class T, bool DIAG>
+__global__ void __launch_bounds__(kThreads)
+blade_map_aos_vec(const T *__restrict__ x, int64_t ldx, T *__restrict__ out, int64_t ldo, int64_t n, int nb, int log2cpr,
+                  const BladeMap map, T scale) {
+    constexpr int W = VecW<T>::value;
+    __shared__ T sfac[256];
+    __shared__ uint16_t ssrc[256];
+    for (int k = threadIdx.x; k < nb; k += kThreads) {
+        const int f = map.factor[k];
+        sfac[k] = f == 0 ? T(0) : (f > 0 ? scale : -scale);
+        ssrc[k] = map.source[k];
+    }
+    __syncthreads();
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t r = c >> log2cpr;
+    if (r >= n) return;
+    const int k0 = (int)(c & ((1 << log2cpr) - 1)) * W;
+    T f[W], v[W];
+    bool any = false;
+#pragma unroll
+    for (int l = 0; l < W; ++l) { f[l] = sfac[k0 + l]; any |= f[l] != T(0); }
+    if (DIAG) {
+        if (any) ldg_stream(x + r * ldx + k0, v);
+#pragma unroll
+        for (int l = 0; l < W; ++l) v[l] = f[l] != T(0) ? mul_rn(v[l], f[l]) : T(0);
+    } else {
+#pragma unroll
+        for (int l = 0; l < W; ++l) v[l] = f[l] != T(0) ? mul_rn(__ldg(x + r * ldx + ssrc[k0 + l]), f[l]) : T(0);
+    }
+    stg_stream(out + r * ldo + k0, v);
+}
+
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+addsub_aos_vec(const T *__restrict__ a, int64_t lda, int a_bc, const T *__restrict__ b, int64_t ldb, int b_bc,
+               T *__restrict__ out, int64_t ldo, int64_t n, int log2cpr, int sub) {
+    constexpr int W = VecW<T>::value;
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t r = c >> log2cpr;
+    if (r >= n) return;
+    const int k0 = (int)(c & ((1 << log2cpr) - 1)) * W;
+    T va[W], vb[W];
+    if (a_bc) {
+#pragma unroll
+        for (int l = 0; l < W; ++l) va[l] = __ldg(a + k0 + l);
+    } else ldg_stream(a + r * lda + k0, va);
+    if (b_bc) {
+#pragma unroll
+        for (int l = 0; l < W; ++l) vb[l] = __ldg(b + k0 + l);
+    } else ldg_stream(b + r * ldb + k0, vb);
+#pragma unroll
+    for (int l = 0; l < W; ++l) va[l] = sub ? va[l] - vb[l] : va[l] + vb[l];
+    stg_stream(out + r * ldo + k0, va);
+}
+
+static inline bool aos_vec_ok(const ViewArg &v, int nb, int W) {
+    return nb >= W && ((uintptr_t)v.data & 15) == 0 && (v.ld % W) == 0;
+}
+
 // ------------------------------------------------------------------------------------------ K4
 // norm^2[r] = sum_k w[k] * x[r][k]^2, k ascending, w[k] = sign[k][k]*reverse_sign(k): the scalar part
 // of x*~x that batch.rs:685-711 reaches through its double loop (only j == i lands on blade 0).
@@ -121,6 +187,101 @@ norm_kernel(const T *__restrict__ x, int64_t ldx, int64_t n, int nb, const Weigh
         const T v = LAYOUT == kSoA ? __ldg(x + (int64_t)k * ldx + r) : __ldg(x + r * ldx + k);
         const T o = divide ? div_rn(v, nrm) : v;
         if (LAYOUT == kSoA) out[(int64_t)k * ldo + r] = o; else out[r * ldo + k] = o;
+    }
+}
+
+// AoS rows by lane groups: a row of nb blades is nb/W consecutive 16-byte chunks = cpr consecutive lanes of one
+// warp (cpr <= 32), every lane loads one chunk (fully coalesced), the running sum travels through the group with
+// warp shuffles in ascending blade order -- the reference's summation order, so STRICT stays bit-exact -- and for
+// `normalized` each lane scales and stores the chunk it already holds: one read and one write per element.
+template <class T, bool STRICT>
+__global__ void __launch_bounds__(kThreads)
+norm_aos_lanes(const T *__restrict__ x, int64_t ldx, int64_t n, int log2cpr, const Weights wt, int mode,
+               T *__restrict__ norms, T *__restrict__ out, int64_t ldo) {
+    constexpr int W = VecW<T>::value;
+    const int cpr = 1 << log2cpr;
+    __shared__ int8_t sw[256];                 // lane-dependent blade index: shared memory, not the constant bank
+    if (threadIdx.x < cpr * W) sw[threadIdx.x] = wt.w[threadIdx.x];
+    __syncthreads();
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t r = c >> log2cpr;
+    const int j = (int)(c & (cpr - 1));       // chunk inside the row == position inside the lane group
+    const bool live = r < n;                   // whole lane groups are live or not (kThreads % cpr == 0)
+    T v[W];
+#pragma unroll
+    for (int l = 0; l < W; ++l) v[l] = T(0);
+    if (live) ldg_stream(x + r * ldx + j * W, v);
+    int w[W];
+#pragma unroll
+    for (int l = 0; l < W; ++l) w[l] = sw[j * W + l];
+    T acc = T(0);
+    if (STRICT) {
+        for (int step = 0; step < cpr; ++step) {   // lane `step` of each group extends the running sum
+            const T incoming = __shfl_up_sync(0xffffffffu, acc, 1, cpr);
+            if (j == step) {
+                if (step > 0) acc = incoming;
+#pragma unroll
+                for (int l = 0; l < W; ++l)
+                    if (w[l] != 0) acc = Arith<true>::madd(w[l] > 0 ? v[l] : -v[l], v[l], acc);
+            }
+        }
+        acc = __shfl_sync(0xffffffffu, acc, cpr - 1, cpr);  // the last lane holds the row's total
+    } else {                                       // default mode: per-lane partial, then a butterfly over the group
+#pragma unroll
+        for (int l = 0; l < W; ++l)
+            if (w[l] != 0) acc = Arith<false>::madd(w[l] > 0 ? v[l] : -v[l], v[l], acc);
+        for (int o = cpr >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, cpr);
+    }
+    if (!live) return;
+    if (mode == 0) { if (j == 0) norms[r] = acc; return; }
+    const T nrm = sqrt_rn(acc < T(0) ? -acc : acc);
+    if (mode == 1) { if (j == 0) norms[r] = nrm; return; }
+    if (nrm > (T)1e-14) {                      // batch.rs:805-811
+        if (STRICT) {
+#pragma unroll
+            for (int l = 0; l < W; ++l) v[l] = div_rn(v[l], nrm);
+        } else {                               // one division per row instead of one per element (<= 1 ulp apart)
+            const T inv = div_rn(T(1), nrm);
+#pragma unroll
+            for (int l = 0; l < W; ++l) v[l] = mul_rn(v[l], inv);
+        }
+    }
+    stg_stream(out + r * ldo + j * W, v);
+}
+
+// SoA `normalized` with the row held in registers (NB known at compile time): one read and one write per element.
+template <class T, bool STRICT, int NB>
+__global__ void __launch_bounds__(kThreads)
+normalized_soa_regs(const T *__restrict__ x, int64_t ldx, int64_t n, const Weights wt, T *__restrict__ out, int64_t ldo) {
+    constexpr int V = NB >= 32 ? 1 : (NB >= 16 && sizeof(T) == 8 ? 1 : VecW<T>::value);
+    const int64_t r0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * V;
+    if (r0 >= n) return;
+    T v[NB][V], acc[V];
+#pragma unroll
+    for (int l = 0; l < V; ++l) acc[l] = T(0);
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        ldg_stream(x + (int64_t)k * ldx + r0, v[k]);
+        const int w = wt.w[k];
+        if (w != 0) {
+#pragma unroll
+            for (int l = 0; l < V; ++l) acc[l] = Arith<STRICT>::madd(w > 0 ? v[k][l] : -v[k][l], v[k][l], acc[l]);
+        }
+    }
+    T nrm[V], inv[V];
+#pragma unroll
+    for (int l = 0; l < V; ++l) {
+        nrm[l] = sqrt_rn(acc[l] < T(0) ? -acc[l] : acc[l]);
+        inv[l] = nrm[l] > (T)1e-14 ? div_rn(T(1), nrm[l]) : T(1);  // default mode: one division per row
+    }
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+#pragma unroll
+        for (int l = 0; l < V; ++l) {
+            if (STRICT) v[k][l] = nrm[l] > (T)1e-14 ? div_rn(v[k][l], nrm[l]) : v[k][l];
+            else if (nrm[l] > (T)1e-14) v[k][l] = mul_rn(v[k][l], inv[l]);
+        }
+        stg_stream(out + (int64_t)k * ldo + r0, v[k]);
     }
 }
 
@@ -172,6 +333,37 @@ sum_partial_aos(const T *__restrict__ x, int64_t ldx, int64_t n, int nb, int64_t
     if (threadIdx.x < nb) {
         double total = 0.0;
         for (int l = 0; l < lanes; ++l) total += lane_part[l * nb + threadIdx.x];
+        partial[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = total;
+    }
+}
+
+// 128-bit form: thread (row lane, chunk j) adds W blades of every (kThreads / cpr)-th row of the block's range in
+// f64, then the row lanes are folded in a fixed order.  Same fixed-tree guarantee, 16-byte coalesced loads.
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+sum_partial_aos_vec(const T *__restrict__ x, int64_t ldx, int64_t n, int nb, int log2cpr, int64_t rows_per_block,
+                    double *__restrict__ partial) {
+    constexpr int W = VecW<T>::value;
+    __shared__ double part[kThreads * W];
+    const int cpr = 1 << log2cpr, lanes = kThreads >> log2cpr;
+    const int j = threadIdx.x & (cpr - 1), lane = threadIdx.x >> log2cpr;
+    const int64_t begin = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t end = begin + rows_per_block < n ? begin + rows_per_block : n;
+    double acc[W];
+#pragma unroll
+    for (int l = 0; l < W; ++l) acc[l] = 0.0;
+    for (int64_t r = begin + lane; r < end; r += lanes) {
+        T v[W];
+        ldg_stream(x + r * ldx + j * W, v);
+#pragma unroll
+        for (int l = 0; l < W; ++l) acc[l] += (double)v[l];
+    }
+#pragma unroll
+    for (int l = 0; l < W; ++l) part[(lane * cpr + j) * W + l] = acc[l];  // [lane][blade]
+    __syncthreads();
+    if (threadIdx.x < nb) {
+        double total = 0.0;
+        for (int l = 0; l < lanes; ++l) total += part[l * nb + threadIdx.x];
         partial[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = total;
     }
 }
@@ -385,6 +577,14 @@ cudaError_t launch_blade_map(int nb, const ViewArg &x, const ViewArg &out, const
             constexpr int W = VecW<T>::value;
             dim3 grid(blocks_for((n + W - 1) / W), nb);
             blade_map_soa<T><<<grid, kThreads, 0, s>>>((const T *)x.data, x.ld, (T *)out.data, out.ld, n, map, (T)scale);
+        } else if (aos_vec_ok(x, nb, VecW<T>::value) && aos_vec_ok(out, nb, VecW<T>::value)) {
+            constexpr int W = VecW<T>::value;
+            const int cpr = nb / W;
+            bool diag = true;
+            for (int k = 0; k < nb; ++k) diag = diag && (map.factor[k] == 0 || map.source[k] == k);
+            const unsigned grid = blocks_for(n * cpr);
+            if (diag) blade_map_aos_vec<T, true><<<grid, kThreads, 0, s>>>((const T *)x.data, x.ld, (T *)out.data, out.ld, n, nb, ilog2(cpr), map, (T)scale);
+            else blade_map_aos_vec<T, false><<<grid, kThreads, 0, s>>>((const T *)x.data, x.ld, (T *)out.data, out.ld, n, nb, ilog2(cpr), map, (T)scale);
         } else {
             blade_map_aos<T><<<blocks_for(n * nb), kThreads, 0, s>>>((const T *)x.data, x.ld, (T *)out.data, out.ld, n, ilog2(nb), map, (T)scale);
         }
@@ -401,6 +601,9 @@ cudaError_t launch_addsub(int nb, int op, const ViewArg &a, bool a_bc, const Vie
             constexpr int W = VecW<T>::value;
             dim3 grid(blocks_for((n + W - 1) / W), nb);
             addsub_soa<T><<<grid, kThreads, 0, s>>>((const T *)a.data, a.ld, a_bc, (const T *)b.data, b.ld, b_bc, (T *)out.data, out.ld, n, op);
+        } else if (aos_vec_ok(a, nb, VecW<T>::value) && aos_vec_ok(b, nb, VecW<T>::value) && aos_vec_ok(out, nb, VecW<T>::value)) {
+            const int cpr = nb / VecW<T>::value;
+            addsub_aos_vec<T><<<blocks_for(n * cpr), kThreads, 0, s>>>((const T *)a.data, a.ld, a_bc, (const T *)b.data, b.ld, b_bc, (T *)out.data, out.ld, n, ilog2(cpr), op);
         } else {
             addsub_aos<T><<<blocks_for(n * nb), kThreads, 0, s>>>((const T *)a.data, a.ld, a_bc, (const T *)b.data, b.ld, b_bc, (T *)out.data, out.ld, n, ilog2(nb), op);
         }
@@ -416,6 +619,35 @@ cudaError_t launch_norm(int nb, int mode, bool strict, const ViewArg &x, const i
     auto run = [&](auto tag) {
         using T = decltype(tag);
         const unsigned g = blocks_for(n);
+        constexpr int W = VecW<T>::value;
+        // strict norms (no output row to write) stay on the row-per-thread kernel: the bit-exact lane chain is
+        // latency-bound and only pays off when it saves the second pass of `normalized`
+        if (x.layout == kAoS && nb / W <= 32 && aos_vec_ok(x, nb, W) && (mode != 2 || aos_vec_ok(out, nb, W)) && !(strict && mode != 2)) {
+            const int cpr = nb / W;
+            const unsigned gl = blocks_for(n * cpr);
+            if (strict) norm_aos_lanes<T, true><<<gl, kThreads, 0, s>>>((const T *)x.data, x.ld, n, ilog2(cpr), wt, mode, (T *)norms, (T *)out.data, out.ld);
+            else norm_aos_lanes<T, false><<<gl, kThreads, 0, s>>>((const T *)x.data, x.ld, n, ilog2(cpr), wt, mode, (T *)norms, (T *)out.data, out.ld);
+            return;
+        }
+        if (x.layout == kSoA && mode == 2 && (nb == 4 || nb == 8 || nb == 16 || nb == 32) && ((uintptr_t)x.data & 15) == 0 &&
+            ((uintptr_t)out.data & 15) == 0 && x.ld % W == 0 && out.ld % W == 0) {
+#define LCC_NORMALIZED_CASE(NBV)                                                                                                  \
+    case NBV: {                                                                                                                   \
+        constexpr int V = NBV >= 32 ? 1 : (NBV >= 16 && sizeof(T) == 8 ? 1 : W);                                                  \
+        const unsigned gr = blocks_for((n + V - 1) / V);                                                                          \
+        if (n % V != 0) break; /* padded rows are addressable (ld >= n rounded up), but keep the tail on the generic kernel */  \
+        if (strict) normalized_soa_regs<T, true, NBV><<<gr, kThreads, 0, s>>>((const T *)x.data, x.ld, n, wt, (T *)out.data, out.ld); \
+        else normalized_soa_regs<T, false, NBV><<<gr, kThreads, 0, s>>>((const T *)x.data, x.ld, n, wt, (T *)out.data, out.ld);   \
+        return;                                                                                                                   \
+    }
+            switch (nb) {
+                LCC_NORMALIZED_CASE(4)
+                LCC_NORMALIZED_CASE(8)
+                LCC_NORMALIZED_CASE(16)
+                LCC_NORMALIZED_CASE(32)
+            }
+#undef LCC_NORMALIZED_CASE
+        }
 #define LCC_NORM_LAUNCH(STRICT, LAYOUT) \
     norm_kernel<T, STRICT, LAYOUT><<<g, kThreads, 0, s>>>((const T *)x.data, x.ld, n, nb, wt, mode, (T *)norms, (T *)out.data, out.ld)
         if (x.layout == kSoA) { if (strict) LCC_NORM_LAUNCH(true, kSoA); else LCC_NORM_LAUNCH(false, kSoA); }
@@ -442,6 +674,9 @@ cudaError_t launch_sum(int nb, const ViewArg &x, void *sums_dev, void *scratch_d
         using T = decltype(tag);
         if (x.layout == kSoA) {
             sum_partial_soa<T><<<dim3(nblocks, nb), kThreads, 0, s>>>((const T *)x.data, x.ld, n, rows_per_block, (double *)scratch_dev);
+        } else if (aos_vec_ok(x, nb, VecW<T>::value)) {
+            const int cpr = nb / VecW<T>::value;
+            sum_partial_aos_vec<T><<<nblocks, kThreads, 0, s>>>((const T *)x.data, x.ld, n, nb, ilog2(cpr), rows_per_block, (double *)scratch_dev);
         } else {
             sum_partial_aos<T><<<nblocks, kThreads, 0, s>>>((const T *)x.data, x.ld, n, nb, rows_per_block, (double *)scratch_dev);
         }

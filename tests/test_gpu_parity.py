@@ -613,3 +613,96 @@ def test_product_family_scalar_multivectors(L):
         a.commutator(f1)
     with pytest.raises(ValueError, match="algebra mismatch"):
         a.right_contraction(f1)
+
+
+# ----------------------------------------------------------------------------------------------- K3 / K4 / K5 on reference-layout views
+@pytest.mark.parametrize("sig", [(3, 0, 0), (3, 0, 1), (4, 1, 0), (2, 0, 0), (1, 0, 0), (6, 0, 0), (8, 0, 0)])
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_unary_norm_sum_on_aos_views(L, sig, dt):
+    """Row-wise maps, add / sub, norms, normalized and the batch sum through the raw C ABI on (N, num_blades)
+    row-major views (what lcc.torch passes): the 128-bit chunk kernels, the lane-group norm (which keeps the
+    reference's ascending-blade summation order, so it is bit-exact in strict mode) and their scalar fallbacks
+    (row pitch not a multiple of 16 bytes)."""
+    from largecrimsoncanine_b200 import cabi
+
+    lib = cabi.lib()
+    o, alg = oracle.OracleAlgebra(*sig), cabi.Algebra(*sig)
+    nb = o.num_blades
+    code = cabi.LCC_F64 if dt == np.float64 else cabi.LCC_F32
+    rng = np.random.default_rng(41)
+    S = cabi.LCC_FLAG_STRICT_FP
+    dev = _Dev(lib)
+    for n, pad in ((1, 0), (37, 0), (1000, 0), (513, 1)):
+        ld = nb + pad
+        a, b = rand(rng, n, nb, dt), rand(rng, n, nb, dt)
+        a[n // 2] = 0.0  # a zero row: normalized leaves it unchanged (batch.rs:805-811)
+
+        def image(x):
+            img = np.full((x.shape[0], ld), 7.0, dt)
+            img[:, :nb] = x
+            return img
+
+        ia = image(a)
+        pa, pb, po = dev.put(ia), dev.put(image(b)), dev.put(image(np.zeros_like(a)))
+        va, vb, vo = (cabi.view(p.value, n, ld, code, cabi.LCC_AOS) for p in (pa, pb, po))
+
+        def result():
+            got = dev.get(po, ia)
+            assert np.all(got[:, nb:] == 7.0)
+            return got[:, :nb]
+
+        for op, ref in ((cabi.LCC_UN_REVERSE, o.reverse), (cabi.LCC_UN_INVOLUTE, o.grade_involution), (cabi.LCC_UN_CONJUGATE, o.clifford_conjugate)):
+            cabi.check(lib.lcc_batch_unary(alg.h, op, 0, C.byref(va), C.byref(vo), None))
+            assert np.array_equal(result(), ref(a))
+        for g in range(0, o.dimension + 1, max(1, o.dimension // 2)):
+            cabi.check(lib.lcc_batch_unary(alg.h, cabi.LCC_UN_GRADE, g, C.byref(va), C.byref(vo), None))
+            assert np.array_equal(result(), o.grade(a, g))
+        if dt == np.float64 and sig[2] == 0:  # the permuting (non-diagonal) map
+            cabi.check(lib.lcc_batch_unary(alg.h, cabi.LCC_UN_DUAL, 0, C.byref(va), C.byref(vo), None))
+            assert np.array_equal(result(), o.dual(a))
+        cabi.check(lib.lcc_batch_scale(alg.h, C.byref(va), 0.375, C.byref(vo), None))
+        assert np.array_equal(result(), o.scale(a, 0.375))
+        for op, ref in ((cabi.LCC_EW_ADD, o.add), (cabi.LCC_EW_SUB, o.sub)):
+            cabi.check(lib.lcc_batch_elementwise(alg.h, op, C.byref(va), C.byref(vb), C.byref(vo), None))
+            assert np.array_equal(result(), ref(a, b))
+        one = rand(rng, 1, nb, dt)
+        p1 = dev.put(np.ascontiguousarray(one))
+        v1 = cabi.view(p1.value, 1, nb, code, cabi.LCC_AOS)
+        if n > 1:
+            cabi.check(lib.lcc_batch_elementwise(alg.h, cabi.LCC_EW_SUB, C.byref(va), C.byref(v1), C.byref(vo), None))
+            assert np.array_equal(result(), o.sub(a, one))
+        norms = np.zeros(n, dt)
+        pn = dev.put(norms)
+        for kind, ref in ((cabi.LCC_NORM_SQUARED, o.norm_squared), (cabi.LCC_NORM, o.norm)):
+            cabi.check(lib.lcc_batch_norm(alg.h, kind, C.byref(va), pn, S, None))
+            assert np.array_equal(dev.get(pn, norms), ref(a))
+            cabi.check(lib.lcc_batch_norm(alg.h, kind, C.byref(va), pn, 0, None))
+            if kind == cabi.LCC_NORM_SQUARED:  # |error| <= tol * sum_k a_k^2 (the cancellation-free bound)
+                assert np.all(np.abs(dev.get(pn, norms).astype(np.float64) - ref(a)) <= TOL[dt] * (a.astype(np.float64) ** 2).sum(axis=1) + 1e-300)
+        cabi.check(lib.lcc_batch_normalized(alg.h, C.byref(va), C.byref(vo), S, None))
+        assert np.array_equal(result(), o.normalized(a))
+        if sig[1] == 0:  # definite signature: no cancellation inside norm^2
+            cabi.check(lib.lcc_batch_normalized(alg.h, C.byref(va), C.byref(vo), 0, None))
+            np.testing.assert_allclose(result(), o.normalized(a), rtol=10 * TOL[dt], atol=TOL[dt])
+        sums = np.zeros(nb, dt)
+        ps = dev.put(sums)
+        cabi.check(lib.lcc_batch_sum(alg.h, C.byref(va), ps, None))
+        want, mag = o.sum(a)
+        assert np.all(np.abs(dev.get(ps, sums) - want) <= (1e-12 if dt == np.float64 else 2e-6) * np.maximum(mag, 1.0))
+        dev.free()
+
+
+@pytest.mark.parametrize("sig", [(3, 0, 0), (3, 0, 1), (4, 1, 0), (2, 0, 0)])
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_normalized_soa_register_kernel(L, strict, sig, dt):
+    """`normalized` on device-resident batches: the compile-time-NB kernel (rows in registers) for row counts
+    that are whole vectors, the generic kernel for the rest; both bit-exact in strict mode."""
+    alg, o = algebras(L, sig)
+    rng = np.random.default_rng(43)
+    for n in (4, 64, 1000, 1001, 4096):
+        a = rand(rng, n, o.num_blades, dt)
+        a[0] = 0.0
+        assert np.array_equal(L.MultivectorBatch.from_numpy(alg, a).normalized().to_numpy(), o.normalized(a))
+    if sig[1] == 0:  # definite signature: norm^2 has no cancellation, so the FMA / one-division-per-row form stays close
+        L.set_strict_fp(False)
+        np.testing.assert_allclose(L.MultivectorBatch.from_numpy(alg, a).normalized().to_numpy(), o.normalized(a), rtol=10 * TOL[dt], atol=TOL[dt])
