@@ -225,6 +225,12 @@ LCC_API lcc_status lcc_pga_points_embed(const lcc_algebra *alg, const void *xyz,
 LCC_API lcc_status lcc_pga_points_extract(const lcc_algebra *alg, const lcc_view *src, void *xyz, void *stream);
 LCC_API lcc_status lcc_cga_points_embed(const lcc_algebra *alg, const void *xyz, const lcc_view *dst, void *stream);
 LCC_API lcc_status lcc_cga_points_extract(const lcc_algebra *alg, const lcc_view *src, void *xyz, void *stream);
+/* Fused  xyz_out = pga_point_coords( M * pga_point(xyz_in) * ~M )  on dense (n,3) device arrays: embedding
+ * (pga.rs:131-134), the two-stage sandwich (batch.rs:452-497) and extraction (pga.rs:579-599) in one pass that
+ * moves 6 elements per point instead of 32.  motor: 16 doubles on the host.  Points whose transformed weight is
+ * below 1e-10 come back as NaN (the scalar API raises ValueError there).  In-place (xyz_out == xyz_in) is allowed. */
+LCC_API lcc_status lcc_pga_points_sandwich(const lcc_algebra *alg, int dtype, const double *motor, const void *xyz_in,
+                                           void *xyz_out, int64_t n, unsigned flags, void *stream);
 /* STA: sta_vector(t,x,y,z) is lcc_batch_scatter_columns onto blades 1,2,4,8 (src/sta.rs:105-109).
  * sta_bivector (src/sta.rs:202-212): eb = dense (n,6) rows (Ex,Ey,Ez,Bx,By,Bz).
  * sta_boost (src/sta.rs:253-296): velocity = dense (n,3); rows with |v| >= 1 (no rotor; ValueError in the

@@ -104,6 +104,7 @@ def lib():
         "lcc_pga_points_extract": (i32, [vp, V, vp, vp]),
         "lcc_cga_points_embed": (i32, [vp, vp, V, vp]),
         "lcc_cga_points_extract": (i32, [vp, V, vp, vp]),
+        "lcc_pga_points_sandwich": (i32, [vp, i32, C.POINTER(dbl), vp, vp, i64, u32, vp]),
         "lcc_sta_bivectors_embed": (i32, [vp, vp, V, vp]),
         "lcc_sta_boosts_embed": (i32, [vp, vp, V, vp]),
         "lcc_host_sandwich": (i32, [vp, i32, C.POINTER(dbl), vp, vp, i64, u32]),

@@ -727,6 +727,123 @@ template <bool STRICT, bool EVEN> static cudaError_t launch_sandwich_soa_tma(con
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------ K2 on compact PGA points
+// out_xyz = pga_point_coords(M * pga_point(xyz) * ~M) without ever materialising the 16-blade rows: 24 bytes per
+// point (f32) instead of the 128 of the dense layout.  Embedding and extraction are the reference's
+// (src/pga.rs:131-134: c[7]=1, c[14]=-x, c[13]=y, c[11]=-z;  :579-599: x=-c[14]/w, y=c[13]/w, z=-c[11]/w, w=c[7]),
+// the two product stages are the sandwich of batch.rs:452-497 with the terms whose x blade is structurally zero
+// left out (the reference skips them at run time: `if b == 0.0 { continue }`) and only the four blades the
+// extraction reads computed in stage two -- same roundings in the same order, so strict mode is bit-exact.
+// Rows whose weight |w| < 1e-10 have no finite point: NaN, as lcc_pga_points_extract writes them.
+// Data movement: a block's 1024 points are one contiguous 12 KB span; it is copied to shared memory with one
+// cp.async.bulk (1-D TMA), each thread handles 4 points (stride 256: bank-conflict free at 3 words per point),
+// the results overwrite the tile and leave with one bulk store.  The last, partial block uses plain accesses.
+#if LCC_NB == 16 && !LCC_RUNTIME_METRIC && defined(LCC_SIG_PGA3D)
+constexpr int kPointsPerBlock = 1024, kPointThreads = 256;
+__host__ __device__ constexpr bool point_blade(int k) { return k == 7 || k == 11 || k == 13 || k == 14; }
+
+template <bool STRICT, bool EVEN>
+static __device__ __forceinline__ void transform_point(const Coeffs &R, const Coeffs &Rrev, real x, real y, real z, real (&o)[3]) {
+    constexpr int V = 1;
+    Tile<real, NB, 1> X, RX;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) { X.v[k][0] = real(0); RX.v[k][0] = real(0); }
+    X.v[7][0] = real(1); X.v[14][0] = -x; X.v[13][0] = y; X.v[11][0] = -z;
+#define LCC_OUT_BEGIN(k) { real acc[V]; acc[0] = real(0);
+#define LCC_TERM(k, i, j, neg, flags)                                                                   \
+    if constexpr (point_blade(j) && (!EVEN || even_grade(i))) {                                        \
+        const real rv = (neg) ? -R.v[i] : R.v[i];                                                      \
+        acc[0] = Arith<STRICT>::madd(rv, X.v[j][0], acc[0]);                                           \
+    }
+#define LCC_OUT_END(k) RX.v[k][0] = acc[0]; }
+#include LCC_TERMS_FILE
+#undef LCC_TERM
+#undef LCC_OUT_END
+    real res[NB];
+#define LCC_TERM(k, i, j, neg, flags)                                                                   \
+    if constexpr (point_blade(k) && (!EVEN || even_grade(j))) {                                        \
+        const real rv = (neg) ? -Rrev.v[j] : Rrev.v[j];                                                \
+        acc[0] = Arith<STRICT>::madd(RX.v[i][0], rv, acc[0]);                                          \
+    }
+#define LCC_OUT_END(k) res[k] = acc[0]; }
+#include LCC_TERMS_FILE
+#undef LCC_OUT_BEGIN
+#undef LCC_TERM
+#undef LCC_OUT_END
+    const real w = res[7];
+    const bool ok = (w < real(0) ? -w : w) >= (real)1e-10;
+    const real nanv = (real)__int_as_float(0x7fc00000);
+    o[0] = ok ? div_rn(-res[14], w) : nanv;
+    o[1] = ok ? div_rn(res[13], w) : nanv;
+    o[2] = ok ? div_rn(-res[11], w) : nanv;
+}
+
+template <bool STRICT, bool EVEN>
+__global__ void __launch_bounds__(kPointThreads)
+pga_points_sandwich_kernel(const real *__restrict__ xyz_in, real *__restrict__ xyz_out, int64_t n, int bulk_ok,
+                           const Coeffs R, const Coeffs Rrev) {
+    __shared__ alignas(128) real tile[kPointsPerBlock * 3];
+    __shared__ uint64_t bar;
+    const int t = threadIdx.x;
+    const int64_t p0 = (int64_t)blockIdx.x * kPointsPerBlock;
+    const bool full = bulk_ok && p0 + kPointsPerBlock <= n;
+    constexpr uint32_t kTileBytes = kPointsPerBlock * 3 * sizeof(real);
+    if (full) {
+        if (t == 0) {
+            tma::mbar_init(&bar, 1);
+            tma::mbar_expect_tx(&bar, kTileBytes);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(tma::smem_u32(tile)), "l"(xyz_in + p0 * 3), "r"(kTileBytes), "r"(tma::smem_u32(&bar)) : "memory");
+        }
+        __syncthreads();
+        tma::mbar_wait(&bar, 0);
+    }
+#pragma unroll
+    for (int q = 0; q < kPointsPerBlock / kPointThreads; ++q) {
+        const int lp = t + q * kPointThreads;
+        const int64_t p = p0 + lp;
+        if (p >= n) break;
+        real x, y, z, o[3];
+        if (full) { x = tile[lp * 3]; y = tile[lp * 3 + 1]; z = tile[lp * 3 + 2]; }
+        else { x = __ldg(xyz_in + p * 3); y = __ldg(xyz_in + p * 3 + 1); z = __ldg(xyz_in + p * 3 + 2); }
+        transform_point<STRICT, EVEN>(R, Rrev, x, y, z, o);
+        if (full) { tile[lp * 3] = o[0]; tile[lp * 3 + 1] = o[1]; tile[lp * 3 + 2] = o[2]; }
+        else { xyz_out[p * 3] = o[0]; xyz_out[p * 3 + 1] = o[1]; xyz_out[p * 3 + 2] = o[2]; }
+    }
+    if (full) {
+        tma::fence_proxy_async();
+        __syncthreads();
+        if (t == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(xyz_out + p0 * 3), "r"(tma::smem_u32(tile)), "r"(kTileBytes) : "memory");
+            tma::store_commit_and_wait_read();
+        }
+    }
+}
+
+cudaError_t pga_points_sandwich(const SandwichArgs &g);  // x / out = dense (n,3) arrays here
+#if LCC_PART == 3 && LCC_PART_STRICT == 0
+template <bool STRICT, bool EVEN> static cudaError_t launch_points_t(const SandwichArgs &g, const Coeffs &R, const Coeffs &Rrev) {
+    const int bulk_ok = ((uintptr_t)g.x % 16 == 0) && ((uintptr_t)g.out % 16 == 0);
+    const unsigned grid = (unsigned)((g.n + kPointsPerBlock - 1) / kPointsPerBlock);
+    pga_points_sandwich_kernel<STRICT, EVEN><<<grid, kPointThreads, 0, g.stream>>>((const real *)g.x, (real *)g.out, g.n, bulk_ok, R, Rrev);
+    note_kernel_launch();
+    return cudaGetLastError();
+}
+cudaError_t pga_points_sandwich(const SandwichArgs &g) {
+    if (g.n <= 0) return cudaSuccess;
+    Coeffs R = to_coeffs(g.rotor, 0.0), Rrev;
+    for (int i = 0; i < NB; ++i) {
+        int grade = 0;
+        for (int b = i; b; b >>= 1) grade += b & 1;
+        Rrev.v[i] = R.v[i] * ((grade % 4 < 2) ? real(1) : real(-1));  // src/batch.rs:452-457
+    }
+    if (g.strict) return g.even ? launch_points_t<true, true>(g, R, Rrev) : launch_points_t<true, false>(g, R, Rrev);
+    return g.even ? launch_points_t<false, true>(g, R, Rrev) : launch_points_t<false, false>(g, R, Rrev);
+}
+#endif
+#endif  // PGA3D
+
 // ------------------------------------------------------------------------------------------ entry points, by part
 // One (signature, precision) is compiled as several object files so that ptxas runs in parallel
 // (_build.py writes one stub per part):

@@ -52,6 +52,9 @@ static const GenericEntry kGenericEntries[] = {
 #undef LCC_GENERIC_ENTRY
     {-1, {nullptr, nullptr}, {nullptr, nullptr}}};
 
+cudaError_t launch_pga_points_sandwich_float(const SandwichArgs &);   // the Cl(3,0,1) translation units
+cudaError_t launch_pga_points_sandwich_double(const SandwichArgs &);
+
 static thread_local uint64_t t_launches = 0;
 void note_kernel_launch() { ++t_launches; }
 
@@ -846,6 +849,26 @@ lcc_status lcc_pga_points_embed(const lcc_algebra *alg, const void *xyz, const l
 lcc_status lcc_pga_points_extract(const lcc_algebra *alg, const lcc_view *src, void *xyz, void *stream) { return points_extract(alg, 0, src, xyz, stream); }
 lcc_status lcc_cga_points_embed(const lcc_algebra *alg, const void *xyz, const lcc_view *dst, void *stream) { return points_embed(alg, 1, xyz, dst, stream); }
 lcc_status lcc_cga_points_extract(const lcc_algebra *alg, const lcc_view *src, void *xyz, void *stream) { return points_extract(alg, 1, src, xyz, stream); }
+lcc_status lcc_pga_points_sandwich(const lcc_algebra *alg, int dtype, const double *motor, const void *xyz_in, void *xyz_out,
+                                   int64_t n, unsigned flags, void *stream) {
+    if (!alg) return fail(LCC_ERR_VALUE, "algebra handle is NULL");
+    LCC_TRY(points_check(alg, 0));
+    if (dtype != LCC_F32 && dtype != LCC_F64) return fail(LCC_ERR_VALUE, "dtype must be LCC_F32 or LCC_F64");
+    if (!motor) return fail(LCC_ERR_VALUE, "motor is NULL");
+    if (n < 0) return fail(LCC_ERR_VALUE, "n must be >= 0");
+    if (n == 0) return LCC_OK;
+    if (!xyz_in || !xyz_out) return fail(LCC_ERR_VALUE, "xyz is NULL");
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    SandwichArgs g;
+    g.dtype = dtype; g.strict = (flags & LCC_FLAG_STRICT_FP) != 0; g.n = n;
+    g.even = true;
+    for (int i = 0; i < 16; ++i)
+        if ((popcount32((unsigned)i) & 1) && motor[i] != 0.0) g.even = false;
+    g.rotor = motor; g.x = xyz_in; g.out = xyz_out; g.stream = s;
+    LCC_CUDA(dtype == LCC_F32 ? launch_pga_points_sandwich_float(g) : launch_pga_points_sandwich_double(g));
+    return LCC_OK;
+}
 lcc_status lcc_sta_bivectors_embed(const lcc_algebra *alg, const void *eb, const lcc_view *dst, void *stream) { return points_embed(alg, 2, eb, dst, stream); }
 lcc_status lcc_sta_boosts_embed(const lcc_algebra *alg, const void *velocity, const lcc_view *dst, void *stream) { return points_embed(alg, 3, velocity, dst, stream); }
 

@@ -479,6 +479,29 @@ PYBIND11_MODULE(largecrimsoncanine, m) {
           "Reproduce the reference's rounding sequence bit for bit (separate multiply and add) instead of FMA.");
     m.def("get_strict_fp", [] { return g_strict_fp; });
     m.def("kernel_launch_count", [] { return lcc_kernel_launch_count(); });
+    m.def("pga_transform_points", [](const PyAlgebra &a, const Multivector &motor, const py::array &xyz_in) {
+        // pga_point_coords(M * pga_point(x,y,z) * ~M) for an (N,3) array, fused on the device (include/lcc_b200.h)
+        require_pga3d(a, "pga_transform_points");
+        if (motor.coeffs.size() != 16) throw py::value_error("motor must be a PGA3D multivector (16 blades)");
+        py::array xyz = contiguous(xyz_in);
+        const int dtype = dtype_of(xyz);
+        if (xyz.ndim() != 2 || xyz.shape(1) != 3) throw py::value_error("points must have 3 columns");
+        py::array out(np_dtype(dtype), std::vector<py::ssize_t>{xyz.shape(0), 3});
+        const size_t bytes = (size_t)xyz.nbytes();
+        if (bytes == 0) return out;
+        const void *host = xyz.data();
+        void *out_ptr = out.mutable_data();
+        const int64_t n = xyz.shape(0);
+        const std::vector<double> m = motor.coeffs;
+        const unsigned flags = fp_flags();
+        py::gil_scoped_release nogil;
+        DeviceTemp stage(bytes);
+        upload(host, bytes, stage.ptr);
+        check(lcc_pga_points_sandwich(a.inner->h, dtype, m.data(), stage.ptr, stage.ptr, n, flags, nullptr));
+        check(lcc_memcpy_d2h(out_ptr, stage.ptr, bytes, nullptr));
+        check(lcc_stream_sync(nullptr));
+        return out;
+    }, "Apply a PGA3D motor to an (N,3) array of points: embed, sandwich and extract fused in one kernel.");
     m.def("set_option", [](const std::string &name, int64_t value) { check(lcc_set_option(name.c_str(), value)); },
           "Tuning knobs of the engine (include/lcc_b200.h, lcc_set_option); results never depend on them.");
     m.def("get_option", [](const std::string &name) { int64_t v = 0; check(lcc_get_option(name.c_str(), &v)); return v; });

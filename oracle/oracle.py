@@ -16,7 +16,7 @@ from . import build as _build
 __all__ = [
     "OracleAlgebra", "basis_square", "reorder_sign", "blade_product", "blade_grade", "reverse_sign",
     "grade_involution_sign", "clifford_conjugate_sign", "grade_mask", "max_threads", "lib_path",
-    "sta_bivectors", "sta_boosts",
+    "sta_bivectors", "sta_boosts", "pga_points_embed", "pga_points_extract", "pga_transform_points",
 ]
 
 _LIB = None
@@ -423,3 +423,29 @@ def sta_boosts(v):
             out[r, 0] = ch
             out[r, 3], out[r, 5], out[r, 9] = -sh * (vx / vmag), -sh * (vy / vmag), -sh * (vz / vmag)
     return out
+
+
+# ----------------------------------------------------------------------------- PGA points (compact form)
+def pga_points_embed(xyz):
+    """Row-wise Multivector::pga_point, src/pga.rs:131-134: c[7]=1, c[14]=-x, c[13]=y, c[11]=-z."""
+    xyz = _arr(xyz)
+    out = np.zeros((xyz.shape[0], 16), dtype=xyz.dtype)
+    out[:, 7] = 1.0
+    out[:, 14], out[:, 13], out[:, 11] = -xyz[:, 0], xyz[:, 1], -xyz[:, 2]
+    return out
+
+
+def pga_points_extract(c):
+    """Row-wise Multivector::pga_point_coords, src/pga.rs:579-599; NaN where the reference raises (|w| < 1e-10)."""
+    c = _arr(c)
+    w = c[:, 7]
+    ok = np.abs(w) >= 1e-10
+    safe = np.where(ok, w, 1)
+    out = np.stack([-c[:, 14] / safe, c[:, 13] / safe, -c[:, 11] / safe], axis=1).astype(c.dtype)
+    out[~ok] = np.nan
+    return out
+
+
+def pga_transform_points(motor, xyz, threads=1):
+    """pga_point_coords(M * pga_point(xyz) * ~M): embedding, batch.rs:434-503 sandwich, extraction."""
+    return pga_points_extract(OracleAlgebra(3, 0, 1).sandwich(motor, pga_points_embed(xyz), threads=threads))

@@ -706,3 +706,32 @@ def test_normalized_soa_register_kernel(L, strict, sig, dt):
     if sig[1] == 0:  # definite signature: norm^2 has no cancellation, so the FMA / one-division-per-row form stays close
         L.set_strict_fp(False)
         np.testing.assert_allclose(L.MultivectorBatch.from_numpy(alg, a).normalized().to_numpy(), o.normalized(a), rtol=10 * TOL[dt], atol=TOL[dt])
+
+
+# ----------------------------------------------------------------------------------------------- compact PGA points
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_pga_points_fused_sandwich(L, dt):
+    """(N,3) xyz -> motor -> (N,3) xyz in one kernel: bit-exact in strict mode against embed + sandwich + extract
+    of the oracle (src/pga.rs:131-134, batch.rs:434-503, pga.rs:579-599), full bulk-copied blocks and the ragged
+    tail, even motors (pruned kernel) and dense versors, and it agrees with the unfused batched path."""
+    pga = L.Algebra.pga(3)
+    rng = np.random.default_rng(47)
+    motor = L.Multivector.pga_motor_from_axis_angle(pga, [1.0, 2.0, 3.0], [0.5, -0.25, 1.0], 0.7)
+    dense = L.Multivector.from_list_in([float(v) for v in rng.standard_normal(16)], pga)
+    for n in (1, 5, 1024, 1027, 5000):
+        xyz = rng.standard_normal((n, 3)).astype(dt)
+        for M in (motor, dense):
+            m = np.array(M.coefficients())
+            L.set_strict_fp(True)
+            try:
+                got = L.pga_transform_points(pga, M, xyz)
+            finally:
+                L.set_strict_fp(False)
+            want = oracle.pga_transform_points(m, xyz)
+            assert got.dtype == dt and np.array_equal(got, want, equal_nan=True), (n, np.abs(got - want).max())
+            fast = L.pga_transform_points(pga, M, xyz)
+            np.testing.assert_allclose(fast, want, rtol=10 * TOL[dt], atol=10 * TOL[dt])
+        unfused = L.MultivectorBatch.from_points_pga(pga, xyz).sandwich(motor).pga_point_coords()
+        np.testing.assert_allclose(L.pga_transform_points(pga, motor, xyz), unfused, rtol=10 * TOL[dt], atol=10 * TOL[dt])
+    with pytest.raises(ValueError):
+        L.pga_transform_points(L.Algebra.cga(3), motor, xyz)
