@@ -14,7 +14,12 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <algorithm>
+#include <array>
+#include <chrono>
 #include <cmath>
+#include <limits>
+#include <optional>
 #include <cstdlib>
 #include <map>
 #include <memory>
@@ -472,6 +477,8 @@ std::string repr_float(double v) { return py::cast<std::string>(py::repr(py::flo
 
 }  // namespace
 
+#include "multivector_methods.inc"
+
 PYBIND11_MODULE(largecrimsoncanine, m) {
     m.doc() = "B200-native drop-in for the batched path of LargeCrimsonCanine (Algebra, Multivector, MultivectorBatch)";
     m.attr("__version__") = lcc_version();
@@ -568,7 +575,16 @@ PYBIND11_MODULE(largecrimsoncanine, m) {
     // ------------------------------------------------------------------ Multivector
     py::class_<Multivector> mv(m, "Multivector");
     mv.def(py::init([](std::vector<double> c) { return Multivector::from_coeffs(std::move(c)); }))
-        .def_static("from_list", [](std::vector<double> c) { return Multivector::from_coeffs(std::move(c)); })
+        .def_static("from_list", [](std::vector<double> c) {  // src/multivector.rs:351-369 (its own messages)
+            const size_t len = c.size();
+            if (len == 0) throw py::value_error("coefficient list must not be empty");
+            if (len & (len - 1)) {
+                std::ostringstream s; s << "coefficient list length " << len << " is not a power of 2; expected 2^dims (e.g., 2, 4, 8, 16, ...)";
+                throw py::value_error(s.str());
+            }
+            int dims = 0; while ((size_t(1) << dims) < len) ++dims;
+            return Multivector{std::move(c), dims, nullptr};
+        })
         .def_static("zero", [](int dims) {
             if (dims <= 0) throw py::value_error("dimension must be at least 1");
             return Multivector{std::vector<double>(size_t(1) << dims, 0.0), dims, nullptr};
@@ -593,11 +609,18 @@ PYBIND11_MODULE(largecrimsoncanine, m) {
             c[size_t(1) << (index - 1)] = 1.0;
             return Multivector{std::move(c), dims, nullptr};
         }, py::arg("index"), py::arg("dims"))
-        .def_static("from_bivector", [](std::vector<double> comps, int dims) {
-            auto bl = blades_of_grade(1 << dims, 2);
-            if (comps.size() != bl.size()) throw py::value_error("wrong number of bivector components");
+        .def_static("from_bivector", [](std::vector<double> comps, int dims) {  // src/multivector.rs:1228-1258
+            if (dims < 2) throw py::value_error("dimension must be at least 2 for bivectors");
+            const size_t expected = (size_t)dims * (dims - 1) / 2;
+            if (comps.size() != expected) {
+                std::ostringstream s; s << "expected " << expected << " bivector components for Cl(" << dims << ") (got " << comps.size() << "); components are [e12, e13, e23, ...] in lexicographic order";
+                throw py::value_error(s.str());
+            }
             std::vector<double> c(size_t(1) << dims, 0.0);
-            for (size_t i = 0; i < bl.size(); ++i) c[bl[i]] = comps[i];
+            size_t next = 0;
+            for (int i = 0; i < dims; ++i)            // e_i ^ e_j, i < j, pairs in lexicographic order:
+                for (int j = i + 1; j < dims; ++j)    // e12, e13, e14, e23, ... (NOT ascending blade index from 4-D on)
+                    c[(size_t(1) << i) | (size_t(1) << j)] = comps[next++];
             return Multivector{std::move(c), dims, nullptr};
         }, py::arg("components"), py::arg("dims"))
         .def_static("from_list_in", [](std::vector<double> c, const PyAlgebra &a) {  // additive: coefficients + explicit algebra
@@ -644,7 +667,7 @@ PYBIND11_MODULE(largecrimsoncanine, m) {
         })
         .def("algebra", [](const Multivector &a) -> py::object { if (!a.algebra_opt) return py::none(); return py::cast(PyAlgebra{a.algebra_opt}); })
         .def_property_readonly("dims", [](const Multivector &a) { return a.dims; })
-        .def("dimension", [](const Multivector &a) { return a.dims; })
+        .def_property_readonly("dimension", [](const Multivector &a) { return a.dims; })  // #[getter], src/multivector.rs:1994-1997
         .def("scalar", [](const Multivector &a) { return a.coeffs[0]; })
         .def("coefficients", [](const Multivector &a) { return a.coeffs; })
         .def("to_list", [](const Multivector &a) { return a.coeffs; })
@@ -1070,6 +1093,8 @@ PYBIND11_MODULE(largecrimsoncanine, m) {
         });
 
     // ------------------------------------------------------------------ MultivectorBatch (src/batch.rs)
+    bind_multivector_methods(m, mv);
+
     py::class_<Batch, BatchPtr>(m, "MultivectorBatch")
         .def_static("from_numpy", &batch_from_numpy, py::arg("algebra"), py::arg("coeffs"))
         .def_static("from_vectors", [](const PyAlgebra &a, const py::array &coords) {  // :112-138
