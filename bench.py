@@ -196,14 +196,18 @@ def run_reference_arm(args):
         times.append(t)
     ms = 1e3 * float(np.mean(times))
     value = rows / (ms / 1e3)
+    cores = oracle.max_threads()
+    all_cores_value = cpu_rate(wl, rows, cores)[0] if cores > threads else value  # what an OpenMP-over-rows port would do
+    n = 1 << (args.log2_rows or log2n)
     line = {
         "impl": "reference", "metric": f"{wl} throughput", "value": value, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": dt, "data": "synthetic",
-        "config": {"workload": workload_name(wl), "sample_rows_per_step": rows},
+        "config": {"workload": workload_name(wl), "rows_per_gpu": n, "layout": "AoS (N, num_blades) row-major in host memory (the reference's Array2)",
+                   "l2_policy": "n/a (CPU arm)", "strict_fp": True, "sample_rows_per_step": rows},
         "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port",
                          "sample": f"{rows} rows per step of the same synthetic workload; the reference is single-threaded (GIL held, no threads)",
-                         "host_threads_available": oracle.max_threads()},
+                         "host_threads_available": cores, "all_cores_value": all_cores_value, "all_cores": cores},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -238,6 +242,10 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # the only collective of the path is a 16..256-element all-reduce: one channel (one CTA) is enough, and every
+        # extra NCCL CTA spin-waiting for a slower rank takes SM slots away from the streaming kernel it overlaps with
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "1")
+        os.environ.setdefault("NCCL_MAX_CTAS", "1")
         dist.init_process_group("nccl", device_id=dev)
     lib = cabi.lib()
     cabi.check(lib.lcc_set_device(local))
@@ -278,6 +286,10 @@ def run_gpu_arm(args):
         return (t[idx] if aos_layout else t[:, idx].T).contiguous().cpu().numpy()
 
     motor = None
+
+    def drain():  # workloads with asynchronous collectives override this
+        pass
+
     if wl == "pga_sandwich":
         x = torch.zeros((nb, n), device=dev, dtype=tdt)
         pts = torch.randn((3, n), device=dev, dtype=tdt, generator=gen)
@@ -318,14 +330,28 @@ def run_gpu_arm(args):
     elif wl == "sta_fused_grade_inner_sum":
         a = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
         b = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
-        sums = torch.zeros(nb, device=dev, dtype=tdt)
+        # the per-GPU partial (16 values) is all-reduced asynchronously on NCCL's stream into a small ring of
+        # result buffers, so the collective of step i overlaps the kernel of step i+1 instead of serialising with it
+        ring = [torch.zeros(nb, device=dev, dtype=tdt) for _ in range(4)]
+        pending = [None] * len(ring)
+        turn = [0]
+        sums = ring[0]
         out = None
         va, vb = soa(a), soa(b)
 
         def step():
-            cabi.check(lib.lcc_batch_product_sum(alg.h, cabi.LCC_OP_LC, C.byref(va), 1, C.byref(vb), C.c_void_p(sums.data_ptr()), flags, sptr))
+            i = turn[0] % len(ring)
+            turn[0] += 1
+            if pending[i] is not None:
+                pending[i].wait()  # the buffer's previous all-reduce (four steps ago) has completed
+            cabi.check(lib.lcc_batch_product_sum(alg.h, cabi.LCC_OP_LC, C.byref(va), 1, C.byref(vb), C.c_void_p(ring[i].data_ptr()), flags, sptr))
             if world > 1:
-                dist.all_reduce(sums)
+                pending[i] = dist.all_reduce(ring[i], async_op=True)
+
+        def drain():
+            for h in pending:
+                if h is not None:
+                    h.wait()
     elif wl == "cl8_fixed_gp":
         b = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
         a = torch.randn((nb, 4), device=dev, dtype=tdt, generator=gen)  # the fixed operand: one-row SoA view, ld = 4
@@ -358,6 +384,7 @@ def run_gpu_arm(args):
 
     for _ in range(max(args.warmup, 3)):
         step()
+    drain()
     barrier()
     lib.lcc_kernel_launch_count_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -366,6 +393,7 @@ def run_gpu_arm(args):
         e0.record(stream)
         for _ in range(args.steps):
             step()
+        drain()  # every outstanding all-reduce is inside the timed region
         e1.record(stream)
         barrier()
     launches = int(lib.lcc_kernel_launch_count())
