@@ -29,6 +29,7 @@ struct ProductArgs {
     double *sum_partial = nullptr;
     int sum_blocks = 0;
     int a_grade = -1;
+    int list = 0;  // term list: 0 forward product; 1 / 2 cotangent of the left / right operand (a, b = the list's operands)
     cudaStream_t stream = nullptr;
 };
 

@@ -8,6 +8,9 @@
 //                          mu[i & j] in {+1,-1,0} arrives as a kernel argument (any Cl(p,q,r))
 //   LCC_REAL            float or double
 //   LCC_TU              token used to name the two exported launchers
+//   LCC_VJP0_FILE / LCC_VJP1_FILE   term lists of the vector-Jacobian products (gen_cayley.py, emit_vjp_terms);
+//                       the product kernels take a LIST template argument: 0 forward, 1 / 2 cotangent of the
+//                       left / right operand (autograd of lcc.torch)
 //
 // Reference semantics (file:line in /root/reference): out[i^j] += sign[i][j]*a[i]*b[j], i outer,
 // j inner, src/batch.rs:384-404 (geometric), :544-568 (outer, (i&j)==0), :615-649 (left
@@ -93,7 +96,7 @@ template <int LAYOUT, int V> struct Sink {
 };
 
 // ------------------------------------------------------------------------------------------ K1
-template <int LAYOUT, int OP, bool STRICT>
+template <int LAYOUT, int OP, bool STRICT, int LIST = 0>
 __global__ void __launch_bounds__(kThreads)
 product_kernel(const real *__restrict__ a, int64_t lda, int a_bcast, const real *__restrict__ b, int64_t ldb,
                int b_bcast, real *__restrict__ out, int64_t ldo, real *__restrict__ out2, int64_t ldo2,
@@ -116,22 +119,32 @@ product_kernel(const real *__restrict__ a, int64_t lda, int a_bcast, const real 
     (void)mu;
 
 #define LCC_OUT_BEGIN(k) { real acc[V]; real acc2[V]; _Pragma("unroll") for (int l = 0; l < V; ++l) { acc[l] = real(0); acc2[l] = real(0); }
-#define LCC_TERM(k, i, j, neg, flags)                                                                   \
+#define LCC_TERM6(k, i, j, neg, flags, mi)                                                                   \
     if constexpr (term_in_op(OP, flags, k)) {                                                             \
         _Pragma("unroll") for (int l = 0; l < V; ++l) {                                                \
             real av = (neg) ? -A.v[i][l] : A.v[i][l];                                                  \
-            if constexpr (kRuntimeMetric) av = mul_rn(av, mu.v[(i) & (j)]);                            \
+            if constexpr (kRuntimeMetric) av = mul_rn(av, mu.v[mi]);                            \
             acc[l] = Arith<STRICT>::madd(av, B.v[j][l], acc[l]);                                       \
             if constexpr (OP == kOpGPOuter && ((flags) & 1)) acc2[l] = Arith<STRICT>::madd(av, B.v[j][l], acc2[l]); \
             if constexpr (two_sided(OP)) {                                                             \
                 real bv = (neg) ? -B.v[i][l] : B.v[i][l];                                              \
-                if constexpr (kRuntimeMetric) bv = mul_rn(bv, mu.v[(i) & (j)]);                        \
+                if constexpr (kRuntimeMetric) bv = mul_rn(bv, mu.v[mi]);                        \
                 acc2[l] = Arith<STRICT>::madd(bv, A.v[j][l], acc2[l]);                                 \
             }                                                                                          \
         }                                                                                              \
     }
 #define LCC_OUT_END(k) finish_two_sided<OP>(acc, acc2); sink.template put<k>(acc); if constexpr (OP == kOpGPOuter) sink2.template put<k>(acc2); }
+#define LCC_TERM(k, i, j, neg, flags) LCC_TERM6(k, i, j, neg, flags, (i) & (j))
+#define LCC_VTERM(k, i, j, neg, flags, mi) LCC_TERM6(k, i, j, neg, flags, mi)
+    if constexpr (LIST == 0) {
 #include LCC_TERMS_FILE
+    } else if constexpr (LIST == 1) {
+#include LCC_VJP0_FILE
+    } else {
+#include LCC_VJP1_FILE
+    }
+#undef LCC_VTERM
+#undef LCC_TERM6
 #undef LCC_OUT_BEGIN
 #undef LCC_TERM
 #undef LCC_OUT_END
@@ -305,7 +318,7 @@ static __device__ __forceinline__ void tma_store_tile(const CUtensorMap *map, co
         tma::store_2d(map, src + sub * TmaTile::kRows * TmaTile::kSpan, sub * (TmaTile::kSpan / (int)sizeof(real)), row0);
 }
 
-template <int OP, bool STRICT>
+template <int OP, bool STRICT, int LIST = 0>
 __global__ void __launch_bounds__(TmaTile::kRows)
 product_kernel_aos_tma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                        const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out2,
@@ -333,20 +346,30 @@ product_kernel_aos_tma(const __grid_constant__ CUtensorMap map_a, const __grid_c
     (void)mu;
     constexpr int V = 1;
 #define LCC_OUT_BEGIN(k) { real acc[V]; real acc2[V]; acc[0] = real(0); acc2[0] = real(0);
-#define LCC_TERM(k, i, j, neg, flags)                                                                   \
+#define LCC_TERM6(k, i, j, neg, flags, mi)                                                                   \
     if constexpr (term_in_op(OP, flags, k)) {                                                             \
         real av = (neg) ? -A.v[i][0] : A.v[i][0];                                                      \
-        if constexpr (kRuntimeMetric) av = mul_rn(av, mu.v[(i) & (j)]);                                \
+        if constexpr (kRuntimeMetric) av = mul_rn(av, mu.v[mi]);                                \
         acc[0] = Arith<STRICT>::madd(av, B.v[j][0], acc[0]);                                           \
         if constexpr (OP == kOpGPOuter && ((flags) & 1)) acc2[0] = Arith<STRICT>::madd(av, B.v[j][0], acc2[0]); \
         if constexpr (two_sided(OP)) {                                                                 \
             real bv = (neg) ? -B.v[i][0] : B.v[i][0];                                                  \
-            if constexpr (kRuntimeMetric) bv = mul_rn(bv, mu.v[(i) & (j)]);                            \
+            if constexpr (kRuntimeMetric) bv = mul_rn(bv, mu.v[mi]);                            \
             acc2[0] = Arith<STRICT>::madd(bv, A.v[j][0], acc2[0]);                                     \
         }                                                                                              \
     }
 #define LCC_OUT_END(k) finish_two_sided<OP>(acc, acc2); sink.template put<k>(acc); if constexpr (OP == kOpGPOuter) sink2.template put<k>(acc2); }
+#define LCC_TERM(k, i, j, neg, flags) LCC_TERM6(k, i, j, neg, flags, (i) & (j))
+#define LCC_VTERM(k, i, j, neg, flags, mi) LCC_TERM6(k, i, j, neg, flags, mi)
+    if constexpr (LIST == 0) {
 #include LCC_TERMS_FILE
+    } else if constexpr (LIST == 1) {
+#include LCC_VJP0_FILE
+    } else {
+#include LCC_VJP1_FILE
+    }
+#undef LCC_VTERM
+#undef LCC_TERM6
 #undef LCC_OUT_BEGIN
 #undef LCC_TERM
 #undef LCC_OUT_END
@@ -522,7 +545,7 @@ static __device__ __forceinline__ void load_bcast_soa(Tile<real, NB, V> &t, cons
     }
 }
 
-template <int OP, bool STRICT>
+template <int OP, bool STRICT, int LIST = 0>
 __global__ void __launch_bounds__(SoaProductTile::kThreads)
 product_kernel_soa_tma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                        const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out2,
@@ -551,22 +574,32 @@ product_kernel_soa_tma(const __grid_constant__ CUtensorMap map_a, const __grid_c
     (void)sink2;
     (void)mu;
 #define LCC_OUT_BEGIN(k) { real acc[V]; real acc2[V]; _Pragma("unroll") for (int l = 0; l < V; ++l) { acc[l] = real(0); acc2[l] = real(0); }
-#define LCC_TERM(k, i, j, neg, flags)                                                                   \
+#define LCC_TERM6(k, i, j, neg, flags, mi)                                                                   \
     if constexpr (term_in_op(OP, flags, k)) {                                                             \
         _Pragma("unroll") for (int l = 0; l < V; ++l) {                                                \
             real av = (neg) ? -A.v[i][l] : A.v[i][l];                                                  \
-            if constexpr (kRuntimeMetric) av = mul_rn(av, mu.v[(i) & (j)]);                            \
+            if constexpr (kRuntimeMetric) av = mul_rn(av, mu.v[mi]);                            \
             acc[l] = Arith<STRICT>::madd(av, B.v[j][l], acc[l]);                                       \
             if constexpr (OP == kOpGPOuter && ((flags) & 1)) acc2[l] = Arith<STRICT>::madd(av, B.v[j][l], acc2[l]); \
             if constexpr (two_sided(OP)) {                                                             \
                 real bv = (neg) ? -B.v[i][l] : B.v[i][l];                                              \
-                if constexpr (kRuntimeMetric) bv = mul_rn(bv, mu.v[(i) & (j)]);                        \
+                if constexpr (kRuntimeMetric) bv = mul_rn(bv, mu.v[mi]);                        \
                 acc2[l] = Arith<STRICT>::madd(bv, A.v[j][l], acc2[l]);                                 \
             }                                                                                          \
         }                                                                                              \
     }
 #define LCC_OUT_END(k) finish_two_sided<OP>(acc, acc2); sink.template put<k>(acc); if constexpr (OP == kOpGPOuter) sink2.template put<k>(acc2); }
+#define LCC_TERM(k, i, j, neg, flags) LCC_TERM6(k, i, j, neg, flags, (i) & (j))
+#define LCC_VTERM(k, i, j, neg, flags, mi) LCC_TERM6(k, i, j, neg, flags, mi)
+    if constexpr (LIST == 0) {
 #include LCC_TERMS_FILE
+    } else if constexpr (LIST == 1) {
+#include LCC_VJP0_FILE
+    } else {
+#include LCC_VJP1_FILE
+    }
+#undef LCC_VTERM
+#undef LCC_TERM6
 #undef LCC_OUT_BEGIN
 #undef LCC_TERM
 #undef LCC_OUT_END
@@ -645,7 +678,7 @@ static inline bool aos_map(CUtensorMap *m, const void *base, int64_t ld, int64_t
 }
 
 // returns cudaErrorNotSupported when the operands do not qualify (caller falls back to the direct kernel)
-template <int OP, bool STRICT> static cudaError_t launch_product_tma(const ProductArgs &g) {
+template <int OP, bool STRICT, int LIST = 0> static cudaError_t launch_product_tma(const ProductArgs &g) {
     if constexpr (!kHasTmaPath) {
         return cudaErrorNotSupported;
     } else {
@@ -656,7 +689,7 @@ template <int OP, bool STRICT> static cudaError_t launch_product_tma(const Produ
         if (!g.a_bcast && !aos_map(&ma, g.a, g.lda, g.n)) return cudaErrorNotSupported;
         if (!g.b_bcast && !aos_map(&mb, g.b, g.ldb, g.n)) return cudaErrorNotSupported;
         if (OP == kOpGPOuter && !aos_map(&mo2, g.out2, g.ldo2, g.n)) return cudaErrorNotSupported;
-        auto kernel = product_kernel_aos_tma<OP, STRICT>;
+        auto kernel = product_kernel_aos_tma<OP, STRICT, LIST>;
         constexpr int smem = 2 * TmaTile::kBytes + 1024 + 16;
         static const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (attr != cudaSuccess) return attr;
@@ -692,7 +725,7 @@ template <class CFG> static inline bool soa_map(CUtensorMap *m, const void *base
     return make_soa_tensor_map(m, base, (int)sizeof(real), NB, ld, n, CFG::kBoxRows);
 }
 
-template <int OP, bool STRICT> static cudaError_t launch_product_soa_tma(const ProductArgs &g) {
+template <int OP, bool STRICT, int LIST = 0> static cudaError_t launch_product_soa_tma(const ProductArgs &g) {
     using T_ = SoaProductTile;
     if (!soa_tma_enabled() || g.n * (int64_t)kRowBytes < option_soa_tma_min_bytes()) return cudaErrorNotSupported;
     CUtensorMap ma, mb, mo, mo2;
@@ -701,7 +734,7 @@ template <int OP, bool STRICT> static cudaError_t launch_product_soa_tma(const P
     if (!g.a_bcast && !soa_map<T_>(&ma, g.a, g.lda, g.n)) return cudaErrorNotSupported;
     if (!g.b_bcast && !soa_map<T_>(&mb, g.b, g.ldb, g.n)) return cudaErrorNotSupported;
     if (OP == kOpGPOuter && !soa_map<T_>(&mo2, g.out2, g.ldo2, g.n)) return cudaErrorNotSupported;
-    auto kernel = product_kernel_soa_tma<OP, STRICT>;
+    auto kernel = product_kernel_soa_tma<OP, STRICT, LIST>;
     constexpr int smem = 2 * T_::kBytes + 1024 + 16;
     static const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (attr != cudaSuccess) return attr;
@@ -851,17 +884,19 @@ cudaError_t pga_points_sandwich(const SandwichArgs &g) {
 //   LCC_PART 2  product kernels on TMA tiles, AoS and SoA    (LCC_PART_STRICT = 0 / 1)
 //   LCC_PART 3  sandwich kernels, direct and TMA             (LCC_PART_STRICT = 0 / 1)
 //   LCC_PART 4  fused product + batch-sum kernels and the two routers the dispatcher calls
+//   LCC_PART 5  vector-Jacobian products (direct and TMA forms)
 cudaError_t product_direct_s0(const ProductArgs &g);
 cudaError_t product_direct_s1(const ProductArgs &g);
 cudaError_t product_tma_s0(const ProductArgs &g);  // cudaErrorNotSupported: operands do not qualify, use the direct kernels
 cudaError_t product_tma_s1(const ProductArgs &g);
 cudaError_t sandwich_s0(const SandwichArgs &g);
 cudaError_t sandwich_s1(const SandwichArgs &g);
+cudaError_t product_vjp(const ProductArgs &g);      // g.list = 1 / 2
 cudaError_t launch_product(const ProductArgs &g);
 cudaError_t launch_sandwich(const SandwichArgs &g);
 
 #ifndef LCC_PART
-#error "define LCC_PART (1-4) before including product_impl.cuh"
+#error "define LCC_PART (1-5) before including product_impl.cuh"
 #endif
 #ifndef LCC_PART_STRICT
 #define LCC_PART_STRICT 0
@@ -908,6 +943,40 @@ cudaError_t LCC_CAT(product_tma_s, LCC_PART_STRICT)(const ProductArgs &g) {
 }
 #endif  // LCC_PART == 2
 
+#if LCC_PART == 5
+// cotangents of gp / outer / left contraction: the same kernels over the VJP term lists (FMA arithmetic; gradients
+// have no reference rounding order).  a = first operand of the list, b = second (lcc_abi.cu, lcc_batch_product_vjp).
+template <int LAYOUT, int OP, int LIST> static cudaError_t launch_vjp_t(const ProductArgs &g) {
+    if (g.n <= 0) return cudaSuccess;
+    cudaError_t e = LAYOUT == kSoA ? launch_product_soa_tma<OP, false, LIST>(g) : launch_product_tma<OP, false, LIST>(g);
+    if (e != cudaErrorNotSupported) return e;
+    constexpr int W = 16 / (int)sizeof(real);
+    int vec_ok = 1;
+    if (LAYOUT == kAoS) {
+        auto ok = [&](const void *p, int64_t ld) { return ((uintptr_t)p % 16 == 0) && (ld % W == 0); };
+        vec_ok = ok(g.a, g.lda) && ok(g.b, g.ldb) && ok(g.out, g.ldo);
+    }
+    product_kernel<LAYOUT, OP, false, LIST><<<grid_for<LAYOUT>(g.n), block_threads(), 0, g.stream>>>(
+        (const real *)g.a, g.lda, g.a_bcast, (const real *)g.b, g.ldb, g.b_bcast, (real *)g.out, g.ldo,
+        nullptr, 0, g.n, vec_ok, to_coeffs(g.mu, 1.0));
+    note_kernel_launch();
+    return cudaGetLastError();
+}
+template <int LAYOUT, int LIST> static cudaError_t launch_vjp_op(const ProductArgs &g) {
+    switch (g.op) {
+        case kOpGP: return launch_vjp_t<LAYOUT, kOpGP, LIST>(g);
+        case kOpOuter: return launch_vjp_t<LAYOUT, kOpOuter, LIST>(g);
+        case kOpLC: return launch_vjp_t<LAYOUT, kOpLC, LIST>(g);
+    }
+    return cudaErrorInvalidValue;
+}
+cudaError_t product_vjp(const ProductArgs &g) {
+    if (g.list == 1) return g.layout == kSoA ? launch_vjp_op<kSoA, 1>(g) : launch_vjp_op<kAoS, 1>(g);
+    if (g.list == 2) return g.layout == kSoA ? launch_vjp_op<kSoA, 2>(g) : launch_vjp_op<kAoS, 2>(g);
+    return cudaErrorInvalidValue;
+}
+#endif  // LCC_PART == 5
+
 #if LCC_PART == 3
 template <int LAYOUT, bool EVEN> static cudaError_t launch_sandwich_t(const SandwichArgs &g) {
     if (g.n <= 0) return cudaSuccess;
@@ -950,6 +1019,7 @@ template <int LAYOUT, bool STRICT> static cudaError_t launch_product_sum_op(cons
     return cudaErrorInvalidValue;
 }
 cudaError_t launch_product(const ProductArgs &g) {
+    if (g.list != 0) return product_vjp(g);
     if (g.sum_partial) {
         if (g.layout == kSoA) return g.strict ? launch_product_sum_op<kSoA, true>(g) : launch_product_sum_op<kSoA, false>(g);
         return g.strict ? launch_product_sum_op<kAoS, true>(g) : launch_product_sum_op<kAoS, false>(g);

@@ -624,9 +624,24 @@ lcc_status lcc_batch_product_vjp(const lcc_algebra *alg, int op, int wrt, const 
     if (grad_out->n == 0) return LCC_OK;
     cudaStream_t s;
     LCC_TRY(resolve_stream(stream, &s));
+    const bool strict = (flags & LCC_FLAG_STRICT_FP) != 0, other_bc = other->n == 1 && grad_out->n > 1;
+    if (alg->nb <= 32 && alg->product[grad_out->dtype]) {
+        // register kernels over the build-time VJP term lists (kernels/product_impl.cuh, LIST = 1 / 2): the cotangent
+        // streams at the same HBM rate as the forward product
+        ProductArgs g;
+        g.op = op; g.dtype = grad_out->dtype; g.layout = grad_out->layout; g.strict = false; g.n = grad_out->n;
+        g.list = 1 + wrt;
+        const lcc_view *first = wrt == 0 ? grad_out : other, *second = wrt == 0 ? other : grad_out;
+        g.a = first->data; g.lda = first->ld; g.a_bcast = wrt == 1 && other_bc;
+        g.b = second->data; g.ldb = second->ld; g.b_bcast = wrt == 0 && other_bc;
+        g.out = grad_in->data; g.ldo = grad_in->ld;
+        g.mu = alg->specialised ? nullptr : alg->mu.data();
+        g.stream = s;
+        LCC_CUDA(alg->product[grad_out->dtype](g));
+        return LCC_OK;
+    }
     const int8_t *gs = nullptr;
     LCC_TRY(gather_signs_on_device(alg, 16 + 16 * wrt + op, &gs));
-    const bool strict = (flags & LCC_FLAG_STRICT_FP) != 0, other_bc = other->n == 1 && grad_out->n > 1;
     if (wrt == 0) LCC_CUDA(launch_table_product(alg->nb, strict, arg_of(grad_out), false, arg_of(other), other_bc, arg_of(grad_in), gs, s));
     else LCC_CUDA(launch_table_product(alg->nb, strict, arg_of(other), other_bc, arg_of(grad_out), false, arg_of(grad_in), gs, s));
     return LCC_OK;

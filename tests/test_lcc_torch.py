@@ -66,12 +66,13 @@ def test_gradients_match_pytorch_autograd_of_the_same_bilinear_map(lt, sig, name
     T = sign_tensor(o, name)
     alg = lt.TorchAlgebra._from_signature(*sig, device="cuda")
     g = torch.Generator().manual_seed(11)
-    for nb_rows in (64, 1):  # full batch and broadcast right operand
-        a = torch.randn(64, o.num_blades, generator=g, dtype=torch.float64)
+    # full batch and broadcast right operand; 64 rows take the direct-load VJP kernels, 4500 rows the TMA-tile ones
+    for n, nb_rows in ((64, 64), (64, 1), (4500, 4500), (4500, 1)):
+        a = torch.randn(n, o.num_blades, generator=g, dtype=torch.float64)
         b = torch.randn(nb_rows, o.num_blades, generator=g, dtype=torch.float64)
-        w = torch.randn(64, o.num_blades, generator=g, dtype=torch.float64)
+        w = torch.randn(n, o.num_blades, generator=g, dtype=torch.float64)
         ar, br = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
-        ref = torch.einsum("ni,nj,ijk->nk", ar, br.expand(64, -1), T)
+        ref = torch.einsum("ni,nj,ijk->nk", ar, br.expand(n, -1), T)
         (ref * w).sum().backward()
         ac, bc = a.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
         A, B = lt.TorchMultivector(alg, ac), lt.TorchMultivector(alg, bc)
