@@ -83,9 +83,23 @@ def test_generated_term_lists_match_oracle():
             assert j == i ^ k and signs[i, j] == (-1 if neg else 1)
             assert last_i.get(k, -1) < i  # ascending left blade inside each output group
             last_i[k] = i
-            assert bool(flags & 1) == ((i & j) == 0) and bool(flags & 2) == ((i & j) == i)
+            assert bool(flags & 1) == ((i & j) == 0) and bool(flags & 2) == ((i & j) == i) and bool(flags & 4) == ((i & j) == j)
             seen[i, j] = signs[i, j]
         assert np.array_equal(seen, signs)  # every non-zero term emitted exactly where it belongs
+        # vector-Jacobian lists (autograd of lcc.torch): the same table transposed onto either operand
+        for wrt in (0, 1):
+            seen = np.zeros((nb, nb), np.int8)
+            for line in open(os.path.join(gen, "cayley_%d_%d_%d_vjp%d.inc" % (sig + (wrt,)))):
+                m = re.match(r"LCC_VTERM\((\d+), (\d+), (\d+), (\d), (\d), (\d+)\)", line)
+                if not m:
+                    continue
+                out, x, y, neg, flags, mi = map(int, m.groups())
+                i, j = (out, y) if wrt == 0 else (x, out)  # forward term (i, j) this cotangent term comes from
+                assert (x == i ^ j and y == j) if wrt == 0 else (x == i and y == i ^ j)
+                assert signs[i, j] == (-1 if neg else 1) and mi == i & j and seen[i, j] == 0
+                assert bool(flags & 1) == ((i & j) == 0) and bool(flags & 2) == ((i & j) == i) and bool(flags & 4) == ((i & j) == j)
+                seen[i, j] = signs[i, j]
+            assert np.array_equal(seen, signs)
     assert cabi.lib().lcc_algebra_is_specialised(cabi.Algebra(3, 0, 1).h) == 1
     assert cabi.lib().lcc_algebra_is_specialised(cabi.Algebra(2, 1, 1).h) == 0
 
