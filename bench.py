@@ -50,7 +50,9 @@ WORKLOADS["sta_fused_grade_inner_sum"] = ((1, 3, 0), "f64", 27, (4 + 16) * 8, "m
 WORKLOADS["pga_points_compact"] = ((3, 0, 1), "f32", 28, 24, "points/s")
 # BASELINE config 5: fixed operand x batch in Cl(8,0,0) on the tensor cores (tf32 x3): bound = tensor
 WORKLOADS["cl8_fixed_gp"] = ((8, 0, 0), "f32", 24, 2048, "products/s")
-TENSOR_FLOPS_PER_UNIT = {"cl8_fixed_gp": 3 * 2 * 256 * 256}  # three tf32 MMAs per term
+# the same product in the reference's own precision, on the FP64 tensor pipe (DMMA)
+WORKLOADS["cl8_fixed_gp_f64"] = ((8, 0, 0), "f64", 24, 4096, "products/s")
+TENSOR_FLOPS_PER_UNIT = {"cl8_fixed_gp": 3 * 2 * 256 * 256, "cl8_fixed_gp_f64": 2 * 256 * 256}  # f32: three tf32 MMAs per term
 HEADLINE = "pga_sandwich"
 
 
@@ -153,7 +155,7 @@ def cpu_rate(workload, sample_rows, threads, repeats=1):
     else:
         a = rng.standard_normal((sample_rows, nb)).astype(ndt)
         b = rng.standard_normal((sample_rows, nb)).astype(ndt)
-        if workload == "cl8_fixed_gp":
+        if workload in ("cl8_fixed_gp", "cl8_fixed_gp_f64"):
             fn = lambda: o.geometric_product(a[:1], b, threads=threads)  # noqa: E731
         elif workload == "cga_gp_outer":
             fn = lambda: (o.geometric_product(a, b, threads=threads), o.outer_product(a, b, threads=threads))  # noqa: E731
@@ -173,7 +175,7 @@ def cpu_rate(workload, sample_rows, threads, repeats=1):
 def cpu_sample_rows(workload):
     return {"pga_sandwich": 1 << 25, "cga_gp": 1 << 22, "cga_gp_outer": 1 << 22, "r3_gp": 1 << 20, "sta_grade_inner_sum": 1 << 23,
             "sta_fused_grade_inner_sum": 1 << 23,
-            "cl8_fixed_gp": 1 << 14}[workload]
+            "cl8_fixed_gp": 1 << 14, "cl8_fixed_gp_f64": 1 << 14, "pga_points_compact": 1 << 25}[workload]
 
 
 def run_reference_arm(args):
@@ -221,6 +223,7 @@ def workload_name(wl):
         "cga_gp_outer": "CGA Cl(4,1,0) fused geometric + outer product", "r3_gp": "Cl(3,0,0) batched geometric product",
         "sta_grade_inner_sum": "STA Cl(1,3,0) grade projection + inner product + batch sum",
         "cl8_fixed_gp": "Cl(8,0,0) fixed-operand left geometric product (tcgen05, 3xTF32)",
+        "cl8_fixed_gp_f64": "Cl(8,0,0) fixed-operand left geometric product, f64 (mma.sync m8n8k4 DMMA)",
         "sta_fused_grade_inner_sum": "STA Cl(1,3,0) fused grade projection + inner product + batch sum (one kernel)",
         "pga_points_compact": "PGA Cl(3,0,1) motor applied to compact (N,3) points, embed + sandwich + extract fused",
     }[wl]
@@ -352,7 +355,7 @@ def run_gpu_arm(args):
             for h in pending:
                 if h is not None:
                     h.wait()
-    elif wl == "cl8_fixed_gp":
+    elif wl in ("cl8_fixed_gp", "cl8_fixed_gp_f64"):
         b = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
         a = torch.randn((nb, 4), device=dev, dtype=tdt, generator=gen)  # the fixed operand: one-row SoA view, ld = 4
         out = torch.empty_like(b)
@@ -436,7 +439,7 @@ def run_gpu_arm(args):
             xs, ys = a[:, idx].T.contiguous().cpu().numpy(), b[:, idx].T.contiguous().cpu().numpy()
             got = out[:, idx].T.contiguous().cpu().numpy()
             want = o.left_contraction(o.grade(xs, 1), ys)
-        elif wl == "cl8_fixed_gp":
+        elif wl in ("cl8_fixed_gp", "cl8_fixed_gp_f64"):
             idx = idx[::64]
             ys = b[:, idx].T.contiguous().cpu().numpy().astype(np.float64)
             got = out[:, idx].T.contiguous().cpu().numpy()
@@ -502,6 +505,12 @@ def l2_policy(bytes_per_pass):
 
 def roofline_block(wl, n, kernel_ms, bytes_per, peaks, peak_kind, traffic):
     hbm = bytes_per * n / (kernel_ms / 1e3) / 1e9
+    if wl == "cl8_fixed_gp_f64":  # FP64 tensor pipe: no measured figure in MEASURED_PEAKS.json, nominal B200 FP64 = 40 TFLOP/s
+        tf = TENSOR_FLOPS_PER_UNIT[wl] * n / (kernel_ms / 1e3) / 1e12
+        return {"bound": "tensor", "achieved": tf, "peak": 40.0, "unit": "TFLOP/s", "frac": tf / 40.0, "traffic": traffic,
+                "peak_source": "nominal B200 FP64 tensor rate (40 TFLOP/s); MEASURED_PEAKS.json has no FP64 figure",
+                "tensor_flops_per_unit": TENSOR_FLOPS_PER_UNIT[wl], "hbm_gbs": hbm, "hbm_frac": hbm / float(peaks["hbm_gbs"]),
+                "algorithmic_bytes_per_unit": bytes_per}
     if wl in TENSOR_FLOPS_PER_UNIT:  # dense contraction: tensor-pipe bound; nominal dense tf32 peak is half the bf16 one
         tf = TENSOR_FLOPS_PER_UNIT[wl] * n / (kernel_ms / 1e3) / 1e12
         peak_tf32 = float(peaks.get("bf16_tflops", 1590.0)) / 2.0

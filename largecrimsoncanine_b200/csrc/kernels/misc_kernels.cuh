@@ -43,6 +43,10 @@ cudaError_t launch_table_product(int nb, bool strict, const ViewArg &x, bool x_b
 // on the tcgen05 tensor cores with the 3xTF32 split.  signs_dev = sign[a*nb+b]; scratch_w = 2*nb*nb floats.
 cudaError_t launch_fixed_product_tf32x3(int nb, int side, const int8_t *signs_dev, const float *fixed_dev, int64_t fixed_stride,
                                         const ViewArg &x, const ViewArg &out, float *scratch_w, cudaStream_t s);
+// K6d (fixed_operand_dmma.cu): the f64 form on the FP64 tensor pipe (mma.sync m8n8k4); scratch_w = nb*nb doubles.
+// cudaErrorNotSupported when the batch view is not 16-byte aligned with an even row pitch.
+cudaError_t launch_fixed_product_f64_dmma(int nb, int side, const int8_t *signs_dev, const double *fixed_dev, int64_t fixed_stride,
+                                          const ViewArg &x, const ViewArg &out, double *scratch_w, cudaStream_t s);
 // PGA3D / CGA3D point embeddings and extractors (src/pga.rs:131-134,579-599; src/cga.rs:189-206,492-508);
 // which 2 / 3: STA bivectors from (E,B) and boost rotors from velocities (src/sta.rs:202-212,253-296)
 cudaError_t launch_points_embed(int which, const void *xyz, const ViewArg &dst, cudaStream_t s);

@@ -501,6 +501,18 @@ static lcc_status run_product(const lcc_algebra *alg, int op, const lcc_view *a,
                                              arg_of(batch), arg_of(out), (float *)w.ptr, s));
         return LCC_OK;
     }
+    // the same contraction in the reference's own precision: f64 on the FP64 tensor pipe (K6d, mma.sync m8n8k4)
+    if (!tensor_path_off && op == kOpGP && !strict && a->dtype == LCC_F64 && a->layout == LCC_SOA && (a_bc != b_bc) &&
+        (alg->nb == 64 || alg->nb == 128 || alg->nb == 256)) {
+        const int8_t *signs_dev = nullptr;
+        LCC_TRY(gather_signs_on_device(alg, 48, &signs_dev));
+        PoolBuffer w;
+        LCC_TRY(w.alloc((size_t)alg->nb * alg->nb * sizeof(double), s));
+        const lcc_view *fixed = a_bc ? a : b, *batch = a_bc ? b : a;
+        const cudaError_t e = launch_fixed_product_f64_dmma(alg->nb, a_bc ? 0 : 1, signs_dev, (const double *)fixed->data, fixed->ld,
+                                                            arg_of(batch), arg_of(out), (double *)w.ptr, s);
+        if (e != cudaErrorNotSupported) { LCC_CUDA(e); return LCC_OK; }
+    }
     // 64..256 blades: table-driven shared-memory kernel (any layout)
     auto one = [&](int single_op, const lcc_view *dst) -> lcc_status {
         const int8_t *gs = nullptr;

@@ -398,6 +398,24 @@ def test_fixed_operand_product_on_tensor_cores(L, sig):
         L.set_strict_fp(False)
 
 
+@pytest.mark.parametrize("sig", [(6, 0, 0), (4, 2, 1), (8, 0, 0)])
+def test_fixed_operand_product_f64_on_the_fp64_tensor_pipe(L, sig):
+    """K6d: the same broadcast product in the reference's own precision -> DMMA GEMM (mma.sync m8n8k4.f64).
+    Tensor-core summation order, so the bar is the f64 tolerance of the path (1e-12 against the magnitude of the
+    terms); ragged sizes cover partial 128-row tiles and the zero-filled rows past the padded pitch."""
+    alg, o = algebras(L, sig)
+    nb = o.num_blades
+    rng = np.random.default_rng(53)
+    for n in (2, 127, 128, 129, 1000, 20001):
+        m = rng.standard_normal((1, nb))
+        x = rng.standard_normal((n, nb))
+        M, X = L.MultivectorBatch.from_numpy(alg, m), L.MultivectorBatch.from_numpy(alg, x)
+        for got, a, b in ((M.geometric_product(X).to_numpy(), m, x), (X.geometric_product(M).to_numpy(), x, m)):
+            ref = o.geometric_product(a, b)
+            bound = o.product_abs_bound("gp", np.abs(a), np.abs(b))
+            assert np.all(np.abs(got - ref) <= 1e-12 * np.maximum(np.abs(ref), bound))
+
+
 @pytest.mark.parametrize("sig", [(1, 3, 0), (3, 0, 1), (4, 1, 0), (2, 1, 1)])
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
 def test_fused_grade_product_sum(L, sig, dt):
