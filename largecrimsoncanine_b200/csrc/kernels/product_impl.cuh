@@ -42,7 +42,7 @@ constexpr bool kRuntimeMetric = LCC_RUNTIME_METRIC != 0;
 using real = LCC_REAL;
 constexpr int kRowsSoA = RowsPerThread<real, NB, kRuntimeMetric ? 256 : 512>::value;  // rows per thread, SoA
 
-struct Coeffs { real v[NB]; };  // a uniform multivector (rotor, metric factors) in the constant bank
+struct Coeffs { real v[NB]; int stream_hint; };  // a uniform multivector (rotor, metric factors) in the constant bank (+ the TMA L2 hint switch)
 
 __host__ __device__ constexpr bool even_grade(int blade) {
     int c = 0;
@@ -307,15 +307,15 @@ struct TileSink {  // collects 16 bytes of consecutive blades, then writes them 
 static __device__ __forceinline__ uint8_t *tma_smem_base(uint8_t *raw) {
     return (uint8_t *)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);  // swizzle patterns are functions of the address bits
 }
-static __device__ __forceinline__ void tma_load_tile(uint8_t *dst, const CUtensorMap *map, uint64_t *bar, int row0) {
+static __device__ __forceinline__ void tma_load_tile(uint8_t *dst, const CUtensorMap *map, uint64_t *bar, int row0, bool hint) {
 #pragma unroll
     for (int sub = 0; sub < TmaTile::kSub; ++sub)
-        tma::load_2d(dst + sub * TmaTile::kRows * TmaTile::kSpan, map, bar, sub * (TmaTile::kSpan / (int)sizeof(real)), row0);
+        tma::load_2d(dst + sub * TmaTile::kRows * TmaTile::kSpan, map, bar, sub * (TmaTile::kSpan / (int)sizeof(real)), row0, hint);
 }
-static __device__ __forceinline__ void tma_store_tile(const CUtensorMap *map, const uint8_t *src, int row0) {
+static __device__ __forceinline__ void tma_store_tile(const CUtensorMap *map, const uint8_t *src, int row0, bool hint) {
 #pragma unroll
     for (int sub = 0; sub < TmaTile::kSub; ++sub)
-        tma::store_2d(map, src + sub * TmaTile::kRows * TmaTile::kSpan, sub * (TmaTile::kSpan / (int)sizeof(real)), row0);
+        tma::store_2d(map, src + sub * TmaTile::kRows * TmaTile::kSpan, sub * (TmaTile::kSpan / (int)sizeof(real)), row0, hint);
 }
 
 template <int OP, bool STRICT, int LIST = 0>
@@ -330,8 +330,8 @@ product_kernel_aos_tma(const __grid_constant__ CUtensorMap map_a, const __grid_c
     if (t == 0) {
         tma::mbar_init(bar, 1);
         tma::mbar_expect_tx(bar, (a_row ? 0u : (uint32_t)TmaTile::kBytes) + (b_row ? 0u : (uint32_t)TmaTile::kBytes));
-        if (!a_row) tma_load_tile(tile_a, &map_a, bar, row0);
-        if (!b_row) tma_load_tile(tile_b, &map_b, bar, row0);
+        if (!a_row) tma_load_tile(tile_a, &map_a, bar, row0, mu.stream_hint != 0);
+        if (!b_row) tma_load_tile(tile_b, &map_b, bar, row0, mu.stream_hint != 0);
     }
     __syncthreads();  // the barrier word is initialised before anyone polls it
     Tile<real, NB, 1> A, B;
@@ -376,8 +376,8 @@ product_kernel_aos_tma(const __grid_constant__ CUtensorMap map_a, const __grid_c
     tma::fence_proxy_async();
     __syncthreads();
     if (t == 0) {
-        tma_store_tile(&map_out, tile_a, row0);
-        if constexpr (OP == kOpGPOuter) tma_store_tile(&map_out2, tile_b, row0);
+        tma_store_tile(&map_out, tile_a, row0, mu.stream_hint != 0);
+        if constexpr (OP == kOpGPOuter) tma_store_tile(&map_out2, tile_b, row0, mu.stream_hint != 0);
         tma::store_commit_and_wait_read();  // the tile must outlive the engine's read of it
     }
 }
@@ -393,7 +393,7 @@ sandwich_kernel_aos_tma(const __grid_constant__ CUtensorMap map_x, const __grid_
     if (t == 0) {
         tma::mbar_init(bar, 1);
         tma::mbar_expect_tx(bar, (uint32_t)TmaTile::kBytes);
-        tma_load_tile(tile, &map_x, bar, row0);
+        tma_load_tile(tile, &map_x, bar, row0, mu.stream_hint != 0);
     }
     __syncthreads();
     tma::mbar_wait(bar, 0);
@@ -427,15 +427,17 @@ sandwich_kernel_aos_tma(const __grid_constant__ CUtensorMap map_x, const __grid_
     tma::fence_proxy_async();
     __syncthreads();
     if (t == 0) {
-        tma_store_tile(&map_out, tile, row0);
+        tma_store_tile(&map_out, tile, row0, mu.stream_hint != 0);
         tma::store_commit_and_wait_read();
     }
 }
 
 // ------------------------------------------------------------------------------------------ host
 static inline Coeffs to_coeffs(const double *src, double fill) {
+    static const int hint = [] { const char *e = std::getenv("LCC_TMA_L2_HINT"); return (e && e[0] == '1') ? 1 : 0; }();
     Coeffs c;
     for (int i = 0; i < NB; ++i) c.v[i] = src ? (real)src[i] : (real)fill;
+    c.stream_hint = hint;
     return c;
 }
 
@@ -503,13 +505,13 @@ template <int TILE_BYTES> struct SoaTileCfg {
     static __device__ __forceinline__ size_t offset(int k, int r) {
         return ((size_t)(r / kBoxRows) * NB * kBoxRows + (size_t)k * kBoxRows + (r % kBoxRows)) * sizeof(real);
     }
-    static __device__ __forceinline__ void tma_load(uint8_t *dst, const CUtensorMap *map, uint64_t *bar, int row0) {
+    static __device__ __forceinline__ void tma_load(uint8_t *dst, const CUtensorMap *map, uint64_t *bar, int row0, bool hint) {
 #pragma unroll
-        for (int box = 0; box < kBoxes; ++box) tma::load_2d(dst + box * kBoxBytes, map, bar, row0 + box * kBoxRows, 0);
+        for (int box = 0; box < kBoxes; ++box) tma::load_2d(dst + box * kBoxBytes, map, bar, row0 + box * kBoxRows, 0, hint);
     }
-    static __device__ __forceinline__ void tma_store(const CUtensorMap *map, const uint8_t *src, int row0) {
+    static __device__ __forceinline__ void tma_store(const CUtensorMap *map, const uint8_t *src, int row0, bool hint) {
 #pragma unroll
-        for (int box = 0; box < kBoxes; ++box) tma::store_2d(map, src + box * kBoxBytes, row0 + box * kBoxRows, 0);
+        for (int box = 0; box < kBoxes; ++box) tma::store_2d(map, src + box * kBoxBytes, row0 + box * kBoxRows, 0, hint);
     }
 };
 using SoaProductTile = SoaTileCfg<LCC_SOA_TILE_BYTES>;
@@ -559,8 +561,8 @@ product_kernel_soa_tma(const __grid_constant__ CUtensorMap map_a, const __grid_c
     if (t == 0) {
         tma::mbar_init(bar, 1);
         tma::mbar_expect_tx(bar, (a_row ? 0u : (uint32_t)T_::kBytes) + (b_row ? 0u : (uint32_t)T_::kBytes));
-        if (!a_row) T_::tma_load(tile_a, &map_a, bar, row0);
-        if (!b_row) T_::tma_load(tile_b, &map_b, bar, row0);
+        if (!a_row) T_::tma_load(tile_a, &map_a, bar, row0, mu.stream_hint != 0);
+        if (!b_row) T_::tma_load(tile_b, &map_b, bar, row0, mu.stream_hint != 0);
     }
     __syncthreads();
     Tile<real, NB, V> A, B;
@@ -606,8 +608,8 @@ product_kernel_soa_tma(const __grid_constant__ CUtensorMap map_a, const __grid_c
     tma::fence_proxy_async();
     __syncthreads();
     if (t == 0) {
-        T_::tma_store(&map_out, tile_a, row0);
-        if constexpr (OP == kOpGPOuter) T_::tma_store(&map_out2, tile_b, row0);
+        T_::tma_store(&map_out, tile_a, row0, mu.stream_hint != 0);
+        if constexpr (OP == kOpGPOuter) T_::tma_store(&map_out2, tile_b, row0, mu.stream_hint != 0);
         tma::store_commit_and_wait_read();
     }
 }
@@ -625,7 +627,7 @@ sandwich_kernel_soa_tma(const __grid_constant__ CUtensorMap map_x, const __grid_
     if (t == 0) {
         tma::mbar_init(bar, 1);
         tma::mbar_expect_tx(bar, (uint32_t)T_::kBytes);
-        T_::tma_load(tile, &map_x, bar, row0);
+        T_::tma_load(tile, &map_x, bar, row0, mu.stream_hint != 0);
     }
     __syncthreads();
     tma::mbar_wait(bar, 0);
@@ -658,7 +660,7 @@ sandwich_kernel_soa_tma(const __grid_constant__ CUtensorMap map_x, const __grid_
     tma::fence_proxy_async();
     __syncthreads();
     if (t == 0) {
-        T_::tma_store(&map_out, tile, row0);
+        T_::tma_store(&map_out, tile, row0, mu.stream_hint != 0);
         tma::store_commit_and_wait_read();
     }
 }
@@ -866,6 +868,7 @@ template <bool STRICT, bool EVEN> static cudaError_t launch_points_t(const Sandw
 cudaError_t pga_points_sandwich(const SandwichArgs &g) {
     if (g.n <= 0) return cudaSuccess;
     Coeffs R = to_coeffs(g.rotor, 0.0), Rrev;
+    Rrev.stream_hint = R.stream_hint;
     for (int i = 0; i < NB; ++i) {
         int grade = 0;
         for (int b = i; b; b >>= 1) grade += b & 1;
@@ -985,6 +988,7 @@ template <int LAYOUT, bool EVEN> static cudaError_t launch_sandwich_t(const Sand
     if (LAYOUT == kAoS)
         vec_ok = ((uintptr_t)g.x % 16 == 0) && (g.ldx % W == 0) && ((uintptr_t)g.out % 16 == 0) && (g.ldo % W == 0);
     Coeffs R = to_coeffs(g.rotor, 0.0), Rrev;
+    Rrev.stream_hint = R.stream_hint;
     for (int i = 0; i < NB; ++i) {
         int grade = 0;
         for (int b = i; b; b >>= 1) grade += b & 1;

@@ -53,16 +53,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "bra LCC_TMA_WAIT;\n\t"
         "LCC_TMA_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// Streaming data is touched exactly once: with `stream_hint` the copies carry an L2 evict-first policy so the
+// 17-68 GB that pass through do not displace each other's lines before they are written back / consumed.
+__device__ __forceinline__ uint64_t evict_first_policy() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 // global -> shared, completion on the mbarrier; c0 = element coordinate inside the row, c1 = row
-__device__ __forceinline__ void load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+__device__ __forceinline__ void load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, bool stream_hint = false) {
+    if (stream_hint) {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+            ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(evict_first_policy()) : "memory");
+    } else {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+            ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+    }
 }
 // shared -> global (rows beyond the tensor's extent are clipped by the hardware)
-__device__ __forceinline__ void store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+__device__ __forceinline__ void store_2d(const CUtensorMap *map, const void *src, int c0, int c1, bool stream_hint = false) {
+    if (stream_hint) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                     ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "l"(evict_first_policy()) : "memory");
+    } else {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                     ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+    }
 }
 __device__ __forceinline__ void store_commit_and_wait_read() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
