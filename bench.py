@@ -514,8 +514,10 @@ def roofline_block(wl, n, kernel_ms, bytes_per, peaks, peak_kind, traffic):
     if wl in TENSOR_FLOPS_PER_UNIT:  # dense contraction: tensor-pipe bound; nominal dense tf32 peak is half the bf16 one
         tf = TENSOR_FLOPS_PER_UNIT[wl] * n / (kernel_ms / 1e3) / 1e12
         peak_tf32 = float(peaks.get("bf16_tflops", 1590.0)) / 2.0
+        sustained = float(peaks.get("bf16_tflops_sustained", 0.0)) / 2.0
         return {"bound": "tensor", "achieved": tf, "peak": peak_tf32, "unit": "TFLOP/s", "frac": tf / peak_tf32, "traffic": traffic,
-                "peak_source": f"{peak_kind} bf16_tflops / 2 (tf32 runs at half the bf16 rate; no direct tf32 measurement)",
+                "peak_source": f"{peak_kind} bf16_tflops / 2 (burst figure; tf32 runs at half the bf16 rate; no direct tf32 measurement)",
+                "peak_sustained": sustained or None, "frac_of_sustained": (tf / sustained) if sustained else None,
                 "tensor_flops_per_unit": TENSOR_FLOPS_PER_UNIT[wl], "useful_tflops": tf / 3.0,
                 "hbm_gbs": hbm, "hbm_frac": hbm / float(peaks["hbm_gbs"]), "algorithmic_bytes_per_unit": bytes_per}
     peak = float(peaks["hbm_gbs"])

@@ -147,3 +147,21 @@ def test_batched_calls_refuse_to_run_without_a_gpu():
         L.MultivectorBatch.from_numpy(L.Algebra.euclidean(3), np.zeros((4, 8)))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         L.Multivector.from_vector([1.0, 0.0, 0.0]).geometric_product(L.Multivector.from_vector([0.0, 1.0, 0.0]))
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` runs on host cores only (the oracle port of the reference loops) and prints ONE
+    JSON line with the keys the driver reads; checked here on the small CPU-runnable configuration."""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "r3_gp",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, check=True).stdout
+    lines = [ln for ln in out.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "products/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert {"workload", "rows_per_gpu", "layout", "l2_policy", "strict_fp"} <= set(d["config"])
