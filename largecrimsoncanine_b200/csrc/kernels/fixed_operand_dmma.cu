@@ -133,7 +133,7 @@ template <int NB> cudaError_t launch_dmma_t(const double *x, int64_t ldx, double
     constexpr int BN = NB < 128 ? NB : 128;
     constexpr int smem = (2 * kBK * kXPitch + 2 * BN * kWPitch) * (int)sizeof(double);
     auto kernel = fixed_product_f64_dmma_kernel<NB>;
-    static const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (attr != cudaSuccess) return attr;
     dim3 grid((unsigned)((n + kBM - 1) / kBM), NB / BN);
     kernel<<<grid, kThreadsDmma, smem, s>>>(x, ldx, out, ldo, n, wt);

@@ -693,7 +693,8 @@ template <int OP, bool STRICT, int LIST = 0> static cudaError_t launch_product_t
         if (OP == kOpGPOuter && !aos_map(&mo2, g.out2, g.ldo2, g.n)) return cudaErrorNotSupported;
         auto kernel = product_kernel_aos_tma<OP, STRICT, LIST>;
         constexpr int smem = 2 * TmaTile::kBytes + 1024 + 16;
-        static const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        // (set on every call: the attribute belongs to the (function, device) pair and one process may drive several devices)
+        const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (attr != cudaSuccess) return attr;
         const unsigned grid = (unsigned)((g.n + TmaTile::kRows - 1) / TmaTile::kRows);
         kernel<<<grid, TmaTile::kRows, smem, g.stream>>>(ma, mb, mo, mo2, g.a_bcast ? (const real *)g.a : nullptr,
@@ -738,7 +739,7 @@ template <int OP, bool STRICT, int LIST = 0> static cudaError_t launch_product_s
     if (OP == kOpGPOuter && !soa_map<T_>(&mo2, g.out2, g.ldo2, g.n)) return cudaErrorNotSupported;
     auto kernel = product_kernel_soa_tma<OP, STRICT, LIST>;
     constexpr int smem = 2 * T_::kBytes + 1024 + 16;
-    static const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (attr != cudaSuccess) return attr;
     const unsigned grid = (unsigned)((g.n + T_::kRows - 1) / T_::kRows);
     kernel<<<grid, T_::kThreads, smem, g.stream>>>(ma, mb, mo, mo2, g.a_bcast ? (const real *)g.a : nullptr, g.lda,
@@ -754,7 +755,7 @@ template <bool STRICT, bool EVEN> static cudaError_t launch_sandwich_soa_tma(con
     if (!soa_map<T_>(&mx, g.x, g.ldx, g.n) || !soa_map<T_>(&mo, g.out, g.ldo, g.n)) return cudaErrorNotSupported;
     auto kernel = sandwich_kernel_soa_tma<STRICT, EVEN>;
     constexpr int smem = T_::kBytes + 1024 + 16;
-    static const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (attr != cudaSuccess) return attr;
     const unsigned grid = (unsigned)((g.n + T_::kRows - 1) / T_::kRows);
     kernel<<<grid, T_::kThreads, smem, g.stream>>>(mx, mo, R, Rrev, to_coeffs(g.mu, 1.0));

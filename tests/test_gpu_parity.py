@@ -753,3 +753,37 @@ def test_pga_points_fused_sandwich(L, dt):
         np.testing.assert_allclose(L.pga_transform_points(pga, motor, xyz), unfused, rtol=10 * TOL[dt], atol=10 * TOL[dt])
     with pytest.raises(ValueError):
         L.pga_transform_points(L.Algebra.cga(3), motor, xyz)
+
+
+def test_second_device_in_the_same_process(L):
+    """One process driving two GPUs (lcc_set_device): kernels that need more than 48 KB of dynamic shared memory
+    (the TMA-staged SoA products, K6 / K6d) must get their launch attribute on every device, not only on the first
+    one that ran them."""
+    if L.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    alg, o = algebras(L, (4, 1, 0))
+    rng = np.random.default_rng(59)
+    a, b = rand(rng, 5000, 32, np.float64), rand(rng, 5000, 32, np.float64)
+    before = L.get_option("soa_tma_min_bytes")
+    L.set_option("soa_tma_min_bytes", 0)
+    L.set_strict_fp(True)
+    try:
+        for dev in (0, 1, 0):
+            L.set_device(dev)
+            A, B = L.MultivectorBatch.from_numpy(alg, a), L.MultivectorBatch.from_numpy(alg, b)
+            assert np.array_equal(A.geometric_product(B).to_numpy(), o.geometric_product(a, b))
+            assert np.array_equal(A.sandwich(rotor_mv(L, alg, a[0].astype(np.float64))).to_numpy(), o.sandwich(a[0].astype(np.float64), a))
+    finally:
+        L.set_strict_fp(False)
+        L.set_option("soa_tma_min_bytes", before)
+        L.set_device(0)
+    alg8, o8 = algebras(L, (8, 0, 0))
+    m, x = rng.standard_normal((1, 256)), rng.standard_normal((300, 256))
+    L.set_device(1)
+    try:
+        for dt, tol in ((np.float64, 1e-12), (np.float32, 1e-5)):
+            got = L.MultivectorBatch.from_numpy(alg8, m.astype(dt)).geometric_product(L.MultivectorBatch.from_numpy(alg8, x.astype(dt))).to_numpy()
+            ref = o8.geometric_product(m.astype(dt).astype(np.float64), x.astype(dt).astype(np.float64))
+            assert np.abs(got - ref).max() <= tol * np.abs(ref).max()
+    finally:
+        L.set_device(0)
