@@ -251,8 +251,9 @@ LCC_API lcc_status lcc_host_product(const lcc_algebra *alg, int dtype, int op, c
 /* ---------------------------------------------------------------- tuning */
 
 /* Process-wide integer options (no reference counterpart):
- *   "aos_tma_min_rows"   AoS batches with at least this many rows use the TMA-staged kernels (default 4096)
- *   "soa_tma_min_bytes"  SoA batches with at least this many bytes per operand do (default 128 MiB)
+ *   "aos_tma_min_rows"   AoS batches with at least this many rows use the TMA-staged kernels (default 4096; rows
+ *                        narrower than 128 bytes need 32x as many)
+ *   "soa_tma_min_bytes"  SoA batches with at least this many bytes per operand do (default 8 GiB)
  * Results do not depend on either: the staged and the direct-load kernels run the same arithmetic. */
 LCC_API lcc_status lcc_set_option(const char *name, int64_t value);
 LCC_API lcc_status lcc_get_option(const char *name, int64_t *value);

@@ -665,12 +665,17 @@ sandwich_kernel_soa_tma(const __grid_constant__ CUtensorMap map_x, const __grid_
     }
 }
 
-// Which batches go through the TMA-staged kernels (lcc_set_option, include/lcc_b200.h):
-//   AoS  at least aos_tma_min_rows rows (default 4096): below it the tensor-map encode on the host costs more
-//        than the wider accesses save.  LCC_AOS_TMA=0 forces the direct-load kernels.
-//   SoA  at least soa_tma_min_bytes per operand (default 128 MiB): the direct-load SoA kernels are already
-//        coalesced, the tiles only win once the launch is long enough to hide their fill latency
-//        (Cl(3,0,0) gp at 2^20 rows: 33.1 us direct vs 35.1 us tiled; CGA gp at 2^26 rows: 6773 vs 7012 GB/s).
+// Which batches go through the TMA-staged kernels (lcc_set_option, include/lcc_b200.h; size sweep in
+// profiles/r01_tma_threshold_sweep.jsonl):
+//   AoS  rows of 128 bytes or more: at least aos_tma_min_rows rows (default 4096; CGA f64 gp already wins at 4096 rows,
+//        6.3 vs 8.3 us, and runs 2.2-2.5x faster from 2^16 rows on).  Narrower rows (PGA f32, R3 f64: 64 bytes) waste
+//        less per direct access and need 32x as many rows (131072) before the tiles win (2^18 rows: 8.3 vs 10.4 us).
+//        LCC_AOS_TMA=0 forces the direct-load kernels.
+//   SoA  at least soa_tma_min_bytes per operand (default 8 GiB): the direct-load SoA kernels are already fully
+//        coalesced and are as fast or faster up to 4 GiB per operand (PGA f32 2^26 rows: 6854 vs 6832 GB/s; 2^22 rows:
+//        84 vs 91 us); the tiles only win on the very largest batches (17 GB operands: 6759 -> 6889 GB/s, CGA f64
+//        6773 -> 7012 GB/s), where the direct kernels' many widely spaced streams start to miss in the TLB.
+constexpr int64_t kAosNarrowRowFactor = kRowBytes >= 128 ? 1 : 32;
 static inline bool tma_path_enabled() {
     static const bool on = [] { const char *e = std::getenv("LCC_AOS_TMA"); return !(e && e[0] == '0'); }();
     return on;
@@ -684,7 +689,7 @@ template <int OP, bool STRICT, int LIST = 0> static cudaError_t launch_product_t
     if constexpr (!kHasTmaPath) {
         return cudaErrorNotSupported;
     } else {
-        if (!tma_path_enabled() || g.n < option_aos_tma_min_rows()) return cudaErrorNotSupported;
+        if (!tma_path_enabled() || g.n < option_aos_tma_min_rows() * kAosNarrowRowFactor) return cudaErrorNotSupported;
         CUtensorMap ma, mb, mo, mo2;
         if (!aos_map(&mo, g.out, g.ldo, g.n)) return cudaErrorNotSupported;
         ma = mb = mo2 = mo;  // placeholders for operands that do not use a tile
@@ -708,7 +713,7 @@ template <bool STRICT, bool EVEN> static cudaError_t launch_sandwich_tma(const S
     if constexpr (!kHasTmaPath) {
         return cudaErrorNotSupported;
     } else {
-        if (!tma_path_enabled() || g.n < option_aos_tma_min_rows()) return cudaErrorNotSupported;
+        if (!tma_path_enabled() || g.n < option_aos_tma_min_rows() * kAosNarrowRowFactor) return cudaErrorNotSupported;
         CUtensorMap mx, mo;
         if (!aos_map(&mx, g.x, g.ldx, g.n) || !aos_map(&mo, g.out, g.ldo, g.n)) return cudaErrorNotSupported;
         auto kernel = sandwich_kernel_aos_tma<STRICT, EVEN>;

@@ -63,7 +63,7 @@ static int64_t env_or(const char *name, int64_t fallback) {
     return e && *e ? atoll(e) : fallback;
 }
 static std::atomic<int64_t> g_aos_tma_min_rows{env_or("LCC_AOS_TMA_MIN_ROWS", 4096)};
-static std::atomic<int64_t> g_soa_tma_min_bytes{env_or("LCC_SOA_TMA_MIN_BYTES", 128ll << 20)};
+static std::atomic<int64_t> g_soa_tma_min_bytes{env_or("LCC_SOA_TMA_MIN_BYTES", 8ll << 30)};
 int64_t option_aos_tma_min_rows() { return g_aos_tma_min_rows.load(std::memory_order_relaxed); }
 int64_t option_soa_tma_min_bytes() { return g_soa_tma_min_bytes.load(std::memory_order_relaxed); }
 

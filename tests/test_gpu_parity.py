@@ -490,6 +490,16 @@ def test_aos_batches_through_tma_tiles(L, sig, dt):
     rng = np.random.default_rng(23)
     S = cabi.LCC_FLAG_STRICT_FP
     dev = _Dev(lib)
+    cabi.check(lib.lcc_set_option(b"aos_tma_min_rows", 128))  # default 4096 (x32 for rows under 128 bytes): force the tiles at test sizes
+    try:
+        _aos_tma_cases(lib, alg, o, nb, code, rng, S, dev, dt)
+    finally:
+        cabi.check(lib.lcc_set_option(b"aos_tma_min_rows", 4096))
+
+
+def _aos_tma_cases(lib, alg, o, nb, code, rng, S, dev, dt):
+    from largecrimsoncanine_b200 import cabi
+
     for n, pad in ((4096, 0), (4096 + 37, 0), (10007, 0), (5000, 16 // np.dtype(dt).itemsize), (4500, 1)):
         ld = nb + pad
         a, b = rand(rng, n, nb, dt), rand(rng, n, nb, dt)

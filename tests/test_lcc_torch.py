@@ -66,7 +66,18 @@ def test_gradients_match_pytorch_autograd_of_the_same_bilinear_map(lt, sig, name
     T = sign_tensor(o, name)
     alg = lt.TorchAlgebra._from_signature(*sig, device="cuda")
     g = torch.Generator().manual_seed(11)
+    from largecrimsoncanine_b200 import cabi
+
     # full batch and broadcast right operand; 64 rows take the direct-load VJP kernels, 4500 rows the TMA-tile ones
+    # (the default threshold is 4096 rows, x32 for rows under 128 bytes: lowered so every signature takes the tiles)
+    cabi.check(cabi.lib().lcc_set_option(b"aos_tma_min_rows", 128))
+    try:
+        _gradient_cases(lt, o, T, alg, g, name)
+    finally:
+        cabi.check(cabi.lib().lcc_set_option(b"aos_tma_min_rows", 4096))
+
+
+def _gradient_cases(lt, o, T, alg, g, name):
     for n, nb_rows in ((64, 64), (64, 1), (4500, 4500), (4500, 1)):
         a = torch.randn(n, o.num_blades, generator=g, dtype=torch.float64)
         b = torch.randn(nb_rows, o.num_blades, generator=g, dtype=torch.float64)
