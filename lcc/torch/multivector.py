@@ -342,6 +342,14 @@ class TorchMultivector:
                     cabi.check(cabi.lib().lcc_batch_sandwich(_handle(self.algebra.signature).h, r.ctypes.data_as(C.POINTER(C.c_double)),
                                                              C.byref(_view(x)), C.byref(_view(out)), _flags(), _stream()))
             return TorchMultivector(self.algebra, out)
+        if not needs_grad and rotor.batch_size == self.batch_size and self.batch_size > 0:
+            # one rotor per row (reference :988-1019): lcc_batch_sandwich_rows on the borrowed tensors
+            x, r = _prep(self.coeffs), _prep(rotor.coeffs.to(self.coeffs.dtype))
+            out = torch.empty_like(x)
+            with torch.cuda.device(x.device):
+                cabi.check(cabi.lib().lcc_batch_sandwich_rows(_handle(self.algebra.signature).h, C.byref(_view(r)), C.byref(_view(x)),
+                                                              C.byref(_view(out)), _flags(), _stream()))
+            return TorchMultivector(self.algebra, out)
         return rotor.geometric_product(self).geometric_product(rotor.reverse())
 
     apply = sandwich

@@ -797,3 +797,35 @@ def test_second_device_in_the_same_process(L):
             assert np.abs(got - ref).max() <= tol * np.abs(ref).max()
     finally:
         L.set_device(0)
+
+
+@pytest.mark.parametrize("sig", [(3, 0, 0), (3, 0, 1), (4, 1, 0), (2, 1, 1), (6, 0, 0)])
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_sandwich_with_one_rotor_per_row(L, sig, dt):
+    """lcc_batch_sandwich_rows: out[r] = R[r] * x[r] * ~R[r] (lcc/torch/multivector.py:988-1019 of the reference,
+    two products in the reference's term order), both layouts, strict mode bit-exact against the oracle's composition."""
+    from largecrimsoncanine_b200 import cabi
+
+    lib = cabi.lib()
+    o, alg = oracle.OracleAlgebra(*sig), cabi.Algebra(*sig)
+    nb = o.num_blades
+    code = cabi.LCC_F64 if dt == np.float64 else cabi.LCC_F32
+    rng = np.random.default_rng(61)
+    dev = _Dev(lib)
+    for n in ((3, 200) if nb > 32 else (1, 77, 5000)):
+        x, r = rand(rng, n, nb, dt), rand(rng, n, nb, dt)
+        want = o.geometric_product(o.geometric_product(r, x), o.reverse(r))
+        for layout in (cabi.LCC_AOS, cabi.LCC_SOA):
+            if layout == cabi.LCC_AOS:
+                ix, ir, ld = np.ascontiguousarray(x), np.ascontiguousarray(r), nb
+            else:
+                ld = ((n + 63) // 64) * 64
+                ix, ir = np.zeros((nb, ld), dt), np.zeros((nb, ld), dt)
+                ix[:, :n], ir[:, :n] = x.T, r.T
+            px, pr, po = dev.put(ix), dev.put(ir), dev.put(np.zeros_like(ix))
+            vx, vr, vo = (cabi.view(p.value, n, ld, code, layout) for p in (px, pr, po))
+            cabi.check(lib.lcc_batch_sandwich_rows(alg.h, C.byref(vr), C.byref(vx), C.byref(vo), cabi.LCC_FLAG_STRICT_FP, None))
+            got = dev.get(po, ix)
+            got = got if layout == cabi.LCC_AOS else got[:, :n].T
+            assert np.array_equal(got, want), (sig, dt, n, layout)
+            dev.free()
