@@ -358,7 +358,7 @@ def test_host_buffer_entry_points(L):
 
 def test_sharded_batch_single_rank(L):
     """ShardedBatch with a world of one (the N > 1 path is covered by tests/test_sharding_gloo.py on CPU
-    and scripts/multi_gpu_check.py under torchrun on GPUs)."""
+    and tests/tools/multi_gpu_check.py under torchrun on GPUs)."""
     from largecrimsoncanine_b200 import sharded
 
     rng = np.random.default_rng(23)

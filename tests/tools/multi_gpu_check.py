@@ -2,14 +2,14 @@
 """Run under torchrun on N GPUs: the same global batch sharded N ways must give the same rows as the
 single-GPU result and a sum / mean within tolerance of the oracle (plan item 5).
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 scripts/multi_gpu_check.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tests/tools/multi_gpu_check.py
 """
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import largecrimsoncanine as L  # noqa: E402
