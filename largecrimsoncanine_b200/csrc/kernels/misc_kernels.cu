@@ -2,6 +2,8 @@
 // K4 norms, K5 batch sums, K7 layout conversion, column movers, the looped product for algebras
 // above 32 blades, and the PGA/CGA point embeddings.  All are streaming, HBM-bound kernels: one
 // read and one write per element (norms: one read, 1/nb write), coalesced along rows for SoA.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "launch_args.h"
 #include "misc_kernels.cuh"
@@ -194,59 +196,69 @@ norm_kernel(const T *__restrict__ x, int64_t ldx, int64_t n, int nb, const Weigh
 // warp (cpr <= 32), every lane loads one chunk (fully coalesced), the running sum travels through the group with
 // warp shuffles in ascending blade order -- the reference's summation order, so STRICT stays bit-exact -- and for
 // `normalized` each lane scales and stores the chunk it already holds: one read and one write per element.
+// Every thread takes kNormRowsInFlight chunks, kThreads chunks apart, and issues all their loads before the first
+// reduction: with one 16-byte load per thread the kernel is latency-bound (3.5-4.5 TB/s, profiles/r01_aux_ops_after.jsonl).
+constexpr int kNormRowsInFlight = 4;
+
 template <class T, bool STRICT>
 __global__ void __launch_bounds__(kThreads)
 norm_aos_lanes(const T *__restrict__ x, int64_t ldx, int64_t n, int log2cpr, const Weights wt, int mode,
                T *__restrict__ norms, T *__restrict__ out, int64_t ldo) {
-    constexpr int W = VecW<T>::value;
+    constexpr int W = VecW<T>::value, U = kNormRowsInFlight;
     const int cpr = 1 << log2cpr;
     __shared__ int8_t sw[256];                 // lane-dependent blade index: shared memory, not the constant bank
     if (threadIdx.x < cpr * W) sw[threadIdx.x] = wt.w[threadIdx.x];
     __syncthreads();
-    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    const int64_t r = c >> log2cpr;
-    const int j = (int)(c & (cpr - 1));       // chunk inside the row == position inside the lane group
-    const bool live = r < n;                   // whole lane groups are live or not (kThreads % cpr == 0)
-    T v[W];
+    const int64_t c0 = (int64_t)blockIdx.x * (kThreads * U) + threadIdx.x;
+    const int j = (int)(c0 & (cpr - 1));      // chunk inside the row == position inside the lane group (kThreads % cpr == 0)
+    T v[U][W];
+    int64_t r[U];
 #pragma unroll
-    for (int l = 0; l < W; ++l) v[l] = T(0);
-    if (live) ldg_stream(x + r * ldx + j * W, v);
+    for (int u = 0; u < U; ++u) {
+        r[u] = (c0 + (int64_t)u * kThreads) >> log2cpr;  // whole lane groups are live or not
+#pragma unroll
+        for (int l = 0; l < W; ++l) v[u][l] = T(0);
+        if (r[u] < n) ldg_stream(x + r[u] * ldx + j * W, v[u]);
+    }
     int w[W];
 #pragma unroll
     for (int l = 0; l < W; ++l) w[l] = sw[j * W + l];
-    T acc = T(0);
-    if (STRICT) {
-        for (int step = 0; step < cpr; ++step) {   // lane `step` of each group extends the running sum
-            const T incoming = __shfl_up_sync(0xffffffffu, acc, 1, cpr);
-            if (j == step) {
-                if (step > 0) acc = incoming;
 #pragma unroll
-                for (int l = 0; l < W; ++l)
-                    if (w[l] != 0) acc = Arith<true>::madd(w[l] > 0 ? v[l] : -v[l], v[l], acc);
+    for (int u = 0; u < U; ++u) {
+        T acc = T(0);
+        if (STRICT) {
+            for (int step = 0; step < cpr; ++step) {   // lane `step` of each group extends the running sum
+                const T incoming = __shfl_up_sync(0xffffffffu, acc, 1, cpr);
+                if (j == step) {
+                    if (step > 0) acc = incoming;
+#pragma unroll
+                    for (int l = 0; l < W; ++l)
+                        if (w[l] != 0) acc = Arith<true>::madd(w[l] > 0 ? v[u][l] : -v[u][l], v[u][l], acc);
+                }
+            }
+            acc = __shfl_sync(0xffffffffu, acc, cpr - 1, cpr);  // the last lane holds the row's total
+        } else {                                       // default mode: per-lane partial, then a butterfly over the group
+#pragma unroll
+            for (int l = 0; l < W; ++l)
+                if (w[l] != 0) acc = Arith<false>::madd(w[l] > 0 ? v[u][l] : -v[u][l], v[u][l], acc);
+            for (int o = cpr >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, cpr);
+        }
+        if (r[u] >= n) continue;
+        if (mode == 0) { if (j == 0) norms[r[u]] = acc; continue; }
+        const T nrm = sqrt_rn(acc < T(0) ? -acc : acc);
+        if (mode == 1) { if (j == 0) norms[r[u]] = nrm; continue; }
+        if (nrm > (T)1e-14) {                      // batch.rs:805-811
+            if (STRICT) {
+#pragma unroll
+                for (int l = 0; l < W; ++l) v[u][l] = div_rn(v[u][l], nrm);
+            } else {                               // one division per row instead of one per element (<= 1 ulp apart)
+                const T inv = div_rn(T(1), nrm);
+#pragma unroll
+                for (int l = 0; l < W; ++l) v[u][l] = mul_rn(v[u][l], inv);
             }
         }
-        acc = __shfl_sync(0xffffffffu, acc, cpr - 1, cpr);  // the last lane holds the row's total
-    } else {                                       // default mode: per-lane partial, then a butterfly over the group
-#pragma unroll
-        for (int l = 0; l < W; ++l)
-            if (w[l] != 0) acc = Arith<false>::madd(w[l] > 0 ? v[l] : -v[l], v[l], acc);
-        for (int o = cpr >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, cpr);
+        stg_stream(out + r[u] * ldo + j * W, v[u]);
     }
-    if (!live) return;
-    if (mode == 0) { if (j == 0) norms[r] = acc; return; }
-    const T nrm = sqrt_rn(acc < T(0) ? -acc : acc);
-    if (mode == 1) { if (j == 0) norms[r] = nrm; return; }
-    if (nrm > (T)1e-14) {                      // batch.rs:805-811
-        if (STRICT) {
-#pragma unroll
-            for (int l = 0; l < W; ++l) v[l] = div_rn(v[l], nrm);
-        } else {                               // one division per row instead of one per element (<= 1 ulp apart)
-            const T inv = div_rn(T(1), nrm);
-#pragma unroll
-            for (int l = 0; l < W; ++l) v[l] = mul_rn(v[l], inv);
-        }
-    }
-    stg_stream(out + r * ldo + j * W, v);
 }
 
 // SoA `normalized` with the row held in registers (NB known at compile time): one read and one write per element.
@@ -304,14 +316,42 @@ __device__ __forceinline__ double block_reduce_sum(double v) {
     return total;  // valid on thread 0
 }
 
+// One blade row per blockIdx.y.  Each thread keeps four independent 128-bit loads in flight (a single scalar load
+// per trip leaves only 2048 x 4-8 bytes per SM outstanding, which is latency-bound far below the HBM rate) and
+// four accumulators that are folded in a fixed order, so the result does not depend on timing.
 template <class T>
 __global__ void __launch_bounds__(kThreads)
-sum_partial_soa(const T *__restrict__ x, int64_t ldx, int64_t n, int64_t rows_per_block, double *__restrict__ partial) {
+sum_partial_soa(const T *__restrict__ x, int64_t ldx, int64_t n, int64_t rows_per_block, int vec_ok, double *__restrict__ partial) {
+    constexpr int W = VecW<T>::value;
     const int k = blockIdx.y;
+    const T *__restrict__ row = x + (int64_t)k * ldx;
     const int64_t begin = (int64_t)blockIdx.x * rows_per_block;
     const int64_t end = begin + rows_per_block < n ? begin + rows_per_block : n;
     double acc = 0.0;
-    for (int64_t r = begin + threadIdx.x; r < end; r += kThreads) acc += (double)__ldg(x + (int64_t)k * ldx + r);
+    if (vec_ok) {  // begin and the row base are multiples of W elements
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        constexpr int64_t kStride = (int64_t)kThreads * W;
+        int64_t r = begin + (int64_t)threadIdx.x * W;
+        for (; r + 3 * kStride + W <= end; r += 4 * kStride) {
+            T v0[W], v1[W], v2[W], v3[W];
+            ldg_stream(row + r, v0);
+            ldg_stream(row + r + kStride, v1);
+            ldg_stream(row + r + 2 * kStride, v2);
+            ldg_stream(row + r + 3 * kStride, v3);
+#pragma unroll
+            for (int l = 0; l < W; ++l) { a0 += (double)v0[l]; a1 += (double)v1[l]; a2 += (double)v2[l]; a3 += (double)v3[l]; }
+        }
+        for (; r + W <= end; r += kStride) {
+            T v0[W];
+            ldg_stream(row + r, v0);
+#pragma unroll
+            for (int l = 0; l < W; ++l) a0 += (double)v0[l];
+        }
+        for (int64_t rr = r; rr < end && rr < r + W; ++rr) a1 += (double)__ldg(row + rr);  // the one partial vector
+        acc = (a0 + a1) + (a2 + a3);
+    } else {
+        for (int64_t r = begin + threadIdx.x; r < end; r += kThreads) acc += (double)__ldg(row + r);
+    }
     const double total = block_reduce_sum(acc);
     if (threadIdx.x == 0) partial[(int64_t)k * gridDim.x + blockIdx.x] = total;
 }
@@ -412,6 +452,78 @@ transpose_kernel(const T *__restrict__ src, int64_t lds, T *__restrict__ dst, in
             const int r = e / C, c = e % C;
             dst[(r0 + r) * ldd + c0 + c] = tile[r * pitch + c];
         }
+    }
+}
+
+// TMA form of K7 for rows of 32-256 bytes: the AoS side of the tile is one contiguous span of HBM and moves as
+// swizzled 2-D boxes (a thread reads / writes 16-byte chunks of its own row without bank conflicts), the SoA side is
+// one (rows x blades) box whose blade segments are 1-2 KB runs; neither side issues a single per-thread global access.
+// The scalar kernel above moves 4 bytes per thread and instruction and stops at 4.0-4.1 TB/s for f32 rows.
+template <int RB> struct TransposeTile {
+    static constexpr int kSpan = RB >= 128 ? 128 : RB;      // bytes per AoS box row == swizzle span
+    static constexpr int kSub = RB / kSpan;                 // AoS boxes per tile
+    static constexpr int kRows = 32768 / RB > 256 ? 256 : 32768 / RB;  // rows per tile == threads per block (TMA boxes: <= 256)
+    static constexpr int kBytes = kRows * RB;               // 8-32 KB per side
+    static constexpr uint32_t kSwzMask = kSpan == 128 ? 7u : (kSpan == 64 ? 3u : 1u);
+    static __device__ __forceinline__ uint32_t chunk_offset(int t, int j) {  // 16-byte chunk j of tile row t (tile base 1024-aligned)
+        const uint32_t byte = (uint32_t)j * 16u;
+        const uint32_t off = (byte / kSpan) * (uint32_t)(kRows * kSpan) + (uint32_t)t * kSpan + (byte % kSpan);
+        return off ^ (((off >> 7) & kSwzMask) << 4);
+    }
+};
+
+template <class T, int NB, bool TO_SOA>
+__global__ void __launch_bounds__(TransposeTile<NB * (int)sizeof(T)>::kRows)
+transpose_tma_kernel(const __grid_constant__ CUtensorMap map_aos, const __grid_constant__ CUtensorMap map_soa) {
+    using TT = TransposeTile<NB * (int)sizeof(T)>;
+    constexpr int W = VecW<T>::value;
+    struct alignas(16) Chunk { T v[W]; };
+    extern __shared__ uint8_t tr_smem_raw[];
+    uint8_t *tile_in = (uint8_t *)(((uintptr_t)tr_smem_raw + 1023) & ~(uintptr_t)1023), *tile_out = tile_in + TT::kBytes;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(tile_out + TT::kBytes);
+    const int t = threadIdx.x, row0 = blockIdx.x * TT::kRows;
+    if (t == 0) {
+        tma::mbar_init(bar, 1);
+        tma::mbar_expect_tx(bar, (uint32_t)TT::kBytes);
+        if (TO_SOA) {
+#pragma unroll
+            for (int sub = 0; sub < TT::kSub; ++sub)
+                tma::load_2d(tile_in + sub * TT::kRows * TT::kSpan, &map_aos, bar, sub * (TT::kSpan / (int)sizeof(T)), row0);
+        } else {
+            tma::load_2d(tile_in, &map_soa, bar, row0, 0);
+        }
+    }
+    __syncthreads();
+    tma::mbar_wait(bar, 0);
+    if (TO_SOA) {
+        T *soa = reinterpret_cast<T *>(tile_out);  // [NB][kRows]
+#pragma unroll
+        for (int j = 0; j < NB / W; ++j) {
+            const Chunk c = *reinterpret_cast<const Chunk *>(tile_in + TT::chunk_offset(t, j));
+#pragma unroll
+            for (int l = 0; l < W; ++l) soa[(j * W + l) * TT::kRows + t] = c.v[l];
+        }
+    } else {
+        const T *soa = reinterpret_cast<const T *>(tile_in);
+#pragma unroll
+        for (int j = 0; j < NB / W; ++j) {
+            Chunk c;
+#pragma unroll
+            for (int l = 0; l < W; ++l) c.v[l] = soa[(j * W + l) * TT::kRows + t];
+            *reinterpret_cast<Chunk *>(tile_out + TT::chunk_offset(t, j)) = c;
+        }
+    }
+    tma::fence_proxy_async();
+    __syncthreads();
+    if (t == 0) {  // rows beyond n are clipped by the engine (and arrived as zeros)
+        if (TO_SOA) {
+            tma::store_2d(&map_soa, tile_out, row0, 0);
+        } else {
+#pragma unroll
+            for (int sub = 0; sub < TT::kSub; ++sub)
+                tma::store_2d(&map_aos, tile_out + sub * TT::kRows * TT::kSpan, sub * (TT::kSpan / (int)sizeof(T)), row0);
+        }
+        tma::store_commit_and_wait_read();
     }
 }
 
@@ -624,7 +736,7 @@ cudaError_t launch_norm(int nb, int mode, bool strict, const ViewArg &x, const i
         // latency-bound and only pays off when it saves the second pass of `normalized`
         if (x.layout == kAoS && nb / W <= 32 && aos_vec_ok(x, nb, W) && (mode != 2 || aos_vec_ok(out, nb, W)) && !(strict && mode != 2)) {
             const int cpr = nb / W;
-            const unsigned gl = blocks_for(n * cpr);
+            const unsigned gl = blocks_for(n * cpr, kThreads * kNormRowsInFlight);
             if (strict) norm_aos_lanes<T, true><<<gl, kThreads, 0, s>>>((const T *)x.data, x.ld, n, ilog2(cpr), wt, mode, (T *)norms, (T *)out.data, out.ld);
             else norm_aos_lanes<T, false><<<gl, kThreads, 0, s>>>((const T *)x.data, x.ld, n, ilog2(cpr), wt, mode, (T *)norms, (T *)out.data, out.ld);
             return;
@@ -669,11 +781,13 @@ cudaError_t launch_sum(int nb, const ViewArg &x, void *sums_dev, void *scratch_d
     const int64_t n = x.n;
     const int nblocks = sum_blocks(n);
     if (scratch_elems < (int64_t)nb * nblocks) return cudaErrorInvalidValue;
-    const int64_t rows_per_block = (n + nblocks - 1) / nblocks;
+    int64_t rows_per_block = (n + nblocks - 1) / nblocks;
+    rows_per_block = (rows_per_block + 3) & ~(int64_t)3;  // block ranges start on 16-byte boundaries
     auto run = [&](auto tag) {
         using T = decltype(tag);
         if (x.layout == kSoA) {
-            sum_partial_soa<T><<<dim3(nblocks, nb), kThreads, 0, s>>>((const T *)x.data, x.ld, n, rows_per_block, (double *)scratch_dev);
+            const int vec_ok = ((uintptr_t)x.data & 15) == 0 && (x.ld % VecW<T>::value) == 0;
+            sum_partial_soa<T><<<dim3(nblocks, nb), kThreads, 0, s>>>((const T *)x.data, x.ld, n, rows_per_block, vec_ok, (double *)scratch_dev);
         } else if (aos_vec_ok(x, nb, VecW<T>::value)) {
             const int cpr = nb / VecW<T>::value;
             sum_partial_aos_vec<T><<<nblocks, kThreads, 0, s>>>((const T *)x.data, x.ld, n, nb, ilog2(cpr), rows_per_block, (double *)scratch_dev);
@@ -691,6 +805,37 @@ cudaError_t launch_sum_final(int nb, int nblocks, const double *partial, void *s
                     [&] { sum_final<double><<<nb, kThreads, 0, s>>>(partial, nblocks, (double *)sums_dev); });
 }
 
+// cudaErrorNotSupported: this pair of views does not qualify (row size, alignment, batch too small) -- scalar kernel
+template <class T, int NB> static cudaError_t launch_convert_tma_nb(const ViewArg &src, const ViewArg &dst, cudaStream_t s) {
+    using TT = TransposeTile<NB * (int)sizeof(T)>;
+    const ViewArg &aos = src.layout == kAoS ? src : dst, &soa = src.layout == kAoS ? dst : src;
+    const int64_t n = src.n;
+    CUtensorMap ma, ms;
+    if (!make_aos_tensor_map(&ma, aos.data, (int)sizeof(T), NB, aos.ld, n, TT::kSpan, TT::kRows)) return cudaErrorNotSupported;
+    if (!make_soa_tensor_map(&ms, soa.data, (int)sizeof(T), NB, soa.ld, n, TT::kRows)) return cudaErrorNotSupported;
+    constexpr int smem = 2 * TT::kBytes + 1024 + 16;
+    const unsigned grid = (unsigned)((n + TT::kRows - 1) / TT::kRows);
+    auto go = [&](auto kernel) {
+        const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (attr != cudaSuccess) return attr;
+        kernel<<<grid, TT::kRows, smem, s>>>(ma, ms);
+        note_kernel_launch();
+        return cudaGetLastError();
+    };
+    return dst.layout == kSoA ? go(transpose_tma_kernel<T, NB, true>) : go(transpose_tma_kernel<T, NB, false>);
+}
+template <class T> static cudaError_t launch_convert_tma(int nb, const ViewArg &src, const ViewArg &dst, cudaStream_t s) {
+    static const bool on = [] { const char *e = std::getenv("LCC_TMA_TRANSPOSE"); return !(e && e[0] == '0'); }();
+    if (!on || src.n < 4096) return cudaErrorNotSupported;  // small batches: launch-bound either way
+    switch (nb * (int)sizeof(T)) {
+        case 32: return launch_convert_tma_nb<T, 32 / (int)sizeof(T)>(src, dst, s);
+        case 64: return launch_convert_tma_nb<T, 64 / (int)sizeof(T)>(src, dst, s);
+        case 128: return launch_convert_tma_nb<T, 128 / (int)sizeof(T)>(src, dst, s);
+        case 256: return launch_convert_tma_nb<T, 256 / (int)sizeof(T)>(src, dst, s);
+    }
+    return cudaErrorNotSupported;
+}
+
 cudaError_t launch_convert(int nb, const ViewArg &src, const ViewArg &dst, cudaStream_t s) {
     const int64_t n = src.n;
     if (n <= 0) return cudaSuccess;
@@ -699,6 +844,10 @@ cudaError_t launch_convert(int nb, const ViewArg &src, const ViewArg &dst, cudaS
         if (src.layout == kSoA)
             return cudaMemcpy2DAsync(dst.data, dst.ld * es, src.data, src.ld * es, n * es, nb, cudaMemcpyDeviceToDevice, s);
         return cudaMemcpy2DAsync(dst.data, dst.ld * es, src.data, src.ld * es, nb * es, n, cudaMemcpyDeviceToDevice, s);
+    }
+    {
+        const cudaError_t e = src.dtype == kF32 ? launch_convert_tma<float>(nb, src, dst, s) : launch_convert_tma<double>(nb, src, dst, s);
+        if (e != cudaErrorNotSupported) return e;
     }
     const int C = nb < 32 ? nb : 32;
     dim3 grid(blocks_for(n, kTileRows), nb / C);

@@ -780,7 +780,11 @@ template <bool STRICT, bool EVEN> static cudaError_t launch_sandwich_soa_tma(con
 // cp.async.bulk (1-D TMA), each thread handles 4 points (stride 256: bank-conflict free at 3 words per point),
 // the results overwrite the tile and leave with one bulk store.  The last, partial block uses plain accesses.
 #if LCC_NB == 16 && !LCC_RUNTIME_METRIC && defined(LCC_SIG_PGA3D)
-constexpr int kPointsPerBlock = 1024, kPointThreads = 256;
+#ifndef LCC_POINTS_SHAPE_DEFAULT
+#define LCC_POINTS_SHAPE_DEFAULT 0
+#endif
+// Block shape: THREADS threads, PPT points per thread.  More bytes per resident block keep more of the HBM pipe
+// busy (Little's law: ~70 KB must be in flight per SM); LCC_POINTS_SHAPE selects among the compiled shapes.
 __host__ __device__ constexpr bool point_blade(int k) { return k == 7 || k == 11 || k == 13 || k == 14; }
 
 template <bool STRICT, bool EVEN>
@@ -814,15 +818,23 @@ static __device__ __forceinline__ void transform_point(const Coeffs &R, const Co
     const real w = res[7];
     const bool ok = (w < real(0) ? -w : w) >= (real)1e-10;
     const real nanv = (real)__int_as_float(0x7fc00000);
-    o[0] = ok ? div_rn(-res[14], w) : nanv;
-    o[1] = ok ? div_rn(res[13], w) : nanv;
-    o[2] = ok ? div_rn(-res[11], w) : nanv;
+    if constexpr (STRICT) {  // the reference's three divisions (pga.rs:579-599)
+        o[0] = ok ? div_rn(-res[14], w) : nanv;
+        o[1] = ok ? div_rn(res[13], w) : nanv;
+        o[2] = ok ? div_rn(-res[11], w) : nanv;
+    } else {                 // default mode: one correctly rounded reciprocal per point, <= 1 ulp from the quotient
+        const real rw = div_rn(real(1), w);
+        o[0] = ok ? mul_rn(-res[14], rw) : nanv;
+        o[1] = ok ? mul_rn(res[13], rw) : nanv;
+        o[2] = ok ? mul_rn(-res[11], rw) : nanv;
+    }
 }
 
-template <bool STRICT, bool EVEN>
+template <bool STRICT, bool EVEN, int kPointThreads, int PPT>
 __global__ void __launch_bounds__(kPointThreads)
 pga_points_sandwich_kernel(const real *__restrict__ xyz_in, real *__restrict__ xyz_out, int64_t n, int bulk_ok,
                            const Coeffs R, const Coeffs Rrev) {
+    constexpr int kPointsPerBlock = kPointThreads * PPT;
     __shared__ alignas(128) real tile[kPointsPerBlock * 3];
     __shared__ uint64_t bar;
     const int t = threadIdx.x;
@@ -864,12 +876,25 @@ pga_points_sandwich_kernel(const real *__restrict__ xyz_in, real *__restrict__ x
 
 cudaError_t pga_points_sandwich(const SandwichArgs &g);  // x / out = dense (n,3) arrays here
 #if LCC_PART == 3 && LCC_PART_STRICT == 0
-template <bool STRICT, bool EVEN> static cudaError_t launch_points_t(const SandwichArgs &g, const Coeffs &R, const Coeffs &Rrev) {
+template <bool STRICT, bool EVEN, int THREADS, int PPT>
+static cudaError_t launch_points_shape(const SandwichArgs &g, const Coeffs &R, const Coeffs &Rrev) {
     const int bulk_ok = ((uintptr_t)g.x % 16 == 0) && ((uintptr_t)g.out % 16 == 0);
+    constexpr int kPointsPerBlock = THREADS * PPT;
     const unsigned grid = (unsigned)((g.n + kPointsPerBlock - 1) / kPointsPerBlock);
-    pga_points_sandwich_kernel<STRICT, EVEN><<<grid, kPointThreads, 0, g.stream>>>((const real *)g.x, (real *)g.out, g.n, bulk_ok, R, Rrev);
+    pga_points_sandwich_kernel<STRICT, EVEN, THREADS, PPT><<<grid, THREADS, 0, g.stream>>>((const real *)g.x, (real *)g.out, g.n, bulk_ok, R, Rrev);
     note_kernel_launch();
     return cudaGetLastError();
+}
+static inline int points_shape() {  // 0: 256 threads x 4 points (12 KB f32 tiles), 1: 256 x 8, 2: 128 x 8
+    static const int shape = [] { const char *e = std::getenv("LCC_POINTS_SHAPE"); return e ? std::atoi(e) : LCC_POINTS_SHAPE_DEFAULT; }();
+    return shape;
+}
+template <bool STRICT, bool EVEN> static cudaError_t launch_points_t(const SandwichArgs &g, const Coeffs &R, const Coeffs &Rrev) {
+    switch (points_shape()) {
+        case 1: return launch_points_shape<STRICT, EVEN, 256, (sizeof(real) == 4 ? 8 : 4)>(g, R, Rrev);  // 24 KB tiles
+        case 2: return launch_points_shape<STRICT, EVEN, 128, 8>(g, R, Rrev);
+        default: return launch_points_shape<STRICT, EVEN, 256, 4>(g, R, Rrev);
+    }
 }
 cudaError_t pga_points_sandwich(const SandwichArgs &g) {
     if (g.n <= 0) return cudaSuccess;

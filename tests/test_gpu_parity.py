@@ -829,3 +829,40 @@ def test_sandwich_with_one_rotor_per_row(L, sig, dt):
             got = got if layout == cabi.LCC_AOS else got[:, :n].T
             assert np.array_equal(got, want), (sig, dt, n, layout)
             dev.free()
+
+
+@pytest.mark.parametrize("sig", [(3, 0, 0), (3, 0, 1), (4, 1, 0), (2, 0, 0), (6, 0, 0)])
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_layout_conversion_through_tma_tiles(L, sig, dt):
+    """lcc_batch_convert (what from_numpy / to_numpy run, batch.rs:79-94,233-235): (N, num_blades) row-major <->
+    blade-major, bit-exact copies in both directions.  From 4096 rows on, rows of 32-256 bytes go through the
+    TMA-staged transpose; ragged last tiles, the padding of the blade rows (canaries) and views the engine cannot
+    describe (pitch not a multiple of 16 bytes) are covered, as is the scalar kernel below the threshold."""
+    from largecrimsoncanine_b200 import cabi
+
+    lib = cabi.lib()
+    alg = cabi.Algebra(*sig)
+    nb = 1 << sum(sig)
+    code = cabi.LCC_F64 if dt == np.float64 else cabi.LCC_F32
+    rng = np.random.default_rng(53)
+    dev = _Dev(lib)
+    for n, aos_pad in ((1000, 0), (4096, 0), (4097, 0), (70_001, 0), (33_333, 4), (5000, 1)):
+        x = rand(rng, n, nb, dt)
+        ld_aos = nb + aos_pad
+        ld_soa = ((n + 63) // 64) * 64
+        aos_img = np.full((n, ld_aos), 7.0, dt)
+        aos_img[:, :nb] = x
+        soa_canary = np.full((nb, ld_soa), -3.0, dt)
+        pa, ps, pb = dev.put(aos_img), dev.put(soa_canary), dev.put(np.full_like(aos_img, 7.0))
+        va = cabi.view(pa.value, n, ld_aos, code, cabi.LCC_AOS)
+        vs = cabi.view(ps.value, n, ld_soa, code, cabi.LCC_SOA)
+        vb = cabi.view(pb.value, n, ld_aos, code, cabi.LCC_AOS)
+        cabi.check(lib.lcc_batch_convert(alg.h, C.byref(va), C.byref(vs), None))
+        soa = dev.get(ps, soa_canary)
+        assert np.array_equal(soa[:, :n], x.T)
+        assert np.all(soa[:, n:] == -3.0)  # the tail of every blade row is not touched
+        cabi.check(lib.lcc_batch_convert(alg.h, C.byref(vs), C.byref(vb), None))
+        back = dev.get(pb, aos_img)
+        assert np.array_equal(back[:, :nb], x)
+        assert np.all(back[:, nb:] == 7.0)
+        dev.free()
