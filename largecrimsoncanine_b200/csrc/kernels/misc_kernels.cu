@@ -223,29 +223,51 @@ norm_aos_lanes(const T *__restrict__ x, int64_t ldx, int64_t n, int log2cpr, con
     int w[W];
 #pragma unroll
     for (int l = 0; l < W; ++l) w[l] = sw[j * W + l];
+    T acc[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        T acc = T(0);
+        acc[u] = T(0);
         if (STRICT) {
             for (int step = 0; step < cpr; ++step) {   // lane `step` of each group extends the running sum
-                const T incoming = __shfl_up_sync(0xffffffffu, acc, 1, cpr);
+                const T incoming = __shfl_up_sync(0xffffffffu, acc[u], 1, cpr);
                 if (j == step) {
-                    if (step > 0) acc = incoming;
+                    if (step > 0) acc[u] = incoming;
 #pragma unroll
                     for (int l = 0; l < W; ++l)
-                        if (w[l] != 0) acc = Arith<true>::madd(w[l] > 0 ? v[u][l] : -v[u][l], v[u][l], acc);
+                        if (w[l] != 0) acc[u] = Arith<true>::madd(w[l] > 0 ? v[u][l] : -v[u][l], v[u][l], acc[u]);
                 }
             }
-            acc = __shfl_sync(0xffffffffu, acc, cpr - 1, cpr);  // the last lane holds the row's total
+            acc[u] = __shfl_sync(0xffffffffu, acc[u], cpr - 1, cpr);  // the last lane holds the row's total
         } else {                                       // default mode: per-lane partial, then a butterfly over the group
 #pragma unroll
             for (int l = 0; l < W; ++l)
-                if (w[l] != 0) acc = Arith<false>::madd(w[l] > 0 ? v[u][l] : -v[u][l], v[u][l], acc);
-            for (int o = cpr >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, cpr);
+                if (w[l] != 0) acc[u] = Arith<false>::madd(w[l] > 0 ? v[u][l] : -v[u][l], v[u][l], acc[u]);
+            for (int o = cpr >> 1; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o, cpr);
         }
+    }
+    if (mode != 2 && cpr >= U) {
+        // Norms only: every lane of a group holds its row's total, but one square root and one store per row are
+        // enough.  The U * (32 / cpr) <= 32 rows of the warp are gathered one per lane (lane = u * G + g), so the
+        // warp issues ONE square-root sequence instead of U and writes runs of G consecutive norms.
+        const int lane = threadIdx.x & 31, G = 32 >> log2cpr;
+        const int g = lane & (G - 1), mu = lane >> (5 - log2cpr);  // G is a power of two: lane / G
+        T mine = T(0);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const T other = __shfl_sync(0xffffffffu, acc[u], g << log2cpr);
+            if (mu == u) mine = other;
+        }
+        if (mu < U) {
+            const int64_t row = (c0 - lane + ((int64_t)g << log2cpr) + (int64_t)mu * kThreads) >> log2cpr;
+            if (row < n) norms[row] = mode == 0 ? mine : sqrt_rn(mine < T(0) ? -mine : mine);
+        }
+        return;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
         if (r[u] >= n) continue;
-        if (mode == 0) { if (j == 0) norms[r[u]] = acc; continue; }
-        const T nrm = sqrt_rn(acc < T(0) ? -acc : acc);
+        if (mode == 0) { if (j == 0) norms[r[u]] = acc[u]; continue; }
+        const T nrm = sqrt_rn(acc[u] < T(0) ? -acc[u] : acc[u]);
         if (mode == 1) { if (j == 0) norms[r[u]] = nrm; continue; }
         if (nrm > (T)1e-14) {                      // batch.rs:805-811
             if (STRICT) {
@@ -389,15 +411,27 @@ sum_partial_aos_vec(const T *__restrict__ x, int64_t ldx, int64_t n, int nb, int
     const int j = threadIdx.x & (cpr - 1), lane = threadIdx.x >> log2cpr;
     const int64_t begin = (int64_t)blockIdx.x * rows_per_block;
     const int64_t end = begin + rows_per_block < n ? begin + rows_per_block : n;
-    double acc[W];
+    double acc[W], acc1[W], acc2[W], acc3[W];
 #pragma unroll
-    for (int l = 0; l < W; ++l) acc[l] = 0.0;
-    for (int64_t r = begin + lane; r < end; r += lanes) {
+    for (int l = 0; l < W; ++l) acc[l] = acc1[l] = acc2[l] = acc3[l] = 0.0;
+    int64_t r = begin + lane;
+    for (; r + 3 * (int64_t)lanes < end; r += 4 * (int64_t)lanes) {  // four loads in flight per thread, folded in a fixed order
+        T v0[W], v1[W], v2[W], v3[W];
+        ldg_stream(x + r * ldx + j * W, v0);
+        ldg_stream(x + (r + lanes) * ldx + j * W, v1);
+        ldg_stream(x + (r + 2 * (int64_t)lanes) * ldx + j * W, v2);
+        ldg_stream(x + (r + 3 * (int64_t)lanes) * ldx + j * W, v3);
+#pragma unroll
+        for (int l = 0; l < W; ++l) { acc[l] += (double)v0[l]; acc1[l] += (double)v1[l]; acc2[l] += (double)v2[l]; acc3[l] += (double)v3[l]; }
+    }
+    for (; r < end; r += lanes) {
         T v[W];
         ldg_stream(x + r * ldx + j * W, v);
 #pragma unroll
         for (int l = 0; l < W; ++l) acc[l] += (double)v[l];
     }
+#pragma unroll
+    for (int l = 0; l < W; ++l) acc[l] = (acc[l] + acc1[l]) + (acc2[l] + acc3[l]);
 #pragma unroll
     for (int l = 0; l < W; ++l) part[(lane * cpr + j) * W + l] = acc[l];  // [lane][blade]
     __syncthreads();
@@ -845,17 +879,33 @@ cudaError_t launch_convert(int nb, const ViewArg &src, const ViewArg &dst, cudaS
             return cudaMemcpy2DAsync(dst.data, dst.ld * es, src.data, src.ld * es, n * es, nb, cudaMemcpyDeviceToDevice, s);
         return cudaMemcpy2DAsync(dst.data, dst.ld * es, src.data, src.ld * es, nb * es, n, cudaMemcpyDeviceToDevice, s);
     }
-    {
-        const cudaError_t e = src.dtype == kF32 ? launch_convert_tma<float>(nb, src, dst, s) : launch_convert_tma<double>(nb, src, dst, s);
-        if (e != cudaErrorNotSupported) return e;
+    // TMA stores clip at 16-byte granularity along the contiguous dimension, so the tiles take the rows up to the last
+    // multiple of 16 bytes of a blade row and the scalar kernel below the 1-3 that remain (a blade-major view may be a
+    // row slice of a larger batch: the element after its last row belongs to somebody else).
+    const int64_t main_rows = n - n % (int64_t)(16 / es);
+    int64_t done = 0;
+    if (main_rows > 0) {
+        ViewArg ms = src, md = dst;
+        ms.n = md.n = main_rows;
+        const cudaError_t e = src.dtype == kF32 ? launch_convert_tma<float>(nb, ms, md, s) : launch_convert_tma<double>(nb, ms, md, s);
+        if (e == cudaSuccess) done = main_rows;
+        else if (e != cudaErrorNotSupported) return e;
     }
+    if (done == n) return cudaSuccess;
+    auto advanced = [&](const ViewArg &v) {
+        ViewArg r = v;
+        r.data = (char *)v.data + (size_t)done * es * (size_t)(v.layout == kAoS ? v.ld : 1);
+        r.n = n - done;
+        return r;
+    };
+    const ViewArg rs = advanced(src), rd = advanced(dst);
     const int C = nb < 32 ? nb : 32;
-    dim3 grid(blocks_for(n, kTileRows), nb / C);
+    dim3 grid(blocks_for(rs.n, kTileRows), nb / C);
     const size_t smem = (size_t)kTileRows * (C + 1) * es;
     auto run = [&](auto tag) {
         using T = decltype(tag);
-        if (dst.layout == kSoA) transpose_kernel<T, true><<<grid, kThreads, smem, s>>>((const T *)src.data, src.ld, (T *)dst.data, dst.ld, n, C);
-        else transpose_kernel<T, false><<<grid, kThreads, smem, s>>>((const T *)src.data, src.ld, (T *)dst.data, dst.ld, n, C);
+        if (dst.layout == kSoA) transpose_kernel<T, true><<<grid, kThreads, smem, s>>>((const T *)rs.data, rs.ld, (T *)rd.data, rd.ld, rs.n, C);
+        else transpose_kernel<T, false><<<grid, kThreads, smem, s>>>((const T *)rs.data, rs.ld, (T *)rd.data, rd.ld, rs.n, C);
     };
     return by_dtype(src.dtype, [&] { run(float()); }, [&] { run(double()); });
 }
@@ -957,6 +1007,9 @@ bool make_soa_tensor_map(CUtensorMap *map, const void *base, int elem_bytes, int
     EncodeFn enc = tensor_map_encoder();
     if (!enc || n <= 0 || n >= (int64_t)1 << 31) return false;
     if (((uintptr_t)base & 15) != 0 || ((ld * elem_bytes) & 15) != 0 || ld < n) return false;
+    // stores are clipped at 16-byte granularity along the row dimension: with n * elem_bytes not a multiple of 16 the
+    // engine would write the element after the last row (zero), which a row-slice view does not own
+    if (((n * elem_bytes) & 15) != 0) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)nb};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * (cuuint64_t)elem_bytes};
     const cuuint32_t box[2] = {(cuuint32_t)rows, (cuuint32_t)nb};

@@ -776,15 +776,18 @@ template <bool STRICT, bool EVEN> static cudaError_t launch_sandwich_soa_tma(con
 // left out (the reference skips them at run time: `if b == 0.0 { continue }`) and only the four blades the
 // extraction reads computed in stage two -- same roundings in the same order, so strict mode is bit-exact.
 // Rows whose weight |w| < 1e-10 have no finite point: NaN, as lcc_pga_points_extract writes them.
-// Data movement: a block's 1024 points are one contiguous 12 KB span; it is copied to shared memory with one
-// cp.async.bulk (1-D TMA), each thread handles 4 points (stride 256: bank-conflict free at 3 words per point),
+// Data movement: a block's 2048 points (f32; 1024 in f64) are one contiguous 24 KB span; it is copied to shared memory
+// with one cp.async.bulk (1-D TMA), each thread handles 8 points (stride 256: bank-conflict free at 3 words per point),
 // the results overwrite the tile and leave with one bulk store.  The last, partial block uses plain accesses.
+// Default mode divides once per point (reciprocal of the weight, then three multiplies; <= 1 ulp from the quotients).
 #if LCC_NB == 16 && !LCC_RUNTIME_METRIC && defined(LCC_SIG_PGA3D)
 #ifndef LCC_POINTS_SHAPE_DEFAULT
-#define LCC_POINTS_SHAPE_DEFAULT 0
+#define LCC_POINTS_SHAPE_DEFAULT 1
 #endif
 // Block shape: THREADS threads, PPT points per thread.  More bytes per resident block keep more of the HBM pipe
 // busy (Little's law: ~70 KB must be in flight per SM); LCC_POINTS_SHAPE selects among the compiled shapes.
+// 2^28 f32 points: 256 x 4 (12 KB tiles) 6201 GB/s, 256 x 8 (24 KB) 6888 GB/s, 128 x 8 (12 KB, 16 blocks per SM)
+// 6874 GB/s (profiles/r01_points_shape_sweep.txt); 256 x 8 is the default.
 __host__ __device__ constexpr bool point_blade(int k) { return k == 7 || k == 11 || k == 13 || k == 14; }
 
 template <bool STRICT, bool EVEN>

@@ -31,6 +31,9 @@ def timed(fn, iters=10):
     return e0.elapsed_time(e1) / iters
 
 
+ONLY = sys.argv[1] if len(sys.argv) > 1 else None  # substring filter on the op name (used for ncu captures)
+
+
 def run(sig, dt, log2n):
     alg = cabi.Algebra(*sig)
     nb, n = alg.num_blades, 1 << log2n
@@ -57,6 +60,8 @@ def run(sig, dt, log2n):
         if alg.r == 0:
             cases["dual"] = (2 * nb * es, lambda: cabi.check(lib.lcc_batch_unary(alg.h, cabi.LCC_UN_DUAL, 0, C.byref(va), C.byref(vo), sptr)))
         for name, (bytes_per, fn) in cases.items():
+            if ONLY and ONLY not in name:
+                continue
             ms = timed(fn)
             print(json.dumps({"sig": sig, "dtype": dt, "rows": n, "layout": layout_name, "op": name, "ms": round(ms, 4),
                               "GBps": round(bytes_per * n / ms / 1e6, 1)}), flush=True)
@@ -66,6 +71,8 @@ def run(sig, dt, log2n):
     vA = cabi.view(x_aos.data_ptr(), n, nb, code, cabi.LCC_AOS)
     vS = cabi.view(x_soa.data_ptr(), n, n, code, cabi.LCC_SOA)
     for name, src, dst in (("convert_aos_to_soa", vA, vS), ("convert_soa_to_aos", vS, vA)):
+        if ONLY and ONLY not in name:
+            continue
         ms = timed(lambda: cabi.check(lib.lcc_batch_convert(alg.h, C.byref(src), C.byref(dst), sptr)))
         print(json.dumps({"sig": sig, "dtype": dt, "rows": n, "layout": "both", "op": name, "ms": round(ms, 4),
                           "GBps": round(2 * nb * es * n / ms / 1e6, 1)}), flush=True)
@@ -73,5 +80,6 @@ def run(sig, dt, log2n):
 
 if __name__ == "__main__":
     run((3, 0, 1), "f32", 26)
-    run((4, 1, 0), "f64", 24)
-    run((3, 0, 0), "f64", 26)
+    if not ONLY:
+        run((4, 1, 0), "f64", 24)
+        run((3, 0, 0), "f64", 26)
