@@ -281,8 +281,16 @@ def run_gpu_arm(args):
             return cabi.view(t.data_ptr(), t.shape[0], t.stride(0), code, cabi.LCC_AOS)
         return cabi.view(t.data_ptr(), t.shape[1], t.stride(0), code, cabi.LCC_SOA)
 
+    def soa_alloc(fill_random):  # (nb, n) blade-major view whose blade rows are n + --ld-pad elements apart
+        t = torch.empty((nb, n + args.ld_pad), device=dev, dtype=tdt)
+        if fill_random:
+            t.normal_(generator=gen)
+        else:
+            t.zero_()
+        return t[:, :n]
+
     def randn_batch():
-        t = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
+        t = soa_alloc(True)
         return t.T.contiguous() if aos_layout else t
 
     def rows_of(t, idx):  # (len(idx), nb) host array of the selected rows
@@ -294,14 +302,14 @@ def run_gpu_arm(args):
         pass
 
     if wl == "pga_sandwich":
-        x = torch.zeros((nb, n), device=dev, dtype=tdt)
+        x = soa_alloc(False)
         pts = torch.randn((3, n), device=dev, dtype=tdt, generator=gen)
         x[7].fill_(1.0)
         x[14].copy_(-pts[0]); x[13].copy_(pts[1]); x[11].copy_(-pts[2])
         del pts
         if aos_layout:
             x = x.T.contiguous()
-        out = torch.empty_like(x)
+        out = torch.empty_like(x) if aos_layout else soa_alloc(False)
         motor = headline_motor()
         mptr = motor.ctypes.data_as(C.POINTER(C.c_double))
         vx, vo = soa(x), soa(out)
@@ -319,10 +327,10 @@ def run_gpu_arm(args):
     elif wl in ("cga_gp", "r3_gp", "cga_gp_outer"):
         a = randn_batch()
         b = randn_batch()
-        out = torch.empty_like(a)
+        out = torch.empty_like(a) if aos_layout else soa_alloc(False)
         va, vb, vo = soa(a), soa(b), soa(out)
         if wl == "cga_gp_outer":
-            out2 = torch.empty_like(a)
+            out2 = torch.empty_like(a) if aos_layout else soa_alloc(False)
             vo2 = soa(out2)
 
             def step():
@@ -604,6 +612,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS))
     ap.add_argument("--log2-rows", type=int, default=0, help="override rows per GPU (power of two exponent)")
+    ap.add_argument("--ld-pad", type=int, default=0, help="experiment: extra elements between consecutive blade rows of the SoA operands (a multiple of 64)")
     ap.add_argument("--layout", default="soa", choices=["soa", "aos"], help="HBM layout of the batches (aos = the reference's (N, num_blades) rows)")
     ap.add_argument("--strict", action="store_true", help="LCC_FLAG_STRICT_FP (bit-exact, no FMA)")
     ap.add_argument("--cpu-threads", type=int, default=0, help="reference arm: OpenMP threads (default 1 = the reference's behaviour)")

@@ -27,25 +27,36 @@ inline unsigned blocks_for(int64_t items, int per_block = kThreads) { return (un
 // out[k][r] = factor[k] == 0 ? +0 : x[source[k]][r] * (factor[k] * scale)
 // reverse / grade_involution multiply by +-1.0 exactly like /root/reference/src/batch.rs:823-860;
 // grade(k) writes literal zeros like batch.rs:1038-1046; scale is batch.rs:957-962.
+// Each thread moves kMapChunks 16-byte chunks, kThreads chunks apart, and issues their loads back to back: with a
+// single chunk per thread the map kernels sat at 6.2-6.6 TB/s while `add` (two loads per thread) reached 7.1 TB/s.
+constexpr int kMapChunks = 2;
+
 template <class T>
 __global__ void __launch_bounds__(kThreads)
 blade_map_soa(const T *__restrict__ x, int64_t ldx, T *__restrict__ out, int64_t ldo, int64_t n, const BladeMap map, T scale) {
-    constexpr int W = VecW<T>::value;
+    constexpr int W = VecW<T>::value, U = kMapChunks;
     const int k = blockIdx.y;
-    const int64_t r0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * W;
-    if (r0 >= n) return;
+    const int64_t r0 = ((int64_t)blockIdx.x * (kThreads * U) + threadIdx.x) * W;
     const int f = map.factor[k];
-    T v[W];
-    if (f == 0) {
+    const T m = (f > 0 ? scale : -scale);
+    T v[U][W];
 #pragma unroll
-        for (int l = 0; l < W; ++l) v[l] = T(0);
-    } else {
-        ldg_stream(x + (int64_t)map.source[k] * ldx + r0, v);
-        const T m = (f > 0 ? scale : -scale);
+    for (int u = 0; u < U; ++u) {
+        const int64_t r = r0 + (int64_t)u * kThreads * W;
 #pragma unroll
-        for (int l = 0; l < W; ++l) v[l] = mul_rn(v[l], m);
+        for (int l = 0; l < W; ++l) v[u][l] = T(0);
+        if (f != 0 && r < n) ldg_stream(x + (int64_t)map.source[k] * ldx + r, v[u]);
     }
-    stg_stream(out + (int64_t)k * ldo + r0, v);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int64_t r = r0 + (int64_t)u * kThreads * W;
+        if (r >= n) break;
+        if (f != 0) {
+#pragma unroll
+            for (int l = 0; l < W; ++l) v[u][l] = mul_rn(v[u][l], m);
+        }
+        stg_stream(out + (int64_t)k * ldo + r, v[u]);
+    }
 }
 
 template <class T>
@@ -117,23 +128,32 @@ blade_map_aos_vec(const T *__restrict__ x, int64_t ldx, T *__restrict__ out, int
         ssrc[k] = map.source[k];
     }
     __syncthreads();
-    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    const int64_t r = c >> log2cpr;
-    if (r >= n) return;
-    const int k0 = (int)(c & ((1 << log2cpr) - 1)) * W;
-    T f[W], v[W];
+    constexpr int U = kMapChunks;
+    const int64_t c0 = (int64_t)blockIdx.x * (kThreads * U) + threadIdx.x;
+    const int k0 = (int)(c0 & ((1 << log2cpr) - 1)) * W;  // the same chunk of the row for every u (kThreads % cpr == 0)
+    T f[W], v[U][W];
     bool any = false;
 #pragma unroll
     for (int l = 0; l < W; ++l) { f[l] = sfac[k0 + l]; any |= f[l] != T(0); }
-    if (DIAG) {
-        if (any) ldg_stream(x + r * ldx + k0, v);
 #pragma unroll
-        for (int l = 0; l < W; ++l) v[l] = f[l] != T(0) ? mul_rn(v[l], f[l]) : T(0);
-    } else {
+    for (int u = 0; u < U; ++u) {
+        const int64_t r = (c0 + (int64_t)u * kThreads) >> log2cpr;
+        if (r >= n) continue;
+        if (DIAG) {
+            if (any) ldg_stream(x + r * ldx + k0, v[u]);
+        } else {
 #pragma unroll
-        for (int l = 0; l < W; ++l) v[l] = f[l] != T(0) ? mul_rn(__ldg(x + r * ldx + ssrc[k0 + l]), f[l]) : T(0);
+            for (int l = 0; l < W; ++l) v[u][l] = f[l] != T(0) ? __ldg(x + r * ldx + ssrc[k0 + l]) : T(0);
+        }
     }
-    stg_stream(out + r * ldo + k0, v);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int64_t r = (c0 + (int64_t)u * kThreads) >> log2cpr;
+        if (r >= n) break;
+#pragma unroll
+        for (int l = 0; l < W; ++l) v[u][l] = f[l] != T(0) ? mul_rn(v[u][l], f[l]) : T(0);
+        stg_stream(out + r * ldo + k0, v[u]);
+    }
 }
 
 template <class T>
@@ -288,7 +308,7 @@ template <class T, bool STRICT, int NB>
 __global__ void __launch_bounds__(kThreads)
 normalized_soa_regs(const T *__restrict__ x, int64_t ldx, int64_t n, const Weights wt, T *__restrict__ out, int64_t ldo) {
     constexpr int V = NB >= 32 ? 1 : (NB >= 16 && sizeof(T) == 8 ? 1 : VecW<T>::value);
-    const int64_t r0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * V;
+    const int64_t r0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
     if (r0 >= n) return;
     T v[NB][V], acc[V];
 #pragma unroll
@@ -721,14 +741,14 @@ cudaError_t launch_blade_map(int nb, const ViewArg &x, const ViewArg &out, const
         using T = decltype(tag);
         if (x.layout == kSoA) {
             constexpr int W = VecW<T>::value;
-            dim3 grid(blocks_for((n + W - 1) / W), nb);
+            dim3 grid(blocks_for((n + W - 1) / W, kThreads * kMapChunks), nb);
             blade_map_soa<T><<<grid, kThreads, 0, s>>>((const T *)x.data, x.ld, (T *)out.data, out.ld, n, map, (T)scale);
         } else if (aos_vec_ok(x, nb, VecW<T>::value) && aos_vec_ok(out, nb, VecW<T>::value)) {
             constexpr int W = VecW<T>::value;
             const int cpr = nb / W;
             bool diag = true;
             for (int k = 0; k < nb; ++k) diag = diag && (map.factor[k] == 0 || map.source[k] == k);
-            const unsigned grid = blocks_for(n * cpr);
+            const unsigned grid = blocks_for(n * cpr, kThreads * kMapChunks);
             if (diag) blade_map_aos_vec<T, true><<<grid, kThreads, 0, s>>>((const T *)x.data, x.ld, (T *)out.data, out.ld, n, nb, ilog2(cpr), map, (T)scale);
             else blade_map_aos_vec<T, false><<<grid, kThreads, 0, s>>>((const T *)x.data, x.ld, (T *)out.data, out.ld, n, nb, ilog2(cpr), map, (T)scale);
         } else {
@@ -780,10 +800,13 @@ cudaError_t launch_norm(int nb, int mode, bool strict, const ViewArg &x, const i
 #define LCC_NORMALIZED_CASE(NBV)                                                                                                  \
     case NBV: {                                                                                                                   \
         constexpr int V = NBV >= 32 ? 1 : (NBV >= 16 && sizeof(T) == 8 ? 1 : W);                                                  \
-        const unsigned gr = blocks_for((n + V - 1) / V);                                                                          \
+        /* 64-thread blocks: the row lives in 64-130 registers, so 256-thread blocks fit twice per SM and move through  \
+         * load / compute / store in lock step (5.3 TB/s); small blocks interleave their phases, as in K1 / K2 */         \
+        constexpr int kBlock = 64;                                                                                                \
+        const unsigned gr = blocks_for((n + V - 1) / V, kBlock);                                                                  \
         if (n % V != 0) break; /* padded rows are addressable (ld >= n rounded up), but keep the tail on the generic kernel */  \
-        if (strict) normalized_soa_regs<T, true, NBV><<<gr, kThreads, 0, s>>>((const T *)x.data, x.ld, n, wt, (T *)out.data, out.ld); \
-        else normalized_soa_regs<T, false, NBV><<<gr, kThreads, 0, s>>>((const T *)x.data, x.ld, n, wt, (T *)out.data, out.ld);   \
+        if (strict) normalized_soa_regs<T, true, NBV><<<gr, kBlock, 0, s>>>((const T *)x.data, x.ld, n, wt, (T *)out.data, out.ld); \
+        else normalized_soa_regs<T, false, NBV><<<gr, kBlock, 0, s>>>((const T *)x.data, x.ld, n, wt, (T *)out.data, out.ld);   \
         return;                                                                                                                   \
     }
             switch (nb) {
