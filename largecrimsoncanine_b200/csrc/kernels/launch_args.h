@@ -34,11 +34,14 @@ struct ProductArgs {
 };
 
 // Fixed grid of the fused reduction: block b always owns the same rows and writes partial[b], so results do not
-// depend on n, on timing or on which SM runs a block.  Many more blocks than resident slots (148 SMs x 4) on
-// purpose: when a concurrent kernel (the NCCL all-reduce of the previous step) holds a slot for a while, the
-// hardware scheduler hands its share to the other slots at block granularity instead of one late block
-// finishing 0.2 ms after everybody else (2 GPUs: 3.79 ms per step with one wave of 592 blocks).
-constexpr int kFusedSumBlocks = 148 * 4 * 8;
+// depend on n, on timing or on which SM runs a block.  Many more blocks than resident slots (148 SMs x 6 at 138
+// registers and 64 threads) on purpose: (1) the tail -- the last, partly filled wave cannot saturate HBM -- shrinks
+// with the block count: 4736 blocks 6775 GB/s, 8288 6989, 16576 7129, 33152 7143 (STA f64, 2^27 rows,
+// profiles/r01_sta_fused_grid_sweep.txt); (2) when a concurrent kernel (the NCCL all-reduce of the previous step)
+// holds a slot for a while, the hardware scheduler hands its share to the other slots at block granularity instead
+// of one late block finishing 0.2 ms after everybody else (2 GPUs: 3.79 ms per step with one wave of 592 blocks).
+// LCC_FUSED_SUM_BLOCKS overrides it for sweeps (lcc_abi.cu).
+constexpr int kFusedSumBlocks = 148 * 112;
 
 struct SandwichArgs {
     int dtype = kF64;

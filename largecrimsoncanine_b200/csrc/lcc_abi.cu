@@ -64,6 +64,11 @@ static int64_t env_or(const char *name, int64_t fallback) {
 }
 static std::atomic<int64_t> g_aos_tma_min_rows{env_or("LCC_AOS_TMA_MIN_ROWS", 4096)};
 static std::atomic<int64_t> g_soa_tma_min_bytes{env_or("LCC_SOA_TMA_MIN_BYTES", 8ll << 30)};
+// grid of the fused product + batch-sum kernel (kernels/launch_args.h); LCC_FUSED_SUM_BLOCKS overrides it for sweeps
+static int fused_sum_blocks() {
+    static const int v = [] { const int64_t e = env_or("LCC_FUSED_SUM_BLOCKS", kFusedSumBlocks); return e >= 1 && e <= (1 << 20) ? (int)e : kFusedSumBlocks; }();
+    return v;
+}
 int64_t option_aos_tma_min_rows() { return g_aos_tma_min_rows.load(std::memory_order_relaxed); }
 int64_t option_soa_tma_min_bytes() { return g_soa_tma_min_bytes.load(std::memory_order_relaxed); }
 
@@ -593,16 +598,16 @@ lcc_status lcc_batch_product_sum(const lcc_algebra *alg, int op, const lcc_view 
     const bool a_bc = a->n == 1 && n > 1, b_bc = b->n == 1 && n > 1;
     if (alg->nb <= 32 && alg->product[a->dtype]) {
         PoolBuffer partial;
-        LCC_TRY(partial.alloc((size_t)alg->nb * kFusedSumBlocks * sizeof(double), s));
+        LCC_TRY(partial.alloc((size_t)alg->nb * fused_sum_blocks() * sizeof(double), s));
         ProductArgs g;
         g.op = op; g.dtype = a->dtype; g.layout = a->layout; g.strict = strict; g.n = n;
         g.a = a->data; g.lda = a->ld; g.a_bcast = a_bc;
         g.b = b->data; g.ldb = b->ld; g.b_bcast = b_bc;
         g.mu = alg->specialised ? nullptr : alg->mu.data();
-        g.sum_partial = (double *)partial.ptr; g.sum_blocks = kFusedSumBlocks; g.a_grade = a_grade < 0 ? -1 : a_grade;
+        g.sum_partial = (double *)partial.ptr; g.sum_blocks = fused_sum_blocks(); g.a_grade = a_grade < 0 ? -1 : a_grade;
         g.stream = s;
         LCC_CUDA(alg->product[a->dtype](g));
-        LCC_CUDA(launch_sum_final(alg->nb, kFusedSumBlocks, (const double *)partial.ptr, sums_dev, a->dtype, s));
+        LCC_CUDA(launch_sum_final(alg->nb, fused_sum_blocks(), (const double *)partial.ptr, sums_dev, a->dtype, s));
         return LCC_OK;
     }
     // large algebras: unfused composition through pool temporaries (grade -> product -> sum)
