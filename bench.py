@@ -463,6 +463,8 @@ def run_gpu_arm(args):
     e2e = None
     if wl == "pga_sandwich" and not args.no_e2e:
         e2e = measure_e2e(args, lib, alg, code, motor, n, nb, world, rank, dev, dist if world > 1 else None, flags)
+    elif wl == "pga_points_compact" and not args.no_e2e:
+        e2e = measure_e2e(args, lib, alg, code, motor, n, nb, world, rank, dev, dist if world > 1 else None, flags, compact=True)
 
     if rank != 0:
         if world > 1:
@@ -547,8 +549,9 @@ def bind_to_gpu_numa_node(local):
         return False
 
 
-def measure_e2e(args, lib, alg, code, motor, n, nb, world, rank, dev, dist, flags):
-    """lcc_host_sandwich on pinned host buffers in the reference's (N, 16) row-major layout."""
+def measure_e2e(args, lib, alg, code, motor, n, nb, world, rank, dev, dist, flags, compact=False):
+    """lcc_host_sandwich on pinned host buffers in the reference's (N, 16) row-major layout; with `compact`,
+    lcc_host_pga_points_sandwich on pinned (N, 3) xyz buffers (the pga_points_compact workload)."""
     import psutil
     import torch
 
@@ -557,6 +560,8 @@ def measure_e2e(args, lib, alg, code, motor, n, nb, world, rank, dev, dist, flag
     from largecrimsoncanine_b200 import cabi
 
     es = 4 if code == cabi.LCC_F32 else 8
+    if compact:
+        return measure_e2e_compact(args, lib, alg, code, motor, n, es, world, rank, dev, dist, flags, numa_bound)
     n_e2e = n
     need = 2 * n_e2e * nb * es * max(world, 1)
     avail = psutil.virtual_memory().available
@@ -602,6 +607,49 @@ def measure_e2e(args, lib, alg, code, motor, n, nb, world, rank, dev, dist, flag
             "api": "lcc_host_sandwich (C ABI, pinned host buffers, chunked H2D/kernel/D2H pipeline)",
             "timer": "host wall clock around the blocking call, max over ranks", "checked_against_oracle": ok,
             "numa_bound": numa_bound}
+
+
+def measure_e2e_compact(args, lib, alg, code, motor, n, es, world, rank, dev, dist, flags, numa_bound):
+    import torch
+
+    from largecrimsoncanine_b200 import cabi
+
+    tdt = torch.float32 if es == 4 else torch.float64
+    xh = torch.empty((n, 3), dtype=tdt, pin_memory=True)
+    oh = torch.empty((n, 3), dtype=tdt, pin_memory=True)
+    g = torch.Generator().manual_seed(7 + rank)
+    blk = 1 << 24
+    for s in range(0, n, blk):
+        e = min(n, s + blk)
+        xh[s:e].normal_(generator=g)
+    mptr = motor.ctypes.data_as(C.POINTER(C.c_double))
+
+    def call():
+        cabi.check(lib.lcc_host_pga_points_sandwich(alg.h, code, mptr, C.c_void_p(xh.data_ptr()), C.c_void_p(oh.data_ptr()), n, flags))
+
+    steps = max(1, min(args.steps, args.e2e_steps))
+    call()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        call()
+    torch.cuda.synchronize()
+    dt_s = time.perf_counter() - t0
+    if dist:
+        t = torch.tensor([dt_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_s = float(t.item())
+    import oracle
+
+    sample = np.r_[0:2048, n - 2048:n]
+    want = oracle.pga_transform_points(motor, xh[sample].numpy())
+    ok = bool(np.abs(oh[sample].numpy() - want).max() <= 1e-4)
+    return {"value": world * n * steps / dt_s, "unit": "points/s", "h2d_bytes_per_step": n * 3 * es, "d2h_bytes_per_step": n * 3 * es,
+            "points_per_gpu": n, "steps": steps,
+            "api": "lcc_host_pga_points_sandwich (C ABI, pinned host (N,3) buffers, chunked H2D/kernel/D2H pipeline)",
+            "timer": "host wall clock around the blocking call, max over ranks", "checked_against_oracle": ok, "numa_bound": numa_bound}
 
 
 def main():

@@ -247,6 +247,11 @@ LCC_API lcc_status lcc_host_sandwich(const lcc_algebra *alg, int dtype, const do
                                      void *out_host, int64_t n, unsigned flags);
 LCC_API lcc_status lcc_host_product(const lcc_algebra *alg, int dtype, int op, const void *a_host, int64_t na,
                                     const void *b_host, int64_t nb_rows, void *out_host, unsigned flags);
+/* lcc_pga_points_sandwich with HOST (n,3) arrays: 2 x 3 elements per point cross PCIe instead of the 2 x 16 of the
+ * dense path (the reference has no batched form: a Python loop over Multivector.pga_point / sandwich /
+ * pga_point_coords, src/pga.rs:110-135,579-599).  xyz_host_out may equal xyz_host_in. */
+LCC_API lcc_status lcc_host_pga_points_sandwich(const lcc_algebra *alg, int dtype, const double *motor, const void *xyz_host_in,
+                                                void *xyz_host_out, int64_t n, unsigned flags);
 
 /* ---------------------------------------------------------------- tuning */
 

@@ -109,6 +109,7 @@ def lib():
         "lcc_sta_boosts_embed": (i32, [vp, vp, V, vp]),
         "lcc_host_sandwich": (i32, [vp, i32, C.POINTER(dbl), vp, vp, i64, u32]),
         "lcc_host_product": (i32, [vp, i32, i32, vp, i64, vp, i64, vp, u32]),
+        "lcc_host_pga_points_sandwich": (i32, [vp, i32, C.POINTER(dbl), vp, vp, i64, u32]),
         "lcc_set_option": (i32, [C.c_char_p, i64]),
         "lcc_get_option": (i32, [C.c_char_p, C.POINTER(i64)]),
         "lcc_kernel_launch_count": (C.c_uint64, []),

@@ -129,6 +129,10 @@ fixed_product_f64_dmma_kernel(const double *__restrict__ x, int64_t ldx, double 
     }
 }
 
+// A persistent variant (one CTA per SM, (tile, chunk) flattened behind a three-stage cp.async ring, one barrier per
+// chunk, next tile's loads in flight during the epilogue) was measured and does not pay: 30.71 vs 30.53 TFLOP/s at 2^24
+// rows of Cl(8,0,0).  The loop is bound by the DMMA pipe itself -- 128 flop/clk/SM x 148 SMs x 1.965 GHz = 37.2 TFLOP/s,
+// of which the kernel sustains 82 % -- not by its prologue or barriers, so the simpler form stays.
 template <int NB> cudaError_t launch_dmma_t(const double *x, int64_t ldx, double *out, int64_t ldo, int64_t n, const double *wt, cudaStream_t s) {
     constexpr int BN = NB < 128 ? NB : 128;
     constexpr int smem = (2 * kBK * kXPitch + 2 * BN * kWPitch) * (int)sizeof(double);

@@ -968,6 +968,44 @@ lcc_status lcc_host_sandwich(const lcc_algebra *alg, int dtype, const double *ro
     return LCC_OK;
 }
 
+lcc_status lcc_host_pga_points_sandwich(const lcc_algebra *alg, int dtype, const double *motor, const void *xyz_host_in,
+                                        void *xyz_host_out, int64_t n, unsigned flags) {
+    if (!alg) return fail(LCC_ERR_VALUE, "algebra handle is NULL");
+    LCC_TRY(points_check(alg, 0));
+    if (dtype != LCC_F32 && dtype != LCC_F64) return fail(LCC_ERR_VALUE, "dtype must be LCC_F32 or LCC_F64");
+    if (n < 0) return fail(LCC_ERR_VALUE, "negative batch size");
+    if (n == 0) return LCC_OK;
+    if (!motor || !xyz_host_in || !xyz_host_out) return fail(LCC_ERR_VALUE, "NULL buffer");
+    Pipeline pl;
+    LCC_TRY(pl.init());
+    const size_t row_bytes = 3 * elem_size(dtype);
+    int64_t chunk = (kChunkBytes / (int64_t)row_bytes) & ~(int64_t)3;
+    if (chunk > n) chunk = n;
+    // separate input and output stages: with an in-place stage the next H2D copy would have to wait for the D2H copy of
+    // the same buffer and the two PCIe directions would run in lock step (42 instead of 48 GB/s each way)
+    PoolBuffer in[2], out[2];
+    for (int i = 0; i < 2; ++i) { LCC_TRY(in[i].alloc(chunk * row_bytes, pl.st->stream)); LCC_TRY(out[i].alloc(chunk * row_bytes, pl.st->stream)); }
+    LCC_CUDA(cudaStreamSynchronize(pl.st->stream));
+    int64_t done = 0;
+    for (int64_t c = 0; done < n; ++c, done += chunk) {
+        const int buf = (int)(c & 1);
+        const int64_t rows = (n - done) < chunk ? (n - done) : chunk;
+        if (c >= 2) LCC_CUDA(cudaStreamWaitEvent(pl.st->copy_in, pl.kern[buf], 0));
+        LCC_CUDA(cudaMemcpyAsync(in[buf].ptr, (const char *)xyz_host_in + done * row_bytes, rows * row_bytes, cudaMemcpyHostToDevice, pl.st->copy_in));
+        LCC_CUDA(cudaEventRecord(pl.h2d[buf], pl.st->copy_in));
+        LCC_CUDA(cudaStreamWaitEvent(pl.st->stream, pl.h2d[buf], 0));
+        if (c >= 2) LCC_CUDA(cudaStreamWaitEvent(pl.st->stream, pl.d2h[buf], 0));
+        LCC_TRY(lcc_pga_points_sandwich(alg, dtype, motor, in[buf].ptr, out[buf].ptr, rows, flags, (void *)pl.st->stream));
+        LCC_CUDA(cudaEventRecord(pl.kern[buf], pl.st->stream));
+        LCC_CUDA(cudaStreamWaitEvent(pl.st->copy_out, pl.kern[buf], 0));
+        LCC_CUDA(cudaMemcpyAsync((char *)xyz_host_out + done * row_bytes, out[buf].ptr, rows * row_bytes, cudaMemcpyDeviceToHost, pl.st->copy_out));
+        LCC_CUDA(cudaEventRecord(pl.d2h[buf], pl.st->copy_out));
+    }
+    LCC_CUDA(cudaStreamSynchronize(pl.st->copy_out));
+    LCC_CUDA(cudaStreamSynchronize(pl.st->stream));
+    return LCC_OK;
+}
+
 lcc_status lcc_host_product(const lcc_algebra *alg, int dtype, int op, const void *a_host, int64_t na, const void *b_host,
                             int64_t nb_rows, void *out_host, unsigned flags) {
     if (!alg) return fail(LCC_ERR_VALUE, "algebra handle is NULL");

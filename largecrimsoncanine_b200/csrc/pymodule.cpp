@@ -502,11 +502,8 @@ PYBIND11_MODULE(largecrimsoncanine, m) {
         const std::vector<double> m = motor.coeffs;
         const unsigned flags = fp_flags();
         py::gil_scoped_release nogil;
-        DeviceTemp stage(bytes);
-        upload(host, bytes, stage.ptr);
-        check(lcc_pga_points_sandwich(a.inner->h, dtype, m.data(), stage.ptr, stage.ptr, n, flags, nullptr));
-        check(lcc_memcpy_d2h(out_ptr, stage.ptr, bytes, nullptr));
-        check(lcc_stream_sync(nullptr));
+        // chunked H2D / kernel / D2H pipeline on host arrays (include/lcc_b200.h): 24 bytes per f32 point cross PCIe
+        check(lcc_host_pga_points_sandwich(a.inner->h, dtype, m.data(), host, out_ptr, n, flags));
         return out;
     }, "Apply a PGA3D motor to an (N,3) array of points: embed, sandwich and extract fused in one kernel.");
     m.def("set_option", [](const std::string &name, int64_t value) { check(lcc_set_option(name.c_str(), value)); },

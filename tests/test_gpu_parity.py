@@ -866,3 +866,32 @@ def test_layout_conversion_through_tma_tiles(L, sig, dt):
         assert np.array_equal(back[:, :nb], x)
         assert np.all(back[:, nb:] == 7.0)
         dev.free()
+
+
+def test_host_pga_points_entry_point(L):
+    """lcc_host_pga_points_sandwich: (N,3) host arrays through the chunked H2D -> fused kernel -> D2H pipeline, several
+    chunks of 64 MiB and a ragged last one, out of place and in place; strict mode is bit-exact against the oracle's
+    embed + sandwich + extract (src/pga.rs:131-134, batch.rs:434-503, pga.rs:579-599)."""
+    from largecrimsoncanine_b200 import cabi
+
+    lib = cabi.lib()
+    alg = cabi.Algebra(3, 0, 1)
+    rng = np.random.default_rng(59)
+    n = 12_000_003  # > 2 chunks at 12 B/point
+    xyz = rng.standard_normal((n, 3), dtype=np.float32)
+    motor = np.zeros(16)
+    motor[[0, 3, 5, 6, 9, 10, 12]] = rng.standard_normal(7)
+    mptr = motor.ctypes.data_as(C.POINTER(C.c_double))
+    out = np.empty_like(xyz)
+    cabi.check(lib.lcc_host_pga_points_sandwich(alg.h, cabi.LCC_F32, mptr, xyz.ctypes.data, out.ctypes.data, n, cabi.LCC_FLAG_STRICT_FP))
+    sample = np.r_[0:4096, n // 2:n // 2 + 4096, n - 4096:n]
+    want = oracle.pga_transform_points(motor, xyz[sample])
+    assert np.array_equal(out[sample], want, equal_nan=True)
+    inplace = xyz.copy()
+    cabi.check(lib.lcc_host_pga_points_sandwich(alg.h, cabi.LCC_F32, mptr, inplace.ctypes.data, inplace.ctypes.data, n, cabi.LCC_FLAG_STRICT_FP))
+    assert np.array_equal(inplace, out, equal_nan=True)
+    small = rng.standard_normal((5, 3))
+    res = np.empty_like(small)
+    cabi.check(lib.lcc_host_pga_points_sandwich(alg.h, cabi.LCC_F64, mptr, small.ctypes.data, res.ctypes.data, 5, cabi.LCC_FLAG_STRICT_FP))
+    assert np.array_equal(res, oracle.pga_transform_points(motor, small), equal_nan=True)
+    assert lib.lcc_host_pga_points_sandwich(cabi.Algebra(3, 0, 0).h, cabi.LCC_F32, mptr, xyz.ctypes.data, out.ctypes.data, 8, 0) == cabi.LCC_ERR_VALUE
