@@ -979,7 +979,8 @@ lcc_status lcc_host_pga_points_sandwich(const lcc_algebra *alg, int dtype, const
     Pipeline pl;
     LCC_TRY(pl.init());
     const size_t row_bytes = 3 * elem_size(dtype);
-    int64_t chunk = (kChunkBytes / (int64_t)row_bytes) & ~(int64_t)3;
+    // 16 MiB chunks: the whole batch is only 12-24 bytes per point, so the un-overlapped first H2D and last D2H copy weigh more
+    int64_t chunk = ((kChunkBytes / 4) / (int64_t)row_bytes) & ~(int64_t)3;
     if (chunk > n) chunk = n;
     // separate input and output stages: with an in-place stage the next H2D copy would have to wait for the D2H copy of
     // the same buffer and the two PCIe directions would run in lock step (42 instead of 48 GB/s each way)
