@@ -212,7 +212,7 @@ def run_reference_arm(args):
                          "host_threads_available": cores, "all_cores_value": all_cores_value, "all_cores": cores},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit_line(line)
     return 0
 
 
@@ -499,7 +499,7 @@ def run_gpu_arm(args):
         "roofline": roofline_block(wl, n, kernel_ms, bytes_per, peaks, peak_kind, traffic),
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(), "parity": parity,
     }
-    print(json.dumps(line))
+    emit_line(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -652,7 +652,27 @@ def measure_e2e_compact(args, lib, alg, code, motor, n, es, world, rank, dev, di
             "timer": "host wall clock around the blocking call, max over ranks", "checked_against_oracle": ok, "numa_bound": numa_bound}
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else that writes to file descriptor 1 during the run (NCCL prints
+    its version banner there when NCCL_DEBUG is set on the box) is sent to stderr instead."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
