@@ -343,7 +343,9 @@ normalized_soa_regs(const T *__restrict__ x, int64_t ldx, int64_t n, const Weigh
 // Column sums with a fixed tree: thread-sequential over a strided chunk, warp shuffle, shared
 // memory across warps, then a second pass over the per-block partials in block order.  f32 data
 // is accumulated in f64 and rounded once at the end.
-constexpr int kSumBlocksMax = 1024;
+constexpr int kSumBlocksMax = 1024;       // blade-major: the grid is (blocks, blades)
+constexpr int kSumBlocksMaxAos = 148 * 32;  // row-major: one block spans all blades; at 64 registers 4 blocks fit per SM, and 1024
+                                           // blocks were 1.7 waves whose tail idled 13 % of the kernel (profiles/r01_aux_ops_r7.jsonl: 5.4 TB/s)
 
 __device__ __forceinline__ double block_reduce_sum(double v) {
     __shared__ double warp_part[kThreads / 32];
@@ -826,17 +828,18 @@ cudaError_t launch_norm(int nb, int mode, bool strict, const ViewArg &x, const i
     return by_dtype(x.dtype, [&] { run(float()); }, [&] { run(double()); });
 }
 
-static int sum_blocks(int64_t n) {
+static int sum_blocks(int64_t n, int layout) {
     int64_t b = (n + (int64_t)kThreads * 16 - 1) / ((int64_t)kThreads * 16);
+    const int64_t cap = layout == kSoA ? kSumBlocksMax : kSumBlocksMaxAos;
     if (b < 1) b = 1;
-    if (b > kSumBlocksMax) b = kSumBlocksMax;
+    if (b > cap) b = cap;
     return (int)b;
 }
-int64_t sum_scratch_elems(int nb, int64_t n) { return (int64_t)nb * sum_blocks(n); }
+int64_t sum_scratch_elems(int nb, int64_t n) { return (int64_t)nb * sum_blocks(n, kAoS); }  // the larger of the two grids
 
 cudaError_t launch_sum(int nb, const ViewArg &x, void *sums_dev, void *scratch_dev, int64_t scratch_elems, cudaStream_t s) {
     const int64_t n = x.n;
-    const int nblocks = sum_blocks(n);
+    const int nblocks = sum_blocks(n, x.layout);
     if (scratch_elems < (int64_t)nb * nblocks) return cudaErrorInvalidValue;
     int64_t rows_per_block = (n + nblocks - 1) / nblocks;
     rows_per_block = (rows_per_block + 3) & ~(int64_t)3;  // block ranges start on 16-byte boundaries

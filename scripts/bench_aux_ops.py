@@ -80,6 +80,6 @@ def run(sig, dt, log2n):
 
 if __name__ == "__main__":
     run((3, 0, 1), "f32", 26)
-    if not ONLY:
+    if not ONLY or os.environ.get("AUX_ALL_SIGS"):
         run((4, 1, 0), "f64", 24)
         run((3, 0, 0), "f64", 26)
