@@ -219,6 +219,9 @@ norm_kernel(const T *__restrict__ x, int64_t ldx, int64_t n, int nb, const Weigh
 // Every thread takes kNormRowsInFlight chunks, kThreads chunks apart, and issues all their loads before the first
 // reduction: with one 16-byte load per thread the kernel is latency-bound (3.5-4.5 TB/s, profiles/r01_aux_ops_after.jsonl).
 constexpr int kNormRowsInFlight = 4;
+#ifndef LCC_NORMALIZED_MODE_DEFAULT
+#define LCC_NORMALIZED_MODE_DEFAULT 2
+#endif
 
 template <class T, bool STRICT>
 __global__ void __launch_bounds__(kThreads)
@@ -304,10 +307,9 @@ norm_aos_lanes(const T *__restrict__ x, int64_t ldx, int64_t n, int log2cpr, con
 }
 
 // SoA `normalized` with the row held in registers (NB known at compile time): one read and one write per element.
-template <class T, bool STRICT, int NB>
+template <class T, bool STRICT, int NB, int V>
 __global__ void __launch_bounds__(kThreads)
 normalized_soa_regs(const T *__restrict__ x, int64_t ldx, int64_t n, const Weights wt, T *__restrict__ out, int64_t ldo) {
-    constexpr int V = NB >= 32 ? 1 : (NB >= 16 && sizeof(T) == 8 ? 1 : VecW<T>::value);
     const int64_t r0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
     if (r0 >= n) return;
     T v[NB][V], acc[V];
@@ -336,6 +338,82 @@ normalized_soa_regs(const T *__restrict__ x, int64_t ldx, int64_t n, const Weigh
             else if (nrm[l] > (T)1e-14) v[k][l] = mul_rn(v[k][l], inv[l]);
         }
         stg_stream(out + (int64_t)k * ldo + r0, v[k]);
+    }
+}
+
+// SoA `normalized` on TMA-staged tiles: the (NB blades x kRows rows) tile arrives through cp.async.bulk.tensor, a thread
+// owns V consecutive rows (one 16-byte shared-memory access per blade), scales them in place and the tile leaves through a
+// TMA store.  Same arithmetic as normalized_soa_regs; the register kernel is bound by the latency of its own loads
+// (long-scoreboard stalls, DRAM 70 % busy), here the copy engine keeps whole tiles in flight.
+template <class T, int NB> struct NormTile {
+    static constexpr int V = VecW<T>::value;
+    static constexpr int kRowsRaw = 32768 / (NB * (int)sizeof(T));
+    static constexpr int kRows = kRowsRaw > 1024 ? 1024 : (kRowsRaw < 32 * V ? 32 * V : kRowsRaw);
+    static constexpr int kBoxRows = kRows > 256 ? 256 : kRows;   // TMA boxes are at most 256 elements wide
+    static constexpr int kBoxes = kRows / kBoxRows;
+    static constexpr int kBoxBytes = kBoxRows * NB * (int)sizeof(T);
+    static constexpr int kBytes = kRows * NB * (int)sizeof(T);
+    static constexpr int kThreadsTile = kRows / V;
+    static __device__ __forceinline__ size_t offset(int k, int r) {
+        return ((size_t)(r / kBoxRows) * NB * kBoxRows + (size_t)k * kBoxRows + (r % kBoxRows)) * sizeof(T);
+    }
+};
+
+template <class T, bool STRICT, int NB>
+__global__ void __launch_bounds__(NormTile<T, NB>::kThreadsTile)
+normalized_soa_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_out, const Weights wt) {
+    using NT = NormTile<T, NB>;
+    constexpr int V = NT::V;
+    struct alignas(16) RowVec { T v[V]; };
+    extern __shared__ uint8_t nt_smem_raw[];
+    uint8_t *tile = (uint8_t *)(((uintptr_t)nt_smem_raw + 127) & ~(uintptr_t)127);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(tile + NT::kBytes);
+    const int t = threadIdx.x, row0 = blockIdx.x * NT::kRows;
+    if (t == 0) {
+        tma::mbar_init(bar, 1);
+        tma::mbar_expect_tx(bar, (uint32_t)NT::kBytes);
+#pragma unroll
+        for (int box = 0; box < NT::kBoxes; ++box) tma::load_2d(tile + box * NT::kBoxBytes, &map_x, bar, row0 + box * NT::kBoxRows, 0);
+    }
+    __syncthreads();
+    tma::mbar_wait(bar, 0);
+    T v[NB][V], acc[V];
+#pragma unroll
+    for (int l = 0; l < V; ++l) acc[l] = T(0);
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        const RowVec c = *reinterpret_cast<const RowVec *>(tile + NT::offset(k, t * V));
+        const int w = wt.w[k];
+#pragma unroll
+        for (int l = 0; l < V; ++l) {
+            v[k][l] = c.v[l];
+            if (w != 0) acc[l] = Arith<STRICT>::madd(w > 0 ? v[k][l] : -v[k][l], v[k][l], acc[l]);
+        }
+    }
+    T nrm[V], inv[V];
+#pragma unroll
+    for (int l = 0; l < V; ++l) {
+        nrm[l] = sqrt_rn(acc[l] < T(0) ? -acc[l] : acc[l]);
+        inv[l] = nrm[l] > (T)1e-14 ? div_rn(T(1), nrm[l]) : T(1);
+    }
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        RowVec c;
+#pragma unroll
+        for (int l = 0; l < V; ++l) {
+            T e = v[k][l];
+            if (STRICT) e = nrm[l] > (T)1e-14 ? div_rn(e, nrm[l]) : e;
+            else if (nrm[l] > (T)1e-14) e = mul_rn(e, inv[l]);
+            c.v[l] = e;
+        }
+        *reinterpret_cast<RowVec *>(tile + NT::offset(k, t * V)) = c;
+    }
+    tma::fence_proxy_async();
+    __syncthreads();
+    if (t == 0) {
+#pragma unroll
+        for (int box = 0; box < NT::kBoxes; ++box) tma::store_2d(&map_out, tile + box * NT::kBoxBytes, row0 + box * NT::kBoxRows, 0);
+        tma::store_commit_and_wait_read();
     }
 }
 
@@ -583,6 +661,70 @@ transpose_tma_kernel(const __grid_constant__ CUtensorMap map_aos, const __grid_c
     }
 }
 
+// K4 on TMA-staged AoS tiles (rows of 32-256 bytes, from 4096 rows on): the tile of kRows consecutive rows is one
+// contiguous span of HBM, a thread owns ONE row -- it reads it from the swizzled tile in 16-byte chunks, adds the weighted
+// squares in ascending blade order (the reference's order, batch.rs:685-711, so the strict mode is bit-exact without any
+// lane chain), takes one square root, and for `normalized` scales the row in place before the tile leaves through a TMA
+// store.  No shuffles and one square root per row: the lane-group kernel above spends 71 % of its issue slots on them.
+template <class T, int NB, bool STRICT>
+__global__ void __launch_bounds__(TransposeTile<NB * (int)sizeof(T)>::kRows)
+norm_aos_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_out, const Weights wt, int mode,
+             T *__restrict__ norms, int64_t n) {
+    using TT = TransposeTile<NB * (int)sizeof(T)>;
+    constexpr int W = VecW<T>::value;
+    struct alignas(16) Chunk { T v[W]; };
+    extern __shared__ uint8_t na_smem_raw[];
+    uint8_t *tile = (uint8_t *)(((uintptr_t)na_smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(tile + TT::kBytes);
+    const int t = threadIdx.x, row0 = blockIdx.x * TT::kRows;
+    if (t == 0) {
+        tma::mbar_init(bar, 1);
+        tma::mbar_expect_tx(bar, (uint32_t)TT::kBytes);
+#pragma unroll
+        for (int sub = 0; sub < TT::kSub; ++sub)
+            tma::load_2d(tile + sub * TT::kRows * TT::kSpan, &map_x, bar, sub * (TT::kSpan / (int)sizeof(T)), row0);
+    }
+    __syncthreads();
+    tma::mbar_wait(bar, 0);
+    T v[NB];
+#pragma unroll
+    for (int j = 0; j < NB / W; ++j) {
+        const Chunk c = *reinterpret_cast<const Chunk *>(tile + TT::chunk_offset(t, j));
+#pragma unroll
+        for (int l = 0; l < W; ++l) v[j * W + l] = c.v[l];
+    }
+    T acc = T(0);
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        const int w = wt.w[k];
+        if (w != 0) acc = Arith<STRICT>::madd(w > 0 ? v[k] : -v[k], v[k], acc);
+    }
+    const int64_t row = (int64_t)row0 + t;
+    if (mode == 0) { if (row < n) norms[row] = acc; return; }
+    const T nrm = sqrt_rn(acc < T(0) ? -acc : acc);
+    if (mode == 1) { if (row < n) norms[row] = nrm; return; }
+    if (nrm > (T)1e-14) {  // batch.rs:805-811
+        const T inv = STRICT ? T(1) : div_rn(T(1), nrm);
+#pragma unroll
+        for (int k = 0; k < NB; ++k) v[k] = STRICT ? div_rn(v[k], nrm) : mul_rn(v[k], inv);
+    }
+#pragma unroll
+    for (int j = 0; j < NB / W; ++j) {
+        Chunk c;
+#pragma unroll
+        for (int l = 0; l < W; ++l) c.v[l] = v[j * W + l];
+        *reinterpret_cast<Chunk *>(tile + TT::chunk_offset(t, j)) = c;
+    }
+    tma::fence_proxy_async();
+    __syncthreads();
+    if (t == 0) {
+#pragma unroll
+        for (int sub = 0; sub < TT::kSub; ++sub)
+            tma::store_2d(&map_out, tile + sub * TT::kRows * TT::kSpan, sub * (TT::kSpan / (int)sizeof(T)), row0);
+        tma::store_commit_and_wait_read();
+    }
+}
+
 // ------------------------------------------------------------------------------------------ column movers
 struct ColumnMap { int16_t col_of_blade[256]; };  // -1: blade stays zero
 
@@ -779,6 +921,56 @@ cudaError_t launch_addsub(int nb, int op, const ViewArg &a, bool a_bc, const Vie
     return by_dtype(out.dtype, [&] { run(float()); }, [&] { run(double()); });
 }
 
+template <class T, int NB> static bool launch_norm_aos_tma_nb(int mode, bool strict, const ViewArg &x, const Weights &wt, void *norms, const ViewArg &out, cudaStream_t s) {
+    using TT = TransposeTile<NB * (int)sizeof(T)>;
+    CUtensorMap mx, mo;
+    if (!make_aos_tensor_map(&mx, x.data, (int)sizeof(T), NB, x.ld, x.n, TT::kSpan, TT::kRows)) return false;
+    mo = mx;
+    if (mode == 2 && !make_aos_tensor_map(&mo, out.data, (int)sizeof(T), NB, out.ld, x.n, TT::kSpan, TT::kRows)) return false;
+    constexpr int smem = TT::kBytes + 1024 + 16;
+    const unsigned grid = (unsigned)((x.n + TT::kRows - 1) / TT::kRows);
+    auto go = [&](auto kernel) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return false;
+        kernel<<<grid, TT::kRows, smem, s>>>(mx, mo, wt, mode, (T *)norms, x.n);
+        return true;
+    };
+    return strict ? go(norm_aos_tma<T, NB, true>) : go(norm_aos_tma<T, NB, false>);
+}
+// false: the view does not qualify (row size, alignment, batch size) -- the lane-group / scalar kernels take it
+template <class T> static bool launch_norm_aos_tma(int nb, int mode, bool strict, const ViewArg &x, const Weights &wt, void *norms, const ViewArg &out, cudaStream_t s) {
+    static const bool on = [] { const char *e = std::getenv("LCC_NORM_AOS_TMA"); return !(e && e[0] == '0'); }();
+    if (!on || x.n < 4096) return false;
+    switch (nb * (int)sizeof(T)) {
+        case 32: return launch_norm_aos_tma_nb<T, 32 / (int)sizeof(T)>(mode, strict, x, wt, norms, out, s);
+        case 64: return launch_norm_aos_tma_nb<T, 64 / (int)sizeof(T)>(mode, strict, x, wt, norms, out, s);
+        case 128: return launch_norm_aos_tma_nb<T, 128 / (int)sizeof(T)>(mode, strict, x, wt, norms, out, s);
+        case 256: return launch_norm_aos_tma_nb<T, 256 / (int)sizeof(T)>(mode, strict, x, wt, norms, out, s);
+    }
+    return false;
+}
+
+// SoA `normalized` (LCC_NORMALIZED_MODE): 2 = TMA tiles from 65536 rows on, thin register kernel below (default);
+// 1 = register kernel with 8-byte accesses; 0 = with 16-byte accesses.  2^26 PGA f32 / 2^24 CGA f64 / 2^26 R3 f64 rows:
+// mode 0 5891 / 6633 / 5736 GB/s, mode 1 6015 / 6638 / 6758, mode 2 6838 / 6794 / 6901 (profiles/r01_normalized_modes.txt).
+static int normalized_mode() {
+    static const int m = [] { const char *e = std::getenv("LCC_NORMALIZED_MODE"); return e ? std::atoi(e) : LCC_NORMALIZED_MODE_DEFAULT; }();
+    return m;
+}
+template <class T, int NB> static bool launch_normalized_tma(const ViewArg &x, const ViewArg &out, const Weights &wt, bool strict, cudaStream_t s) {
+    using NT = NormTile<T, NB>;
+    CUtensorMap mx, mo;
+    if (!make_soa_tensor_map(&mx, x.data, (int)sizeof(T), NB, x.ld, x.n, NT::kBoxRows)) return false;
+    if (!make_soa_tensor_map(&mo, out.data, (int)sizeof(T), NB, out.ld, x.n, NT::kBoxRows)) return false;
+    constexpr int smem = NT::kBytes + 128 + 16;
+    const unsigned grid = (unsigned)((x.n + NT::kRows - 1) / NT::kRows);
+    auto go = [&](auto kernel) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return false;
+        kernel<<<grid, NT::kThreadsTile, smem, s>>>(mx, mo, wt);
+        return true;
+    };
+    return strict ? go(normalized_soa_tma<T, true, NB>) : go(normalized_soa_tma<T, false, NB>);
+}
+
 cudaError_t launch_norm(int nb, int mode, bool strict, const ViewArg &x, const int8_t *weights, void *norms, const ViewArg &out, cudaStream_t s) {
     const int64_t n = x.n;
     if (n <= 0) return cudaSuccess;
@@ -788,6 +980,7 @@ cudaError_t launch_norm(int nb, int mode, bool strict, const ViewArg &x, const i
         using T = decltype(tag);
         const unsigned g = blocks_for(n);
         constexpr int W = VecW<T>::value;
+        if (x.layout == kAoS && launch_norm_aos_tma<T>(nb, mode, strict, x, wt, norms, out, s)) return;
         // strict norms (no output row to write) stay on the row-per-thread kernel: the bit-exact lane chain is
         // latency-bound and only pays off when it saves the second pass of `normalized`
         if (x.layout == kAoS && nb / W <= 32 && aos_vec_ok(x, nb, W) && (mode != 2 || aos_vec_ok(out, nb, W)) && !(strict && mode != 2)) {
@@ -801,14 +994,23 @@ cudaError_t launch_norm(int nb, int mode, bool strict, const ViewArg &x, const i
             ((uintptr_t)out.data & 15) == 0 && x.ld % W == 0 && out.ld % W == 0) {
 #define LCC_NORMALIZED_CASE(NBV)                                                                                                  \
     case NBV: {                                                                                                                   \
-        constexpr int V = NBV >= 32 ? 1 : (NBV >= 16 && sizeof(T) == 8 ? 1 : W);                                                  \
+        if (normalized_mode() == 2 && n >= 65536 && launch_normalized_tma<T, NBV>(x, out, wt, strict, s)) return;               \
         /* 64-thread blocks: the row lives in 64-130 registers, so 256-thread blocks fit twice per SM and move through  \
          * load / compute / store in lock step (5.3 TB/s); small blocks interleave their phases, as in K1 / K2 */         \
         constexpr int kBlock = 64;                                                                                                \
+        constexpr int VW = NBV >= 32 ? 1 : (NBV >= 16 && sizeof(T) == 8 ? 1 : W);                                                 \
+        constexpr int V8 = 8 / (int)sizeof(T) < VW ? 8 / (int)sizeof(T) : VW;  /* mode 1: 8-byte accesses, thinner threads */   \
+        if (normalized_mode() >= 1 && n % V8 == 0) {                                                                              \
+            const unsigned gr = blocks_for((n + V8 - 1) / V8, kBlock);                                                            \
+            if (strict) normalized_soa_regs<T, true, NBV, V8><<<gr, kBlock, 0, s>>>((const T *)x.data, x.ld, n, wt, (T *)out.data, out.ld); \
+            else normalized_soa_regs<T, false, NBV, V8><<<gr, kBlock, 0, s>>>((const T *)x.data, x.ld, n, wt, (T *)out.data, out.ld);   \
+            return;                                                                                                               \
+        }                                                                                                                         \
+        constexpr int V = VW;                                                                                                     \
         const unsigned gr = blocks_for((n + V - 1) / V, kBlock);                                                                  \
         if (n % V != 0) break; /* padded rows are addressable (ld >= n rounded up), but keep the tail on the generic kernel */  \
-        if (strict) normalized_soa_regs<T, true, NBV><<<gr, kBlock, 0, s>>>((const T *)x.data, x.ld, n, wt, (T *)out.data, out.ld); \
-        else normalized_soa_regs<T, false, NBV><<<gr, kBlock, 0, s>>>((const T *)x.data, x.ld, n, wt, (T *)out.data, out.ld);   \
+        if (strict) normalized_soa_regs<T, true, NBV, V><<<gr, kBlock, 0, s>>>((const T *)x.data, x.ld, n, wt, (T *)out.data, out.ld); \
+        else normalized_soa_regs<T, false, NBV, V><<<gr, kBlock, 0, s>>>((const T *)x.data, x.ld, n, wt, (T *)out.data, out.ld);   \
         return;                                                                                                                   \
     }
             switch (nb) {

@@ -660,7 +660,7 @@ def test_unary_norm_sum_on_aos_views(L, sig, dt):
     rng = np.random.default_rng(41)
     S = cabi.LCC_FLAG_STRICT_FP
     dev = _Dev(lib)
-    for n, pad in ((1, 0), (37, 0), (1000, 0), (513, 1)):
+    for n, pad in ((1, 0), (37, 0), (1000, 0), (513, 1), (5003, 0)):  # from 4096 rows on: the TMA-tiled norm kernels (rows of 32-256 bytes)
         ld = nb + pad
         a, b = rand(rng, n, nb, dt), rand(rng, n, nb, dt)
         a[n // 2] = 0.0  # a zero row: normalized leaves it unchanged (batch.rs:805-811)
@@ -727,7 +727,7 @@ def test_normalized_soa_register_kernel(L, strict, sig, dt):
     that are whole vectors, the generic kernel for the rest; both bit-exact in strict mode."""
     alg, o = algebras(L, sig)
     rng = np.random.default_rng(43)
-    for n in (4, 64, 1000, 1001, 4096):
+    for n in (4, 64, 1000, 1001, 4096, 70_000, 65_537):  # from 65536 rows on the TMA-tiled form may run (whole 16-byte row counts)
         a = rand(rng, n, o.num_blades, dt)
         a[0] = 0.0
         assert np.array_equal(L.MultivectorBatch.from_numpy(alg, a).normalized().to_numpy(), o.normalized(a))
