@@ -76,7 +76,7 @@ def main(cases):
         nb = o.num_blades
         dt = np.float64 if rng.random() < 0.5 else np.float32
         layout = cabi.LCC_AOS if rng.random() < 0.5 else cabi.LCC_SOA
-        n = int(rng.choice([1, 2, 3, 31, 64, 65, 255, 1000, 4096, 4097, 6000, 20011, 70001]))
+        n = int(rng.choice([1, 2, 3, 31, 64, 65, 255, 1000, 4096, 4097, 6000, 20011, 70000, 70001, 131072]))
         cabi.check(lib.lcc_set_option(b"aos_tma_min_rows", int(rng.choice([0, 128, 4096, 1 << 40]))))
         cabi.check(lib.lcc_set_option(b"soa_tma_min_bytes", int(rng.choice([0, 1 << 20, 1 << 40]))))
         a = rng.standard_normal((n, nb)).astype(dt)
@@ -85,7 +85,7 @@ def main(cases):
         a_used, b_used = (a[:1] if bc == 1 else a), (b[:1] if bc == 2 else b)
         A, B = Operand(a_used, layout, dt), Operand(b_used, layout, dt)
         out, out2 = Operand(np.zeros((n, nb), dt), layout, dt), Operand(np.zeros((n, nb), dt), layout, dt)
-        kind = rng.integers(6)
+        kind = rng.integers(7)
         label = f"case {case}: sig {sig} {np.dtype(dt).name} layout {layout} n {n} bc {bc} kind {kind}"
         try:
             if kind == 0:
@@ -125,6 +125,19 @@ def main(cases):
                 cabi.check(lib.lcc_batch_norm(alg.h, cabi.LCC_NORM_SQUARED, C.byref(A.view), pn, S, None))
                 assert np.array_equal(dev_get(pn, norms), o.norm_squared(a)), label
                 cabi.check(lib.lcc_device_free(pn, None))
+            elif kind == 6 and bc == 0:  # layout conversion both ways (TMA transpose from 4096 rows on, scalar tail and fallbacks)
+                other = Operand(np.zeros((n, nb), dt), cabi.LCC_SOA if layout == cabi.LCC_AOS else cabi.LCC_AOS, dt)
+                cabi.check(lib.lcc_batch_convert(alg.h, C.byref(A.view), C.byref(other.view), None))
+                assert np.array_equal(other.read(), a), label + " (convert)"
+                cabi.check(lib.lcc_batch_convert(alg.h, C.byref(other.view), C.byref(out.view), None))
+                assert np.array_equal(out.read(), a), label + " (convert back)"
+                sums = np.zeros(nb, dt)
+                ps = dev_put(sums)
+                cabi.check(lib.lcc_batch_sum(alg.h, C.byref(A.view), ps, None))
+                want, mag = o.sum(a)
+                assert np.all(np.abs(dev_get(ps, sums) - want) <= (1e-12 if dt == np.float64 else 2e-6) * np.maximum(mag, 1.0)), label + " (sum)"
+                cabi.check(lib.lcc_device_free(ps, None))
+                other.free()
             else:
                 continue
             assert np.array_equal(A.read(), a_used) and np.array_equal(B.read(), b_used), label + " (inputs modified)"
