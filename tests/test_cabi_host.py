@@ -147,6 +147,18 @@ def test_batched_calls_refuse_to_run_without_a_gpu():
         L.MultivectorBatch.from_numpy(L.Algebra.euclidean(3), np.zeros((4, 8)))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         L.Multivector.from_vector([1.0, 0.0, 0.0]).geometric_product(L.Multivector.from_vector([0.0, 1.0, 0.0]))
+    # the host-buffer entry points validate their arguments first and then fail the same way (no host arithmetic anywhere)
+    lib = cabi.lib()
+    xyz, motor = np.zeros((8, 3), np.float32), np.zeros(16)
+    motor[0] = 1.0
+    mptr = motor.ctypes.data_as(C.POINTER(C.c_double))
+    assert lib.lcc_host_pga_points_sandwich(cabi.Algebra(3, 0, 0).h, cabi.LCC_F32, mptr, xyz.ctypes.data, xyz.ctypes.data, 8, 0) == cabi.LCC_ERR_VALUE
+    assert b"PGA3D" in lib.lcc_last_error()
+    assert lib.lcc_host_pga_points_sandwich(cabi.Algebra(3, 0, 1).h, cabi.LCC_F32, mptr, xyz.ctypes.data, xyz.ctypes.data, 0, 0) == cabi.LCC_OK
+    assert lib.lcc_host_pga_points_sandwich(cabi.Algebra(3, 0, 1).h, cabi.LCC_F32, mptr, xyz.ctypes.data, xyz.ctypes.data, 8, 0) == cabi.LCC_ERR_NO_DEVICE
+    assert b"no CPU fallback" in lib.lcc_last_error()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        L.pga_transform_points(L.Algebra.pga(3), L.Multivector.from_scalar(1.0, 4), np.zeros((4, 3)))
 
 
 def test_bench_reference_arm_prints_the_contract_line():
