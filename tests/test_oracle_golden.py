@@ -197,3 +197,103 @@ def test_threads_do_not_change_results():
     assert np.array_equal(alg.geometric_product(a, b, threads=1), alg.geometric_product(a, b, threads=4))
     r = rng.standard_normal(32)
     assert np.array_equal(alg.sandwich(r, a, threads=1), alg.sandwich(r, a, threads=3))
+
+
+# ----------------------------------------------------------------------------------------------- CGA / STA known answers
+def _cga_point(x, y, z):
+    """Multivector::cga_point, src/cga.rs:171-205: x e1 + y e2 + z e3 + (|x|^2/2 - 1/2) e+ + (|x|^2/2 + 1/2) e-,
+    e+ = blade 8, e- = blade 16 (cga.rs:45-53)."""
+    c = np.zeros(32)
+    c[1], c[2], c[4] = x, y, z
+    n2 = x * x + y * y + z * z
+    c[8], c[16] = 0.5 * n2 - 0.5, 0.5 * n2 + 0.5
+    return c
+
+
+def test_cga_kats():
+    """Known answers of the reference's tests/test_cga.py (35-61 null basis, 249-319 incidence and distances) and
+    src/cga.rs:734-851, evaluated with the oracle's products on the reference's coefficient layouts."""
+    o = oracle.OracleAlgebra(4, 1, 0)
+    gp = lambda a, b: o.geometric_product(a[None, :], b[None, :])[0]  # noqa: E731
+    dot = lambda a, b: gp(a, b)[0]  # noqa: E731  (two vectors: the scalar part of the product is their inner product)
+    eo, einf = np.zeros(32), np.zeros(32)
+    eo[8], eo[16] = -0.5, 0.5      # e_o = (e- - e+) / 2, cga.rs:92-97
+    einf[8], einf[16] = 1.0, 1.0   # e_inf = e- + e+, cga.rs:135-140
+    assert dot(eo, eo) == 0.0 and dot(einf, einf) == 0.0 and dot(eo, einf) == -1.0
+    assert np.array_equal(_cga_point(0.0, 0.0, 0.0), eo)
+    for p in ((1.0, 2.0, 3.0), (-0.5, 4.0, 0.25), (3.0, 4.0, 0.0)):
+        assert abs(dot(_cga_point(*p), _cga_point(*p))) < 1e-12            # conformal points are null
+        assert abs(dot(_cga_point(*p), einf) + 1.0) < 1e-12                # normalised: P . e_inf = -1
+    dist = lambda p, q: np.sqrt(-2.0 * dot(_cga_point(*p), _cga_point(*q)))  # noqa: E731  (cga_distance, cga.rs)
+    assert abs(dist((0.0, 0.0, 0.0), (3.0, 4.0, 0.0)) - 5.0) < 1e-10       # test_cga.py:283-290
+    assert abs(dist((1.0, 2.0, 3.0), (4.0, 6.0, 3.0)) - 5.0) < 1e-10       # :292-300
+    assert abs(dist((1.0, 2.0, 3.0), (4.0, 5.0, 6.0)) - dist((4.0, 5.0, 6.0), (1.0, 2.0, 3.0))) < 1e-12
+    sphere = _cga_point(0.0, 0.0, 0.0) - 0.5 * einf                        # unit sphere, cga.rs:294-309 (S = P - r^2/2 e_inf)
+    assert abs(dot(_cga_point(1.0, 0.0, 0.0), sphere)) < 1e-12 and abs(dot(_cga_point(0.0, 1.0, 0.0), sphere)) < 1e-12
+    assert dot(_cga_point(0.5, 0.0, 0.0), sphere) > 1e-3 and dot(_cga_point(2.0, 0.0, 0.0), sphere) < -1e-3
+    # a batch of points against one sphere through the broadcast rule of batch.rs:361-376: P . S = (r^2 - |p - c|^2) / 2
+    rng = np.random.default_rng(5)
+    pts = rng.standard_normal((257, 3))
+    P = np.stack([_cga_point(*p) for p in pts])
+    S = (_cga_point(1.0, 2.0, 3.0) - 0.5 * 25.0 * einf)[None, :]
+    got = o.geometric_product(P, S)[:, 0]
+    want = 0.5 * (25.0 - ((pts - np.array([1.0, 2.0, 3.0])) ** 2).sum(axis=1))
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
+
+
+def test_sta_kats():
+    """Known answers of the reference's tests/test_sta.py (54-160 metric, anticommutation, pseudoscalar; 189-436
+    intervals, boosts, rotations, field bivectors) and src/sta.rs:675-934 with the oracle's products, sandwich and
+    the row-wise boost / bivector constructors.  gamma_mu = blades 1, 2, 4, 8 (sta.rs:34-37)."""
+    o = oracle.OracleAlgebra(1, 3, 0)
+    gp = lambda a, b: o.geometric_product(a[None, :], b[None, :])[0]  # noqa: E731
+    g = [np.eye(16)[i] for i in (1, 2, 4, 8)]
+    eta = np.diag([1.0, -1.0, -1.0, -1.0])
+    for mu in range(4):
+        for nu in range(4):
+            anti = gp(g[mu], g[nu]) + gp(g[nu], g[mu])
+            assert anti[0] == 2.0 * eta[mu, nu] and not anti[1:].any()       # {gamma_mu, gamma_nu} = 2 eta, test_sta.py:109-127
+    I = gp(gp(g[0], g[1]), gp(g[2], g[3]))
+    assert I[15] == 1.0 and np.count_nonzero(I) == 1 and gp(I, I)[0] == -1.0  # test_sta.py:133-141
+
+    def vec(t, x, y, z):  # sta_vector, sta.rs:105-109
+        c = np.zeros(16)
+        c[1], c[2], c[4], c[8] = t, x, y, z
+        return c
+
+    interval = lambda v: gp(v, v)[0]  # noqa: E731
+    assert interval(vec(5.0, 3.0, 0.0, 0.0)) == 16.0 and interval(vec(1.0, 5.0, 0.0, 0.0)) == -24.0   # test_sta.py:190-213
+    assert interval(vec(1.0, 1.0, 0.0, 0.0)) == 0.0 and abs(interval(vec(np.sqrt(3.0), 1.0, 1.0, 1.0))) < 1e-15
+    # boosts (sta.rs:253-296): gamma = 2 s^2 - 1 (sta.rs:641-653), intervals are preserved by R x ~R
+    R = oracle.sta_boosts(np.array([[0.6, 0.0, 0.0], [0.8, 0.0, 0.0], [0.0, 0.6, 0.0], [0.0, 0.0, 0.0], [0.5, 0.0, 0.0]]))
+    np.testing.assert_allclose(2.0 * R[:4, 0] ** 2 - 1.0, [1.25, 5.0 / 3.0, 1.25, 1.0], rtol=1e-14)    # test_sta.py:247-291
+    assert np.array_equal(R[3], np.eye(16)[0])
+    x = vec(5.0, 3.0, 0.0, 0.0)
+    xb = o.sandwich(R[4], x[None, :])[0]
+    assert abs(interval(xb) - 16.0) < 1e-12                                                             # test_sta.py:230-245
+    np.testing.assert_allclose(np.delete(xb, [1, 2, 4, 8]), 0.0, atol=1e-14)                           # stays a vector
+    # a boost of the rest observer gamma_0 by v has time component gamma(v)
+    np.testing.assert_allclose(o.sandwich(R[0], g[0][None, :])[0][1], 1.25, rtol=1e-14)
+    # composition of two collinear boosts: rapidities add, so gamma grows (test_sta.py:262-271); (0.3 + 0.3)/(1 + 0.09)
+    R1 = oracle.sta_boosts(np.array([[0.3, 0.0, 0.0]]))[0]
+    R12 = gp(R1, R1)
+    v12 = 0.6 / 1.09
+    np.testing.assert_allclose(2.0 * R12[0] ** 2 - 1.0, 1.0 / np.sqrt(1.0 - v12 * v12), rtol=1e-13)
+    # spatial rotations (sta.rs:329-376): R = cos(a/2) + sin(a/2) (nx g23 - ny g13 + nz g12), blades 12, 10, 6
+    def rotation(axis, angle):
+        n = np.asarray(axis, float) / np.linalg.norm(axis)
+        c = np.zeros(16)
+        c[0], c[12], c[10], c[6] = np.cos(angle / 2), np.sin(angle / 2) * n[0], -np.sin(angle / 2) * n[1], np.sin(angle / 2) * n[2]
+        return c
+    xr = o.sandwich(rotation([0.0, 0.0, 1.0], np.pi / 2), vec(0.0, 1.0, 0.0, 0.0)[None, :])[0]
+    np.testing.assert_allclose(xr[[1, 2, 4, 8]], [0.0, 0.0, 1.0, 0.0], atol=1e-15)                     # x -> y, test_sta.py:343-353
+    xr = o.sandwich(rotation([1.0, 0.0, 0.0], np.pi / 2), vec(0.0, 0.0, 1.0, 0.0)[None, :])[0]
+    np.testing.assert_allclose(xr[[1, 2, 4, 8]], [0.0, 0.0, 0.0, 1.0], atol=1e-15)                     # y -> z, :355-364
+    xr = o.sandwich(rotation([0.0, 0.0, 1.0], np.pi / 4), vec(5.0, 3.0, 4.0, 0.0)[None, :])[0]
+    assert abs(interval(xr) - 0.0) < 1e-12 and abs(xr[1] - 5.0) < 1e-14                                # interval and time are invariant
+    # field bivector F = E + I B (sta.rs:202-212): the two Lorentz invariants F^2 = (E^2 - B^2) + 2 (E.B) I
+    E, B = np.array([1.0, 2.0, 3.0]), np.array([0.5, -0.5, 1.0])
+    F = oracle.sta_bivectors(E[None, :], B[None, :])[0]
+    F2 = gp(F, F)
+    np.testing.assert_allclose([F2[0], F2[15]], [E @ E - B @ B, 2.0 * (E @ B)], rtol=1e-14)
+    np.testing.assert_allclose(np.delete(F2, [0, 15]), 0.0, atol=1e-15)
