@@ -186,7 +186,9 @@ LCC_API lcc_status lcc_batch_product_sum(const lcc_algebra *alg, int op, const l
  *   wrt = 0  grad_in[i] = sum_j sign[i][j] * grad_out[i^j] * other[j]   (other = the right operand b)
  *   wrt = 1  grad_in[j] = sum_i sign[i][j] * other[i] * grad_out[i^j]   (other = the left operand a)
  * restricted to the op's term set.  `other` may be a one-row batch (broadcast); the caller sums
- * grad_in over rows (lcc_batch_sum) when the differentiated operand itself was broadcast. */
+ * grad_in over rows (lcc_batch_sum) when the differentiated operand itself was broadcast.
+ * Cotangents have no reference rounding order: up to 32 blades they are always computed with FMA in
+ * ascending-term order and LCC_FLAG_STRICT_FP is ignored; above 32 blades the table kernel honours it. */
 LCC_API lcc_status lcc_batch_product_vjp(const lcc_algebra *alg, int op, int wrt, const lcc_view *grad_out,
                                          const lcc_view *other, const lcc_view *grad_in, unsigned flags, void *stream);
 /* out[row] = R * x[row] * ~R with one rotor/motor (host array of num_blades doubles) for the whole
@@ -237,12 +239,35 @@ LCC_API lcc_status lcc_pga_points_sandwich(const lcc_algebra *alg, int dtype, co
  * scalar API) come back as NaN. */
 LCC_API lcc_status lcc_sta_bivectors_embed(const lcc_algebra *alg, const void *eb, const lcc_view *dst, void *stream);
 LCC_API lcc_status lcc_sta_boosts_embed(const lcc_algebra *alg, const void *velocity, const lcc_view *dst, void *stream);
+/* ---------------------------------------------------------------- host <-> device (from_numpy / to_numpy) */
+
+/* from_numpy / to_numpy, src/batch.rs:79-94,233-235: copy a HOST array in the reference's (n, num_blades) row-major
+ * layout into / out of a device batch of the same dtype (any layout; rows must match).  The copy is chunked and
+ * pipelined: pinned host memory (lcc_host_alloc_pinned, lcc_host_cache_alloc, cudaHostRegister'ed arrays -- detected,
+ * not declared) is DMA'd directly, pageable memory goes through a ring of pinned bounce slots filled by a small pool of
+ * host threads; the layout transpose of chunk c runs while chunk c+1 crosses PCIe, and the only extra device memory is
+ * two chunk-sized staging buffers per device (option "host_chunk_bytes", default 64 MiB).
+ * lcc_batch_upload returns when the host array has been read completely (it may be reused); the batch itself is
+ * complete in `stream` order.  lcc_batch_download returns when `host` holds the whole batch. */
+LCC_API lcc_status lcc_batch_upload(const lcc_algebra *alg, const void *host, int64_t n, const lcc_view *dst, void *stream);
+LCC_API lcc_status lcc_batch_download(const lcc_algebra *alg, const lcc_view *src, void *host, void *stream);
+/* Cache of pinned host blocks: what to_numpy() hands out for results of at least "pinned_output_min_bytes" (default
+ * 1 MiB), so that repeated exports pay neither cudaHostAlloc nor first-touch page faults.  Freed blocks stay cached up
+ * to LCC_PINNED_CACHE_MAX_BYTES (default: a quarter of the box's RAM); lcc_host_cache_trim releases the idle ones. */
+LCC_API lcc_status lcc_host_cache_alloc(void **ptr, size_t bytes);
+LCC_API lcc_status lcc_host_cache_free(void *ptr);
+LCC_API lcc_status lcc_host_cache_trim(void);
+LCC_API lcc_status lcc_host_cache_stats(size_t *live_bytes, size_t *idle_bytes);
+LCC_API int lcc_host_is_pinned(const void *ptr, size_t bytes); /* 1 when the DMA engines can address the range directly */
+
 /* ---------------------------------------------------------------- host-buffer (end-to-end) entry points */
 
 /* Same operations with HOST buffers in the reference's (n, num_blades) row-major layout: the
  * library chunks the batch, overlaps H2D copy / kernel / D2H copy on three streams and returns
- * when `out` is complete.  Pinned buffers (lcc_host_alloc_pinned) run at PCIe speed; pageable
- * ones work but are staged by the driver.  These are what from_numpy -> op -> to_numpy costs. */
+ * when `out` is complete.  Pinned buffers (lcc_host_alloc_pinned) run at PCIe speed in both directions at once;
+ * pageable ones are staged through the same pinned bounce rings as lcc_batch_upload / download.  Unlike the
+ * three-call sequence from_numpy -> op -> to_numpy, whose upload and download cannot overlap (each call must
+ * finish before the next starts), these keep both PCIe directions busy at the same time. */
 LCC_API lcc_status lcc_host_sandwich(const lcc_algebra *alg, int dtype, const double *rotor, const void *x_host,
                                      void *out_host, int64_t n, unsigned flags);
 LCC_API lcc_status lcc_host_product(const lcc_algebra *alg, int dtype, int op, const void *a_host, int64_t na,
@@ -259,6 +284,9 @@ LCC_API lcc_status lcc_host_pga_points_sandwich(const lcc_algebra *alg, int dtyp
  *   "aos_tma_min_rows"   AoS batches with at least this many rows use the TMA-staged kernels (default 4096; rows
  *                        narrower than 128 bytes need 32x as many)
  *   "soa_tma_min_bytes"  SoA batches with at least this many bytes per operand do (default 8 GiB)
+ *   "host_chunk_bytes"   chunk size of the host <-> device pipelines (default 64 MiB)
+ *   "pinned_output_min_bytes"  to_numpy() results of at least this size come from the pinned host cache (default 1 MiB;
+ *                        a very large value switches the cache off)
  * Results do not depend on either: the staged and the direct-load kernels run the same arithmetic. */
 LCC_API lcc_status lcc_set_option(const char *name, int64_t value);
 LCC_API lcc_status lcc_get_option(const char *name, int64_t *value);

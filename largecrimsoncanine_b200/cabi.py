@@ -107,6 +107,13 @@ def lib():
         "lcc_pga_points_sandwich": (i32, [vp, i32, C.POINTER(dbl), vp, vp, i64, u32, vp]),
         "lcc_sta_bivectors_embed": (i32, [vp, vp, V, vp]),
         "lcc_sta_boosts_embed": (i32, [vp, vp, V, vp]),
+        "lcc_batch_upload": (i32, [vp, vp, i64, V, vp]),
+        "lcc_batch_download": (i32, [vp, V, vp, vp]),
+        "lcc_host_cache_alloc": (i32, [C.POINTER(vp), sz]),
+        "lcc_host_cache_free": (i32, [vp]),
+        "lcc_host_cache_trim": (i32, []),
+        "lcc_host_cache_stats": (i32, [C.POINTER(sz), C.POINTER(sz)]),
+        "lcc_host_is_pinned": (i32, [vp, sz]),
         "lcc_host_sandwich": (i32, [vp, i32, C.POINTER(dbl), vp, vp, i64, u32]),
         "lcc_host_product": (i32, [vp, i32, i32, vp, i64, vp, i64, vp, u32]),
         "lcc_host_pga_points_sandwich": (i32, [vp, i32, C.POINTER(dbl), vp, vp, i64, u32]),

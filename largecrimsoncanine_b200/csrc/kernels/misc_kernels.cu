@@ -1103,8 +1103,18 @@ cudaError_t launch_convert(int nb, const ViewArg &src, const ViewArg &dst, cudaS
     if (n <= 0) return cudaSuccess;
     const size_t es = src.dtype == kF32 ? 4 : 8;
     if (src.layout == dst.layout) {  // same layout, possibly different leading dimensions: strided copy
-        if (src.layout == kSoA)
-            return cudaMemcpy2DAsync(dst.data, dst.ld * es, src.data, src.ld * es, n * es, nb, cudaMemcpyDeviceToDevice, s);
+        if (src.layout == kSoA) {
+            // cudaMemcpy2DAsync rejects pitches above cudaDeviceProp::memPitch (2^31 - 1): a 2^28-row f64 batch has a
+            // 2 GiB pitch, so such batches are copied one blade row at a time (at most 256 plain copies)
+            if ((uint64_t)dst.ld * es <= 0x7fffffffull && (uint64_t)src.ld * es <= 0x7fffffffull)
+                return cudaMemcpy2DAsync(dst.data, dst.ld * es, src.data, src.ld * es, n * es, nb, cudaMemcpyDeviceToDevice, s);
+            for (int k = 0; k < nb; ++k) {
+                cudaError_t e = cudaMemcpyAsync((char *)dst.data + (size_t)k * dst.ld * es, (const char *)src.data + (size_t)k * src.ld * es,
+                                                (size_t)n * es, cudaMemcpyDeviceToDevice, s);
+                if (e != cudaSuccess) return e;
+            }
+            return cudaSuccess;
+        }
         return cudaMemcpy2DAsync(dst.data, dst.ld * es, src.data, src.ld * es, nb * es, n, cudaMemcpyDeviceToDevice, s);
     }
     // TMA stores clip at 16-byte granularity along the contiguous dimension, so the tiles take the rows up to the last

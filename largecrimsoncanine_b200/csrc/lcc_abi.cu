@@ -15,11 +15,11 @@
 
 #include <cuda_runtime.h>
 
-#include "../../include/lcc_b200.h"
-#include "algebra_host.hpp"
+#include <nvtx3/nvToolsExt.h>
+
+#include "abi_internal.hpp"
 #include "generated/cayley_tables.h"
 #include "kernels/launch_args.h"
-#include "kernels/misc_kernels.cuh"
 
 // ------------------------------------------------------------------ generated kernel registry
 namespace lcc {
@@ -119,50 +119,64 @@ void build_algebra(lcc_algebra &alg, int p, int q, int r) {
 
 using namespace lcc;
 
-// ------------------------------------------------------------------ errors
+// ------------------------------------------------------------------ errors, tracing
 static thread_local std::string t_error;
 
-static lcc_status fail(lcc_status code, const char *fmt, ...) {
+namespace lcc {
+namespace abi {
+lcc_status fail(lcc_status code, const char *fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
     t_error = buf;
+    if (log_enabled()) log_line("error %d: %s", (int)code, buf);
     return code;
 }
-static lcc_status cuda_fail(cudaError_t e, const char *what) {
+lcc_status cuda_fail(cudaError_t e, const char *what) {
     if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver)
         return fail(LCC_ERR_NO_DEVICE, "%s: no usable CUDA device (%s); batched operations have no CPU fallback",
                     what, cudaGetErrorString(e));
     return fail(LCC_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
 }
-#define LCC_CUDA(call)                                          \
-    do {                                                        \
-        cudaError_t e__ = (call);                               \
-        if (e__ != cudaSuccess) return cuda_fail(e__, #call);   \
-    } while (0)
-#define LCC_TRY(expr)                               \
-    do {                                            \
-        lcc_status s__ = (expr);                    \
-        if (s__ != LCC_OK) return s__;              \
-    } while (0)
-
-static std::string sig_str(const lcc_algebra *a) {
+std::string sig_str(const lcc_algebra *a) {
     char b[64];
     snprintf(b, sizeof b, "Cl(%d,%d,%d)", a->p, a->q, a->r);
     return b;
 }
+bool log_enabled() {
+    static const bool on = [] { const char *e = getenv("LCC_LOG"); return e && e[0] && e[0] != '0'; }();
+    return on;
+}
+void log_line(const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    fprintf(stderr, "[lcc] %s\n", buf);
+}
+static bool nvtx_enabled() {  // LCC_NVTX=0 switches the ranges off (they cost ~20 ns each without a profiler attached)
+    static const bool on = [] { const char *e = getenv("LCC_NVTX"); return !(e && e[0] == '0'); }();
+    return on;
+}
+TraceRange::TraceRange(const char *name) {
+    if (nvtx_enabled()) nvtxRangePushA(name);
+    if (log_enabled()) log_line("%s", name);
+}
+TraceRange::~TraceRange() {
+    if (nvtx_enabled()) nvtxRangePop();
+}
+}  // namespace abi
+}  // namespace lcc
+using namespace lcc::abi;
 
 // ------------------------------------------------------------------ device state
-namespace {
-struct DeviceState {
-    cudaStream_t stream = nullptr;  // compute
-    cudaStream_t copy_in = nullptr, copy_out = nullptr;
-    bool ready = false;
-};
-std::mutex g_dev_mutex;
-DeviceState g_devices[64];
+namespace lcc {
+namespace abi {
+static std::mutex g_dev_mutex;
+static DeviceState g_devices[64];
 
 lcc_status device_state(DeviceState **out) {
     int dev = 0;
@@ -171,6 +185,7 @@ lcc_status device_state(DeviceState **out) {
     std::lock_guard<std::mutex> lock(g_dev_mutex);
     DeviceState &st = g_devices[dev];
     if (!st.ready) {
+        st.device = dev;
         LCC_CUDA(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
         LCC_CUDA(cudaStreamCreateWithFlags(&st.copy_in, cudaStreamNonBlocking));
         LCC_CUDA(cudaStreamCreateWithFlags(&st.copy_out, cudaStreamNonBlocking));
@@ -192,9 +207,7 @@ lcc_status resolve_stream(void *stream, cudaStream_t *out) {
     return LCC_OK;
 }
 
-inline size_t elem_size(int dtype) { return dtype == LCC_F32 ? 4 : 8; }
-
-lcc_status check_view(const lcc_algebra *alg, const lcc_view *v, const char *name, bool allow_null_data = false) {
+lcc_status check_view(const lcc_algebra *alg, const lcc_view *v, const char *name, bool allow_null_data) {
     if (!alg) return fail(LCC_ERR_VALUE, "algebra handle is NULL");
     if (!v) return fail(LCC_ERR_VALUE, "%s: view is NULL", name);
     if (v->dtype != LCC_F32 && v->dtype != LCC_F64) return fail(LCC_ERR_VALUE, "%s: dtype must be LCC_F32 or LCC_F64", name);
@@ -212,8 +225,6 @@ lcc_status check_view(const lcc_algebra *alg, const lcc_view *v, const char *nam
     return LCC_OK;
 }
 
-ViewArg arg_of(const lcc_view *v) { return ViewArg{v->data, v->n, v->ld, v->dtype, v->layout}; }
-
 // batch.rs:361-376
 lcc_status broadcast_rows(int64_t na, int64_t nbr, int64_t *n) {
     if (na == nbr || nbr == 1) { *n = na; return LCC_OK; }
@@ -221,6 +232,11 @@ lcc_status broadcast_rows(int64_t na, int64_t nbr, int64_t *n) {
     return fail(LCC_ERR_VALUE, "batch sizes must match or be 1 for broadcasting: %lld vs %lld", (long long)na, (long long)nbr);
 }
 
+int64_t padded_ld(int64_t n) { return n <= 0 ? 64 : ((n + 63) / 64) * 64; }
+}  // namespace abi
+}  // namespace lcc
+
+namespace {
 lcc_status same_kind(const lcc_view *a, const lcc_view *b, const char *what) {
     if (a->dtype != b->dtype) return fail(LCC_ERR_VALUE, "%s: operands must share one dtype", what);
     if (a->layout != b->layout) return fail(LCC_ERR_VALUE, "%s: operands must share one layout", what);
@@ -265,20 +281,6 @@ lcc_status gather_signs_on_device(const lcc_algebra *calg, int kind, const int8_
     *out = d;
     return LCC_OK;
 }
-
-// RAII for stream-ordered temporaries
-struct PoolBuffer {
-    void *ptr = nullptr; cudaStream_t stream = nullptr;
-    ~PoolBuffer() { if (ptr) cudaFreeAsync(ptr, stream); }
-    lcc_status alloc(size_t bytes, cudaStream_t s) {
-        stream = s;
-        cudaError_t e = cudaMallocAsync(&ptr, bytes ? bytes : 16, s);
-        if (e != cudaSuccess) { ptr = nullptr; return cuda_fail(e, "cudaMallocAsync"); }
-        return LCC_OK;
-    }
-};
-
-int64_t padded_ld(int64_t n) { return n <= 0 ? 64 : ((n + 63) / 64) * 64; }
 
 lcc_status make_soa_temp(const lcc_algebra *alg, int dtype, int64_t n, PoolBuffer &buf, lcc_view *v, cudaStream_t s) {
     v->n = n; v->ld = padded_ld(n); v->dtype = dtype; v->layout = LCC_SOA;
@@ -410,6 +412,7 @@ lcc_status lcc_batch_free(lcc_view *view, void *stream) {
 
 // ================================================================== layout conversion / movers
 lcc_status lcc_batch_convert(const lcc_algebra *alg, const lcc_view *src, const lcc_view *dst, void *stream) {
+    TraceRange tr("lcc_batch_convert");
     LCC_TRY(check_view(alg, src, "src"));
     LCC_TRY(check_view(alg, dst, "dst"));
     if (src->dtype != dst->dtype) return fail(LCC_ERR_VALUE, "convert: dtype mismatch");
@@ -422,6 +425,7 @@ lcc_status lcc_batch_convert(const lcc_algebra *alg, const lcc_view *src, const 
 
 lcc_status lcc_batch_scatter_columns(const lcc_algebra *alg, const void *cols, int ncols, const int32_t *blade_of_col,
                                      const lcc_view *dst, void *stream) {
+    TraceRange tr("lcc_batch_scatter_columns");
     LCC_TRY(check_view(alg, dst, "dst"));
     if (ncols < 0 || ncols > alg->nb) return fail(LCC_ERR_VALUE, "scatter: bad column count %d", ncols);
     for (int c = 0; c < ncols; ++c)
@@ -434,6 +438,7 @@ lcc_status lcc_batch_scatter_columns(const lcc_algebra *alg, const void *cols, i
 
 lcc_status lcc_batch_gather_columns(const lcc_algebra *alg, const lcc_view *src, int ncols, const int32_t *blade_of_col,
                                     void *cols, void *stream) {
+    TraceRange tr("lcc_batch_gather_columns");
     LCC_TRY(check_view(alg, src, "src"));
     if (ncols < 0 || ncols > alg->nb) return fail(LCC_ERR_VALUE, "gather: bad column count %d", ncols);
     for (int c = 0; c < ncols; ++c)
@@ -446,10 +451,11 @@ lcc_status lcc_batch_gather_columns(const lcc_algebra *alg, const lcc_view *src,
 
 lcc_status lcc_batch_copy_rows(const lcc_algebra *alg, const lcc_view *src, int64_t start, int64_t end,
                                const lcc_view *dst, int64_t dst_start, void *stream) {
+    TraceRange tr("lcc_batch_copy_rows");
     LCC_TRY(check_view(alg, src, "src"));
     LCC_TRY(check_view(alg, dst, "dst"));
     if (src->dtype != dst->dtype) return fail(LCC_ERR_VALUE, "copy_rows: dtype mismatch");
-    if (start > src->n || end > src->n || start > end)  // batch.rs:1085-1090
+    if (start < 0 || end < 0 || start > src->n || end > src->n || start > end)  // batch.rs:1085-1090 (usize there: negatives cannot occur)
         return fail(LCC_ERR_INDEX, "invalid slice [%lld:%lld] for batch of size %lld", (long long)start, (long long)end, (long long)src->n);
     if (dst_start < 0 || dst_start + (end - start) > dst->n)
         return fail(LCC_ERR_INDEX, "index %lld out of bounds for batch of size %lld", (long long)dst_start, (long long)dst->n);
@@ -495,16 +501,17 @@ static lcc_status run_product(const lcc_algebra *alg, int op, const lcc_view *a,
     // 64..256 blades with ONE fixed operand (the broadcast branch, batch.rs:365-376), f32 SoA, FMA mode:
     // a GEMM against the operand's multiplication matrix on the tcgen05 tensor cores (K6, 3xTF32)
     static const bool tensor_path_off = [] { const char *e = getenv("LCC_DISABLE_TENSOR_PATH"); return e && e[0] == '1'; }();
+    // (the X tensor map covers rows in strips of 32: a pitch that is not a multiple of 32 would leave the last rows outside it)
     if (!tensor_path_off && op == kOpGP && !strict && a->dtype == LCC_F32 && a->layout == LCC_SOA && (a_bc != b_bc) &&
-        (alg->nb == 64 || alg->nb == 128 || alg->nb == 256)) {
+        (alg->nb == 64 || alg->nb == 128 || alg->nb == 256) && (a_bc ? b : a)->ld % 32 == 0 && out->ld % 4 == 0) {
         const int8_t *signs_dev = nullptr;
         LCC_TRY(gather_signs_on_device(alg, 48, &signs_dev));
         PoolBuffer w;
         LCC_TRY(w.alloc((size_t)2 * alg->nb * alg->nb * sizeof(float), s));
         const lcc_view *fixed = a_bc ? a : b, *batch = a_bc ? b : a;
-        LCC_CUDA(launch_fixed_product_tf32x3(alg->nb, a_bc ? 0 : 1, signs_dev, (const float *)fixed->data, fixed->ld,
-                                             arg_of(batch), arg_of(out), (float *)w.ptr, s));
-        return LCC_OK;
+        const cudaError_t e = launch_fixed_product_tf32x3(alg->nb, a_bc ? 0 : 1, signs_dev, (const float *)fixed->data, fixed->ld,
+                                                          arg_of(batch), arg_of(out), (float *)w.ptr, s);
+        if (e != cudaErrorNotSupported) { LCC_CUDA(e); return LCC_OK; }
     }
     // the same contraction in the reference's own precision: f64 on the FP64 tensor pipe (K6d, mma.sync m8n8k4)
     if (!tensor_path_off && op == kOpGP && !strict && a->dtype == LCC_F64 && a->layout == LCC_SOA && (a_bc != b_bc) &&
@@ -566,6 +573,7 @@ static lcc_status run_regressive(const lcc_algebra *alg, const lcc_view *a, cons
 
 lcc_status lcc_batch_product(const lcc_algebra *alg, int op, const lcc_view *a, const lcc_view *b, const lcc_view *out,
                              unsigned flags, void *stream) {
+    TraceRange tr("lcc_batch_product");
     switch (op) {
         case LCC_OP_GP: case LCC_OP_OUTER: case LCC_OP_LC: case LCC_OP_RC: case LCC_OP_SCALAR:
         case LCC_OP_COMMUTATOR: case LCC_OP_ANTICOMMUTATOR:
@@ -578,12 +586,14 @@ lcc_status lcc_batch_product(const lcc_algebra *alg, int op, const lcc_view *a, 
 
 lcc_status lcc_batch_gp_outer(const lcc_algebra *alg, const lcc_view *a, const lcc_view *b, const lcc_view *gp_out,
                               const lcc_view *outer_out, unsigned flags, void *stream) {
+    TraceRange tr("lcc_batch_gp_outer");
     if (!outer_out) return fail(LCC_ERR_VALUE, "outer_out is NULL");
     return run_product(alg, kOpGPOuter, a, b, gp_out, outer_out, flags, stream);
 }
 
 lcc_status lcc_batch_product_sum(const lcc_algebra *alg, int op, const lcc_view *a, int a_grade, const lcc_view *b, void *sums_dev,
                                  unsigned flags, void *stream) {
+    TraceRange tr("lcc_batch_product_sum");
     if (op != LCC_OP_GP && op != LCC_OP_OUTER && op != LCC_OP_LC) return fail(LCC_ERR_VALUE, "unknown product op %d", op);
     LCC_TRY(check_view(alg, a, "a"));
     LCC_TRY(check_view(alg, b, "b"));
@@ -628,6 +638,7 @@ lcc_status lcc_batch_product_sum(const lcc_algebra *alg, int op, const lcc_view 
 
 lcc_status lcc_batch_product_vjp(const lcc_algebra *alg, int op, int wrt, const lcc_view *grad_out, const lcc_view *other,
                                  const lcc_view *grad_in, unsigned flags, void *stream) {
+    TraceRange tr("lcc_batch_product_vjp");
     if (op != LCC_OP_GP && op != LCC_OP_OUTER && op != LCC_OP_LC) return fail(LCC_ERR_VALUE, "unknown product op %d", op);
     if (wrt != 0 && wrt != 1) return fail(LCC_ERR_VALUE, "wrt must be 0 (left operand) or 1 (right operand)");
     LCC_TRY(check_view(alg, grad_out, "grad_out"));
@@ -646,7 +657,7 @@ lcc_status lcc_batch_product_vjp(const lcc_algebra *alg, int op, int wrt, const 
         // register kernels over the build-time VJP term lists (kernels/product_impl.cuh, LIST = 1 / 2): the cotangent
         // streams at the same HBM rate as the forward product
         ProductArgs g;
-        g.op = op; g.dtype = grad_out->dtype; g.layout = grad_out->layout; g.strict = false; g.n = grad_out->n;
+        g.op = op; g.dtype = grad_out->dtype; g.layout = grad_out->layout; g.strict = false; g.n = grad_out->n;  // cotangents always use FMA (no reference rounding order exists for them)
         g.list = 1 + wrt;
         const lcc_view *first = wrt == 0 ? grad_out : other, *second = wrt == 0 ? other : grad_out;
         g.a = first->data; g.lda = first->ld; g.a_bcast = wrt == 1 && other_bc;
@@ -666,6 +677,7 @@ lcc_status lcc_batch_product_vjp(const lcc_algebra *alg, int op, int wrt, const 
 
 lcc_status lcc_batch_sandwich(const lcc_algebra *alg, const double *rotor, const lcc_view *x, const lcc_view *out,
                               unsigned flags, void *stream) {
+    TraceRange tr("lcc_batch_sandwich");
     LCC_TRY(check_view(alg, x, "x"));
     LCC_TRY(check_view(alg, out, "out"));
     LCC_TRY(same_kind(x, out, "sandwich"));
@@ -717,6 +729,7 @@ lcc_status lcc_batch_sandwich(const lcc_algebra *alg, const double *rotor, const
 
 lcc_status lcc_batch_sandwich_rows(const lcc_algebra *alg, const lcc_view *rotors, const lcc_view *x, const lcc_view *out,
                                    unsigned flags, void *stream) {
+    TraceRange tr("lcc_batch_sandwich_rows");
     LCC_TRY(check_view(alg, rotors, "rotors"));
     LCC_TRY(check_view(alg, x, "x"));
     LCC_TRY(check_view(alg, out, "out"));
@@ -738,6 +751,7 @@ lcc_status lcc_batch_sandwich_rows(const lcc_algebra *alg, const lcc_view *rotor
 }
 
 lcc_status lcc_batch_unary(const lcc_algebra *alg, int op, int arg, const lcc_view *x, const lcc_view *out, void *stream) {
+    TraceRange tr("lcc_batch_unary");
     LCC_TRY(check_view(alg, x, "x"));
     LCC_TRY(check_view(alg, out, "out"));
     LCC_TRY(same_kind(x, out, "unary"));
@@ -780,6 +794,7 @@ lcc_status lcc_batch_unary(const lcc_algebra *alg, int op, int arg, const lcc_vi
 }
 
 lcc_status lcc_batch_scale(const lcc_algebra *alg, const lcc_view *x, double factor, const lcc_view *out, void *stream) {
+    TraceRange tr("lcc_batch_scale");
     LCC_TRY(check_view(alg, x, "x"));
     LCC_TRY(check_view(alg, out, "out"));
     LCC_TRY(same_kind(x, out, "scale"));
@@ -794,6 +809,7 @@ lcc_status lcc_batch_scale(const lcc_algebra *alg, const lcc_view *x, double fac
 }
 
 lcc_status lcc_batch_elementwise(const lcc_algebra *alg, int op, const lcc_view *a, const lcc_view *b, const lcc_view *out, void *stream) {
+    TraceRange tr("lcc_batch_elementwise");
     LCC_TRY(check_view(alg, a, "a"));
     LCC_TRY(check_view(alg, b, "b"));
     LCC_TRY(check_view(alg, out, "out"));
@@ -811,6 +827,7 @@ lcc_status lcc_batch_elementwise(const lcc_algebra *alg, int op, const lcc_view 
 }
 
 lcc_status lcc_batch_norm(const lcc_algebra *alg, int kind, const lcc_view *x, void *norms, unsigned flags, void *stream) {
+    TraceRange tr("lcc_batch_norm");
     LCC_TRY(check_view(alg, x, "x"));
     if (kind != LCC_NORM_SQUARED && kind != LCC_NORM) return fail(LCC_ERR_VALUE, "unknown norm kind %d", kind);
     if (x->n == 0) return LCC_OK;
@@ -824,6 +841,7 @@ lcc_status lcc_batch_norm(const lcc_algebra *alg, int kind, const lcc_view *x, v
 }
 
 lcc_status lcc_batch_normalized(const lcc_algebra *alg, const lcc_view *x, const lcc_view *out, unsigned flags, void *stream) {
+    TraceRange tr("lcc_batch_normalized");
     LCC_TRY(check_view(alg, x, "x"));
     LCC_TRY(check_view(alg, out, "out"));
     LCC_TRY(same_kind(x, out, "normalized"));
@@ -836,6 +854,7 @@ lcc_status lcc_batch_normalized(const lcc_algebra *alg, const lcc_view *x, const
 }
 
 lcc_status lcc_batch_sum(const lcc_algebra *alg, const lcc_view *x, void *sums_dev, void *stream) {
+    TraceRange tr("lcc_batch_sum");
     LCC_TRY(check_view(alg, x, "x"));
     if (!sums_dev) return fail(LCC_ERR_VALUE, "sums_dev is NULL");
     cudaStream_t s;
@@ -883,6 +902,7 @@ lcc_status lcc_cga_points_embed(const lcc_algebra *alg, const void *xyz, const l
 lcc_status lcc_cga_points_extract(const lcc_algebra *alg, const lcc_view *src, void *xyz, void *stream) { return points_extract(alg, 1, src, xyz, stream); }
 lcc_status lcc_pga_points_sandwich(const lcc_algebra *alg, int dtype, const double *motor, const void *xyz_in, void *xyz_out,
                                    int64_t n, unsigned flags, void *stream) {
+    TraceRange tr("lcc_pga_points_sandwich");
     if (!alg) return fail(LCC_ERR_VALUE, "algebra handle is NULL");
     LCC_TRY(points_check(alg, 0));
     if (dtype != LCC_F32 && dtype != LCC_F64) return fail(LCC_ERR_VALUE, "dtype must be LCC_F32 or LCC_F64");
@@ -904,156 +924,8 @@ lcc_status lcc_pga_points_sandwich(const lcc_algebra *alg, int dtype, const doub
 lcc_status lcc_sta_bivectors_embed(const lcc_algebra *alg, const void *eb, const lcc_view *dst, void *stream) { return points_embed(alg, 2, eb, dst, stream); }
 lcc_status lcc_sta_boosts_embed(const lcc_algebra *alg, const void *velocity, const lcc_view *dst, void *stream) { return points_embed(alg, 3, velocity, dst, stream); }
 
-// ================================================================== host-buffer (end-to-end) entry points
-// Chunked three-stream pipeline: H2D copy of chunk c+1, kernel of chunk c and D2H copy of chunk
-// c-1 overlap.  Kernels run directly on the reference's AoS layout, so each chunk crosses HBM once
-// in each direction and PCIe is the only bound.
-namespace {
-constexpr int64_t kChunkBytes = 64ll << 20;
-
-struct Pipeline {
-    DeviceState *st = nullptr;
-    cudaEvent_t h2d[2]{}, kern[2]{}, d2h[2]{};
-    bool made = false;
-    lcc_status init() {
-        LCC_TRY(device_state(&st));
-        for (int i = 0; i < 2; ++i) {
-            LCC_CUDA(cudaEventCreateWithFlags(&h2d[i], cudaEventDisableTiming));
-            LCC_CUDA(cudaEventCreateWithFlags(&kern[i], cudaEventDisableTiming));
-            LCC_CUDA(cudaEventCreateWithFlags(&d2h[i], cudaEventDisableTiming));
-        }
-        made = true;
-        return LCC_OK;
-    }
-    ~Pipeline() {
-        if (!made) return;
-        for (int i = 0; i < 2; ++i) { cudaEventDestroy(h2d[i]); cudaEventDestroy(kern[i]); cudaEventDestroy(d2h[i]); }
-    }
-};
-}  // namespace
-
-lcc_status lcc_host_sandwich(const lcc_algebra *alg, int dtype, const double *rotor, const void *x_host, void *out_host,
-                             int64_t n, unsigned flags) {
-    if (!alg) return fail(LCC_ERR_VALUE, "algebra handle is NULL");
-    if (dtype != LCC_F32 && dtype != LCC_F64) return fail(LCC_ERR_VALUE, "dtype must be LCC_F32 or LCC_F64");
-    if (n < 0) return fail(LCC_ERR_VALUE, "negative batch size");
-    if (n == 0) return LCC_OK;
-    if (!rotor || !x_host || !out_host) return fail(LCC_ERR_VALUE, "NULL buffer");
-    Pipeline pl;
-    LCC_TRY(pl.init());
-    const size_t row_bytes = (size_t)alg->nb * elem_size(dtype);
-    int64_t chunk = kChunkBytes / (int64_t)row_bytes;
-    if (chunk > n) chunk = n;
-    PoolBuffer in[2], out[2];
-    for (int i = 0; i < 2; ++i) { LCC_TRY(in[i].alloc(chunk * row_bytes, pl.st->stream)); LCC_TRY(out[i].alloc(chunk * row_bytes, pl.st->stream)); }
-    LCC_CUDA(cudaStreamSynchronize(pl.st->stream));  // buffers exist before the copy streams touch them
-    int64_t done = 0;
-    for (int64_t c = 0; done < n; ++c, done += chunk) {
-        const int buf = (int)(c & 1);
-        const int64_t rows = (n - done) < chunk ? (n - done) : chunk;
-        if (c >= 2) LCC_CUDA(cudaStreamWaitEvent(pl.st->copy_in, pl.kern[buf], 0));
-        LCC_CUDA(cudaMemcpyAsync(in[buf].ptr, (const char *)x_host + done * row_bytes, rows * row_bytes, cudaMemcpyHostToDevice, pl.st->copy_in));
-        LCC_CUDA(cudaEventRecord(pl.h2d[buf], pl.st->copy_in));
-        LCC_CUDA(cudaStreamWaitEvent(pl.st->stream, pl.h2d[buf], 0));
-        if (c >= 2) LCC_CUDA(cudaStreamWaitEvent(pl.st->stream, pl.d2h[buf], 0));
-        lcc_view vx{in[buf].ptr, rows, alg->nb, dtype, LCC_AOS}, vo{out[buf].ptr, rows, alg->nb, dtype, LCC_AOS};
-        LCC_TRY(lcc_batch_sandwich(alg, rotor, &vx, &vo, flags, (void *)pl.st->stream));
-        LCC_CUDA(cudaEventRecord(pl.kern[buf], pl.st->stream));
-        LCC_CUDA(cudaStreamWaitEvent(pl.st->copy_out, pl.kern[buf], 0));
-        LCC_CUDA(cudaMemcpyAsync((char *)out_host + done * row_bytes, out[buf].ptr, rows * row_bytes, cudaMemcpyDeviceToHost, pl.st->copy_out));
-        LCC_CUDA(cudaEventRecord(pl.d2h[buf], pl.st->copy_out));
-    }
-    LCC_CUDA(cudaStreamSynchronize(pl.st->copy_out));
-    LCC_CUDA(cudaStreamSynchronize(pl.st->stream));
-    return LCC_OK;
-}
-
-lcc_status lcc_host_pga_points_sandwich(const lcc_algebra *alg, int dtype, const double *motor, const void *xyz_host_in,
-                                        void *xyz_host_out, int64_t n, unsigned flags) {
-    if (!alg) return fail(LCC_ERR_VALUE, "algebra handle is NULL");
-    LCC_TRY(points_check(alg, 0));
-    if (dtype != LCC_F32 && dtype != LCC_F64) return fail(LCC_ERR_VALUE, "dtype must be LCC_F32 or LCC_F64");
-    if (n < 0) return fail(LCC_ERR_VALUE, "negative batch size");
-    if (n == 0) return LCC_OK;
-    if (!motor || !xyz_host_in || !xyz_host_out) return fail(LCC_ERR_VALUE, "NULL buffer");
-    Pipeline pl;
-    LCC_TRY(pl.init());
-    const size_t row_bytes = 3 * elem_size(dtype);
-    // 16 MiB chunks: the whole batch is only 12-24 bytes per point, so the un-overlapped first H2D and last D2H copy weigh more
-    int64_t chunk = ((kChunkBytes / 4) / (int64_t)row_bytes) & ~(int64_t)3;
-    if (chunk > n) chunk = n;
-    // separate input and output stages: with an in-place stage the next H2D copy would have to wait for the D2H copy of
-    // the same buffer and the two PCIe directions would run in lock step (42 instead of 48 GB/s each way)
-    PoolBuffer in[2], out[2];
-    for (int i = 0; i < 2; ++i) { LCC_TRY(in[i].alloc(chunk * row_bytes, pl.st->stream)); LCC_TRY(out[i].alloc(chunk * row_bytes, pl.st->stream)); }
-    LCC_CUDA(cudaStreamSynchronize(pl.st->stream));
-    int64_t done = 0;
-    for (int64_t c = 0; done < n; ++c, done += chunk) {
-        const int buf = (int)(c & 1);
-        const int64_t rows = (n - done) < chunk ? (n - done) : chunk;
-        if (c >= 2) LCC_CUDA(cudaStreamWaitEvent(pl.st->copy_in, pl.kern[buf], 0));
-        LCC_CUDA(cudaMemcpyAsync(in[buf].ptr, (const char *)xyz_host_in + done * row_bytes, rows * row_bytes, cudaMemcpyHostToDevice, pl.st->copy_in));
-        LCC_CUDA(cudaEventRecord(pl.h2d[buf], pl.st->copy_in));
-        LCC_CUDA(cudaStreamWaitEvent(pl.st->stream, pl.h2d[buf], 0));
-        if (c >= 2) LCC_CUDA(cudaStreamWaitEvent(pl.st->stream, pl.d2h[buf], 0));
-        LCC_TRY(lcc_pga_points_sandwich(alg, dtype, motor, in[buf].ptr, out[buf].ptr, rows, flags, (void *)pl.st->stream));
-        LCC_CUDA(cudaEventRecord(pl.kern[buf], pl.st->stream));
-        LCC_CUDA(cudaStreamWaitEvent(pl.st->copy_out, pl.kern[buf], 0));
-        LCC_CUDA(cudaMemcpyAsync((char *)xyz_host_out + done * row_bytes, out[buf].ptr, rows * row_bytes, cudaMemcpyDeviceToHost, pl.st->copy_out));
-        LCC_CUDA(cudaEventRecord(pl.d2h[buf], pl.st->copy_out));
-    }
-    LCC_CUDA(cudaStreamSynchronize(pl.st->copy_out));
-    LCC_CUDA(cudaStreamSynchronize(pl.st->stream));
-    return LCC_OK;
-}
-
-lcc_status lcc_host_product(const lcc_algebra *alg, int dtype, int op, const void *a_host, int64_t na, const void *b_host,
-                            int64_t nb_rows, void *out_host, unsigned flags) {
-    if (!alg) return fail(LCC_ERR_VALUE, "algebra handle is NULL");
-    if (dtype != LCC_F32 && dtype != LCC_F64) return fail(LCC_ERR_VALUE, "dtype must be LCC_F32 or LCC_F64");
-    if (op != LCC_OP_GP && op != LCC_OP_OUTER && op != LCC_OP_LC) return fail(LCC_ERR_VALUE, "unknown product op %d", op);
-    int64_t n = 0;
-    LCC_TRY(broadcast_rows(na, nb_rows, &n));
-    if (n == 0) return LCC_OK;
-    if (!a_host || !b_host || !out_host) return fail(LCC_ERR_VALUE, "NULL buffer");
-    Pipeline pl;
-    LCC_TRY(pl.init());
-    const size_t row_bytes = (size_t)alg->nb * elem_size(dtype);
-    int64_t chunk = kChunkBytes / (int64_t)row_bytes;
-    if (chunk > n) chunk = n;
-    const bool a_bc = na == 1 && n > 1, b_bc = nb_rows == 1 && n > 1;
-    PoolBuffer ia[2], ib[2], out[2];
-    for (int i = 0; i < 2; ++i) {
-        LCC_TRY(ia[i].alloc((a_bc ? 1 : chunk) * row_bytes, pl.st->stream));
-        LCC_TRY(ib[i].alloc((b_bc ? 1 : chunk) * row_bytes, pl.st->stream));
-        LCC_TRY(out[i].alloc(chunk * row_bytes, pl.st->stream));
-    }
-    if (a_bc) LCC_CUDA(cudaMemcpyAsync(ia[0].ptr, a_host, row_bytes, cudaMemcpyHostToDevice, pl.st->stream));
-    if (b_bc) LCC_CUDA(cudaMemcpyAsync(ib[0].ptr, b_host, row_bytes, cudaMemcpyHostToDevice, pl.st->stream));
-    LCC_CUDA(cudaStreamSynchronize(pl.st->stream));
-    int64_t done = 0;
-    for (int64_t c = 0; done < n; ++c, done += chunk) {
-        const int buf = (int)(c & 1);
-        const int64_t rows = (n - done) < chunk ? (n - done) : chunk;
-        if (c >= 2) LCC_CUDA(cudaStreamWaitEvent(pl.st->copy_in, pl.kern[buf], 0));
-        if (!a_bc) LCC_CUDA(cudaMemcpyAsync(ia[buf].ptr, (const char *)a_host + done * row_bytes, rows * row_bytes, cudaMemcpyHostToDevice, pl.st->copy_in));
-        if (!b_bc) LCC_CUDA(cudaMemcpyAsync(ib[buf].ptr, (const char *)b_host + done * row_bytes, rows * row_bytes, cudaMemcpyHostToDevice, pl.st->copy_in));
-        LCC_CUDA(cudaEventRecord(pl.h2d[buf], pl.st->copy_in));
-        LCC_CUDA(cudaStreamWaitEvent(pl.st->stream, pl.h2d[buf], 0));
-        if (c >= 2) LCC_CUDA(cudaStreamWaitEvent(pl.st->stream, pl.d2h[buf], 0));
-        lcc_view va{a_bc ? ia[0].ptr : ia[buf].ptr, a_bc ? 1 : rows, alg->nb, dtype, LCC_AOS};
-        lcc_view vb{b_bc ? ib[0].ptr : ib[buf].ptr, b_bc ? 1 : rows, alg->nb, dtype, LCC_AOS};
-        lcc_view vo{out[buf].ptr, rows, alg->nb, dtype, LCC_AOS};
-        LCC_TRY(lcc_batch_product(alg, op, &va, &vb, &vo, flags, (void *)pl.st->stream));
-        LCC_CUDA(cudaEventRecord(pl.kern[buf], pl.st->stream));
-        LCC_CUDA(cudaStreamWaitEvent(pl.st->copy_out, pl.kern[buf], 0));
-        LCC_CUDA(cudaMemcpyAsync((char *)out_host + done * row_bytes, out[buf].ptr, rows * row_bytes, cudaMemcpyDeviceToHost, pl.st->copy_out));
-        LCC_CUDA(cudaEventRecord(pl.d2h[buf], pl.st->copy_out));
-    }
-    LCC_CUDA(cudaStreamSynchronize(pl.st->copy_out));
-    LCC_CUDA(cudaStreamSynchronize(pl.st->stream));
-    return LCC_OK;
-}
+// (host-buffer entry points, lcc_batch_upload / download and the pinned host cache: host_transfer.cu;
+//  multi-GPU row sharding + NCCL: shard_group.cu)
 
 // ================================================================== tuning
 lcc_status lcc_set_option(const char *name, int64_t value) {
@@ -1061,12 +933,16 @@ lcc_status lcc_set_option(const char *name, int64_t value) {
     if (value < 0) return fail(LCC_ERR_VALUE, "option %s: value must be >= 0", name);
     if (!strcmp(name, "aos_tma_min_rows")) { g_aos_tma_min_rows = value; return LCC_OK; }
     if (!strcmp(name, "soa_tma_min_bytes")) { g_soa_tma_min_bytes = value; return LCC_OK; }
+    if (!strcmp(name, "host_chunk_bytes")) { set_option_host_chunk_bytes(value); return LCC_OK; }
+    if (!strcmp(name, "pinned_output_min_bytes")) { set_option_pinned_output_min_bytes(value); return LCC_OK; }
     return fail(LCC_ERR_VALUE, "unknown option %s", name);
 }
 lcc_status lcc_get_option(const char *name, int64_t *value) {
     if (!name || !value) return fail(LCC_ERR_VALUE, "option name / value is NULL");
     if (!strcmp(name, "aos_tma_min_rows")) { *value = g_aos_tma_min_rows; return LCC_OK; }
     if (!strcmp(name, "soa_tma_min_bytes")) { *value = g_soa_tma_min_bytes; return LCC_OK; }
+    if (!strcmp(name, "host_chunk_bytes")) { *value = option_host_chunk_bytes(); return LCC_OK; }
+    if (!strcmp(name, "pinned_output_min_bytes")) { *value = option_pinned_output_min_bytes(); return LCC_OK; }
     return fail(LCC_ERR_VALUE, "unknown option %s", name);
 }
 

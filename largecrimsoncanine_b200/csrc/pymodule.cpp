@@ -277,12 +277,11 @@ BatchPtr batch_from_numpy(const PyAlgebra &alg, const py::array &coeffs_in) {  /
     auto b = std::make_shared<Batch>(alg.inner, dtype, n);
     if (n == 0) return b;
     const void *host = coeffs.data();
-    const size_t bytes = (size_t)coeffs.nbytes();
     py::gil_scoped_release nogil;
-    DeviceTemp stage(bytes);
-    upload(host, bytes, stage.ptr);
-    lcc_view src{stage.ptr, n, nb, dtype, LCC_AOS};
-    check(lcc_batch_convert(alg.inner->h, &src, &b->view, nullptr));
+    // chunked pipeline (host_transfer.cu): the array is read exactly once -- directly by the DMA engine when it is
+    // pinned, through the pinned bounce ring otherwise -- and each chunk is transposed into the blade-major batch while
+    // the next one crosses PCIe.  Returns once the NumPy buffer has been consumed (it may change afterwards).
+    check(lcc_batch_upload(alg.inner->h, host, n, &b->view, nullptr));
     return b;
 }
 
@@ -318,17 +317,42 @@ py::array batch_gather(const Batch &b, const std::vector<int32_t> &blades, bool 
     return out;
 }
 
-py::array batch_to_numpy(const Batch &b) {  // src/batch.rs:233-235
-    py::array out(np_dtype(b.view.dtype), std::vector<py::ssize_t>{(py::ssize_t)b.n(), (py::ssize_t)b.nb()});
+// A NumPy array over a block of the pinned host cache (lcc_host_cache_*); the block returns to the cache when the
+// array is garbage collected.  Used for large results so the D2H copy is a direct DMA into the array's memory.
+py::array pinned_array(int dtype, const std::vector<py::ssize_t> &shape) {
+    size_t bytes = dtype == LCC_F32 ? 4 : 8;
+    for (auto d : shape) bytes *= (size_t)d;
+    void *p = nullptr;
+    check(lcc_host_cache_alloc(&p, bytes));
+    py::capsule owner(p, [](void *q) { lcc_host_cache_free(q); });
+    return py::array(np_dtype(dtype), shape, p, owner);
+}
+py::array output_array(int dtype, const std::vector<py::ssize_t> &shape) {
+    size_t bytes = dtype == LCC_F32 ? 4 : 8;
+    for (auto d : shape) bytes *= (size_t)d;
+    int64_t min_bytes = 0;
+    lcc_get_option("pinned_output_min_bytes", &min_bytes);
+    if (min_bytes >= 0 && (int64_t)bytes >= min_bytes && bytes > 0) {
+        try { return pinned_array(dtype, shape); } catch (const std::exception &) { /* no pinned memory left: pageable */ }
+    }
+    return py::array(np_dtype(dtype), shape);
+}
+
+py::array batch_to_numpy(const Batch &b, py::object out_obj = py::none()) {  // src/batch.rs:233-235
+    const std::vector<py::ssize_t> shape{(py::ssize_t)b.n(), (py::ssize_t)b.nb()};
+    py::array out;
+    if (out_obj.is_none()) {
+        out = output_array(b.view.dtype, shape);
+    } else {  // additive: export into a caller-provided (e.g. pinned) array
+        out = py::array::ensure(out_obj);
+        if (!out || dtype_of(out) != b.view.dtype || out.ndim() != 2 || out.shape(0) != shape[0] || out.shape(1) != shape[1] ||
+            !(out.flags() & py::array::c_style) || !out.writeable())
+            throw py::value_error("out must be a writeable C-contiguous (N, num_blades) array of the batch's dtype");
+    }
     void *out_ptr = out.mutable_data();
     if (b.n() == 0) return out;
     py::gil_scoped_release nogil;
-    const size_t bytes = (size_t)b.n() * b.nb() * b.es();
-    DeviceTemp stage(bytes);
-    lcc_view dst{stage.ptr, b.n(), b.nb(), b.view.dtype, LCC_AOS};
-    check(lcc_batch_convert(b.algebra->h, &b.view, &dst, nullptr));
-    check(lcc_memcpy_d2h(out_ptr, stage.ptr, bytes, nullptr));
-    check(lcc_stream_sync(nullptr));
+    check(lcc_batch_download(b.algebra->h, &b.view, out_ptr, nullptr));
     return out;
 }
 
@@ -493,7 +517,7 @@ PYBIND11_MODULE(largecrimsoncanine, m) {
         py::array xyz = contiguous(xyz_in);
         const int dtype = dtype_of(xyz);
         if (xyz.ndim() != 2 || xyz.shape(1) != 3) throw py::value_error("points must have 3 columns");
-        py::array out(np_dtype(dtype), std::vector<py::ssize_t>{xyz.shape(0), 3});
+        py::array out = output_array(dtype, std::vector<py::ssize_t>{xyz.shape(0), 3});
         const size_t bytes = (size_t)xyz.nbytes();
         if (bytes == 0) return out;
         const void *host = xyz.data();
@@ -506,6 +530,19 @@ PYBIND11_MODULE(largecrimsoncanine, m) {
         check(lcc_host_pga_points_sandwich(a.inner->h, dtype, m.data(), host, out_ptr, n, flags));
         return out;
     }, "Apply a PGA3D motor to an (N,3) array of points: embed, sandwich and extract fused in one kernel.");
+    m.def("pinned_empty", [](std::vector<py::ssize_t> shape, const py::object &dtype) {
+        const py::dtype dt = py::dtype::from_args(dtype);
+        int code;
+        if (dt.is(py::dtype::of<double>())) code = LCC_F64;
+        else if (dt.is(py::dtype::of<float>())) code = LCC_F32;
+        else throw py::type_error("pinned_empty supports float64 and float32");
+        return pinned_array(code, shape);
+    }, py::arg("shape"), py::arg("dtype") = py::dtype::of<double>(),
+          "Uninitialised NumPy array in page-locked host memory (from the engine's pinned cache): from_numpy / sandwich_numpy "
+          "DMA such arrays directly instead of staging them.");
+    m.def("is_pinned", [](const py::array &a) { return lcc_host_is_pinned(a.data(), (size_t)a.nbytes()) != 0; });
+    m.def("host_cache_trim", [] { check(lcc_host_cache_trim()); });
+    m.def("host_cache_stats", [] { size_t live = 0, idle = 0; check(lcc_host_cache_stats(&live, &idle)); return py::make_tuple(live, idle); });
     m.def("set_option", [](const std::string &name, int64_t value) { check(lcc_set_option(name.c_str(), value)); },
           "Tuning knobs of the engine (include/lcc_b200.h, lcc_set_option); results never depend on them.");
     m.def("get_option", [](const std::string &name) { int64_t v = 0; check(lcc_get_option(name.c_str(), &v)); return v; });
@@ -1115,7 +1152,7 @@ PYBIND11_MODULE(largecrimsoncanine, m) {
             }
             return batch_from_columns(a, biv, blades_of_grade(a.inner->nb(), 2), "bivector_coeffs");
         }, py::arg("algebra"), py::arg("bivector_coeffs"))
-        .def("to_numpy", [](const Batch &b) { return batch_to_numpy(b); })
+        .def("to_numpy", [](const Batch &b, py::object out) { return batch_to_numpy(b, out); }, py::arg("out") = py::none())
         .def("to_vector_coords", [](const Batch &b) { return batch_gather(b, vector_blades(b.algebra->dim()), false); })
         .def("scalar", [](const Batch &b) { return batch_gather(b, std::vector<int32_t>{0}, true); })
         .def("len", &Batch::n)
@@ -1150,6 +1187,40 @@ PYBIND11_MODULE(largecrimsoncanine, m) {
         .def("meet", [](const Batch &a, const Batch &b) { return batch_product(a, b, LCC_OP_REGRESSIVE); })
         .def("sandwich", &batch_sandwich)
         .def("apply", &batch_sandwich)
+        .def_static("sandwich_numpy", [](const PyAlgebra &alg, const Multivector &rotor, const py::array &x_in, py::object out_obj) {
+            // from_numpy(x).sandwich(rotor).to_numpy() as ONE host-array call (lcc_host_sandwich): the upload of chunk
+            // c+1, the kernel of chunk c and the download of chunk c-1 overlap, so both PCIe directions are busy at once
+            // -- the three-call sequence cannot do that, each of its calls has to finish before the next starts
+            AlgebraPtr ralg = rotor.get_algebra();
+            if (!alg.inner->same_signature(*ralg))
+                throw py::value_error("algebra mismatch: batch is " + alg.inner->str() + " but rotor is " + ralg->str());
+            py::array x = contiguous(x_in);
+            const int dtype = dtype_of(x);
+            const int nb = alg.inner->nb();
+            if (x.ndim() != 2) throw py::type_error("coeffs must be a 2-D array of shape (N, num_blades)");
+            if (x.shape(1) != nb) {
+                std::ostringstream s; s << "coeffs must have " << nb << " columns for " << alg.inner->str() << " but got " << x.shape(1);
+                throw py::value_error(s.str());
+            }
+            const std::vector<py::ssize_t> shape{x.shape(0), (py::ssize_t)nb};
+            py::array out;
+            if (out_obj.is_none()) out = output_array(dtype, shape);
+            else {
+                out = py::array::ensure(out_obj);
+                if (!out || dtype_of(out) != dtype || out.ndim() != 2 || out.shape(0) != shape[0] || out.shape(1) != shape[1] ||
+                    !(out.flags() & py::array::c_style) || !out.writeable())
+                    throw py::value_error("out must be a writeable C-contiguous (N, num_blades) array of x's dtype");
+            }
+            const int64_t n = x.shape(0);
+            if (n == 0) return out;
+            const void *host = x.data();
+            void *out_ptr = out.mutable_data();
+            const std::vector<double> r = rotor.coeffs;
+            const unsigned flags = fp_flags();
+            py::gil_scoped_release nogil;
+            check(lcc_host_sandwich(alg.inner->h, dtype, r.data(), host, out_ptr, n, flags));
+            return out;
+        }, py::arg("algebra"), py::arg("rotor"), py::arg("x"), py::arg("out") = py::none())
         .def("norm", [](const Batch &a) { return batch_norm(a, LCC_NORM); })
         .def("norm_squared", [](const Batch &a) { return batch_norm(a, LCC_NORM_SQUARED); })
         .def("normalized", [](const Batch &a) {

@@ -17,6 +17,7 @@ There is no CPU path: tensors must live on a CUDA device (`.cuda()`); CPU tensor
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Optional, Tuple, Union
 
 import numpy as np
@@ -45,6 +46,24 @@ def _handle(signature: Tuple[int, int, int]) -> cabi.Algebra:
     if h is None:
         h = _HANDLES[signature] = cabi.Algebra(*signature)
     return h
+
+
+_ROTOR_CACHE: list = [None]  # (weakref to the rotor tensor, its version counter, host float64 copy)
+
+
+def _rotor_on_host(t: Tensor) -> np.ndarray:
+    """Host float64 copy of a one-row rotor tensor for the fixed-versor kernel (its coefficients travel as kernel
+    parameters).  The device->host read is a synchronisation point, so the copy is cached per tensor object and
+    version counter: applying the same motor to many batches syncs once, not once per call."""
+    hit = _ROTOR_CACHE[0]
+    if hit is not None and hit[0]() is t and hit[1] == t._version:
+        return hit[2]
+    r = t.detach().to(torch.float64).cpu().numpy().reshape(-1).copy()
+    try:
+        _ROTOR_CACHE[0] = (weakref.ref(t), t._version, r)
+    except TypeError:
+        _ROTOR_CACHE[0] = None
+    return r
 
 
 def _blade_grade(blade: int) -> int:
@@ -124,6 +143,9 @@ class _Product(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a: Tensor, b: Tensor, sig, op: int):
         ctx.sig, ctx.op = sig, op
+        ctx.b_dtype = b.dtype
+        if b.dtype != a.dtype:  # the product runs in a's dtype; save what the kernels actually saw
+            b = b.to(a.dtype)
         ctx.save_for_backward(a, b)
         return _product_forward(sig, op, a, b)
 
@@ -139,6 +161,8 @@ class _Product(torch.autograd.Function):
             gb = _product_vjp(ctx.sig, ctx.op, 1, grad_out, a)
             if b.shape[0] == 1 and gb.shape[0] > 1:
                 gb = gb.sum(dim=0, keepdim=True)
+            if gb.dtype != ctx.b_dtype:
+                gb = gb.to(ctx.b_dtype)
         return ga, gb, None, None
 
 
@@ -337,7 +361,7 @@ class TorchMultivector:
             x = _prep(self.coeffs)
             out = torch.empty_like(x)
             if x.shape[0]:
-                r = rotor.coeffs.detach().to(torch.float64).cpu().numpy().reshape(-1).copy()
+                r = _rotor_on_host(rotor.coeffs)
                 with torch.cuda.device(x.device):
                     cabi.check(cabi.lib().lcc_batch_sandwich(_handle(self.algebra.signature).h, r.ctypes.data_as(C.POINTER(C.c_double)),
                                                              C.byref(_view(x)), C.byref(_view(out)), _flags(), _stream()))

@@ -398,6 +398,35 @@ def test_fixed_operand_product_on_tensor_cores(L, sig):
         L.set_strict_fp(False)
 
 
+def test_fixed_operand_product_with_a_pitch_the_tensor_map_cannot_cover(L):
+    """A raw SoA f32 view whose pitch is not a multiple of 32 rows (a torch (nb, n) tensor with n = 1000): the K6 tensor
+    map walks rows in strips of 32, so the dispatcher must take the exact kernel instead of returning zeros for rows
+    992..999 (round-1 advisor finding)."""
+    from largecrimsoncanine_b200 import cabi
+
+    lib, alg, o = cabi.lib(), cabi.Algebra(6, 0, 0), oracle.OracleAlgebra(6, 0, 0)
+    nb, n, ld = 64, 1000, 1000
+    rng = np.random.default_rng(77)
+    m, x = rng.standard_normal((1, nb)).astype(np.float32), rng.standard_normal((n, nb)).astype(np.float32)
+    px, pm, po = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    for p, bytes_ in ((px, nb * ld * 4), (pm, nb * 4 * 4), (po, nb * ld * 4)):
+        cabi.check(lib.lcc_device_alloc(C.byref(p), bytes_, None))
+    xi = np.ascontiguousarray(x.T)
+    mi = np.zeros((nb, 4), np.float32)
+    mi[:, 0] = m[0]
+    cabi.check(lib.lcc_memcpy_h2d(px, xi.ctypes.data, xi.nbytes, None))
+    cabi.check(lib.lcc_memcpy_h2d(pm, mi.ctypes.data, mi.nbytes, None))
+    vx, vm, vo = cabi.view(px.value, n, ld, cabi.LCC_F32, cabi.LCC_SOA), cabi.view(pm.value, 1, 4, cabi.LCC_F32, cabi.LCC_SOA), cabi.view(po.value, n, ld, cabi.LCC_F32, cabi.LCC_SOA)
+    cabi.check(lib.lcc_batch_product(alg.h, cabi.LCC_OP_GP, C.byref(vm), C.byref(vx), C.byref(vo), 0, None))
+    out = np.empty_like(xi)
+    cabi.check(lib.lcc_memcpy_d2h(out.ctypes.data, po, out.nbytes, None))
+    cabi.check(lib.lcc_stream_sync(None))
+    ref = o.geometric_product(m.astype(np.float64), x.astype(np.float64))
+    assert np.all(np.abs(out.T - ref).max(axis=1) <= 1e-5 * np.abs(ref).max(axis=1))  # every row, including the last 8
+    for p in (px, pm, po):
+        cabi.check(lib.lcc_device_free(p, None))
+
+
 @pytest.mark.parametrize("sig", [(6, 0, 0), (4, 2, 1), (8, 0, 0)])
 def test_fixed_operand_product_f64_on_the_fp64_tensor_pipe(L, sig):
     """K6d: the same broadcast product in the reference's own precision -> DMMA GEMM (mma.sync m8n8k4.f64).
