@@ -53,7 +53,13 @@ WORKLOADS["cl8_fixed_gp"] = ((8, 0, 0), "f32", 24, 2048, "products/s")
 # the same product in the reference's own precision, on the FP64 tensor pipe (DMMA)
 WORKLOADS["cl8_fixed_gp_f64"] = ((8, 0, 0), "f64", 24, 4096, "products/s")
 TENSOR_FLOPS_PER_UNIT = {"cl8_fixed_gp": 3 * 2 * 256 * 256, "cl8_fixed_gp_f64": 2 * 256 * 256}  # f32: three tf32 MMAs per term
+# the headline input is a PGA point (12 of its 16 blade rows are zeros); this variant streams 16 dense rows
+WORKLOADS["pga_sandwich_dense16"] = ((3, 0, 1), "f32", 28, 128, "points/s")
 HEADLINE = "pga_sandwich"
+
+
+TRAFFIC_SOURCE = ("static: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at this size "
+                  "(profiles/traffic.json names the capture); NOT measured in this run -- a bench process cannot read DRAM counters")
 
 
 def load_peaks():
@@ -146,7 +152,11 @@ def cpu_rate(workload, sample_rows, threads, repeats=1):
     ndt = np.float32 if dt == "f32" else np.float64
     rng = np.random.default_rng(42)
     nb = o.num_blades
-    if workload == "pga_sandwich":
+    if workload == "pga_sandwich_dense16":
+        x = rng.standard_normal((sample_rows, 16)).astype(ndt)
+        motor = headline_motor()
+        fn = lambda: o.sandwich(motor, x, threads=threads)  # noqa: E731
+    elif workload == "pga_sandwich":
         pts = rng.standard_normal((sample_rows, 3)).astype(ndt)
         x = np.zeros((sample_rows, 16), ndt)
         x[:, 7], x[:, 14], x[:, 13], x[:, 11] = 1.0, -pts[:, 0], pts[:, 1], -pts[:, 2]
@@ -175,17 +185,16 @@ def cpu_rate(workload, sample_rows, threads, repeats=1):
 def cpu_sample_rows(workload):
     return {"pga_sandwich": 1 << 25, "cga_gp": 1 << 22, "cga_gp_outer": 1 << 22, "r3_gp": 1 << 20, "sta_grade_inner_sum": 1 << 23,
             "sta_fused_grade_inner_sum": 1 << 23,
-            "cl8_fixed_gp": 1 << 14, "cl8_fixed_gp_f64": 1 << 14, "pga_points_compact": 1 << 25}[workload]
+            "cl8_fixed_gp": 1 << 14, "cl8_fixed_gp_f64": 1 << 14, "pga_points_compact": 1 << 25, "pga_sandwich_dense16": 1 << 25}[workload]
 
 
 def run_reference_arm(args):
     """`--impl reference`: the reference's own CPU implementation of the path (oracle port of the Rust
-    loops -- the crate itself cannot be built here) on this box's host cores."""
+    loops -- the crate itself cannot be built here) on this box's host cores.  Prints the same `config`
+    block as the GPU arm (same workload, rows per GPU); how the CPU run was bounded is under `cpu_baseline`."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import oracle
-
     wl = args.workload
     sig, dt, log2n, bytes_per, unit = WORKLOADS[wl]
     threads = args.cpu_threads or 1
@@ -198,17 +207,19 @@ def run_reference_arm(args):
         times.append(t)
     ms = 1e3 * float(np.mean(times))
     value = rows / (ms / 1e3)
-    cores = oracle.max_threads()
+    cores = host_cores()  # torchrun exports OMP_NUM_THREADS=1: ask the scheduler, not OpenMP
     all_cores_value = cpu_rate(wl, rows, cores)[0] if cores > threads else value  # what an OpenMP-over-rows port would do
     n = 1 << (args.log2_rows or log2n)
     line = {
         "impl": "reference", "metric": f"{wl} throughput", "value": value, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": dt, "data": "synthetic",
-        "config": {"workload": workload_name(wl), "rows_per_gpu": n, "layout": "AoS (N, num_blades) row-major in host memory (the reference's Array2)",
-                   "l2_policy": "n/a (CPU arm)", "strict_fp": True, "sample_rows_per_step": rows},
+        "config": config_block(wl, n),
+        "impl_config": {"layout": "AoS (N, num_blades) row-major in host memory (the reference's Array2)", "strict_fp": True,
+                        "sample_rows_per_step": rows},
         "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port",
-                         "sample": f"{rows} rows per step of the same synthetic workload; the reference is single-threaded (GIL held, no threads)",
+                         "sample": f"{rows} rows per step of the same synthetic workload (the rate does not depend on the row count once out of "
+                                   "cache); the reference is single-threaded (GIL held, no threads)",
                          "host_threads_available": cores, "all_cores_value": all_cores_value, "all_cores": cores},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -216,7 +227,7 @@ def run_reference_arm(args):
     return 0
 
 
-def workload_name(wl):
+def workload_name(wl, n=None):
     sig, dt, log2n, _, _ = WORKLOADS[wl]
     desc = {
         "pga_sandwich": "PGA Cl(3,0,1) motor sandwich", "cga_gp": "CGA Cl(4,1,0) batched geometric product",
@@ -226,54 +237,84 @@ def workload_name(wl):
         "cl8_fixed_gp_f64": "Cl(8,0,0) fixed-operand left geometric product, f64 (mma.sync m8n8k4 DMMA)",
         "sta_fused_grade_inner_sum": "STA Cl(1,3,0) fused grade projection + inner product + batch sum (one kernel)",
         "pga_points_compact": "PGA Cl(3,0,1) motor applied to compact (N,3) points, embed + sandwich + extract fused",
+        "pga_sandwich_dense16": "PGA Cl(3,0,1) motor sandwich on fully dense 16-blade multivectors",
     }[wl]
-    return f"{desc}, 2^{log2n} rows per GPU, {dt}, {1 << sum(sig)} blades"
+    rows = f"2^{log2n}" if n is None or n == (1 << log2n) else (f"2^{n.bit_length() - 1}" if n & (n - 1) == 0 else str(n))
+    return f"{desc}, {rows} rows per GPU, {dt}, {1 << sum(sig)} blades"
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
-def run_gpu_arm(args):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """Everything one rank needs to run workloads: library, device, the launching stream, the native shard group."""
 
-    from largecrimsoncanine_b200 import cabi
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the batched path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        # the only collective of the path is a 16..256-element all-reduce: one channel (one CTA) is enough, and every
-        # extra NCCL CTA spin-waiting for a slower rank takes SM slots away from the streaming kernel it overlaps with
-        os.environ.setdefault("NCCL_MAX_NCHANNELS", "1")
-        os.environ.setdefault("NCCL_MAX_CTAS", "1")
-        dist.init_process_group("nccl", device_id=dev)
-    lib = cabi.lib()
-    cabi.check(lib.lcc_set_device(local))
+        from largecrimsoncanine_b200 import cabi, sharded
 
-    wl = args.workload
-    sig, dt, log2n, bytes_per, unit = WORKLOADS[wl]
-    if args.log2_rows:
-        log2n = args.log2_rows
-    n = 1 << log2n
+        self.torch, self.cabi, self.args = torch, cabi, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the batched path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.dist = None
+        if self.world > 1:
+            # the only collective of the path is a 16..256-element all-reduce: one channel (one CTA) is enough, and every
+            # extra NCCL CTA spin-waiting for a slower rank takes SM slots away from the streaming kernel it overlaps with
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", "1")
+            os.environ.setdefault("NCCL_MAX_CTAS", "1")
+            dist.init_process_group("nccl", device_id=self.dev)  # plumbing only: barriers and the max-over-ranks of the timings
+            self.dist = dist
+        self.lib = cabi.lib()
+        cabi.check(self.lib.lcc_set_device(self.local))
+        # the native shard group (csrc/shard_group.cu): its compute stream is the launching stream of every workload, its
+        # NCCL communicator carries the one collective of the path.  torch events are recorded on that same stream.
+        self.group = sharded.ShardGroup.from_env(device=self.local)
+        self.stream = torch.cuda.ExternalStream(self.group.stream(0), device=self.dev)
+        torch.cuda.set_stream(self.stream)
+        self.sptr = C.c_void_p(self.group.stream(0))
+        self.flags = cabi.LCC_FLAG_STRICT_FP if args.strict else 0
+        self.gen = torch.Generator(device=self.dev)
+        self.gen.manual_seed(42 + self.rank)
+        self._algs = {}
+
+    def alg(self, sig):
+        if sig not in self._algs:
+            self._algs[sig] = self.cabi.Algebra(*sig)
+        return self._algs[sig]
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if not self.dist:
+            return v
+        t = self.torch.tensor([v], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def close(self):
+        self.group.close()
+        if self.dist:
+            self.dist.destroy_process_group()
+
+
+def setup_workload(ctx, wl, n, layout="soa", collective=True, ld_pad=0):
+    """Allocate the synthetic inputs of `wl` (n rows on this rank) and return (step, drain, parity, keepalive)."""
+    torch, cabi, lib, dev, gen, sptr, flags = ctx.torch, ctx.cabi, ctx.lib, ctx.dev, ctx.gen, ctx.sptr, ctx.flags
+    sig, dt, _, bytes_per, unit = WORKLOADS[wl]
     tdt = torch.float32 if dt == "f32" else torch.float64
     code = cabi.LCC_F32 if dt == "f32" else cabi.LCC_F64
-    alg = cabi.Algebra(*sig)
+    alg = ctx.alg(sig)
     nb = alg.num_blades
-    flags = cabi.LCC_FLAG_STRICT_FP if args.strict else 0
-    # a dedicated non-default stream: its handle is non-zero (NULL would mean "the library's own stream"),
-    # kernels are launched on it and the CUDA events below are recorded on it
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    sptr = C.c_void_p(stream.cuda_stream)
-    assert stream.cuda_stream != 0
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(42 + rank)
-
-    aos_layout = args.layout == "aos"
-    if aos_layout and wl not in ("pga_sandwich", "cga_gp", "r3_gp", "cga_gp_outer"):
+    aos_layout = layout == "aos"
+    if aos_layout and wl not in ("pga_sandwich", "pga_sandwich_dense16", "cga_gp", "r3_gp", "cga_gp_outer"):
         raise SystemExit("--layout aos is available for pga_sandwich, cga_gp, cga_gp_outer and r3_gp")
 
     def soa(t):  # torch (nb, n) tensor == engine-native SoA view with ld = n
@@ -281,8 +322,8 @@ def run_gpu_arm(args):
             return cabi.view(t.data_ptr(), t.shape[0], t.stride(0), code, cabi.LCC_AOS)
         return cabi.view(t.data_ptr(), t.shape[1], t.stride(0), code, cabi.LCC_SOA)
 
-    def soa_alloc(fill_random):  # (nb, n) blade-major view whose blade rows are n + --ld-pad elements apart
-        t = torch.empty((nb, n + args.ld_pad), device=dev, dtype=tdt)
+    def soa_alloc(fill_random):  # (nb, n) blade-major view whose blade rows are n + ld_pad elements apart
+        t = torch.empty((nb, n + ld_pad), device=dev, dtype=tdt)
         if fill_random:
             t.normal_(generator=gen)
         else:
@@ -296,81 +337,134 @@ def run_gpu_arm(args):
     def rows_of(t, idx):  # (len(idx), nb) host array of the selected rows
         return (t[idx] if aos_layout else t[:, idx].T).contiguous().cpu().numpy()
 
-    motor = None
+    import oracle
 
-    def drain():  # workloads with asynchronous collectives override this
+    o = oracle.OracleAlgebra(*sig)
+    span = min(4096, max(1, n // 3))
+    idx = torch.cat([torch.arange(0, span), torch.arange(n // 2, n // 2 + span), torch.arange(n - span, n)]).to(dev)
+    tol = 1e-5 if dt == "f32" else 1e-12
+    keep = {}
+
+    def drain():
         pass
 
-    if wl == "pga_sandwich":
-        x = soa_alloc(False)
-        pts = torch.randn((3, n), device=dev, dtype=tdt, generator=gen)
-        x[7].fill_(1.0)
-        x[14].copy_(-pts[0]); x[13].copy_(pts[1]); x[11].copy_(-pts[2])
-        del pts
+    def finish(got, want, rows):
+        err = float(np.abs(got.astype(np.float64) - want.astype(np.float64)).max() / np.abs(want).max())
+        return {"rows_checked": int(rows), "max_rel_err": err, "tolerance": tol, "ok": bool(err <= tol)}
+
+    if wl in ("pga_sandwich", "pga_sandwich_dense16"):
+        if wl == "pga_sandwich":
+            x = soa_alloc(False)
+            pts = torch.randn((3, n), device=dev, dtype=tdt, generator=gen)
+            x[7].fill_(1.0)
+            x[14].copy_(-pts[0]); x[13].copy_(pts[1]); x[11].copy_(-pts[2])
+            del pts
+        else:  # every one of the 16 blade rows is dense random data (SURVEY 8d asks for both variants)
+            x = soa_alloc(True)
         if aos_layout:
             x = x.T.contiguous()
         out = torch.empty_like(x) if aos_layout else soa_alloc(False)
         motor = headline_motor()
         mptr = motor.ctypes.data_as(C.POINTER(C.c_double))
         vx, vo = soa(x), soa(out)
+        keep.update(x=x, out=out, motor=motor)
 
         def step():
             cabi.check(lib.lcc_batch_sandwich(alg.h, mptr, C.byref(vx), C.byref(vo), flags, sptr))
+
+        def parity():
+            return finish(rows_of(out, idx), o.sandwich(motor, rows_of(x, idx)), idx.numel())
     elif wl == "pga_points_compact":
         x = torch.randn((n, 3), device=dev, dtype=tdt, generator=gen)
         out = torch.empty_like(x)
         motor = headline_motor()
         mptr = motor.ctypes.data_as(C.POINTER(C.c_double))
+        keep.update(x=x, out=out, motor=motor)
 
         def step():
             cabi.check(lib.lcc_pga_points_sandwich(alg.h, code, mptr, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), n, flags, sptr))
+
+        def parity():
+            return finish(out[idx].cpu().numpy(), oracle.pga_transform_points(motor, x[idx].cpu().numpy()), idx.numel())
     elif wl in ("cga_gp", "r3_gp", "cga_gp_outer"):
         a = randn_batch()
         b = randn_batch()
         out = torch.empty_like(a) if aos_layout else soa_alloc(False)
         va, vb, vo = soa(a), soa(b), soa(out)
+        keep.update(a=a, b=b, out=out)
         if wl == "cga_gp_outer":
             out2 = torch.empty_like(a) if aos_layout else soa_alloc(False)
             vo2 = soa(out2)
+            keep.update(out2=out2)
 
             def step():
                 cabi.check(lib.lcc_batch_gp_outer(alg.h, C.byref(va), C.byref(vb), C.byref(vo), C.byref(vo2), flags, sptr))
         else:
             def step():
                 cabi.check(lib.lcc_batch_product(alg.h, cabi.LCC_OP_GP, C.byref(va), C.byref(vb), C.byref(vo), flags, sptr))
+
+        def parity():
+            xs, ys = rows_of(a, idx), rows_of(b, idx)
+            res = finish(rows_of(out, idx), o.geometric_product(xs, ys), idx.numel())
+            if wl == "cga_gp_outer":
+                second = finish(rows_of(out2, idx), o.outer_product(xs, ys), idx.numel())
+                res["max_rel_err"] = max(res["max_rel_err"], second["max_rel_err"])
+                res["ok"] = res["ok"] and second["ok"]
+            return res
     elif wl == "sta_fused_grade_inner_sum":
         a = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
         b = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
-        # the per-GPU partial (16 values) is all-reduced asynchronously on NCCL's stream into a small ring of
-        # result buffers, so the collective of step i overlaps the kernel of step i+1 instead of serialising with it
-        ring = [torch.zeros(nb, device=dev, dtype=tdt) for _ in range(4)]
-        pending = [None] * len(ring)
+        keep.update(a=a, b=b)
+        grp = ctx.group
+        views_a, views_b = grp.views(), grp.views()
+        views_a[0], views_b[0] = soa(a), soa(b)
         turn = [0]
-        sums = ring[0]
-        out = None
-        va, vb = soa(a), soa(b)
+        # BASELINE config 4, fused: per step ONE kernel reads <x>_1 and w and leaves 16 partial sums in a slot of the
+        # group's ring; the NCCL all-reduce of that slot is enqueued behind it on the group's high-priority
+        # communication stream (lcc_shard_product_sum_async), so the collective of step i overlaps the kernel of step
+        # i+1.  Every all-reduce is fetched (drain) inside the timed region.  collective=False: the same kernel alone.
+        if collective:
+            def step():
+                cabi.check(lib.lcc_shard_product_sum_async(grp.h, alg.h, cabi.LCC_OP_LC, views_a, 1, views_b, 0, turn[0] % 8, flags))
+                turn[0] += 1
 
-        def step():
-            i = turn[0] % len(ring)
-            turn[0] += 1
-            if pending[i] is not None:
-                pending[i].wait()  # the buffer's previous all-reduce (four steps ago) has completed
-            cabi.check(lib.lcc_batch_product_sum(alg.h, cabi.LCC_OP_LC, C.byref(va), 1, C.byref(vb), C.c_void_p(ring[i].data_ptr()), flags, sptr))
-            if world > 1:
-                pending[i] = dist.all_reduce(ring[i], async_op=True)
+            res_host = np.empty(nb, np.float32 if dt == "f32" else np.float64)
 
-        def drain():
-            for h in pending:
-                if h is not None:
-                    h.wait()
+            def drain():
+                for slot in range(min(turn[0], 8)):
+                    cabi.check(lib.lcc_shard_reduce_fetch(grp.h, alg.h, code, slot, res_host.ctypes.data))
+        else:
+            sums = torch.zeros(nb, device=dev, dtype=tdt)
+            keep.update(sums=sums)
+
+            def step():
+                cabi.check(lib.lcc_batch_product_sum(alg.h, cabi.LCC_OP_LC, C.byref(views_a[0]), 1, C.byref(views_b[0]), C.c_void_p(sums.data_ptr()), flags, sptr))
+
+        def parity():
+            m = min(n, 1 << 20)  # the fused kernel only returns sums: re-run it on the first 2^20 rows and compare with the oracle
+            sa, sb = cabi.view(a.data_ptr(), m, a.stride(0), code, cabi.LCC_SOA), cabi.view(b.data_ptr(), m, b.stride(0), code, cabi.LCC_SOA)
+            chk = torch.zeros(nb, device=dev, dtype=tdt)
+            cabi.check(lib.lcc_batch_product_sum(alg.h, cabi.LCC_OP_LC, C.byref(sa), 1, C.byref(sb), C.c_void_p(chk.data_ptr()), flags, sptr))
+            torch.cuda.synchronize()
+            xs, ys = a[:, :m].T.contiguous().cpu().numpy(), b[:, :m].T.contiguous().cpu().numpy()
+            want, mag = o.sum(o.left_contraction(o.grade(xs, 1), ys))
+            scale = np.abs(mag).max() / np.maximum(mag, 1e-300)  # compare on the scale of the summed magnitudes
+            return finish(chk.cpu().numpy() * scale, want * scale, m)
     elif wl in ("cl8_fixed_gp", "cl8_fixed_gp_f64"):
         b = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
         a = torch.randn((nb, 4), device=dev, dtype=tdt, generator=gen)  # the fixed operand: one-row SoA view, ld = 4
         out = torch.empty_like(b)
         va, vb, vo = cabi.view(a.data_ptr(), 1, 4, code, cabi.LCC_SOA), soa(b), soa(out)
+        keep.update(a=a, b=b, out=out)
 
         def step():
             cabi.check(lib.lcc_batch_product(alg.h, cabi.LCC_OP_GP, C.byref(va), C.byref(vb), C.byref(vo), flags, sptr))
+
+        def parity():
+            sub = idx[::64]
+            ys = b[:, sub].T.contiguous().cpu().numpy().astype(np.float64)
+            want = o.geometric_product(a[:, 0].cpu().numpy().astype(np.float64)[None, :], ys)
+            return finish(out[:, sub].T.contiguous().cpu().numpy(), want, sub.numel())
     elif wl == "sta_grade_inner_sum":
         a = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
         b = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
@@ -378,131 +472,199 @@ def run_gpu_arm(args):
         out = torch.empty_like(a)
         sums = torch.zeros(nb, device=dev, dtype=tdt)
         va, vb, vg, vo = soa(a), soa(b), soa(g1), soa(out)
+        keep.update(a=a, b=b, g1=g1, out=out, sums=sums)
 
         def step():
             cabi.check(lib.lcc_batch_unary(alg.h, cabi.LCC_UN_GRADE, 1, C.byref(va), C.byref(vg), sptr))
             cabi.check(lib.lcc_batch_product(alg.h, cabi.LCC_OP_LC, C.byref(vg), C.byref(vb), C.byref(vo), flags, sptr))
             cabi.check(lib.lcc_batch_sum(alg.h, C.byref(vo), C.c_void_p(sums.data_ptr()), sptr))
-            if world > 1:
-                dist.all_reduce(sums)  # the one collective of the path: 16 elements over NCCL
+
+        def parity():
+            xs, ys = a[:, idx].T.contiguous().cpu().numpy(), b[:, idx].T.contiguous().cpu().numpy()
+            return finish(out[:, idx].T.contiguous().cpu().numpy(), o.left_contraction(o.grade(xs, 1), ys), idx.numel())
     else:
         raise SystemExit(f"unknown workload {wl}")
+    return step, drain, parity, keep
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    drain()
-    barrier()
-    lib.lcc_kernel_launch_count_reset()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
-        barrier()
-        e0.record(stream)
-        for _ in range(args.steps):
+def measure(ctx, wl, n, steps, warmup, layout="soa", collective=True, parity=True, solo=False, ld_pad=0):
+    """W warm-up steps, then exactly K timed steps bracketed by barrier + synchronize; CUDA events on the launching
+    stream around every step (mean = the contract's ms_per_step, min / median beside it); max over ranks.
+    solo=True: only rank 0 runs (the other ranks idle at the barriers) -- the N = 1 figure measured inside an N > 1 job."""
+    torch = ctx.torch
+    active = (not solo) or ctx.rank == 0
+    step, drain, parity_fn, keep = setup_workload(ctx, wl, n, layout, collective, ld_pad) if active else (None, None, None, {})
+    if active:
+        for _ in range(max(warmup, 3)):
             step()
-        drain()  # every outstanding all-reduce is inside the timed region
-        e1.record(stream)
-        barrier()
-    launches = int(lib.lcc_kernel_launch_count())
-    elapsed_ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-    ms_per_step = elapsed_ms / args.steps
-    value = world * n / (ms_per_step / 1e3)
+        drain()
+    ctx.barrier()
+    ctx.lib.lcc_kernel_launch_count_reset()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    with ClockSampler(ctx.local) as clocks:
+        ctx.barrier()
+        if active:
+            ev[0].record(ctx.stream)
+            for i in range(steps):
+                step()
+                if i + 1 < steps:
+                    ev[i + 1].record(ctx.stream)
+            drain()  # every outstanding all-reduce is inside the timed region
+            ev[steps].record(ctx.stream)
+        ctx.barrier()
+    launches = int(ctx.lib.lcc_kernel_launch_count())
+    if active:
+        total_ms = ev[0].elapsed_time(ev[steps])
+        per = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+    else:
+        total_ms, per = 0.0, [0.0]
+    if not solo:
+        total_ms = ctx.max_over_ranks(total_ms)
+    rec = {"ms_per_step": total_ms / steps, "ms_min": float(np.min(per)), "ms_median": float(np.median(per)), "steps": steps,
+           "gpu_launches": launches, "clocks": clocks.summary()}
+    rec["parity"] = parity_fn() if (parity and active and ctx.rank == 0) else None
+    return rec, keep
 
-    # ---- parity spot check against the oracle on sampled rows (outside every timed region)
-    parity = None
-    if rank == 0 and not args.no_parity:
-        import oracle
 
-        o = oracle.OracleAlgebra(*sig)
-        idx = torch.cat([torch.arange(0, 4096), torch.arange(n // 2, n // 2 + 4096), torch.arange(n - 4096, n)]).to(dev)
-        tol = 1e-5 if dt == "f32" else 1e-12
-        if wl == "pga_sandwich":
-            xs = rows_of(x, idx)
-            got = rows_of(out, idx)
-            want = o.sandwich(motor, xs)
-        elif wl == "pga_points_compact":
-            xs, got = x[idx].cpu().numpy(), out[idx].cpu().numpy()
-            want = oracle.pga_transform_points(motor, xs)
-        elif wl == "sta_fused_grade_inner_sum":
-            m = 1 << 20  # the fused kernel only returns the sums: re-run it on the first 2^20 rows and compare with the oracle
-            sa, sb = cabi.view(a.data_ptr(), m, a.stride(0), code, cabi.LCC_SOA), cabi.view(b.data_ptr(), m, b.stride(0), code, cabi.LCC_SOA)
-            chk = torch.zeros(nb, device=dev, dtype=tdt)
-            cabi.check(lib.lcc_batch_product_sum(alg.h, cabi.LCC_OP_LC, C.byref(sa), 1, C.byref(sb), C.c_void_p(chk.data_ptr()), flags, sptr))
-            torch.cuda.synchronize()
-            xs, ys = a[:, :m].T.contiguous().cpu().numpy(), b[:, :m].T.contiguous().cpu().numpy()
-            prod = o.left_contraction(o.grade(xs, 1), ys)
-            want, mag = o.sum(prod)
-            got = chk.cpu().numpy()
-            want = want / np.maximum(mag, 1e-300) * np.abs(mag).max()  # compare on the scale of the summed magnitudes
-            got = got / np.maximum(mag, 1e-300) * np.abs(mag).max()
-        elif wl == "sta_grade_inner_sum":
-            xs, ys = a[:, idx].T.contiguous().cpu().numpy(), b[:, idx].T.contiguous().cpu().numpy()
-            got = out[:, idx].T.contiguous().cpu().numpy()
-            want = o.left_contraction(o.grade(xs, 1), ys)
-        elif wl in ("cl8_fixed_gp", "cl8_fixed_gp_f64"):
-            idx = idx[::64]
-            ys = b[:, idx].T.contiguous().cpu().numpy().astype(np.float64)
-            got = out[:, idx].T.contiguous().cpu().numpy()
-            want = o.geometric_product(a[:, 0].cpu().numpy().astype(np.float64)[None, :], ys)
-        else:
-            xs, ys = rows_of(a, idx), rows_of(b, idx)
-            got = rows_of(out, idx)
-            want = o.geometric_product(xs, ys)
-        err = float(np.abs(got.astype(np.float64) - want.astype(np.float64)).max() / np.abs(want).max())
-        parity = {"rows_checked": int(idx.numel()), "max_rel_err": err, "tolerance": tol, "ok": bool(err <= tol)}
+def release(ctx, keep):
+    keep.clear()
+    ctx.torch.cuda.synchronize()
+    ctx.torch.cuda.empty_cache()
 
-    # ---- end to end through the C-ABI host-buffer entry point (headline workload only)
-    e2e = None
-    if wl == "pga_sandwich" and not args.no_e2e:
-        e2e = measure_e2e(args, lib, alg, code, motor, n, nb, world, rank, dev, dist if world > 1 else None, flags)
-    elif wl == "pga_points_compact" and not args.no_e2e:
-        e2e = measure_e2e(args, lib, alg, code, motor, n, nb, world, rank, dev, dist if world > 1 else None, flags, compact=True)
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
-
-    peaks, peak_kind = load_peaks()
-    kernel_ms = ms_per_step  # one kernel per step for the headline; the step IS the kernel
-    traffic = None
+def traffic_of(wl):
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(wl)
+            return json.load(f).get(wl)
     except Exception:
-        pass
+        return None
+
+
+def config_block(wl, n):
+    """The workload definition -- identical for the GPU arm and the --impl reference arm (same_config)."""
+    _, _, log2n, bytes_per, _ = WORKLOADS[wl]
+    return {"workload": workload_name(wl, n), "rows_per_gpu": n, "l2_policy": l2_policy(bytes_per * n)}
+
+
+def secondary_record(ctx, wl, steps, peaks, peak_kind, n=None, layout="soa"):
+    sig, dt, log2n, bytes_per, unit = WORKLOADS[wl]
+    n = n or (1 << log2n)
+    rec, keep = measure(ctx, wl, n, steps, 3, layout)
+    release(ctx, keep)
+    if ctx.rank != 0:
+        return None
+    out = {"workload": wl, "config": config_block(wl, n), "layout": layout, "dtype": dt, "unit": unit, "n_gpus": ctx.world,
+           "value": ctx.world * n / (rec["ms_per_step"] / 1e3),
+           "roofline": roofline_block(wl, n, rec["ms_per_step"], bytes_per, peaks, peak_kind, traffic_of(wl))}
+    out.update(rec)
+    return out
+
+
+def run_gpu_arm(args):
+    ctx = Ctx(args)
+    torch, cabi, lib, rank, world = ctx.torch, ctx.cabi, ctx.lib, ctx.rank, ctx.world
+    wl = args.workload
+    sig, dt, log2n, bytes_per, unit = WORKLOADS[wl]
+    if args.log2_rows:
+        log2n = args.log2_rows
+    n = 1 << log2n
+    code = cabi.LCC_F32 if dt == "f32" else cabi.LCC_F64
+    alg = ctx.alg(sig)
+    nb = alg.num_blades
+    peaks, peak_kind = load_peaks()
+
+    rec, keep = measure(ctx, wl, n, args.steps, args.warmup, args.layout, parity=not args.no_parity, ld_pad=args.ld_pad)
+    ms_per_step = rec["ms_per_step"]
+    value = world * n / (ms_per_step / 1e3)
+    motor = keep.get("motor")
+    release(ctx, keep)
+
+    # ---- end to end through the drop-in Python API / the C-ABI host-buffer entry points (headline workload only)
+    e2e = None
+    if wl == "pga_sandwich" and not args.no_e2e:
+        e2e = measure_e2e(args, lib, alg, code, motor, n, nb, world, rank, ctx.dev, ctx.dist, ctx.flags)
+    elif wl == "pga_points_compact" and not args.no_e2e:
+        e2e = measure_e2e(args, lib, alg, code, motor, n, nb, world, rank, ctx.dev, ctx.dist, ctx.flags, compact=True)
+    if e2e is not None:
+        import largecrimsoncanine as L
+
+        L.host_cache_trim()
+
+    # ---- the default line also carries: the collective-bearing config (4, fused) with its all-reduce, config 2 sharded
+    # strongly (2^28 points in total), and the other BASELINE configs at full size on this rank's GPU
+    collective = strong = None
+    secondary = []
+    if wl == HEADLINE and not args.no_secondary and not args.log2_rows:
+        k = max(3, min(args.steps, 10))
+        cw = "sta_fused_grade_inner_sum"
+        cn = 1 << WORKLOADS[cw][2]
+        crec, ckeep = measure(ctx, cw, cn, k, 3, collective=True)
+        release(ctx, ckeep)
+        collective = {"workload": workload_name(cw, cn), "rows_per_gpu": cn, "n_gpus": world, "scaling": "weak",
+                      "api": "lcc_shard_product_sum_async + lcc_shard_reduce_fetch (native group: fused partial -> ncclAllReduce(16 x f64) "
+                             "on a high-priority stream, every all-reduce inside the timed region)",
+                      "value": world * cn / (crec["ms_per_step"] / 1e3), "unit": WORKLOADS[cw][4], "nccl_version": int(lib.lcc_shard_nccl_version())}
+        collective.update(crec)
+        if world > 1:
+            nrec, nkeep = measure(ctx, cw, cn, k, 3, collective=False, parity=False)
+            release(ctx, nkeep)
+            srec, skeep = measure(ctx, cw, cn, k, 3, collective=False, parity=False, solo=True)
+            release(ctx, skeep)
+            collective.update(ms_per_step_without_collective=nrec["ms_per_step"], ms_per_step_one_gpu_alone=srec["ms_per_step"],
+                              efficiency_vs_one_gpu_alone=srec["ms_per_step"] / crec["ms_per_step"] if rank == 0 else None,
+                              note="one_gpu_alone: rank 0 runs the same kernel while the other GPUs of the box idle, measured in this same job")
+        sn = (1 << WORKLOADS[HEADLINE][2]) // world
+        srec2, skeep2 = measure(ctx, HEADLINE, sn, k, 3, parity=True)
+        release(ctx, skeep2)
+        strong = {"workload": workload_name(HEADLINE, sn), "rows_total": sn * world, "rows_per_gpu": sn, "n_gpus": world, "scaling": "strong",
+                  "value": world * sn / (srec2["ms_per_step"] / 1e3), "unit": unit,
+                  "roofline_per_gpu": roofline_block(HEADLINE, sn, srec2["ms_per_step"], bytes_per, peaks, peak_kind, None)}
+        strong.update(srec2)
+        for swl, slayout in (("r3_gp", "soa"), ("cga_gp_outer", "soa"), ("cga_gp", "aos"), ("sta_grade_inner_sum", "soa"), ("cl8_fixed_gp", "soa"),
+                             ("cl8_fixed_gp_f64", "soa"), ("pga_sandwich_dense16", "soa"), ("pga_sandwich", "aos")):
+            try:
+                r = secondary_record(ctx, swl, k, peaks, peak_kind, layout=slayout)
+            except Exception as exc:  # one workload failing must not take the headline line down
+                r = {"workload": swl, "error": f"{type(exc).__name__}: {exc}"} if rank == 0 else None
+            if r:
+                secondary.append(r)
+
+    if rank != 0:
+        ctx.close()
+        return 0
+
     cpu = None
     if not args.no_cpu and world == 1:  # CPU baseline on rank 0 at N = 1 only
         rows = cpu_sample_rows(wl)
         rate1, t1 = cpu_rate(wl, rows, 1)
-        import oracle
-
-        cores = oracle.max_threads()
+        cores = host_cores()
         rate_all, _ = cpu_rate(wl, rows, cores) if cores > 1 else (rate1, t1)
         cpu = {"value": rate1, "unit": unit, "cores": 1, "kind": "port",
                "sample": f"{rows} rows of the same synthetic workload ({t1:.1f} s); the reference is single-threaded",
                "all_cores_value": rate_all, "all_cores": cores}
+    aos_layout = args.layout == "aos"
     line = {
         "metric": f"{wl} throughput", "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "ms_min": rec["ms_min"], "ms_median": rec["ms_median"],
+        "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": dt, "data": "synthetic",
-        "config": {"workload": workload_name(wl), "rows_per_gpu": n, "layout": "dense (N,3) xyz rows" if wl == "pga_points_compact" else ("AoS (N, num_blades) row-major in HBM, TMA-staged tiles" if aos_layout else "SoA (blade-major) in HBM"),
-                   "l2_policy": l2_policy(bytes_per * n), "strict_fp": bool(args.strict)},
-        "roofline": roofline_block(wl, n, kernel_ms, bytes_per, peaks, peak_kind, traffic),
-        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(), "parity": parity,
+        "config": config_block(wl, n),
+        "impl_config": {"layout": "dense (N,3) xyz rows" if wl == "pga_points_compact" else ("AoS (N, num_blades) row-major in HBM, TMA-staged tiles" if aos_layout else "SoA (blade-major) in HBM"),
+                        "strict_fp": bool(args.strict), "launch_stream": "compute stream of the native shard group (lcc_shard_group_stream)"},
+        "roofline": roofline_block(wl, n, ms_per_step, bytes_per, peaks, peak_kind, traffic_of(wl)),
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": rec["gpu_launches"], "clocks": rec["clocks"], "parity": rec["parity"],
+        "collective": collective, "strong": strong, "secondary": secondary,
     }
     emit_line(line)
-    if world > 1:
-        dist.destroy_process_group()
+    ctx.close()
     return 0
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 def l2_policy(bytes_per_pass):
@@ -513,25 +675,42 @@ def l2_policy(bytes_per_pass):
             "CPU-runnable case and is reported for completeness; use --log2-rows 26 for the HBM-bound figure")
 
 
+def local_peaks():
+    """profiles/peaks_local.json: cuBLAS TF32 / FP64 GEMM peaks micro-benchmarked on a B200 of this pool with
+    scripts/measure_peaks.py (MEASURED_PEAKS.json carries only the bf16 figure and the copy bandwidth)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "peaks_local.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def roofline_block(wl, n, kernel_ms, bytes_per, peaks, peak_kind, traffic):
     hbm = bytes_per * n / (kernel_ms / 1e3) / 1e9
-    if wl == "cl8_fixed_gp_f64":  # FP64 tensor pipe: no measured figure in MEASURED_PEAKS.json, nominal B200 FP64 = 40 TFLOP/s
+    hbm_peak = float(peaks["hbm_gbs"])
+    if wl in TENSOR_FLOPS_PER_UNIT:
+        # dense contraction.  `achieved` counts the flops of the multiplication-matrix GEMM the north_star names
+        # (2 * nb^2 per row; x3 for the 3xTF32 split), whatever algorithm the kernel actually runs; the HBM figures beside
+        # it say how far the kernel is from the streaming floor of the same rows.
         tf = TENSOR_FLOPS_PER_UNIT[wl] * n / (kernel_ms / 1e3) / 1e12
-        return {"bound": "tensor", "achieved": tf, "peak": 40.0, "unit": "TFLOP/s", "frac": tf / 40.0, "traffic": traffic,
-                "peak_source": "nominal B200 FP64 tensor rate (40 TFLOP/s); MEASURED_PEAKS.json has no FP64 figure",
-                "tensor_flops_per_unit": TENSOR_FLOPS_PER_UNIT[wl], "hbm_gbs": hbm, "hbm_frac": hbm / float(peaks["hbm_gbs"]),
-                "algorithmic_bytes_per_unit": bytes_per}
-    if wl in TENSOR_FLOPS_PER_UNIT:  # dense contraction: tensor-pipe bound; nominal dense tf32 peak is half the bf16 one
-        tf = TENSOR_FLOPS_PER_UNIT[wl] * n / (kernel_ms / 1e3) / 1e12
-        peak_tf32 = float(peaks.get("bf16_tflops", 1590.0)) / 2.0
-        sustained = float(peaks.get("bf16_tflops_sustained", 0.0)) / 2.0
-        return {"bound": "tensor", "achieved": tf, "peak": peak_tf32, "unit": "TFLOP/s", "frac": tf / peak_tf32, "traffic": traffic,
-                "peak_source": f"{peak_kind} bf16_tflops / 2 (burst figure; tf32 runs at half the bf16 rate; no direct tf32 measurement)",
-                "peak_sustained": sustained or None, "frac_of_sustained": (tf / sustained) if sustained else None,
-                "tensor_flops_per_unit": TENSOR_FLOPS_PER_UNIT[wl], "useful_tflops": tf / 3.0,
-                "hbm_gbs": hbm, "hbm_frac": hbm / float(peaks["hbm_gbs"]), "algorithmic_bytes_per_unit": bytes_per}
-    peak = float(peaks["hbm_gbs"])
-    return {"bound": "hbm", "achieved": hbm, "peak": peak, "unit": "GB/s", "frac": hbm / peak, "traffic": traffic,
+        lp = local_peaks()
+        key = "fp64" if wl == "cl8_fixed_gp_f64" else "tf32"
+        if lp and key in lp:
+            peak, sustained = float(lp[key]["burst_tflops"]), float(lp[key]["sustained_tflops"])
+            src = f"profiles/peaks_local.json: cuBLAS {key} GEMM 8192^3 measured with scripts/measure_peaks.py (burst; sustained beside it)"
+        elif key == "fp64":
+            peak, sustained, src = 40.0, None, "nominal B200 FP64 tensor rate (40 TFLOP/s); no measured figure available"
+        else:
+            peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0
+            sustained = float(peaks.get("bf16_tflops_sustained", 0.0)) / 2.0 or None
+            src = f"{peak_kind} bf16_tflops / 2 (tf32 runs at half the bf16 rate; no direct tf32 measurement available)"
+        return {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": traffic,
+                "traffic_source": TRAFFIC_SOURCE if traffic else None, "peak_source": src,
+                "peak_sustained": sustained, "frac_of_sustained": (tf / sustained) if sustained else None,
+                "tensor_flops_per_unit": TENSOR_FLOPS_PER_UNIT[wl], "useful_tflops": tf / 3.0 if key == "tf32" else tf,
+                "hbm_gbs": hbm, "hbm_frac": hbm / hbm_peak, "algorithmic_bytes_per_unit": bytes_per}
+    return {"bound": "hbm", "achieved": hbm, "peak": hbm_peak, "unit": "GB/s", "frac": hbm / hbm_peak, "traffic": traffic,
+            "traffic_source": TRAFFIC_SOURCE if traffic else None,
             "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)", "algorithmic_bytes_per_unit": bytes_per,
             "frac_of_nominal_8TBs": hbm / 8000.0}
 
@@ -550,8 +729,15 @@ def bind_to_gpu_numa_node(local):
 
 
 def measure_e2e(args, lib, alg, code, motor, n, nb, world, rank, dev, dist, flags, compact=False):
-    """lcc_host_sandwich on pinned host buffers in the reference's (N, 16) row-major layout; with `compact`,
-    lcc_host_pga_points_sandwich on pinned (N, 3) xyz buffers (the pga_points_compact workload)."""
+    """End to end from HOST arrays in the reference's (N, 16) row-major layout, copies inside the timed region.
+
+    value = the reference's own call sequence through the drop-in Python API,
+            MultivectorBatch.from_numpy(alg, x).sandwich(M).to_numpy()            (src/batch.rs:79-94,434-503,233-235)
+            on a pinned NumPy array.  Its upload and download cannot overlap (each call must finish before the next
+            starts), so it is bounded by one PCIe direction at a time.
+    variants: the same sequence on a PAGEABLE array; the fused one-call form MultivectorBatch.sandwich_numpy (both PCIe
+            directions busy at once); and the C-ABI entry point lcc_host_sandwich it maps to.
+    With `compact`, lcc_host_pga_points_sandwich on pinned (N, 3) xyz buffers (the pga_points_compact workload)."""
     import psutil
     import torch
 
@@ -562,51 +748,98 @@ def measure_e2e(args, lib, alg, code, motor, n, nb, world, rank, dev, dist, flag
     es = 4 if code == cabi.LCC_F32 else 8
     if compact:
         return measure_e2e_compact(args, lib, alg, code, motor, n, es, world, rank, dev, dist, flags, numa_bound)
+    import largecrimsoncanine as L
+
     n_e2e = n
-    need = 2 * n_e2e * nb * es * max(world, 1)
+    copies = 3 if world == 1 else 2  # pinned in, pinned out (+ one pageable input at N = 1)
+    need = copies * n_e2e * nb * es * max(world, 1)
     avail = psutil.virtual_memory().available
     while need > 0.5 * avail and n_e2e > (1 << 20):
         n_e2e //= 2
         need //= 2
-    tdt = torch.float32 if es == 4 else torch.float64
-    xh = torch.empty((n_e2e, nb), dtype=tdt, pin_memory=True)
-    oh = torch.empty((n_e2e, nb), dtype=tdt, pin_memory=True)
-    xh.zero_()
-    g = torch.Generator().manual_seed(7 + rank)
+    ndt = np.float32 if es == 4 else np.float64
+    L.set_device(dev.index or 0)
+    palg = L.Algebra(3, 0, 1)
+    pmotor = L.Multivector.from_list_in([float(v) for v in motor], palg)
+    xh = L.pinned_empty((n_e2e, nb), ndt)
+    oh = L.pinned_empty((n_e2e, nb), ndt)
+    g = np.random.default_rng(7 + rank)
     blk = 1 << 22
     for s in range(0, n_e2e, blk):  # fill in blocks: (N,3) normals embedded as PGA points
         e = min(n_e2e, s + blk)
-        p = torch.randn((e - s, 3), dtype=tdt, generator=g)
+        p = g.standard_normal((e - s, 3)).astype(ndt)
+        xh[s:e] = 0
         xh[s:e, 7] = 1.0
         xh[s:e, 14], xh[s:e, 13], xh[s:e, 11] = -p[:, 0], p[:, 1], -p[:, 2]
     mptr = motor.ctypes.data_as(C.POINTER(C.c_double))
+    if flags:
+        L.set_strict_fp(True)
 
-    def call():
-        cabi.check(lib.lcc_host_sandwich(alg.h, code, mptr, C.c_void_p(xh.data_ptr()), C.c_void_p(oh.data_ptr()), n_e2e, flags))
+    def three_call(x):
+        return L.MultivectorBatch.from_numpy(palg, x).sandwich(pmotor).to_numpy()
 
-    steps = max(1, min(args.steps, args.e2e_steps))
-    call()
-    if dist:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        call()
-    torch.cuda.synchronize()
-    dt_s = time.perf_counter() - t0
-    if dist:
-        t = torch.tensor([dt_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt_s = float(t.item())
+    def fused(x):
+        return L.MultivectorBatch.sandwich_numpy(palg, pmotor, x, out=oh)
+
+    def c_abi(x):
+        cabi.check(lib.lcc_host_sandwich(alg.h, code, mptr, C.c_void_p(x.ctypes.data), C.c_void_p(oh.ctypes.data), n_e2e, flags))
+        return oh
+
     import oracle
 
     o = oracle.OracleAlgebra(3, 0, 1)
-    ok = bool(np.abs(oh[:2048].numpy() - o.sandwich(motor, xh[:2048].numpy())).max() <= 1e-4)
-    return {"value": world * n_e2e * steps / dt_s, "unit": "points/s", "h2d_bytes_per_step": n_e2e * nb * es,
-            "d2h_bytes_per_step": n_e2e * nb * es, "points_per_gpu": n_e2e, "steps": steps,
-            "api": "lcc_host_sandwich (C ABI, pinned host buffers, chunked H2D/kernel/D2H pipeline)",
-            "timer": "host wall clock around the blocking call, max over ranks", "checked_against_oracle": ok,
-            "numa_bound": numa_bound}
+    want_head = o.sandwich(motor, xh[:2048])
+    want_tail = o.sandwich(motor, xh[n_e2e - 2048:])
+
+    def timed(fn, x, steps):
+        out = fn(x)  # warm-up: stream-ordered pools, pinned cache, staging buffers
+        ok = bool(np.abs(out[:2048] - want_head).max() <= 1e-4 and np.abs(out[n_e2e - 2048:] - want_tail).max() <= 1e-4)
+        del out
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = fn(x)
+            del out
+        torch.cuda.synchronize()
+        dt_s = time.perf_counter() - t0
+        if dist:
+            t = torch.tensor([dt_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_s = float(t.item())
+        return {"value": world * n_e2e * steps / dt_s, "s_per_step": dt_s / steps, "steps": steps, "checked_against_oracle": ok}
+
+    steps = max(1, min(args.steps, args.e2e_steps))
+    variants = {}
+    plan = [("three_call_pinned", three_call, "pinned", steps), ("fused_pinned", fused, "pinned", steps), ("c_abi_pinned", c_abi, "pinned", steps)]
+    if world == 1:
+        plan += [("three_call_pageable", three_call, "pageable", max(1, steps // 2)), ("fused_pageable", fused, "pageable", max(1, steps // 2))]
+    xp = None
+    for name, fn, kind, k in plan:
+        try:
+            if kind == "pageable" and xp is None:
+                xp = np.empty((n_e2e, nb), ndt)
+                for s in range(0, n_e2e, blk):
+                    xp[s:min(n_e2e, s + blk)] = xh[s:min(n_e2e, s + blk)]
+            variants[name] = timed(fn, xh if kind == "pinned" else xp, k)
+        except Exception as exc:  # a variant that cannot run (host memory) must not take the bench line down
+            variants[name] = {"error": f"{type(exc).__name__}: {exc}"}
+    if flags:
+        L.set_strict_fp(False)
+    head = variants.get("three_call_pinned", {})
+    bytes_step = n_e2e * nb * es
+    return {"value": head.get("value"), "unit": "points/s", "h2d_bytes_per_step": bytes_step, "d2h_bytes_per_step": bytes_step,
+            "points_per_gpu": n_e2e, "steps": head.get("steps"),
+            "api": "largecrimsoncanine.MultivectorBatch.from_numpy(alg, x).sandwich(M).to_numpy() on a pinned NumPy array "
+                   "(the reference's own call sequence; chunked lcc_batch_upload / kernel / lcc_batch_download)",
+            "timer": "host wall clock around the blocking calls, max over ranks",
+            "checked_against_oracle": head.get("checked_against_oracle"), "numa_bound": numa_bound,
+            "host_copy_threads": int(os.environ.get("LCC_HOST_COPY_THREADS", "0")) or None,
+            "variants": variants,
+            "variants_note": "three_call_*: from_numpy -> sandwich -> to_numpy (upload and download are serial by the API's "
+                             "semantics); fused_*: MultivectorBatch.sandwich_numpy (one call, both PCIe directions at once); "
+                             "c_abi_pinned: lcc_host_sandwich, the C-ABI entry point behind sandwich_numpy"}
 
 
 def measure_e2e_compact(args, lib, alg, code, motor, n, es, world, rank, dev, dist, flags, numa_bound):
@@ -688,6 +921,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads / collective / strong records of the default line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

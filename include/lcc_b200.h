@@ -278,6 +278,64 @@ LCC_API lcc_status lcc_host_product(const lcc_algebra *alg, int dtype, int op, c
 LCC_API lcc_status lcc_host_pga_points_sandwich(const lcc_algebra *alg, int dtype, const double *motor, const void *xyz_host_in,
                                                 void *xyz_host_out, int64_t n, unsigned flags);
 
+/* ---------------------------------------------------------------- multi-GPU: row shards + the NCCL sum / mean */
+
+/* Every batched operation is row-independent (`for row in 0..n`, src/batch.rs:384), so N rows are split into
+ * contiguous blocks, shard k of W owning rows [k*N/W, (k+1)*N/W), each resident on its own GPU and driven on its own
+ * non-blocking stream; one-row (broadcast) operands and rotors are replicated.  No data-path collective exists.  The
+ * only exchange is the batch sum / mean (new surface): per-GPU fused partial of num_blades values, then
+ * ncclAllReduce(count = num_blades, ncclSum) enqueued right behind it on the same stream, no host synchronisation in
+ * between; the mean's division runs as a one-block kernel after the all-reduce.
+ *
+ * A group is either all GPUs of ONE process (lcc_shard_group_create: ncclCommInitAll, one host thread issues the
+ * asynchronous launches of every GPU) or one member of a multi-process job with one rank per GPU
+ * (lcc_shard_group_create_rank: ncclCommInitRank; rank 0 makes the 128-byte id with lcc_shard_unique_id and the
+ * launcher distributes it).  Functions taking `views` expect one lcc_view per LOCAL device, in local order.
+ * NCCL is loaded with dlopen on first use; one-device groups never need it. */
+typedef struct lcc_shard_group lcc_shard_group;
+
+LCC_API lcc_status lcc_shard_rows(int64_t n_total, int rank, int world, int64_t *begin, int64_t *end); /* host only */
+LCC_API lcc_status lcc_shard_unique_id(void *id128);
+LCC_API lcc_status lcc_shard_group_create(int ndev, const int *devices /* NULL: 0..ndev-1; ndev <= 0: all */, lcc_shard_group **out);
+LCC_API lcc_status lcc_shard_group_create_rank(int device, int world, int rank, const void *id128, lcc_shard_group **out);
+LCC_API void lcc_shard_group_destroy(lcc_shard_group *group);
+LCC_API int lcc_shard_group_local_size(const lcc_shard_group *group);
+LCC_API int lcc_shard_group_world_size(const lcc_shard_group *group);
+LCC_API int lcc_shard_group_first_rank(const lcc_shard_group *group);
+LCC_API int lcc_shard_group_device(const lcc_shard_group *group, int local_index);
+LCC_API int lcc_shard_nccl_version(void); /* 0 when NCCL could not be loaded */
+LCC_API lcc_status lcc_shard_group_stream(const lcc_shard_group *group, int local_index, void **stream);
+LCC_API lcc_status lcc_shard_group_sync(lcc_shard_group *group);
+/* One engine-native batch per local device holding that shard's rows of an n_total-row batch. */
+LCC_API lcc_status lcc_shard_batch_alloc(lcc_shard_group *group, const lcc_algebra *alg, int dtype, int64_t n_total,
+                                         lcc_view *views, int64_t *row_begin /* may be NULL */);
+/* A one-row (broadcast) operand replicated on every local device from a host row of num_blades elements. */
+LCC_API lcc_status lcc_shard_broadcast_alloc(lcc_shard_group *group, const lcc_algebra *alg, int dtype, const void *host_row, lcc_view *views);
+LCC_API lcc_status lcc_shard_batch_free(lcc_shard_group *group, lcc_view *views);
+/* Host (n_total, num_blades) array <-> the local shards (each GPU runs lcc_batch_upload / download on its own rows,
+ * all local GPUs concurrently). */
+LCC_API lcc_status lcc_shard_upload(lcc_shard_group *group, const lcc_algebra *alg, const void *host, int64_t n_total, const lcc_view *views);
+LCC_API lcc_status lcc_shard_download(lcc_shard_group *group, const lcc_algebra *alg, const lcc_view *views, void *host, int64_t n_total);
+/* Row-wise operations: one asynchronous launch per local GPU on its own stream (lcc_batch_product / _sandwich / _unary). */
+LCC_API lcc_status lcc_shard_product(lcc_shard_group *group, const lcc_algebra *alg, int op, const lcc_view *a, const lcc_view *b,
+                                     const lcc_view *out, unsigned flags);
+LCC_API lcc_status lcc_shard_sandwich(lcc_shard_group *group, const lcc_algebra *alg, const double *rotor, const lcc_view *x,
+                                      const lcc_view *out, unsigned flags);
+LCC_API lcc_status lcc_shard_unary(lcc_shard_group *group, const lcc_algebra *alg, int op, int arg, const lcc_view *x, const lcc_view *out);
+/* The collective: result_host[k] = sum over ALL rows of ALL shards of x[.][k] (num_blades elements of the batch dtype;
+ * may be NULL), divided by mean_divisor when mean_divisor > 0 (pass the global row count for the mean).  Every rank /
+ * local device ends up with the same values.  lcc_shard_product_sum is the fused config-4 form (lcc_batch_product_sum
+ * per GPU, then the all-reduce). */
+LCC_API lcc_status lcc_shard_sum(lcc_shard_group *group, const lcc_algebra *alg, const lcc_view *x, int64_t mean_divisor, void *result_host);
+LCC_API lcc_status lcc_shard_product_sum(lcc_shard_group *group, const lcc_algebra *alg, int op, const lcc_view *a, int a_grade,
+                                         const lcc_view *b, int64_t mean_divisor, void *result_host, unsigned flags);
+/* Pipelined form: the partial runs on the compute stream and the all-reduce of `slot` (0..7) on a high-priority
+ * communication stream behind an event, so the collective of step i overlaps the kernel of step i+1;
+ * lcc_shard_reduce_fetch waits for that slot and copies its result to the host. */
+LCC_API lcc_status lcc_shard_product_sum_async(lcc_shard_group *group, const lcc_algebra *alg, int op, const lcc_view *a, int a_grade,
+                                               const lcc_view *b, int64_t mean_divisor, int slot, unsigned flags);
+LCC_API lcc_status lcc_shard_reduce_fetch(lcc_shard_group *group, const lcc_algebra *alg, int dtype, int slot, void *result_host);
+
 /* ---------------------------------------------------------------- tuning */
 
 /* Process-wide integer options (no reference counterpart):

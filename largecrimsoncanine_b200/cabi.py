@@ -117,6 +117,30 @@ def lib():
         "lcc_host_sandwich": (i32, [vp, i32, C.POINTER(dbl), vp, vp, i64, u32]),
         "lcc_host_product": (i32, [vp, i32, i32, vp, i64, vp, i64, vp, u32]),
         "lcc_host_pga_points_sandwich": (i32, [vp, i32, C.POINTER(dbl), vp, vp, i64, u32]),
+        "lcc_shard_rows": (i32, [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]),
+        "lcc_shard_unique_id": (i32, [vp]),
+        "lcc_shard_group_create": (i32, [i32, C.POINTER(i32), C.POINTER(vp)]),
+        "lcc_shard_group_create_rank": (i32, [i32, i32, i32, vp, C.POINTER(vp)]),
+        "lcc_shard_group_destroy": (None, [vp]),
+        "lcc_shard_group_local_size": (i32, [vp]),
+        "lcc_shard_group_world_size": (i32, [vp]),
+        "lcc_shard_group_first_rank": (i32, [vp]),
+        "lcc_shard_group_device": (i32, [vp, i32]),
+        "lcc_shard_nccl_version": (i32, []),
+        "lcc_shard_group_stream": (i32, [vp, i32, C.POINTER(vp)]),
+        "lcc_shard_group_sync": (i32, [vp]),
+        "lcc_shard_batch_alloc": (i32, [vp, vp, i32, i64, V, C.POINTER(i64)]),
+        "lcc_shard_broadcast_alloc": (i32, [vp, vp, i32, vp, V]),
+        "lcc_shard_batch_free": (i32, [vp, V]),
+        "lcc_shard_upload": (i32, [vp, vp, vp, i64, V]),
+        "lcc_shard_download": (i32, [vp, vp, V, vp, i64]),
+        "lcc_shard_product": (i32, [vp, vp, i32, V, V, V, u32]),
+        "lcc_shard_sandwich": (i32, [vp, vp, C.POINTER(dbl), V, V, u32]),
+        "lcc_shard_unary": (i32, [vp, vp, i32, i32, V, V]),
+        "lcc_shard_sum": (i32, [vp, vp, V, i64, vp]),
+        "lcc_shard_product_sum": (i32, [vp, vp, i32, V, i32, V, i64, vp, u32]),
+        "lcc_shard_product_sum_async": (i32, [vp, vp, i32, V, i32, V, i64, i32, u32]),
+        "lcc_shard_reduce_fetch": (i32, [vp, vp, i32, i32, vp]),
         "lcc_set_option": (i32, [C.c_char_p, i64]),
         "lcc_get_option": (i32, [C.c_char_p, C.POINTER(i64)]),
         "lcc_kernel_launch_count": (C.c_uint64, []),

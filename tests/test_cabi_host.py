@@ -176,4 +176,5 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "products/s" and d["higher_is_better"] is True and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert {"workload", "rows_per_gpu", "layout", "l2_policy", "strict_fp"} <= set(d["config"])
+    assert set(d["config"]) == {"workload", "rows_per_gpu", "l2_policy"}  # the workload definition, identical to the GPU arm's
+    assert d["impl_config"]["strict_fp"] is True and "host memory" in d["impl_config"]["layout"]

@@ -357,45 +357,36 @@ def test_host_buffer_entry_points(L):
 
 
 def test_sharded_batch_single_rank(L):
-    """ShardedBatch with a world of one (the N > 1 path is covered by tests/test_sharding_gloo.py on CPU
-    and tests/tools/multi_gpu_check.py under torchrun on GPUs)."""
-    from largecrimsoncanine_b200 import sharded
+    """The native sharding API (lcc_shard_*) with a group of one GPU -- no NCCL involved; with two or more GPUs in the
+    box the same calls run as a single-process multi-GPU group (ncclCommInitAll) and must agree with the oracle too.
+    (Host logic on CPU: tests/test_sharding_gloo.py; both group modes at N >= 2: tests/tools/multi_gpu_check.py.)"""
+    from largecrimsoncanine_b200 import cabi, sharded
 
     rng = np.random.default_rng(23)
     x, w = rng.standard_normal((5001, 16)), rng.standard_normal((5001, 16))
-    o = oracle.OracleAlgebra(1, 3, 0)
-    X = sharded.ShardedBatch.from_numpy(L.Algebra.sta(), x, 0, 1)
-    W = sharded.ShardedBatch.from_numpy(L.Algebra.sta(), w, 0, 1)
-    prod = X.grade(1).left_contraction(W)
+    o, alg = oracle.OracleAlgebra(1, 3, 0), cabi.Algebra(1, 3, 0)
     ref = o.left_contraction(o.grade(x, 1), w)
     want, mag = o.sum(ref)
-    assert np.all(np.abs(prod.sum() - want) <= 1e-12 * mag)
-    assert np.all(np.abs(prod.mean() - want / 5001) <= 1e-12 * mag / 5001)
-    assert len(prod) == 5001 and prod.info.rows == 5001
-
-
-@pytest.mark.parametrize("sig", [(6, 0, 0), (4, 2, 1), (8, 0, 0)])
-def test_fixed_operand_product_on_tensor_cores(L, sig):
-    """K6: one-row operand x batch in a 64..256-blade algebra, f32, FMA mode -> tcgen05 GEMM with the
-    3xTF32 split (BASELINE config 5 shape at small N).  Must stay within the f32 bar of 1e-5 against
-    the f64 reference arithmetic; strict mode takes the exact table-driven kernel instead."""
-    alg, o = algebras(L, sig)
-    nb = o.num_blades
-    rng = np.random.default_rng(31)
-    for n in (1, 127, 128, 129, 257, 5000, 40001):  # 40001 rows: several 256-row tiles per CTA pair, ragged tail
-        m = rng.standard_normal((1, nb)).astype(np.float32)
-        x = rng.standard_normal((n, nb)).astype(np.float32)
-        M, X = L.MultivectorBatch.from_numpy(alg, m), L.MultivectorBatch.from_numpy(alg, x)
-        for got, a, b in ((M.geometric_product(X).to_numpy(), m, x), (X.geometric_product(M).to_numpy(), x, m)):
-            ref = o.geometric_product(a.astype(np.float64), b.astype(np.float64))
-            bound = o.product_abs_bound("gp", np.abs(a.astype(np.float64)), np.abs(b.astype(np.float64)))
-            assert np.all(np.abs(got - ref) <= 1e-5 * np.maximum(np.abs(ref), bound))
-            assert np.all(np.abs(got - ref).max(axis=1) <= 1e-5 * np.abs(ref).max(axis=1))
-    L.set_strict_fp(True)
-    try:
-        assert np.array_equal(M.geometric_product(X).to_numpy(), o.geometric_product(m, x))
-    finally:
-        L.set_strict_fp(False)
+    for devices in ([0], None):
+        group = sharded.ShardGroup(devices)
+        assert group.world == group.local_size == (1 if devices else L.device_count())
+        X, W = sharded.ShardedBatch.from_numpy(group, alg, x), sharded.ShardedBatch.from_numpy(group, alg, w)
+        prod = X.grade(1).left_contraction(W, cabi.LCC_FLAG_STRICT_FP)
+        assert np.array_equal(prod.to_numpy(), ref)  # every shard, gathered back in row order
+        assert np.all(np.abs(prod.sum() - want) <= 1e-12 * mag)
+        assert np.all(np.abs(prod.mean() - want / 5001) <= 1e-12 * mag / 5001)
+        fused = X.product_sum(W, "inner", grade=1)
+        assert np.all(np.abs(fused - want) <= 1e-12 * mag)
+        assert np.all(np.abs(X.product_sum(W, "inner", grade=1, mean=True) - want / 5001) <= 1e-12 * mag / 5001)
+        m = rng.standard_normal(16)
+        assert np.array_equal(X.sandwich(m, cabi.LCC_FLAG_STRICT_FP).to_numpy(), o.sandwich(m, x))
+        B = sharded.ShardedBatch.broadcast(group, alg, w[0])
+        assert np.array_equal(B.geometric_product(X, cabi.LCC_FLAG_STRICT_FP).to_numpy(), o.geometric_product(w[:1], x))
+        assert len(prod) == 5001 and sum(e - b for b, e in prod.local_rows()) == 5001
+        group.sync()
+        for t in (X, W, prod, B):
+            t.free()
+        group.close()
 
 
 def test_fixed_operand_product_with_a_pitch_the_tensor_map_cannot_cover(L):

@@ -1,13 +1,13 @@
-"""Host logic of the N > 1 path on CPU: world_size-2 gloo process group (no GPU).
-
-Covers the row partition (tiles [0, N) exactly for ragged N) and the all-reduce that combines
-per-rank partial column sums into the global sum / mean -- checked against the oracle's column
-sums of the whole array.  The per-rank partial itself is a CUDA kernel (tests/test_gpu_parity.py)."""
+"""Host logic of the N > 1 path on CPU (no GPU): the row partition through the C ABI (lcc_shard_rows), argument
+validation of the sharding entry points, and -- in a world_size-2 gloo process group -- the one piece of plumbing that
+is Python: getting rank 0's 128-byte NCCL unique id to every rank.  The partials, the launches and the all-reduce are
+native (csrc/shard_group.cu) and run on GPUs (tests/test_gpu_parity.py::test_sharded_batch_single_rank,
+tests/tools/multi_gpu_check.py)."""
+import ctypes as C
 import os
 import socket
 import sys
 
-import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -16,45 +16,60 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_shard_rows_tiles_the_batch():
     from largecrimsoncanine_b200.sharded import shard_rows
 
-    for n in (0, 1, 2, 7, 8, 1000, 2**28 + 3):
+    for n in (0, 1, 2, 7, 8, 1000, 2**28 + 3, 2**40 + 11):
         for world in (1, 2, 3, 4, 8):
             blocks = [shard_rows(n, r, world) for r in range(world)]
             assert blocks[0].start == 0 and blocks[-1].end == n
             assert all(a.end == b.start for a, b in zip(blocks, blocks[1:]))
             sizes = [b.rows for b in blocks]
             assert max(sizes) - min(sizes) <= 1 and sum(sizes) == n
+            assert [(b.start, b.end) for b in blocks] == [(r * n // world, (r + 1) * n // world) for r in range(world)]
     with pytest.raises(ValueError):
         shard_rows(10, 2, 2)
+    with pytest.raises(ValueError):
+        shard_rows(-1, 0, 2)
 
 
-def _worker(rank, world, port, n, out):
+def test_shard_entry_points_validate_and_refuse_without_a_gpu():
+    from largecrimsoncanine_b200 import cabi
+
+    lib = cabi.lib()
+    g = C.c_void_p()
+    assert lib.lcc_shard_group_create_rank(0, 2, 2, None, C.byref(g)) == cabi.LCC_ERR_VALUE  # rank outside the world
+    assert lib.lcc_shard_group_create_rank(0, 2, 1, None, C.byref(g)) == cabi.LCC_ERR_VALUE  # multi-rank group without an id
+    assert b"unique id" in lib.lcc_last_error()
+    assert lib.lcc_shard_group_local_size(None) == 0 and lib.lcc_shard_group_world_size(None) == 0
+    if not os.path.exists("/dev/nvidiactl"):
+        assert lib.lcc_shard_group_create(0, None, C.byref(g)) == cabi.LCC_ERR_NO_DEVICE  # never emulated on the host
+        assert b"no CPU fallback" in lib.lcc_last_error()
+
+
+def _worker(rank, world, port, out):
     sys.path.insert(0, ROOT)
-    import torch
     import torch.distributed as dist
 
-    import oracle
     from largecrimsoncanine_b200 import sharded
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    token = bytes(range(128))
+    calls = []
+
+    def make_id():  # stands in for lcc_shard_unique_id (NCCL), which only rank 0 may call
+        calls.append(rank)
+        return token
+
     try:
-        rng = np.random.default_rng(5)
-        x = rng.standard_normal((n, 16))  # same global array on every rank (seeded)
-        info = sharded.shard_rows(n, rank, world)
-        o = oracle.OracleAlgebra(1, 3, 0)
-        local = x[info.start:info.end]
-        partial = torch.tensor(local.sum(axis=0)) if len(local) else torch.zeros(16, dtype=torch.float64)
-        total = sharded.allreduce_sum(partial.clone()).numpy()
-        mean = sharded.allreduce_mean(partial.clone(), info.rows).numpy()
-        want, mag = o.sum(x)
-        ok = bool(np.all(np.abs(total - want) <= 1e-13 * mag) and np.all(np.abs(mean - want / n) <= 1e-13 * mag / n))
-        out.put((rank, ok, info.rows))
+        via_store = sharded.distribute_unique_id(make_id, rank, world)  # no process group yet: TCPStore on MASTER_PORT+17
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        via_group = sharded.distribute_unique_id(make_id, rank, world)  # process group present: one broadcast
+        info = sharded.shard_rows(1001, rank, world)
+        out.put((rank, via_store == token and via_group == token, calls == ([0, 0] if rank == 0 else []), info.rows))
     finally:
-        dist.destroy_process_group()
+        if dist.is_initialized():
+            dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n", [1001, 1])
-def test_two_rank_sum_and_mean_over_gloo(n):
+def test_two_ranks_share_the_unique_id_over_gloo():
     import torch.multiprocessing as mp
 
     with socket.socket() as s:
@@ -62,12 +77,12 @@ def test_two_rank_sum_and_mean_over_gloo(n):
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
     results = [q.get(timeout=120) for _ in procs]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert all(ok for _, ok, _ in results)
-    assert sum(rows for _, _, rows in results) == n
+    assert all(same and only_rank0 for _, same, only_rank0, _ in results)
+    assert sum(rows for _, _, _, rows in results) == 1001
