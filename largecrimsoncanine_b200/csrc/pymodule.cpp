@@ -2,9 +2,9 @@
 // PyO3 boundary (/root/reference/src/lib.rs:37-45) over the C ABI of include/lcc_b200.h.
 //
 //   Algebra          <- src/pyalgebra.rs:30-200
-//   Multivector      <- the host value type of src/multivector.rs (the subset SURVEY.md Appendix B
-//                       lists).  It only carries coefficients; every PRODUCT it offers is executed by
-//                       the same CUDA kernels as a one-row batch -- there is no CPU product loop here.
+//   Multivector      <- the host value type of src/multivector.rs.  ONE-pair products run in a host C++ loop that
+//                       restates the reference's per-object product (host_pair_product below) --
+//                       a single pair is ~1 us of arithmetic, not GPU work.  Nothing batched ever takes that loop.
 //   MultivectorBatch <- src/batch.rs:39-1098, device resident (structure-of-arrays in HBM)
 //
 // Same names, argument meaning, exception types and message substrings as the reference so its own
@@ -109,6 +109,56 @@ std::vector<double> device_pair_product(const AlgebraPtr &alg, int op, const std
     return out;
 }
 
+// ------------------------------------------------------------------ single-pair products on the host
+// The reference's per-object product (src/multivector.rs:1438-1715) for ONE pair, restated in C++ (SURVEY.md section 2.1:
+// "the single-Multivector CPU product keeps a scalar C++ loop").  A one-pair product is ~1 us of arithmetic; routing it
+// through the GPU costs an allocation, two uploads, a launch, a download and a synchronisation (tens of microseconds).
+// This is NOT a fallback of the batched path: MultivectorBatch / lcc_batch_* never come here and still refuse to run
+// without a CUDA device.  Term order and rounding follow the reference exactly (compiled with -ffp-contract=off):
+//   * geometric product, fewer than 16 blades: i outer, j inner, zero operands skipped, (sign*a)*b, sequential adds
+//   * geometric product, 16 blades and more: the f64x4 path of src/simd.rs:55-135 -- (a*b)*sign, b == 0 is NOT skipped
+//     and sign-0 terms are added as (+/-)0; identical to the scalar order except for (+/-)0 / NaN / Inf operands
+//   * outer / left / right contraction / scalar product: the masked scalar loops of :1497-1715
+// LCC_SINGLE_PAIR=device keeps the old behaviour (n = 1 through the CUDA kernels) for cross-checks.
+bool single_pair_on_device() {
+    static const bool dev = [] { const char *e = std::getenv("LCC_SINGLE_PAIR"); return e && std::string(e) == "device"; }();
+    return dev;
+}
+
+std::vector<double> host_pair_product(const AlgebraPtr &alg, int op, const std::vector<double> &a, const std::vector<double> &b) {
+    const int nb = alg->nb();
+    const int8_t *signs = lcc_algebra_cayley_signs(alg->h);
+    std::vector<double> out(nb, 0.0);
+    if (op == LCC_OP_GP && nb >= 16) {  // src/simd.rs:21-30 (SIMD_THRESHOLD = 16), :55-135; nb is a power of two: no remainder loop
+        for (int i = 0; i < nb; ++i) {
+            const double ai = a[i];
+            if (ai == 0.0) continue;
+            const int8_t *row = signs + (size_t)i * nb;
+            for (int j = 0; j < nb; ++j) out[i ^ j] += (ai * b[j]) * (double)row[j];
+        }
+        return out;
+    }
+    for (int i = 0; i < nb; ++i) {
+        const double ai = a[i];
+        if (ai == 0.0) continue;
+        const int8_t *row = signs + (size_t)i * nb;
+        for (int j = 0; j < nb; ++j) {
+            const double bj = b[j];
+            if (bj == 0.0) continue;
+            switch (op) {
+                case LCC_OP_GP: break;
+                case LCC_OP_OUTER: if ((i & j) != 0) continue; break;                  // :1510-1513
+                case LCC_OP_LC: if ((i & j) != i) continue; break;                     // :1570-1583 (the grade tests are implied by the subset test)
+                case LCC_OP_RC: if ((i & j) != j) continue; break;                     // :1637-1650
+                case LCC_OP_SCALAR: if (i != j) continue; break;                       // :1697-1700 (blade == 0 iff i == j)
+                default: throw std::runtime_error("host_pair_product: unexpected op");
+            }
+            out[i ^ j] += ((double)row[j] * ai) * bj;
+        }
+    }
+    return out;
+}
+
 // ------------------------------------------------------------------ Multivector (host value type)
 struct Multivector {
     std::vector<double> coeffs;
@@ -144,7 +194,22 @@ struct Multivector {
             s << "algebra mismatch: left operand is Cl(" << dims << ") but right operand is Cl(" << o.dims << "); both multivectors must be in the same algebra";
             throw py::value_error(s.str());
         }
-        return like(device_pair_product(get_algebra(), op, coeffs, o.coeffs));
+        AlgebraPtr alg = get_algebra();
+        if (single_pair_on_device()) return like(device_pair_product(alg, op, coeffs, o.coeffs));
+        switch (op) {
+            case LCC_OP_COMMUTATOR: case LCC_OP_ANTICOMMUTATOR: {  // src/multivector.rs:1732-1768: a*b, b*a, -/+, scale(0.5)
+                std::vector<double> ab = host_pair_product(alg, LCC_OP_GP, coeffs, o.coeffs), ba = host_pair_product(alg, LCC_OP_GP, o.coeffs, coeffs);
+                for (size_t k = 0; k < ab.size(); ++k) ab[k] = (op == LCC_OP_COMMUTATOR ? ab[k] - ba[k] : ab[k] + ba[k]) * 0.5;
+                return like(std::move(ab));
+            }
+            case LCC_OP_REGRESSIVE: {  // :1781-1794: undual(dual(A) ^ dual(B)); inverse() raises when the pseudoscalar is null
+                const Multivector ps = pseudoscalar_like(), ps_inv = ps.inverse();
+                std::vector<double> da = host_pair_product(alg, LCC_OP_GP, coeffs, ps_inv.coeffs), db = host_pair_product(alg, LCC_OP_GP, o.coeffs, ps_inv.coeffs);
+                std::vector<double> w = host_pair_product(alg, LCC_OP_OUTER, da, db);
+                return like(host_pair_product(alg, LCC_OP_GP, w, ps.coeffs));
+            }
+            default: return like(host_pair_product(alg, op, coeffs, o.coeffs));
+        }
     }
     // commutator / anticommutator / regressive test the dimension only (src/multivector.rs:1733-1739,1782-1788)
     Multivector product_same_dims(int op, const Multivector &o) const {

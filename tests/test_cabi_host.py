@@ -145,8 +145,10 @@ def test_batched_calls_refuse_to_run_without_a_gpu():
 
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         L.MultivectorBatch.from_numpy(L.Algebra.euclidean(3), np.zeros((4, 8)))
-    with pytest.raises(RuntimeError, match="no CPU fallback"):
-        L.Multivector.from_vector([1.0, 0.0, 0.0]).geometric_product(L.Multivector.from_vector([0.0, 1.0, 0.0]))
+    # ONE-pair Multivector products are host C++ (the reference's per-object path, src/multivector.rs:1438-1481 /
+    # src/simd.rs:55-135 -- SURVEY.md 2.1); they are not a fallback of anything batched, which still refuses above
+    e12 = L.Multivector.from_vector([1.0, 0.0, 0.0]).geometric_product(L.Multivector.from_vector([0.0, 1.0, 0.0]))
+    assert e12.coefficients() == [0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0]
     # the host-buffer entry points validate their arguments first and then fail the same way (no host arithmetic anywhere)
     lib = cabi.lib()
     xyz, motor = np.zeros((8, 3), np.float32), np.zeros(16)
@@ -159,6 +161,33 @@ def test_batched_calls_refuse_to_run_without_a_gpu():
     assert b"no CPU fallback" in lib.lcc_last_error()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         L.pga_transform_points(L.Algebra.pga(3), L.Multivector.from_scalar(1.0, 4), np.zeros((4, 3)))
+
+
+@pytest.mark.parametrize("sig", [(3, 0, 0), (3, 0, 1), (4, 1, 0), (1, 3, 0), (2, 1, 1), (6, 0, 0)])
+def test_single_pair_products_follow_the_reference_loops(sig):
+    """Multivector (op) Multivector on the host == the oracle's restatement of the same reference loops, bit for bit,
+    for the whole product family; 16 blades and more take the src/simd.rs order ((a*b)*sign)."""
+    import largecrimsoncanine as L
+
+    alg, o = L.Algebra(*sig), oracle.OracleAlgebra(*sig)
+    nb = o.num_blades
+    rng = np.random.default_rng(sum(sig) * 7 + sig[1])
+    for trial in range(5):
+        a, b = rng.standard_normal(nb), rng.standard_normal(nb)
+        if trial == 3:
+            a[rng.integers(0, nb, nb // 2)] = 0.0  # zero-skips
+            b[rng.integers(0, nb, nb // 2)] = 0.0
+        A, B = L.Multivector.from_list_in(list(a), alg), L.Multivector.from_list_in(list(b), alg)
+        assert np.array_equal(A.geometric_product(B).coefficients(), o.geometric_product(a[None], b[None])[0])
+        assert np.array_equal(A.outer_product(B).coefficients(), o.outer_product(a[None], b[None])[0])
+        assert np.array_equal(A.left_contraction(B).coefficients(), o.left_contraction(a[None], b[None])[0])
+        assert np.array_equal((A * B).coefficients(), (A.geometric_product(B)).coefficients())
+        ab, ba = o.geometric_product(a[None], b[None])[0], o.geometric_product(b[None], a[None])[0]
+        assert np.array_equal(A.commutator(B).coefficients(), (ab - ba) * 0.5)
+        assert np.array_equal(A.anticommutator(B).coefficients(), (ab + ba) * 0.5)
+        rx = o.geometric_product(a[None], b[None])
+        rev = a * np.array([1.0 if (bin(i).count("1") % 4) < 2 else -1.0 for i in range(nb)])
+        assert np.array_equal(A.sandwich(B).coefficients(), o.geometric_product(rx, rev[None])[0])  # R x ~R, two rounded stages
 
 
 def test_bench_reference_arm_prints_the_contract_line():
