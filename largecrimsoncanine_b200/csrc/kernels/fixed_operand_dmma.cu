@@ -42,17 +42,6 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) 
                  : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-// Wt[n][k] of the fixed multivector m (nb doubles, stride m_stride), see the header comment
-__global__ void build_wt_f64_kernel(const int8_t *__restrict__ signs, const double *__restrict__ m, int64_t m_stride, int nb, int side,
-                                    double *__restrict__ wt) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nb * nb) return;
-    const int n = idx / nb, k = idx % nb, other = n ^ k;
-    const int s = side == 0 ? signs[other * nb + k] : signs[k * nb + other];
-    const double mv = m[(int64_t)other * m_stride];
-    wt[idx] = s == 0 ? 0.0 : (s > 0 ? mv : -mv);
-}
-
 template <int NB>
 __global__ void __launch_bounds__(kThreadsDmma, 1)
 fixed_product_f64_dmma_kernel(const double *__restrict__ x, int64_t ldx, double *__restrict__ out, int64_t ldo, int64_t n,
@@ -147,20 +136,15 @@ template <int NB> cudaError_t launch_dmma_t(const double *x, int64_t ldx, double
 
 }  // namespace
 
-// out (n x nb, SoA f64) = fixed (op) x (side 0) or x (op) fixed (side 1) through the FP64 tensor pipe.
-// signs_dev: sign table of the algebra on the device; fixed_dev: nb doubles with stride fixed_stride; scratch_w: nb*nb doubles.
-cudaError_t launch_fixed_product_f64_dmma(int nb, int side, const int8_t *signs_dev, const double *fixed_dev, int64_t fixed_stride,
-                                          const ViewArg &x, const ViewArg &out, double *scratch_w, cudaStream_t s) {
+// out (n x nb, SoA f64) = X * Wt^T for a given nb x nb f64 matrix (fixed_operand_matrix.cu) on the FP64 tensor pipe.
+// cudaErrorNotSupported when the batch view is not 16-byte aligned with an even row pitch.
+cudaError_t launch_matrix_product_f64_dmma(int nb, const double *wt, const ViewArg &x, const ViewArg &out, cudaStream_t s) {
     if (x.n <= 0) return cudaSuccess;
     if (((uintptr_t)x.data & 15) != 0 || (x.ld & 1) != 0) return cudaErrorNotSupported;  // 16-byte row pairs
-    build_wt_f64_kernel<<<(nb * nb + 255) / 256, 256, 0, s>>>(signs_dev, fixed_dev, fixed_stride, nb, side, scratch_w);
-    note_kernel_launch();
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
     switch (nb) {
-        case 64: return launch_dmma_t<64>((const double *)x.data, x.ld, (double *)out.data, out.ld, x.n, scratch_w, s);
-        case 128: return launch_dmma_t<128>((const double *)x.data, x.ld, (double *)out.data, out.ld, x.n, scratch_w, s);
-        case 256: return launch_dmma_t<256>((const double *)x.data, x.ld, (double *)out.data, out.ld, x.n, scratch_w, s);
+        case 64: return launch_dmma_t<64>((const double *)x.data, x.ld, (double *)out.data, out.ld, x.n, wt, s);
+        case 128: return launch_dmma_t<128>((const double *)x.data, x.ld, (double *)out.data, out.ld, x.n, wt, s);
+        case 256: return launch_dmma_t<256>((const double *)x.data, x.ld, (double *)out.data, out.ld, x.n, wt, s);
     }
     return cudaErrorNotSupported;
 }

@@ -132,20 +132,15 @@ __device__ __forceinline__ float tf32_rn(float x) {
     return __uint_as_float(r);
 }
 
-// ------------------------------------------------------------------ W = left / right multiplication matrix, split hi + lo
-// signs = sign[a*nb+b] on the device; m = the fixed multivector (nb floats, device)
-__global__ void build_w_kernel(const int8_t *__restrict__ signs, const float *__restrict__ m, int64_t m_stride, int nb, int side,
-                               float *__restrict__ w_hi, float *__restrict__ w_lo) {
+// ------------------------------------------------------------------ W split
+// Wt given in f64 (fixed_operand_matrix.cu) -> tf32 hi + lo
+__global__ void split_w_kernel(const double *__restrict__ wt, int count, float *__restrict__ w_hi, float *__restrict__ w_lo) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nb * nb) return;
-    const int n = idx / nb, k = idx % nb;  // Wt[n][k]: output blade n, input blade k
-    const int other = n ^ k;
-    const int s = side == 0 ? signs[other * nb + k] : signs[k * nb + other];
-    const float mv = m[(int64_t)other * m_stride];
-    const float w = s == 0 ? 0.f : (s > 0 ? mv : -mv);
-    const float hi = tf32_rn(w);
+    if (idx >= count) return;
+    const double w = wt[idx];
+    const float hi = tf32_rn((float)w);
     w_hi[idx] = hi;
-    w_lo[idx] = tf32_rn(w - hi);
+    w_lo[idx] = tf32_rn((float)(w - (double)hi));
 }
 
 // ------------------------------------------------------------------ the GEMM kernel
@@ -602,13 +597,14 @@ cudaError_t launch_pair_t(const float *x, int64_t ldx, float *out, int64_t ldo, 
 
 }  // namespace
 
-// out (n x nb, SoA f32) = fixed (op) x  or  x (op) fixed, geometric product, through the tensor cores.
-// signs_dev: sign table of the algebra on the device; fixed_dev: nb floats; scratch_w: 2*nb*nb floats.
-cudaError_t launch_fixed_product_tf32x3(int nb, int side, const int8_t *signs_dev, const float *fixed_dev, int64_t fixed_stride,
-                                        const ViewArg &x, const ViewArg &out, float *scratch_w, cudaStream_t s) {
+// out (n x nb, SoA f32) = X * Wt^T for a given nb x nb matrix Wt (f64 on the device: a fixed operand's multiplication
+// matrix, a masked one, or a whole sandwich -- fixed_operand_matrix.cu), through the tcgen05 tensor cores with the
+// 3xTF32 split.  scratch_w: 2*nb*nb floats.  cudaErrorNotSupported: no tensor-map encoder, or a view the map cannot cover.
+cudaError_t launch_matrix_product_tf32x3(int nb, const double *wt64, const ViewArg &x, const ViewArg &out, float *scratch_w, cudaStream_t s) {
     if (x.n <= 0) return cudaSuccess;
+    if (!encode_tiled() || x.ld % 32 != 0 || out.ld % 4 != 0 || ((uintptr_t)x.data & 15) != 0 || ((uintptr_t)out.data & 15) != 0) return cudaErrorNotSupported;
     float *w_hi = scratch_w, *w_lo = scratch_w + (size_t)nb * nb;
-    build_w_kernel<<<(nb * nb + 255) / 256, 256, 0, s>>>(signs_dev, fixed_dev, fixed_stride, nb, side, w_hi, w_lo);
+    split_w_kernel<<<(nb * nb + 255) / 256, 256, 0, s>>>(wt64, nb * nb, w_hi, w_lo);
     note_kernel_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

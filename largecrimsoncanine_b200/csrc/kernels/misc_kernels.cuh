@@ -39,14 +39,18 @@ cudaError_t launch_copy_rows(int nb, const ViewArg &src, int64_t start, int64_t 
 // algebras above 32 blades and the vector-Jacobian products of lcc.torch.  gsign is on the device.
 cudaError_t launch_table_product(int nb, bool strict, const ViewArg &x, bool x_bcast, const ViewArg &y, bool y_bcast,
                                  const ViewArg &out, const int8_t *gsign_dev, cudaStream_t s);
-// K6 (fixed_operand_gemm.cu): out = fixed * x (side 0) or x * fixed (side 1) for 64/128/256 blades, f32 SoA,
-// on the tcgen05 tensor cores with the 3xTF32 split.  signs_dev = sign[a*nb+b]; scratch_w = 2*nb*nb floats.
-cudaError_t launch_fixed_product_tf32x3(int nb, int side, const int8_t *signs_dev, const float *fixed_dev, int64_t fixed_stride,
-                                        const ViewArg &x, const ViewArg &out, float *scratch_w, cudaStream_t s);
-// K6d (fixed_operand_dmma.cu): the f64 form on the FP64 tensor pipe (mma.sync m8n8k4); scratch_w = nb*nb doubles.
-// cudaErrorNotSupported when the batch view is not 16-byte aligned with an even row pitch.
-cudaError_t launch_fixed_product_f64_dmma(int nb, int side, const int8_t *signs_dev, const double *fixed_dev, int64_t fixed_stride,
-                                          const ViewArg &x, const ViewArg &out, double *scratch_w, cudaStream_t s);
+// Fixed-operand linear maps in 64 / 128 / 256-blade algebras (fixed_operand_matrix.cu): the nb x nb matrix Wt (f64, device)
+// of  x -> fixed (op) x (side 0) / x (op) fixed (side 1)  with the op's term mask folded in, or of  x -> R x ~R.
+cudaError_t launch_build_product_matrix(int nb, int op, int side, const int8_t *signs_dev, const void *fixed_dev, int64_t fixed_stride,
+                                        int fixed_dtype, double *wt, cudaStream_t s);
+cudaError_t launch_build_sandwich_matrix(int nb, const int8_t *signs_dev, const double *rotor_host, double *wt, cudaStream_t s);
+// rotor and ~rotor as two one-row operands (2*nb elements of `dtype`) written from kernel parameters: no host staging
+cudaError_t launch_write_rotor_rows(int nb, int dtype, const double *rotor_host, void *rows_dev, cudaStream_t s);
+// K6 (fixed_operand_gemm.cu): Out = X * Wt^T, f32 SoA, tcgen05 tensor cores with the 3xTF32 split; scratch_w = 2*nb*nb floats.
+// K6d (fixed_operand_dmma.cu): the f64 form on the FP64 tensor pipe (mma.sync m8n8k4).
+// Both return cudaErrorNotSupported for views they cannot take (pitch / alignment): the caller falls back to the table kernel.
+cudaError_t launch_matrix_product_tf32x3(int nb, const double *wt64, const ViewArg &x, const ViewArg &out, float *scratch_w, cudaStream_t s);
+cudaError_t launch_matrix_product_f64_dmma(int nb, const double *wt64, const ViewArg &x, const ViewArg &out, cudaStream_t s);
 // PGA3D / CGA3D point embeddings and extractors (src/pga.rs:131-134,579-599; src/cga.rs:189-206,492-508);
 // which 2 / 3: STA bivectors from (E,B) and boost rotors from velocities (src/sta.rs:202-212,253-296)
 cudaError_t launch_points_embed(int which, const void *xyz, const ViewArg &dst, cudaStream_t s);

@@ -468,6 +468,38 @@ lcc_status lcc_batch_copy_rows(const lcc_algebra *alg, const lcc_view *src, int6
 }
 
 // ================================================================== the hot path
+static bool tensor_path_off() {
+    static const bool off = [] { const char *e = getenv("LCC_DISABLE_TENSOR_PATH"); return e && e[0] == '1'; }();
+    return off;
+}
+
+// Out = X * Wt^T on the tensor cores for a 64 / 128 / 256-blade batch in either layout and dtype (K6 / K6d).  The kernels
+// read and write blade-major tiles, so a reference-layout (AoS) batch is transposed in and out through two pool
+// temporaries (K7, 6.9 TB/s).  *handled stays false when the kernels cannot take the views (caller falls back).
+static lcc_status tensor_matrix_product(const lcc_algebra *alg, const double *wt64, const lcc_view *x, const lcc_view *out, cudaStream_t s, bool *handled) {
+    *handled = false;
+    const int nb = alg->nb;
+    PoolBuffer tin, tout, wsplit;
+    lcc_view sx = *x, so = *out;
+    if (x->layout == LCC_AOS) {
+        LCC_TRY(make_soa_temp(alg, x->dtype, x->n, tin, &sx, s));
+        LCC_TRY(make_soa_temp(alg, x->dtype, x->n, tout, &so, s));
+        LCC_CUDA(launch_convert(nb, arg_of(x), arg_of(&sx), s));
+    }
+    cudaError_t e;
+    if (x->dtype == LCC_F32) {
+        LCC_TRY(wsplit.alloc((size_t)2 * nb * nb * sizeof(float), s));
+        e = launch_matrix_product_tf32x3(nb, wt64, arg_of(&sx), arg_of(&so), (float *)wsplit.ptr, s);
+    } else {
+        e = launch_matrix_product_f64_dmma(nb, wt64, arg_of(&sx), arg_of(&so), s);
+    }
+    if (e == cudaErrorNotSupported) return LCC_OK;
+    LCC_CUDA(e);
+    if (x->layout == LCC_AOS) LCC_CUDA(launch_convert(nb, arg_of(&so), arg_of(out), s));
+    *handled = true;
+    return LCC_OK;
+}
+
 static lcc_status run_product(const lcc_algebra *alg, int op, const lcc_view *a, const lcc_view *b, const lcc_view *out,
                               const lcc_view *out2, unsigned flags, void *stream) {
     LCC_TRY(check_view(alg, a, "a"));
@@ -498,32 +530,36 @@ static lcc_status run_product(const lcc_algebra *alg, int op, const lcc_view *a,
         LCC_CUDA(launch(g));
         return LCC_OK;
     }
-    // 64..256 blades with ONE fixed operand (the broadcast branch, batch.rs:365-376), f32 SoA, FMA mode:
-    // a GEMM against the operand's multiplication matrix on the tcgen05 tensor cores (K6, 3xTF32)
-    static const bool tensor_path_off = [] { const char *e = getenv("LCC_DISABLE_TENSOR_PATH"); return e && e[0] == '1'; }();
-    // (the X tensor map covers rows in strips of 32: a pitch that is not a multiple of 32 would leave the last rows outside it)
-    if (!tensor_path_off && op == kOpGP && !strict && a->dtype == LCC_F32 && a->layout == LCC_SOA && (a_bc != b_bc) &&
-        (alg->nb == 64 || alg->nb == 128 || alg->nb == 256) && (a_bc ? b : a)->ld % 32 == 0 && out->ld % 4 == 0) {
-        const int8_t *signs_dev = nullptr;
-        LCC_TRY(gather_signs_on_device(alg, 48, &signs_dev));
-        PoolBuffer w;
-        LCC_TRY(w.alloc((size_t)2 * alg->nb * alg->nb * sizeof(float), s));
-        const lcc_view *fixed = a_bc ? a : b, *batch = a_bc ? b : a;
-        const cudaError_t e = launch_fixed_product_tf32x3(alg->nb, a_bc ? 0 : 1, signs_dev, (const float *)fixed->data, fixed->ld,
-                                                          arg_of(batch), arg_of(out), (float *)w.ptr, s);
-        if (e != cudaErrorNotSupported) { LCC_CUDA(e); return LCC_OK; }
-    }
-    // the same contraction in the reference's own precision: f64 on the FP64 tensor pipe (K6d, mma.sync m8n8k4)
-    if (!tensor_path_off && op == kOpGP && !strict && a->dtype == LCC_F64 && a->layout == LCC_SOA && (a_bc != b_bc) &&
-        (alg->nb == 64 || alg->nb == 128 || alg->nb == 256)) {
+    // 64..256 blades with ONE fixed operand (the broadcast branch, batch.rs:365-376), FMA mode: the map x -> fixed (op) x is
+    // linear, so it is a GEMM against its nb x nb matrix (term mask of outer / contractions folded in) on the tensor
+    // cores -- K6 (tcgen05, 3xTF32) for f32, K6d (FP64 tensor pipe) for f64; AoS views are transposed through pool
+    // temporaries.  Strict mode, and views the kernels cannot take, keep the exact-order table kernel below.
+    const bool fixed_operand = (a_bc != b_bc) && (alg->nb == 64 || alg->nb == 128 || alg->nb == 256);
+    auto tensor_one = [&](int single_op, const lcc_view *dst, bool *handled) -> lcc_status {
+        *handled = false;
+        if (tensor_path_off() || strict || !fixed_operand) return LCC_OK;
+        if (single_op != kOpGP && single_op != kOpOuter && single_op != kOpLC && single_op != kOpRC && single_op != kOpScalar) return LCC_OK;
         const int8_t *signs_dev = nullptr;
         LCC_TRY(gather_signs_on_device(alg, 48, &signs_dev));
         PoolBuffer w;
         LCC_TRY(w.alloc((size_t)alg->nb * alg->nb * sizeof(double), s));
         const lcc_view *fixed = a_bc ? a : b, *batch = a_bc ? b : a;
-        const cudaError_t e = launch_fixed_product_f64_dmma(alg->nb, a_bc ? 0 : 1, signs_dev, (const double *)fixed->data, fixed->ld,
-                                                            arg_of(batch), arg_of(out), (double *)w.ptr, s);
-        if (e != cudaErrorNotSupported) { LCC_CUDA(e); return LCC_OK; }
+        LCC_CUDA(launch_build_product_matrix(alg->nb, single_op, a_bc ? 0 : 1, signs_dev, fixed->data, fixed->layout == LCC_SOA ? fixed->ld : 1,
+                                             fixed->dtype, (double *)w.ptr, s));
+        return tensor_matrix_product(alg, (const double *)w.ptr, batch, dst, s, handled);
+    };
+    {
+        bool handled = false;
+        if (op == kOpGPOuter) {
+            LCC_TRY(tensor_one(kOpGP, out, &handled));
+            if (handled) {
+                LCC_TRY(tensor_one(kOpOuter, out2, &handled));
+                if (handled) return LCC_OK;
+            }
+        } else {
+            LCC_TRY(tensor_one(op, out, &handled));
+            if (handled) return LCC_OK;
+        }
     }
     // 64..256 blades: table-driven shared-memory kernel (any layout)
     auto one = [&](int single_op, const lcc_view *dst) -> lcc_status {
@@ -702,25 +738,30 @@ lcc_status lcc_batch_sandwich(const lcc_algebra *alg, const double *rotor, const
         LCC_CUDA(launch(g));
         return LCC_OK;
     }
-    // > 32 blades: two table-driven products with the rotor as a one-row batch (batch.rs:462-496)
-    const size_t es = elem_size(x->dtype);
-    std::vector<unsigned char> host((size_t)2 * nb * es);
-    for (int i = 0; i < nb; ++i) {
-        const int rs = reverse_sign_of_grade(popcount32((unsigned)i));
-        if (x->dtype == LCC_F32) { ((float *)host.data())[i] = (float)rotor[i]; ((float *)host.data())[nb + i] = (float)rotor[i] * (float)rs; }
-        else { ((double *)host.data())[i] = rotor[i]; ((double *)host.data())[nb + i] = rotor[i] * rs; }
+    const int8_t *gs = nullptr;
+    // > 32 blades, FMA mode: x -> R x ~R is ONE linear map; its nb x nb matrix is built on the device from the rotor
+    // (kernel parameter, no host staging, no synchronisation) and the whole sandwich is one tensor-core GEMM
+    if (!strict && !tensor_path_off() && (nb == 64 || nb == 128 || nb == 256)) {
+        LCC_TRY(gather_signs_on_device(alg, 48, &gs));
+        PoolBuffer w;
+        LCC_TRY(w.alloc((size_t)nb * nb * sizeof(double), s));
+        LCC_CUDA(launch_build_sandwich_matrix(nb, gs, rotor, (double *)w.ptr, s));
+        bool handled = false;
+        LCC_TRY(tensor_matrix_product(alg, (const double *)w.ptr, x, out, s, &handled));
+        if (handled) return LCC_OK;
     }
+    // strict mode (or views the GEMM cannot take): two exact-order table products with the rotor as a one-row batch
+    // (batch.rs:462-496); R and ~R are written to the device by a kernel from its parameters
+    const size_t es = elem_size(x->dtype);
     PoolBuffer br, brx;
-    LCC_TRY(br.alloc(host.size(), s));
-    LCC_CUDA(cudaMemcpyAsync(br.ptr, host.data(), host.size(), cudaMemcpyHostToDevice, s));
-    LCC_CUDA(cudaStreamSynchronize(s));  // the host staging vector goes out of scope
+    LCC_TRY(br.alloc((size_t)2 * nb * es, s));
+    LCC_CUDA(launch_write_rotor_rows(nb, x->dtype, rotor, br.ptr, s));
     // one-row views of the rotor in x's layout: SoA with ld = 1 or AoS with ld = nb both put blade k at data[k]
     lcc_view r1{br.ptr, 1, x->layout == LCC_SOA ? 1 : nb, x->dtype, x->layout};
     lcc_view r2{(char *)br.ptr + nb * es, 1, r1.ld, x->dtype, x->layout};
     lcc_view rx = *x;  // intermediate R*x with x's shape
     LCC_TRY(brx.alloc((size_t)(x->layout == LCC_SOA ? nb * x->ld : x->n * x->ld) * es, s));
     rx.data = brx.ptr;
-    const int8_t *gs = nullptr;
     LCC_TRY(gather_signs_on_device(alg, kOpGP, &gs));
     LCC_CUDA(launch_table_product(nb, strict, arg_of(&r1), true, arg_of(x), false, arg_of(&rx), gs, s));
     LCC_CUDA(launch_table_product(nb, strict, arg_of(&rx), false, arg_of(&r2), true, arg_of(out), gs, s));

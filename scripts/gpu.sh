@@ -55,6 +55,10 @@ stage_multi() {          # torchrun at $NGPU ranks: headline + collective + stro
 stage_shard_check() {    # native single-process multi-GPU dispatcher against the oracle
   timeout 600 $PY tests/tools/multi_gpu_check.py 2>&1 | tail -20 | tee gpurun_out/shard_check.log
 }
+stage_shard_check_ranks() {  # the same check with one rank per GPU (ncclCommInitRank)
+  N=${NGPU:-2}
+  timeout 600 $PY -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 tests/tools/multi_gpu_check.py 2>&1 | grep -v "^W\|^\*\*\*\|OMP_NUM" | tail -12 | tee gpurun_out/shard_check_ranks.log
+}
 stage_peaks() {          # cuBLAS TF32 / FP64 / BF16 GEMM and copy micro-benchmarks -> gpurun_out/peaks_local.json
   timeout 300 $PY scripts/measure_peaks.py > gpurun_out/peaks_local.json 2> gpurun_out/peaks_local.err; echo "peaks rc=$?"; cat gpurun_out/peaks_local.json
 }

@@ -436,6 +436,85 @@ def test_fixed_operand_product_f64_on_the_fp64_tensor_pipe(L, sig):
             assert np.all(np.abs(got - ref) <= 1e-12 * np.maximum(np.abs(ref), bound))
 
 
+@pytest.mark.parametrize("sig", [(6, 0, 0), (4, 2, 1), (8, 0, 0)])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_fixed_rotor_sandwich_and_masked_products_on_tensor_cores(L, sig, dt):
+    """64..256 blades, FMA mode: x -> R x ~R with one rotor is ONE linear map -> one tensor-core GEMM against the
+    sandwich matrix (reference: two rounded products, /root/reference/src/batch.rs:452-497); fixed-operand outer
+    product / left contraction -> the same GEMM with the op's term mask folded into the matrix (batch.rs:514-574,585-655).
+    Bar: the path's tolerance against the reference arithmetic in f64; strict mode stays bit-exact (table kernel)."""
+    alg, o = algebras(L, sig)
+    nb = o.num_blades
+    tol = TOL[dt]
+    rng = np.random.default_rng(97 + nb)
+    for n in (1, 255, 257, 40001):
+        x = rng.standard_normal((n, nb)).astype(dt)
+        r = rng.standard_normal(nb) / np.sqrt(nb)
+        X = L.MultivectorBatch.from_numpy(alg, x)
+        got = X.sandwich(rotor_mv(L, alg, r)).to_numpy()
+        ref = o.sandwich(r, x.astype(np.float64))
+        assert np.all(np.abs(got - ref).max(axis=1) <= tol * np.abs(ref).max(axis=1)), f"sandwich n={n}"
+        m = rng.standard_normal((1, nb)).astype(dt)
+        M = L.MultivectorBatch.from_numpy(alg, m)
+        for name, fn in (("outer", o.outer_product), ("lc", o.left_contraction)):
+            for got, a, b in ((getattr(M, name if name == "lc" else "outer_product")(X).to_numpy(), m, x),
+                              (getattr(X, name if name == "lc" else "outer_product")(M).to_numpy(), x, m)):
+                ref = fn(a.astype(np.float64), b.astype(np.float64))
+                bound = o.product_abs_bound("outer" if name == "outer" else "lc", np.abs(a.astype(np.float64)), np.abs(b.astype(np.float64)))
+                assert np.all(np.abs(got - ref) <= tol * np.maximum(np.abs(ref), bound) + 1e-300), f"{name} n={n}"
+        gp, outer = M.gp_and_outer(X)
+        ref_gp = o.geometric_product(m.astype(np.float64), x.astype(np.float64))
+        assert np.all(np.abs(gp.to_numpy() - ref_gp).max(axis=1) <= tol * np.abs(ref_gp).max(axis=1))
+    x = rng.standard_normal((300, nb)).astype(dt)
+    r = rng.standard_normal(nb)
+    L.set_strict_fp(True)
+    try:
+        assert np.array_equal(L.MultivectorBatch.from_numpy(alg, x).sandwich(rotor_mv(L, alg, r)).to_numpy(), o.sandwich(r, x))
+    finally:
+        L.set_strict_fp(False)
+
+
+@pytest.mark.parametrize("sig", [(6, 0, 0), (8, 0, 0)])
+def test_reference_layout_views_reach_the_tensor_cores(L, sig):
+    """Raw C ABI on LCC_AOS views (what lcc.torch and lcc_host_product pass) in 64 / 256-blade algebras: fixed-operand
+    product and fixed-rotor sandwich go through the tensor-core GEMMs (transposed in and out), not the table kernel --
+    same tolerance, padded row pitch left untouched."""
+    from largecrimsoncanine_b200 import cabi
+
+    lib, alg, o = cabi.lib(), cabi.Algebra(*sig), oracle.OracleAlgebra(*sig)
+    nb, n, ld = o.num_blades, 5003, o.num_blades + 8
+    rng = np.random.default_rng(5)
+    for dt, code, tol in ((np.float32, cabi.LCC_F32, 1e-5), (np.float64, cabi.LCC_F64, 1e-12)):
+        x = rng.standard_normal((n, nb)).astype(dt)
+        m = rng.standard_normal((1, nb)).astype(dt)
+        img = np.full((n, ld), -3.5, dt)
+        img[:, :nb] = x
+        es = img.itemsize
+        px, pm, po = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        cabi.check(lib.lcc_device_alloc(C.byref(px), img.nbytes, None))
+        cabi.check(lib.lcc_device_alloc(C.byref(po), img.nbytes, None))
+        cabi.check(lib.lcc_device_alloc(C.byref(pm), nb * es, None))
+        cabi.check(lib.lcc_memcpy_h2d(px, img.ctypes.data, img.nbytes, None))
+        cabi.check(lib.lcc_memcpy_h2d(po, img.ctypes.data, img.nbytes, None))
+        cabi.check(lib.lcc_memcpy_h2d(pm, m.ctypes.data, m.nbytes, None))
+        vx, vo, vm = cabi.view(px.value, n, ld, code, cabi.LCC_AOS), cabi.view(po.value, n, ld, code, cabi.LCC_AOS), cabi.view(pm.value, 1, nb, code, cabi.LCC_AOS)
+        before = lib.lcc_kernel_launch_count()
+        cabi.check(lib.lcc_batch_product(alg.h, cabi.LCC_OP_GP, C.byref(vm), C.byref(vx), C.byref(vo), 0, None))
+        out = np.empty_like(img)
+        cabi.check(lib.lcc_memcpy_d2h(out.ctypes.data, po, out.nbytes, None))
+        cabi.check(lib.lcc_stream_sync(None))
+        ref = o.geometric_product(m.astype(np.float64), x.astype(np.float64))
+        assert np.all(np.abs(out[:, :nb] - ref).max(axis=1) <= tol * np.abs(ref).max(axis=1)) and np.all(out[:, nb:] == -3.5)
+        r = rng.standard_normal(nb) / np.sqrt(nb)
+        cabi.check(lib.lcc_batch_sandwich(alg.h, r.ctypes.data_as(C.POINTER(C.c_double)), C.byref(vx), C.byref(vo), 0, None))
+        cabi.check(lib.lcc_memcpy_d2h(out.ctypes.data, po, out.nbytes, None))
+        cabi.check(lib.lcc_stream_sync(None))
+        ref = o.sandwich(r, x.astype(np.float64))
+        assert np.all(np.abs(out[:, :nb] - ref).max(axis=1) <= tol * np.abs(ref).max(axis=1)) and np.all(out[:, nb:] == -3.5)
+        for p in (px, pm, po):
+            cabi.check(lib.lcc_device_free(p, None))
+
+
 @pytest.mark.parametrize("sig", [(1, 3, 0), (3, 0, 1), (4, 1, 0), (2, 1, 1)])
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
 def test_fused_grade_product_sum(L, sig, dt):
