@@ -52,7 +52,13 @@ WORKLOADS["pga_points_compact"] = ((3, 0, 1), "f32", 28, 24, "points/s")
 WORKLOADS["cl8_fixed_gp"] = ((8, 0, 0), "f32", 24, 2048, "products/s")
 # the same product in the reference's own precision, on the FP64 tensor pipe (DMMA)
 WORKLOADS["cl8_fixed_gp_f64"] = ((8, 0, 0), "f64", 24, 4096, "products/s")
-TENSOR_FLOPS_PER_UNIT = {"cl8_fixed_gp": 3 * 2 * 256 * 256, "cl8_fixed_gp_f64": 2 * 256 * 256}  # f32: three tf32 MMAs per term
+# the same two products with the matrix representation switched off: the dense nb x nb GEMM of round 1 (tensor-pipe bound)
+WORKLOADS["cl8_fixed_gp_gemm"] = ((8, 0, 0), "f32", 24, 2048, "products/s")
+WORKLOADS["cl8_fixed_gp_f64_gemm"] = ((8, 0, 0), "f64", 24, 4096, "products/s")
+CL8_WORKLOADS = ("cl8_fixed_gp", "cl8_fixed_gp_f64", "cl8_fixed_gp_gemm", "cl8_fixed_gp_f64_gemm")
+# tensor flops of the dense multiplication-matrix GEMM (f32: three tf32 MMAs per term); the default K8 path needs 16x fewer
+# flops and is HBM-bound, so only the *_gemm variants report against the tensor roofline
+TENSOR_FLOPS_PER_UNIT = {"cl8_fixed_gp_gemm": 3 * 2 * 256 * 256, "cl8_fixed_gp_f64_gemm": 2 * 256 * 256}
 # the headline input is a PGA point (12 of its 16 blade rows are zeros); this variant streams 16 dense rows
 WORKLOADS["pga_sandwich_dense16"] = ((3, 0, 1), "f32", 28, 128, "points/s")
 HEADLINE = "pga_sandwich"
@@ -165,7 +171,7 @@ def cpu_rate(workload, sample_rows, threads, repeats=1):
     else:
         a = rng.standard_normal((sample_rows, nb)).astype(ndt)
         b = rng.standard_normal((sample_rows, nb)).astype(ndt)
-        if workload in ("cl8_fixed_gp", "cl8_fixed_gp_f64"):
+        if workload in CL8_WORKLOADS:
             fn = lambda: o.geometric_product(a[:1], b, threads=threads)  # noqa: E731
         elif workload == "cga_gp_outer":
             fn = lambda: (o.geometric_product(a, b, threads=threads), o.outer_product(a, b, threads=threads))  # noqa: E731
@@ -185,7 +191,7 @@ def cpu_rate(workload, sample_rows, threads, repeats=1):
 def cpu_sample_rows(workload):
     return {"pga_sandwich": 1 << 25, "cga_gp": 1 << 22, "cga_gp_outer": 1 << 22, "r3_gp": 1 << 20, "sta_grade_inner_sum": 1 << 23,
             "sta_fused_grade_inner_sum": 1 << 23,
-            "cl8_fixed_gp": 1 << 14, "cl8_fixed_gp_f64": 1 << 14, "pga_points_compact": 1 << 25, "pga_sandwich_dense16": 1 << 25}[workload]
+            "cl8_fixed_gp": 1 << 14, "cl8_fixed_gp_f64": 1 << 14, "cl8_fixed_gp_gemm": 1 << 14, "cl8_fixed_gp_f64_gemm": 1 << 14, "pga_points_compact": 1 << 25, "pga_sandwich_dense16": 1 << 25}[workload]
 
 
 def run_reference_arm(args):
@@ -233,8 +239,10 @@ def workload_name(wl, n=None):
         "pga_sandwich": "PGA Cl(3,0,1) motor sandwich", "cga_gp": "CGA Cl(4,1,0) batched geometric product",
         "cga_gp_outer": "CGA Cl(4,1,0) fused geometric + outer product", "r3_gp": "Cl(3,0,0) batched geometric product",
         "sta_grade_inner_sum": "STA Cl(1,3,0) grade projection + inner product + batch sum",
-        "cl8_fixed_gp": "Cl(8,0,0) fixed-operand left geometric product (tcgen05, 3xTF32)",
-        "cl8_fixed_gp_f64": "Cl(8,0,0) fixed-operand left geometric product, f64 (mma.sync m8n8k4 DMMA)",
+        "cl8_fixed_gp": "Cl(8,0,0) fixed-operand left geometric product (K8: block-diagonalised in the M16(R) representation)",
+        "cl8_fixed_gp_f64": "Cl(8,0,0) fixed-operand left geometric product, f64 (K8: block-diagonalised in the M16(R) representation)",
+        "cl8_fixed_gp_gemm": "Cl(8,0,0) fixed-operand left geometric product as the dense 256 x 256 GEMM (tcgen05, 3xTF32)",
+        "cl8_fixed_gp_f64_gemm": "Cl(8,0,0) fixed-operand left geometric product as the dense 256 x 256 GEMM, f64 (mma.sync m8n8k4 DMMA)",
         "sta_fused_grade_inner_sum": "STA Cl(1,3,0) fused grade projection + inner product + batch sum (one kernel)",
         "pga_points_compact": "PGA Cl(3,0,1) motor applied to compact (N,3) points, embed + sandwich + extract fused",
         "pga_sandwich_dense16": "PGA Cl(3,0,1) motor sandwich on fully dense 16-blade multivectors",
@@ -450,15 +458,21 @@ def setup_workload(ctx, wl, n, layout="soa", collective=True, ld_pad=0):
             want, mag = o.sum(o.left_contraction(o.grade(xs, 1), ys))
             scale = np.abs(mag).max() / np.maximum(mag, 1e-300)  # compare on the scale of the summed magnitudes
             return finish(chk.cpu().numpy() * scale, want * scale, m)
-    elif wl in ("cl8_fixed_gp", "cl8_fixed_gp_f64"):
+    elif wl in CL8_WORKLOADS:
         b = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
         a = torch.randn((nb, 4), device=dev, dtype=tdt, generator=gen)  # the fixed operand: one-row SoA view, ld = 4
         out = torch.empty_like(b)
         va, vb, vo = cabi.view(a.data_ptr(), 1, 4, code, cabi.LCC_SOA), soa(b), soa(out)
-        keep.update(a=a, b=b, out=out)
+        fixed = a[:, 0].to(torch.float64).cpu().numpy().copy()  # the fixed operand, known on the host (as in MultivectorBatch.from_numpy(1 x nb))
+        fptr = fixed.ctypes.data_as(C.POINTER(C.c_double))
+        keep.update(a=a, b=b, out=out, fixed=fixed)
+        # cl8_fixed_gp / _f64: lcc_batch_fixed_product -- block-diagonalised in the algebra's 16 x 16 matrix representation (K8)
+        # *_gemm: option matrix_rep = 0 -- the dense multiplication-matrix GEMM on the tensor cores (K6 tcgen05 / K6d DMMA)
+        rep = 0 if wl.endswith("_gemm") else 1
 
         def step():
-            cabi.check(lib.lcc_batch_product(alg.h, cabi.LCC_OP_GP, C.byref(va), C.byref(vb), C.byref(vo), flags, sptr))
+            cabi.check(lib.lcc_set_option(b"matrix_rep", rep))
+            cabi.check(lib.lcc_batch_fixed_product(alg.h, cabi.LCC_OP_GP, 0, fptr, C.byref(vb), C.byref(vo), flags, sptr))
 
         def parity():
             sub = idx[::64]
@@ -621,7 +635,7 @@ def run_gpu_arm(args):
                   "roofline_per_gpu": roofline_block(HEADLINE, sn, srec2["ms_per_step"], bytes_per, peaks, peak_kind, None)}
         strong.update(srec2)
         for swl, slayout in (("r3_gp", "soa"), ("cga_gp_outer", "soa"), ("cga_gp", "aos"), ("sta_grade_inner_sum", "soa"), ("cl8_fixed_gp", "soa"),
-                             ("cl8_fixed_gp_f64", "soa"), ("pga_sandwich_dense16", "soa"), ("pga_sandwich", "aos")):
+                             ("cl8_fixed_gp_f64", "soa"), ("cl8_fixed_gp_gemm", "soa"), ("cl8_fixed_gp_f64_gemm", "soa"), ("pga_sandwich_dense16", "soa"), ("pga_sandwich", "aos")):
             try:
                 r = secondary_record(ctx, swl, k, peaks, peak_kind, layout=slayout)
             except Exception as exc:  # one workload failing must not take the headline line down
@@ -694,7 +708,7 @@ def roofline_block(wl, n, kernel_ms, bytes_per, peaks, peak_kind, traffic):
         # it say how far the kernel is from the streaming floor of the same rows.
         tf = TENSOR_FLOPS_PER_UNIT[wl] * n / (kernel_ms / 1e3) / 1e12
         lp = local_peaks()
-        key = "fp64" if wl == "cl8_fixed_gp_f64" else "tf32"
+        key = "fp64" if wl == "cl8_fixed_gp_f64_gemm" else "tf32"
         if lp and key in lp:
             peak, sustained = float(lp[key]["burst_tflops"]), float(lp[key]["sustained_tflops"])
             src = f"profiles/peaks_local.json: cuBLAS {key} GEMM 8192^3 measured with scripts/measure_peaks.py (burst; sustained beside it)"

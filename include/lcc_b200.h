@@ -136,6 +136,12 @@ LCC_API int lcc_reverse_sign(int blade_index);
 LCC_API int lcc_grade_involution_sign(int blade_index);
 LCC_API int lcc_clifford_conjugate_sign(int blade_index);
 
+/* Real matrix representation of a non-degenerate 7- or 8-dimensional algebra by 16 x 16 signed permutation matrices
+ * (csrc/matrix_rep.hpp; host side, no GPU needed): blade A = sign_of_blade[A] * X^a Z^b with string_of_blade[A] = a << 4 | b,
+ * X^a Z^b [i][j] = [i == j ^ a] * (-1)^popcount(b & j).  Returns the matrix size (16), or 0 when the algebra has no such
+ * representation (then fixed-operand products stay on the dense GEMM).  Buffers hold num_blades entries; either may be NULL. */
+LCC_API int lcc_algebra_matrix_rep(const lcc_algebra *alg, uint8_t *string_of_blade, int8_t *sign_of_blade);
+
 /* ---------------------------------------------------------------- device memory (stream-ordered pool) */
 
 LCC_API lcc_status lcc_device_alloc(void **ptr, size_t bytes, void *stream);
@@ -176,6 +182,14 @@ LCC_API lcc_status lcc_batch_product(const lcc_algebra *alg, int op, const lcc_v
 /* Fused dual-output: gp_out = a*b and outer_out = a^b reading a and b once (BASELINE config 3). */
 LCC_API lcc_status lcc_batch_gp_outer(const lcc_algebra *alg, const lcc_view *a, const lcc_view *b,
                                       const lcc_view *gp_out, const lcc_view *outer_out, unsigned flags, void *stream);
+/* The broadcast branch with the fixed operand on the HOST (num_blades doubles): out = fixed (op) x (side 0) or
+ * x (op) fixed (side 1), batch.rs:365-404 with a one-row left / right batch.  Knowing the operand on the host lets the
+ * engine pick the cheapest form without reading device memory back: in 128 / 256-blade non-degenerate algebras that have
+ * a real 16 x 16 matrix representation (Cl(8,0), Cl(4,4), Cl(7,0), ... -- csrc/matrix_rep.hpp) the geometric product runs
+ * block-diagonalised (K8: two Walsh-Hadamard passes + a 16 x 16 x 16 product per row, HBM-bound) instead of as the
+ * nb x nb tensor-core GEMM; option "matrix_rep" = 0 keeps the GEMM.  Strict mode always takes the exact-order kernel. */
+LCC_API lcc_status lcc_batch_fixed_product(const lcc_algebra *alg, int op, int side, const double *fixed_host, const lcc_view *x,
+                                           const lcc_view *out, unsigned flags, void *stream);
 /* Fused pipeline  sums[k] = sum over rows of ( <a>_g (op) b )[k]  -- grade projection of the left operand
  * (a_grade < 0: none; batch.rs:1027-1052), product (batch.rs:353-655) and batch sum in ONE pass that reads
  * only the needed blade rows and writes num_blades values (BASELINE config 4; the per-GPU partial that
@@ -342,6 +356,8 @@ LCC_API lcc_status lcc_shard_reduce_fetch(lcc_shard_group *group, const lcc_alge
  *   "aos_tma_min_rows"   AoS batches with at least this many rows use the TMA-staged kernels (default 4096; rows
  *                        narrower than 128 bytes need 32x as many)
  *   "soa_tma_min_bytes"  SoA batches with at least this many bytes per operand do (default 8 GiB)
+ *   "matrix_rep"         1 (default): fixed-operand products / sandwiches of 128- and 256-blade algebras use the 16 x 16
+ *                        matrix representation (K8) where one exists; 0: always the nb x nb tensor-core GEMM (K6 / K6d)
  *   "host_chunk_bytes"   chunk size of the host <-> device pipelines (default 64 MiB)
  *   "pinned_output_min_bytes"  to_numpy() results of at least this size come from the pinned host cache (default 1 MiB;
  *                        a very large value switches the cache off)

@@ -71,6 +71,7 @@ def lib():
         "lcc_algebra_grade_mask": (i32, [vp, i32, C.POINTER(C.c_uint64), i32]),
         "lcc_algebra_blade_name": (i32, [vp, i32, C.c_char_p, i32]),
         "lcc_algebra_is_specialised": (i32, [vp]),
+        "lcc_algebra_matrix_rep": (i32, [vp, C.POINTER(C.c_uint8), C.POINTER(C.c_int8)]),
         "lcc_reverse_sign": (i32, [i32]),
         "lcc_grade_involution_sign": (i32, [i32]),
         "lcc_clifford_conjugate_sign": (i32, [i32]),
@@ -90,6 +91,7 @@ def lib():
         "lcc_batch_copy_rows": (i32, [vp, V, i64, i64, V, i64, vp]),
         "lcc_batch_product": (i32, [vp, i32, V, V, V, u32, vp]),
         "lcc_batch_gp_outer": (i32, [vp, V, V, V, V, u32, vp]),
+        "lcc_batch_fixed_product": (i32, [vp, i32, i32, C.POINTER(dbl), V, V, u32, vp]),
         "lcc_batch_product_sum": (i32, [vp, i32, V, i32, V, vp, u32, vp]),
         "lcc_batch_product_vjp": (i32, [vp, i32, i32, V, V, V, u32, vp]),
         "lcc_batch_sandwich": (i32, [vp, C.POINTER(dbl), V, V, u32, vp]),

@@ -28,6 +28,10 @@ struct lcc_algebra {
     // kinds 0..2 forward gp / outer / lc, 3..5 their VJP wrt the left operand, 6..8 wrt the right one
     std::mutex mu_dev;
     std::map<std::pair<int, int>, int8_t *> gather_signs_dev;
+    // 16 x 16 real matrix representation (matrix_rep.hpp), searched on first use; rep_state: 0 not tried, 1 found, 2 none
+    int rep_state = 0;
+    std::vector<uint8_t> rep_string_of, rep_blade_at;  // blade -> string, string -> blade (0 when none)
+    std::vector<int8_t> rep_sign_of, rep_sign_at;      // blade -> sign, string -> sign (0 when none)
 };
 
 namespace lcc {

@@ -18,6 +18,7 @@
 #include <nvtx3/nvToolsExt.h>
 
 #include "abi_internal.hpp"
+#include "matrix_rep.hpp"
 #include "generated/cayley_tables.h"
 #include "kernels/launch_args.h"
 
@@ -64,6 +65,7 @@ static int64_t env_or(const char *name, int64_t fallback) {
 }
 static std::atomic<int64_t> g_aos_tma_min_rows{env_or("LCC_AOS_TMA_MIN_ROWS", 4096)};
 static std::atomic<int64_t> g_soa_tma_min_bytes{env_or("LCC_SOA_TMA_MIN_BYTES", 8ll << 30)};
+static std::atomic<int64_t> g_matrix_rep{env_or("LCC_MATRIX_REP", 1)};
 // grid of the fused product + batch-sum kernel (kernels/launch_args.h); LCC_FUSED_SUM_BLOCKS overrides it for sweeps
 static int fused_sum_blocks() {
     static const int v = [] { const int64_t e = env_or("LCC_FUSED_SUM_BLOCKS", kFusedSumBlocks); return e >= 1 && e <= (1 << 20) ? (int)e : kFusedSumBlocks; }();
@@ -500,6 +502,83 @@ static lcc_status tensor_matrix_product(const lcc_algebra *alg, const double *wt
     return LCC_OK;
 }
 
+// The algebra's 16 x 16 matrix representation (matrix_rep.hpp), searched once.
+static bool matrix_rep_of(const lcc_algebra *calg) {
+    lcc_algebra *alg = const_cast<lcc_algebra *>(calg);
+    std::lock_guard<std::mutex> lock(alg->mu_dev);
+    if (alg->rep_state == 0) {
+        const MatrixRep rep = find_matrix_rep(*alg);
+        alg->rep_state = rep.ok ? 1 : 2;
+        if (rep.ok) {
+            alg->rep_string_of.assign(rep.string_of, rep.string_of + 256);
+            alg->rep_sign_of.assign(rep.sign_of, rep.sign_of + 256);
+            alg->rep_blade_at.assign(256, 0);
+            alg->rep_sign_at.assign(256, 0);
+            for (int sidx = 0; sidx < 256; ++sidx)
+                if (rep.blade_at[sidx] >= 0) { alg->rep_blade_at[sidx] = (uint8_t)rep.blade_at[sidx]; alg->rep_sign_at[sidx] = rep.sign_of[rep.blade_at[sidx]]; }
+        }
+    }
+    return alg->rep_state == 1;
+}
+
+// rho(M) (row-major 16 x 16) from num_blades coefficients; scale folds the 1/16 of the inverse transform in
+static void rep_matrix_of(const lcc_algebra *alg, const double *coeffs, double scale, bool transpose, double *out) {
+    double m[256];
+    for (int i = 0; i < 256; ++i) m[i] = 0.0;
+    for (int A = 0; A < alg->nb; ++A) {
+        if (coeffs[A] == 0.0) continue;
+        const unsigned a = alg->rep_string_of[A] >> 4, b = alg->rep_string_of[A] & 15;
+        const double v = coeffs[A] * alg->rep_sign_of[A];
+        for (unsigned j = 0; j < 16; ++j) m[(j ^ a) * 16 + j] += (__builtin_popcount(b & j) & 1) ? -v : v;
+    }
+    for (int i = 0; i < 16; ++i)
+        for (int j = 0; j < 16; ++j) out[i * 16 + j] = scale * (transpose ? m[j * 16 + i] : m[i * 16 + j]);
+}
+
+static bool matrix_rep_usable(const lcc_algebra *alg, const lcc_view *x, bool strict) {
+    return !strict && g_matrix_rep.load(std::memory_order_relaxed) != 0 && (alg->nb == 128 || alg->nb == 256) && x->n >= 64 && matrix_rep_of(alg);
+}
+
+// K8 on x -> out for the rows it can take: all of them for reference-layout (AoS) views, which are transposed in and out
+// through pool temporaries; for blade-major views the rows up to the last multiple of 16 bytes (TMA stores clip there) --
+// *rows_done tells the caller where its exact kernels have to pick up the 1-3 that remain.
+static lcc_status matrix_rep_apply(const lcc_algebra *alg, int mode, const double *p1, const double *p2, const lcc_view *x,
+                                   const lcc_view *out, cudaStream_t s, int64_t *rows_done) {
+    *rows_done = 0;
+    const int nb = alg->nb;
+    const int64_t w = 16 / (int64_t)elem_size(x->dtype);
+    PoolBuffer tin, tout;
+    lcc_view sx = *x, so = *out;
+    if (x->layout == LCC_AOS) {
+        LCC_TRY(make_soa_temp(alg, x->dtype, x->n, tin, &sx, s));
+        LCC_TRY(make_soa_temp(alg, x->dtype, x->n, tout, &so, s));
+        LCC_CUDA(launch_convert(nb, arg_of(x), arg_of(&sx), s));
+        sx.n = so.n = (x->n + w - 1) / w * w;  // the temporaries are padded: whole 16-byte groups, the extra rows are never copied back
+    } else {
+        sx.n = so.n = x->n - x->n % w;
+    }
+    if (sx.n > 0) {
+        const cudaError_t e = launch_matrix_rep_product(nb, mode, p1, p2, alg->rep_blade_at.data(), alg->rep_sign_at.data(), arg_of(&sx), arg_of(&so), s);
+        if (e == cudaErrorNotSupported) return LCC_OK;
+        LCC_CUDA(e);
+    }
+    if (x->layout == LCC_AOS) {
+        so.n = x->n;
+        LCC_CUDA(launch_convert(nb, arg_of(&so), arg_of(out), s));
+        *rows_done = x->n;
+    } else {
+        *rows_done = sx.n;
+    }
+    return LCC_OK;
+}
+
+static lcc_view tail_view(const lcc_view *v, int64_t first) {  // rows [first, n) of a view
+    lcc_view t = *v;
+    t.n = v->n - first;
+    t.data = (char *)v->data + (size_t)(v->layout == LCC_SOA ? first : first * v->ld) * elem_size(v->dtype);
+    return t;
+}
+
 static lcc_status run_product(const lcc_algebra *alg, int op, const lcc_view *a, const lcc_view *b, const lcc_view *out,
                               const lcc_view *out2, unsigned flags, void *stream) {
     LCC_TRY(check_view(alg, a, "a"));
@@ -627,6 +706,59 @@ lcc_status lcc_batch_gp_outer(const lcc_algebra *alg, const lcc_view *a, const l
     return run_product(alg, kOpGPOuter, a, b, gp_out, outer_out, flags, stream);
 }
 
+int lcc_algebra_matrix_rep(const lcc_algebra *alg, uint8_t *string_of_blade, int8_t *sign_of_blade) {
+    if (!alg || !matrix_rep_of(alg)) return 0;
+    for (int A = 0; A < alg->nb; ++A) {
+        if (string_of_blade) string_of_blade[A] = alg->rep_string_of[A];
+        if (sign_of_blade) sign_of_blade[A] = alg->rep_sign_of[A];
+    }
+    return 16;
+}
+
+lcc_status lcc_batch_fixed_product(const lcc_algebra *alg, int op, int side, const double *fixed_host, const lcc_view *x, const lcc_view *out,
+                                   unsigned flags, void *stream) {
+    TraceRange tr("lcc_batch_fixed_product");
+    LCC_TRY(check_view(alg, x, "x"));
+    LCC_TRY(check_view(alg, out, "out"));
+    LCC_TRY(same_kind(x, out, "fixed_product"));
+    if (!fixed_host) return fail(LCC_ERR_VALUE, "fixed operand is NULL");
+    if (side != 0 && side != 1) return fail(LCC_ERR_VALUE, "side must be 0 (fixed * x) or 1 (x * fixed)");
+    if (x->n != out->n) return fail(LCC_ERR_VALUE, "fixed_product: output has %lld rows, expected %lld", (long long)out->n, (long long)x->n);
+    if (x->n == 0) return LCC_OK;
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    const bool strict = (flags & LCC_FLAG_STRICT_FP) != 0;
+    const int nb = alg->nb;
+    lcc_view xt = *x, ot = *out;
+    if (op == LCC_OP_GP && matrix_rep_usable(alg, x, strict)) {
+        double p1[256];
+        rep_matrix_of(alg, fixed_host, 1.0 / 16.0, side == 1, p1);
+        int64_t rows_done = 0;
+        LCC_TRY(matrix_rep_apply(alg, side, p1, nullptr, x, out, s, &rows_done));
+        if (rows_done == x->n) return LCC_OK;
+        xt = tail_view(x, rows_done); ot = tail_view(out, rows_done);
+    }
+    // everything else: the operand becomes a one-row device batch (written by a kernel from its parameters: no host
+    // staging, no synchronisation) and the broadcast branch of lcc_batch_product does the rest
+    PoolBuffer row;
+    LCC_TRY(row.alloc((size_t)2 * 256 * sizeof(double), s));
+    double padded[256];
+    for (int i = 0; i < 256; ++i) padded[i] = i < nb ? fixed_host[i] : 0.0;
+    LCC_CUDA(launch_write_rotor_rows(nb, x->dtype, padded, row.ptr, s));
+    lcc_view one{row.ptr, 1, x->layout == LCC_SOA ? 1 : nb, x->dtype, x->layout};
+    if (x->layout == LCC_SOA) one.ld = 16 / (int64_t)elem_size(x->dtype);  // check_view wants a 16-byte multiple; blade k must sit at data[k * ld]
+    if (x->layout == LCC_SOA) {
+        // re-space the row so that blade k sits at data[k * ld]: write it as an AoS row and convert
+        PoolBuffer spaced;
+        LCC_TRY(spaced.alloc((size_t)nb * one.ld * elem_size(x->dtype), s));
+        lcc_view src{row.ptr, 1, nb, x->dtype, LCC_AOS}, dst{spaced.ptr, 1, one.ld, x->dtype, LCC_SOA};
+        LCC_CUDA(launch_convert(nb, arg_of(&src), arg_of(&dst), s));
+        one.data = spaced.ptr;
+        return side == 0 ? lcc_batch_product(alg, op, &one, &xt, &ot, flags, (void *)s) : lcc_batch_product(alg, op, &xt, &one, &ot, flags, (void *)s);
+    }
+    return side == 0 ? lcc_batch_product(alg, op, &one, &xt, &ot, flags, (void *)s) : lcc_batch_product(alg, op, &xt, &one, &ot, flags, (void *)s);
+}
+
 lcc_status lcc_batch_product_sum(const lcc_algebra *alg, int op, const lcc_view *a, int a_grade, const lcc_view *b, void *sums_dev,
                                  unsigned flags, void *stream) {
     TraceRange tr("lcc_batch_product_sum");
@@ -737,6 +869,19 @@ lcc_status lcc_batch_sandwich(const lcc_algebra *alg, const double *rotor, const
         g.stream = s;
         LCC_CUDA(launch(g));
         return LCC_OK;
+    }
+    // 128 / 256 blades with a 16 x 16 matrix representation, FMA mode: R x ~R = rho(R) rho(x) rho(~R) per row (K8, HBM-bound)
+    lcc_view xt = *x, ot = *out;  // what is left for the kernels below (all of it, or the 1-3 rows K8 cannot store)
+    if (matrix_rep_usable(alg, x, strict)) {
+        double p1[256], p2[256], rrev[256];
+        for (int i = 0; i < nb; ++i) rrev[i] = rotor[i] * reverse_sign_of_grade(popcount32((unsigned)i));
+        rep_matrix_of(alg, rotor, 1.0 / 16.0, false, p1);
+        rep_matrix_of(alg, rrev, 1.0, true, p2);
+        int64_t rows_done = 0;
+        LCC_TRY(matrix_rep_apply(alg, 2, p1, p2, x, out, s, &rows_done));
+        if (rows_done == x->n) return LCC_OK;
+        xt = tail_view(x, rows_done); ot = tail_view(out, rows_done);
+        x = &xt; out = &ot;
     }
     const int8_t *gs = nullptr;
     // > 32 blades, FMA mode: x -> R x ~R is ONE linear map; its nb x nb matrix is built on the device from the rotor
@@ -974,6 +1119,7 @@ lcc_status lcc_set_option(const char *name, int64_t value) {
     if (value < 0) return fail(LCC_ERR_VALUE, "option %s: value must be >= 0", name);
     if (!strcmp(name, "aos_tma_min_rows")) { g_aos_tma_min_rows = value; return LCC_OK; }
     if (!strcmp(name, "soa_tma_min_bytes")) { g_soa_tma_min_bytes = value; return LCC_OK; }
+    if (!strcmp(name, "matrix_rep")) { g_matrix_rep = value; return LCC_OK; }
     if (!strcmp(name, "host_chunk_bytes")) { set_option_host_chunk_bytes(value); return LCC_OK; }
     if (!strcmp(name, "pinned_output_min_bytes")) { set_option_pinned_output_min_bytes(value); return LCC_OK; }
     return fail(LCC_ERR_VALUE, "unknown option %s", name);
@@ -982,6 +1128,7 @@ lcc_status lcc_get_option(const char *name, int64_t *value) {
     if (!name || !value) return fail(LCC_ERR_VALUE, "option name / value is NULL");
     if (!strcmp(name, "aos_tma_min_rows")) { *value = g_aos_tma_min_rows; return LCC_OK; }
     if (!strcmp(name, "soa_tma_min_bytes")) { *value = g_soa_tma_min_bytes; return LCC_OK; }
+    if (!strcmp(name, "matrix_rep")) { *value = g_matrix_rep; return LCC_OK; }
     if (!strcmp(name, "host_chunk_bytes")) { *value = option_host_chunk_bytes(); return LCC_OK; }
     if (!strcmp(name, "pinned_output_min_bytes")) { *value = option_pinned_output_min_bytes(); return LCC_OK; }
     return fail(LCC_ERR_VALUE, "unknown option %s", name);

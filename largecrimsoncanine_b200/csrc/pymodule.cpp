@@ -292,6 +292,9 @@ struct Batch {
     AlgebraPtr algebra;
     lcc_view view{nullptr, 0, 0, LCC_F64, LCC_SOA};
     int device = 0;
+    // host copy of a ONE-row batch that came from host data (from_numpy / set): lets a broadcast product hand the fixed
+    // operand to lcc_batch_fixed_product without reading device memory back (empty when unknown)
+    std::vector<double> host_row;
 
     Batch(AlgebraPtr alg, int dtype, int64_t n) : algebra(std::move(alg)) {
         check(lcc_get_device(&device));
@@ -342,6 +345,10 @@ BatchPtr batch_from_numpy(const PyAlgebra &alg, const py::array &coeffs_in) {  /
     auto b = std::make_shared<Batch>(alg.inner, dtype, n);
     if (n == 0) return b;
     const void *host = coeffs.data();
+    if (n == 1) {
+        b->host_row.resize(nb);
+        for (int k = 0; k < nb; ++k) b->host_row[k] = dtype == LCC_F64 ? ((const double *)host)[k] : (double)((const float *)host)[k];
+    }
     py::gil_scoped_release nogil;
     // chunked pipeline (host_transfer.cu): the array is read exactly once -- directly by the DMA engine when it is
     // pinned, through the pinned bounce ring otherwise -- and each chunk is transposed into the blade-major batch while
@@ -437,6 +444,15 @@ BatchPtr batch_product(const Batch &a, const Batch &b, int op) {
     require_same_algebra(a, b);
     auto out = a.empty_like(broadcast_n(a, b));
     py::gil_scoped_release nogil;
+    // broadcast branch (src/batch.rs:365-376) in a 128 / 256-blade algebra with the one-row operand known on the host:
+    // lcc_batch_fixed_product can run it block-diagonalised (K8) instead of as the dense GEMM
+    if (a.nb() >= 128 && (a.n() == 1) != (b.n() == 1)) {
+        const Batch &fixed = a.n() == 1 ? a : b, &batch = a.n() == 1 ? b : a;
+        if (!fixed.host_row.empty() && batch.n() > 1) {
+            check(lcc_batch_fixed_product(a.algebra->h, op, a.n() == 1 ? 0 : 1, fixed.host_row.data(), &batch.view, &out->view, fp_flags(), nullptr));
+            return out;
+        }
+    }
     check(lcc_batch_product(a.algebra->h, op, &a.view, &b.view, &out->view, fp_flags(), nullptr));
     return out;
 }
@@ -522,6 +538,10 @@ void batch_set(Batch &b, int64_t index, const Multivector &mv) {  // src/batch.r
     lcc_view row{stage.ptr, 1, nb, b.view.dtype, LCC_AOS};
     check(lcc_batch_copy_rows(b.algebra->h, &row, 0, 1, &b.view, index, nullptr));
     check(lcc_stream_sync(nullptr));
+    if (b.n() == 1) {
+        b.host_row.resize(nb);
+        for (int k = 0; k < nb; ++k) b.host_row[k] = b.view.dtype == LCC_F64 ? mv.coeffs[k] : (double)(float)mv.coeffs[k];
+    }
 }
 BatchPtr batch_slice(const Batch &b, int64_t start, int64_t end) {  // src/batch.rs:1083-1097
     if (start < 0 || end < 0 || start > b.n() || end > b.n() || start > end) {

@@ -104,6 +104,39 @@ def test_generated_term_lists_match_oracle():
     assert cabi.lib().lcc_algebra_is_specialised(cabi.Algebra(2, 1, 1).h) == 0
 
 
+@pytest.mark.parametrize("sig,has_rep", [((8, 0, 0), True), ((4, 4, 0), True), ((5, 3, 0), True), ((0, 8, 0), True), ((1, 7, 0), True),
+                                         ((7, 0, 0), True), ((4, 3, 0), True), ((0, 7, 0), True), ((7, 1, 0), False), ((6, 1, 0), False),
+                                         ((6, 2, 0), False), ((7, 0, 1), False), ((6, 0, 0), False), ((3, 0, 1), False)])
+def test_matrix_representation_is_an_algebra_homomorphism(sig, has_rep):
+    """csrc/matrix_rep.hpp: the 16 x 16 signed-permutation matrices found for Cl(p,q) reproduce the algebra's own Cayley
+    table -- rho(e_A) rho(e_B) == sign[A][B] rho(e_{A^B}) -- and are linearly independent (distinct strings), so the
+    block-diagonalised product of K8 is the reference product in another basis.  Checked with dense NumPy matrices."""
+    L = cabi.lib()
+    a = cabi.Algebra(*sig)
+    nb = a.num_blades
+    strings, signs = (C.c_uint8 * nb)(), (C.c_int8 * nb)()
+    d = L.lcc_algebra_matrix_rep(a.h, strings, signs)
+    assert (d == 16) == has_rep
+    if not has_rep:
+        return
+    strings, signs = np.array(strings[:]), np.array(signs[:])
+    assert len(set(strings.tolist())) == nb and set(np.abs(signs).tolist()) == {1}
+    j = np.arange(16)
+
+    def mat(A):
+        x, z = int(strings[A]) >> 4, int(strings[A]) & 15
+        m = np.zeros((16, 16))
+        m[j ^ x, j] = np.array([(-1.0) ** bin(z & int(t)).count("1") for t in j])
+        return signs[A] * m
+
+    table = a.cayley_signs().reshape(nb, nb)
+    assert np.array_equal(mat(0), np.eye(16))
+    rng = np.random.default_rng(nb + sig[1])
+    pairs = [(1 << i, 1 << k) for i in range(a.dimension) for k in range(a.dimension)] + [tuple(rng.integers(0, nb, 2)) for _ in range(300)]
+    for A, B in pairs:
+        assert np.array_equal(mat(A) @ mat(B), table[A, B] * mat(A ^ B)), (A, B)
+
+
 def test_host_side_errors():
     L = cabi.lib()
     h = C.c_void_p()

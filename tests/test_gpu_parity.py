@@ -474,6 +474,44 @@ def test_fixed_rotor_sandwich_and_masked_products_on_tensor_cores(L, sig, dt):
         L.set_strict_fp(False)
 
 
+@pytest.mark.parametrize("sig", [(8, 0, 0), (4, 4, 0), (5, 3, 0), (0, 8, 0), (7, 0, 0), (4, 3, 0), (1, 6, 0)])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_block_diagonalised_fixed_operand_product_and_sandwich(L, sig, dt):
+    """K8: M * x, x * M and R x ~R in the algebra's 16 x 16 matrix representation (two Walsh-Hadamard passes + one 16^3
+    product per row) against the reference arithmetic (/root/reference/src/batch.rs:365-404,452-497) in f64, at ragged
+    sizes (the last 1-3 rows of a blade-major batch go through the exact kernels), and against the dense GEMM path."""
+    alg, o = algebras(L, sig)
+    nb, tol = o.num_blades, TOL[dt]
+    rng = np.random.default_rng(1000 + nb + sig[1])
+    assert L.get_option("matrix_rep") == 1
+    for n in (64, 65, 4099, 40003):
+        x = rng.standard_normal((n, nb)).astype(dt)
+        m = rng.standard_normal((1, nb)).astype(dt)
+        X, M = L.MultivectorBatch.from_numpy(alg, x), L.MultivectorBatch.from_numpy(alg, m)
+        x64, m64 = x.astype(np.float64), m.astype(np.float64)
+        before = L.kernel_launch_count()
+        left, right = M.geometric_product(X).to_numpy(), X.geometric_product(M).to_numpy()
+        for got, ref, bound in ((left, o.geometric_product(m64, x64), o.product_abs_bound("gp", np.abs(m64), np.abs(x64))),
+                                (right, o.geometric_product(x64, m64), o.product_abs_bound("gp", np.abs(x64), np.abs(m64)))):
+            assert np.all(np.abs(got - ref) <= tol * np.maximum(np.abs(ref), bound))
+            assert np.all(np.abs(got - ref).max(axis=1) <= tol * np.abs(ref).max(axis=1))
+        r = rng.standard_normal(nb) / np.sqrt(nb)
+        got = X.sandwich(rotor_mv(L, alg, r)).to_numpy()
+        ref = o.sandwich(r, x64)
+        assert np.all(np.abs(got - ref).max(axis=1) <= tol * np.abs(ref).max(axis=1))
+        L.set_option("matrix_rep", 0)  # the dense GEMM of the same map must agree within the same bar
+        try:
+            dense = M.geometric_product(X).to_numpy()
+        finally:
+            L.set_option("matrix_rep", 1)
+        assert np.all(np.abs(dense - left).max(axis=1) <= 2 * tol * np.abs(left).max(axis=1))
+    # a basis-blade operand is a signed permutation: exact in both paths
+    e = np.zeros((1, nb), dt)
+    e[0, nb - 1] = 1.0
+    got = L.MultivectorBatch.from_numpy(alg, e).geometric_product(X).to_numpy()
+    assert np.allclose(got, o.geometric_product(e.astype(np.float64), x64), rtol=0, atol=tol * np.abs(x64).max())
+
+
 @pytest.mark.parametrize("sig", [(6, 0, 0), (8, 0, 0)])
 def test_reference_layout_views_reach_the_tensor_cores(L, sig):
     """Raw C ABI on LCC_AOS views (what lcc.torch and lcc_host_product pass) in 64 / 256-blade algebras: fixed-operand
