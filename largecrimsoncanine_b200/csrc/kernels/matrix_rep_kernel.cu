@@ -59,7 +59,8 @@ template <typename T, int MODE, int NS>
 __global__ void __launch_bounds__(kThreadsRep, 1)
 matrix_rep_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_out,
                   const __grid_constant__ RepParams<T> P, int nb, int64_t n) {
-    constexpr int kOuterUnroll = sizeof(T) == 4 ? 16 : 1;
+    constexpr int kG = 4;                                   // outputs accumulated side by side
+    constexpr int kOuterUnroll = sizeof(T) == 4 ? 4 : 1;   // of the 4 groups of kG outputs
     constexpr uint32_t kStageElems = 256 * kTileRows;
     constexpr uint32_t kStageBytes = kStageElems * sizeof(T);
     extern __shared__ __align__(1024) uint8_t smem[];  // no static shared memory in this kernel: the window starts aligned
@@ -117,19 +118,24 @@ matrix_rep_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 16; ++j) st[(((j ^ w) << 4) | j) * kTileRows] = v[j];
             consumer_sync();
-            // stage 2: 16 x 16 x 16 in place; the fixed factor is a constant-bank operand
+            // stage 2: 16 x 16 x 16 in place.  The column (row) is in registers, so each result goes straight back to its
+            // slot; kG outputs are accumulated side by side so that the FMA chains (16 dependent FMAs per output) overlap.
+            // f32: fully unrolled, the factor enters the FFMAs as uniform-register operands.  f64: the group loop stays
+            // rolled (unrolled, ptxas hoists all 256 doubles out of the tile loop and spills them to local memory).
             if (MODE == 0 || MODE == 2) {  // column j = w:  C[i][j] = sum_k P1[i][k] X[k][j]
 #pragma unroll
                 for (int k = 0; k < 16; ++k) v[k] = st[((k << 4) | w) * kTileRows];
-                // the column is in registers: each result goes straight back to its slot.  f32: fully unrolled, the factor
-                // enters the FFMAs as uniform-register operands (64 LDCU.128 per tile).  f64: the output loop stays rolled --
-                // unrolled, ptxas hoists all 256 doubles out of the tile loop and spills them to local memory
 #pragma unroll kOuterUnroll
-                for (int i = 0; i < 16; ++i) {
-                    T a0 = T(0);
+                for (int i0 = 0; i0 < 16; i0 += kG) {
+                    T a0[kG];
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) a0 = fma(P.p1[i * 16 + k], v[k], a0);
-                    st[((i << 4) | w) * kTileRows] = a0;
+                    for (int g = 0; g < kG; ++g) a0[g] = T(0);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k)
+#pragma unroll
+                        for (int g = 0; g < kG; ++g) a0[g] = fma(P.p1[(i0 + g) * 16 + k], v[k], a0[g]);
+#pragma unroll
+                    for (int g = 0; g < kG; ++g) st[(((i0 + g) << 4) | w) * kTileRows] = a0[g];
                 }
                 if (MODE == 2) consumer_sync();
             }
@@ -137,11 +143,16 @@ matrix_rep_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 #pragma unroll
                 for (int k = 0; k < 16; ++k) v[k] = st[((w << 4) | k) * kTileRows];
 #pragma unroll kOuterUnroll
-                for (int j = 0; j < 16; ++j) {
-                    T a0 = T(0);
+                for (int j0 = 0; j0 < 16; j0 += kG) {
+                    T a0[kG];
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) a0 = fma(MODE == 2 ? P.p2[j * 16 + k] : P.p1[j * 16 + k], v[k], a0);
-                    st[((w << 4) | j) * kTileRows] = a0;
+                    for (int g = 0; g < kG; ++g) a0[g] = T(0);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k)
+#pragma unroll
+                        for (int g = 0; g < kG; ++g) a0[g] = fma(MODE == 2 ? P.p2[(j0 + g) * 16 + k] : P.p1[(j0 + g) * 16 + k], v[k], a0[g]);
+#pragma unroll
+                    for (int g = 0; g < kG; ++g) st[((w << 4) | (j0 + g)) * kTileRows] = a0[g];
                 }
             }
             consumer_sync();
