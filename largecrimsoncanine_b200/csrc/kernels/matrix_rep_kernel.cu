@@ -10,13 +10,16 @@
 //     stage 3   z[c][.] = WHT_j(C[j^c][j]) ;  out_A = sign_A z[c][b]                  (the 1/16 is folded into rho(M))
 // = 8192 + 2048 flops instead of 131 072: the product becomes HBM-bound (2 * nb * sizeof(T) bytes per row).
 //
-// Shape: persistent, one CTA per SM.  Warp 16 streams 32-row tiles (32 x nb box of the blade-major batch) into a ring of
-// shared-memory stages with TMA, warps 0-15 transform a stage IN PLACE, warp 17 hands it back to the TMA engine for the
-// store and frees the stage once the engine has read it -- loads run several tiles ahead of the arithmetic, stores
-// trail it.  Inside a stage, element (slot s, row r) lives at [s * 32 + r]: a warp always works on ONE slot for 32
-// consecutive rows, so every shared-memory access is conflict free, and the three stages only re-index the 256 slots
-// (blade index -> matrix entry -> blade index).  The 16 x 16 factor(s) travel as kernel parameters and are compile-time
-// indexed, so they enter the FMAs as constant-bank operands: no loads for the fixed operand at all.
+// Shape: persistent, one CTA per SM.  One thread of warp 16 streams 32-row tiles (32 x nb box of the blade-major batch)
+// into a ring of shared-memory stages with TMA, warps 0-15 transform a stage IN PLACE, and the same TMA thread hands the
+// finished stage to the engine for the store and refills it with the tile NS ahead once the engine has read it -- loads
+// run several tiles ahead of the arithmetic, stores trail it.  Inside a stage, slot s holds 32 rows; in the transform
+// stages a warp works on ONE slot per instruction with its 32 lanes on the 32 rows (conflict free), and the three stages
+// only re-index the 256 slots (blade index -> matrix entry -> blade index).  Stage 2 runs on the tensor cores with the
+// fixed 16 x 16 factor held in registers as MMA A-fragments for the whole kernel: mma.sync m16n8k8 TF32 x 3 (hi/lo
+// split, the same error budget as K6) for f32, mma.sync m8n8k4 on the FP64 tensor pipe for f64.  (The first version did
+// stage 2 with FFMA / DFMA against constant-bank operands: issue-bound at 67 % for f32 and bound by indexed constant
+// loads -- ADU pipe 75 % busy -- for f64: 10.1 / 25.9 ms at 2^24 rows, profiles/r02_k8_*_v1.)
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -30,7 +33,7 @@ namespace lcc {
 namespace {
 
 constexpr int kTileRows = 32;
-constexpr int kConsumerWarps = 16, kConsumers = kConsumerWarps * 32, kThreadsRep = kConsumers + 64;
+constexpr int kConsumerWarps = 16, kConsumers = kConsumerWarps * 32, kThreadsRep = kConsumers + 32;
 
 template <typename T> struct RepParams {
     T p1[256];           // first factor, [o * 16 + k]:  acc[o] += p1[o][k] * x[k]
@@ -52,121 +55,200 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tma::smem_u32(bar)) : "memory");
 }
 
-// MODE 0: out = M * x   (C = P1 * X, a thread owns column j)
-// MODE 1: out = x * M   (C = X * P1^T-indexed, a thread owns row i)
-// MODE 2: out = R x ~R  (MODE 0 with p1 = rho(R) / 16, then MODE 1 with p2 = rho(~R))
+// Matrix slots: entry (f, s) of a 16 x 16 matrix lives in slot f * 16 + s; inside a slot row r sits at position
+// r ^ swz(f).  The XOR spreads the four k-lanes of an MMA B-fragment load and the m-lanes of a D-fragment store over
+// different banks (derivation in DESIGN.md section 4, K8); in the transform stages f is warp-uniform per instruction, so
+// there the swizzle is a permutation of the 32 lanes and costs nothing.
+template <typename T> struct Swz;
+template <> struct Swz<float> { static __device__ __forceinline__ int of(int f) { return (f & 3) << 3; } };
+template <> struct Swz<double> { static __device__ __forceinline__ int of(int f) { return ((f & 1) << 3) | ((f & 2) << 1); } };
+
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], float b0, float b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+                   "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+__device__ __forceinline__ void mma_f64(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+
+// The fixed 16 x 16 factor as MMA A-fragments, loaded once per kernel from the parameter block.
+template <typename T> struct Factor;
+template <> struct Factor<float> {  // m16n8k8, 3xTF32: hi + lo parts, two k-steps
+    float hi[2][4], lo[2][4];
+    __device__ __forceinline__ void load(const float *p, int g, int t) {
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const float a[4] = {p[g * 16 + 8 * ks + t], p[(g + 8) * 16 + 8 * ks + t], p[g * 16 + 8 * ks + t + 4], p[(g + 8) * 16 + 8 * ks + t + 4]};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { hi[ks][e] = tf32_rna(a[e]); lo[ks][e] = tf32_rna(a[e] - hi[ks][e]); }
+        }
+    }
+};
+template <> struct Factor<double> {  // m8n8k4: two m-blocks x four k-steps
+    double a[2][4];
+    __device__ __forceinline__ void load(const double *p, int g, int t) {
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) a[mb][ks] = p[(8 * mb + g) * 16 + 4 * ks + t];
+    }
+};
+
+// D = F * Z for the 32 rows of one column (second index = w) of the matrix in `st`, in place: Z[k][w] -> D[o][w].
+// Four n-blocks of 8 rows; every B fragment of an n-block is read before its D fragments are written.
+__device__ __forceinline__ void column_gemm(float *st, const Factor<float> &F, int w, int g, int t) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        float b[2][2];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) b[ks][h] = st[((8 * ks + 4 * h + t) * 16 + w) * kTileRows + (8 * (q ^ t) + g)];  // (8q + g) ^ (t << 3)
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const float b0 = tf32_rna(b[ks][0]), b1 = tf32_rna(b[ks][1]);
+            const float l0 = tf32_rna(b[ks][0] - b0), l1 = tf32_rna(b[ks][1] - b1);
+            mma_tf32(d, F.lo[ks], b0, b1);   // small terms first
+            mma_tf32(d, F.hi[ks], l0, l1);
+            mma_tf32(d, F.hi[ks], b0, b1);
+        }
+        const int pos = 8 * (q ^ (g & 3)) + 2 * t;  // (8q + 2t) ^ ((g & 3) << 3); rows 2t, 2t+1 stay adjacent
+        *reinterpret_cast<float2 *>(st + (g * 16 + w) * kTileRows + pos) = make_float2(d[0], d[1]);
+        *reinterpret_cast<float2 *>(st + ((g + 8) * 16 + w) * kTileRows + pos) = make_float2(d[2], d[3]);
+    }
+}
+__device__ __forceinline__ void column_gemm(double *st, const Factor<double> &F, int w, int g, int t) {
+    const int sb = ((t & 1) << 3) | ((t & 2) << 1), sd = ((g & 1) << 3) | ((g & 2) << 1);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        double d[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        double b[4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) b[ks] = st[((4 * ks + t) * 16 + w) * kTileRows + ((8 * q + g) ^ sb)];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb) mma_f64(d[mb], F.a[mb][ks], b[ks]);
+        const int pos = (8 * q + 2 * t) ^ sd;
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+            *reinterpret_cast<double2 *>(st + ((8 * mb + g) * 16 + w) * kTileRows + pos) = make_double2(d[mb][0], d[mb][1]);
+    }
+}
+
+// MODE 0: out = M * x      C = P1 X            matrix slots hold X / C as (row index, column index)
+// MODE 1: out = x * M      C^T = P1 X^T        the same column GEMM on the TRANSPOSED slots (p1 arrives as [j][k] = rho(M)[k][j])
+// MODE 2: out = R x ~R     T = P1 X, transpose pass, C^T = P2 T^T   (p1 = rho(R) / 16, p2[j][k] = rho(~R)[k][j])
 template <typename T, int MODE, int NS>
 __global__ void __launch_bounds__(kThreadsRep, 1)
 matrix_rep_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_out,
                   const __grid_constant__ RepParams<T> P, int nb, int64_t n) {
-    constexpr int kG = 4;                                   // outputs accumulated side by side
-    constexpr int kOuterUnroll = sizeof(T) == 4 ? 4 : 1;   // of the 4 groups of kG outputs
     constexpr uint32_t kStageElems = 256 * kTileRows;
     constexpr uint32_t kStageBytes = kStageElems * sizeof(T);
     extern __shared__ __align__(1024) uint8_t smem[];  // no static shared memory in this kernel: the window starts aligned
     uint64_t *bars = (uint64_t *)(smem + (size_t)NS * kStageBytes);
-    uint64_t *full = bars, *done = bars + NS, *empty = bars + 2 * NS;
+    uint64_t *full = bars, *done = bars + NS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NS; ++s) { tma::mbar_init(&full[s], 1); tma::mbar_init(&done[s], 1); tma::mbar_init(&empty[s], 1); }
+        for (int s = 0; s < NS; ++s) { tma::mbar_init(&full[s], 1); tma::mbar_init(&done[s], 1); }
     }
     __syncthreads();
     const int64_t tiles = (n + kTileRows - 1) / kTileRows;
     const uint32_t box_bytes = (uint32_t)nb * kTileRows * sizeof(T);
 
-    if (warp == kConsumerWarps) {            // ---- loader
+    if (warp == kConsumerWarps) {            // ---- the TMA warp: one thread streams tiles in and hands finished stages back
         if (lane == 0) {
             tma::prefetch_map(&map_x);
-            int s = 0; uint32_t ph = 0;
-            for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-                tma::mbar_wait(&empty[s], ph ^ 1);
-                tma::mbar_expect_tx(&full[s], box_bytes);
-                tma::load_2d(smem + (size_t)s * kStageBytes, &map_x, &full[s], (int)(t * kTileRows), 0);
-                if (++s == NS) { s = 0; ph ^= 1; }
-            }
-        }
-    } else if (warp == kConsumerWarps + 1) {  // ---- storer
-        if (lane == 0) {
             tma::prefetch_map(&map_out);
+            const int64_t mine = tiles > blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+            for (int64_t k = 0; k < mine && k < NS; ++k) {  // fill the ring
+                tma::mbar_expect_tx(&full[k], box_bytes);
+                tma::load_2d(smem + (size_t)k * kStageBytes, &map_x, &full[k], (int)((blockIdx.x + k * gridDim.x) * kTileRows), 0);
+            }
             int s = 0; uint32_t ph = 0;
-            for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+            for (int64_t k = 0; k < mine; ++k) {
                 tma::mbar_wait(&done[s], ph);
-                tma::store_2d(&map_out, smem + (size_t)s * kStageBytes, (int)(t * kTileRows), 0);
-                tma::store_commit_and_wait_read();  // the engine has read the stage: it may be refilled
-                mbar_arrive(&empty[s]);
+                tma::store_2d(&map_out, smem + (size_t)s * kStageBytes, (int)((blockIdx.x + k * gridDim.x) * kTileRows), 0);
+                tma::store_commit_and_wait_read();  // the engine has read the stage: refill it with the tile NS ahead
+                if (k + NS < mine) {
+                    tma::mbar_expect_tx(&full[s], box_bytes);
+                    tma::load_2d(smem + (size_t)s * kStageBytes, &map_x, &full[s], (int)((blockIdx.x + (k + NS) * gridDim.x) * kTileRows), 0);
+                }
                 if (++s == NS) { s = 0; ph ^= 1; }
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // global writes complete before the CTA exits
         }
-    } else {                                  // ---- 16 consumer warps: warp w = one index (a, j, i or c), lane = row
-        const int w = warp;
+    } else {                                  // ---- 16 consumer warps: warp w = one index (a, j or c), lane = row
+        const int w = warp, g = lane >> 2, t4 = lane & 3;
+        // per-thread tables, built once: where the 16 blades of string row w live in a stage and their signs; where the 16
+        // matrix entries this thread transforms live (stage 1 writes them, stage 3 reads them)
+        int off_blade[16], off_first[16], off_last[16];
+        uint32_t neg = 0, valid = 0;
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+            const int str = (w << 4) | b;
+            const int sg = P.sign[str];
+            off_blade[b] = (int)P.blade[str] * kTileRows + lane;
+            neg |= (sg < 0 ? 1u : 0u) << b;
+            valid |= (sg != 0 ? 1u : 0u) << b;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            // X[j^w][j] (normal slots) or, transposed, X^T[j][j^w]
+            const int f1 = MODE == 1 ? j : (j ^ w), s1 = MODE == 1 ? (j ^ w) : j;
+            off_first[j] = (f1 * 16 + s1) * kTileRows + (lane ^ Swz<T>::of(f1));
+            const int f3 = MODE == 0 ? (j ^ w) : j, s3 = MODE == 0 ? j : (j ^ w);  // modes 1 and 2 end on transposed slots
+            off_last[j] = (f3 * 16 + s3) * kTileRows + (lane ^ Swz<T>::of(f3));
+        }
+        Factor<T> F1, F2;
+        F1.load(P.p1, g, t4);
+        if (MODE == 2) F2.load(P.p2, g, t4);
         int s = 0; uint32_t ph = 0;
         for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-            T *st = (T *)(smem + (size_t)s * kStageBytes) + lane;
+            T *st = (T *)(smem + (size_t)s * kStageBytes);
             tma::mbar_wait(&full[s], ph);
             T v[16];
-            // stage 1: gather y[a][.] (a = w) from the blade slots, transform, scatter to the matrix slots (j^a, j)
+            // stage 1: gather y[w][.] from the blade slots, transform, scatter to the matrix slots
 #pragma unroll
             for (int b = 0; b < 16; ++b) {
-                const int str = (w << 4) | b;
-                const int sg = P.sign[str];
-                const T x = st[(int)P.blade[str] * kTileRows];
-                v[b] = sg == 0 ? T(0) : (sg > 0 ? x : -x);
+                const T x = st[off_blade[b]];
+                v[b] = ((valid >> b) & 1u) ? (((neg >> b) & 1u) ? -x : x) : T(0);
             }
             wht16(v);
             consumer_sync();  // every blade slot has been read
 #pragma unroll
-            for (int j = 0; j < 16; ++j) st[(((j ^ w) << 4) | j) * kTileRows] = v[j];
+            for (int j = 0; j < 16; ++j) st[off_first[j]] = v[j];
             consumer_sync();
-            // stage 2: 16 x 16 x 16 in place.  The column (row) is in registers, so each result goes straight back to its
-            // slot; kG outputs are accumulated side by side so that the FMA chains (16 dependent FMAs per output) overlap.
-            // f32: fully unrolled, the factor enters the FFMAs as uniform-register operands.  f64: the group loop stays
-            // rolled (unrolled, ptxas hoists all 256 doubles out of the tile loop and spills them to local memory).
-            if (MODE == 0 || MODE == 2) {  // column j = w:  C[i][j] = sum_k P1[i][k] X[k][j]
+            // stage 2 on the tensor cores: the column with second index w, in place
+            column_gemm(st, F1, w, g, t4);
+            if (MODE == 2) {
+                consumer_sync();
+                // transpose pass: T[i][w] -> T^T[w][i] (the first index is warp-uniform on both sides: conflict free)
 #pragma unroll
-                for (int k = 0; k < 16; ++k) v[k] = st[((k << 4) | w) * kTileRows];
-#pragma unroll kOuterUnroll
-                for (int i0 = 0; i0 < 16; i0 += kG) {
-                    T a0[kG];
+                for (int i = 0; i < 16; ++i) v[i] = st[(i * 16 + w) * kTileRows + (lane ^ Swz<T>::of(i))];
+                consumer_sync();
 #pragma unroll
-                    for (int g = 0; g < kG; ++g) a0[g] = T(0);
-#pragma unroll
-                    for (int k = 0; k < 16; ++k)
-#pragma unroll
-                        for (int g = 0; g < kG; ++g) a0[g] = fma(P.p1[(i0 + g) * 16 + k], v[k], a0[g]);
-#pragma unroll
-                    for (int g = 0; g < kG; ++g) st[(((i0 + g) << 4) | w) * kTileRows] = a0[g];
-                }
-                if (MODE == 2) consumer_sync();
-            }
-            if (MODE == 1 || MODE == 2) {  // row i = w:  C[i][j] = sum_k X[i][k] P[k][j],  factor stored as [j][k]
-#pragma unroll
-                for (int k = 0; k < 16; ++k) v[k] = st[((w << 4) | k) * kTileRows];
-#pragma unroll kOuterUnroll
-                for (int j0 = 0; j0 < 16; j0 += kG) {
-                    T a0[kG];
-#pragma unroll
-                    for (int g = 0; g < kG; ++g) a0[g] = T(0);
-#pragma unroll
-                    for (int k = 0; k < 16; ++k)
-#pragma unroll
-                        for (int g = 0; g < kG; ++g) a0[g] = fma(MODE == 2 ? P.p2[(j0 + g) * 16 + k] : P.p1[(j0 + g) * 16 + k], v[k], a0[g]);
-#pragma unroll
-                    for (int g = 0; g < kG; ++g) st[((w << 4) | (j0 + g)) * kTileRows] = a0[g];
-                }
+                for (int i = 0; i < 16; ++i) st[(w * 16 + i) * kTileRows + (lane ^ Swz<T>::of(w))] = v[i];
+                consumer_sync();
+                column_gemm(st, F2, w, g, t4);
             }
             consumer_sync();
-            // stage 3: gather C[j^c][j] (c = w), transform back, scatter to the blade slots
+            // stage 3: gather the 16 matrix entries of string row w, transform back, scatter to the blade slots
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = st[(((j ^ w) << 4) | j) * kTileRows];
+            for (int j = 0; j < 16; ++j) v[j] = st[off_last[j]];
             wht16(v);
             consumer_sync();  // every matrix slot has been read
 #pragma unroll
-            for (int b = 0; b < 16; ++b) {
-                const int str = (w << 4) | b;
-                const int sg = P.sign[str];
-                if (sg != 0) st[(int)P.blade[str] * kTileRows] = sg > 0 ? v[b] : -v[b];
-            }
+            for (int b = 0; b < 16; ++b)
+                if ((valid >> b) & 1u) st[off_blade[b]] = ((neg >> b) & 1u) ? -v[b] : v[b];
             tma::fence_proxy_async();
             consumer_sync();
             if (threadIdx.x == 0) mbar_arrive(&done[s]);
@@ -184,7 +266,7 @@ cudaError_t launch_rep_t(int nb, const void *x, int64_t ldx, void *out, int64_t 
     if (!make_soa_tensor_map(&mx, x, (int)sizeof(T), nb, ldx, n, kTileRows) || !make_soa_tensor_map(&mo, out, (int)sizeof(T), nb, ldo, n, kTileRows))
         return cudaErrorNotSupported;
     auto kernel = matrix_rep_kernel<T, MODE, NS>;
-    constexpr int smem = NS * 256 * kTileRows * (int)sizeof(T) + 3 * NS * 8;
+    constexpr int smem = NS * 256 * kTileRows * (int)sizeof(T) + 2 * NS * 8;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     static int sm_count = [] { int d = 0, c = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, d); return c > 0 ? c : 148; }();
