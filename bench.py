@@ -52,13 +52,15 @@ WORKLOADS["pga_points_compact"] = ((3, 0, 1), "f32", 28, 24, "points/s")
 WORKLOADS["cl8_fixed_gp"] = ((8, 0, 0), "f32", 24, 2048, "products/s")
 # the same product in the reference's own precision, on the FP64 tensor pipe (DMMA)
 WORKLOADS["cl8_fixed_gp_f64"] = ((8, 0, 0), "f64", 24, 4096, "products/s")
-# the same two products with the matrix representation switched off: the dense nb x nb GEMM of round 1 (tensor-pipe bound)
-WORKLOADS["cl8_fixed_gp_gemm"] = ((8, 0, 0), "f32", 24, 2048, "products/s")
+# Library defaults: f32 = the dense nb x nb GEMM on tcgen05 (cl8_fixed_gp, tensor-bound), f64 = K8, block-diagonalised in the
+# M16(R) representation (cl8_fixed_gp_f64, HBM-side bound).  The two other combinations are measured beside them:
+# cl8_fixed_gp_rep = K8 in f32 (option matrix_rep = 2), cl8_fixed_gp_f64_gemm = the round-1 DMMA GEMM (matrix_rep = 0)
+WORKLOADS["cl8_fixed_gp_rep"] = ((8, 0, 0), "f32", 24, 2048, "products/s")
 WORKLOADS["cl8_fixed_gp_f64_gemm"] = ((8, 0, 0), "f64", 24, 4096, "products/s")
-CL8_WORKLOADS = ("cl8_fixed_gp", "cl8_fixed_gp_f64", "cl8_fixed_gp_gemm", "cl8_fixed_gp_f64_gemm")
+CL8_WORKLOADS = ("cl8_fixed_gp", "cl8_fixed_gp_f64", "cl8_fixed_gp_rep", "cl8_fixed_gp_f64_gemm")
 # tensor flops of the dense multiplication-matrix GEMM (f32: three tf32 MMAs per term); the default K8 path needs 16x fewer
 # flops and is HBM-bound, so only the *_gemm variants report against the tensor roofline
-TENSOR_FLOPS_PER_UNIT = {"cl8_fixed_gp_gemm": 3 * 2 * 256 * 256, "cl8_fixed_gp_f64_gemm": 2 * 256 * 256}
+TENSOR_FLOPS_PER_UNIT = {"cl8_fixed_gp": 3 * 2 * 256 * 256, "cl8_fixed_gp_f64_gemm": 2 * 256 * 256}
 # the headline input is a PGA point (12 of its 16 blade rows are zeros); this variant streams 16 dense rows
 WORKLOADS["pga_sandwich_dense16"] = ((3, 0, 1), "f32", 28, 128, "points/s")
 HEADLINE = "pga_sandwich"
@@ -191,7 +193,7 @@ def cpu_rate(workload, sample_rows, threads, repeats=1):
 def cpu_sample_rows(workload):
     return {"pga_sandwich": 1 << 25, "cga_gp": 1 << 22, "cga_gp_outer": 1 << 22, "r3_gp": 1 << 20, "sta_grade_inner_sum": 1 << 23,
             "sta_fused_grade_inner_sum": 1 << 23,
-            "cl8_fixed_gp": 1 << 14, "cl8_fixed_gp_f64": 1 << 14, "cl8_fixed_gp_gemm": 1 << 14, "cl8_fixed_gp_f64_gemm": 1 << 14, "pga_points_compact": 1 << 25, "pga_sandwich_dense16": 1 << 25}[workload]
+            "cl8_fixed_gp": 1 << 14, "cl8_fixed_gp_f64": 1 << 14, "cl8_fixed_gp_rep": 1 << 14, "cl8_fixed_gp_f64_gemm": 1 << 14, "pga_points_compact": 1 << 25, "pga_sandwich_dense16": 1 << 25}[workload]
 
 
 def run_reference_arm(args):
@@ -239,9 +241,9 @@ def workload_name(wl, n=None):
         "pga_sandwich": "PGA Cl(3,0,1) motor sandwich", "cga_gp": "CGA Cl(4,1,0) batched geometric product",
         "cga_gp_outer": "CGA Cl(4,1,0) fused geometric + outer product", "r3_gp": "Cl(3,0,0) batched geometric product",
         "sta_grade_inner_sum": "STA Cl(1,3,0) grade projection + inner product + batch sum",
-        "cl8_fixed_gp": "Cl(8,0,0) fixed-operand left geometric product (K8: block-diagonalised in the M16(R) representation)",
+        "cl8_fixed_gp": "Cl(8,0,0) fixed-operand left geometric product as the dense 256 x 256 GEMM (tcgen05, 3xTF32)",
         "cl8_fixed_gp_f64": "Cl(8,0,0) fixed-operand left geometric product, f64 (K8: block-diagonalised in the M16(R) representation)",
-        "cl8_fixed_gp_gemm": "Cl(8,0,0) fixed-operand left geometric product as the dense 256 x 256 GEMM (tcgen05, 3xTF32)",
+        "cl8_fixed_gp_rep": "Cl(8,0,0) fixed-operand left geometric product, f32 through K8 (block-diagonalised in the M16(R) representation)",
         "cl8_fixed_gp_f64_gemm": "Cl(8,0,0) fixed-operand left geometric product as the dense 256 x 256 GEMM, f64 (mma.sync m8n8k4 DMMA)",
         "sta_fused_grade_inner_sum": "STA Cl(1,3,0) fused grade projection + inner product + batch sum (one kernel)",
         "pga_points_compact": "PGA Cl(3,0,1) motor applied to compact (N,3) points, embed + sandwich + extract fused",
@@ -466,13 +468,14 @@ def setup_workload(ctx, wl, n, layout="soa", collective=True, ld_pad=0):
         fixed = a[:, 0].to(torch.float64).cpu().numpy().copy()  # the fixed operand, known on the host (as in MultivectorBatch.from_numpy(1 x nb))
         fptr = fixed.ctypes.data_as(C.POINTER(C.c_double))
         keep.update(a=a, b=b, out=out, fixed=fixed)
-        # cl8_fixed_gp / _f64: lcc_batch_fixed_product -- block-diagonalised in the algebra's 16 x 16 matrix representation (K8)
-        # *_gemm: option matrix_rep = 0 -- the dense multiplication-matrix GEMM on the tensor cores (K6 tcgen05 / K6d DMMA)
-        rep = 0 if wl.endswith("_gemm") else 1
+        # lcc_batch_fixed_product; the option selects K8 (block-diagonalised in the 16 x 16 matrix representation) or the dense
+        # multiplication-matrix GEMM on the tensor cores (K6 tcgen05 / K6d DMMA) -- see WORKLOADS for which is the default
+        rep = {"cl8_fixed_gp": 0, "cl8_fixed_gp_f64_gemm": 0, "cl8_fixed_gp_rep": 2, "cl8_fixed_gp_f64": 2}[wl]
 
         def step():
             cabi.check(lib.lcc_set_option(b"matrix_rep", rep))
             cabi.check(lib.lcc_batch_fixed_product(alg.h, cabi.LCC_OP_GP, 0, fptr, C.byref(vb), C.byref(vo), flags, sptr))
+            cabi.check(lib.lcc_set_option(b"matrix_rep", 1))  # back to the library default
 
         def parity():
             sub = idx[::64]
@@ -635,7 +638,7 @@ def run_gpu_arm(args):
                   "roofline_per_gpu": roofline_block(HEADLINE, sn, srec2["ms_per_step"], bytes_per, peaks, peak_kind, None)}
         strong.update(srec2)
         for swl, slayout in (("r3_gp", "soa"), ("cga_gp_outer", "soa"), ("cga_gp", "aos"), ("sta_grade_inner_sum", "soa"), ("cl8_fixed_gp", "soa"),
-                             ("cl8_fixed_gp_f64", "soa"), ("cl8_fixed_gp_gemm", "soa"), ("cl8_fixed_gp_f64_gemm", "soa"), ("pga_sandwich_dense16", "soa"), ("pga_sandwich", "aos")):
+                             ("cl8_fixed_gp_f64", "soa"), ("cl8_fixed_gp_rep", "soa"), ("cl8_fixed_gp_f64_gemm", "soa"), ("pga_sandwich_dense16", "soa"), ("pga_sandwich", "aos")):
             try:
                 r = secondary_record(ctx, swl, k, peaks, peak_kind, layout=slayout)
             except Exception as exc:  # one workload failing must not take the headline line down

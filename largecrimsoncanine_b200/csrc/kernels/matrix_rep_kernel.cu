@@ -24,6 +24,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
+#include <type_traits>
 
 #include "launch_args.h"
 #include "misc_kernels.cuh"
@@ -32,7 +34,6 @@
 namespace lcc {
 namespace {
 
-constexpr int kTileRows = 32;
 constexpr int kConsumerWarps = 16, kConsumers = kConsumerWarps * 32, kThreadsRep = kConsumers + 32;
 
 template <typename T> struct RepParams {
@@ -40,6 +41,9 @@ template <typename T> struct RepParams {
     T p2[256];           // second factor (sandwich only), applied from the right
     uint8_t blade[256];  // string (a << 4 | b) -> blade index
     int8_t sign[256];    // string -> +1 / -1, 0 when no blade maps to the string (128-blade algebras)
+    // the string -> blade map is LINEAR over F_2 (the string of a product of blades is the XOR of their strings), so
+    // blade(a << 4 | b) = lin_hi(a) ^ lin_lo(b): the kernel needs 8 bytes, not a table lookup per element
+    uint8_t lin[8];      // image of string bit i (bits 0-3 = b, bits 4-7 = a)
 };
 
 template <typename T> __device__ __forceinline__ void wht16(T (&v)[16]) {
@@ -68,101 +72,160 @@ __device__ __forceinline__ float tf32_rna(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// (not volatile: pure functions of their operands, so the compiler may interleave independent accumulation chains)
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], float b0, float b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
-                   "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+          "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
 }
 __device__ __forceinline__ void mma_f64(double (&d)[2], double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
 }
 
-// The fixed 16 x 16 factor as MMA A-fragments, loaded once per kernel from the parameter block.
+// The fixed 16 x 16 factor as MMA A-fragments.  They depend on the lane only, so warp 0 builds them once per kernel from
+// the parameter block into shared memory ([chunk][lane], 16 bytes per lane and chunk: conflict-free LDS.128) and every
+// warp re-reads the chunk it needs right before its MMAs.  (Held in registers for the whole kernel they did not survive
+// the 96-register budget: ptxas re-materialised them inside the tile loop with lane-indexed constant loads, and the
+// MMAs waited on those -- 40 % of all stall samples in profiles/r02_prof_k8_v2_f64.)
 template <typename T> struct Factor;
-template <> struct Factor<float> {  // m16n8k8, 3xTF32: hi + lo parts, two k-steps
-    float hi[2][4], lo[2][4];
-    __device__ __forceinline__ void load(const float *p, int g, int t) {
+template <> struct Factor<float> {  // m16n8k8, 3xTF32: chunks hi[ks=0], lo[0], hi[1], lo[1]
+    static constexpr int kChunks = 4;
+    const float4 *frag;
+    static __device__ __forceinline__ void build(float4 *dst, const float *p, int lane) {
+        const int g = lane >> 2, t = lane & 3;
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
             const float a[4] = {p[g * 16 + 8 * ks + t], p[(g + 8) * 16 + 8 * ks + t], p[g * 16 + 8 * ks + t + 4], p[(g + 8) * 16 + 8 * ks + t + 4]};
+            float hi[4], lo[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { hi[ks][e] = tf32_rna(a[e]); lo[ks][e] = tf32_rna(a[e] - hi[ks][e]); }
+            for (int e = 0; e < 4; ++e) { hi[e] = tf32_rna(a[e]); lo[e] = tf32_rna(a[e] - hi[e]); }
+            dst[(2 * ks) * 32 + lane] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            dst[(2 * ks + 1) * 32 + lane] = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
     }
 };
-template <> struct Factor<double> {  // m8n8k4: two m-blocks x four k-steps
-    double a[2][4];
-    __device__ __forceinline__ void load(const double *p, int g, int t) {
+template <> struct Factor<double> {  // m8n8k4: chunk ks = {a[mb = 0][ks], a[mb = 1][ks]}
+    static constexpr int kChunks = 4;
+    const double2 *frag;
+    static __device__ __forceinline__ void build(double2 *dst, const double *p, int lane) {
+        const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-        for (int mb = 0; mb < 2; ++mb)
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) a[mb][ks] = p[(8 * mb + g) * 16 + 4 * ks + t];
+        for (int ks = 0; ks < 4; ++ks) dst[ks * 32 + lane] = make_double2(p[g * 16 + 4 * ks + t], p[(8 + g) * 16 + 4 * ks + t]);
     }
 };
 
-// D = F * Z for the 32 rows of one column (second index = w) of the matrix in `st`, in place: Z[k][w] -> D[o][w].
-// Four n-blocks of 8 rows; every B fragment of an n-block is read before its D fragments are written.
-__device__ __forceinline__ void column_gemm(float *st, const Factor<float> &F, int w, int g, int t) {
+// D = F * Z for all rows of one column (second index = w) of the matrix in `st`, in place: Z[k][w] -> D[o][w].
+// n-blocks of 8 rows, kQ of them side by side so that their accumulation chains (6 dependent MMAs for f32, 4 for f64)
+// overlap; every B fragment of a group of n-blocks is read before any of its D fragments is written.
+template <int TR>
+__device__ __forceinline__ void column_gemm(float *st, const Factor<float> &F, int w, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int kQ = 4;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        float d[4] = {0.f, 0.f, 0.f, 0.f};
-        float b[2][2];
+    for (int q0 = 0; q0 < TR / 8; q0 += kQ) {
+        float d[kQ][4], b[kQ][2][2];
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks)
+        for (int qq = 0; qq < kQ; ++qq) {
+            const int q = q0 + qq;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) b[ks][h] = st[((8 * ks + 4 * h + t) * 16 + w) * kTileRows + (8 * (q ^ t) + g)];  // (8q + g) ^ (t << 3)
+            for (int e = 0; e < 4; ++e) d[qq][e] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)  // row (8q + g) of the half it is in, XOR (t << 3)
+                    b[qq][ks][h] = st[((8 * ks + 4 * h + t) * 16 + w) * TR + (q >> 2) * 32 + (8 * ((q & 3) ^ t) + g)];
+        }
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
-            const float b0 = tf32_rna(b[ks][0]), b1 = tf32_rna(b[ks][1]);
-            const float l0 = tf32_rna(b[ks][0] - b0), l1 = tf32_rna(b[ks][1] - b1);
-            mma_tf32(d, F.lo[ks], b0, b1);   // small terms first
-            mma_tf32(d, F.hi[ks], l0, l1);
-            mma_tf32(d, F.hi[ks], b0, b1);
+            const float4 fh = F.frag[(2 * ks) * 32 + lane], fl = F.frag[(2 * ks + 1) * 32 + lane];
+            const float hi[4] = {fh.x, fh.y, fh.z, fh.w}, lo[4] = {fl.x, fl.y, fl.z, fl.w};
+            float bh[kQ][2], bl[kQ][2];
+#pragma unroll
+            for (int qq = 0; qq < kQ; ++qq)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) { bh[qq][h] = tf32_rna(b[qq][ks][h]); bl[qq][h] = tf32_rna(b[qq][ks][h] - bh[qq][h]); }
+#pragma unroll
+            for (int qq = 0; qq < kQ; ++qq) mma_tf32(d[qq], lo, bh[qq][0], bh[qq][1]);  // small terms first
+#pragma unroll
+            for (int qq = 0; qq < kQ; ++qq) mma_tf32(d[qq], hi, bl[qq][0], bl[qq][1]);
+#pragma unroll
+            for (int qq = 0; qq < kQ; ++qq) mma_tf32(d[qq], hi, bh[qq][0], bh[qq][1]);
         }
-        const int pos = 8 * (q ^ (g & 3)) + 2 * t;  // (8q + 2t) ^ ((g & 3) << 3); rows 2t, 2t+1 stay adjacent
-        *reinterpret_cast<float2 *>(st + (g * 16 + w) * kTileRows + pos) = make_float2(d[0], d[1]);
-        *reinterpret_cast<float2 *>(st + ((g + 8) * 16 + w) * kTileRows + pos) = make_float2(d[2], d[3]);
+#pragma unroll
+        for (int qq = 0; qq < kQ; ++qq) {
+            const int q = q0 + qq;
+            const int pos = (q >> 2) * 32 + 8 * ((q & 3) ^ (g & 3)) + 2 * t;  // (8q + 2t) ^ ((g & 3) << 3); rows 2t, 2t+1 stay adjacent
+            *reinterpret_cast<float2 *>(st + (g * 16 + w) * TR + pos) = make_float2(d[qq][0], d[qq][1]);
+            *reinterpret_cast<float2 *>(st + ((g + 8) * 16 + w) * TR + pos) = make_float2(d[qq][2], d[qq][3]);
+        }
     }
 }
-__device__ __forceinline__ void column_gemm(double *st, const Factor<double> &F, int w, int g, int t) {
+template <int TR>
+__device__ __forceinline__ void column_gemm(double *st, const Factor<double> &F, int w, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int kQ = 2;
     const int sb = ((t & 1) << 3) | ((t & 2) << 1), sd = ((g & 1) << 3) | ((g & 2) << 1);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        double d[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-        double b[4];
+    for (int q0 = 0; q0 < TR / 8; q0 += kQ) {
+        double d[kQ][2][2], b[kQ][4];
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) b[ks] = st[((4 * ks + t) * 16 + w) * kTileRows + ((8 * q + g) ^ sb)];
+        for (int qq = 0; qq < kQ; ++qq) {
+            const int q = q0 + qq;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
+            for (int mb = 0; mb < 2; ++mb) d[qq][mb][0] = d[qq][mb][1] = 0.0;
 #pragma unroll
-            for (int mb = 0; mb < 2; ++mb) mma_f64(d[mb], F.a[mb][ks], b[ks]);
-        const int pos = (8 * q + 2 * t) ^ sd;
+            for (int ks = 0; ks < 4; ++ks) b[qq][ks] = st[((4 * ks + t) * 16 + w) * TR + (q >> 2) * 32 + (((8 * (q & 3)) + g) ^ sb)];
+        }
 #pragma unroll
-        for (int mb = 0; mb < 2; ++mb)
-            *reinterpret_cast<double2 *>(st + ((8 * mb + g) * 16 + w) * kTileRows + pos) = make_double2(d[mb][0], d[mb][1]);
+        for (int ks = 0; ks < 4; ++ks) {
+            const double2 f = F.frag[ks * 32 + lane];
+#pragma unroll
+            for (int qq = 0; qq < kQ; ++qq) {
+                mma_f64(d[qq][0], f.x, b[qq][ks]);
+                mma_f64(d[qq][1], f.y, b[qq][ks]);
+            }
+        }
+#pragma unroll
+        for (int qq = 0; qq < kQ; ++qq) {
+            const int q = q0 + qq;
+            const int pos = (q >> 2) * 32 + ((8 * (q & 3) + 2 * t) ^ sd);
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+                *reinterpret_cast<double2 *>(st + ((8 * mb + g) * 16 + w) * TR + pos) = make_double2(d[qq][mb][0], d[qq][mb][1]);
+        }
     }
 }
+
+template <typename T> struct RepShape;  // rows per tile (32 per lane-row) and ring depth
+template <> struct RepShape<float> { static constexpr int kRowsPerLane = 2, kStages = 3; };   // 64-row tiles: 256-byte TMA segments, 64 KB stages
+template <> struct RepShape<double> { static constexpr int kRowsPerLane = 1, kStages = 3; };  // 32-row tiles: 256-byte TMA segments, 64 KB stages
 
 // MODE 0: out = M * x      C = P1 X            matrix slots hold X / C as (row index, column index)
 // MODE 1: out = x * M      C^T = P1 X^T        the same column GEMM on the TRANSPOSED slots (p1 arrives as [j][k] = rho(M)[k][j])
 // MODE 2: out = R x ~R     T = P1 X, transpose pass, C^T = P2 T^T   (p1 = rho(R) / 16, p2[j][k] = rho(~R)[k][j])
-template <typename T, int MODE, int NS>
+template <typename T, int MODE>
 __global__ void __launch_bounds__(kThreadsRep, 1)
 matrix_rep_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_out,
-                  const __grid_constant__ RepParams<T> P, int nb, int64_t n) {
-    constexpr uint32_t kStageElems = 256 * kTileRows;
-    constexpr uint32_t kStageBytes = kStageElems * sizeof(T);
+                  const __grid_constant__ RepParams<T> P, int nb, int64_t n, int dbg) {
+    constexpr int RPL = RepShape<T>::kRowsPerLane, TR = 32 * RPL, NS = RepShape<T>::kStages;
+    constexpr uint32_t kStageBytes = 256u * TR * sizeof(T);
     extern __shared__ __align__(1024) uint8_t smem[];  // no static shared memory in this kernel: the window starts aligned
     uint64_t *bars = (uint64_t *)(smem + (size_t)NS * kStageBytes);
     uint64_t *full = bars, *done = bars + NS;
+    using Frag = typename std::remove_const<typename std::remove_pointer<decltype(Factor<T>::frag)>::type>::type;
+    Frag *frag1 = (Frag *)(smem + (size_t)NS * kStageBytes + 64), *frag2 = frag1 + Factor<T>::kChunks * 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) { tma::mbar_init(&full[s], 1); tma::mbar_init(&done[s], 1); }
     }
+    if (warp == 0) {
+        Factor<T>::build(frag1, P.p1, lane);
+        if (MODE == 2) Factor<T>::build(frag2, P.p2, lane);
+    }
     __syncthreads();
-    const int64_t tiles = (n + kTileRows - 1) / kTileRows;
-    const uint32_t box_bytes = (uint32_t)nb * kTileRows * sizeof(T);
+    const int64_t tiles = (n + TR - 1) / TR;
+    const uint32_t box_bytes = (uint32_t)nb * TR * sizeof(T);
 
     if (warp == kConsumerWarps) {            // ---- the TMA warp: one thread streams tiles in and hands finished stages back
         if (lane == 0) {
@@ -171,32 +234,35 @@ matrix_rep_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             const int64_t mine = tiles > blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
             for (int64_t k = 0; k < mine && k < NS; ++k) {  // fill the ring
                 tma::mbar_expect_tx(&full[k], box_bytes);
-                tma::load_2d(smem + (size_t)k * kStageBytes, &map_x, &full[k], (int)((blockIdx.x + k * gridDim.x) * kTileRows), 0);
+                tma::load_2d(smem + (size_t)k * kStageBytes, &map_x, &full[k], (int)((blockIdx.x + k * gridDim.x) * TR), 0);
             }
             int s = 0; uint32_t ph = 0;
             for (int64_t k = 0; k < mine; ++k) {
                 tma::mbar_wait(&done[s], ph);
-                tma::store_2d(&map_out, smem + (size_t)s * kStageBytes, (int)((blockIdx.x + k * gridDim.x) * kTileRows), 0);
+                tma::store_2d(&map_out, smem + (size_t)s * kStageBytes, (int)((blockIdx.x + k * gridDim.x) * TR), 0);
                 tma::store_commit_and_wait_read();  // the engine has read the stage: refill it with the tile NS ahead
                 if (k + NS < mine) {
                     tma::mbar_expect_tx(&full[s], box_bytes);
-                    tma::load_2d(smem + (size_t)s * kStageBytes, &map_x, &full[s], (int)((blockIdx.x + (k + NS) * gridDim.x) * kTileRows), 0);
+                    tma::load_2d(smem + (size_t)s * kStageBytes, &map_x, &full[s], (int)((blockIdx.x + (k + NS) * gridDim.x) * TR), 0);
                 }
                 if (++s == NS) { s = 0; ph ^= 1; }
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // global writes complete before the CTA exits
         }
-    } else {                                  // ---- 16 consumer warps: warp w = one index (a, j or c), lane = row
-        const int w = warp, g = lane >> 2, t4 = lane & 3;
+    } else {                                  // ---- 16 consumer warps: warp w = one index (a, j or c), lane = row (and row + 32)
+        const int w = warp;
         // per-thread tables, built once: where the 16 blades of string row w live in a stage and their signs; where the 16
         // matrix entries this thread transforms live (stage 1 writes them, stage 3 reads them)
-        int off_blade[16], off_first[16], off_last[16];
+        int off_first[16], off_last[MODE == 2 ? 16 : 1];  // modes 0 and 1 end on the slots they started on
         uint32_t neg = 0, valid = 0;
+        int blade_hi = 0;   // blade of string (w << 4): the part of the blade index that depends on the warp
+        int blade_lo[16];   // blade of string b: the same for every thread of the grid (uniform registers)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) blade_hi ^= ((w >> i) & 1) ? (int)P.lin[4 + i] : 0;
 #pragma unroll
         for (int b = 0; b < 16; ++b) {
-            const int str = (w << 4) | b;
-            const int sg = P.sign[str];
-            off_blade[b] = (int)P.blade[str] * kTileRows + lane;
+            blade_lo[b] = ((b & 1) ? (int)P.lin[0] : 0) ^ ((b & 2) ? (int)P.lin[1] : 0) ^ ((b & 4) ? (int)P.lin[2] : 0) ^ ((b & 8) ? (int)P.lin[3] : 0);
+            const int sg = P.sign[(w << 4) | b];
             neg |= (sg < 0 ? 1u : 0u) << b;
             valid |= (sg != 0 ? 1u : 0u) << b;
         }
@@ -204,51 +270,70 @@ matrix_rep_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         for (int j = 0; j < 16; ++j) {
             // X[j^w][j] (normal slots) or, transposed, X^T[j][j^w]
             const int f1 = MODE == 1 ? j : (j ^ w), s1 = MODE == 1 ? (j ^ w) : j;
-            off_first[j] = (f1 * 16 + s1) * kTileRows + (lane ^ Swz<T>::of(f1));
-            const int f3 = MODE == 0 ? (j ^ w) : j, s3 = MODE == 0 ? j : (j ^ w);  // modes 1 and 2 end on transposed slots
-            off_last[j] = (f3 * 16 + s3) * kTileRows + (lane ^ Swz<T>::of(f3));
+            off_first[j] = (f1 * 16 + s1) * TR + (lane ^ Swz<T>::of(f1));
+            if (MODE == 2) off_last[j] = (j * 16 + (j ^ w)) * TR + (lane ^ Swz<T>::of(j));  // the sandwich ends on transposed slots
         }
         Factor<T> F1, F2;
-        F1.load(P.p1, g, t4);
-        if (MODE == 2) F2.load(P.p2, g, t4);
+        F1.frag = frag1;
+        F2.frag = frag2;
         int s = 0; uint32_t ph = 0;
         for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
             T *st = (T *)(smem + (size_t)s * kStageBytes);
             tma::mbar_wait(&full[s], ph);
-            T v[16];
+            if (dbg == 1) {  // LCC_K8_DEBUG=1: tiles pass through untouched (memory pipeline alone)
+                consumer_sync();
+                if (threadIdx.x == 0) mbar_arrive(&done[s]);
+                if (++s == NS) { s = 0; ph ^= 1; }
+                continue;
+            }
+            T v[RPL][16];
             // stage 1: gather y[w][.] from the blade slots, transform, scatter to the matrix slots
 #pragma unroll
-            for (int b = 0; b < 16; ++b) {
-                const T x = st[off_blade[b]];
-                v[b] = ((valid >> b) & 1u) ? (((neg >> b) & 1u) ? -x : x) : T(0);
-            }
-            wht16(v);
+            for (int h = 0; h < RPL; ++h)
+#pragma unroll
+                for (int b = 0; b < 16; ++b) {
+                    const T x = st[(blade_hi ^ blade_lo[b]) * TR + lane + 32 * h];
+                    v[h][b] = ((valid >> b) & 1u) ? (((neg >> b) & 1u) ? -x : x) : T(0);
+                }
+#pragma unroll
+            for (int h = 0; h < RPL; ++h) wht16(v[h]);
             consumer_sync();  // every blade slot has been read
 #pragma unroll
-            for (int j = 0; j < 16; ++j) st[off_first[j]] = v[j];
+            for (int h = 0; h < RPL; ++h)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) st[off_first[j] + 32 * h] = v[h][j];
             consumer_sync();
             // stage 2 on the tensor cores: the column with second index w, in place
-            column_gemm(st, F1, w, g, t4);
+            if (dbg != 2) column_gemm<TR>(st, F1, w, lane);  // LCC_K8_DEBUG=2: transforms only
             if (MODE == 2) {
                 consumer_sync();
                 // transpose pass: T[i][w] -> T^T[w][i] (the first index is warp-uniform on both sides: conflict free)
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = st[(i * 16 + w) * kTileRows + (lane ^ Swz<T>::of(i))];
+                for (int h = 0; h < RPL; ++h)
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[h][i] = st[(i * 16 + w) * TR + 32 * h + (lane ^ Swz<T>::of(i))];
                 consumer_sync();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) st[(w * 16 + i) * kTileRows + (lane ^ Swz<T>::of(w))] = v[i];
+                for (int h = 0; h < RPL; ++h)
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) st[(w * 16 + i) * TR + 32 * h + (lane ^ Swz<T>::of(w))] = v[h][i];
                 consumer_sync();
-                column_gemm(st, F2, w, g, t4);
+                column_gemm<TR>(st, F2, w, lane);
             }
             consumer_sync();
             // stage 3: gather the 16 matrix entries of string row w, transform back, scatter to the blade slots
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = st[off_last[j]];
-            wht16(v);
+            for (int h = 0; h < RPL; ++h)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[h][j] = st[(MODE == 2 ? off_last[j] : off_first[j]) + 32 * h];
+#pragma unroll
+            for (int h = 0; h < RPL; ++h) wht16(v[h]);
             consumer_sync();  // every matrix slot has been read
 #pragma unroll
-            for (int b = 0; b < 16; ++b)
-                if ((valid >> b) & 1u) st[off_blade[b]] = ((neg >> b) & 1u) ? -v[b] : v[b];
+            for (int h = 0; h < RPL; ++h)
+#pragma unroll
+                for (int b = 0; b < 16; ++b)
+                    if ((valid >> b) & 1u) st[(blade_hi ^ blade_lo[b]) * TR + lane + 32 * h] = ((neg >> b) & 1u) ? -v[h][b] : v[h][b];
             tma::fence_proxy_async();
             consumer_sync();
             if (threadIdx.x == 0) mbar_arrive(&done[s]);
@@ -257,22 +342,21 @@ matrix_rep_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     }
 }
 
-template <typename T> struct RepStages { static constexpr int value = sizeof(T) == 4 ? 5 : 3; };  // 160 / 192 KB of stages
-
 template <typename T, int MODE>
 cudaError_t launch_rep_t(int nb, const void *x, int64_t ldx, void *out, int64_t ldo, int64_t n, const RepParams<T> &P, cudaStream_t s) {
-    constexpr int NS = RepStages<T>::value;
+    constexpr int TR = 32 * RepShape<T>::kRowsPerLane, NS = RepShape<T>::kStages;
     CUtensorMap mx, mo;
-    if (!make_soa_tensor_map(&mx, x, (int)sizeof(T), nb, ldx, n, kTileRows) || !make_soa_tensor_map(&mo, out, (int)sizeof(T), nb, ldo, n, kTileRows))
+    if (!make_soa_tensor_map(&mx, x, (int)sizeof(T), nb, ldx, n, TR) || !make_soa_tensor_map(&mo, out, (int)sizeof(T), nb, ldo, n, TR))
         return cudaErrorNotSupported;
-    auto kernel = matrix_rep_kernel<T, MODE, NS>;
-    constexpr int smem = NS * 256 * kTileRows * (int)sizeof(T) + 2 * NS * 8;
+    auto kernel = matrix_rep_kernel<T, MODE>;
+    constexpr int smem = NS * 256 * TR * (int)sizeof(T) + 64 + 2 * Factor<T>::kChunks * 32 * 16;  // stages, barriers, two factors
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     static int sm_count = [] { int d = 0, c = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, d); return c > 0 ? c : 148; }();
-    const int64_t tiles = (n + kTileRows - 1) / kTileRows;
+    const int64_t tiles = (n + TR - 1) / TR;
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
-    kernel<<<grid, kThreadsRep, smem, s>>>(mx, mo, P, nb, n);
+    static const int dbg = [] { const char *e = getenv("LCC_K8_DEBUG"); return e ? atoi(e) : 0; }();
+    kernel<<<grid, kThreadsRep, smem, s>>>(mx, mo, P, nb, n, dbg);
     note_kernel_launch();
     return cudaGetLastError();
 }
@@ -286,6 +370,29 @@ cudaError_t launch_rep(int nb, int mode, const double *p1, const double *p2, con
         P.p2[i] = p2 ? (T)p2[i] : T(0);
         P.blade[i] = blade_at[i];
         P.sign[i] = sign_at[i];
+    }
+    // linear extension of string -> blade to all 256 strings: close the valid (string, blade) pairs of the basis blades
+    // under XOR; a 128-blade algebra spans only half the strings, the other half gets blade indices 128..255 (slots that
+    // exist in a stage but hold no data: such strings are masked out by sign == 0 anyway)
+    {
+        int lin[256], have[256];
+        for (int i = 0; i < 256; ++i) { lin[i] = 0; have[i] = 0; }
+        have[0] = 1;
+        int count = 1, next_blade = 1;
+        auto add = [&](int str, int blade) {
+            if (have[str]) return;
+            for (int t = 0; t < 256; ++t)
+                if (have[t] == 1) { lin[t ^ str] = lin[t] ^ blade; have[t ^ str] = 2; }
+            for (int t = 0; t < 256; ++t) if (have[t] == 2) have[t] = 1;
+            count *= 2;
+        };
+        for (int str = 1; str < 256; ++str)
+            if (sign_at[str] != 0 && (blade_at[str] & (blade_at[str] - 1)) == 0) { add(str, blade_at[str]); if (blade_at[str] >= next_blade) next_blade = blade_at[str] << 1; }
+        for (int str = 1; str < 256 && count < 256; ++str)
+            if (!have[str]) { add(str, next_blade); next_blade <<= 1; }
+        for (int str = 0; str < 256; ++str)
+            if (sign_at[str] != 0 && lin[str] != blade_at[str]) return cudaErrorNotSupported;  // cannot happen for a homomorphism
+        for (int i = 0; i < 8; ++i) P.lin[i] = (uint8_t)lin[1 << i];
     }
     switch (mode) {
         case 0: return launch_rep_t<T, 0>(nb, x.data, x.ld, out.data, out.ld, x.n, P, s);
