@@ -49,7 +49,8 @@ struct SandwichArgs {
     bool strict = false;
     bool even = false;  // rotor has no odd-grade part: odd blades are pruned at compile time
     int64_t n = 0;
-    const double *rotor = nullptr;  // host, num_blades
+    const double *rotor = nullptr;  // host, num_blades (one rotor for the whole batch, kernel parameters)
+    const void *rotors = nullptr; int64_t ldr = 0; bool r_bcast = false;  // or: device rotors, one per row (r_bcast: one row for all)
     const void *x = nullptr; int64_t ldx = 0;
     void *out = nullptr; int64_t ldo = 0;
     const double *mu = nullptr;

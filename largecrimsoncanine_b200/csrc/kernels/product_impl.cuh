@@ -914,6 +914,109 @@ cudaError_t pga_points_sandwich(const SandwichArgs &g) {
 #endif
 #endif  // PGA3D
 
+// ------------------------------------------------------------------------------------------ K2r: one rotor PER ROW
+// out[row] = R[row] * x[row] * ~R[row]  (reference: lcc/torch/multivector.py:988-1019 -- rx = gp(R, x), then gp(rx, ~R)
+// with ~R = R * reverse signs).  One pass: R and x in registers, the intermediate rx rounded to storage precision as the
+// reference's tensor, ~R never materialised (its sign is folded into the term's sign at compile time).  3 * nb * s bytes
+// per row instead of the 8 * nb * s of reverse + two products through two full-size temporaries.  `r_bcast`: one rotor
+// row on the DEVICE for the whole batch (what lcc.torch has when the rotor is a CUDA tensor: no host read-back).
+__host__ __device__ constexpr bool reverse_negative(int blade) {
+    int g = 0;
+    for (int b = blade; b; b >>= 1) g += b & 1;
+    return (g % 4) >= 2;  // blades.rs:128-135
+}
+
+template <int LAYOUT, bool STRICT>
+__global__ void __launch_bounds__(kThreads)
+sandwich_rows_kernel(const real *__restrict__ r, int64_t ldr, int r_bcast, const real *__restrict__ x, int64_t ldx,
+                     real *__restrict__ out, int64_t ldo, int64_t n, int vec_ok, const Coeffs mu) {
+    constexpr int V = LAYOUT == kSoA ? kRowsSoA : 1;
+    const int64_t r0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
+    if (r0 >= n) return;
+    Tile<real, NB, V> R, X, RX;
+    if constexpr (LAYOUT == kSoA) { load_soa(R, r, ldr, r0, r_bcast != 0); load_soa(X, x, ldx, r0, false); }
+    else { load_aos(R, r, ldr, r0, r_bcast != 0, vec_ok != 0); load_aos(X, x, ldx, r0, false, vec_ok != 0); }
+    (void)mu;
+#define LCC_OUT_BEGIN(k) { real acc[V]; _Pragma("unroll") for (int l = 0; l < V; ++l) acc[l] = real(0);
+#define LCC_TERM(k, i, j, neg, flags)                                                                   \
+    _Pragma("unroll") for (int l = 0; l < V; ++l) {                                                    \
+        real rv = (neg) ? -R.v[i][l] : R.v[i][l];                                                      \
+        if constexpr (kRuntimeMetric) rv = mul_rn(rv, mu.v[(i) & (j)]);                                \
+        acc[l] = Arith<STRICT>::madd(rv, X.v[j][l], acc[l]);                                           \
+    }
+#define LCC_OUT_END(k) _Pragma("unroll") for (int l = 0; l < V; ++l) RX.v[k][l] = acc[l]; }
+#include LCC_TERMS_FILE
+#undef LCC_TERM
+#undef LCC_OUT_END
+    Sink<LAYOUT, V> sink{out, ldo, r0, vec_ok != 0, {}};
+#define LCC_TERM(k, i, j, neg, flags)                                                                   \
+    _Pragma("unroll") for (int l = 0; l < V; ++l) {                                                    \
+        real av = (neg) ? -RX.v[i][l] : RX.v[i][l];                                                    \
+        if constexpr (kRuntimeMetric) av = mul_rn(av, mu.v[(i) & (j)]);                                \
+        const real rv = reverse_negative(j) ? -R.v[j][l] : R.v[j][l];                                  \
+        acc[l] = Arith<STRICT>::madd(av, rv, acc[l]);                                                  \
+    }
+#define LCC_OUT_END(k) sink.template put<k>(acc); }
+#include LCC_TERMS_FILE
+#undef LCC_OUT_BEGIN
+#undef LCC_TERM
+#undef LCC_OUT_END
+}
+
+// the same on TMA-staged AoS tiles (two input tiles; the result overwrites the x tile and leaves by TMA store)
+template <bool STRICT>
+__global__ void __launch_bounds__(TmaTile::kRows)
+sandwich_rows_kernel_aos_tma(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_x,
+                             const __grid_constant__ CUtensorMap map_out, const real *__restrict__ r_row, const Coeffs mu) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *tile_r = tma_smem_base(smem_raw), *tile_x = tile_r + TmaTile::kBytes;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(tile_x + TmaTile::kBytes);
+    const int t = threadIdx.x, row0 = blockIdx.x * TmaTile::kRows;
+    if (t == 0) {
+        tma::mbar_init(bar, 1);
+        tma::mbar_expect_tx(bar, (r_row ? 0u : (uint32_t)TmaTile::kBytes) + (uint32_t)TmaTile::kBytes);
+        if (!r_row) tma_load_tile(tile_r, &map_r, bar, row0, mu.stream_hint != 0);
+        tma_load_tile(tile_x, &map_x, bar, row0, mu.stream_hint != 0);
+    }
+    __syncthreads();
+    Tile<real, NB, 1> R, X, RX;
+    if (r_row) load_bcast_row(R, r_row);
+    tma::mbar_wait(bar, 0);
+    if (!r_row) load_tile_row(R, tile_r, t);
+    load_tile_row(X, tile_x, t);
+    (void)mu;
+#define LCC_OUT_BEGIN(k) { real acc[1]; acc[0] = real(0);
+#define LCC_TERM(k, i, j, neg, flags)                                                                   \
+    {                                                                                                  \
+        real rv = (neg) ? -R.v[i][0] : R.v[i][0];                                                      \
+        if constexpr (kRuntimeMetric) rv = mul_rn(rv, mu.v[(i) & (j)]);                                \
+        acc[0] = Arith<STRICT>::madd(rv, X.v[j][0], acc[0]);                                           \
+    }
+#define LCC_OUT_END(k) RX.v[k][0] = acc[0]; }
+#include LCC_TERMS_FILE
+#undef LCC_TERM
+#undef LCC_OUT_END
+    TileSink sink{tile_x, t, {}};
+#define LCC_TERM(k, i, j, neg, flags)                                                                   \
+    {                                                                                                  \
+        real av = (neg) ? -RX.v[i][0] : RX.v[i][0];                                                    \
+        if constexpr (kRuntimeMetric) av = mul_rn(av, mu.v[(i) & (j)]);                                \
+        const real rv = reverse_negative(j) ? -R.v[j][0] : R.v[j][0];                                  \
+        acc[0] = Arith<STRICT>::madd(av, rv, acc[0]);                                                  \
+    }
+#define LCC_OUT_END(k) sink.template put<k>(acc); }
+#include LCC_TERMS_FILE
+#undef LCC_OUT_BEGIN
+#undef LCC_TERM
+#undef LCC_OUT_END
+    tma::fence_proxy_async();
+    __syncthreads();
+    if (t == 0) {
+        tma_store_tile(&map_out, tile_x, row0, mu.stream_hint != 0);
+        tma::store_commit_and_wait_read();
+    }
+}
+
 // ------------------------------------------------------------------------------------------ entry points, by part
 // One (signature, precision) is compiled as several object files so that ptxas runs in parallel
 // (_build.py writes one stub per part):
@@ -922,6 +1025,7 @@ cudaError_t pga_points_sandwich(const SandwichArgs &g) {
 //   LCC_PART 3  sandwich kernels, direct and TMA             (LCC_PART_STRICT = 0 / 1)
 //   LCC_PART 4  fused product + batch-sum kernels and the two routers the dispatcher calls
 //   LCC_PART 5  vector-Jacobian products (direct and TMA forms)
+//   LCC_PART 6  per-row sandwich (direct and AoS-TMA forms, both rounding modes)
 cudaError_t product_direct_s0(const ProductArgs &g);
 cudaError_t product_direct_s1(const ProductArgs &g);
 cudaError_t product_tma_s0(const ProductArgs &g);  // cudaErrorNotSupported: operands do not qualify, use the direct kernels
@@ -929,11 +1033,12 @@ cudaError_t product_tma_s1(const ProductArgs &g);
 cudaError_t sandwich_s0(const SandwichArgs &g);
 cudaError_t sandwich_s1(const SandwichArgs &g);
 cudaError_t product_vjp(const ProductArgs &g);      // g.list = 1 / 2
+cudaError_t sandwich_rows(const SandwichArgs &g);   // g.rotors set: one rotor per row (or one device row for all)
 cudaError_t launch_product(const ProductArgs &g);
 cudaError_t launch_sandwich(const SandwichArgs &g);
 
 #ifndef LCC_PART
-#error "define LCC_PART (1-5) before including product_impl.cuh"
+#error "define LCC_PART (1-6) before including product_impl.cuh"
 #endif
 #ifndef LCC_PART_STRICT
 #define LCC_PART_STRICT 0
@@ -1014,6 +1119,46 @@ cudaError_t product_vjp(const ProductArgs &g) {
 }
 #endif  // LCC_PART == 5
 
+#if LCC_PART == 6
+template <int LAYOUT, bool STRICT> static cudaError_t launch_sandwich_rows_t(const SandwichArgs &g) {
+    if (g.n <= 0) return cudaSuccess;
+    if constexpr (NB > 16) {
+        return cudaErrorNotSupported;  // three 32-blade tiles do not fit the register file: the caller composes two products
+    } else {
+        constexpr int W = 16 / (int)sizeof(real);
+        const real *r = (const real *)g.rotors;
+        if constexpr (LAYOUT == kAoS && kHasTmaPath) {
+            if (tma_path_enabled() && g.n >= option_aos_tma_min_rows() * kAosNarrowRowFactor) {
+                CUtensorMap mr, mx, mo;
+                if (aos_map(&mx, g.x, g.ldx, g.n) && aos_map(&mo, g.out, g.ldo, g.n) && (g.r_bcast || aos_map(&mr, g.rotors, g.ldr, g.n))) {
+                    if (g.r_bcast) mr = mx;
+                    auto kernel = sandwich_rows_kernel_aos_tma<STRICT>;
+                    constexpr int smem = 2 * TmaTile::kBytes + 1024 + 16;
+                    const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                    if (attr != cudaSuccess) return attr;
+                    const unsigned grid = (unsigned)((g.n + TmaTile::kRows - 1) / TmaTile::kRows);
+                    kernel<<<grid, TmaTile::kRows, smem, g.stream>>>(mr, mx, mo, g.r_bcast ? r : nullptr, to_coeffs(g.mu, 1.0));
+                    note_kernel_launch();
+                    return cudaGetLastError();
+                }
+            }
+        }
+        int vec_ok = 1;
+        if (LAYOUT == kAoS)
+            vec_ok = ((uintptr_t)g.x % 16 == 0) && (g.ldx % W == 0) && ((uintptr_t)g.out % 16 == 0) && (g.ldo % W == 0) &&
+                     ((uintptr_t)g.rotors % 16 == 0) && (g.r_bcast || g.ldr % W == 0);
+        sandwich_rows_kernel<LAYOUT, STRICT><<<grid_for<LAYOUT>(g.n), block_threads(), 0, g.stream>>>(
+            r, g.ldr, g.r_bcast ? 1 : 0, (const real *)g.x, g.ldx, (real *)g.out, g.ldo, g.n, vec_ok, to_coeffs(g.mu, 1.0));
+        note_kernel_launch();
+        return cudaGetLastError();
+    }
+}
+cudaError_t sandwich_rows(const SandwichArgs &g) {
+    if (g.layout == kSoA) return g.strict ? launch_sandwich_rows_t<kSoA, true>(g) : launch_sandwich_rows_t<kSoA, false>(g);
+    return g.strict ? launch_sandwich_rows_t<kAoS, true>(g) : launch_sandwich_rows_t<kAoS, false>(g);
+}
+#endif  // LCC_PART == 6
+
 #if LCC_PART == 3
 template <int LAYOUT, bool EVEN> static cudaError_t launch_sandwich_t(const SandwichArgs &g) {
     if (g.n <= 0) return cudaSuccess;
@@ -1067,7 +1212,10 @@ cudaError_t launch_product(const ProductArgs &g) {
     if (e != cudaErrorNotSupported) return e;
     return g.strict ? product_direct_s1(g) : product_direct_s0(g);
 }
-cudaError_t launch_sandwich(const SandwichArgs &g) { return g.strict ? sandwich_s1(g) : sandwich_s0(g); }
+cudaError_t launch_sandwich(const SandwichArgs &g) {
+    if (g.rotors) return sandwich_rows(g);
+    return g.strict ? sandwich_s1(g) : sandwich_s0(g);
+}
 #endif  // LCC_PART == 4
 
 }  // namespace LCC_TU

@@ -926,6 +926,22 @@ lcc_status lcc_batch_sandwich_rows(const lcc_algebra *alg, const lcc_view *rotor
     if (rotors->n != x->n && rotors->n != 1) return fail(LCC_ERR_VALUE, "batch sizes must match or be 1 for broadcasting: %lld vs %lld", (long long)rotors->n, (long long)x->n);
     cudaStream_t s;
     LCC_TRY(resolve_stream(stream, &s));
+    LCC_TRY(same_kind(rotors, x, "sandwich_rows"));
+    LCC_TRY(same_kind(x, out, "sandwich_rows"));
+    if (x->n != out->n) return fail(LCC_ERR_VALUE, "sandwich_rows: output has %lld rows, expected %lld", (long long)out->n, (long long)x->n);
+    if (x->n == 0) return LCC_OK;
+    // up to 16 blades: ONE kernel, R and x in registers per row, rx rounded in registers, ~R folded into the signs
+    // (K2r; 3 * nb * s bytes per row).  cudaErrorNotSupported (32 blades and more): the composition below.
+    if (alg->nb <= 32 && alg->sandwich[x->dtype]) {
+        SandwichArgs g;
+        g.dtype = x->dtype; g.layout = x->layout; g.strict = (flags & LCC_FLAG_STRICT_FP) != 0; g.n = x->n;
+        g.rotors = rotors->data; g.ldr = rotors->ld; g.r_bcast = rotors->n == 1 && x->n > 1;
+        g.x = x->data; g.ldx = x->ld; g.out = out->data; g.ldo = out->ld;
+        g.mu = alg->specialised ? nullptr : alg->mu.data();
+        g.stream = s;
+        const cudaError_t e = alg->sandwich[x->dtype](g);
+        if (e != cudaErrorNotSupported) { LCC_CUDA(e); return LCC_OK; }
+    }
     // rx = R * x ; out = rx * ~R   (lcc/torch/multivector.py:1006-1017), composed from K1 and K3
     PoolBuffer brev, brx;
     lcc_view rev = *rotors, rx = *x;

@@ -66,6 +66,32 @@ def _rotor_on_host(t: Tensor) -> np.ndarray:
     return r
 
 
+def _rotor_if_on_host(t: Tensor) -> Optional[np.ndarray]:
+    """Host float64 copy of a one-row rotor tensor WITHOUT ever blocking: the first call with a given tensor (object and
+    version counter) starts an asynchronous copy into pinned memory and returns None -- the caller then uses the
+    device-rotor kernel; later calls return the copy once its event has completed."""
+    hit = _ROTOR_CACHE[0]
+    if hit is not None and hit[0]() is t and hit[1] == t._version:
+        if isinstance(hit[2], np.ndarray):
+            return hit[2]
+        pinned, event = hit[2]
+        if event.query():
+            r = pinned.numpy().reshape(-1).copy()
+            _ROTOR_CACHE[0] = (hit[0], hit[1], r)
+            return r
+        return None
+    try:
+        pinned = torch.empty(t.shape, dtype=torch.float64, pin_memory=True)
+        with torch.cuda.device(t.device):
+            pinned.copy_(t.detach().to(torch.float64), non_blocking=True)
+            event = torch.cuda.Event()
+            event.record()
+        _ROTOR_CACHE[0] = (weakref.ref(t), t._version, (pinned, event))
+    except (TypeError, RuntimeError):
+        _ROTOR_CACHE[0] = None
+    return None
+
+
 def _blade_grade(blade: int) -> int:
     return bin(blade).count("1")
 
@@ -361,10 +387,15 @@ class TorchMultivector:
             x = _prep(self.coeffs)
             out = torch.empty_like(x)
             if x.shape[0]:
-                r = _rotor_on_host(rotor.coeffs)
+                r = _rotor_if_on_host(rotor.coeffs)
                 with torch.cuda.device(x.device):
-                    cabi.check(cabi.lib().lcc_batch_sandwich(_handle(self.algebra.signature).h, r.ctypes.data_as(C.POINTER(C.c_double)),
-                                                             C.byref(_view(x)), C.byref(_view(out)), _flags(), _stream()))
+                    if r is not None:  # host copy known: the fixed-versor kernel (rotor in the constant bank, even-versor pruning)
+                        cabi.check(cabi.lib().lcc_batch_sandwich(_handle(self.algebra.signature).h, r.ctypes.data_as(C.POINTER(C.c_double)),
+                                                                 C.byref(_view(x)), C.byref(_view(out)), _flags(), _stream()))
+                    else:  # first sight of this rotor tensor: read it on the DEVICE (one broadcast row), no host synchronisation
+                        rd = _prep(rotor.coeffs.detach().to(x.dtype))
+                        cabi.check(cabi.lib().lcc_batch_sandwich_rows(_handle(self.algebra.signature).h, C.byref(_view(rd)), C.byref(_view(x)),
+                                                                      C.byref(_view(out)), _flags(), _stream()))
             return TorchMultivector(self.algebra, out)
         if not needs_grad and rotor.batch_size == self.batch_size and self.batch_size > 0:
             # one rotor per row (reference :988-1019): lcc_batch_sandwich_rows on the borrowed tensors

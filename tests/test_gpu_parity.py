@@ -436,6 +436,53 @@ def test_fixed_operand_product_f64_on_the_fp64_tensor_pipe(L, sig):
             assert np.all(np.abs(got - ref) <= 1e-12 * np.maximum(np.abs(ref), bound))
 
 
+@pytest.mark.parametrize("sig", [(3, 0, 0), (3, 0, 1), (1, 3, 0), (2, 1, 1), (4, 1, 0)])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_per_row_sandwich_through_the_c_abi(sig, dt):
+    """lcc_batch_sandwich_rows: one rotor per row, or ONE device-resident rotor row for all (the no-read-back path of
+    lcc.torch), both layouts.  Up to 16 blades it is one fused kernel (K2r: direct loads, TMA-staged AoS tiles from 4096 /
+    131072 rows on); strict mode is bit-exact against the reference composition gp(gp(R, x), ~R)
+    (/root/reference/lcc/torch/multivector.py:988-1019); 32 blades take the composed products -- same bits."""
+    from largecrimsoncanine_b200 import cabi
+
+    lib, alg, o = cabi.lib(), cabi.Algebra(*sig), oracle.OracleAlgebra(*sig)
+    nb = o.num_blades
+    code = cabi.LCC_F32 if dt == np.float32 else cabi.LCC_F64
+    rev = np.array([1.0 if bin(i).count("1") % 4 < 2 else -1.0 for i in range(nb)], dt)
+    rng = np.random.default_rng(4 + nb)
+    big = 131072 + 37 if nb * np.dtype(dt).itemsize <= 64 else 4096 + 37  # past the AoS TMA threshold of this row size
+    for n in (1, 63, 1000, big):
+        x, r = rand(rng, n, nb, dt), rand(rng, n, nb, dt)
+        for rr in (r, r[:1]):
+            want = o.geometric_product(o.geometric_product(rr, x), rr * rev)
+            for layout in (cabi.LCC_AOS, cabi.LCC_SOA):
+                def put(a):
+                    rows = a.shape[0]
+                    ld = nb if layout == cabi.LCC_AOS else ((rows + 63) // 64) * 64
+                    img = np.ascontiguousarray(a) if layout == cabi.LCC_AOS else np.zeros((nb, ld), dt)
+                    if layout == cabi.LCC_SOA:
+                        img[:, :rows] = a.T
+                    p = C.c_void_p()
+                    cabi.check(lib.lcc_device_alloc(C.byref(p), max(img.nbytes, 16), None))
+                    cabi.check(lib.lcc_memcpy_h2d(p, img.ctypes.data, img.nbytes, None))
+                    return p, cabi.view(p.value, rows, ld, code, layout), img
+                px, vx, _ = put(x)
+                pr, vr, _ = put(rr)
+                po, vo, img = put(np.zeros_like(x))
+                cabi.check(lib.lcc_batch_sandwich_rows(alg.h, C.byref(vr), C.byref(vx), C.byref(vo), cabi.LCC_FLAG_STRICT_FP, None))
+                cabi.check(lib.lcc_memcpy_d2h(img.ctypes.data, po, img.nbytes, None))
+                cabi.check(lib.lcc_stream_sync(None))
+                got = img if layout == cabi.LCC_AOS else img[:, :n].T
+                assert np.array_equal(got, want), (n, rr.shape[0], layout)
+                cabi.check(lib.lcc_batch_sandwich_rows(alg.h, C.byref(vr), C.byref(vx), C.byref(vo), 0, None))  # FMA mode: tolerance
+                cabi.check(lib.lcc_memcpy_d2h(img.ctypes.data, po, img.nbytes, None))
+                cabi.check(lib.lcc_stream_sync(None))
+                got = img if layout == cabi.LCC_AOS else img[:, :n].T
+                assert np.all(np.abs(got - want).max(axis=1) <= 10 * TOL[dt] * np.abs(want).max(axis=1))
+                for p in (px, pr, po):
+                    cabi.check(lib.lcc_device_free(p, None))
+
+
 @pytest.mark.parametrize("sig", [(6, 0, 0), (4, 2, 1), (8, 0, 0)])
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 def test_fixed_rotor_sandwich_and_masked_products_on_tensor_cores(L, sig, dt):
