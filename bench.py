@@ -504,7 +504,7 @@ def setup_workload(ctx, wl, n, layout="soa", collective=True, ld_pad=0):
     return step, drain, parity, keep
 
 
-def measure(ctx, wl, n, steps, warmup, layout="soa", collective=True, parity=True, solo=False, ld_pad=0):
+def measure(ctx, wl, n, steps, warmup, layout="soa", collective=True, parity=True, solo=False, ld_pad=0, graph=False):
     """W warm-up steps, then exactly K timed steps bracketed by barrier + synchronize; CUDA events on the launching
     stream around every step (mean = the contract's ms_per_step, min / median beside it); max over ranks.
     solo=True: only rank 0 runs (the other ranks idle at the barriers) -- the N = 1 figure measured inside an N > 1 job."""
@@ -539,6 +539,26 @@ def measure(ctx, wl, n, steps, warmup, layout="soa", collective=True, parity=Tru
         total_ms = ctx.max_over_ranks(total_ms)
     rec = {"ms_per_step": total_ms / steps, "ms_min": float(np.min(per)), "ms_median": float(np.median(per)), "steps": steps,
            "gpu_launches": launches, "clocks": clocks.summary()}
+    if graph and active:
+        # launch-bound configurations: the same K steps captured once into a CUDA graph and replayed (no per-launch host
+        # work, back-to-back kernel starts) -- reported beside the stream-launch figure, never instead of it
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=ctx.stream):
+                for _ in range(steps):
+                    step()
+            g.replay()
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(ctx.stream)
+            for _ in range(5):
+                g.replay()
+            g1.record(ctx.stream)
+            torch.cuda.synchronize()
+            rec["ms_per_step_cuda_graph"] = g0.elapsed_time(g1) / (5 * steps)
+        except Exception as exc:
+            rec["ms_per_step_cuda_graph"] = None
+            rec["cuda_graph_error"] = f"{type(exc).__name__}: {exc}"
     rec["parity"] = parity_fn() if (parity and active and ctx.rank == 0) else None
     return rec, keep
 
@@ -566,7 +586,7 @@ def config_block(wl, n):
 def secondary_record(ctx, wl, steps, peaks, peak_kind, n=None, layout="soa"):
     sig, dt, log2n, bytes_per, unit = WORKLOADS[wl]
     n = n or (1 << log2n)
-    rec, keep = measure(ctx, wl, n, steps, 3, layout)
+    rec, keep = measure(ctx, wl, n, steps, 3, layout, graph=(wl == "r3_gp"))
     release(ctx, keep)
     if ctx.rank != 0:
         return None
@@ -574,6 +594,8 @@ def secondary_record(ctx, wl, steps, peaks, peak_kind, n=None, layout="soa"):
            "value": ctx.world * n / (rec["ms_per_step"] / 1e3),
            "roofline": roofline_block(wl, n, rec["ms_per_step"], bytes_per, peaks, peak_kind, traffic_of(wl))}
     out.update(rec)
+    if rec.get("ms_per_step_cuda_graph"):
+        out["roofline_cuda_graph"] = roofline_block(wl, n, rec["ms_per_step_cuda_graph"], bytes_per, peaks, peak_kind, None)
     return out
 
 

@@ -521,8 +521,16 @@ sum_partial_aos_vec(const T *__restrict__ x, int64_t ldx, int64_t n, int nb, int
         ldg_stream(x + (r + lanes) * ldx + j * W, v1);
         ldg_stream(x + (r + 2 * (int64_t)lanes) * ldx + j * W, v2);
         ldg_stream(x + (r + 3 * (int64_t)lanes) * ldx + j * W, v3);
+        if constexpr (sizeof(T) == 4) {
+            // f32: the four rows are added pairwise in f32 first (fixed order), then once in f64 -- a quarter of the
+            // f32 -> f64 conversions, which run at a fraction of the FP32 rate and were what held this kernel at 6.0 TB/s;
+            // the extra rounding is 2 f32 ulps of a 4-term partial, far inside the f32 result's own precision
 #pragma unroll
-        for (int l = 0; l < W; ++l) { acc[l] += (double)v0[l]; acc1[l] += (double)v1[l]; acc2[l] += (double)v2[l]; acc3[l] += (double)v3[l]; }
+            for (int l = 0; l < W; ++l) acc[l] += (double)((v0[l] + v1[l]) + (v2[l] + v3[l]));
+        } else {
+#pragma unroll
+            for (int l = 0; l < W; ++l) { acc[l] += (double)v0[l]; acc1[l] += (double)v1[l]; acc2[l] += (double)v2[l]; acc3[l] += (double)v3[l]; }
+        }
     }
     for (; r < end; r += lanes) {
         T v[W];

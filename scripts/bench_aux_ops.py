@@ -57,6 +57,10 @@ def run(sig, dt, log2n):
             "normalized": (2 * nb * es, lambda: cabi.check(lib.lcc_batch_normalized(alg.h, C.byref(va), C.byref(vo), 0, sptr))),
             "sum": (nb * es, lambda: cabi.check(lib.lcc_batch_sum(alg.h, C.byref(va), C.c_void_p(sums.data_ptr()), sptr))),
         }
+        if nb <= 16:  # K2r: one rotor per row (3 tiles), and one device-resident rotor row for the whole batch (2 tiles)
+            r1 = cabi.view(b.data_ptr(), 1, b.stride(0) if layout == cabi.LCC_SOA else nb, code, layout)
+            cases["sandwich_rows"] = (3 * nb * es, lambda: cabi.check(lib.lcc_batch_sandwich_rows(alg.h, C.byref(vb), C.byref(va), C.byref(vo), 0, sptr)))
+            cases["sandwich_rows_bcast"] = (2 * nb * es, lambda: cabi.check(lib.lcc_batch_sandwich_rows(alg.h, C.byref(r1), C.byref(va), C.byref(vo), 0, sptr)))
         if alg.r == 0:
             cases["dual"] = (2 * nb * es, lambda: cabi.check(lib.lcc_batch_unary(alg.h, cabi.LCC_UN_DUAL, 0, C.byref(va), C.byref(vo), sptr)))
         for name, (bytes_per, fn) in cases.items():
