@@ -7,16 +7,25 @@ Default workload = BASELINE.json configs[1]: PGA Cl(3,0,1) motor sandwich applie
 f32, dense 16-blade rows (128 algorithmic bytes per point: 64 read + 64 written).  A "step" is one
 pass of the sandwich kernel over the whole device-resident batch.  For N > 1 (torchrun, one process
 per GPU) every rank owns its own 2^28-point shard (weak scaling, no data-path collective); timing is
-bracketed by a barrier + synchronize and the MAX over ranks is reported.
+bracketed by a barrier + synchronize and the MAX over ranks is reported.  Kernels are launched on the
+compute stream of the native shard group (csrc/shard_group.cu), CUDA events are recorded on that stream.
 
 One JSON line on stdout (rank 0):
-  value       points/s with inputs already resident in HBM (CUDA events on the launching stream)
-  e2e         the same metric through the C-ABI host-buffer entry point lcc_host_sandwich: pinned HOST
-              buffers in the reference's (N, 16) layout, H2D and D2H copies inside the timed region
-  roofline    algorithmic bytes / kernel time against the measured HBM peak (MEASURED_PEAKS.json)
-  cpu_baseline  the oracle port of the reference's Rust loop timed on this box's host cores
-`--impl reference` times only that CPU implementation (bounded sample per step) and prints the same
-line shape with "impl": "reference".
+  value       points/s with inputs already resident in HBM (mean over K steps; ms_min / ms_median beside it)
+  e2e         the same metric from HOST arrays through the drop-in Python API -- value = the reference's own call
+              sequence MultivectorBatch.from_numpy(alg, x).sandwich(M).to_numpy() on a pinned NumPy array, H2D and D2H
+              inside the timed region; `variants` adds the pageable-array run, the one-call MultivectorBatch.sandwich_numpy
+              and the C-ABI entry point lcc_host_sandwich behind it
+  roofline    algorithmic bytes / kernel time against the measured HBM peak (MEASURED_PEAKS.json); tensor-bound
+              workloads against profiles/peaks_local.json (cuBLAS TF32 / FP64 measured with scripts/measure_peaks.py)
+  cpu_baseline  the oracle port of the reference's Rust loop timed on this box's host cores (N = 1 only)
+  collective  BASELINE config 4 fused (grade projection + inner product + batch sum in one kernel, 2^27 rows per GPU) with
+              its NCCL all-reduce every step, through lcc_shard_product_sum_async; at N > 1 also the same kernel without the
+              collective and on one GPU of the job alone
+  strong      BASELINE config 2 with 2^28 points IN TOTAL (2^28 / N per GPU)
+  secondary   the other BASELINE configs at full size on this rank's GPU (ms_per_step, roofline, parity, clocks each)
+`--impl reference` times only the CPU implementation (bounded sample per step) and prints the same
+line shape with "impl": "reference" and the same `config` block.
 """
 from __future__ import annotations
 
