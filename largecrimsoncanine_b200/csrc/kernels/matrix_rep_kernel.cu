@@ -10,16 +10,20 @@
 //     stage 3   z[c][.] = WHT_j(C[j^c][j]) ;  out_A = sign_A z[c][b]                  (the 1/16 is folded into rho(M))
 // = 8192 + 2048 flops instead of 131 072: the product becomes HBM-bound (2 * nb * sizeof(T) bytes per row).
 //
-// Shape: persistent, one CTA per SM.  One thread of warp 16 streams 32-row tiles (32 x nb box of the blade-major batch)
-// into a ring of shared-memory stages with TMA, warps 0-15 transform a stage IN PLACE, and the same TMA thread hands the
-// finished stage to the engine for the store and refills it with the tile NS ahead once the engine has read it -- loads
-// run several tiles ahead of the arithmetic, stores trail it.  Inside a stage, slot s holds 32 rows; in the transform
-// stages a warp works on ONE slot per instruction with its 32 lanes on the 32 rows (conflict free), and the three stages
-// only re-index the 256 slots (blade index -> matrix entry -> blade index).  Stage 2 runs on the tensor cores with the
-// fixed 16 x 16 factor held in registers as MMA A-fragments for the whole kernel: mma.sync m16n8k8 TF32 x 3 (hi/lo
-// split, the same error budget as K6) for f32, mma.sync m8n8k4 on the FP64 tensor pipe for f64.  (The first version did
-// stage 2 with FFMA / DFMA against constant-bank operands: issue-bound at 67 % for f32 and bound by indexed constant
-// loads -- ADU pipe 75 % busy -- for f64: 10.1 / 25.9 ms at 2^24 rows, profiles/r02_k8_*_v1.)
+// Shape: persistent, one CTA of 16 warps per SM (512 threads, so each may hold 128 registers), a ring of three 64 KB
+// stages (64-row tiles in f32, 32-row tiles in f64: 256-byte TMA segments per blade row).  The warps form TWO groups of
+// eight; group g transforms the tiles g, g + 2, ... of its CTA IN PLACE, each behind its own named barrier, so the groups
+// sit in different phases instead of sixteen warps marching through the five barriers of a tile in lockstep.  The first
+// thread of a group is its TMA thread: it stores the finished stage and, one barrier into the group's next tile (by then
+// the engine has read the stage), refills it with the tile three ahead.  Inside a stage, slot s holds the rows of one
+// blade / matrix entry; in the transform stages a warp works on ONE slot per instruction with its 32 lanes on 32 rows
+// (conflict free), and the three stages only re-index the 256 slots (blade index -> matrix entry -> blade index; the
+// blade of a string is linear over F_2, so an address costs one XOR and one IMAD).  Stage 2 runs on the tensor cores with
+// the fixed 16 x 16 factor as MMA A-fragments in shared memory: mma.sync m16n8k8 TF32 x 3 (hi/lo split, the same error
+// budget as K6) for f32, mma.sync m8n8k4 on the FP64 tensor pipe for f64.
+// History (profiles/r02_prof_k8_*): v1 did stage 2 with FFMA / DFMA against constant-bank operands --
+// issue-bound at 67 % for f32, bound by lane-indexed constant loads (ADU pipe 75 % busy) for f64: 10.1 / 25.9 ms at 2^24
+// rows; v2 kept the MMA fragments in registers and ptxas re-materialised them with indexed LDC inside the tile loop.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -34,7 +38,7 @@
 namespace lcc {
 namespace {
 
-constexpr int kConsumerWarps = 16, kConsumers = kConsumerWarps * 32, kThreadsRep = kConsumers + 32;
+constexpr int kThreadsRep = 512;  // 16 warps: with no 17th warp every thread may hold 128 registers
 
 template <typename T> struct RepParams {
     T p1[256];           // first factor, [o * 16 + k]:  acc[o] += p1[o][k] * x[k]
@@ -54,10 +58,6 @@ template <typename T> __device__ __forceinline__ void wht16(T (&v)[16]) {
             if (!(i & h)) { const T x = v[i], y = v[i | h]; v[i] = x + y; v[i | h] = x - y; }
 }
 
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tma::smem_u32(bar)) : "memory");
-}
 
 // Matrix slots: entry (f, s) of a 16 x 16 matrix lives in slot f * 16 + s; inside a slot row r sits at position
 // r ^ swz(f).  The XOR spreads the four k-lanes of an MMA B-fragment load and the m-lanes of a D-fragment store over
@@ -211,134 +211,179 @@ matrix_rep_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     constexpr int RPL = RepShape<T>::kRowsPerLane, TR = 32 * RPL, NS = RepShape<T>::kStages;
     constexpr uint32_t kStageBytes = 256u * TR * sizeof(T);
     extern __shared__ __align__(1024) uint8_t smem[];  // no static shared memory in this kernel: the window starts aligned
-    uint64_t *bars = (uint64_t *)(smem + (size_t)NS * kStageBytes);
-    uint64_t *full = bars, *done = bars + NS;
+    uint64_t *full = (uint64_t *)(smem + (size_t)NS * kStageBytes);
     using Frag = typename std::remove_const<typename std::remove_pointer<decltype(Factor<T>::frag)>::type>::type;
     Frag *frag1 = (Frag *)(smem + (size_t)NS * kStageBytes + 64), *frag2 = frag1 + Factor<T>::kChunks * 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tiles = (n + TR - 1) / TR;
+    const uint32_t box_bytes = (uint32_t)nb * TR * sizeof(T);
+    const int64_t mine = tiles > blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto tile_row = [&](int64_t k) { return (int)((blockIdx.x + k * gridDim.x) * TR); };
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NS; ++s) { tma::mbar_init(&full[s], 1); tma::mbar_init(&done[s], 1); }
+        for (int s = 0; s < NS; ++s) tma::mbar_init(&full[s], 1);
+        tma::prefetch_map(&map_x);
+        tma::prefetch_map(&map_out);
     }
     if (warp == 0) {
         Factor<T>::build(frag1, P.p1, lane);
         if (MODE == 2) Factor<T>::build(frag2, P.p2, lane);
     }
     __syncthreads();
-    const int64_t tiles = (n + TR - 1) / TR;
-    const uint32_t box_bytes = (uint32_t)nb * TR * sizeof(T);
-
-    if (warp == kConsumerWarps) {            // ---- the TMA warp: one thread streams tiles in and hands finished stages back
-        if (lane == 0) {
-            tma::prefetch_map(&map_x);
-            tma::prefetch_map(&map_out);
-            const int64_t mine = tiles > blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-            for (int64_t k = 0; k < mine && k < NS; ++k) {  // fill the ring
-                tma::mbar_expect_tx(&full[k], box_bytes);
-                tma::load_2d(smem + (size_t)k * kStageBytes, &map_x, &full[k], (int)((blockIdx.x + k * gridDim.x) * TR), 0);
-            }
-            int s = 0; uint32_t ph = 0;
-            for (int64_t k = 0; k < mine; ++k) {
-                tma::mbar_wait(&done[s], ph);
-                tma::store_2d(&map_out, smem + (size_t)s * kStageBytes, (int)((blockIdx.x + k * gridDim.x) * TR), 0);
-                tma::store_commit_and_wait_read();  // the engine has read the stage: refill it with the tile NS ahead
-                if (k + NS < mine) {
-                    tma::mbar_expect_tx(&full[s], box_bytes);
-                    tma::load_2d(smem + (size_t)s * kStageBytes, &map_x, &full[s], (int)((blockIdx.x + (k + NS) * gridDim.x) * TR), 0);
-                }
-                if (++s == NS) { s = 0; ph ^= 1; }
-            }
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // global writes complete before the CTA exits
+    if (threadIdx.x == 0)
+        for (int64_t k = 0; k < mine && k < NS; ++k) {  // fill the ring
+            tma::mbar_expect_tx(&full[k], box_bytes);
+            tma::load_2d(smem + (size_t)k * kStageBytes, &map_x, &full[k], tile_row(k), 0);
         }
-    } else {                                  // ---- 16 consumer warps: warp w = one index (a, j or c), lane = row (and row + 32)
-        const int w = warp;
-        // per-thread tables, built once: where the 16 blades of string row w live in a stage and their signs; where the 16
-        // matrix entries this thread transforms live (stage 1 writes them, stage 3 reads them)
-        int off_first[16], off_last[MODE == 2 ? 16 : 1];  // modes 0 and 1 end on the slots they started on
-        uint32_t neg = 0, valid = 0;
-        int blade_hi = 0;   // blade of string (w << 4): the part of the blade index that depends on the warp
-        int blade_lo[16];   // blade of string b: the same for every thread of the grid (uniform registers)
+    {
+        // ---- 16 compute warps in TWO groups of 8: group g transforms the tiles g, g + 2, g + 4, ... of this CTA, each on
+        // its own stage and behind its own named barrier, so the two groups sit in different phases (one in a
+        // shared-memory pass while the other is in its MMAs) instead of all 16 warps marching through the five barriers
+        // of a tile in lockstep.  A warp owns TWO indices (wl and wl + 8) of its group's tile; lane = row (and row + 32).
+        const int grp = warp >> 3, wl = warp & 7;
+        const int gtid = threadIdx.x & 255;
+        auto group_sync = [&]() {
+            if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+            else asm volatile("bar.sync 2, 256;" ::: "memory");
+        };
+        // per-index constants (two indices per warp): the warp-dependent part of the blade index, sign-flip masks of the
+        // 16 blades of string row w (applied to the sign bit: one XOR per element), validity mask (128-blade algebras)
+        int blade_hi[2];
+        uint32_t neg[2], valid[2];
+        int lsw[2];  // lane ^ swz(w): with swz linear over XOR, lane ^ swz(j ^ w) = lsw ^ swz(j)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) blade_hi ^= ((w >> i) & 1) ? (int)P.lin[4 + i] : 0;
+        for (int ii = 0; ii < 2; ++ii) {
+            const int w = wl + 8 * ii;
+            blade_hi[ii] = 0; neg[ii] = 0; valid[ii] = 0;
 #pragma unroll
-        for (int b = 0; b < 16; ++b) {
+            for (int i = 0; i < 4; ++i) blade_hi[ii] ^= ((w >> i) & 1) ? (int)P.lin[4 + i] : 0;
+#pragma unroll
+            for (int b = 0; b < 16; ++b) {
+                const int sg = P.sign[(w << 4) | b];
+                neg[ii] |= (sg < 0 ? 1u : 0u) << b;
+                valid[ii] |= (sg != 0 ? 1u : 0u) << b;
+            }
+            lsw[ii] = lane ^ Swz<T>::of(w);
+        }
+        int blade_lo[16];   // blade of string b: the same for every thread of the grid
+#pragma unroll
+        for (int b = 0; b < 16; ++b)
             blade_lo[b] = ((b & 1) ? (int)P.lin[0] : 0) ^ ((b & 2) ? (int)P.lin[1] : 0) ^ ((b & 4) ? (int)P.lin[2] : 0) ^ ((b & 8) ? (int)P.lin[3] : 0);
-            const int sg = P.sign[(w << 4) | b];
-            neg |= (sg < 0 ? 1u : 0u) << b;
-            valid |= (sg != 0 ? 1u : 0u) << b;
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            // X[j^w][j] (normal slots) or, transposed, X^T[j][j^w]
-            const int f1 = MODE == 1 ? j : (j ^ w), s1 = MODE == 1 ? (j ^ w) : j;
-            off_first[j] = (f1 * 16 + s1) * TR + (lane ^ Swz<T>::of(f1));
-            if (MODE == 2) off_last[j] = (j * 16 + (j ^ w)) * TR + (lane ^ Swz<T>::of(j));  // the sandwich ends on transposed slots
-        }
+        const bool full_algebra = nb == 256;
+        // matrix-slot offset of entry j of index w: normal slots X[j^w][j] or transposed X^T[j][j^w]
+        auto slot_off = [&](int j, int w, int ls, bool transposed) {
+            const int f = transposed ? j : (j ^ w), sec = transposed ? (j ^ w) : j;
+            const int pos = transposed ? (lane ^ Swz<T>::of(j)) : (ls ^ Swz<T>::of(j));
+            return (f * 16 + sec) * TR + pos;
+        };
+        auto flip = [](T x, bool negative) { return negative ? -x : x; };
         Factor<T> F1, F2;
         F1.frag = frag1;
         F2.frag = frag2;
-        int s = 0; uint32_t ph = 0;
-        for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        // The group's first thread is also its TMA thread: it stores the group's finished tile and, one barrier into the
+        // NEXT tile (by then the engine has read the stage), refills that stage with the tile NS ahead.
+        int64_t stored = -1;  // tile whose store this thread issued last (its stage is refilled once the store has been read)
+        auto refill = [&]() {
+            if (gtid == 0 && stored >= 0) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                if (stored + NS < mine) {
+                    const int rs = (int)(stored % NS);
+                    tma::mbar_expect_tx(&full[rs], box_bytes);
+                    tma::load_2d(smem + (size_t)rs * kStageBytes, &map_x, &full[rs], tile_row(stored + NS), 0);
+                }
+                stored = -1;
+            }
+        };
+        auto store_tile = [&](int64_t it, int s) {
+            if (gtid == 0) {
+                tma::store_2d(&map_out, smem + (size_t)s * kStageBytes, tile_row(it), 0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                stored = it;
+            }
+        };
+        for (int64_t it = grp; it < mine; it += 2) {
+            const int s = (int)(it % NS);
+            const uint32_t ph = (uint32_t)((it / NS) & 1);
             T *st = (T *)(smem + (size_t)s * kStageBytes);
             tma::mbar_wait(&full[s], ph);
             if (dbg == 1) {  // LCC_K8_DEBUG=1: tiles pass through untouched (memory pipeline alone)
-                consumer_sync();
-                if (threadIdx.x == 0) mbar_arrive(&done[s]);
-                if (++s == NS) { s = 0; ph ^= 1; }
+                refill();
+                group_sync();
+                store_tile(it, s);
                 continue;
             }
-            T v[RPL][16];
+            T v[2][RPL][16];
             // stage 1: gather y[w][.] from the blade slots, transform, scatter to the matrix slots
 #pragma unroll
-            for (int h = 0; h < RPL; ++h)
+            for (int ii = 0; ii < 2; ++ii)
 #pragma unroll
-                for (int b = 0; b < 16; ++b) {
-                    const T x = st[(blade_hi ^ blade_lo[b]) * TR + lane + 32 * h];
-                    v[h][b] = ((valid >> b) & 1u) ? (((neg >> b) & 1u) ? -x : x) : T(0);
+                for (int h = 0; h < RPL; ++h) {
+#pragma unroll
+                    for (int b = 0; b < 16; ++b) {
+                        const T x = st[(blade_hi[ii] ^ blade_lo[b]) * TR + lane + 32 * h];
+                        v[ii][h][b] = flip(x, (neg[ii] >> b) & 1u);
+                        if (!full_algebra && !((valid[ii] >> b) & 1u)) v[ii][h][b] = T(0);
+                    }
+                    wht16(v[ii][h]);
                 }
+            refill();      // the previous tile's store has long been read: put the next load in flight
+            group_sync();  // every blade slot of the tile has been read
 #pragma unroll
-            for (int h = 0; h < RPL; ++h) wht16(v[h]);
-            consumer_sync();  // every blade slot has been read
+            for (int ii = 0; ii < 2; ++ii)
 #pragma unroll
-            for (int h = 0; h < RPL; ++h)
+                for (int h = 0; h < RPL; ++h)
 #pragma unroll
-                for (int j = 0; j < 16; ++j) st[off_first[j] + 32 * h] = v[h][j];
-            consumer_sync();
-            // stage 2 on the tensor cores: the column with second index w, in place
-            if (dbg != 2) column_gemm<TR>(st, F1, w, lane);  // LCC_K8_DEBUG=2: transforms only
+                    for (int j = 0; j < 16; ++j) st[slot_off(j, wl + 8 * ii, lsw[ii], MODE == 1) + 32 * h] = v[ii][h][j];
+            group_sync();
+            // stage 2 on the tensor cores: the columns with second index w, in place
+            if (dbg != 2) {  // LCC_K8_DEBUG=2: transforms only
+                column_gemm<TR>(st, F1, wl, lane);
+                column_gemm<TR>(st, F1, wl + 8, lane);
+            }
             if (MODE == 2) {
-                consumer_sync();
+                group_sync();
                 // transpose pass: T[i][w] -> T^T[w][i] (the first index is warp-uniform on both sides: conflict free)
 #pragma unroll
-                for (int h = 0; h < RPL; ++h)
+                for (int ii = 0; ii < 2; ++ii)
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[h][i] = st[(i * 16 + w) * TR + 32 * h + (lane ^ Swz<T>::of(i))];
-                consumer_sync();
+                    for (int h = 0; h < RPL; ++h)
 #pragma unroll
-                for (int h = 0; h < RPL; ++h)
+                        for (int i = 0; i < 16; ++i) v[ii][h][i] = st[(i * 16 + wl + 8 * ii) * TR + 32 * h + (lane ^ Swz<T>::of(i))];
+                group_sync();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) st[(w * 16 + i) * TR + 32 * h + (lane ^ Swz<T>::of(w))] = v[h][i];
-                consumer_sync();
-                column_gemm<TR>(st, F2, w, lane);
+                for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+                    for (int h = 0; h < RPL; ++h)
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) st[((wl + 8 * ii) * 16 + i) * TR + 32 * h + lsw[ii]] = v[ii][h][i];
+                group_sync();
+                column_gemm<TR>(st, F2, wl, lane);
+                column_gemm<TR>(st, F2, wl + 8, lane);
             }
-            consumer_sync();
+            group_sync();
             // stage 3: gather the 16 matrix entries of string row w, transform back, scatter to the blade slots
 #pragma unroll
-            for (int h = 0; h < RPL; ++h)
+            for (int ii = 0; ii < 2; ++ii)
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[h][j] = st[(MODE == 2 ? off_last[j] : off_first[j]) + 32 * h];
+                for (int h = 0; h < RPL; ++h) {
 #pragma unroll
-            for (int h = 0; h < RPL; ++h) wht16(v[h]);
-            consumer_sync();  // every matrix slot has been read
+                    for (int j = 0; j < 16; ++j) v[ii][h][j] = st[slot_off(j, wl + 8 * ii, lsw[ii], MODE != 0) + 32 * h];
+                    wht16(v[ii][h]);
+                }
+            group_sync();  // every matrix slot has been read
 #pragma unroll
-            for (int h = 0; h < RPL; ++h)
+            for (int ii = 0; ii < 2; ++ii)
 #pragma unroll
-                for (int b = 0; b < 16; ++b)
-                    if ((valid >> b) & 1u) st[(blade_hi ^ blade_lo[b]) * TR + lane + 32 * h] = ((neg >> b) & 1u) ? -v[h][b] : v[h][b];
+                for (int h = 0; h < RPL; ++h)
+#pragma unroll
+                    for (int b = 0; b < 16; ++b)
+                        if (full_algebra || ((valid[ii] >> b) & 1u))
+                            st[(blade_hi[ii] ^ blade_lo[b]) * TR + lane + 32 * h] = flip(v[ii][h][b], (neg[ii] >> b) & 1u);
             tma::fence_proxy_async();
-            consumer_sync();
-            if (threadIdx.x == 0) mbar_arrive(&done[s]);
-            if (++s == NS) { s = 0; ph ^= 1; }
+            group_sync();
+            store_tile(it, s);
         }
+        refill();  // (waits for the read of the last store; nothing left to load)
+        if (gtid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // global writes complete before the CTA exits
     }
 }
 
