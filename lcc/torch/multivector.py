@@ -192,6 +192,38 @@ class _Product(torch.autograd.Function):
         return ga, gb, None, None
 
 
+class _SandwichFixed(torch.autograd.Function):
+    """out = R x ~R with ONE rotor that needs no gradient: forward is the fused sandwich kernel (one pass over x instead of
+    two products and a full-size intermediate); x -> R x ~R is linear, so the cotangent of x is two vector-Jacobian
+    passes with broadcast operands -- g_rx = vjp_left(g, ~R), g_x = vjp_right(g_rx, R) -- and nothing has to be saved
+    but the rotor."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, r: Tensor, sig):
+        ctx.sig = sig
+        x, r = _prep(x), _prep(r.detach().to(x.dtype))
+        ctx.save_for_backward(r)
+        out = torch.empty_like(x)
+        if x.shape[0]:
+            host = _rotor_if_on_host(r)
+            with torch.cuda.device(x.device):
+                if host is not None:
+                    cabi.check(cabi.lib().lcc_batch_sandwich(_handle(sig).h, host.ctypes.data_as(C.POINTER(C.c_double)),
+                                                             C.byref(_view(x)), C.byref(_view(out)), _flags(), _stream()))
+                else:
+                    cabi.check(cabi.lib().lcc_batch_sandwich_rows(_handle(sig).h, C.byref(_view(r)), C.byref(_view(x)),
+                                                                  C.byref(_view(out)), _flags(), _stream()))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        (r,) = ctx.saved_tensors
+        nb = r.shape[1]
+        rev = torch.tensor([_reverse_sign(_blade_grade(i)) for i in range(nb)], dtype=r.dtype, device=r.device)
+        g_rx = _product_vjp(ctx.sig, cabi.LCC_OP_GP, 0, grad_out, r * rev)
+        return _product_vjp(ctx.sig, cabi.LCC_OP_GP, 1, g_rx, r), None, None
+
+
 class TorchAlgebra:
     """An algebra's Cayley tables as tensors plus the handle of the native engine.
 
@@ -397,6 +429,9 @@ class TorchMultivector:
                         cabi.check(cabi.lib().lcc_batch_sandwich_rows(_handle(self.algebra.signature).h, C.byref(_view(rd)), C.byref(_view(x)),
                                                                       C.byref(_view(out)), _flags(), _stream()))
             return TorchMultivector(self.algebra, out)
+        if rotor.batch_size == 1 and not (torch.is_grad_enabled() and rotor.coeffs.requires_grad):
+            # gradients flow to x only: fused forward, two broadcast VJP passes backward
+            return TorchMultivector(self.algebra, _SandwichFixed.apply(self.coeffs, rotor.coeffs, self.algebra.signature))
         if not needs_grad and rotor.batch_size == self.batch_size and self.batch_size > 0:
             # one rotor per row (reference :988-1019): lcc_batch_sandwich_rows on the borrowed tensors
             x, r = _prep(self.coeffs), _prep(rotor.coeffs.to(self.coeffs.dtype))
