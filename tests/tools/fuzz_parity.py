@@ -85,7 +85,8 @@ def main(cases):
         a_used, b_used = (a[:1] if bc == 1 else a), (b[:1] if bc == 2 else b)
         A, B = Operand(a_used, layout, dt), Operand(b_used, layout, dt)
         out, out2 = Operand(np.zeros((n, nb), dt), layout, dt), Operand(np.zeros((n, nb), dt), layout, dt)
-        kind = rng.integers(7)
+        kind = rng.integers(10)
+        cabi.check(lib.lcc_set_option(b"host_chunk_bytes", int(rng.choice([1 << 16, 1 << 18, 64 << 20]))))
         label = f"case {case}: sig {sig} {np.dtype(dt).name} layout {layout} n {n} bc {bc} kind {kind}"
         try:
             if kind == 0:
@@ -138,6 +139,31 @@ def main(cases):
                 assert np.all(np.abs(dev_get(ps, sums) - want) <= (1e-12 if dt == np.float64 else 2e-6) * np.maximum(mag, 1.0)), label + " (sum)"
                 cabi.check(lib.lcc_device_free(ps, None))
                 other.free()
+            elif kind == 7 and bc != 2:  # one rotor per row, or (bc == 1) ONE device-resident rotor row for the whole batch (K2r / composed)
+                cabi.check(lib.lcc_batch_sandwich_rows(alg.h, C.byref(A.view), C.byref(B.view), C.byref(out.view), S, None))
+                rev = np.array([1.0 if bin(i).count("1") % 4 < 2 else -1.0 for i in range(nb)], dt)
+                assert np.array_equal(out.read(), o.geometric_product(o.geometric_product(a_used, b), a_used * rev)), label
+            elif kind == 8 and bc == 0:  # host array -> batch -> host array through the chunked pipelines (pageable and pinned)
+                host = a
+                if rng.random() < 0.5:
+                    pp = C.c_void_p()
+                    cabi.check(lib.lcc_host_cache_alloc(C.byref(pp), a.nbytes))
+                    host = np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_double if dt == np.float64 else C.c_float)), shape=a.shape)
+                    host[...] = a
+                cabi.check(lib.lcc_batch_upload(alg.h, host.ctypes.data, n, C.byref(out.view), None))
+                assert np.array_equal(out.read(), a), label + " (upload)"
+                back = np.zeros_like(a)
+                cabi.check(lib.lcc_batch_download(alg.h, C.byref(out.view), back.ctypes.data, None))
+                assert np.array_equal(back, a), label + " (download)"
+                if host is not a:
+                    cabi.check(lib.lcc_host_cache_free(pp))
+            elif kind == 9 and bc == 0:  # broadcast product with the fixed operand on the host
+                side = int(rng.integers(2))
+                op, ref = [(cabi.LCC_OP_GP, o.geometric_product), (cabi.LCC_OP_OUTER, o.outer_product), (cabi.LCC_OP_LC, o.left_contraction)][rng.integers(3)]
+                fixed = b[0].astype(np.float64)
+                cabi.check(lib.lcc_batch_fixed_product(alg.h, op, side, fixed.ctypes.data_as(C.POINTER(C.c_double)), C.byref(A.view), C.byref(out.view), S, None))
+                want = ref(b[:1], a) if side == 0 else ref(a, b[:1])
+                assert np.array_equal(out.read(), want), label + f" (fixed product op {op} side {side})"
             else:
                 continue
             assert np.array_equal(A.read(), a_used) and np.array_equal(B.read(), b_used), label + " (inputs modified)"
