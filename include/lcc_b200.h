@@ -141,6 +141,12 @@ LCC_API int lcc_clifford_conjugate_sign(int blade_index);
  * X^a Z^b [i][j] = [i == j ^ a] * (-1)^popcount(b & j).  Returns the matrix size (16), or 0 when the algebra has no such
  * representation (then fixed-operand products stay on the dense GEMM).  Buffers hold num_blades entries; either may be NULL. */
 LCC_API int lcc_algebra_matrix_rep(const lcc_algebra *alg, uint8_t *string_of_blade, int8_t *sign_of_blade);
+/* Diagnostic (host side): the shared-memory layout K8 derives from that representation (csrc/matrix_rep.hpp, RepLayout).
+ * tables receives 8 x 16 words: byte offsets F(blade of string b), F(blade of string a << 4); then for the column pass
+ * (fixed factor on the left) and the row pass (on the right) each: slot offsets of the contraction index at the MMA's
+ * physical positions, slot offsets Gamma(w) of the free index, and the physical -> logical index map.  Returns 1, or 0
+ * when the algebra has no representation / no conflict-free layout (K8 is then not used).  tables may be NULL. */
+LCC_API int lcc_algebra_matrix_rep_layout(const lcc_algebra *alg, uint32_t *tables);
 
 /* ---------------------------------------------------------------- device memory (stream-ordered pool) */
 
@@ -213,6 +219,15 @@ LCC_API lcc_status lcc_batch_sandwich(const lcc_algebra *alg, const double *roto
 /* Per-row rotors (rotors.n == x.n): lcc/torch/multivector.py:988-1019. */
 LCC_API lcc_status lcc_batch_sandwich_rows(const lcc_algebra *alg, const lcc_view *rotors, const lcc_view *x,
                                            const lcc_view *out, unsigned flags, void *stream);
+/* Cotangents of lcc_batch_sandwich_rows (autograd of lcc.torch; the reference's backward pass is torch autograd through
+ * the two products and the reverse of lcc/torch/multivector.py:988-1019): given grad_out = d loss / d out,
+ * grad_x = d loss / d x and grad_rotors = d loss / d rotors, one row each per row of x -- for a broadcast rotor
+ * (rotors.n == 1) the caller sums grad_rotors over the rows.  Up to 16 blades this is ONE kernel with R, x and grad_out in
+ * registers (5 * num_blades * s bytes per row); larger algebras compose the five bilinear passes with R x recomputed.
+ * FMA arithmetic (LCC_FLAG_STRICT_FP is ignored up to 16 blades, as for lcc_batch_product_vjp). */
+LCC_API lcc_status lcc_batch_sandwich_rows_vjp(const lcc_algebra *alg, const lcc_view *rotors, const lcc_view *x,
+                                               const lcc_view *grad_out, const lcc_view *grad_x, const lcc_view *grad_rotors,
+                                               unsigned flags, void *stream);
 /* Signed permutations / masks, see lcc_unary_op.  `arg` is the grade for LCC_UN_GRADE. */
 LCC_API lcc_status lcc_batch_unary(const lcc_algebra *alg, int op, int arg, const lcc_view *x,
                                    const lcc_view *out, void *stream);

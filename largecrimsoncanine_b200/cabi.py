@@ -72,6 +72,7 @@ def lib():
         "lcc_algebra_blade_name": (i32, [vp, i32, C.c_char_p, i32]),
         "lcc_algebra_is_specialised": (i32, [vp]),
         "lcc_algebra_matrix_rep": (i32, [vp, C.POINTER(C.c_uint8), C.POINTER(C.c_int8)]),
+        "lcc_algebra_matrix_rep_layout": (i32, [vp, C.POINTER(C.c_uint32)]),
         "lcc_reverse_sign": (i32, [i32]),
         "lcc_grade_involution_sign": (i32, [i32]),
         "lcc_clifford_conjugate_sign": (i32, [i32]),
@@ -96,6 +97,7 @@ def lib():
         "lcc_batch_product_vjp": (i32, [vp, i32, i32, V, V, V, u32, vp]),
         "lcc_batch_sandwich": (i32, [vp, C.POINTER(dbl), V, V, u32, vp]),
         "lcc_batch_sandwich_rows": (i32, [vp, V, V, V, u32, vp]),
+        "lcc_batch_sandwich_rows_vjp": (i32, [vp, V, V, V, V, V, u32, vp]),
         "lcc_batch_unary": (i32, [vp, i32, i32, V, V, vp]),
         "lcc_batch_scale": (i32, [vp, V, dbl, V, vp]),
         "lcc_batch_elementwise": (i32, [vp, i32, V, V, V, vp]),

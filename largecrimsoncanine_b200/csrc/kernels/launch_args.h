@@ -53,6 +53,10 @@ struct SandwichArgs {
     const void *rotors = nullptr; int64_t ldr = 0; bool r_bcast = false;  // or: device rotors, one per row (r_bcast: one row for all)
     const void *x = nullptr; int64_t ldx = 0;
     void *out = nullptr; int64_t ldo = 0;
+    // fused cotangent pass of the per-row sandwich (rotors set): grad = d/d out -> gx = d/dx, gr = d/d rotor rows
+    const void *grad = nullptr; int64_t ldg = 0;
+    void *gx = nullptr; int64_t ldgx = 0;
+    void *gr = nullptr; int64_t ldgr = 0;
     const double *mu = nullptr;
     cudaStream_t stream = nullptr;
 };

@@ -10,20 +10,23 @@
 //     stage 3   z[c][.] = WHT_j(C[j^c][j]) ;  out_A = sign_A z[c][b]                  (the 1/16 is folded into rho(M))
 // = 8192 + 2048 flops instead of 131 072: the product becomes HBM-bound (2 * nb * sizeof(T) bytes per row).
 //
-// Shape: persistent, one CTA of 16 warps per SM (512 threads, so each may hold 128 registers), a ring of three 64 KB
-// stages (64-row tiles in f32, 32-row tiles in f64: 256-byte TMA segments per blade row).  The warps form TWO groups of
-// eight; group g transforms the tiles g, g + 2, ... of its CTA IN PLACE, each behind its own named barrier, so the groups
-// sit in different phases instead of sixteen warps marching through the five barriers of a tile in lockstep.  The first
-// thread of a group is its TMA thread: it stores the finished stage and, one barrier into the group's next tile (by then
-// the engine has read the stage), refills it with the tile three ahead.  Inside a stage, slot s holds the rows of one
-// blade / matrix entry; in the transform stages a warp works on ONE slot per instruction with its 32 lanes on 32 rows
-// (conflict free), and the three stages only re-index the 256 slots (blade index -> matrix entry -> blade index; the
-// blade of a string is linear over F_2, so an address costs one XOR and one IMAD).  Stage 2 runs on the tensor cores with
-// the fixed 16 x 16 factor as MMA A-fragments in shared memory: mma.sync m16n8k8 TF32 x 3 (hi/lo split, the same error
-// budget as K6) for f32, mma.sync m8n8k4 on the FP64 tensor pipe for f64.
-// History (profiles/r02_prof_k8_*): v1 did stage 2 with FFMA / DFMA against constant-bank operands --
-// issue-bound at 67 % for f32, bound by lane-indexed constant loads (ADU pipe 75 % busy) for f64: 10.1 / 25.9 ms at 2^24
-// rows; v2 kept the MMA fragments in registers and ptxas re-materialised them with indexed LDC inside the tile loop.
+// v7 layout (matrix_rep.hpp, RepLayout): a unit = 128 bytes of rows (32 f32 / 16 f64) x 256 slots = 32 KB, delivered by
+// TMA with the hardware 128-byte swizzle, slot = blade.  Matrix entry (f, s) lives IN the slot of the coefficient with
+// string (a = f ^ s, b = s) -- nothing is ever scattered to another place:
+//   * stage 1 / 3: a thread owns one 8-byte element (a row pair in f32, a row in f64) of the 16 slots of ONE string row a
+//     and transforms them in place, in registers: no barrier inside the stage, 32 live data registers, packed f32x2
+//     arithmetic (FADD2) in f32; signs and the validity mask (128-blade algebras) are one AND-XOR per word from a table
+//     in shared memory;
+//   * stage 2: mma.sync on the slots of one column (left factor) or one row (right factor) -- the slot of index k is
+//     Lambda(k) ^ Gamma(w), both linear, so a fragment address is two XORs; the sandwich is a column pass followed by a
+//     row pass, no transpose pass in between;
+//   * 3 barriers per unit (4 for the sandwich), each over one group of 8 warps; 2 or 3 groups per CTA work on different
+//     units of a ring of six, so the groups sit in different stages while TMA refills behind them.
+// History (profiles/r02_prof_k8_*): v1 FFMA / DFMA against constant-bank operands (issue-bound / ADU-bound), v2-v5 stage 2
+// on the tensor cores, v6 two 8-warp groups: 9.2 ms f32 / 18.5 ms f64 at 2^24 rows -- ncu showed 2.9 (f32) / 7.2 (f64)
+// warps per issue stalled on long_scoreboard: the per-thread slot tables had spilled, and with 200 KB of the SM carved out
+// as shared memory every reload missed L1 (31 M local loads per 2^22 rows); plus five barriers and ~2300 instructions per
+// thread and tile.  v7 has no per-thread tables (offsets are constant-bank operands), ~1000 instructions, no spills.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -31,6 +34,7 @@
 #include <cstdlib>
 #include <type_traits>
 
+#include "../matrix_rep.hpp"
 #include "launch_args.h"
 #include "misc_kernels.cuh"
 #include "tma_tile.cuh"
@@ -38,39 +42,78 @@
 namespace lcc {
 namespace {
 
-constexpr int kThreadsRep = 512;  // 16 warps: with no 17th warp every thread may hold 128 registers
+constexpr int kGroupThreads = 256;   // 8 warps: 16 half-warps = the 16 string rows of a unit
+constexpr int kUnitBytes = 32768;    // 256 slots x 128 bytes
+constexpr int kRing = 6;             // units in flight per CTA (192 KB)
 
 template <typename T> struct RepParams {
-    T p1[256];           // first factor, [o * 16 + k]:  acc[o] += p1[o][k] * x[k]
-    T p2[256];           // second factor (sandwich only), applied from the right
-    uint8_t blade[256];  // string (a << 4 | b) -> blade index
-    int8_t sign[256];    // string -> +1 / -1, 0 when no blade maps to the string (128-blade algebras)
-    // the string -> blade map is LINEAR over F_2 (the string of a product of blades is the XOR of their strings), so
-    // blade(a << 4 | b) = lin_hi(a) ^ lin_lo(b): the kernel needs 8 bytes, not a table lookup per element
-    uint8_t lin[8];      // image of string bit i (bits 0-3 = b, bits 4-7 = a)
+    T factor[2][256];     // per pass: the fixed 16 x 16 factor in MMA "A" orientation, PHYSICAL order [m * 16 + k]
+    uint32_t f_lo[16];    // F(blade of string b)        F(s) = s << 7 | (s & 7) << 4: byte offset of slot s, swizzle folded in
+    uint32_t f_hi[16];    // F(blade of string a << 4)
+    uint32_t fk[2][16];   // per pass: F(Lambda(logical index at physical MMA position i))
+    uint32_t cw[2][16];   // per pass: F(Gamma(w))
+    uint32_t neg[8];      // bit s: string s carries sign -1
+    uint32_t valid[8];    // bit s: a blade maps to string s
 };
 
-template <typename T> __device__ __forceinline__ void wht16(T (&v)[16]) {
+// ---- packed arithmetic: an 8-byte element is a pair of f32 rows or one f64 row
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+    static __device__ __forceinline__ uint64_t add(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+    static __device__ __forceinline__ uint64_t sub(uint64_t a, uint64_t b) { uint64_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+    // sign / validity: both words are values
+    static __device__ __forceinline__ uint64_t mask(uint64_t v, uint2 m) {
+        const uint32_t lo = ((uint32_t)v & m.x) ^ m.y, hi = ((uint32_t)(v >> 32) & m.x) ^ m.y;
+        return ((uint64_t)hi << 32) | lo;
+    }
+};
+template <> struct Elem<double> {
+    static __device__ __forceinline__ uint64_t add(uint64_t a, uint64_t b) { return (uint64_t)__double_as_longlong(__longlong_as_double((long long)a) + __longlong_as_double((long long)b)); }
+    static __device__ __forceinline__ uint64_t sub(uint64_t a, uint64_t b) { return (uint64_t)__double_as_longlong(__longlong_as_double((long long)a) - __longlong_as_double((long long)b)); }
+    static __device__ __forceinline__ uint64_t mask(uint64_t v, uint2 m) {  // the sign bit sits in the high word
+        const uint32_t lo = (uint32_t)v & m.x, hi = ((uint32_t)(v >> 32) & m.x) ^ m.y;
+        return ((uint64_t)hi << 32) | lo;
+    }
+};
+
+template <typename T> __device__ __forceinline__ void wht16(uint64_t (&v)[16]) {
 #pragma unroll
     for (int h = 1; h < 16; h <<= 1)
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-            if (!(i & h)) { const T x = v[i], y = v[i | h]; v[i] = x + y; v[i | h] = x - y; }
+            if (!(i & h)) { const uint64_t x = v[i], y = v[i | h]; v[i] = Elem<T>::add(x, y); v[i | h] = Elem<T>::sub(x, y); }
 }
 
-
-// Matrix slots: entry (f, s) of a 16 x 16 matrix lives in slot f * 16 + s; inside a slot row r sits at position
-// r ^ swz(f).  The XOR spreads the four k-lanes of an MMA B-fragment load and the m-lanes of a D-fragment store over
-// different banks (derivation in DESIGN.md section 4, K8); in the transform stages f is warp-uniform per instruction, so
-// there the swizzle is a permutation of the 32 lanes and costs nothing.
-template <typename T> struct Swz;
-template <> struct Swz<float> { static __device__ __forceinline__ int of(int f) { return (f & 3) << 3; } };
-template <> struct Swz<double> { static __device__ __forceinline__ int of(int f) { return ((f & 1) << 3) | ((f & 2) << 1); } };
+// Stage 1 (INPUT) / stage 3: the 16 slots of string row a at this thread's element, in place.  t0 = F(lin_hi(a)) ^ byte
+// offset of the element in its line; the slot of string (a, b) is at unit + (t0 ^ f_lo[b]) -- f_lo[b] is a constant-bank
+// operand, so an address is one XOR.  tbl_a = the 16 {and, xor} masks of the row (warp-broadcast loads).
+template <typename T, bool INPUT>
+__device__ __forceinline__ void transform_row(uint8_t *unit, uint32_t t0, const uint2 *tbl_a, const RepParams<T> &P) {
+    uint64_t v[16];
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+        v[b] = *reinterpret_cast<const uint64_t *>(unit + (t0 ^ P.f_lo[b]));
+        if (INPUT) v[b] = Elem<T>::mask(v[b], tbl_a[b]);
+    }
+    wht16<T>(v);
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+        if (!INPUT) v[b] = Elem<T>::mask(v[b], tbl_a[b]);
+        *reinterpret_cast<uint64_t *>(unit + (t0 ^ P.f_lo[b])) = v[b];
+    }
+}
 
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
+}
+// x = hi + lo with hi = x rounded to tf32 (nearest, ties away) by integer arithmetic: cvt.rna.tf32.f32 is a five-instruction
+// sequence on sm_100a (it tests for Inf / NaN), and the MMA ignores the 13 low mantissa bits of its operands anyway, so lo
+// needs no rounding of its own (it is truncated at 2^-10 |lo| <= 2^-21 |x|).
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+    lo = x - hi;
 }
 // (not volatile: pure functions of their operands, so the compiler may interleave independent accumulation chains)
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], float b0, float b1) {
@@ -83,16 +126,12 @@ __device__ __forceinline__ void mma_f64(double (&d)[2], double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
 }
 
-// The fixed 16 x 16 factor as MMA A-fragments.  They depend on the lane only, so warp 0 builds them once per kernel from
-// the parameter block into shared memory ([chunk][lane], 16 bytes per lane and chunk: conflict-free LDS.128) and every
-// warp re-reads the chunk it needs right before its MMAs.  (Held in registers for the whole kernel they did not survive
-// the 96-register budget: ptxas re-materialised them inside the tile loop with lane-indexed constant loads, and the
-// MMAs waited on those -- 40 % of all stall samples in profiles/r02_prof_k8_v2_f64.)
+// The fixed 16 x 16 factor as MMA A-fragments ([chunk][lane], 16 bytes per lane and chunk: conflict-free LDS.128), built
+// once per kernel from the parameter block (already in physical m / k order) and re-read right before the MMAs.
 template <typename T> struct Factor;
 template <> struct Factor<float> {  // m16n8k8, 3xTF32: chunks hi[ks=0], lo[0], hi[1], lo[1]
-    static constexpr int kChunks = 4;
-    const float4 *frag;
-    static __device__ __forceinline__ void build(float4 *dst, const float *p, int lane) {
+    using Frag = float4;
+    static __device__ __forceinline__ void build(Frag *dst, const float *p, int lane) {
         const int g = lane >> 2, t = lane & 3;
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
@@ -106,353 +145,270 @@ template <> struct Factor<float> {  // m16n8k8, 3xTF32: chunks hi[ks=0], lo[0], 
     }
 };
 template <> struct Factor<double> {  // m8n8k4: chunk ks = {a[mb = 0][ks], a[mb = 1][ks]}
-    static constexpr int kChunks = 4;
-    const double2 *frag;
-    static __device__ __forceinline__ void build(double2 *dst, const double *p, int lane) {
+    using Frag = double2;
+    static __device__ __forceinline__ void build(Frag *dst, const double *p, int lane) {
         const int g = lane >> 2, t = lane & 3;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) dst[ks * 32 + lane] = make_double2(p[g * 16 + 4 * ks + t], p[(8 + g) * 16 + 4 * ks + t]);
     }
 };
 
-// D = F * Z for all rows of one column (second index = w) of the matrix in `st`, in place: Z[k][w] -> D[o][w].
-// n-blocks of 8 rows, kQ of them side by side so that their accumulation chains (6 dependent MMAs for f32, 4 for f64)
-// overlap; every B fragment of a group of n-blocks is read before any of its D fragments is written.
-template <int TR>
-__device__ __forceinline__ void column_gemm(float *st, const Factor<float> &F, int w, int lane) {
+// Stage 2, one pass: D[o] = sum_k A[o][k] Z[k] on the 16 slots {Lambda(k) ^ Gamma(w)} of index w, all rows, in place, for
+// w = wl and wl + 8.  tabs = fk[16] then cw[16] of the pass.  Row bytes r of slot offset F sit at F ^ r.  Every B fragment
+// of a group of n-blocks is read before any of its D fragments is written (the MMAs are warp-synchronous in between).
+__device__ __forceinline__ void gemm_pass(uint8_t *unit, const float4 *frag, const uint32_t *tabs, int wl, int lane, float) {
     const int g = lane >> 2, t = lane & 3;
-    constexpr int kQ = 4;
+    uint32_t lk[2][2], lo[2];
 #pragma unroll
-    for (int q0 = 0; q0 < TR / 8; q0 += kQ) {
-        float d[kQ][4], b[kQ][2][2];
+    for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-        for (int qq = 0; qq < kQ; ++qq) {
-            const int q = q0 + qq;
+        for (int h = 0; h < 2; ++h) lk[ks][h] = tabs[8 * ks + 4 * h + t] ^ (uint32_t)(g << 2);  // B[k = 8ks + 4h + t][n = g]: row 8q + g
 #pragma unroll
-            for (int e = 0; e < 4; ++e) d[qq][e] = 0.f;
+    for (int mb = 0; mb < 2; ++mb) lo[mb] = tabs[g + 8 * mb] ^ (uint32_t)(t << 3);              // D[m = g + 8mb][n = 2t, 2t + 1]: rows 8q + 2t, + 1
+#pragma unroll 1
+    for (int wi = 0; wi < 2; ++wi) {
+        const uint32_t cw = tabs[16 + wl + 8 * wi];
+        float d[4][4], b[4][2][2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) d[q][e] = 0.f;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-                for (int h = 0; h < 2; ++h)  // row (8q + g) of the half it is in, XOR (t << 3)
-                    b[qq][ks][h] = st[((8 * ks + 4 * h + t) * 16 + w) * TR + (q >> 2) * 32 + (8 * ((q & 3) ^ t) + g)];
+                for (int h = 0; h < 2; ++h) b[q][ks][h] = *reinterpret_cast<const float *>(unit + (lk[ks][h] ^ cw ^ (uint32_t)(q << 5)));
         }
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
-            const float4 fh = F.frag[(2 * ks) * 32 + lane], fl = F.frag[(2 * ks + 1) * 32 + lane];
-            const float hi[4] = {fh.x, fh.y, fh.z, fh.w}, lo[4] = {fl.x, fl.y, fl.z, fl.w};
-            float bh[kQ][2], bl[kQ][2];
+            const float4 fh = frag[(2 * ks) * 32 + lane], fl = frag[(2 * ks + 1) * 32 + lane];
+            const float hi[4] = {fh.x, fh.y, fh.z, fh.w}, lw[4] = {fl.x, fl.y, fl.z, fl.w};
+            float bh[4][2], bl[4][2];
 #pragma unroll
-            for (int qq = 0; qq < kQ; ++qq)
+            for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int h = 0; h < 2; ++h) { bh[qq][h] = tf32_rna(b[qq][ks][h]); bl[qq][h] = tf32_rna(b[qq][ks][h] - bh[qq][h]); }
+                for (int h = 0; h < 2; ++h) split_tf32(b[q][ks][h], bh[q][h], bl[q][h]);
 #pragma unroll
-            for (int qq = 0; qq < kQ; ++qq) mma_tf32(d[qq], lo, bh[qq][0], bh[qq][1]);  // small terms first
+            for (int q = 0; q < 4; ++q) mma_tf32(d[q], lw, bh[q][0], bh[q][1]);  // small terms first
 #pragma unroll
-            for (int qq = 0; qq < kQ; ++qq) mma_tf32(d[qq], hi, bl[qq][0], bl[qq][1]);
+            for (int q = 0; q < 4; ++q) mma_tf32(d[q], hi, bl[q][0], bl[q][1]);
 #pragma unroll
-            for (int qq = 0; qq < kQ; ++qq) mma_tf32(d[qq], hi, bh[qq][0], bh[qq][1]);
+            for (int q = 0; q < 4; ++q) mma_tf32(d[q], hi, bh[q][0], bh[q][1]);
         }
 #pragma unroll
-        for (int qq = 0; qq < kQ; ++qq) {
-            const int q = q0 + qq;
-            const int pos = (q >> 2) * 32 + 8 * ((q & 3) ^ (g & 3)) + 2 * t;  // (8q + 2t) ^ ((g & 3) << 3); rows 2t, 2t+1 stay adjacent
-            *reinterpret_cast<float2 *>(st + (g * 16 + w) * TR + pos) = make_float2(d[qq][0], d[qq][1]);
-            *reinterpret_cast<float2 *>(st + ((g + 8) * 16 + w) * TR + pos) = make_float2(d[qq][2], d[qq][3]);
-        }
-    }
-}
-template <int TR>
-__device__ __forceinline__ void column_gemm(double *st, const Factor<double> &F, int w, int lane) {
-    const int g = lane >> 2, t = lane & 3;
-    constexpr int kQ = 2;
-    const int sb = ((t & 1) << 3) | ((t & 2) << 1), sd = ((g & 1) << 3) | ((g & 2) << 1);
-#pragma unroll
-    for (int q0 = 0; q0 < TR / 8; q0 += kQ) {
-        double d[kQ][2][2], b[kQ][4];
-#pragma unroll
-        for (int qq = 0; qq < kQ; ++qq) {
-            const int q = q0 + qq;
-#pragma unroll
-            for (int mb = 0; mb < 2; ++mb) d[qq][mb][0] = d[qq][mb][1] = 0.0;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) b[qq][ks] = st[((4 * ks + t) * 16 + w) * TR + (q >> 2) * 32 + (((8 * (q & 3)) + g) ^ sb)];
-        }
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            const double2 f = F.frag[ks * 32 + lane];
-#pragma unroll
-            for (int qq = 0; qq < kQ; ++qq) {
-                mma_f64(d[qq][0], f.x, b[qq][ks]);
-                mma_f64(d[qq][1], f.y, b[qq][ks]);
-            }
-        }
-#pragma unroll
-        for (int qq = 0; qq < kQ; ++qq) {
-            const int q = q0 + qq;
-            const int pos = (q >> 2) * 32 + ((8 * (q & 3) + 2 * t) ^ sd);
+        for (int q = 0; q < 4; ++q)
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb)
-                *reinterpret_cast<double2 *>(st + ((8 * mb + g) * 16 + w) * TR + pos) = make_double2(d[qq][mb][0], d[qq][mb][1]);
-        }
+                *reinterpret_cast<float2 *>(unit + (lo[mb] ^ cw ^ (uint32_t)(q << 5))) = make_float2(d[q][2 * mb], d[q][2 * mb + 1]);
     }
 }
+__device__ __forceinline__ void gemm_pass(uint8_t *unit, const double2 *frag, const uint32_t *tabs, int wl, int lane, double) {
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t lk[4], lo[2];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) lk[ks] = tabs[4 * ks + t] ^ (uint32_t)(g << 3);              // B[k = 4ks + t][n = g]: row 8q + g
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) lo[mb] = tabs[g + 8 * mb] ^ (uint32_t)(t << 4);              // D[m = g + 8mb][n = 2t, 2t + 1]
+    const uint32_t cw[2] = {tabs[16 + wl], tabs[16 + wl + 8]};
+    double d[2][2][2][2], b[2][2][4];  // [wi][q]...: four independent chains of four DMMAs per m-block
+#pragma unroll
+    for (int wi = 0; wi < 2; ++wi)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb) d[wi][q][mb][0] = d[wi][q][mb][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) b[wi][q][ks] = *reinterpret_cast<const double *>(unit + (lk[ks] ^ cw[wi] ^ (uint32_t)(q << 6)));
+        }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const double2 f = frag[ks * 32 + lane];
+#pragma unroll
+        for (int wi = 0; wi < 2; ++wi)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                mma_f64(d[wi][q][0], f.x, b[wi][q][ks]);
+                mma_f64(d[wi][q][1], f.y, b[wi][q][ks]);
+            }
+    }
+#pragma unroll
+    for (int wi = 0; wi < 2; ++wi)
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+                *reinterpret_cast<double2 *>(unit + (lo[mb] ^ cw[wi] ^ (uint32_t)(q << 6))) = make_double2(d[wi][q][mb][0], d[wi][q][mb][1]);
+}
 
-template <typename T> struct RepShape;  // rows per tile (32 per lane-row) and ring depth
-template <> struct RepShape<float> { static constexpr int kRowsPerLane = 2, kStages = 3; };   // 64-row tiles: 256-byte TMA segments, 64 KB stages
-template <> struct RepShape<double> { static constexpr int kRowsPerLane = 1, kStages = 3; };  // 32-row tiles: 256-byte TMA segments, 64 KB stages
+// shared memory behind the ring: barriers, sign table, pass tables, factor fragments
+constexpr int kTblPitch = 17;  // entries per string row: the two rows a warp reads sit 136 bytes apart
+constexpr int kAuxBar = 0, kAuxTbl = 64, kAuxTabs = kAuxTbl + 16 * kTblPitch * 8, kAuxFrag = kAuxTabs + 2 * 32 * 4, kAuxBytes = kAuxFrag + 2 * 4 * 32 * 16;
 
-// MODE 0: out = M * x      C = P1 X            matrix slots hold X / C as (row index, column index)
-// MODE 1: out = x * M      C^T = P1 X^T        the same column GEMM on the TRANSPOSED slots (p1 arrives as [j][k] = rho(M)[k][j])
-// MODE 2: out = R x ~R     T = P1 X, transpose pass, C^T = P2 T^T   (p1 = rho(R) / 16, p2[j][k] = rho(~R)[k][j])
-template <typename T, int MODE>
-__global__ void __launch_bounds__(kThreadsRep, 1)
+// NPASS 1: out = M x (column pass) or x M (row pass) -- the host chooses the tables; NPASS 2: out = R x ~R (column pass
+// with rho(R) / 16, row pass with rho(~R)).  NG groups of 8 warps.
+template <typename T, int NPASS, int NG>
+__global__ void __launch_bounds__(NG *kGroupThreads, 1)
 matrix_rep_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_out,
-                  const __grid_constant__ RepParams<T> P, int nb, int64_t n, int dbg) {
-    constexpr int RPL = RepShape<T>::kRowsPerLane, TR = 32 * RPL, NS = RepShape<T>::kStages;
-    constexpr uint32_t kStageBytes = 256u * TR * sizeof(T);
+                  const __grid_constant__ RepParams<T> P, int nb, int64_t n, int dbg, int order) {
+    constexpr int TR = 128 / (int)sizeof(T);
+    using Frag = typename Factor<T>::Frag;
     extern __shared__ __align__(1024) uint8_t smem[];  // no static shared memory in this kernel: the window starts aligned
-    uint64_t *full = (uint64_t *)(smem + (size_t)NS * kStageBytes);
-    using Frag = typename std::remove_const<typename std::remove_pointer<decltype(Factor<T>::frag)>::type>::type;
-    Frag *frag1 = (Frag *)(smem + (size_t)NS * kStageBytes + 64), *frag2 = frag1 + Factor<T>::kChunks * 32;
+    uint8_t *aux = smem + (size_t)kRing * kUnitBytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(aux + kAuxBar);
+    uint2 *tbl = reinterpret_cast<uint2 *>(aux + kAuxTbl);
+    uint32_t *tabs = reinterpret_cast<uint32_t *>(aux + kAuxTabs);
+    Frag *frag = reinterpret_cast<Frag *>(aux + kAuxFrag);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t tiles = (n + TR - 1) / TR;
-    const uint32_t box_bytes = (uint32_t)nb * TR * sizeof(T);
-    const int64_t mine = tiles > blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    auto tile_row = [&](int64_t k) { return (int)((blockIdx.x + k * gridDim.x) * TR); };
+    const int64_t units = (n + TR - 1) / TR;
+    const uint32_t box_bytes = (uint32_t)nb * 128u;
+    // order 0: unit k of this CTA is unit blockIdx.x + k * gridDim.x of the batch (neighbouring CTAs work on neighbouring
+    // rows at about the same time); order 1: every CTA owns one contiguous range of units, so the six units of its ring
+    // are neighbouring 128-byte pieces of the same DRAM pages
+    const int64_t per_cta = (units + gridDim.x - 1) / gridDim.x;
+    const int64_t first = order ? (int64_t)blockIdx.x * per_cta : (int64_t)blockIdx.x;
+    const int64_t step = order ? 1 : (int64_t)gridDim.x;
+    const int64_t mine = order ? (first >= units ? 0 : (units - first < per_cta ? units - first : per_cta))
+                               : (units > blockIdx.x ? (units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+    auto unit_row = [&](int64_t k) { return (int)((first + k * step) * TR); };
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NS; ++s) tma::mbar_init(&full[s], 1);
+        for (int s = 0; s < kRing; ++s) tma::mbar_init(&full[s], 1);
         tma::prefetch_map(&map_x);
         tma::prefetch_map(&map_out);
     }
-    if (warp == 0) {
-        Factor<T>::build(frag1, P.p1, lane);
-        if (MODE == 2) Factor<T>::build(frag2, P.p2, lane);
+    for (int s = threadIdx.x; s < 256; s += NG * kGroupThreads)
+        tbl[(s >> 4) * kTblPitch + (s & 15)] = make_uint2(((P.valid[s >> 5] >> (s & 31)) & 1u) ? 0xffffffffu : 0u, ((P.neg[s >> 5] >> (s & 31)) & 1u) ? 0x80000000u : 0u);
+    if (threadIdx.x < 64) {
+        const int p = threadIdx.x >> 5, i = threadIdx.x & 31;
+        tabs[threadIdx.x] = i < 16 ? P.fk[p][i] : P.cw[p][i - 16];
     }
+    if (warp < NPASS) Factor<T>::build(frag + warp * 4 * 32, P.factor[warp], lane);
     __syncthreads();
     if (threadIdx.x == 0)
-        for (int64_t k = 0; k < mine && k < NS; ++k) {  // fill the ring
+        for (int64_t k = 0; k < mine && k < kRing; ++k) {  // fill the ring
             tma::mbar_expect_tx(&full[k], box_bytes);
-            tma::load_2d(smem + (size_t)k * kStageBytes, &map_x, &full[k], tile_row(k), 0);
+            tma::load_2d(smem + (size_t)k * kUnitBytes, &map_x, &full[k], unit_row(k), 0);
         }
-    {
-        // ---- 16 compute warps in TWO groups of 8: group g transforms the tiles g, g + 2, g + 4, ... of this CTA, each on
-        // its own stage and behind its own named barrier, so the two groups sit in different phases (one in a
-        // shared-memory pass while the other is in its MMAs) instead of all 16 warps marching through the five barriers
-        // of a tile in lockstep.  A warp owns TWO indices (wl and wl + 8) of its group's tile; lane = row (and row + 32).
-        const int grp = warp >> 3, wl = warp & 7;
-        const int gtid = threadIdx.x & 255;
-        auto group_sync = [&]() {
-            if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
-            else asm volatile("bar.sync 2, 256;" ::: "memory");
-        };
-        // per-index constants (two indices per warp): the warp-dependent part of the blade index, sign-flip masks of the
-        // 16 blades of string row w (applied to the sign bit: one XOR per element), validity mask (128-blade algebras)
-        int blade_hi[2];
-        uint32_t neg[2], valid[2];
-        int lsw[2];  // lane ^ swz(w): with swz linear over XOR, lane ^ swz(j ^ w) = lsw ^ swz(j)
-#pragma unroll
-        for (int ii = 0; ii < 2; ++ii) {
-            const int w = wl + 8 * ii;
-            blade_hi[ii] = 0; neg[ii] = 0; valid[ii] = 0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) blade_hi[ii] ^= ((w >> i) & 1) ? (int)P.lin[4 + i] : 0;
-#pragma unroll
-            for (int b = 0; b < 16; ++b) {
-                const int sg = P.sign[(w << 4) | b];
-                neg[ii] |= (sg < 0 ? 1u : 0u) << b;
-                valid[ii] |= (sg != 0 ? 1u : 0u) << b;
+    const int grp = warp >> 3, wl = warp & 7;
+    const int gtid = threadIdx.x & (kGroupThreads - 1);
+    auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kGroupThreads) : "memory"); };
+    // stage 1 / 3 role: string row a = 2 * wl + (lane >> 4), 8-byte element lane & 15 of the 128-byte line
+    const int a_row = 2 * wl + (lane >> 4);
+    const uint32_t t0 = P.f_hi[a_row] ^ (uint32_t)((lane & 15) << 3);
+    const uint2 *tbl_a = tbl + a_row * kTblPitch;
+    // The group's first thread is also its TMA thread: it stores the group's finished unit and, one barrier into the
+    // group's NEXT unit (by then the engine has read the slot), refills that slot with the unit kRing ahead.
+    int64_t stored = -1;
+    auto refill = [&]() {
+        if (gtid == 0 && stored >= 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (stored + kRing < mine) {
+                const int rs = (int)(stored % kRing);
+                tma::mbar_expect_tx(&full[rs], box_bytes);
+                tma::load_2d(smem + (size_t)rs * kUnitBytes, &map_x, &full[rs], unit_row(stored + kRing), 0);
             }
-            lsw[ii] = lane ^ Swz<T>::of(w);
+            stored = -1;
         }
-        int blade_lo[16];   // blade of string b: the same for every thread of the grid
-#pragma unroll
-        for (int b = 0; b < 16; ++b)
-            blade_lo[b] = ((b & 1) ? (int)P.lin[0] : 0) ^ ((b & 2) ? (int)P.lin[1] : 0) ^ ((b & 4) ? (int)P.lin[2] : 0) ^ ((b & 8) ? (int)P.lin[3] : 0);
-        const bool full_algebra = nb == 256;
-        // matrix-slot offset of entry j of index w: normal slots X[j^w][j] or transposed X^T[j][j^w]
-        auto slot_off = [&](int j, int w, int ls, bool transposed) {
-            const int f = transposed ? j : (j ^ w), sec = transposed ? (j ^ w) : j;
-            const int pos = transposed ? (lane ^ Swz<T>::of(j)) : (ls ^ Swz<T>::of(j));
-            return (f * 16 + sec) * TR + pos;
-        };
-        auto flip = [](T x, bool negative) { return negative ? -x : x; };
-        Factor<T> F1, F2;
-        F1.frag = frag1;
-        F2.frag = frag2;
-        // The group's first thread is also its TMA thread: it stores the group's finished tile and, one barrier into the
-        // NEXT tile (by then the engine has read the stage), refills that stage with the tile NS ahead.
-        int64_t stored = -1;  // tile whose store this thread issued last (its stage is refilled once the store has been read)
-        auto refill = [&]() {
-            if (gtid == 0 && stored >= 0) {
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                if (stored + NS < mine) {
-                    const int rs = (int)(stored % NS);
-                    tma::mbar_expect_tx(&full[rs], box_bytes);
-                    tma::load_2d(smem + (size_t)rs * kStageBytes, &map_x, &full[rs], tile_row(stored + NS), 0);
-                }
-                stored = -1;
-            }
-        };
-        auto store_tile = [&](int64_t it, int s) {
-            if (gtid == 0) {
-                tma::store_2d(&map_out, smem + (size_t)s * kStageBytes, tile_row(it), 0);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                stored = it;
-            }
-        };
-        for (int64_t it = grp; it < mine; it += 2) {
-            const int s = (int)(it % NS);
-            const uint32_t ph = (uint32_t)((it / NS) & 1);
-            T *st = (T *)(smem + (size_t)s * kStageBytes);
-            tma::mbar_wait(&full[s], ph);
-            if (dbg == 1) {  // LCC_K8_DEBUG=1: tiles pass through untouched (memory pipeline alone)
-                refill();
-                group_sync();
-                store_tile(it, s);
-                continue;
-            }
-            T v[2][RPL][16];
-            // stage 1: gather y[w][.] from the blade slots, transform, scatter to the matrix slots
-#pragma unroll
-            for (int ii = 0; ii < 2; ++ii)
-#pragma unroll
-                for (int h = 0; h < RPL; ++h) {
-#pragma unroll
-                    for (int b = 0; b < 16; ++b) {
-                        const T x = st[(blade_hi[ii] ^ blade_lo[b]) * TR + lane + 32 * h];
-                        v[ii][h][b] = flip(x, (neg[ii] >> b) & 1u);
-                        if (!full_algebra && !((valid[ii] >> b) & 1u)) v[ii][h][b] = T(0);
-                    }
-                    wht16(v[ii][h]);
-                }
-            refill();      // the previous tile's store has long been read: put the next load in flight
-            group_sync();  // every blade slot of the tile has been read
-#pragma unroll
-            for (int ii = 0; ii < 2; ++ii)
-#pragma unroll
-                for (int h = 0; h < RPL; ++h)
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) st[slot_off(j, wl + 8 * ii, lsw[ii], MODE == 1) + 32 * h] = v[ii][h][j];
-            group_sync();
-            // stage 2 on the tensor cores: the columns with second index w, in place
-            if (dbg != 2) {  // LCC_K8_DEBUG=2: transforms only
-                column_gemm<TR>(st, F1, wl, lane);
-                column_gemm<TR>(st, F1, wl + 8, lane);
-            }
-            if (MODE == 2) {
-                group_sync();
-                // transpose pass: T[i][w] -> T^T[w][i] (the first index is warp-uniform on both sides: conflict free)
-#pragma unroll
-                for (int ii = 0; ii < 2; ++ii)
-#pragma unroll
-                    for (int h = 0; h < RPL; ++h)
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[ii][h][i] = st[(i * 16 + wl + 8 * ii) * TR + 32 * h + (lane ^ Swz<T>::of(i))];
-                group_sync();
-#pragma unroll
-                for (int ii = 0; ii < 2; ++ii)
-#pragma unroll
-                    for (int h = 0; h < RPL; ++h)
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) st[((wl + 8 * ii) * 16 + i) * TR + 32 * h + lsw[ii]] = v[ii][h][i];
-                group_sync();
-                column_gemm<TR>(st, F2, wl, lane);
-                column_gemm<TR>(st, F2, wl + 8, lane);
-            }
-            group_sync();
-            // stage 3: gather the 16 matrix entries of string row w, transform back, scatter to the blade slots
-#pragma unroll
-            for (int ii = 0; ii < 2; ++ii)
-#pragma unroll
-                for (int h = 0; h < RPL; ++h) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[ii][h][j] = st[slot_off(j, wl + 8 * ii, lsw[ii], MODE != 0) + 32 * h];
-                    wht16(v[ii][h]);
-                }
-            group_sync();  // every matrix slot has been read
-#pragma unroll
-            for (int ii = 0; ii < 2; ++ii)
-#pragma unroll
-                for (int h = 0; h < RPL; ++h)
-#pragma unroll
-                    for (int b = 0; b < 16; ++b)
-                        if (full_algebra || ((valid[ii] >> b) & 1u))
-                            st[(blade_hi[ii] ^ blade_lo[b]) * TR + lane + 32 * h] = flip(v[ii][h][b], (neg[ii] >> b) & 1u);
-            tma::fence_proxy_async();
-            group_sync();
-            store_tile(it, s);
+    };
+    auto store_unit = [&](int64_t it, int s) {
+        if (gtid == 0) {
+            tma::store_2d(&map_out, smem + (size_t)s * kUnitBytes, unit_row(it), 0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            stored = it;
         }
-        refill();  // (waits for the read of the last store; nothing left to load)
-        if (gtid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // global writes complete before the CTA exits
+    };
+    for (int64_t it = grp; it < mine; it += NG) {
+        const int s = (int)(it % kRing);
+        const uint32_t ph = (uint32_t)((it / kRing) & 1);
+        uint8_t *unit = smem + (size_t)s * kUnitBytes;
+        tma::mbar_wait(&full[s], ph);
+        if (dbg == 1) {  // LCC_K8_DEBUG=1: units pass through untouched (memory pipeline alone)
+            refill();
+            group_sync();
+            store_unit(it, s);
+            continue;
+        }
+        transform_row<T, true>(unit, t0, tbl_a, P);
+        refill();      // the previous unit's store has long been read: put the next load in flight
+        group_sync();
+        if (dbg != 2) {  // LCC_K8_DEBUG=2: transforms only
+#pragma unroll
+            for (int p = 0; p < NPASS; ++p) {
+                gemm_pass(unit, frag + p * 4 * 32, tabs + p * 32, wl, lane, T());
+                group_sync();
+            }
+        }
+        transform_row<T, false>(unit, t0, tbl_a, P);
+        tma::fence_proxy_async();
+        group_sync();
+        store_unit(it, s);
     }
+    refill();  // (waits for the read of the last store; nothing left to load)
+    if (gtid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // global writes complete before the CTA exits
 }
 
-template <typename T, int MODE>
+int rep_groups() {
+    static const int g = [] { const char *e = getenv("LCC_K8_GROUPS"); const int v = e ? atoi(e) : 0; return v == 2 || v == 3 ? v : 0; }();
+    return g;
+}
+
+template <typename T, int NPASS, int NG>
 cudaError_t launch_rep_t(int nb, const void *x, int64_t ldx, void *out, int64_t ldo, int64_t n, const RepParams<T> &P, cudaStream_t s) {
-    constexpr int TR = 32 * RepShape<T>::kRowsPerLane, NS = RepShape<T>::kStages;
+    constexpr int TR = 128 / (int)sizeof(T);
     CUtensorMap mx, mo;
-    if (!make_soa_tensor_map(&mx, x, (int)sizeof(T), nb, ldx, n, TR) || !make_soa_tensor_map(&mo, out, (int)sizeof(T), nb, ldo, n, TR))
+    static const int promo = [] { const char *e = getenv("LCC_K8_L2PROMO"); return e ? atoi(e) : 256; }();
+    static const int order = [] { const char *e = getenv("LCC_K8_ORDER"); return e ? atoi(e) : 1; }();
+    static const bool swz = [] { const char *e = getenv("LCC_K8_SWIZZLE"); return !(e && e[0] == '0'); }();  // 0: only meaningful with LCC_K8_DEBUG=1
+    if (!make_soa_tensor_map(&mx, x, (int)sizeof(T), nb, ldx, n, TR, swz, promo) || !make_soa_tensor_map(&mo, out, (int)sizeof(T), nb, ldo, n, TR, swz, promo))
         return cudaErrorNotSupported;
-    auto kernel = matrix_rep_kernel<T, MODE>;
-    constexpr int smem = NS * 256 * TR * (int)sizeof(T) + 64 + 2 * Factor<T>::kChunks * 32 * 16;  // stages, barriers, two factors
+    auto kernel = matrix_rep_kernel<T, NPASS, NG>;
+    constexpr int smem = kRing * kUnitBytes + kAuxBytes;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     static int sm_count = [] { int d = 0, c = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, d); return c > 0 ? c : 148; }();
-    const int64_t tiles = (n + TR - 1) / TR;
-    const int grid = (int)(tiles < sm_count ? tiles : sm_count);
+    const int64_t units = (n + TR - 1) / TR;
+    const int grid = (int)(units < sm_count ? units : sm_count);
     static const int dbg = [] { const char *e = getenv("LCC_K8_DEBUG"); return e ? atoi(e) : 0; }();
-    kernel<<<grid, kThreadsRep, smem, s>>>(mx, mo, P, nb, n, dbg);
+    kernel<<<grid, NG * kGroupThreads, smem, s>>>(mx, mo, P, nb, n, dbg, order);
     note_kernel_launch();
     return cudaGetLastError();
 }
 
+template <typename T> constexpr int default_groups() { return sizeof(T) == 4 ? 3 : 3; }
+
 template <typename T>
 cudaError_t launch_rep(int nb, int mode, const double *p1, const double *p2, const uint8_t *blade_at, const int8_t *sign_at,
                        const ViewArg &x, const ViewArg &out, cudaStream_t s) {
+    const RepLayout L = make_rep_layout(blade_at, sign_at);
+    if (!L.ok) return cudaErrorNotSupported;
     RepParams<T> P;
-    for (int i = 0; i < 256; ++i) {
-        P.p1[i] = (T)p1[i];
-        P.p2[i] = p2 ? (T)p2[i] : T(0);
-        P.blade[i] = blade_at[i];
-        P.sign[i] = sign_at[i];
+    // mode 0: column pass with p1; mode 1: row pass with p1; mode 2: column pass with p1, row pass with p2
+    const RepPass *pass[2] = {mode == 1 ? &L.row : &L.column, &L.row};
+    const double *fac[2] = {p1, p2};
+    for (int p = 0; p < 2; ++p)
+        for (int i = 0; i < 16; ++i) {
+            P.fk[p][i] = pass[p]->fk[i];
+            P.cw[p][i] = pass[p]->cw[i];
+            for (int k = 0; k < 16; ++k) P.factor[p][i * 16 + k] = fac[p] ? (T)fac[p][pass[p]->kmap[i] * 16 + pass[p]->kmap[k]] : T(0);
+        }
+    for (int i = 0; i < 16; ++i) { P.f_lo[i] = L.f_lo[i]; P.f_hi[i] = L.f_hi[i]; }
+    for (int i = 0; i < 8; ++i) P.neg[i] = P.valid[i] = 0;
+    for (int str = 0; str < 256; ++str) {
+        if (sign_at[str] != 0) P.valid[str >> 5] |= 1u << (str & 31);
+        if (sign_at[str] < 0) P.neg[str >> 5] |= 1u << (str & 31);
     }
-    // linear extension of string -> blade to all 256 strings: close the valid (string, blade) pairs of the basis blades
-    // under XOR; a 128-blade algebra spans only half the strings, the other half gets blade indices 128..255 (slots that
-    // exist in a stage but hold no data: such strings are masked out by sign == 0 anyway)
-    {
-        int lin[256], have[256];
-        for (int i = 0; i < 256; ++i) { lin[i] = 0; have[i] = 0; }
-        have[0] = 1;
-        int count = 1, next_blade = 1;
-        auto add = [&](int str, int blade) {
-            if (have[str]) return;
-            for (int t = 0; t < 256; ++t)
-                if (have[t] == 1) { lin[t ^ str] = lin[t] ^ blade; have[t ^ str] = 2; }
-            for (int t = 0; t < 256; ++t) if (have[t] == 2) have[t] = 1;
-            count *= 2;
-        };
-        for (int str = 1; str < 256; ++str)
-            if (sign_at[str] != 0 && (blade_at[str] & (blade_at[str] - 1)) == 0) { add(str, blade_at[str]); if (blade_at[str] >= next_blade) next_blade = blade_at[str] << 1; }
-        for (int str = 1; str < 256 && count < 256; ++str)
-            if (!have[str]) { add(str, next_blade); next_blade <<= 1; }
-        for (int str = 0; str < 256; ++str)
-            if (sign_at[str] != 0 && lin[str] != blade_at[str]) return cudaErrorNotSupported;  // cannot happen for a homomorphism
-        for (int i = 0; i < 8; ++i) P.lin[i] = (uint8_t)lin[1 << i];
-    }
-    switch (mode) {
-        case 0: return launch_rep_t<T, 0>(nb, x.data, x.ld, out.data, out.ld, x.n, P, s);
-        case 1: return launch_rep_t<T, 1>(nb, x.data, x.ld, out.data, out.ld, x.n, P, s);
-        case 2: return launch_rep_t<T, 2>(nb, x.data, x.ld, out.data, out.ld, x.n, P, s);
-    }
+    const int ng = rep_groups() ? rep_groups() : default_groups<T>();
+    if (mode == 2)
+        return ng == 2 ? launch_rep_t<T, 2, 2>(nb, x.data, x.ld, out.data, out.ld, x.n, P, s) : launch_rep_t<T, 2, 3>(nb, x.data, x.ld, out.data, out.ld, x.n, P, s);
+    if (mode == 0 || mode == 1)
+        return ng == 2 ? launch_rep_t<T, 1, 2>(nb, x.data, x.ld, out.data, out.ld, x.n, P, s) : launch_rep_t<T, 1, 3>(nb, x.data, x.ld, out.data, out.ld, x.n, P, s);
     return cudaErrorInvalidValue;
 }
 
 }  // namespace
 
 // K8 launcher.  mode 0 / 1 / 2 = left product, right product, sandwich; p1 (and p2 for the sandwich) are row-major 16 x 16
-// f64 factors already in the orientation the kernel indexes ([o][k], see RepParams) with the 1/16 of the inverse
-// transform folded into p1; blade_at / sign_at map a string to its blade and sign.  x and out are blade-major (SoA) views
-// of nb = 128 or 256 blades whose row count is a multiple of 16 bytes (TMA stores clip at that granularity).
+// f64 factors in the orientation the MMA contracts ([o][k]: mode 0 rho(M) / 16, mode 1 rho(M)^T / 16, mode 2 rho(R) / 16 and
+// rho(~R)^T); blade_at / sign_at map a string to its blade and sign.  x and out are blade-major (SoA) views of nb = 128 or
+// 256 blades whose row count is a multiple of 16 bytes (TMA stores clip at that granularity).
 cudaError_t launch_matrix_rep_product(int nb, int mode, const double *p1, const double *p2, const uint8_t *blade_at, const int8_t *sign_at,
                                       const ViewArg &x, const ViewArg &out, cudaStream_t s) {
     if (x.n <= 0) return cudaSuccess;

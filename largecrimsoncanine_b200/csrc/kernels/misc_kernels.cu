@@ -1060,7 +1060,26 @@ cudaError_t launch_sum(int nb, const ViewArg &x, void *sums_dev, void *scratch_d
             sum_partial_soa<T><<<dim3(nblocks, nb), kThreads, 0, s>>>((const T *)x.data, x.ld, n, rows_per_block, vec_ok, (double *)scratch_dev);
         } else if (aos_vec_ok(x, nb, VecW<T>::value)) {
             const int cpr = nb / VecW<T>::value;
-            sum_partial_aos_vec<T><<<nblocks, kThreads, 0, s>>>((const T *)x.data, x.ld, n, nb, ilog2(cpr), rows_per_block, (double *)scratch_dev);
+            // Whole waves only: at 34 (f32) / 42 (f64) registers 6 / 5 blocks are resident per SM, so the full grid of
+            // 148 * 32 blocks was 5.3 / 6.4 waves and the last, partly filled wave left half of the SMs idle for a
+            // block's lifetime (5.98-6.4 TB/s where the sibling kernels stream at 6.9+).  The largest multiple of
+            // (SMs x resident blocks) below the cap keeps every wave full; the partial sums stay a fixed tree.
+            static const int wave = [] {
+                int dev = 0, sms = 148, occ = 0;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sum_partial_aos_vec<T>, kThreads, 0) != cudaSuccess || occ < 1) occ = 4;
+                return sms * occ;
+            }();
+            int grid = nblocks;
+            if (nblocks == kSumBlocksMaxAos && wave <= kSumBlocksMaxAos) {
+                grid = kSumBlocksMaxAos / wave * wave;
+                rows_per_block = ((n + grid - 1) / grid + 3) & ~(int64_t)3;
+            }
+            sum_partial_aos_vec<T><<<grid, kThreads, 0, s>>>((const T *)x.data, x.ld, n, nb, ilog2(cpr), rows_per_block, (double *)scratch_dev);
+            note_kernel_launch();
+            sum_final<T><<<nb, kThreads, 0, s>>>((const double *)scratch_dev, grid, (T *)sums_dev);
+            return;
         } else {
             sum_partial_aos<T><<<nblocks, kThreads, 0, s>>>((const T *)x.data, x.ld, n, nb, rows_per_block, (double *)scratch_dev);
         }
@@ -1249,7 +1268,7 @@ EncodeFn tensor_map_encoder() {
 }
 }  // namespace
 
-bool make_soa_tensor_map(CUtensorMap *map, const void *base, int elem_bytes, int nb, int64_t ld, int64_t n, int rows) {
+bool make_soa_tensor_map(CUtensorMap *map, const void *base, int elem_bytes, int nb, int64_t ld, int64_t n, int rows, bool swizzle128, int l2_promotion) {
     EncodeFn enc = tensor_map_encoder();
     if (!enc || n <= 0 || n >= (int64_t)1 << 31) return false;
     if (((uintptr_t)base & 15) != 0 || ((ld * elem_bytes) & 15) != 0 || ld < n) return false;
@@ -1261,8 +1280,11 @@ bool make_soa_tensor_map(CUtensorMap *map, const void *base, int elem_bytes, int
     const cuuint32_t box[2] = {(cuuint32_t)rows, (cuuint32_t)nb};
     const cuuint32_t estr[2] = {1, 1};
     const CUtensorMapDataType dt = elem_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    if (swizzle128 && rows * elem_bytes != 128) return false;  // the swizzle span is one 128-byte box row
     return enc(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+               l2_promotion >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : (l2_promotion >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : (l2_promotion >= 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE)),
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 bool make_aos_tensor_map(CUtensorMap *map, const void *base, int elem_bytes, int nb, int64_t ld, int64_t n,

@@ -95,6 +95,14 @@ template <int LAYOUT, int V> struct Sink {
     }
 };
 
+// every blade of a one-row tile through a sink, in ascending order (the AoS sink collects 16-byte groups)
+template <int K, int LAYOUT> static __device__ __forceinline__ void put_all(Sink<LAYOUT, 1> &sink, const Tile<real, NB, 1> &t) {
+    if constexpr (K < NB) {
+        sink.template put<K>(t.v[K]);
+        put_all<K + 1>(sink, t);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ K1
 template <int LAYOUT, int OP, bool STRICT, int LIST = 0>
 __global__ void __launch_bounds__(kThreads)
@@ -1017,6 +1025,66 @@ sandwich_rows_kernel_aos_tma(const __grid_constant__ CUtensorMap map_r, const __
     }
 }
 
+// Cotangents of the per-row sandwich  y = R x ~R  (autograd of lcc.torch, /root/reference/lcc/torch/multivector.py:988-1019:
+// there the backward pass is torch autograd through two products and a reverse).  ONE kernel: R, x and the incoming
+// cotangent g in registers per row; with t = R x and y = t ~R every generated term  out[k] += s a[i] b[j]  gives its two
+// transposed terms  ga[i] += s g[k] b[j],  gb[j] += s a[i] g[k]:
+//     g_t = dy/dt^T g,  g_(~R) = dy/d(~R)^T g      (second product)
+//     g_R = dt/dR^T g_t + rev . g_(~R),  g_x = dt/dx^T g_t      (first product; ~R[j] = rev(j) R[j])
+// 3 reads + 2 writes of nb values per row (5 * nb * s bytes) instead of five product-shaped passes (15 * nb * s) plus
+// the saved intermediate of the composed form.  FMA arithmetic: gradients have no reference rounding order.
+template <int LAYOUT>
+__global__ void __launch_bounds__(kThreads)
+sandwich_rows_vjp_kernel(const real *__restrict__ r, int64_t ldr, int r_bcast, const real *__restrict__ x, int64_t ldx,
+                         const real *__restrict__ g, int64_t ldg, real *__restrict__ gx, int64_t ldgx,
+                         real *__restrict__ gr, int64_t ldgr, int64_t n, int vec_ok, const Coeffs mu) {
+    const int64_t r0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one row per thread in both layouts
+    if (r0 >= n) return;
+    Tile<real, NB, 1> R, X, G, T, GT, GR, GX;
+    if constexpr (LAYOUT == kSoA) { load_soa(R, r, ldr, r0, r_bcast != 0); load_soa(X, x, ldx, r0, false); load_soa(G, g, ldg, r0, false); }
+    else { load_aos(R, r, ldr, r0, r_bcast != 0, vec_ok != 0); load_aos(X, x, ldx, r0, false, vec_ok != 0); load_aos(G, g, ldg, r0, false, vec_ok != 0); }
+    (void)mu;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) { T.v[k][0] = real(0); GT.v[k][0] = real(0); GR.v[k][0] = real(0); GX.v[k][0] = real(0); }
+#define LCC_OUT_BEGIN(k) {
+#define LCC_OUT_END(k) }
+    // t = R x
+#define LCC_TERM(k, i, j, neg, flags)                                                                   \
+    {                                                                                                  \
+        real rv = (neg) ? -R.v[i][0] : R.v[i][0];                                                      \
+        if constexpr (kRuntimeMetric) rv = mul_rn(rv, mu.v[(i) & (j)]);                                \
+        T.v[k][0] = Arith<false>::madd(rv, X.v[j][0], T.v[k][0]);                                      \
+    }
+#include LCC_TERMS_FILE
+#undef LCC_TERM
+    // y = t ~R:  g_t[i] += s g[k] ~R[j];  g_(~R)[j] += s t[i] g[k], accumulated into g_R[j] with the reverse sign
+#define LCC_TERM(k, i, j, neg, flags)                                                                   \
+    {                                                                                                  \
+        real gv = (neg) ? -G.v[k][0] : G.v[k][0];                                                      \
+        if constexpr (kRuntimeMetric) gv = mul_rn(gv, mu.v[(i) & (j)]);                                \
+        const real gs = reverse_negative(j) ? -gv : gv;                                                \
+        GT.v[i][0] = Arith<false>::madd(gs, R.v[j][0], GT.v[i][0]);                                    \
+        GR.v[j][0] = Arith<false>::madd(gs, T.v[i][0], GR.v[j][0]);                                    \
+    }
+#include LCC_TERMS_FILE
+#undef LCC_TERM
+    // t = R x:  g_R[i] += s g_t[k] x[j];  g_x[j] += s R[i] g_t[k]
+#define LCC_TERM(k, i, j, neg, flags)                                                                   \
+    {                                                                                                  \
+        real gv = (neg) ? -GT.v[k][0] : GT.v[k][0];                                                    \
+        if constexpr (kRuntimeMetric) gv = mul_rn(gv, mu.v[(i) & (j)]);                                \
+        GR.v[i][0] = Arith<false>::madd(gv, X.v[j][0], GR.v[i][0]);                                    \
+        GX.v[j][0] = Arith<false>::madd(gv, R.v[i][0], GX.v[j][0]);                                    \
+    }
+#include LCC_TERMS_FILE
+#undef LCC_TERM
+#undef LCC_OUT_BEGIN
+#undef LCC_OUT_END
+    Sink<LAYOUT, 1> sx{gx, ldgx, r0, vec_ok != 0, {}}, sr{gr, ldgr, r0, vec_ok != 0, {}};
+    put_all<0>(sx, GX);
+    put_all<0>(sr, GR);
+}
+
 // ------------------------------------------------------------------------------------------ entry points, by part
 // One (signature, precision) is compiled as several object files so that ptxas runs in parallel
 // (_build.py writes one stub per part):
@@ -1025,7 +1093,7 @@ sandwich_rows_kernel_aos_tma(const __grid_constant__ CUtensorMap map_r, const __
 //   LCC_PART 3  sandwich kernels, direct and TMA             (LCC_PART_STRICT = 0 / 1)
 //   LCC_PART 4  fused product + batch-sum kernels and the two routers the dispatcher calls
 //   LCC_PART 5  vector-Jacobian products (direct and TMA forms)
-//   LCC_PART 6  per-row sandwich (direct and AoS-TMA forms, both rounding modes)
+//   LCC_PART 6  per-row sandwich (direct and AoS-TMA forms, both rounding modes) and its fused cotangent kernel
 cudaError_t product_direct_s0(const ProductArgs &g);
 cudaError_t product_direct_s1(const ProductArgs &g);
 cudaError_t product_tma_s0(const ProductArgs &g);  // cudaErrorNotSupported: operands do not qualify, use the direct kernels
@@ -1034,6 +1102,7 @@ cudaError_t sandwich_s0(const SandwichArgs &g);
 cudaError_t sandwich_s1(const SandwichArgs &g);
 cudaError_t product_vjp(const ProductArgs &g);      // g.list = 1 / 2
 cudaError_t sandwich_rows(const SandwichArgs &g);   // g.rotors set: one rotor per row (or one device row for all)
+cudaError_t sandwich_rows_vjp(const SandwichArgs &g);  // g.grad set as well: cotangents of x and of the rotor rows
 cudaError_t launch_product(const ProductArgs &g);
 cudaError_t launch_sandwich(const SandwichArgs &g);
 
@@ -1157,6 +1226,29 @@ cudaError_t sandwich_rows(const SandwichArgs &g) {
     if (g.layout == kSoA) return g.strict ? launch_sandwich_rows_t<kSoA, true>(g) : launch_sandwich_rows_t<kSoA, false>(g);
     return g.strict ? launch_sandwich_rows_t<kAoS, true>(g) : launch_sandwich_rows_t<kAoS, false>(g);
 }
+template <int LAYOUT> static cudaError_t launch_sandwich_rows_vjp_t(const SandwichArgs &g) {
+    if (g.n <= 0) return cudaSuccess;
+    if constexpr (NB > 16 || (NB > 8 && sizeof(real) == 8 && kRuntimeMetric)) {
+        return cudaErrorNotSupported;  // seven tiles do not fit the register file: the caller composes products
+    } else {
+        constexpr int W = 16 / (int)sizeof(real);
+        int vec_ok = 1;
+        if (LAYOUT == kAoS) {
+            auto ok = [&](const void *p, int64_t ld) { return ((uintptr_t)p % 16 == 0) && (ld % W == 0); };
+            vec_ok = ok(g.x, g.ldx) && ok(g.grad, g.ldg) && ok(g.gx, g.ldgx) && ok(g.gr, g.ldgr) && ((uintptr_t)g.rotors % 16 == 0) && (g.r_bcast || g.ldr % W == 0);
+        }
+        const int block = 64;  // 7 tiles of registers per thread: small blocks keep several resident and out of phase
+        const unsigned grid = (unsigned)((g.n + block - 1) / block);
+        sandwich_rows_vjp_kernel<LAYOUT><<<grid, block, 0, g.stream>>>(
+            (const real *)g.rotors, g.ldr, g.r_bcast ? 1 : 0, (const real *)g.x, g.ldx, (const real *)g.grad, g.ldg,
+            (real *)g.gx, g.ldgx, (real *)g.gr, g.ldgr, g.n, vec_ok, to_coeffs(g.mu, 1.0));
+        note_kernel_launch();
+        return cudaGetLastError();
+    }
+}
+cudaError_t sandwich_rows_vjp(const SandwichArgs &g) {
+    return g.layout == kSoA ? launch_sandwich_rows_vjp_t<kSoA>(g) : launch_sandwich_rows_vjp_t<kAoS>(g);
+}
 #endif  // LCC_PART == 6
 
 #if LCC_PART == 3
@@ -1213,6 +1305,7 @@ cudaError_t launch_product(const ProductArgs &g) {
     return g.strict ? product_direct_s1(g) : product_direct_s0(g);
 }
 cudaError_t launch_sandwich(const SandwichArgs &g) {
+    if (g.rotors && g.grad) return sandwich_rows_vjp(g);
     if (g.rotors) return sandwich_rows(g);
     return g.strict ? sandwich_s1(g) : sandwich_s0(g);
 }

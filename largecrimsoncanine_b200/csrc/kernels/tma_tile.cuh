@@ -104,6 +104,10 @@ bool make_aos_tensor_map(CUtensorMap *map, const void *base, int elem_bytes, int
 // Blade-major (SoA) batch: element (row r, blade k) at base[k*ld + r].  Tensor = (n rows, nb blades) with
 // the rows contiguous; box = (rows, nb), no swizzle (a thread reads consecutive rows of one blade, so
 // neighbouring threads already hit neighbouring banks).  Rows beyond n are zero-filled / clipped.
-bool make_soa_tensor_map(CUtensorMap *map, const void *base, int elem_bytes, int nb, int64_t ld, int64_t n, int rows);
+// swizzle128 (K8): box rows of exactly 128 bytes with the hardware 128-byte swizzle -- 16-byte chunk c of blade k lands at
+// chunk c ^ (k & 7) of its 128-byte line, so that accesses ACROSS blades at fixed rows spread over the banks.
+// l2_promotion: bytes the L2 fetches from DRAM per request (64 / 128 / 256; 0 = none).
+bool make_soa_tensor_map(CUtensorMap *map, const void *base, int elem_bytes, int nb, int64_t ld, int64_t n, int rows,
+                         bool swizzle128 = false, int l2_promotion = 128);
 
 }  // namespace lcc

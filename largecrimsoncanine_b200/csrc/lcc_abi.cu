@@ -507,15 +507,29 @@ static bool matrix_rep_of(const lcc_algebra *calg) {
     lcc_algebra *alg = const_cast<lcc_algebra *>(calg);
     std::lock_guard<std::mutex> lock(alg->mu_dev);
     if (alg->rep_state == 0) {
-        const MatrixRep rep = find_matrix_rep(*alg);
-        alg->rep_state = rep.ok ? 1 : 2;
-        if (rep.ok) {
+        // Equivalent representations differ in their string -> blade map; K8 wants one whose map gives its MMA fragment
+        // accesses distinct shared-memory banks (make_rep_layout).  Variant 0 is the search result itself; the others
+        // relabel it by Clifford automorphisms of the Pauli group (a few hundred cheap candidates, tried once per algebra).
+        auto install = [&](const MatrixRep &rep) {
             alg->rep_string_of.assign(rep.string_of, rep.string_of + 256);
             alg->rep_sign_of.assign(rep.sign_of, rep.sign_of + 256);
             alg->rep_blade_at.assign(256, 0);
             alg->rep_sign_at.assign(256, 0);
             for (int sidx = 0; sidx < 256; ++sidx)
                 if (rep.blade_at[sidx] >= 0) { alg->rep_blade_at[sidx] = (uint8_t)rep.blade_at[sidx]; alg->rep_sign_at[sidx] = rep.sign_of[rep.blade_at[sidx]]; }
+        };
+        alg->rep_state = 2;
+        for (int variant = 0; variant < 1 + 384 * 13; ++variant) {
+            const MatrixRep rep = find_matrix_rep(*alg, variant);
+            if (!rep.ok) { if (variant == 0) break; else continue; }
+            if (variant == 0) { install(rep); alg->rep_state = 1; }
+            MatrixRep tmp = rep;
+            uint8_t blade_at[256]; int8_t sign_at[256];
+            for (int sidx = 0; sidx < 256; ++sidx) {
+                blade_at[sidx] = tmp.blade_at[sidx] >= 0 ? (uint8_t)tmp.blade_at[sidx] : 0;
+                sign_at[sidx] = tmp.blade_at[sidx] >= 0 ? tmp.sign_of[tmp.blade_at[sidx]] : 0;
+            }
+            if (make_rep_layout(blade_at, sign_at).ok) { install(rep); break; }
         }
     }
     return alg->rep_state == 1;
@@ -717,6 +731,19 @@ int lcc_algebra_matrix_rep(const lcc_algebra *alg, uint8_t *string_of_blade, int
         if (sign_of_blade) sign_of_blade[A] = alg->rep_sign_of[A];
     }
     return 16;
+}
+
+int lcc_algebra_matrix_rep_layout(const lcc_algebra *alg, uint32_t *tables) {
+    if (!alg || !matrix_rep_of(alg)) return 0;
+    const RepLayout L = make_rep_layout(alg->rep_blade_at.data(), alg->rep_sign_at.data());
+    if (!L.ok) return 0;
+    if (tables)
+        for (int i = 0; i < 16; ++i) {
+            tables[0 * 16 + i] = L.f_lo[i];        tables[1 * 16 + i] = L.f_hi[i];
+            tables[2 * 16 + i] = L.column.fk[i];   tables[3 * 16 + i] = L.column.cw[i];   tables[4 * 16 + i] = L.column.kmap[i];
+            tables[5 * 16 + i] = L.row.fk[i];      tables[6 * 16 + i] = L.row.cw[i];      tables[7 * 16 + i] = L.row.kmap[i];
+        }
+    return 1;
 }
 
 lcc_status lcc_batch_fixed_product(const lcc_algebra *alg, int op, int side, const double *fixed_host, const lcc_view *x, const lcc_view *out,
@@ -954,6 +981,58 @@ lcc_status lcc_batch_sandwich_rows(const lcc_algebra *alg, const lcc_view *rotor
     LCC_TRY(lcc_batch_unary(alg, LCC_UN_REVERSE, 0, rotors, &rev, (void *)s));
     LCC_TRY(run_product(alg, kOpGP, rotors, x, &rx, nullptr, flags, (void *)s));
     return run_product(alg, kOpGP, &rx, &rev, out, nullptr, flags, (void *)s);
+}
+
+lcc_status lcc_batch_sandwich_rows_vjp(const lcc_algebra *alg, const lcc_view *rotors, const lcc_view *x, const lcc_view *grad_out,
+                                       const lcc_view *grad_x, const lcc_view *grad_rotors, unsigned flags, void *stream) {
+    TraceRange tr("lcc_batch_sandwich_rows_vjp");
+    LCC_TRY(check_view(alg, rotors, "rotors"));
+    LCC_TRY(check_view(alg, x, "x"));
+    LCC_TRY(check_view(alg, grad_out, "grad_out"));
+    LCC_TRY(check_view(alg, grad_x, "grad_x"));
+    LCC_TRY(check_view(alg, grad_rotors, "grad_rotors"));
+    if (rotors->n != x->n && rotors->n != 1) return fail(LCC_ERR_VALUE, "batch sizes must match or be 1 for broadcasting: %lld vs %lld", (long long)rotors->n, (long long)x->n);
+    LCC_TRY(same_kind(rotors, x, "sandwich_rows_vjp"));
+    LCC_TRY(same_kind(x, grad_out, "sandwich_rows_vjp"));
+    LCC_TRY(same_kind(x, grad_x, "sandwich_rows_vjp"));
+    LCC_TRY(same_kind(x, grad_rotors, "sandwich_rows_vjp"));
+    if (grad_out->n != x->n || grad_x->n != x->n || grad_rotors->n != x->n)
+        return fail(LCC_ERR_VALUE, "sandwich_rows_vjp: grad_out, grad_x and grad_rotors must have %lld rows", (long long)x->n);
+    if (x->n == 0) return LCC_OK;
+    cudaStream_t s;
+    LCC_TRY(resolve_stream(stream, &s));
+    // up to 16 blades: ONE kernel (product_impl.cuh, sandwich_rows_vjp_kernel): 5 * nb * s bytes per row
+    if (alg->nb <= 32 && alg->sandwich[x->dtype]) {
+        SandwichArgs g;
+        g.dtype = x->dtype; g.layout = x->layout; g.strict = false; g.n = x->n;
+        g.rotors = rotors->data; g.ldr = rotors->ld; g.r_bcast = rotors->n == 1 && x->n > 1;
+        g.x = x->data; g.ldx = x->ld;
+        g.grad = grad_out->data; g.ldg = grad_out->ld;
+        g.gx = grad_x->data; g.ldgx = grad_x->ld; g.gr = grad_rotors->data; g.ldgr = grad_rotors->ld;
+        g.mu = alg->specialised ? nullptr : alg->mu.data();
+        g.stream = s;
+        const cudaError_t e = alg->sandwich[x->dtype](g);
+        if (e != cudaErrorNotSupported) { LCC_CUDA(e); return LCC_OK; }
+    }
+    // larger algebras: the same five bilinear passes composed from the product and cotangent entry points, with
+    // t = R x recomputed (nothing was saved by the forward call) and three pool temporaries
+    const size_t es = elem_size(x->dtype);
+    auto full_bytes = [&](const lcc_view *v) { return (size_t)(v->layout == LCC_SOA ? (int64_t)alg->nb * v->ld : v->n * v->ld) * es; };
+    PoolBuffer brev, bt, bgt;
+    lcc_view rev = *rotors, t = *x, gt = *x;
+    LCC_TRY(brev.alloc(full_bytes(rotors), s));
+    LCC_TRY(bt.alloc(full_bytes(x), s));
+    LCC_TRY(bgt.alloc(full_bytes(x), s));
+    rev.data = brev.ptr; t.data = bt.ptr; gt.data = bgt.ptr;
+    void *vs = (void *)s;
+    LCC_TRY(lcc_batch_unary(alg, LCC_UN_REVERSE, 0, rotors, &rev, vs));
+    LCC_TRY(run_product(alg, kOpGP, rotors, x, &t, nullptr, flags & ~LCC_FLAG_STRICT_FP, vs));         // t = R x
+    LCC_TRY(lcc_batch_product_vjp(alg, LCC_OP_GP, 0, grad_out, &rev, &gt, flags, vs));                  // g_t = d(t ~R)/dt ^T g
+    LCC_TRY(lcc_batch_product_vjp(alg, LCC_OP_GP, 1, grad_out, &t, grad_rotors, flags, vs));            // g_(~R), held in grad_rotors
+    LCC_TRY(lcc_batch_unary(alg, LCC_UN_REVERSE, 0, grad_rotors, grad_rotors, vs));                     // rev . g_(~R)
+    LCC_TRY(lcc_batch_product_vjp(alg, LCC_OP_GP, 0, &gt, x, &t, flags, vs));                           // d(R x)/dR ^T g_t (t is free again)
+    LCC_TRY(lcc_batch_elementwise(alg, LCC_EW_ADD, grad_rotors, &t, grad_rotors, vs));
+    return lcc_batch_product_vjp(alg, LCC_OP_GP, 1, &gt, rotors, grad_x, flags, vs);                    // d(R x)/dx ^T g_t
 }
 
 lcc_status lcc_batch_unary(const lcc_algebra *alg, int op, int arg, const lcc_view *x, const lcc_view *out, void *stream) {

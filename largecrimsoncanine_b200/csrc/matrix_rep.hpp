@@ -74,7 +74,33 @@ inline bool search(int p, int q, int k, std::vector<unsigned> &gens, std::vector
 // Representation of `alg` by real 16 x 16 signed permutation matrices, or ok == false when none exists in that size
 // (degenerate metrics, fewer than 7 dimensions -- the dense GEMM is already HBM-bound there -- and the signatures whose
 // algebra is quaternionic or a direct sum, e.g. Cl(7,1) ~ M_8(H)).
-inline MatrixRep find_matrix_rep(const lcc_algebra &alg) {
+//
+// `variant` > 0 relabels the strings of the generators by a real Clifford automorphism of the Pauli group (a qubit
+// permutation, X <-> Z swaps on a subset of the qubits, optionally a CNOT): commutation relations and squares are
+// preserved, so the images still generate a faithful representation -- equivalent as a representation, but with a different
+// string -> blade map.  K8 needs one whose map gives it conflict-free MMA fragment accesses (make_rep_layout below).
+inline unsigned relabel_string(unsigned s, int variant) {
+    if (variant <= 0) return s;
+    const int v = variant - 1;
+    const int perm_id = v % 24, hmask = (v / 24) % 16, cnot = (v / 384) % 13;  // cnot: 0 none, else control/target pair
+    static const int perms[24][4] = {{0,1,2,3},{0,1,3,2},{0,2,1,3},{0,2,3,1},{0,3,1,2},{0,3,2,1},{1,0,2,3},{1,0,3,2},{1,2,0,3},{1,2,3,0},{1,3,0,2},{1,3,2,0},
+                                     {2,0,1,3},{2,0,3,1},{2,1,0,3},{2,1,3,0},{2,3,0,1},{2,3,1,0},{3,0,1,2},{3,0,2,1},{3,1,0,2},{3,1,2,0},{3,2,0,1},{3,2,1,0}};
+    unsigned a = s >> 4, b = s & 15, na = 0, nb = 0;
+    for (int qb = 0; qb < 4; ++qb) {
+        unsigned aq = (a >> qb) & 1, bq = (b >> qb) & 1;
+        if ((hmask >> qb) & 1) { const unsigned t = aq; aq = bq; bq = t; }
+        na |= aq << perms[perm_id][qb];
+        nb |= bq << perms[perm_id][qb];
+    }
+    if (cnot) {
+        const int c = (cnot - 1) / 3, t0 = (cnot - 1) % 3, t = t0 >= c ? t0 + 1 : t0;  // 12 ordered pairs
+        na ^= ((na >> c) & 1) << t;   // a_t ^= a_c
+        nb ^= ((nb >> t) & 1) << c;   // b_c ^= b_t
+    }
+    return (na << 4) | nb;
+}
+
+inline MatrixRep find_matrix_rep(const lcc_algebra &alg, int variant = 0) {
     using namespace matrix_rep_detail;
     MatrixRep rep;
     for (int i = 0; i < 256; ++i) { rep.string_of[i] = 0; rep.sign_of[i] = 0; rep.blade_at[i] = -1; }
@@ -86,6 +112,7 @@ inline MatrixRep find_matrix_rep(const lcc_algebra &alg) {
     if (alg.dim == 8 ? !(cls == 0 || cls == 2) : !(cls == 1 || cls == 3 || cls == 7)) return rep;
     std::vector<unsigned> gens, echelon;
     if (!search(alg.p, alg.q, 0, gens, echelon)) return rep;
+    for (unsigned &g : gens) g = relabel_string(g, variant);
     const int nb = alg.nb;
     for (int A = 0; A < nb; ++A) {
         PS acc{0, 0, 1};
@@ -122,6 +149,113 @@ inline void rep_matrix(const MatrixRep &rep, int nb, const double *coeffs, doubl
             out[(j ^ a) * 16 + j] += matrix_rep_detail::par(b & j) ? -v : v;
         }
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Shared-memory layout of K8 (kernels/matrix_rep_kernel.cu), computed on the host once per launch.
+//
+// The string -> blade map is LINEAR over F_2 (the string of a product of blades is the XOR of their strings), so
+// blade(a << 4 | b) = lin_hi(a) ^ lin_lo(b).  A 32 KB unit of the kernel holds 256 slots of 128 bytes (slot = blade, as the
+// TMA engine delivers them, hardware 128-byte swizzle: 16-byte chunk c of slot s sits at chunk c ^ (s & 7)).  Matrix entry
+// (f, s) of rho(x) lives IN the slot of the coefficient it is built from first, blade(f ^ s, s); then
+//   * the Walsh-Hadamard transforms (string row a fixed) touch the 16 slots blade(a, .) -- the same 16 on the way in and
+//     on the way out, so a thread transforms its rows in place without any barrier;
+//   * a product with a fixed factor from the LEFT contracts the first index at fixed second index w (column pass): entry
+//     (k, w) sits in slot Lambda(k) ^ Gamma(w) with Lambda(k) = lin_hi(k), Gamma(w) = lin_hi(w) ^ lin_lo(w);
+//   * a product from the RIGHT contracts the second index at fixed first index w (row pass): entry (w, k) sits in slot
+//     Lambda(k) ^ Gamma(w) with Lambda(k) = lin_hi(k) ^ lin_lo(k), Gamma(w) = lin_hi(w).
+// Byte offset of slot s with the swizzle pre-applied: F(s) = s << 7 | (s & 7) << 4 (linear too); the byte offset of row
+// bytes r inside the slot is F(s) ^ r.  An MMA B-fragment load reads four slots (the k-lanes of a quad) at eight rows:
+// conflict free iff those four slots differ in blade bits 1-2, so the contraction index is laid onto the MMA's physical k
+// (and m) positions through a basis v0..v3 of F_2^4 whose first two vectors have independent (Lambda >> 1) & 3 and whose
+// first has blade bit 2 set (f64 D-fragment stores); pick_basis() finds one or reports that this representation has none.
+struct RepPass {
+    uint32_t fk[16];   // F(Lambda(kmap[physical index]))
+    uint32_t cw[16];   // F(Gamma(w))
+    uint8_t kmap[16];  // physical MMA index (k or m) -> logical matrix index
+};
+struct RepLayout {
+    bool ok = false;
+    uint8_t lin[256];     // string -> blade, extended linearly to strings no blade maps to (128-blade algebras: blades 128..255)
+    uint32_t f_lo[16];    // F(lin_lo(b))
+    uint32_t f_hi[16];    // F(lin_hi(a))
+    RepPass column, row;
+};
+
+namespace matrix_rep_detail {
+inline uint32_t slot_offset(unsigned s) { return (s << 7) | ((s & 7u) << 4); }
+inline bool pick_basis(const unsigned lam[16], unsigned v[4]) {
+    auto phi = [&](unsigned x) { return (lam[x] >> 1) & 3u; };
+    for (unsigned v0 = 1; v0 < 16; ++v0) {
+        if (!((lam[v0] >> 2) & 1u)) continue;
+        for (unsigned v1 = 1; v1 < 16; ++v1) {
+            if (v1 == v0 || phi(v1) == 0 || phi(v1) == phi(v0)) continue;
+            for (unsigned v2 = 1; v2 < 16; ++v2) {
+                if (v2 == v0 || v2 == v1 || v2 == (v0 ^ v1)) continue;
+                for (unsigned v3 = 1; v3 < 16; ++v3) {
+                    bool in_span = false;
+                    for (unsigned m = 0; m < 8; ++m)
+                        if (v3 == (((m & 1) ? v0 : 0) ^ ((m & 2) ? v1 : 0) ^ ((m & 4) ? v2 : 0))) in_span = true;
+                    if (in_span) continue;
+                    v[0] = v0; v[1] = v1; v[2] = v2; v[3] = v3;
+                    return true;
+                }
+            }
+        }
+    }
+    return false;
+}
+inline bool make_pass(const unsigned lam[16], const unsigned gam[16], RepPass &p) {
+    unsigned v[4];
+    if (!pick_basis(lam, v)) return false;
+    for (unsigned i = 0; i < 16; ++i) {
+        unsigned k = 0;
+        for (int bit = 0; bit < 4; ++bit) if ((i >> bit) & 1) k ^= v[bit];
+        p.kmap[i] = (uint8_t)k;
+        p.fk[i] = slot_offset(lam[k]);
+        p.cw[i] = slot_offset(gam[i]);
+    }
+    return true;
+}
+}  // namespace matrix_rep_detail
+
+// blade_at / sign_at: string -> blade / sign (0 where no blade maps to the string)
+inline RepLayout make_rep_layout(const uint8_t *blade_at, const int8_t *sign_at) {
+    using namespace matrix_rep_detail;
+    RepLayout L;
+    // linear extension of string -> blade to all 256 strings: close the (string, blade) pairs of the basis blades under
+    // XOR; a 128-blade algebra spans only half the strings, the other half gets blades 128..255 (slots that exist in a
+    // unit but hold no data: such strings are masked out by sign == 0)
+    int lin[256], have[256];
+    for (int i = 0; i < 256; ++i) { lin[i] = 0; have[i] = 0; }
+    have[0] = 1;
+    int count = 1, next_blade = 1;
+    auto add = [&](int str, int blade) {
+        if (have[str]) return;
+        for (int t = 0; t < 256; ++t)
+            if (have[t] == 1) { lin[t ^ str] = lin[t] ^ blade; have[t ^ str] = 2; }
+        for (int t = 0; t < 256; ++t) if (have[t] == 2) have[t] = 1;
+        count *= 2;
+    };
+    for (int str = 1; str < 256; ++str)
+        if (sign_at[str] != 0 && (blade_at[str] & (blade_at[str] - 1)) == 0) { add(str, blade_at[str]); if (blade_at[str] >= next_blade) next_blade = blade_at[str] << 1; }
+    for (int str = 1; str < 256 && count < 256; ++str)
+        if (!have[str]) { add(str, next_blade); next_blade <<= 1; }
+    for (int str = 0; str < 256; ++str) {
+        if (sign_at[str] != 0 && lin[str] != blade_at[str]) return L;  // cannot happen for a homomorphism
+        if (lin[str] < 0 || lin[str] > 255) return L;
+        L.lin[str] = (uint8_t)lin[str];
+    }
+    unsigned lam_c[16], gam_c[16], lam_r[16], gam_r[16];
+    for (unsigned i = 0; i < 16; ++i) {
+        L.f_lo[i] = slot_offset(L.lin[i]);
+        L.f_hi[i] = slot_offset(L.lin[i << 4]);
+        lam_c[i] = L.lin[i << 4];            gam_c[i] = L.lin[(i << 4) | i];
+        lam_r[i] = L.lin[(i << 4) | i];      gam_r[i] = L.lin[i << 4];
+    }
+    L.ok = make_pass(lam_c, gam_c, L.column) && make_pass(lam_r, gam_r, L.row);
+    return L;
 }
 
 }  // namespace lcc

@@ -224,6 +224,43 @@ class _SandwichFixed(torch.autograd.Function):
         return _product_vjp(ctx.sig, cabi.LCC_OP_GP, 1, g_rx, r), None, None
 
 
+class _SandwichRows(torch.autograd.Function):
+    """out = R x ~R with gradients to x and / or R (one rotor per row, or one rotor for all rows): forward is the fused
+    per-row kernel (K2r), backward ONE fused cotangent kernel (lcc_batch_sandwich_rows_vjp: R, x and the incoming
+    cotangent in registers, 5 * num_blades values of traffic per row) instead of autograd through two products, a
+    reverse and a saved intermediate (reference: lcc/torch/multivector.py:988-1019)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, r: Tensor, sig):
+        ctx.sig, ctx.r_dtype = sig, r.dtype
+        x = _prep(x)
+        r = _prep(r if r.dtype == x.dtype else r.to(x.dtype))
+        ctx.save_for_backward(x, r)
+        out = torch.empty_like(x)
+        if x.shape[0]:
+            with torch.cuda.device(x.device):
+                cabi.check(cabi.lib().lcc_batch_sandwich_rows(_handle(sig).h, C.byref(_view(r)), C.byref(_view(x)),
+                                                              C.byref(_view(out)), _flags(), _stream()))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        x, r = ctx.saved_tensors
+        grad_out = _prep(grad_out)
+        gx, gr = torch.empty_like(x), torch.empty_like(x)
+        if x.shape[0]:
+            with torch.cuda.device(x.device):
+                cabi.check(cabi.lib().lcc_batch_sandwich_rows_vjp(_handle(ctx.sig).h, C.byref(_view(r)), C.byref(_view(x)), C.byref(_view(grad_out)),
+                                                                  C.byref(_view(gx)), C.byref(_view(gr)), _flags(), _stream()))
+        else:
+            gr = torch.zeros_like(r)
+        if r.shape[0] == 1 and gr.shape[0] != 1:
+            gr = gr.sum(dim=0, keepdim=True)
+        if gr.dtype != ctx.r_dtype:
+            gr = gr.to(ctx.r_dtype)
+        return (gx if ctx.needs_input_grad[0] else None), (gr if ctx.needs_input_grad[1] else None), None
+
+
 class TorchAlgebra:
     """An algebra's Cayley tables as tensors plus the handle of the native engine.
 
@@ -412,8 +449,10 @@ class TorchMultivector:
 
     def sandwich(self, rotor: "TorchMultivector") -> "TorchMultivector":
         """rotor * self * ~rotor (reference: lcc/torch/multivector.py:635-659, 988-1019).
-        One rotor and no gradients -> the fused fixed-versor kernel (K2, one pass over HBM);
-        otherwise two differentiable products, exactly the reference's composition."""
+        One rotor and no gradients -> the fused fixed-versor kernel (K2, one pass over HBM); gradients to x only -> the
+        same forward with two broadcast cotangent passes; gradients to the rotor(s) -> the fused per-row kernel with ONE
+        fused cotangent kernel; what is left (a one-row x against many rotors) composes two differentiable products as
+        the reference does."""
         needs_grad = torch.is_grad_enabled() and (self.coeffs.requires_grad or rotor.coeffs.requires_grad)
         if rotor.batch_size == 1 and not needs_grad:
             x = _prep(self.coeffs)
@@ -440,6 +479,9 @@ class TorchMultivector:
                 cabi.check(cabi.lib().lcc_batch_sandwich_rows(_handle(self.algebra.signature).h, C.byref(_view(r)), C.byref(_view(x)),
                                                               C.byref(_view(out)), _flags(), _stream()))
             return TorchMultivector(self.algebra, out)
+        if needs_grad and self.batch_size > 0 and rotor.batch_size in (1, self.batch_size):
+            # gradients to the rotor(s) too: fused forward, ONE fused cotangent kernel backward
+            return TorchMultivector(self.algebra, _SandwichRows.apply(self.coeffs, rotor.coeffs, self.algebra.signature))
         return rotor.geometric_product(self).geometric_product(rotor.reverse())
 
     apply = sandwich

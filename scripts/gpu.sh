@@ -77,6 +77,32 @@ stage_ncu() {            # one --set full capture: NCU_KERNEL regex, NCU_CMD com
   timeout 900 $NCU --set full --import-source on -k "regex:${NCU_KERNEL}" -c ${NCU_COUNT:-1} -s ${NCU_SKIP:-3} -o gpurun_out/${NCU_OUT} -f ${NCU_CMD} > gpurun_out/${NCU_OUT}.log 2>&1; echo "ncu rc=$?"; tail -3 gpurun_out/${NCU_OUT}.log
 }
 stage_fuzz() { for seed in ${SEEDS:-21 22}; do FUZZ_SEED=$seed timeout 120 $PY tests/tools/fuzz_parity.py 2000 > gpurun_out/fuzz_$seed.log 2>&1; echo "seed $seed rc=$?"; tail -2 gpurun_out/fuzz_$seed.log | cut -c1-300; done; }
+stage_k8() {             # K8 (matrix-representation kernel): parity tests, then f32 / f64 at 2^24 rows per group count and debug mode
+  timeout 600 $PY -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "block_diagonalised or tensor_cores or reference_layout" 2>&1 | tail -8 | tee gpurun_out/pytest_k8.log
+  for g in ${K8_GROUPS:-3 2}; do for wl in cl8_fixed_gp_rep cl8_fixed_gp_f64; do
+    LCC_K8_GROUPS=$g timeout 300 $PY bench.py --workload $wl --no-e2e --no-cpu --no-secondary --steps 10 > gpurun_out/k8_${wl}_g$g.json 2> gpurun_out/k8_${wl}_g$g.err
+    echo "$wl groups=$g rc=$?"; summ gpurun_out/k8_${wl}_g$g.json
+  done; done
+  for dbg in ${K8_DEBUG:-1 2}; do for wl in cl8_fixed_gp_rep cl8_fixed_gp_f64; do
+    LCC_K8_DEBUG=$dbg timeout 300 $PY bench.py --workload $wl --no-e2e --no-cpu --no-secondary --no-parity --steps 10 > gpurun_out/k8_${wl}_dbg$dbg.json 2> gpurun_out/k8_${wl}_dbg$dbg.err
+    echo "$wl debug=$dbg rc=$?"; summ gpurun_out/k8_${wl}_dbg$dbg.json
+  done; done
+}
+stage_k8_mem() {         # K8 memory pipeline experiments: L2 promotion x unit order (pass-through and full), swizzle off (pass-through)
+  run1() { # name, env..., workload, extra flags
+    local name=$1; shift; local wl=$1; shift
+    env "$@" timeout 300 $PY bench.py --workload $wl --no-e2e --no-cpu --no-secondary --steps 10 ${NOPAR} > gpurun_out/k8m_${wl}_$name.json 2> gpurun_out/k8m_${wl}_$name.err
+    echo "$wl $name rc=$?"; summ gpurun_out/k8m_${wl}_$name.json
+  }
+  for wl in cl8_fixed_gp_rep cl8_fixed_gp_f64; do
+    for promo in 128 256; do for order in 0 1; do
+      NOPAR=--no-parity run1 pass_p${promo}_o${order} $wl LCC_K8_DEBUG=1 LCC_K8_L2PROMO=$promo LCC_K8_ORDER=$order
+    done; done
+    NOPAR=--no-parity run1 pass_noswz_p256_o1 $wl LCC_K8_DEBUG=1 LCC_K8_SWIZZLE=0
+    NOPAR= run1 full_default $wl LCC_K8_GROUPS=3
+    NOPAR= run1 full_default_g2 $wl LCC_K8_GROUPS=2
+  done
+}
 stage_info() { nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit,memory.total --format=csv; nproc; free -g | head -2; nvidia-smi topo -m 2>/dev/null | head -12; }
 
 for st in "$@"; do

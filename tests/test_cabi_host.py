@@ -137,6 +137,115 @@ def test_matrix_representation_is_an_algebra_homomorphism(sig, has_rep):
         assert np.array_equal(mat(A) @ mat(B), table[A, B] * mat(A ^ B)), (A, B)
 
 
+def _rep_matrix(strings, signs, coeffs):
+    """rho(M) from coefficients (csrc/matrix_rep.hpp, rep_matrix)."""
+    m = np.zeros((16, 16))
+    j = np.arange(16)
+    for A, c in enumerate(coeffs):
+        x, z = int(strings[A]) >> 4, int(strings[A]) & 15
+        m[j ^ x, j] += c * signs[A] * np.array([(-1.0) ** bin(z & int(t)).count("1") for t in j])
+    return m
+
+
+def _wht16(v):
+    v = np.array(v, dtype=np.float64)
+    h = 1
+    while h < 16:
+        for i in range(16):
+            if not i & h:
+                v[i], v[i | h] = v[i] + v[i | h], v[i] - v[i | h]
+        h <<= 1
+    return v
+
+
+@pytest.mark.parametrize("sig", [(8, 0, 0), (4, 4, 0), (5, 3, 0), (0, 8, 0), (1, 7, 0), (7, 0, 0), (4, 3, 0), (0, 7, 0), (3, 4, 0)])
+def test_k8_shared_memory_layout(sig):
+    """K8 v7 (kernels/matrix_rep_kernel.cu) never moves a value to another slot: matrix entry (f, s) lives in the slot of the
+    coefficient with string (f ^ s, s), the Walsh-Hadamard passes and both GEMM passes work in place, and every address is
+    F(slot) ^ row bytes from the host tables of csrc/matrix_rep.hpp (RepLayout).  This replays the kernel's address
+    arithmetic on the host for one row -- stage 1, column pass and / or row pass, stage 3 -- against the algebra's own
+    Cayley table for the left product, the right product and the sandwich, and checks that every warp-wide fragment
+    access the kernel makes touches each bank once (the property the layout's basis is chosen for)."""
+    L = cabi.lib()
+    a = cabi.Algebra(*sig)
+    nb = a.num_blades
+    strings, signs = (C.c_uint8 * nb)(), (C.c_int8 * nb)()
+    assert L.lcc_algebra_matrix_rep(a.h, strings, signs) == 16
+    strings, signs = np.array(strings[:]), np.array(signs[:], dtype=np.float64)
+    tables = (C.c_uint32 * 128)()
+    assert L.lcc_algebra_matrix_rep_layout(a.h, tables) == 1
+    t = np.array(tables[:], dtype=np.int64).reshape(8, 16)
+    f_lo, f_hi = t[0], t[1]
+    passes = {"column": (t[2], t[3], t[4]), "row": (t[5], t[6], t[7])}
+    sign_at = np.zeros(256)
+    for A in range(nb):
+        sign_at[strings[A]] = signs[A]
+    # every offset is a swizzle-consistent slot offset: F(s) = s << 7 | (s & 7) << 4
+    for off in list(f_lo) + list(f_hi) + [o for p in passes.values() for o in list(p[0]) + list(p[1])]:
+        assert off == ((off >> 7) << 7 | ((off >> 7) & 7) << 4)
+    # the slots of string row a are the blades of its strings (the TMA engine delivers slot = blade)
+    for A in range(nb):
+        sa, sb = int(strings[A]) >> 4, int(strings[A]) & 15
+        assert (f_hi[sa] ^ f_lo[sb]) >> 7 == A
+    table = a.cayley_signs().reshape(nb, nb).astype(np.float64)
+    rng = np.random.default_rng(sum(sig) * 7 + sig[1])
+    x, m, r = rng.standard_normal(nb), rng.standard_normal(nb), rng.standard_normal(nb)
+    idx = np.arange(nb)
+
+    def gp(u, v):
+        out = np.zeros(nb)
+        for A in range(nb):
+            np.add.at(out, A ^ idx, u[A] * table[A] * v)
+        return out
+
+    def run(plan):
+        slots = np.full(256, np.nan)
+        slots[:nb] = x
+        for sa in range(16):  # stage 1
+            where = [(f_hi[sa] ^ f_lo[b]) >> 7 for b in range(16)]
+            v = [slots[where[b]] * sign_at[sa << 4 | b] if sign_at[sa << 4 | b] else 0.0 for b in range(16)]
+            slots[where] = _wht16(v)
+        for kind, fac in plan:  # stage 2: D[o] = sum_k fac[o][k] Z[k] in physical order
+            fk, cw, kmap = passes[kind]
+            phys = fac[np.ix_(kmap, kmap)]
+            for w in range(16):
+                where = [(fk[i] ^ cw[w]) >> 7 for i in range(16)]
+                slots[where] = phys @ slots[where]
+        for sa in range(16):  # stage 3
+            where = [(f_hi[sa] ^ f_lo[b]) >> 7 for b in range(16)]
+            v = _wht16(slots[where])
+            slots[where] = [v[b] * sign_at[sa << 4 | b] for b in range(16)]
+        return slots[:nb]
+
+    rho_m = _rep_matrix(strings, signs, m)
+    assert np.allclose(run([("column", rho_m / 16)]), gp(m, x), rtol=0, atol=1e-11)
+    assert np.allclose(run([("row", rho_m.T / 16)]), gp(x, m), rtol=0, atol=1e-11)
+    rev = np.array([1.0 if (bin(A).count("1") % 4) < 2 else -1.0 for A in range(nb)])
+    rho_r, rho_rr = _rep_matrix(strings, signs, r), _rep_matrix(strings, signs, r * rev)
+    assert np.allclose(run([("column", rho_r / 16), ("row", rho_rr.T)]), gp(gp(r, x), r * rev), rtol=0, atol=1e-9)
+    # bank checks: lane = 4 g + t
+    for fk, cw, _ in passes.values():
+        for w in range(16):
+            for q in range(4):  # f32, m16n8k8: B loads (32 lanes x 4 bytes), D stores (half-warps x 8 bytes)
+                for ks in range(2):
+                    for h in range(2):
+                        banks = {((fk[8 * ks + 4 * h + tt] ^ (g << 2) ^ cw[w] ^ (q << 5)) >> 2) & 31 for g in range(8) for tt in range(4)}
+                        assert len(banks) == 32
+                for mb in range(2):
+                    for half in range(2):
+                        banks = {((fk[g + 8 * mb] ^ (tt << 3) ^ cw[w] ^ (q << 5)) >> 3) & 15 for g in range(4 * half, 4 * half + 4) for tt in range(4)}
+                        assert len(banks) == 16
+            for q in range(2):  # f64, m8n8k4: B loads (half-warps x 8 bytes), D stores (quarter-warps x 16 bytes)
+                for ks in range(4):
+                    for half in range(2):
+                        banks = {((fk[4 * ks + tt] ^ (g << 3) ^ cw[w] ^ (q << 6)) >> 3) & 15 for g in range(4 * half, 4 * half + 4) for tt in range(4)}
+                        assert len(banks) == 16
+                for mb in range(2):
+                    for quarter in range(4):
+                        banks = {((fk[g + 8 * mb] ^ (tt << 4) ^ cw[w] ^ (q << 6)) >> 4) & 7 for g in range(2 * quarter, 2 * quarter + 2) for tt in range(4)}
+                        assert len(banks) == 8
+
+
 def test_host_side_errors():
     L = cabi.lib()
     h = C.c_void_p()

@@ -142,8 +142,9 @@ def test_fixed_rotor_sandwich_gradient_matches_the_composed_products(lt, sig, dt
         out = lt.TorchMultivector(alg, xa).sandwich(R)
         (out.coeffs * cot).sum().backward()
         xb = x.clone().requires_grad_(True)
-        rb = r.clone().requires_grad_(True)  # a rotor that needs a gradient takes the composed path
-        ref = lt.TorchMultivector(alg, xb).sandwich(lt.TorchMultivector(alg, rb))
+        rb = r.clone().requires_grad_(True)
+        Rb = lt.TorchMultivector(alg, rb)  # the reference's composition, differentiated by autograd
+        ref = Rb.geometric_product(lt.TorchMultivector(alg, xb)).geometric_product(Rb.reverse())
         (ref.coeffs * cot).sum().backward()
         scale = float(ref.coeffs.abs().max())
         assert float((out.coeffs - ref.coeffs).abs().max()) <= tol * scale
@@ -152,9 +153,43 @@ def test_fixed_rotor_sandwich_gradient_matches_the_composed_products(lt, sig, dt
         torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("sig,dt", [((3, 0, 1), torch.float64), ((3, 0, 1), torch.float32), ((3, 0, 0), torch.float64), ((1, 3, 0), torch.float64),
+                                    ((2, 0, 1), torch.float32), ((2, 1, 1), torch.float64), ((4, 1, 0), torch.float64)])
+@pytest.mark.parametrize("per_row", [True, False])
+def test_fused_sandwich_cotangents_match_autograd_of_the_composed_products(lt, sig, dt, per_row):
+    """Gradients to the rotor(s): forward = the fused per-row sandwich, backward = lcc_batch_sandwich_rows_vjp (ONE kernel up
+    to 16 blades -- specialised and run-time-metric signatures; the composed five passes behind the same entry point for
+    Cl(2,1,1) in f64 and for 32 blades), against torch autograd through gp(gp(R, x), ~R)
+    (/root/reference/lcc/torch/multivector.py:988-1019) for a random cotangent, at a size with a ragged last block."""
+    alg = lt.TorchAlgebra(sig, device="cuda")
+    nb = alg.num_blades
+    g = torch.Generator().manual_seed(17 + nb)
+    n = 4099
+    x = torch.randn(n, nb, generator=g, dtype=dt).cuda()
+    r = torch.randn(n if per_row else 1, nb, generator=g, dtype=dt).cuda()
+    cot = torch.randn(n, nb, generator=g, dtype=dt).cuda()
+    tol = 1e-11 if dt == torch.float64 else 2e-4
+    xa, ra = x.clone().requires_grad_(True), r.clone().requires_grad_(True)
+    out = lt.TorchMultivector(alg, xa).sandwich(lt.TorchMultivector(alg, ra))
+    (out.coeffs * cot).sum().backward()
+    xb, rb = x.clone().requires_grad_(True), r.clone().requires_grad_(True)
+    Rb = lt.TorchMultivector(alg, rb)
+    ref = Rb.geometric_product(lt.TorchMultivector(alg, xb)).geometric_product(Rb.reverse())
+    (ref.coeffs * cot).sum().backward()
+    assert float((out.coeffs - ref.coeffs).abs().max()) <= tol * float(ref.coeffs.abs().max())
+    assert xa.grad.shape == x.shape and ra.grad.shape == r.shape
+    assert float((xa.grad - xb.grad).abs().max()) <= tol * float(xb.grad.abs().max())
+    assert float((ra.grad - rb.grad).abs().max()) <= (tol if per_row else 20 * tol) * float(rb.grad.abs().max())
+    # only the rotor needs a gradient
+    rc = r.clone().requires_grad_(True)
+    out = lt.TorchMultivector(alg, x).sandwich(lt.TorchMultivector(alg, rc))
+    (out.coeffs * cot).sum().backward()
+    assert float((rc.grad - rb.grad).abs().max()) <= (tol if per_row else 20 * tol) * float(rb.grad.abs().max())
+
+
 def test_sandwich_with_a_batch_of_rotors(lt):
-    """One rotor per row, no gradients: the C-ABI per-row sandwich on the borrowed tensors; with gradients: the
-    reference's composition of two differentiable products.  Both agree with the oracle."""
+    """One rotor per row, no gradients: the C-ABI per-row sandwich on the borrowed tensors; with gradients: the same forward
+    kernel inside an autograd function.  Both agree with the oracle."""
     alg = lt.TorchAlgebra.pga(3, device="cuda")
     o = oracle.OracleAlgebra(3, 0, 1)
     g = torch.Generator().manual_seed(13)
