@@ -333,8 +333,8 @@ def setup_workload(ctx, wl, n, layout="soa", collective=True, ld_pad=0):
     alg = ctx.alg(sig)
     nb = alg.num_blades
     aos_layout = layout == "aos"
-    if aos_layout and wl not in ("pga_sandwich", "pga_sandwich_dense16", "cga_gp", "r3_gp", "cga_gp_outer"):
-        raise SystemExit("--layout aos is available for pga_sandwich, cga_gp, cga_gp_outer and r3_gp")
+    if aos_layout and wl not in ("pga_sandwich", "pga_sandwich_dense16", "cga_gp", "r3_gp", "cga_gp_outer", "cl8_fixed_gp_rep", "cl8_fixed_gp_f64"):
+        raise SystemExit("--layout aos is available for pga_sandwich, cga_gp, cga_gp_outer, r3_gp and the K8 workloads cl8_fixed_gp_rep / cl8_fixed_gp_f64")
 
     def soa(t):  # torch (nb, n) tensor == engine-native SoA view with ld = n
         if aos_layout:  # torch (n, nb) tensor == the reference's row-major layout (src/batch.rs:41-47)
@@ -470,10 +470,14 @@ def setup_workload(ctx, wl, n, layout="soa", collective=True, ld_pad=0):
             scale = np.abs(mag).max() / np.maximum(mag, 1e-300)  # compare on the scale of the summed magnitudes
             return finish(chk.cpu().numpy() * scale, want * scale, m)
     elif wl in CL8_WORKLOADS:
-        b = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
+        # blade-major (nb, n) or, with --layout aos, the reference's (n, nb) rows: K8 then works on units of whole rows
+        b = torch.randn((n, nb) if aos_layout else (nb, n), device=dev, dtype=tdt, generator=gen)
         a = torch.randn((nb, 4), device=dev, dtype=tdt, generator=gen)  # the fixed operand: one-row SoA view, ld = 4
         out = torch.empty_like(b)
-        va, vb, vo = cabi.view(a.data_ptr(), 1, 4, code, cabi.LCC_SOA), soa(b), soa(out)
+        if aos_layout:
+            vb, vo = (cabi.view(t.data_ptr(), n, nb, code, cabi.LCC_AOS) for t in (b, out))
+        else:
+            vb, vo = soa(b), soa(out)
         fixed = a[:, 0].to(torch.float64).cpu().numpy().copy()  # the fixed operand, known on the host (as in MultivectorBatch.from_numpy(1 x nb))
         fptr = fixed.ctypes.data_as(C.POINTER(C.c_double))
         keep.update(a=a, b=b, out=out, fixed=fixed)
@@ -488,9 +492,9 @@ def setup_workload(ctx, wl, n, layout="soa", collective=True, ld_pad=0):
 
         def parity():
             sub = idx[::64]
-            ys = b[:, sub].T.contiguous().cpu().numpy().astype(np.float64)
+            ys = (b[sub] if aos_layout else b[:, sub].T).contiguous().cpu().numpy().astype(np.float64)
             want = o.geometric_product(a[:, 0].cpu().numpy().astype(np.float64)[None, :], ys)
-            return finish(out[:, sub].T.contiguous().cpu().numpy(), want, sub.numel())
+            return finish((out[sub] if aos_layout else out[:, sub].T).contiguous().cpu().numpy(), want, sub.numel())
     elif wl == "sta_grade_inner_sum":
         a = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)
         b = torch.randn((nb, n), device=dev, dtype=tdt, generator=gen)

@@ -147,6 +147,12 @@ LCC_API int lcc_algebra_matrix_rep(const lcc_algebra *alg, uint8_t *string_of_bl
  * physical positions, slot offsets Gamma(w) of the free index, and the physical -> logical index map.  Returns 1, or 0
  * when the algebra has no representation / no conflict-free layout (K8 is then not used).  tables may be NULL. */
 LCC_API int lcc_algebra_matrix_rep_layout(const lcc_algebra *alg, uint32_t *tables);
+/* The same for K8's units of whole reference-layout rows (RepLayoutAos; element (row r, blade A) of a unit at G(A) ^ R(r)):
+ * elem_bytes 4 or 8; tables receives 13 x 16 words: G(blade of string b), G(blade of string row amap[i] << 4), amap, then per
+ * pass (column, row): G of the contraction index at the MMA's k positions, G of the output index at its m positions,
+ * G(Gamma(w)), and the two physical -> logical maps.  Returns 1, or 0 when there is none (reference-layout batches are then
+ * transposed through temporaries).  tables may be NULL. */
+LCC_API int lcc_algebra_matrix_rep_layout_aos(const lcc_algebra *alg, int elem_bytes, uint32_t *tables);
 
 /* ---------------------------------------------------------------- device memory (stream-ordered pool) */
 

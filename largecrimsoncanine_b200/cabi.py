@@ -73,6 +73,7 @@ def lib():
         "lcc_algebra_is_specialised": (i32, [vp]),
         "lcc_algebra_matrix_rep": (i32, [vp, C.POINTER(C.c_uint8), C.POINTER(C.c_int8)]),
         "lcc_algebra_matrix_rep_layout": (i32, [vp, C.POINTER(C.c_uint32)]),
+        "lcc_algebra_matrix_rep_layout_aos": (i32, [vp, i32, C.POINTER(C.c_uint32)]),
         "lcc_reverse_sign": (i32, [i32]),
         "lcc_grade_involution_sign": (i32, [i32]),
         "lcc_clifford_conjugate_sign": (i32, [i32]),

@@ -50,8 +50,10 @@ template <typename T> struct RepParams {
     T factor[2][256];     // per pass: the fixed 16 x 16 factor in MMA "A" orientation, PHYSICAL order [m * 16 + k]
     uint32_t f_lo[16];    // F(blade of string b)        F(s) = s << 7 | (s & 7) << 4: byte offset of slot s, swizzle folded in
     uint32_t f_hi[16];    // F(blade of string a << 4)
-    uint32_t fk[2][16];   // per pass: F(Lambda(logical index at physical MMA position i))
+    uint32_t fk[2][16];   // per pass: F(Lambda(logical index at physical MMA k position i))
     uint32_t cw[2][16];   // per pass: F(Gamma(w))
+    uint32_t fo[2][16];   // per pass: F(Lambda(logical index at physical MMA m position i)) (blade-major units: == fk)
+    uint32_t amap[16];    // reference-layout units: physical string-row index -> string row a (f_hi is indexed physically there)
     uint32_t neg[8];      // bit s: string s carries sign -1
     uint32_t valid[8];    // bit s: a blade maps to string s
 };
@@ -239,36 +241,167 @@ __device__ __forceinline__ void gemm_pass(uint8_t *unit, const double2 *frag, co
                 *reinterpret_cast<double2 *>(unit + (lo[mb] ^ cw[wi] ^ (uint32_t)(q << 6))) = make_double2(d[wi][q][mb][0], d[wi][q][mb][1]);
 }
 
+// ---- reference-layout (AoS) units: [chunk][row][128 bytes swizzled], element (row r, blade A) at G(A) ^ R(r) with
+// R(r) = r << 7 | (r & 7) << 4 (matrix_rep.hpp, RepLayoutAos).  A warp's lanes are 8 rows x 4 indices.
+__device__ __forceinline__ uint32_t aos_row_term(int r) { return ((uint32_t)r << 7) | (((uint32_t)r & 7u) << 4); }
+
+// Stage 1 / 3: the 16 slots of string row a at row r -- f32: packed with row r + 16 (same a, same masks; R(r + 16) =
+// R(r) + 2048 for r < 16), f64: one row.  t0 = G(lin_hi(a)) ^ R(r).
+template <typename T, bool INPUT>
+__device__ __forceinline__ void transform_row_aos(uint8_t *unit, uint32_t t0, const uint2 *tbl_a, const RepParams<T> &P) {
+    uint64_t v[16];
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+        const uint8_t *p = unit + (t0 ^ P.f_lo[b]);
+        if constexpr (sizeof(T) == 4) v[b] = (uint64_t) * reinterpret_cast<const uint32_t *>(p) | ((uint64_t) * reinterpret_cast<const uint32_t *>(p + 2048) << 32);
+        else v[b] = *reinterpret_cast<const uint64_t *>(p);
+        if (INPUT) v[b] = Elem<T>::mask(v[b], tbl_a[b]);
+    }
+    wht16<T>(v);
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+        if (!INPUT) v[b] = Elem<T>::mask(v[b], tbl_a[b]);
+        uint8_t *p = unit + (t0 ^ P.f_lo[b]);
+        if constexpr (sizeof(T) == 4) {
+            *reinterpret_cast<uint32_t *>(p) = (uint32_t)v[b];
+            *reinterpret_cast<uint32_t *>(p + 2048) = (uint32_t)(v[b] >> 32);
+        } else {
+            *reinterpret_cast<uint64_t *>(p) = v[b];
+        }
+    }
+}
+
+// Stage 2 on a reference-layout unit.  tabs = fk[16], cw[16], fo[16] of the pass.  B[k][n = g] is row 8 q + g of the slot
+// at k position; D[m][n = 2 t, 2 t + 1] are two rows (128 bytes apart): two stores.
+__device__ __forceinline__ void gemm_pass_aos(uint8_t *unit, const float4 *frag, const uint32_t *tabs, int wl, int lane, float) {
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t lk[2][2], lo[2][2];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) lk[ks][h] = tabs[8 * ks + 4 * h + t] ^ aos_row_term(g);
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) lo[mb][e] = tabs[32 + g + 8 * mb] ^ aos_row_term(2 * t + e);
+#pragma unroll 1
+    for (int wi = 0; wi < 2; ++wi) {
+        const uint32_t cw = tabs[16 + wl + 8 * wi];
+        float d[4][4], b[4][2][2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) d[q][e] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) b[q][ks][h] = *reinterpret_cast<const float *>(unit + ((lk[ks][h] ^ cw) + (uint32_t)(q << 10)));
+        }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const float4 fh = frag[(2 * ks) * 32 + lane], fl = frag[(2 * ks + 1) * 32 + lane];
+            const float hi[4] = {fh.x, fh.y, fh.z, fh.w}, lw[4] = {fl.x, fl.y, fl.z, fl.w};
+            float bh[4][2], bl[4][2];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) split_tf32(b[q][ks][h], bh[q][h], bl[q][h]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mma_tf32(d[q], lw, bh[q][0], bh[q][1]);  // small terms first
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mma_tf32(d[q], hi, bl[q][0], bl[q][1]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mma_tf32(d[q], hi, bh[q][0], bh[q][1]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) *reinterpret_cast<float *>(unit + ((lo[mb][e] ^ cw) + (uint32_t)(q << 10))) = d[q][2 * mb + e];
+    }
+}
+__device__ __forceinline__ void gemm_pass_aos(uint8_t *unit, const double2 *frag, const uint32_t *tabs, int wl, int lane, double) {
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t lk[4], lo[2][2];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) lk[ks] = tabs[4 * ks + t] ^ aos_row_term(g);
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) lo[mb][e] = tabs[32 + g + 8 * mb] ^ aos_row_term(2 * t + e);
+    const uint32_t cw[2] = {tabs[16 + wl], tabs[16 + wl + 8]};
+    double d[2][2][2][2], b[2][2][4];
+#pragma unroll
+    for (int wi = 0; wi < 2; ++wi)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb) d[wi][q][mb][0] = d[wi][q][mb][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) b[wi][q][ks] = *reinterpret_cast<const double *>(unit + ((lk[ks] ^ cw[wi]) + (uint32_t)(q << 10)));
+        }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const double2 f = frag[ks * 32 + lane];
+#pragma unroll
+        for (int wi = 0; wi < 2; ++wi)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                mma_f64(d[wi][q][0], f.x, b[wi][q][ks]);
+                mma_f64(d[wi][q][1], f.y, b[wi][q][ks]);
+            }
+    }
+#pragma unroll
+    for (int wi = 0; wi < 2; ++wi)
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) *reinterpret_cast<double *>(unit + ((lo[mb][e] ^ cw[wi]) + (uint32_t)(q << 10))) = d[wi][q][mb][e];
+}
+
 // shared memory behind the ring: barriers, sign table, pass tables, factor fragments
 constexpr int kTblPitch = 17;  // entries per string row: the two rows a warp reads sit 136 bytes apart
-constexpr int kAuxBar = 0, kAuxTbl = 64, kAuxTabs = kAuxTbl + 16 * kTblPitch * 8, kAuxFrag = kAuxTabs + 2 * 32 * 4, kAuxBytes = kAuxFrag + 2 * 4 * 32 * 16;
+constexpr int kAuxBar = 0, kAuxSlot = 64, kAuxTbl = 128, kAuxTabs = kAuxTbl + 16 * kTblPitch * 8, kAuxFrag = kAuxTabs + 2 * 48 * 4, kAuxBytes = kAuxFrag + 2 * 4 * 32 * 16;
 
 // NPASS 1: out = M x (column pass) or x M (row pass) -- the host chooses the tables; NPASS 2: out = R x ~R (column pass
 // with rho(R) / 16, row pass with rho(~R)).  NG groups of 8 warps.
-template <typename T, int NPASS, int NG>
+template <typename T, int NPASS, int NG, bool AOS>
 __global__ void __launch_bounds__(NG *kGroupThreads, 1)
 matrix_rep_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_out,
-                  const __grid_constant__ RepParams<T> P, int nb, int64_t n, int dbg, int order) {
+                  const __grid_constant__ RepParams<T> P, int nb, int64_t n, int dbg, int order, unsigned long long *counter) {
     constexpr int TR = 128 / (int)sizeof(T);
     using Frag = typename Factor<T>::Frag;
     extern __shared__ __align__(1024) uint8_t smem[];  // no static shared memory in this kernel: the window starts aligned
     uint8_t *aux = smem + (size_t)kRing * kUnitBytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(aux + kAuxBar);
+    int *slot_row = reinterpret_cast<int *>(aux + kAuxSlot);  // first row of the unit in each ring slot, -1: no unit left
     uint2 *tbl = reinterpret_cast<uint2 *>(aux + kAuxTbl);
     uint32_t *tabs = reinterpret_cast<uint32_t *>(aux + kAuxTabs);
     Frag *frag = reinterpret_cast<Frag *>(aux + kAuxFrag);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t units = (n + TR - 1) / TR;
     const uint32_t box_bytes = (uint32_t)nb * 128u;
-    // order 0: unit k of this CTA is unit blockIdx.x + k * gridDim.x of the batch (neighbouring CTAs work on neighbouring
-    // rows at about the same time); order 1: every CTA owns one contiguous range of units, so the six units of its ring
-    // are neighbouring 128-byte pieces of the same DRAM pages
+    // Which units a CTA works on.  With a counter (the default for batches of more units than CTAs): the next unit is taken
+    // from a global counter whenever a ring slot is refilled -- SMs do not get the same share of the HBM bandwidth (two
+    // dies, different distances to the memory partitions), and with equal static shares the slowest SM sets the time: a
+    // pass-through ring moves 6.2 TB/s with static shares and 6.9-7.0 with the counter (scripts/tma_passthrough_probe.cu,
+    // profiles/r02_tma_passthrough_probe.jsonl).  Without one, order 0: unit k of this CTA is unit blockIdx.x + k * gridDim.x
+    // of the batch; order 1: every CTA owns one contiguous range of units.
     const int64_t per_cta = (units + gridDim.x - 1) / gridDim.x;
     const int64_t first = order ? (int64_t)blockIdx.x * per_cta : (int64_t)blockIdx.x;
     const int64_t step = order ? 1 : (int64_t)gridDim.x;
     const int64_t mine = order ? (first >= units ? 0 : (units - first < per_cta ? units - first : per_cta))
                                : (units > blockIdx.x ? (units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
-    auto unit_row = [&](int64_t k) { return (int)((first + k * step) * TR); };
+    auto next_row = [&](int64_t k) -> int {  // first row of local unit k, or -1 when the batch is exhausted
+        if (counter) {
+            const int64_t u = (int64_t)atomicAdd(counter, 1ull);
+            return u < units ? (int)(u * TR) : -1;
+        }
+        return k < mine ? (int)((first + k * step) * TR) : -1;
+    };
     if (threadIdx.x == 0) {
         for (int s = 0; s < kRing; ++s) tma::mbar_init(&full[s], 1);
         tma::prefetch_map(&map_x);
@@ -276,23 +409,33 @@ matrix_rep_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     }
     for (int s = threadIdx.x; s < 256; s += NG * kGroupThreads)
         tbl[(s >> 4) * kTblPitch + (s & 15)] = make_uint2(((P.valid[s >> 5] >> (s & 31)) & 1u) ? 0xffffffffu : 0u, ((P.neg[s >> 5] >> (s & 31)) & 1u) ? 0x80000000u : 0u);
-    if (threadIdx.x < 64) {
-        const int p = threadIdx.x >> 5, i = threadIdx.x & 31;
-        tabs[threadIdx.x] = i < 16 ? P.fk[p][i] : P.cw[p][i - 16];
+    if (threadIdx.x < 96) {
+        const int p = threadIdx.x / 48, i = threadIdx.x % 48;
+        tabs[threadIdx.x] = i < 16 ? P.fk[p][i] : (i < 32 ? P.cw[p][i - 16] : P.fo[p][i - 32]);
     }
     if (warp < NPASS) Factor<T>::build(frag + warp * 4 * 32, P.factor[warp], lane);
     __syncthreads();
-    if (threadIdx.x == 0)
-        for (int64_t k = 0; k < mine && k < kRing; ++k) {  // fill the ring
-            tma::mbar_expect_tx(&full[k], box_bytes);
-            tma::load_2d(smem + (size_t)k * kUnitBytes, &map_x, &full[k], unit_row(k), 0);
+    auto load_slot = [&](int64_t k) {  // local unit k into ring slot k % kRing (TMA threads only)
+        const int rs = (int)(k % kRing), row = next_row(k);
+        slot_row[rs] = row;
+        if (row >= 0) {
+            tma::mbar_expect_tx(&full[rs], box_bytes);
+            if (AOS) tma::load_3d(smem + (size_t)rs * kUnitBytes, &map_x, &full[rs], 0, row, 0);
+            else tma::load_2d(smem + (size_t)rs * kUnitBytes, &map_x, &full[rs], row, 0);
         }
+    };
+    if (threadIdx.x == 0)
+        for (int64_t k = 0; k < kRing; ++k) load_slot(k);  // fill the ring
+    __syncthreads();  // slot_row of the first ring is visible to every group
     const int grp = warp >> 3, wl = warp & 7;
     const int gtid = threadIdx.x & (kGroupThreads - 1);
     auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kGroupThreads) : "memory"); };
-    // stage 1 / 3 role: string row a = 2 * wl + (lane >> 4), 8-byte element lane & 15 of the 128-byte line
-    const int a_row = 2 * wl + (lane >> 4);
-    const uint32_t t0 = P.f_hi[a_row] ^ (uint32_t)((lane & 15) << 3);
+    // stage 1 / 3 role.  Blade-major units: string row a = 2 * wl + (lane >> 4), 8-byte element lane & 15 of the 128-byte
+    // line.  Reference-layout units: physical string row 4 * (wl >> 1) + (lane >> 3) at row 8 * (wl & 1) + (lane & 7) (f32:
+    // and that row + 16).
+    const int a_phys = AOS ? 4 * (wl >> 1) + (lane >> 3) : 2 * wl + (lane >> 4);
+    const int a_row = AOS ? (int)P.amap[a_phys] : a_phys;
+    const uint32_t t0 = P.f_hi[a_phys] ^ (AOS ? aos_row_term(8 * (wl & 1) + (lane & 7)) : (uint32_t)((lane & 15) << 3));
     const uint2 *tbl_a = tbl + a_row * kTblPitch;
     // The group's first thread is also its TMA thread: it stores the group's finished unit and, one barrier into the
     // group's NEXT unit (by then the engine has read the slot), refills that slot with the unit kRing ahead.
@@ -300,23 +443,21 @@ matrix_rep_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     auto refill = [&]() {
         if (gtid == 0 && stored >= 0) {
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            if (stored + kRing < mine) {
-                const int rs = (int)(stored % kRing);
-                tma::mbar_expect_tx(&full[rs], box_bytes);
-                tma::load_2d(smem + (size_t)rs * kUnitBytes, &map_x, &full[rs], unit_row(stored + kRing), 0);
-            }
+            load_slot(stored + kRing);  // (published to the group by the barriers between here and its use, two units on)
             stored = -1;
         }
     };
     auto store_unit = [&](int64_t it, int s) {
         if (gtid == 0) {
-            tma::store_2d(&map_out, smem + (size_t)s * kUnitBytes, unit_row(it), 0);
+            if (AOS) tma::store_3d(&map_out, smem + (size_t)s * kUnitBytes, 0, slot_row[s], 0);
+            else tma::store_2d(&map_out, smem + (size_t)s * kUnitBytes, slot_row[s], 0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             stored = it;
         }
     };
-    for (int64_t it = grp; it < mine; it += NG) {
+    for (int64_t it = grp;; it += NG) {
         const int s = (int)(it % kRing);
+        if (slot_row[s] < 0) break;  // units are dealt in increasing order: nothing comes after an empty slot
         const uint32_t ph = (uint32_t)((it / kRing) & 1);
         uint8_t *unit = smem + (size_t)s * kUnitBytes;
         tma::mbar_wait(&full[s], ph);
@@ -326,17 +467,20 @@ matrix_rep_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             store_unit(it, s);
             continue;
         }
-        transform_row<T, true>(unit, t0, tbl_a, P);
+        if (AOS) transform_row_aos<T, true>(unit, t0, tbl_a, P);
+        else transform_row<T, true>(unit, t0, tbl_a, P);
         refill();      // the previous unit's store has long been read: put the next load in flight
         group_sync();
         if (dbg != 2) {  // LCC_K8_DEBUG=2: transforms only
 #pragma unroll
             for (int p = 0; p < NPASS; ++p) {
-                gemm_pass(unit, frag + p * 4 * 32, tabs + p * 32, wl, lane, T());
+                if (AOS) gemm_pass_aos(unit, frag + p * 4 * 32, tabs + p * 48, wl, lane, T());
+                else gemm_pass(unit, frag + p * 4 * 32, tabs + p * 48, wl, lane, T());
                 group_sync();
             }
         }
-        transform_row<T, false>(unit, t0, tbl_a, P);
+        if (AOS) transform_row_aos<T, false>(unit, t0, tbl_a, P);
+        else transform_row<T, false>(unit, t0, tbl_a, P);
         tma::fence_proxy_async();
         group_sync();
         store_unit(it, s);
@@ -350,16 +494,20 @@ int rep_groups() {
     return g;
 }
 
-template <typename T, int NPASS, int NG>
+template <typename T, int NPASS, int NG, bool AOS>
 cudaError_t launch_rep_t(int nb, const void *x, int64_t ldx, void *out, int64_t ldo, int64_t n, const RepParams<T> &P, cudaStream_t s) {
     constexpr int TR = 128 / (int)sizeof(T);
     CUtensorMap mx, mo;
     static const int promo = [] { const char *e = getenv("LCC_K8_L2PROMO"); return e ? atoi(e) : 256; }();
     static const int order = [] { const char *e = getenv("LCC_K8_ORDER"); return e ? atoi(e) : 1; }();
     static const bool swz = [] { const char *e = getenv("LCC_K8_SWIZZLE"); return !(e && e[0] == '0'); }();  // 0: only meaningful with LCC_K8_DEBUG=1
-    if (!make_soa_tensor_map(&mx, x, (int)sizeof(T), nb, ldx, n, TR, swz, promo) || !make_soa_tensor_map(&mo, out, (int)sizeof(T), nb, ldo, n, TR, swz, promo))
+    if (AOS) {
+        if (!make_aos_chunked_tensor_map(&mx, x, (int)sizeof(T), nb, ldx, n, TR) || !make_aos_chunked_tensor_map(&mo, out, (int)sizeof(T), nb, ldo, n, TR))
+            return cudaErrorNotSupported;
+    } else if (!make_soa_tensor_map(&mx, x, (int)sizeof(T), nb, ldx, n, TR, swz, promo) || !make_soa_tensor_map(&mo, out, (int)sizeof(T), nb, ldo, n, TR, swz, promo)) {
         return cudaErrorNotSupported;
-    auto kernel = matrix_rep_kernel<T, NPASS, NG>;
+    }
+    auto kernel = matrix_rep_kernel<T, NPASS, NG, AOS>;
     constexpr int smem = kRing * kUnitBytes + kAuxBytes;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
@@ -367,52 +515,84 @@ cudaError_t launch_rep_t(int nb, const void *x, int64_t ldx, void *out, int64_t 
     const int64_t units = (n + TR - 1) / TR;
     const int grid = (int)(units < sm_count ? units : sm_count);
     static const int dbg = [] { const char *e = getenv("LCC_K8_DEBUG"); return e ? atoi(e) : 0; }();
-    kernel<<<grid, NG * kGroupThreads, smem, s>>>(mx, mo, P, nb, n, dbg, order);
+    // more units than CTAs: deal them out through a counter (stream-ordered scratch word, zeroed before the launch)
+    static const bool dyn = [] { const char *e = getenv("LCC_K8_DYNAMIC"); return !(e && e[0] == '0'); }();
+    unsigned long long *counter = nullptr;
+    if (dyn && units > grid) {
+        e = cudaMallocAsync((void **)&counter, sizeof(unsigned long long), s);
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s);
+        if (e != cudaSuccess) { cudaFreeAsync(counter, s); return e; }
+    }
+    kernel<<<grid, NG * kGroupThreads, smem, s>>>(mx, mo, P, nb, n, dbg, order, counter);
     note_kernel_launch();
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    if (counter) cudaFreeAsync(counter, s);
+    return e;
 }
 
 template <typename T> constexpr int default_groups() { return sizeof(T) == 4 ? 3 : 3; }
+
+template <typename T, bool AOS>
+cudaError_t launch_rep_p(int nb, int mode, const RepParams<T> &P, const ViewArg &x, const ViewArg &out, cudaStream_t s) {
+    const int ng = rep_groups() ? rep_groups() : default_groups<T>();
+    if (mode == 2)
+        return ng == 2 ? launch_rep_t<T, 2, 2, AOS>(nb, x.data, x.ld, out.data, out.ld, x.n, P, s) : launch_rep_t<T, 2, 3, AOS>(nb, x.data, x.ld, out.data, out.ld, x.n, P, s);
+    if (mode == 0 || mode == 1)
+        return ng == 2 ? launch_rep_t<T, 1, 2, AOS>(nb, x.data, x.ld, out.data, out.ld, x.n, P, s) : launch_rep_t<T, 1, 3, AOS>(nb, x.data, x.ld, out.data, out.ld, x.n, P, s);
+    return cudaErrorInvalidValue;
+}
 
 template <typename T>
 cudaError_t launch_rep(int nb, int mode, const double *p1, const double *p2, const uint8_t *blade_at, const int8_t *sign_at,
                        const ViewArg &x, const ViewArg &out, cudaStream_t s) {
     const RepLayout L = make_rep_layout(blade_at, sign_at);
-    if (!L.ok) return cudaErrorNotSupported;
+    const bool aos = x.layout == kAoS;
     RepParams<T> P;
-    // mode 0: column pass with p1; mode 1: row pass with p1; mode 2: column pass with p1, row pass with p2
-    const RepPass *pass[2] = {mode == 1 ? &L.row : &L.column, &L.row};
     const double *fac[2] = {p1, p2};
-    for (int p = 0; p < 2; ++p)
-        for (int i = 0; i < 16; ++i) {
-            P.fk[p][i] = pass[p]->fk[i];
-            P.cw[p][i] = pass[p]->cw[i];
-            for (int k = 0; k < 16; ++k) P.factor[p][i * 16 + k] = fac[p] ? (T)fac[p][pass[p]->kmap[i] * 16 + pass[p]->kmap[k]] : T(0);
-        }
-    for (int i = 0; i < 16; ++i) { P.f_lo[i] = L.f_lo[i]; P.f_hi[i] = L.f_hi[i]; }
+    // mode 0: column pass with p1; mode 1: row pass with p1; mode 2: column pass with p1, row pass with p2
+    if (aos) {
+        const RepLayoutAos A = make_rep_layout_aos(L, (int)sizeof(T));
+        if (!A.ok) return cudaErrorNotSupported;
+        const RepPassAos *pass[2] = {mode == 1 ? &A.row : &A.column, &A.row};
+        for (int p = 0; p < 2; ++p)
+            for (int i = 0; i < 16; ++i) {
+                P.fk[p][i] = pass[p]->fk[i];
+                P.cw[p][i] = pass[p]->cw[i];
+                P.fo[p][i] = pass[p]->fo[i];
+                for (int k = 0; k < 16; ++k) P.factor[p][i * 16 + k] = fac[p] ? (T)fac[p][pass[p]->omap[i] * 16 + pass[p]->kmap[k]] : T(0);
+            }
+        for (int i = 0; i < 16; ++i) { P.f_lo[i] = A.g_lo[i]; P.f_hi[i] = A.g_hi[i]; P.amap[i] = A.amap[i]; }
+    } else {
+        if (!L.ok) return cudaErrorNotSupported;
+        const RepPass *pass[2] = {mode == 1 ? &L.row : &L.column, &L.row};
+        for (int p = 0; p < 2; ++p)
+            for (int i = 0; i < 16; ++i) {
+                P.fk[p][i] = P.fo[p][i] = pass[p]->fk[i];
+                P.cw[p][i] = pass[p]->cw[i];
+                for (int k = 0; k < 16; ++k) P.factor[p][i * 16 + k] = fac[p] ? (T)fac[p][pass[p]->kmap[i] * 16 + pass[p]->kmap[k]] : T(0);
+            }
+        for (int i = 0; i < 16; ++i) { P.f_lo[i] = L.f_lo[i]; P.f_hi[i] = L.f_hi[i]; P.amap[i] = (uint32_t)i; }
+    }
     for (int i = 0; i < 8; ++i) P.neg[i] = P.valid[i] = 0;
     for (int str = 0; str < 256; ++str) {
         if (sign_at[str] != 0) P.valid[str >> 5] |= 1u << (str & 31);
         if (sign_at[str] < 0) P.neg[str >> 5] |= 1u << (str & 31);
     }
-    const int ng = rep_groups() ? rep_groups() : default_groups<T>();
-    if (mode == 2)
-        return ng == 2 ? launch_rep_t<T, 2, 2>(nb, x.data, x.ld, out.data, out.ld, x.n, P, s) : launch_rep_t<T, 2, 3>(nb, x.data, x.ld, out.data, out.ld, x.n, P, s);
-    if (mode == 0 || mode == 1)
-        return ng == 2 ? launch_rep_t<T, 1, 2>(nb, x.data, x.ld, out.data, out.ld, x.n, P, s) : launch_rep_t<T, 1, 3>(nb, x.data, x.ld, out.data, out.ld, x.n, P, s);
-    return cudaErrorInvalidValue;
+    return aos ? launch_rep_p<T, true>(nb, mode, P, x, out, s) : launch_rep_p<T, false>(nb, mode, P, x, out, s);
 }
 
 }  // namespace
 
 // K8 launcher.  mode 0 / 1 / 2 = left product, right product, sandwich; p1 (and p2 for the sandwich) are row-major 16 x 16
 // f64 factors in the orientation the MMA contracts ([o][k]: mode 0 rho(M) / 16, mode 1 rho(M)^T / 16, mode 2 rho(R) / 16 and
-// rho(~R)^T); blade_at / sign_at map a string to its blade and sign.  x and out are blade-major (SoA) views of nb = 128 or
-// 256 blades whose row count is a multiple of 16 bytes (TMA stores clip at that granularity).
+// rho(~R)^T); blade_at / sign_at map a string to its blade and sign.  x and out are views of nb = 128 or 256 blades in ONE
+// layout: blade-major (SoA) with a row count that is a multiple of 16 bytes (TMA stores clip at that granularity), or the
+// reference's row-major (AoS) layout with any row count -- whole rows are contiguous there, and a unit is one 16-32 KB span.
 cudaError_t launch_matrix_rep_product(int nb, int mode, const double *p1, const double *p2, const uint8_t *blade_at, const int8_t *sign_at,
                                       const ViewArg &x, const ViewArg &out, cudaStream_t s) {
     if (x.n <= 0) return cudaSuccess;
-    if (x.layout != kSoA || out.layout != kSoA || (nb != 128 && nb != 256)) return cudaErrorNotSupported;
+    if (x.layout != out.layout || (nb != 128 && nb != 256)) return cudaErrorNotSupported;
     return x.dtype == kF32 ? launch_rep<float>(nb, mode, p1, p2, blade_at, sign_at, x, out, s)
                            : launch_rep<double>(nb, mode, p1, p2, blade_at, sign_at, x, out, s);
 }

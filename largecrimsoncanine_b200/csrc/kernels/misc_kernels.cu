@@ -1303,4 +1303,18 @@ bool make_aos_tensor_map(CUtensorMap *map, const void *base, int elem_bytes, int
                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+bool make_aos_chunked_tensor_map(CUtensorMap *map, const void *base, int elem_bytes, int nb, int64_t ld, int64_t n, int rows) {
+    EncodeFn enc = tensor_map_encoder();
+    if (!enc || n <= 0 || n >= (int64_t)1 << 31 || rows > 256) return false;
+    if (((uintptr_t)base & 15) != 0 || ((ld * elem_bytes) & 15) != 0 || ld < nb || (nb * elem_bytes) % 128 != 0) return false;
+    const cuuint32_t per_line = (cuuint32_t)(128 / elem_bytes), chunks = (cuuint32_t)(nb * elem_bytes / 128);
+    const cuuint64_t dims[3] = {per_line, (cuuint64_t)n, chunks};
+    const cuuint64_t strides[2] = {(cuuint64_t)ld * (cuuint64_t)elem_bytes, 128};
+    const cuuint32_t box[3] = {per_line, (cuuint32_t)rows, chunks};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapDataType dt = elem_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    return enc(map, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace lcc

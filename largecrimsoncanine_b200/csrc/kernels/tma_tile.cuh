@@ -82,6 +82,16 @@ __device__ __forceinline__ void store_2d(const CUtensorMap *map, const void *src
                      ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
     }
 }
+// 3-D forms (K8 on reference-layout batches: one box = {128 bytes of blades, rows, chunks})
+__device__ __forceinline__ void load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void store_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void store_commit_and_wait_read() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -109,5 +119,11 @@ bool make_aos_tensor_map(CUtensorMap *map, const void *base, int elem_bytes, int
 // l2_promotion: bytes the L2 fetches from DRAM per request (64 / 128 / 256; 0 = none).
 bool make_soa_tensor_map(CUtensorMap *map, const void *base, int elem_bytes, int nb, int64_t ld, int64_t n, int rows,
                          bool swizzle128 = false, int l2_promotion = 128);
+
+// Reference-layout (AoS) batch seen as (128 bytes of blades, n rows, nb * elem_bytes / 128 chunks): a box of
+// (128 bytes, rows, all chunks) is `rows` whole multivectors -- one contiguous span of HBM when ld == nb -- and lands in
+// shared memory as [chunk][row][128 bytes] with the hardware 128-byte swizzle (K8, matrix_rep_kernel.cu).  Rows of at least
+// 128 bytes only; any row count (whole rows are clipped / zero-filled at the end).
+bool make_aos_chunked_tensor_map(CUtensorMap *map, const void *base, int elem_bytes, int nb, int64_t ld, int64_t n, int rows);
 
 }  // namespace lcc

@@ -519,17 +519,28 @@ static bool matrix_rep_of(const lcc_algebra *calg) {
                 if (rep.blade_at[sidx] >= 0) { alg->rep_blade_at[sidx] = (uint8_t)rep.blade_at[sidx]; alg->rep_sign_at[sidx] = rep.sign_of[rep.blade_at[sidx]]; }
         };
         alg->rep_state = 2;
-        for (int variant = 0; variant < 1 + 384 * 13; ++variant) {
-            const MatrixRep rep = find_matrix_rep(*alg, variant);
+        // K8 has three shared-memory layouts -- blade-major units (make_rep_layout) and reference-layout units in f32 and
+        // f64 (make_rep_layout_aos) -- each with its own bank conditions on the string -> blade map.  Take the first
+        // variant that satisfies all three; failing that, the first that satisfies the blade-major one.
+        std::vector<unsigned> gens;
+        int best = -1, best_score = -1;
+        for (int variant = 0; variant < 1 + 384 * 13 && best_score < 3; ++variant) {
+            const MatrixRep rep = find_matrix_rep(*alg, variant, &gens, variant == 0);
             if (!rep.ok) { if (variant == 0) break; else continue; }
             if (variant == 0) { install(rep); alg->rep_state = 1; }
-            MatrixRep tmp = rep;
             uint8_t blade_at[256]; int8_t sign_at[256];
             for (int sidx = 0; sidx < 256; ++sidx) {
-                blade_at[sidx] = tmp.blade_at[sidx] >= 0 ? (uint8_t)tmp.blade_at[sidx] : 0;
-                sign_at[sidx] = tmp.blade_at[sidx] >= 0 ? tmp.sign_of[tmp.blade_at[sidx]] : 0;
+                blade_at[sidx] = rep.blade_at[sidx] >= 0 ? (uint8_t)rep.blade_at[sidx] : 0;
+                sign_at[sidx] = rep.blade_at[sidx] >= 0 ? rep.sign_of[rep.blade_at[sidx]] : 0;
             }
-            if (make_rep_layout(blade_at, sign_at).ok) { install(rep); break; }
+            const RepLayout L = make_rep_layout(blade_at, sign_at);
+            if (!L.ok) continue;
+            const int score = 1 + (make_rep_layout_aos(L, 4).ok ? 1 : 0) + (make_rep_layout_aos(L, 8).ok ? 1 : 0);
+            if (score > best_score) { best_score = score; best = variant; }
+        }
+        if (best > 0) {
+            const MatrixRep rep = find_matrix_rep(*alg, best, &gens, true);  // verified against the Cayley table before use
+            if (rep.ok) install(rep);
         }
     }
     return alg->rep_state == 1;
@@ -567,6 +578,17 @@ static lcc_status matrix_rep_apply(const lcc_algebra *alg, int mode, const doubl
     const int64_t w = 16 / (int64_t)elem_size(x->dtype);
     PoolBuffer tin, tout;
     lcc_view sx = *x, so = *out;
+    // reference-layout views run in place on units of whole rows (one contiguous 16-32 KB span each: 6.3 TB/s of TMA
+    // traffic against 4.6 for the 128-byte pieces of a blade-major unit, profiles/r02_tma_passthrough_probe.jsonl)
+    static const bool aos_direct = [] { const char *e = getenv("LCC_K8_AOS"); return !(e && e[0] == '0'); }();
+    if (aos_direct && x->layout == LCC_AOS && out->layout == LCC_AOS) {
+        const cudaError_t e = launch_matrix_rep_product(nb, mode, p1, p2, alg->rep_blade_at.data(), alg->rep_sign_at.data(), arg_of(x), arg_of(out), s);
+        if (e != cudaErrorNotSupported) {
+            LCC_CUDA(e);
+            *rows_done = x->n;
+            return LCC_OK;
+        }
+    }
     if (x->layout == LCC_AOS) {
         LCC_TRY(make_soa_temp(alg, x->dtype, x->n, tin, &sx, s));
         LCC_TRY(make_soa_temp(alg, x->dtype, x->n, tout, &so, s));
@@ -742,6 +764,23 @@ int lcc_algebra_matrix_rep_layout(const lcc_algebra *alg, uint32_t *tables) {
             tables[0 * 16 + i] = L.f_lo[i];        tables[1 * 16 + i] = L.f_hi[i];
             tables[2 * 16 + i] = L.column.fk[i];   tables[3 * 16 + i] = L.column.cw[i];   tables[4 * 16 + i] = L.column.kmap[i];
             tables[5 * 16 + i] = L.row.fk[i];      tables[6 * 16 + i] = L.row.cw[i];      tables[7 * 16 + i] = L.row.kmap[i];
+        }
+    return 1;
+}
+
+int lcc_algebra_matrix_rep_layout_aos(const lcc_algebra *alg, int elem_bytes, uint32_t *tables) {
+    if (!alg || (elem_bytes != 4 && elem_bytes != 8) || !matrix_rep_of(alg)) return 0;
+    const RepLayout L = make_rep_layout(alg->rep_blade_at.data(), alg->rep_sign_at.data());
+    const RepLayoutAos A = make_rep_layout_aos(L, elem_bytes);
+    if (!A.ok) return 0;
+    if (tables)
+        for (int i = 0; i < 16; ++i) {
+            tables[0 * 16 + i] = A.g_lo[i];        tables[1 * 16 + i] = A.g_hi[i];        tables[2 * 16 + i] = A.amap[i];
+            const RepPassAos *pass[2] = {&A.column, &A.row};
+            for (int p = 0; p < 2; ++p) {
+                tables[(3 + 5 * p) * 16 + i] = pass[p]->fk[i];   tables[(4 + 5 * p) * 16 + i] = pass[p]->fo[i];   tables[(5 + 5 * p) * 16 + i] = pass[p]->cw[i];
+                tables[(6 + 5 * p) * 16 + i] = pass[p]->kmap[i]; tables[(7 + 5 * p) * 16 + i] = pass[p]->omap[i];
+            }
         }
     return 1;
 }

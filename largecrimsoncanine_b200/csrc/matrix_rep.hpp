@@ -100,7 +100,9 @@ inline unsigned relabel_string(unsigned s, int variant) {
     return (na << 4) | nb;
 }
 
-inline MatrixRep find_matrix_rep(const lcc_algebra &alg, int variant = 0) {
+// `base_gens` (optional): generator strings of an earlier variant-0 search, so that relabelled variants skip the search;
+// `verify` = false skips the all-pairs check (the caller verifies the variant it finally installs).
+inline MatrixRep find_matrix_rep(const lcc_algebra &alg, int variant = 0, std::vector<unsigned> *base_gens = nullptr, bool verify = true) {
     using namespace matrix_rep_detail;
     MatrixRep rep;
     for (int i = 0; i < 256; ++i) { rep.string_of[i] = 0; rep.sign_of[i] = 0; rep.blade_at[i] = -1; }
@@ -111,7 +113,11 @@ inline MatrixRep find_matrix_rep(const lcc_algebra &alg, int variant = 0) {
     const int cls = (((alg.p - alg.q) % 8) + 8) % 8;
     if (alg.dim == 8 ? !(cls == 0 || cls == 2) : !(cls == 1 || cls == 3 || cls == 7)) return rep;
     std::vector<unsigned> gens, echelon;
-    if (!search(alg.p, alg.q, 0, gens, echelon)) return rep;
+    if (base_gens && !base_gens->empty()) gens = *base_gens;
+    else {
+        if (!search(alg.p, alg.q, 0, gens, echelon)) return rep;
+        if (base_gens) *base_gens = gens;
+    }
     for (unsigned &g : gens) g = relabel_string(g, variant);
     const int nb = alg.nb;
     for (int A = 0; A < nb; ++A) {
@@ -125,7 +131,7 @@ inline MatrixRep find_matrix_rep(const lcc_algebra &alg, int variant = 0) {
         rep.blade_at[s] = (int16_t)A;
     }
     // verify against the algebra's own sign table for every pair of blades: rho(e_A) rho(e_B) == sign[A][B] rho(e_{A^B})
-    for (int A = 0; A < nb; ++A)
+    for (int A = 0; verify && A < nb; ++A)
         for (int B = 0; B < nb; ++B) {
             const PS x{(unsigned)rep.string_of[A] >> 4, (unsigned)rep.string_of[A] & 15, rep.sign_of[A]};
             const PS y{(unsigned)rep.string_of[B] >> 4, (unsigned)rep.string_of[B] & 15, rep.sign_of[B]};
@@ -177,6 +183,7 @@ struct RepPass {
 };
 struct RepLayout {
     bool ok = false;
+    bool lin_ok = false;  // lin is filled (the passes may still have failed)
     uint8_t lin[256];     // string -> blade, extended linearly to strings no blade maps to (128-blade algebras: blades 128..255)
     uint32_t f_lo[16];    // F(lin_lo(b))
     uint32_t f_hi[16];    // F(lin_hi(a))
@@ -247,6 +254,7 @@ inline RepLayout make_rep_layout(const uint8_t *blade_at, const int8_t *sign_at)
         if (lin[str] < 0 || lin[str] > 255) return L;
         L.lin[str] = (uint8_t)lin[str];
     }
+    L.lin_ok = true;
     unsigned lam_c[16], gam_c[16], lam_r[16], gam_r[16];
     for (unsigned i = 0; i < 16; ++i) {
         L.f_lo[i] = slot_offset(L.lin[i]);
@@ -255,6 +263,135 @@ inline RepLayout make_rep_layout(const uint8_t *blade_at, const int8_t *sign_at)
         lam_r[i] = L.lin[(i << 4) | i];      gam_r[i] = L.lin[i << 4];
     }
     L.ok = make_pass(lam_c, gam_c, L.column) && make_pass(lam_r, gam_r, L.row);
+    return L;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K8 on reference-layout (AoS) batches: a unit is 128 / sizeof(T) consecutive ROWS (32 f32, 16 f64) of the (n, nb) array --
+// one contiguous 16-32 KB span of HBM -- delivered by ONE 3-D TMA box {128 bytes of blades, rows, nb * sizeof(T) / 128
+// chunks} with the 128-byte swizzle, so its shared-memory image is [chunk][row][128 bytes]:
+//     offset(row r, blade A) = G(A) ^ R(r),   R(r) = r << 7 | (r & 7) << 4,
+//     G(A) = (A >> 5) << 12 | ((A >> 2) & 7) << 4 | (A & 3) << 2        (f32: 32 blades per line, 4 KB per chunk)
+//     G(A) = (A >> 4) << 11 | ((A >> 1) & 7) << 4 | (A & 1) << 3        (f64: 16 blades per line, 2 KB per chunk)
+// -- the same "linear slot offset XOR row term" algebra as the blade-major layout above, with other constants.  A warp's
+// lanes are 8 rows x 4 indices (string rows a in the transforms, contraction / output indices in the MMA fragments); the 8
+// rows always fall on 8 different 16-byte columns (the swizzle), so an access is conflict free iff the 4 (f64 half-warps:
+// 2 to 4) indices differ in the low blade bits that select the word inside the 16-byte column (or, for the f64 B
+// fragments whose half-warps hold only 4 rows, in blade bit 3).  Three index bases are searched for that:
+//     amap   string rows of the transforms          f32: lin_hi & 3 independent on (u0, u1); f64: lin_hi(u0) & 1
+//     kmap   contraction index at the MMA's k       f32: Lambda & 3 independent on (v0, v1); f64: bits {0, 3} of Lambda
+//     omap   output index at the MMA's m            f32: Lambda & 7 independent on (w0, w1, w2); f64: Lambda & 3 on (w0, w1)
+// and every warp-wide access the kernel makes is then replayed against the bank rule before the layout is accepted.
+struct RepPassAos {
+    uint32_t fk[16];   // G(Lambda(kmap[physical k]))
+    uint32_t fo[16];   // G(Lambda(omap[physical m]))
+    uint32_t cw[16];   // G(Gamma(w))
+    uint8_t kmap[16], omap[16];
+};
+struct RepLayoutAos {
+    bool ok = false;
+    uint32_t g_lo[16];   // G(lin_lo(b))
+    uint32_t g_hi[16];   // G(lin_hi(amap[i])): physical string-row index i
+    uint8_t amap[16];    // physical string-row index -> string row a
+    RepPassAos column, row;
+};
+
+namespace matrix_rep_detail {
+inline uint32_t aos_offset(unsigned A, int elem_bytes) {
+    return elem_bytes == 4 ? ((A >> 5) << 12) | (((A >> 2) & 7u) << 4) | ((A & 3u) << 2) : ((A >> 4) << 11) | (((A >> 1) & 7u) << 4) | ((A & 1u) << 3);
+}
+inline uint32_t aos_row_term(unsigned r) { return (r << 7) | ((r & 7u) << 4); }
+// do the `lanes` byte offsets of one access of `bytes` bytes per lane fall on distinct banks (4-byte accesses: 32 lanes;
+// 8-byte accesses: the hardware serves half-warps)?
+inline bool banks_distinct(const uint32_t *off, int lanes, int bytes) {
+    uint32_t seen = 0;
+    for (int i = 0; i < lanes; ++i) {
+        const uint32_t bank = bytes == 4 ? (off[i] >> 2) & 31u : (off[i] >> 3) & 15u;
+        if (seen & (1u << bank)) return false;
+        seen |= 1u << bank;
+    }
+    return true;
+}
+// first basis (ascending search) of F_2^4 whose index map i -> XOR of the basis vectors of the set bits of i passes `good`
+template <class F> inline bool pick_map(uint8_t map[16], F good) {
+    for (unsigned v0 = 1; v0 < 16; ++v0)
+        for (unsigned v1 = 1; v1 < 16; ++v1) {
+            if (v1 == v0) continue;
+            for (unsigned v2 = 1; v2 < 16; ++v2) {
+                if (v2 == v0 || v2 == v1 || v2 == (v0 ^ v1)) continue;
+                for (unsigned v3 = 1; v3 < 16; ++v3) {
+                    bool in_span = false;
+                    for (unsigned m = 0; m < 8; ++m)
+                        if (v3 == (((m & 1) ? v0 : 0) ^ ((m & 2) ? v1 : 0) ^ ((m & 4) ? v2 : 0))) in_span = true;
+                    if (in_span) continue;
+                    const unsigned v[4] = {v0, v1, v2, v3};
+                    for (unsigned i = 0; i < 16; ++i) {
+                        unsigned k = 0;
+                        for (int bit = 0; bit < 4; ++bit) if ((i >> bit) & 1) k ^= v[bit];
+                        map[i] = (uint8_t)k;
+                    }
+                    if (good(map)) return true;
+                    break;  // the conditions only involve v0..v2: another v3 cannot help
+                }
+            }
+        }
+    return false;
+}
+inline bool make_pass_aos(const unsigned lam[16], const unsigned gam[16], int es, RepPassAos &p) {
+    // B fragments: lane = 4 g + t reads index position (4 j + t) at row g;  D fragments: lane holds output position g (+ 8)
+    // at rows 2 t and 2 t + 1 (two separate stores)
+    auto k_ok = [&](const uint8_t *map) {
+        for (int j = 0; j < 4; ++j) {
+            uint32_t off[32];
+            for (int g = 0; g < 8; ++g)
+                for (int t = 0; t < 4; ++t) off[4 * g + t] = aos_offset(lam[map[4 * j + t]], es) ^ aos_row_term(g);
+            if (es == 4 ? !banks_distinct(off, 32, 4) : !(banks_distinct(off, 16, 8) && banks_distinct(off + 16, 16, 8))) return false;
+        }
+        return true;
+    };
+    auto o_ok = [&](const uint8_t *map) {
+        for (int mb = 0; mb < 2; ++mb)
+            for (int e = 0; e < 2; ++e) {
+                uint32_t off[32];
+                for (int g = 0; g < 8; ++g)
+                    for (int t = 0; t < 4; ++t) off[4 * g + t] = aos_offset(lam[map[g + 8 * mb]], es) ^ aos_row_term(2 * t + e);
+                if (es == 4 ? !banks_distinct(off, 32, 4) : !(banks_distinct(off, 16, 8) && banks_distinct(off + 16, 16, 8))) return false;
+            }
+        return true;
+    };
+    if (!pick_map(p.kmap, k_ok) || !pick_map(p.omap, o_ok)) return false;
+    for (unsigned i = 0; i < 16; ++i) {
+        p.fk[i] = aos_offset(lam[p.kmap[i]], es);
+        p.fo[i] = aos_offset(lam[p.omap[i]], es);
+        p.cw[i] = aos_offset(gam[i], es);
+    }
+    return true;
+}
+}  // namespace matrix_rep_detail
+
+inline RepLayoutAos make_rep_layout_aos(const RepLayout &base, int elem_bytes) {
+    using namespace matrix_rep_detail;
+    RepLayoutAos L;
+    if (!base.lin_ok) return L;
+    unsigned lam_c[16], gam_c[16], lam_r[16], gam_r[16];
+    for (unsigned i = 0; i < 16; ++i) {
+        L.g_lo[i] = aos_offset(base.lin[i], elem_bytes);
+        lam_c[i] = base.lin[i << 4];              gam_c[i] = base.lin[(i << 4) | i];
+        lam_r[i] = base.lin[(i << 4) | i];        gam_r[i] = base.lin[i << 4];
+    }
+    // transforms: lane = 8 alpha + rho handles string row amap[4 * group + alpha] at row rho (+ 8, + 16, ...)
+    auto a_ok = [&](const uint8_t *map) {
+        for (int grp = 0; grp < 4; ++grp) {
+            uint32_t off[32];
+            for (int al = 0; al < 4; ++al)
+                for (int rho = 0; rho < 8; ++rho) off[8 * al + rho] = aos_offset(base.lin[(unsigned)map[4 * grp + al] << 4], elem_bytes) ^ aos_row_term(rho);
+            if (elem_bytes == 4 ? !banks_distinct(off, 32, 4) : !(banks_distinct(off, 16, 8) && banks_distinct(off + 16, 16, 8))) return false;
+        }
+        return true;
+    };
+    if (!pick_map(L.amap, a_ok)) return L;
+    for (unsigned i = 0; i < 16; ++i) L.g_hi[i] = aos_offset(base.lin[(unsigned)L.amap[i] << 4], elem_bytes);
+    L.ok = make_pass_aos(lam_c, gam_c, elem_bytes, L.column) && make_pass_aos(lam_r, gam_r, elem_bytes, L.row);
     return L;
 }
 

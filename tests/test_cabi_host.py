@@ -246,6 +246,99 @@ def test_k8_shared_memory_layout(sig):
                         assert len(banks) == 8
 
 
+@pytest.mark.parametrize("es", [4, 8])
+@pytest.mark.parametrize("sig", [(8, 0, 0), (4, 4, 0), (5, 3, 0), (0, 8, 0), (1, 7, 0), (7, 0, 0), (4, 3, 0), (0, 7, 0), (3, 4, 0)])
+def test_k8_reference_layout_units(sig, es):
+    """K8 on reference-layout (AoS) batches (kernels/matrix_rep_kernel.cu, AOS = true): a unit is 32 (f32) / 16 (f64) whole
+    rows, delivered by one 3-D TMA box as [chunk][row][128 bytes swizzled]; element (row r, blade A) sits at G(A) ^ R(r)
+    (csrc/matrix_rep.hpp, RepLayoutAos).  Replays the kernel's address arithmetic for one row against the algebra's Cayley
+    table -- left product, right product, sandwich -- and checks every warp-wide access against the bank rule."""
+    L = cabi.lib()
+    a = cabi.Algebra(*sig)
+    nb = a.num_blades
+    strings, signs = (C.c_uint8 * nb)(), (C.c_int8 * nb)()
+    assert L.lcc_algebra_matrix_rep(a.h, strings, signs) == 16
+    strings, signs = np.array(strings[:]), np.array(signs[:], dtype=np.float64)
+    tables = (C.c_uint32 * (13 * 16))()
+    assert L.lcc_algebra_matrix_rep_layout_aos(a.h, es, tables) == 1
+    t = np.array(tables[:], dtype=np.int64).reshape(13, 16)
+    g_lo, g_hi, amap = t[0], t[1], t[2]
+    passes = {"column": tuple(t[3:8]), "row": tuple(t[8:13])}  # fk, fo, cw, kmap, omap
+
+    def G(A):
+        return ((A >> 5) << 12 | ((A >> 2) & 7) << 4 | (A & 3) << 2) if es == 4 else ((A >> 4) << 11 | ((A >> 1) & 7) << 4 | (A & 1) << 3)
+
+    def R(r):
+        return r << 7 | (r & 7) << 4
+
+    blade_of_offset = {G(A): A for A in range(256)}
+    assert sorted(amap) == list(range(16))
+    sign_at = np.zeros(256)
+    for A in range(nb):
+        sign_at[strings[A]] = signs[A]
+        sa, sb = int(strings[A]) >> 4, int(strings[A]) & 15
+        assert g_hi[list(amap).index(sa)] ^ g_lo[sb] == G(A)
+    table = a.cayley_signs().reshape(nb, nb).astype(np.float64)
+    rng = np.random.default_rng(sum(sig) * 11 + sig[1] + es)
+    x, m, r = rng.standard_normal(nb), rng.standard_normal(nb), rng.standard_normal(nb)
+    idx = np.arange(nb)
+
+    def gp(u, v):
+        out = np.zeros(nb)
+        for A in range(nb):
+            np.add.at(out, A ^ idx, u[A] * table[A] * v)
+        return out
+
+    def run(plan):
+        slots = np.full(256, np.nan)
+        slots[:nb] = x
+        for i in range(16):  # stage 1, physical string row i
+            sa = amap[i]
+            where = [blade_of_offset[g_hi[i] ^ g_lo[b]] for b in range(16)]
+            v = [slots[where[b]] * sign_at[sa << 4 | b] if sign_at[sa << 4 | b] else 0.0 for b in range(16)]
+            slots[where] = _wht16(v)
+        for kind, fac in plan:  # stage 2: D[m] = sum_k fac[omap[m]][kmap[k]] Z[k]
+            fk, fo, cw, kmap, omap = passes[kind]
+            phys = fac[np.ix_(omap, kmap)]
+            for w in range(16):
+                src = [blade_of_offset[fk[i] ^ cw[w]] for i in range(16)]
+                dst = [blade_of_offset[fo[i] ^ cw[w]] for i in range(16)]
+                assert sorted(src) == sorted(dst)  # in place: the pass writes the slots it read
+                slots[dst] = phys @ slots[src]
+        for i in range(16):  # stage 3
+            sa = amap[i]
+            where = [blade_of_offset[g_hi[i] ^ g_lo[b]] for b in range(16)]
+            v = _wht16(slots[where])
+            slots[where] = [v[b] * sign_at[sa << 4 | b] for b in range(16)]
+        return slots[:nb]
+
+    rho_m = _rep_matrix(strings, signs, m)
+    assert np.allclose(run([("column", rho_m / 16)]), gp(m, x), rtol=0, atol=1e-11)
+    assert np.allclose(run([("row", rho_m.T / 16)]), gp(x, m), rtol=0, atol=1e-11)
+    rev = np.array([1.0 if (bin(A).count("1") % 4) < 2 else -1.0 for A in range(nb)])
+    rho_r, rho_rr = _rep_matrix(strings, signs, r), _rep_matrix(strings, signs, r * rev)
+    assert np.allclose(run([("column", rho_r / 16), ("row", rho_rr.T)]), gp(gp(r, x), r * rev), rtol=0, atol=1e-9)
+
+    def conflict_free(offsets):  # offsets in lane order; 4-byte accesses: the warp, 8-byte accesses: each half-warp
+        if es == 4:
+            return len({(o >> 2) & 31 for o in offsets}) == 32
+        return all(len({(o >> 3) & 15 for o in offsets[h * 16:h * 16 + 16]}) == 16 for h in range(2))
+
+    rows = 128 // es
+    for wl in range(8):  # transforms: lane = 8 alpha + rho -> physical string row 4 (wl >> 1) + alpha at row 8 (wl & 1) + rho
+        for b in range(16):
+            for extra in ([0, 16] if es == 4 else [0]):
+                assert conflict_free([g_hi[4 * (wl >> 1) + (lane >> 3)] ^ R(8 * (wl & 1) + (lane & 7) + extra) ^ g_lo[b] for lane in range(32)])
+    for fk, fo, cw, _, _ in passes.values():  # MMA fragments: lane = 4 g + t
+        for w in range(16):
+            for q in range(rows // 8):
+                for j in range(4):
+                    assert conflict_free([fk[4 * j + (lane & 3)] ^ R(8 * q + (lane >> 2)) ^ cw[w] for lane in range(32)])
+                for mb in range(2):
+                    for e in range(2):
+                        assert conflict_free([fo[(lane >> 2) + 8 * mb] ^ R(8 * q + 2 * (lane & 3) + e) ^ cw[w] for lane in range(32)])
+
+
 def test_host_side_errors():
     L = cabi.lib()
     h = C.c_void_p()

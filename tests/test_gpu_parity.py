@@ -602,6 +602,62 @@ def test_reference_layout_views_reach_the_tensor_cores(L, sig):
             cabi.check(lib.lcc_device_free(p, None))
 
 
+@pytest.mark.parametrize("sig", [(8, 0, 0), (4, 4, 0), (5, 3, 0), (0, 8, 0), (1, 7, 0), (7, 0, 0), (4, 3, 0), (0, 7, 0), (3, 4, 0)])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_block_diagonalised_product_on_reference_layout_units(L, sig, dt):
+    """K8 on LCC_AOS views (the reference's (N, num_blades) row-major layout, /root/reference/src/batch.rs:41-47): units of
+    whole rows, no transposes -- M * x, x * M (batch.rs:365-404) and R x ~R (:452-497) at ragged sizes, with a tight and a
+    padded row pitch (padding must stay untouched), in place (out == x), against the reference arithmetic in f64."""
+    from largecrimsoncanine_b200 import cabi
+
+    lib, alg, o = cabi.lib(), cabi.Algebra(*sig), oracle.OracleAlgebra(*sig)
+    nb, tol = o.num_blades, TOL[dt]
+    code = cabi.LCC_F32 if dt == np.float32 else cabi.LCC_F64
+    tables = (C.c_uint32 * (13 * 16))()
+    assert lib.lcc_algebra_matrix_rep_layout_aos(alg.h, np.dtype(dt).itemsize, tables) == 1
+    rng = np.random.default_rng(2000 + nb + sig[1])
+    L.set_option("matrix_rep", 2)
+    try:
+        for n, pad in ((64, 0), (65, 8), (4099, 0), (12003, 4)):
+            ld = nb + pad
+            x = rng.standard_normal((n, nb)).astype(dt)
+            m = rng.standard_normal((1, nb)).astype(dt)
+            x64, m64 = x.astype(np.float64), m.astype(np.float64)
+            img = np.full((n, ld), -3.5, dt)
+            img[:, :nb] = x
+            px, po = C.c_void_p(), C.c_void_p()
+            for ptr in (px, po):
+                cabi.check(lib.lcc_device_alloc(C.byref(ptr), img.nbytes, None))
+                cabi.check(lib.lcc_memcpy_h2d(ptr, img.ctypes.data, img.nbytes, None))
+            vx, vo = cabi.view(px.value, n, ld, code, cabi.LCC_AOS), cabi.view(po.value, n, ld, code, cabi.LCC_AOS)
+            out = np.empty_like(img)
+
+            def fetch(ptr=po):
+                cabi.check(lib.lcc_memcpy_d2h(out.ctypes.data, ptr, out.nbytes, None))
+                cabi.check(lib.lcc_stream_sync(None))
+                assert np.all(out[:, nb:] == -3.5)
+                return out[:, :nb]
+
+            fixed = m64[0].copy()  # the fixed operand is known on the host (MultivectorBatch keeps the row it was built from)
+            fptr = fixed.ctypes.data_as(C.POINTER(C.c_double))
+            before = lib.lcc_kernel_launch_count()
+            cabi.check(lib.lcc_batch_fixed_product(alg.h, cabi.LCC_OP_GP, 0, fptr, C.byref(vx), C.byref(vo), 0, None))
+            assert lib.lcc_kernel_launch_count() - before == 1  # one K8 launch: no transposes, no tail kernel
+            ref = o.geometric_product(m64, x64)
+            assert np.all(np.abs(fetch() - ref).max(axis=1) <= tol * np.abs(ref).max(axis=1)), f"left n={n}"
+            cabi.check(lib.lcc_batch_fixed_product(alg.h, cabi.LCC_OP_GP, 1, fptr, C.byref(vx), C.byref(vo), 0, None))
+            ref = o.geometric_product(x64, m64)
+            assert np.all(np.abs(fetch() - ref).max(axis=1) <= tol * np.abs(ref).max(axis=1)), f"right n={n}"
+            r = rng.standard_normal(nb) / np.sqrt(nb)
+            cabi.check(lib.lcc_batch_sandwich(alg.h, r.ctypes.data_as(C.POINTER(C.c_double)), C.byref(vx), C.byref(vx), 0, None))  # in place
+            ref = o.sandwich(r, x64)
+            assert np.all(np.abs(fetch(px) - ref).max(axis=1) <= tol * np.abs(ref).max(axis=1)), f"sandwich n={n}"
+            for ptr in (px, po):
+                cabi.check(lib.lcc_device_free(ptr, None))
+    finally:
+        L.set_option("matrix_rep", 1)
+
+
 @pytest.mark.parametrize("sig", [(1, 3, 0), (3, 0, 1), (4, 1, 0), (2, 1, 1)])
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
 def test_fused_grade_product_sum(L, sig, dt):
