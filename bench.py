@@ -61,9 +61,9 @@ WORKLOADS["pga_points_compact"] = ((3, 0, 1), "f32", 28, 24, "points/s")
 WORKLOADS["cl8_fixed_gp"] = ((8, 0, 0), "f32", 24, 2048, "products/s")
 # the same product in the reference's own precision, on the FP64 tensor pipe (DMMA)
 WORKLOADS["cl8_fixed_gp_f64"] = ((8, 0, 0), "f64", 24, 4096, "products/s")
-# Library defaults: f32 = the dense nb x nb GEMM on tcgen05 (cl8_fixed_gp, tensor-bound), f64 = K8, block-diagonalised in the
-# M16(R) representation (cl8_fixed_gp_f64, HBM-side bound).  The two other combinations are measured beside them:
-# cl8_fixed_gp_rep = K8 in f32 (option matrix_rep = 2), cl8_fixed_gp_f64_gemm = the round-1 DMMA GEMM (matrix_rep = 0)
+# Library default for both precisions: K8, block-diagonalised in the M16(R) representation (cl8_fixed_gp_rep f32,
+# cl8_fixed_gp_f64; HBM-side bound).  The dense nb x nb multiplication-matrix GEMMs are measured beside them (option
+# matrix_rep = 0): cl8_fixed_gp = tcgen05 3xTF32 (tensor-bound), cl8_fixed_gp_f64_gemm = the round-1 DMMA GEMM
 WORKLOADS["cl8_fixed_gp_rep"] = ((8, 0, 0), "f32", 24, 2048, "products/s")
 WORKLOADS["cl8_fixed_gp_f64_gemm"] = ((8, 0, 0), "f64", 24, 4096, "products/s")
 CL8_WORKLOADS = ("cl8_fixed_gp", "cl8_fixed_gp_f64", "cl8_fixed_gp_rep", "cl8_fixed_gp_f64_gemm")
@@ -488,7 +488,7 @@ def setup_workload(ctx, wl, n, layout="soa", collective=True, ld_pad=0):
         def step():
             cabi.check(lib.lcc_set_option(b"matrix_rep", rep))
             cabi.check(lib.lcc_batch_fixed_product(alg.h, cabi.LCC_OP_GP, 0, fptr, C.byref(vb), C.byref(vo), flags, sptr))
-            cabi.check(lib.lcc_set_option(b"matrix_rep", 1))  # back to the library default
+            cabi.check(lib.lcc_set_option(b"matrix_rep", 2))  # back to the library default
 
         def parity():
             sub = idx[::64]
@@ -673,7 +673,7 @@ def run_gpu_arm(args):
                   "roofline_per_gpu": roofline_block(HEADLINE, sn, srec2["ms_per_step"], bytes_per, peaks, peak_kind, None)}
         strong.update(srec2)
         for swl, slayout in (("r3_gp", "soa"), ("cga_gp_outer", "soa"), ("cga_gp", "aos"), ("sta_grade_inner_sum", "soa"), ("cl8_fixed_gp", "soa"),
-                             ("cl8_fixed_gp_f64", "soa"), ("cl8_fixed_gp_rep", "soa"), ("cl8_fixed_gp_f64_gemm", "soa"), ("pga_sandwich_dense16", "soa"), ("pga_sandwich", "aos")):
+                             ("cl8_fixed_gp_f64", "soa"), ("cl8_fixed_gp_f64", "aos"), ("cl8_fixed_gp_rep", "soa"), ("cl8_fixed_gp_rep", "aos"), ("cl8_fixed_gp_f64_gemm", "soa"), ("pga_sandwich_dense16", "soa"), ("pga_sandwich", "aos")):
             try:
                 r = secondary_record(ctx, swl, k, peaks, peak_kind, layout=slayout)
             except Exception as exc:  # one workload failing must not take the headline line down

@@ -199,8 +199,9 @@ LCC_API lcc_status lcc_batch_gp_outer(const lcc_algebra *alg, const lcc_view *a,
  * engine pick the cheapest form without reading device memory back: in 128 / 256-blade non-degenerate algebras that have
  * a real 16 x 16 matrix representation (Cl(8,0), Cl(4,4), Cl(7,0), ... -- csrc/matrix_rep.hpp) the geometric product runs
  * block-diagonalised (K8: two Walsh-Hadamard passes + a 16 x 16 x 16 product per row) instead of as the nb x nb
- * tensor-core GEMM -- by default for f64 batches, where it is 4x faster; option "matrix_rep" (below) widens or disables
- * it.  Strict mode always takes the exact-order kernel. */
+ * tensor-core GEMM (f64: 6x faster, f32: 1.5x); option "matrix_rep" (below) narrows or disables it.  Views in the
+ * reference's row-major layout are processed in place as units of whole rows, blade-major views as units of 128 bytes of
+ * rows per blade.  Strict mode always takes the exact-order kernel. */
 LCC_API lcc_status lcc_batch_fixed_product(const lcc_algebra *alg, int op, int side, const double *fixed_host, const lcc_view *x,
                                            const lcc_view *out, unsigned flags, void *stream);
 /* Fused pipeline  sums[k] = sum over rows of ( <a>_g (op) b )[k]  -- grade projection of the left operand
@@ -379,8 +380,8 @@ LCC_API lcc_status lcc_shard_reduce_fetch(lcc_shard_group *group, const lcc_alge
  *                        narrower than 128 bytes need 32x as many)
  *   "soa_tma_min_bytes"  SoA batches with at least this many bytes per operand do (default 8 GiB)
  *   "matrix_rep"         fixed-operand products / sandwiches of 128- and 256-blade algebras in the 16 x 16 matrix
- *                        representation (K8) where one exists: 1 (default) for f64 batches, 2 for f32 batches too,
- *                        0 never (always the nb x nb tensor-core GEMM, K6 / K6d)
+ *                        representation (K8) where one exists: 2 (default) for f64 and f32 batches, 1 for f64 batches
+ *                        only, 0 never (always the nb x nb tensor-core GEMM, K6 / K6d)
  *   "host_chunk_bytes"   chunk size of the host <-> device pipelines (default 64 MiB)
  *   "pinned_output_min_bytes"  to_numpy() results of at least this size come from the pinned host cache (default 1 MiB;
  *                        a very large value switches the cache off)

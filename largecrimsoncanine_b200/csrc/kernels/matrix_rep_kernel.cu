@@ -58,22 +58,28 @@ template <typename T> struct RepParams {
     uint32_t valid[8];    // bit s: a blade maps to string s
 };
 
+// signs and validity of the 16 strings of one string row, as bits (a thread works on one string row for the whole kernel)
+struct RowMask { uint32_t neg, valid; };
+
 // ---- packed arithmetic: an 8-byte element is a pair of f32 rows or one f64 row
 template <typename T> struct Elem;
 template <> struct Elem<float> {
     static __device__ __forceinline__ uint64_t add(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
     static __device__ __forceinline__ uint64_t sub(uint64_t a, uint64_t b) { uint64_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-    // sign / validity: both words are values
-    static __device__ __forceinline__ uint64_t mask(uint64_t v, uint2 m) {
-        const uint32_t lo = ((uint32_t)v & m.x) ^ m.y, hi = ((uint32_t)(v >> 32) & m.x) ^ m.y;
+    // sign (bit b of row.neg) / validity (bit b of row.valid, 128-blade algebras only): both words are values
+    template <bool HALF> static __device__ __forceinline__ uint64_t mask(uint64_t v, RowMask row, int b) {
+        const uint32_t m = (row.neg << (31 - b)) & 0x80000000u;
+        uint32_t lo = (uint32_t)v ^ m, hi = (uint32_t)(v >> 32) ^ m;
+        if (HALF && !((row.valid >> b) & 1u)) lo = hi = 0u;
         return ((uint64_t)hi << 32) | lo;
     }
 };
 template <> struct Elem<double> {
     static __device__ __forceinline__ uint64_t add(uint64_t a, uint64_t b) { return (uint64_t)__double_as_longlong(__longlong_as_double((long long)a) + __longlong_as_double((long long)b)); }
     static __device__ __forceinline__ uint64_t sub(uint64_t a, uint64_t b) { return (uint64_t)__double_as_longlong(__longlong_as_double((long long)a) - __longlong_as_double((long long)b)); }
-    static __device__ __forceinline__ uint64_t mask(uint64_t v, uint2 m) {  // the sign bit sits in the high word
-        const uint32_t lo = (uint32_t)v & m.x, hi = ((uint32_t)(v >> 32) & m.x) ^ m.y;
+    template <bool HALF> static __device__ __forceinline__ uint64_t mask(uint64_t v, RowMask row, int b) {  // the sign bit sits in the high word
+        uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32) ^ ((row.neg << (31 - b)) & 0x80000000u);
+        if (HALF && !((row.valid >> b) & 1u)) lo = hi = 0u;
         return ((uint64_t)hi << 32) | lo;
     }
 };
@@ -88,19 +94,20 @@ template <typename T> __device__ __forceinline__ void wht16(uint64_t (&v)[16]) {
 
 // Stage 1 (INPUT) / stage 3: the 16 slots of string row a at this thread's element, in place.  t0 = F(lin_hi(a)) ^ byte
 // offset of the element in its line; the slot of string (a, b) is at unit + (t0 ^ f_lo[b]) -- f_lo[b] is a constant-bank
-// operand, so an address is one XOR.  tbl_a = the 16 {and, xor} masks of the row (warp-broadcast loads).
-template <typename T, bool INPUT>
-__device__ __forceinline__ void transform_row(uint8_t *unit, uint32_t t0, const uint2 *tbl_a, const RepParams<T> &P) {
+// operand, so an address is one XOR.  tbl_a = sign / validity bits of the row's 16 strings.
+template <typename T, bool INPUT, bool HALF>
+__device__ __forceinline__ void transform_row(uint8_t *unit, uint32_t t0, RowMask tbl_a, const RepParams<T> &P) {
     uint64_t v[16];
+    asm volatile("" : "+r"(tbl_a.neg), "+r"(tbl_a.valid), "+r"(t0));  // keeps the 16 per-string masks and offsets from being hoisted out of the unit loop (registers)
 #pragma unroll
     for (int b = 0; b < 16; ++b) {
         v[b] = *reinterpret_cast<const uint64_t *>(unit + (t0 ^ P.f_lo[b]));
-        if (INPUT) v[b] = Elem<T>::mask(v[b], tbl_a[b]);
+        if (INPUT) v[b] = Elem<T>::template mask<HALF>(v[b], tbl_a, b);
     }
     wht16<T>(v);
 #pragma unroll
     for (int b = 0; b < 16; ++b) {
-        if (!INPUT) v[b] = Elem<T>::mask(v[b], tbl_a[b]);
+        if (!INPUT) v[b] = Elem<T>::template mask<HALF>(v[b], tbl_a, b);
         *reinterpret_cast<uint64_t *>(unit + (t0 ^ P.f_lo[b])) = v[b];
     }
 }
@@ -247,20 +254,21 @@ __device__ __forceinline__ uint32_t aos_row_term(int r) { return ((uint32_t)r <<
 
 // Stage 1 / 3: the 16 slots of string row a at row r -- f32: packed with row r + 16 (same a, same masks; R(r + 16) =
 // R(r) + 2048 for r < 16), f64: one row.  t0 = G(lin_hi(a)) ^ R(r).
-template <typename T, bool INPUT>
-__device__ __forceinline__ void transform_row_aos(uint8_t *unit, uint32_t t0, const uint2 *tbl_a, const RepParams<T> &P) {
+template <typename T, bool INPUT, bool HALF>
+__device__ __forceinline__ void transform_row_aos(uint8_t *unit, uint32_t t0, RowMask tbl_a, const RepParams<T> &P) {
     uint64_t v[16];
+    asm volatile("" : "+r"(tbl_a.neg), "+r"(tbl_a.valid), "+r"(t0));  // keeps the 16 per-string masks and offsets from being hoisted out of the unit loop (registers)
 #pragma unroll
     for (int b = 0; b < 16; ++b) {
         const uint8_t *p = unit + (t0 ^ P.f_lo[b]);
         if constexpr (sizeof(T) == 4) v[b] = (uint64_t) * reinterpret_cast<const uint32_t *>(p) | ((uint64_t) * reinterpret_cast<const uint32_t *>(p + 2048) << 32);
         else v[b] = *reinterpret_cast<const uint64_t *>(p);
-        if (INPUT) v[b] = Elem<T>::mask(v[b], tbl_a[b]);
+        if (INPUT) v[b] = Elem<T>::template mask<HALF>(v[b], tbl_a, b);
     }
     wht16<T>(v);
 #pragma unroll
     for (int b = 0; b < 16; ++b) {
-        if (!INPUT) v[b] = Elem<T>::mask(v[b], tbl_a[b]);
+        if (!INPUT) v[b] = Elem<T>::template mask<HALF>(v[b], tbl_a, b);
         uint8_t *p = unit + (t0 ^ P.f_lo[b]);
         if constexpr (sizeof(T) == 4) {
             *reinterpret_cast<uint32_t *>(p) = (uint32_t)v[b];
@@ -363,60 +371,52 @@ __device__ __forceinline__ void gemm_pass_aos(uint8_t *unit, const double2 *frag
 }
 
 // shared memory behind the ring: barriers, sign table, pass tables, factor fragments
-constexpr int kTblPitch = 17;  // entries per string row: the two rows a warp reads sit 136 bytes apart
-constexpr int kAuxBar = 0, kAuxSlot = 64, kAuxTbl = 128, kAuxTabs = kAuxTbl + 16 * kTblPitch * 8, kAuxFrag = kAuxTabs + 2 * 48 * 4, kAuxBytes = kAuxFrag + 2 * 4 * 32 * 16;
+constexpr int kAuxBar = 0, kAuxSlot = 64, kAuxTabs = 128, kAuxFrag = kAuxTabs + 2 * 48 * 4, kAuxBytes = kAuxFrag + 2 * 4 * 32 * 16;
 
 // NPASS 1: out = M x (column pass) or x M (row pass) -- the host chooses the tables; NPASS 2: out = R x ~R (column pass
 // with rho(R) / 16, row pass with rho(~R)).  NG groups of 8 warps.
-template <typename T, int NPASS, int NG, bool AOS>
+template <typename T, int NPASS, int NG, bool AOS, bool HALF>
 __global__ void __launch_bounds__(NG *kGroupThreads, 1)
 matrix_rep_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_out,
-                  const __grid_constant__ RepParams<T> P, int nb, int64_t n, int dbg, int order, unsigned long long *counter) {
+                  const __grid_constant__ RepParams<T> P, int nb, int64_t n, int dbg, unsigned int *counter) {
     constexpr int TR = 128 / (int)sizeof(T);
     using Frag = typename Factor<T>::Frag;
     extern __shared__ __align__(1024) uint8_t smem[];  // no static shared memory in this kernel: the window starts aligned
     uint8_t *aux = smem + (size_t)kRing * kUnitBytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(aux + kAuxBar);
     int *slot_row = reinterpret_cast<int *>(aux + kAuxSlot);  // first row of the unit in each ring slot, -1: no unit left
-    uint2 *tbl = reinterpret_cast<uint2 *>(aux + kAuxTbl);
     uint32_t *tabs = reinterpret_cast<uint32_t *>(aux + kAuxTabs);
     Frag *frag = reinterpret_cast<Frag *>(aux + kAuxFrag);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t units = (n + TR - 1) / TR;
+    const int units = (int)((n + TR - 1) / TR);
     const uint32_t box_bytes = (uint32_t)nb * 128u;
-    // Which units a CTA works on.  With a counter (the default for batches of more units than CTAs): the next unit is taken
-    // from a global counter whenever a ring slot is refilled -- SMs do not get the same share of the HBM bandwidth (two
-    // dies, different distances to the memory partitions), and with equal static shares the slowest SM sets the time: a
-    // pass-through ring moves 6.2 TB/s with static shares and 6.9-7.0 with the counter (scripts/tma_passthrough_probe.cu,
-    // profiles/r02_tma_passthrough_probe.jsonl).  Without one, order 0: unit k of this CTA is unit blockIdx.x + k * gridDim.x
-    // of the batch; order 1: every CTA owns one contiguous range of units.
-    const int64_t per_cta = (units + gridDim.x - 1) / gridDim.x;
-    const int64_t first = order ? (int64_t)blockIdx.x * per_cta : (int64_t)blockIdx.x;
-    const int64_t step = order ? 1 : (int64_t)gridDim.x;
-    const int64_t mine = order ? (first >= units ? 0 : (units - first < per_cta ? units - first : per_cta))
-                               : (units > blockIdx.x ? (units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
-    auto next_row = [&](int64_t k) -> int {  // first row of local unit k, or -1 when the batch is exhausted
-        if (counter) {
-            const int64_t u = (int64_t)atomicAdd(counter, 1ull);
-            return u < units ? (int)(u * TR) : -1;
-        }
-        return k < mine ? (int)((first + k * step) * TR) : -1;
+    // Which units a CTA works on: its first ring is static (unit blockIdx.x + k * gridDim.x in slot k); after that a TMA
+    // thread takes the next unit from a global counter whenever it refills a slot.  SMs do not get the same share of the HBM
+    // bandwidth (two dies, different distances to the memory partitions), and with equal static shares the slowest SM sets
+    // the time: a pass-through ring moves 6.2 TB/s with static shares and 6.9-7.0 with the counter
+    // (scripts/tma_passthrough_probe.cu, profiles/r02_tma_passthrough_probe.jsonl).  The thread asks one refill ahead, so
+    // the round trip of the atomic is off its group's critical path.  counter == nullptr (batches of at most one ring per
+    // CTA, LCC_K8_DYNAMIC=0): the static interleaved sequence goes on.
+    int pending = 0;
+    auto ask = [&]() { if (counter) pending = (int)gridDim.x * kRing + (int)atomicAdd(counter, 1u); };
+    auto next_row = [&](int k) -> int {  // first row of local unit k, or -1 when the batch is exhausted
+        int u = (int)blockIdx.x + k * (int)gridDim.x;
+        if (counter && k >= kRing) { u = pending; ask(); }
+        return u < units ? u * TR : -1;
     };
     if (threadIdx.x == 0) {
         for (int s = 0; s < kRing; ++s) tma::mbar_init(&full[s], 1);
         tma::prefetch_map(&map_x);
         tma::prefetch_map(&map_out);
     }
-    for (int s = threadIdx.x; s < 256; s += NG * kGroupThreads)
-        tbl[(s >> 4) * kTblPitch + (s & 15)] = make_uint2(((P.valid[s >> 5] >> (s & 31)) & 1u) ? 0xffffffffu : 0u, ((P.neg[s >> 5] >> (s & 31)) & 1u) ? 0x80000000u : 0u);
     if (threadIdx.x < 96) {
         const int p = threadIdx.x / 48, i = threadIdx.x % 48;
         tabs[threadIdx.x] = i < 16 ? P.fk[p][i] : (i < 32 ? P.cw[p][i - 16] : P.fo[p][i - 32]);
     }
     if (warp < NPASS) Factor<T>::build(frag + warp * 4 * 32, P.factor[warp], lane);
     __syncthreads();
-    auto load_slot = [&](int64_t k) {  // local unit k into ring slot k % kRing (TMA threads only)
-        const int rs = (int)(k % kRing), row = next_row(k);
+    auto load_slot = [&](int k) {  // local unit k into ring slot k % kRing (TMA threads only)
+        const int rs = k % kRing, row = next_row(k);
         slot_row[rs] = row;
         if (row >= 0) {
             tma::mbar_expect_tx(&full[rs], box_bytes);
@@ -425,8 +425,9 @@ matrix_rep_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         }
     };
     if (threadIdx.x == 0)
-        for (int64_t k = 0; k < kRing; ++k) load_slot(k);  // fill the ring
+        for (int k = 0; k < kRing; ++k) load_slot(k);  // fill the ring
     __syncthreads();  // slot_row of the first ring is visible to every group
+    if ((threadIdx.x & (kGroupThreads - 1)) == 0) ask();
     const int grp = warp >> 3, wl = warp & 7;
     const int gtid = threadIdx.x & (kGroupThreads - 1);
     auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kGroupThreads) : "memory"); };
@@ -436,10 +437,10 @@ matrix_rep_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const int a_phys = AOS ? 4 * (wl >> 1) + (lane >> 3) : 2 * wl + (lane >> 4);
     const int a_row = AOS ? (int)P.amap[a_phys] : a_phys;
     const uint32_t t0 = P.f_hi[a_phys] ^ (AOS ? aos_row_term(8 * (wl & 1) + (lane & 7)) : (uint32_t)((lane & 15) << 3));
-    const uint2 *tbl_a = tbl + a_row * kTblPitch;
+    const RowMask tbl_a = {(P.neg[a_row >> 1] >> ((a_row & 1) * 16)) & 0xffffu, (P.valid[a_row >> 1] >> ((a_row & 1) * 16)) & 0xffffu};
     // The group's first thread is also its TMA thread: it stores the group's finished unit and, one barrier into the
     // group's NEXT unit (by then the engine has read the slot), refills that slot with the unit kRing ahead.
-    int64_t stored = -1;
+    int stored = -1;
     auto refill = [&]() {
         if (gtid == 0 && stored >= 0) {
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -447,7 +448,7 @@ matrix_rep_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             stored = -1;
         }
     };
-    auto store_unit = [&](int64_t it, int s) {
+    auto store_unit = [&](int it, int s) {
         if (gtid == 0) {
             if (AOS) tma::store_3d(&map_out, smem + (size_t)s * kUnitBytes, 0, slot_row[s], 0);
             else tma::store_2d(&map_out, smem + (size_t)s * kUnitBytes, slot_row[s], 0);
@@ -455,8 +456,8 @@ matrix_rep_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             stored = it;
         }
     };
-    for (int64_t it = grp;; it += NG) {
-        const int s = (int)(it % kRing);
+    for (int it = grp;; it += NG) {
+        const int s = it % kRing;
         if (slot_row[s] < 0) break;  // units are dealt in increasing order: nothing comes after an empty slot
         const uint32_t ph = (uint32_t)((it / kRing) & 1);
         uint8_t *unit = smem + (size_t)s * kUnitBytes;
@@ -467,8 +468,8 @@ matrix_rep_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             store_unit(it, s);
             continue;
         }
-        if (AOS) transform_row_aos<T, true>(unit, t0, tbl_a, P);
-        else transform_row<T, true>(unit, t0, tbl_a, P);
+        if (AOS) transform_row_aos<T, true, HALF>(unit, t0, tbl_a, P);
+        else transform_row<T, true, HALF>(unit, t0, tbl_a, P);
         refill();      // the previous unit's store has long been read: put the next load in flight
         group_sync();
         if (dbg != 2) {  // LCC_K8_DEBUG=2: transforms only
@@ -479,8 +480,8 @@ matrix_rep_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 group_sync();
             }
         }
-        if (AOS) transform_row_aos<T, false>(unit, t0, tbl_a, P);
-        else transform_row<T, false>(unit, t0, tbl_a, P);
+        if (AOS) transform_row_aos<T, false, HALF>(unit, t0, tbl_a, P);
+        else transform_row<T, false, HALF>(unit, t0, tbl_a, P);
         tma::fence_proxy_async();
         group_sync();
         store_unit(it, s);
@@ -494,12 +495,11 @@ int rep_groups() {
     return g;
 }
 
-template <typename T, int NPASS, int NG, bool AOS>
-cudaError_t launch_rep_t(int nb, const void *x, int64_t ldx, void *out, int64_t ldo, int64_t n, const RepParams<T> &P, cudaStream_t s) {
+template <typename T, int NPASS, int NG, bool AOS, bool HALF>
+cudaError_t launch_rep_h(int nb, const void *x, int64_t ldx, void *out, int64_t ldo, int64_t n, const RepParams<T> &P, cudaStream_t s) {
     constexpr int TR = 128 / (int)sizeof(T);
     CUtensorMap mx, mo;
     static const int promo = [] { const char *e = getenv("LCC_K8_L2PROMO"); return e ? atoi(e) : 256; }();
-    static const int order = [] { const char *e = getenv("LCC_K8_ORDER"); return e ? atoi(e) : 1; }();
     static const bool swz = [] { const char *e = getenv("LCC_K8_SWIZZLE"); return !(e && e[0] == '0'); }();  // 0: only meaningful with LCC_K8_DEBUG=1
     if (AOS) {
         if (!make_aos_chunked_tensor_map(&mx, x, (int)sizeof(T), nb, ldx, n, TR) || !make_aos_chunked_tensor_map(&mo, out, (int)sizeof(T), nb, ldo, n, TR))
@@ -507,7 +507,7 @@ cudaError_t launch_rep_t(int nb, const void *x, int64_t ldx, void *out, int64_t 
     } else if (!make_soa_tensor_map(&mx, x, (int)sizeof(T), nb, ldx, n, TR, swz, promo) || !make_soa_tensor_map(&mo, out, (int)sizeof(T), nb, ldo, n, TR, swz, promo)) {
         return cudaErrorNotSupported;
     }
-    auto kernel = matrix_rep_kernel<T, NPASS, NG, AOS>;
+    auto kernel = matrix_rep_kernel<T, NPASS, NG, AOS, HALF>;
     constexpr int smem = kRing * kUnitBytes + kAuxBytes;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
@@ -515,27 +515,35 @@ cudaError_t launch_rep_t(int nb, const void *x, int64_t ldx, void *out, int64_t 
     const int64_t units = (n + TR - 1) / TR;
     const int grid = (int)(units < sm_count ? units : sm_count);
     static const int dbg = [] { const char *e = getenv("LCC_K8_DEBUG"); return e ? atoi(e) : 0; }();
-    // more units than CTAs: deal them out through a counter (stream-ordered scratch word, zeroed before the launch)
+    // more units than one ring per CTA: deal the rest out through a counter (stream-ordered scratch word, zeroed before the launch)
     static const bool dyn = [] { const char *e = getenv("LCC_K8_DYNAMIC"); return !(e && e[0] == '0'); }();
-    unsigned long long *counter = nullptr;
-    if (dyn && units > grid) {
-        e = cudaMallocAsync((void **)&counter, sizeof(unsigned long long), s);
+    unsigned int *counter = nullptr;
+    if (dyn && units > (int64_t)grid * kRing) {
+        e = cudaMallocAsync((void **)&counter, sizeof(unsigned int), s);
         if (e != cudaSuccess) return e;
-        e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s);
+        e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), s);
         if (e != cudaSuccess) { cudaFreeAsync(counter, s); return e; }
     }
-    kernel<<<grid, NG * kGroupThreads, smem, s>>>(mx, mo, P, nb, n, dbg, order, counter);
+    kernel<<<grid, NG * kGroupThreads, smem, s>>>(mx, mo, P, nb, n, dbg, counter);
     note_kernel_launch();
     e = cudaGetLastError();
     if (counter) cudaFreeAsync(counter, s);
     return e;
 }
 
-template <typename T> constexpr int default_groups() { return sizeof(T) == 4 ? 3 : 3; }
+template <typename T, int NPASS, int NG, bool AOS>
+cudaError_t launch_rep_t(int nb, const void *x, int64_t ldx, void *out, int64_t ldo, int64_t n, const RepParams<T> &P, cudaStream_t s) {
+    return nb == 128 ? launch_rep_h<T, NPASS, NG, AOS, true>(nb, x, ldx, out, ldo, n, P, s) : launch_rep_h<T, NPASS, NG, AOS, false>(nb, x, ldx, out, ldo, n, P, s);
+}
+
+// groups of 8 warps per CTA, measured at 2^24 rows of Cl(8,0,0) (profiles/r02_k8_v8_*): three groups are capped at 80
+// registers and spill a little; f32 5.78 ms with two groups against 5.93 with three (reference layout), 6.39 / 6.99
+// (blade-major); f64 11.37 / 11.02 (reference layout), 12.36 / 12.51 (blade-major)
+template <typename T, bool AOS> constexpr int default_groups() { return sizeof(T) == 8 && AOS ? 3 : 2; }
 
 template <typename T, bool AOS>
 cudaError_t launch_rep_p(int nb, int mode, const RepParams<T> &P, const ViewArg &x, const ViewArg &out, cudaStream_t s) {
-    const int ng = rep_groups() ? rep_groups() : default_groups<T>();
+    const int ng = rep_groups() ? rep_groups() : default_groups<T, AOS>();
     if (mode == 2)
         return ng == 2 ? launch_rep_t<T, 2, 2, AOS>(nb, x.data, x.ld, out.data, out.ld, x.n, P, s) : launch_rep_t<T, 2, 3, AOS>(nb, x.data, x.ld, out.data, out.ld, x.n, P, s);
     if (mode == 0 || mode == 1)

@@ -65,7 +65,7 @@ static int64_t env_or(const char *name, int64_t fallback) {
 }
 static std::atomic<int64_t> g_aos_tma_min_rows{env_or("LCC_AOS_TMA_MIN_ROWS", 4096)};
 static std::atomic<int64_t> g_soa_tma_min_bytes{env_or("LCC_SOA_TMA_MIN_BYTES", 8ll << 30)};
-static std::atomic<int64_t> g_matrix_rep{env_or("LCC_MATRIX_REP", 1)};
+static std::atomic<int64_t> g_matrix_rep{env_or("LCC_MATRIX_REP", 2)};
 // grid of the fused product + batch-sum kernel (kernels/launch_args.h); LCC_FUSED_SUM_BLOCKS overrides it for sweeps
 static int fused_sum_blocks() {
     static const int v = [] { const int64_t e = env_or("LCC_FUSED_SUM_BLOCKS", kFusedSumBlocks); return e >= 1 && e <= (1 << 20) ? (int)e : kFusedSumBlocks; }();
@@ -560,8 +560,8 @@ static void rep_matrix_of(const lcc_algebra *alg, const double *coeffs, double s
         for (int j = 0; j < 16; ++j) out[i * 16 + j] = scale * (transpose ? m[j * 16 + i] : m[i * 16 + j]);
 }
 
-// option "matrix_rep": 0 never, 1 (default) f64 batches, 2 f32 batches too.  Measured at 2^24 rows of Cl(8,0,0):
-// f64 K8 18.4 ms against 72.1 ms for the DMMA GEMM; f32 K8 9.9 ms against 9.0-9.4 ms for the tcgen05 GEMM, so f32 stays on the GEMM.
+// option "matrix_rep": 0 never, 1 f64 batches only, 2 (default) f32 batches too.  Measured at 2^24 rows of Cl(8,0,0) (DESIGN.md
+// section 5): f64 K8 11.0-12.4 ms against 72 ms for the DMMA GEMM; f32 K8 5.8-6.4 ms against 9.0-10.2 ms for the tcgen05 GEMM.
 static bool matrix_rep_usable(const lcc_algebra *alg, const lcc_view *x, bool strict) {
     const int64_t mode = g_matrix_rep.load(std::memory_order_relaxed);
     if (strict || mode == 0 || (x->dtype == LCC_F32 && mode < 2)) return false;

@@ -94,13 +94,13 @@ stage_k8_aos() {         # K8 on reference-layout units: parity, then f32 / f64 
     timeout 300 $PY bench.py --workload $wl --layout $lay --no-e2e --no-cpu --no-secondary --steps 10 > gpurun_out/k8_${wl}_$lay.json 2> gpurun_out/k8_${wl}_$lay.err
     echo "$wl $lay rc=$?"; summ gpurun_out/k8_${wl}_$lay.json
   done; done
-  for dbg in ${K8_DEBUG:-1 2}; do for wl in cl8_fixed_gp_rep cl8_fixed_gp_f64; do
+  for dbg in ${K8_DEBUG-1 2}; do for wl in cl8_fixed_gp_rep cl8_fixed_gp_f64; do
     LCC_K8_DEBUG=$dbg timeout 300 $PY bench.py --workload $wl --layout aos --no-e2e --no-cpu --no-secondary --no-parity --steps 10 > gpurun_out/k8_${wl}_aos_dbg$dbg.json 2> gpurun_out/k8_${wl}_aos_dbg$dbg.err
     echo "$wl aos debug=$dbg rc=$?"; summ gpurun_out/k8_${wl}_aos_dbg$dbg.json
   done; done
-  for g in 2; do for wl in cl8_fixed_gp_rep cl8_fixed_gp_f64; do
-    LCC_K8_GROUPS=$g timeout 300 $PY bench.py --workload $wl --layout aos --no-e2e --no-cpu --no-secondary --steps 10 > gpurun_out/k8_${wl}_aos_g$g.json 2> gpurun_out/k8_${wl}_aos_g$g.err
-    echo "$wl aos groups=$g rc=$?"; summ gpurun_out/k8_${wl}_aos_g$g.json
+  for lay in aos soa; do for wl in cl8_fixed_gp_rep cl8_fixed_gp_f64; do
+    LCC_K8_GROUPS=2 timeout 300 $PY bench.py --workload $wl --layout $lay --no-e2e --no-cpu --no-secondary --steps 10 > gpurun_out/k8_${wl}_${lay}_g2.json 2> gpurun_out/k8_${wl}_${lay}_g2.err
+    echo "$wl $lay groups=2 rc=$?"; summ gpurun_out/k8_${wl}_${lay}_g2.json
   done; done
 }
 stage_k8_mem() {         # K8 memory pipeline experiments: L2 promotion x unit order (pass-through and full), swizzle off (pass-through)

@@ -530,8 +530,7 @@ def test_block_diagonalised_fixed_operand_product_and_sandwich(L, sig, dt):
     alg, o = algebras(L, sig)
     nb, tol = o.num_blades, TOL[dt]
     rng = np.random.default_rng(1000 + nb + sig[1])
-    assert L.get_option("matrix_rep") == 1  # default: K8 for f64 batches only (f32 stays on the tcgen05 GEMM, which is as fast)
-    L.set_option("matrix_rep", 2)           # this test wants K8 for both precisions
+    assert L.get_option("matrix_rep") == 2  # default: K8 for both precisions
     for n in (64, 65, 4099, 40003):
         x = rng.standard_normal((n, nb)).astype(dt)
         m = rng.standard_normal((1, nb)).astype(dt)
@@ -557,7 +556,6 @@ def test_block_diagonalised_fixed_operand_product_and_sandwich(L, sig, dt):
     e = np.zeros((1, nb), dt)
     e[0, nb - 1] = 1.0
     got = L.MultivectorBatch.from_numpy(alg, e).geometric_product(X).to_numpy()
-    L.set_option("matrix_rep", 1)
     assert np.allclose(got, o.geometric_product(e.astype(np.float64), x64), rtol=0, atol=tol * np.abs(x64).max())
 
 
@@ -655,7 +653,7 @@ def test_block_diagonalised_product_on_reference_layout_units(L, sig, dt):
             for ptr in (px, po):
                 cabi.check(lib.lcc_device_free(ptr, None))
     finally:
-        L.set_option("matrix_rep", 1)
+        L.set_option("matrix_rep", 2)
 
 
 @pytest.mark.parametrize("sig", [(1, 3, 0), (3, 0, 1), (4, 1, 0), (2, 1, 1)])
