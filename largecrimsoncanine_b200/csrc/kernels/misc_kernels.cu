@@ -1038,9 +1038,13 @@ cudaError_t launch_norm(int nb, int mode, bool strict, const ViewArg &x, const i
     return by_dtype(x.dtype, [&] { run(float()); }, [&] { run(double()); });
 }
 
+static int sum_blocks_cap_aos() {  // LCC_SUM_AOS_BLOCKS: experiment knob for the row-major grid
+    static const int cap = [] { const char *e = std::getenv("LCC_SUM_AOS_BLOCKS"); const int v = e ? std::atoi(e) : 0; return v > 0 ? v : kSumBlocksMaxAos; }();
+    return cap;
+}
 static int sum_blocks(int64_t n, int layout) {
     int64_t b = (n + (int64_t)kThreads * 16 - 1) / ((int64_t)kThreads * 16);
-    const int64_t cap = layout == kSoA ? kSumBlocksMax : kSumBlocksMaxAos;
+    const int64_t cap = layout == kSoA ? kSumBlocksMax : sum_blocks_cap_aos();
     if (b < 1) b = 1;
     if (b > cap) b = cap;
     return (int)b;
@@ -1072,8 +1076,8 @@ cudaError_t launch_sum(int nb, const ViewArg &x, void *sums_dev, void *scratch_d
                 return sms * occ;
             }();
             int grid = nblocks;
-            if (nblocks == kSumBlocksMaxAos && wave <= kSumBlocksMaxAos) {
-                grid = kSumBlocksMaxAos / wave * wave;
+            if (nblocks == sum_blocks_cap_aos() && wave <= nblocks) {
+                grid = nblocks / wave * wave;
                 rows_per_block = ((n + grid - 1) / grid + 3) & ~(int64_t)3;
             }
             sum_partial_aos_vec<T><<<grid, kThreads, 0, s>>>((const T *)x.data, x.ld, n, nb, ilog2(cpr), rows_per_block, (double *)scratch_dev);

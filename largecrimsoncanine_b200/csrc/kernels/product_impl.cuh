@@ -934,6 +934,49 @@ __host__ __device__ constexpr bool reverse_negative(int blade) {
     return (g % 4) >= 2;  // blades.rs:128-135
 }
 
+// The two stages on register tiles.  EVEN: the odd-grade coefficients of R are known to be zero (rotors, motors), their
+// terms are pruned at compile time -- half of both products; pruned terms would only have added +-0.
+template <bool STRICT, bool EVEN, int V, class SinkT>
+static __device__ __forceinline__ void sandwich_rows_body(const Tile<real, NB, V> &R, const Tile<real, NB, V> &X, SinkT &sink, const Coeffs &mu) {
+    Tile<real, NB, V> RX;
+    (void)mu;
+#define LCC_OUT_BEGIN(k) { real acc[V]; _Pragma("unroll") for (int l = 0; l < V; ++l) acc[l] = real(0);
+#define LCC_TERM(k, i, j, neg, flags)                                                                   \
+    if constexpr (!EVEN || even_grade(i)) {                                                            \
+        _Pragma("unroll") for (int l = 0; l < V; ++l) {                                                \
+            real rv = (neg) ? -R.v[i][l] : R.v[i][l];                                                  \
+            if constexpr (kRuntimeMetric) rv = mul_rn(rv, mu.v[(i) & (j)]);                            \
+            acc[l] = Arith<STRICT>::madd(rv, X.v[j][l], acc[l]);                                       \
+        }                                                                                              \
+    }
+#define LCC_OUT_END(k) _Pragma("unroll") for (int l = 0; l < V; ++l) RX.v[k][l] = acc[l]; }
+#include LCC_TERMS_FILE
+#undef LCC_TERM
+#undef LCC_OUT_END
+#define LCC_TERM(k, i, j, neg, flags)                                                                   \
+    if constexpr (!EVEN || even_grade(j)) {                                                            \
+        _Pragma("unroll") for (int l = 0; l < V; ++l) {                                                \
+            real av = (neg) ? -RX.v[i][l] : RX.v[i][l];                                                \
+            if constexpr (kRuntimeMetric) av = mul_rn(av, mu.v[(i) & (j)]);                            \
+            const real rv = reverse_negative(j) ? -R.v[j][l] : R.v[j][l];                              \
+            acc[l] = Arith<STRICT>::madd(av, rv, acc[l]);                                              \
+        }                                                                                              \
+    }
+#define LCC_OUT_END(k) sink.template put<k>(acc); }
+#include LCC_TERMS_FILE
+#undef LCC_OUT_BEGIN
+#undef LCC_TERM
+#undef LCC_OUT_END
+}
+// one DEVICE rotor for the whole batch: is it even?  (every thread holds the same row, so the branch is uniform)
+template <int V> static __device__ __forceinline__ bool bcast_rotor_is_even(const Tile<real, NB, V> &R) {
+    bool even = true;
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+        if (!even_grade(i)) even = even && (R.v[i][0] == real(0));
+    return even;
+}
+
 template <int LAYOUT, bool STRICT>
 __global__ void __launch_bounds__(kThreads)
 sandwich_rows_kernel(const real *__restrict__ r, int64_t ldr, int r_bcast, const real *__restrict__ x, int64_t ldx,
@@ -941,34 +984,12 @@ sandwich_rows_kernel(const real *__restrict__ r, int64_t ldr, int r_bcast, const
     constexpr int V = LAYOUT == kSoA ? kRowsSoA : 1;
     const int64_t r0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
     if (r0 >= n) return;
-    Tile<real, NB, V> R, X, RX;
+    Tile<real, NB, V> R, X;
     if constexpr (LAYOUT == kSoA) { load_soa(R, r, ldr, r0, r_bcast != 0); load_soa(X, x, ldx, r0, false); }
     else { load_aos(R, r, ldr, r0, r_bcast != 0, vec_ok != 0); load_aos(X, x, ldx, r0, false, vec_ok != 0); }
-    (void)mu;
-#define LCC_OUT_BEGIN(k) { real acc[V]; _Pragma("unroll") for (int l = 0; l < V; ++l) acc[l] = real(0);
-#define LCC_TERM(k, i, j, neg, flags)                                                                   \
-    _Pragma("unroll") for (int l = 0; l < V; ++l) {                                                    \
-        real rv = (neg) ? -R.v[i][l] : R.v[i][l];                                                      \
-        if constexpr (kRuntimeMetric) rv = mul_rn(rv, mu.v[(i) & (j)]);                                \
-        acc[l] = Arith<STRICT>::madd(rv, X.v[j][l], acc[l]);                                           \
-    }
-#define LCC_OUT_END(k) _Pragma("unroll") for (int l = 0; l < V; ++l) RX.v[k][l] = acc[l]; }
-#include LCC_TERMS_FILE
-#undef LCC_TERM
-#undef LCC_OUT_END
     Sink<LAYOUT, V> sink{out, ldo, r0, vec_ok != 0, {}};
-#define LCC_TERM(k, i, j, neg, flags)                                                                   \
-    _Pragma("unroll") for (int l = 0; l < V; ++l) {                                                    \
-        real av = (neg) ? -RX.v[i][l] : RX.v[i][l];                                                    \
-        if constexpr (kRuntimeMetric) av = mul_rn(av, mu.v[(i) & (j)]);                                \
-        const real rv = reverse_negative(j) ? -R.v[j][l] : R.v[j][l];                                  \
-        acc[l] = Arith<STRICT>::madd(av, rv, acc[l]);                                                  \
-    }
-#define LCC_OUT_END(k) sink.template put<k>(acc); }
-#include LCC_TERMS_FILE
-#undef LCC_OUT_BEGIN
-#undef LCC_TERM
-#undef LCC_OUT_END
+    if (r_bcast && bcast_rotor_is_even(R)) sandwich_rows_body<STRICT, true, V>(R, X, sink, mu);
+    else sandwich_rows_body<STRICT, false, V>(R, X, sink, mu);
 }
 
 // the same on TMA-staged AoS tiles (two input tiles; the result overwrites the x tile and leaves by TMA store)
@@ -987,36 +1008,14 @@ sandwich_rows_kernel_aos_tma(const __grid_constant__ CUtensorMap map_r, const __
         tma_load_tile(tile_x, &map_x, bar, row0, mu.stream_hint != 0);
     }
     __syncthreads();
-    Tile<real, NB, 1> R, X, RX;
+    Tile<real, NB, 1> R, X;
     if (r_row) load_bcast_row(R, r_row);
     tma::mbar_wait(bar, 0);
     if (!r_row) load_tile_row(R, tile_r, t);
     load_tile_row(X, tile_x, t);
-    (void)mu;
-#define LCC_OUT_BEGIN(k) { real acc[1]; acc[0] = real(0);
-#define LCC_TERM(k, i, j, neg, flags)                                                                   \
-    {                                                                                                  \
-        real rv = (neg) ? -R.v[i][0] : R.v[i][0];                                                      \
-        if constexpr (kRuntimeMetric) rv = mul_rn(rv, mu.v[(i) & (j)]);                                \
-        acc[0] = Arith<STRICT>::madd(rv, X.v[j][0], acc[0]);                                           \
-    }
-#define LCC_OUT_END(k) RX.v[k][0] = acc[0]; }
-#include LCC_TERMS_FILE
-#undef LCC_TERM
-#undef LCC_OUT_END
     TileSink sink{tile_x, t, {}};
-#define LCC_TERM(k, i, j, neg, flags)                                                                   \
-    {                                                                                                  \
-        real av = (neg) ? -RX.v[i][0] : RX.v[i][0];                                                    \
-        if constexpr (kRuntimeMetric) av = mul_rn(av, mu.v[(i) & (j)]);                                \
-        const real rv = reverse_negative(j) ? -R.v[j][0] : R.v[j][0];                                  \
-        acc[0] = Arith<STRICT>::madd(av, rv, acc[0]);                                                  \
-    }
-#define LCC_OUT_END(k) sink.template put<k>(acc); }
-#include LCC_TERMS_FILE
-#undef LCC_OUT_BEGIN
-#undef LCC_TERM
-#undef LCC_OUT_END
+    if (r_row && bcast_rotor_is_even(R)) sandwich_rows_body<STRICT, true, 1>(R, X, sink, mu);
+    else sandwich_rows_body<STRICT, false, 1>(R, X, sink, mu);
     tma::fence_proxy_async();
     __syncthreads();
     if (t == 0) {

@@ -80,9 +80,9 @@ def test_two_ranks_share_the_unique_id_over_gloo():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=120) for _ in procs]
+    results = [q.get(timeout=900) for _ in procs]  # a cold `import torch` in a spawned worker can take minutes right after a build
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=300)
         assert p.exitcode == 0
     assert all(same and only_rank0 for _, same, only_rank0, _ in results)
     assert sum(rows for _, _, _, rows in results) == 1001
