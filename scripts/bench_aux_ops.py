@@ -61,6 +61,13 @@ def run(sig, dt, log2n):
             r1 = cabi.view(b.data_ptr(), 1, b.stride(0) if layout == cabi.LCC_SOA else nb, code, layout)
             cases["sandwich_rows"] = (3 * nb * es, lambda: cabi.check(lib.lcc_batch_sandwich_rows(alg.h, C.byref(vb), C.byref(va), C.byref(vo), 0, sptr)))
             cases["sandwich_rows_bcast"] = (2 * nb * es, lambda: cabi.check(lib.lcc_batch_sandwich_rows(alg.h, C.byref(r1), C.byref(va), C.byref(vo), 0, sptr)))
+            # the usual case: the one rotor is an even versor (rotor / motor) -- its odd-grade coefficients are zero, which the
+            # kernel tests once per thread and then runs the pruned term lists
+            rot = torch.randn(nb, device=dev, dtype=tdt)
+            rot[[k for k in range(nb) if bin(k).count("1") % 2]] = 0
+            keep_rot = rot.reshape(nb, 1).repeat(1, 4).contiguous() if layout == cabi.LCC_SOA else rot.reshape(1, nb).contiguous()
+            r2 = cabi.view(keep_rot.data_ptr(), 1, 4 if layout == cabi.LCC_SOA else nb, code, layout)
+            cases["sandwich_rows_bcast_even"] = (2 * nb * es, lambda: cabi.check(lib.lcc_batch_sandwich_rows(alg.h, C.byref(r2), C.byref(va), C.byref(vo), 0, sptr)))
         if alg.r == 0:
             cases["dual"] = (2 * nb * es, lambda: cabi.check(lib.lcc_batch_unary(alg.h, cabi.LCC_UN_DUAL, 0, C.byref(va), C.byref(vo), sptr)))
         for name, (bytes_per, fn) in cases.items():
