@@ -378,7 +378,7 @@ constexpr int kAuxBar = 0, kAuxSlot = 64, kAuxTabs = 128, kAuxFrag = kAuxTabs + 
 template <typename T, int NPASS, int NG, bool AOS, bool HALF>
 __global__ void __launch_bounds__(NG *kGroupThreads, 1)
 matrix_rep_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_out,
-                  const __grid_constant__ RepParams<T> P, int nb, int64_t n, int dbg, unsigned int *counter) {
+                  const __grid_constant__ RepParams<T> P, int nb, int64_t n, int dbg, unsigned int *counter, const T *__restrict__ factor_dev) {
     constexpr int TR = 128 / (int)sizeof(T);
     using Frag = typename Factor<T>::Frag;
     extern __shared__ __align__(1024) uint8_t smem[];  // no static shared memory in this kernel: the window starts aligned
@@ -413,7 +413,9 @@ matrix_rep_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         const int p = threadIdx.x / 48, i = threadIdx.x % 48;
         tabs[threadIdx.x] = i < 16 ? P.fk[p][i] : (i < 32 ? P.cw[p][i - 16] : P.fo[p][i - 32]);
     }
-    if (warp < NPASS) Factor<T>::build(frag + warp * 4 * 32, P.factor[warp], lane);
+    // the fixed factor comes with the parameters (operand known on the host) or from a device buffer a builder kernel
+    // filled from a device-resident operand (no host read-back)
+    if (warp < NPASS) Factor<T>::build(frag + warp * 4 * 32, factor_dev ? factor_dev + warp * 256 : P.factor[warp], lane);
     __syncthreads();
     auto load_slot = [&](int k) {  // local unit k into ring slot k % kRing (TMA threads only)
         const int rs = k % kRing, row = next_row(k);
@@ -496,7 +498,7 @@ int rep_groups() {
 }
 
 template <typename T, int NPASS, int NG, bool AOS, bool HALF>
-cudaError_t launch_rep_h(int nb, const void *x, int64_t ldx, void *out, int64_t ldo, int64_t n, const RepParams<T> &P, cudaStream_t s) {
+cudaError_t launch_rep_h(int nb, const void *x, int64_t ldx, void *out, int64_t ldo, int64_t n, const RepParams<T> &P, const T *factor_dev, cudaStream_t s) {
     constexpr int TR = 128 / (int)sizeof(T);
     CUtensorMap mx, mo;
     static const int promo = [] { const char *e = getenv("LCC_K8_L2PROMO"); return e ? atoi(e) : 256; }();
@@ -524,7 +526,7 @@ cudaError_t launch_rep_h(int nb, const void *x, int64_t ldx, void *out, int64_t 
         e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), s);
         if (e != cudaSuccess) { cudaFreeAsync(counter, s); return e; }
     }
-    kernel<<<grid, NG * kGroupThreads, smem, s>>>(mx, mo, P, nb, n, dbg, counter);
+    kernel<<<grid, NG * kGroupThreads, smem, s>>>(mx, mo, P, nb, n, dbg, counter, factor_dev);
     note_kernel_launch();
     e = cudaGetLastError();
     if (counter) cudaFreeAsync(counter, s);
@@ -532,8 +534,9 @@ cudaError_t launch_rep_h(int nb, const void *x, int64_t ldx, void *out, int64_t 
 }
 
 template <typename T, int NPASS, int NG, bool AOS>
-cudaError_t launch_rep_t(int nb, const void *x, int64_t ldx, void *out, int64_t ldo, int64_t n, const RepParams<T> &P, cudaStream_t s) {
-    return nb == 128 ? launch_rep_h<T, NPASS, NG, AOS, true>(nb, x, ldx, out, ldo, n, P, s) : launch_rep_h<T, NPASS, NG, AOS, false>(nb, x, ldx, out, ldo, n, P, s);
+cudaError_t launch_rep_t(int nb, const void *x, int64_t ldx, void *out, int64_t ldo, int64_t n, const RepParams<T> &P, const T *factor_dev, cudaStream_t s) {
+    return nb == 128 ? launch_rep_h<T, NPASS, NG, AOS, true>(nb, x, ldx, out, ldo, n, P, factor_dev, s)
+                     : launch_rep_h<T, NPASS, NG, AOS, false>(nb, x, ldx, out, ldo, n, P, factor_dev, s);
 }
 
 // groups of 8 warps per CTA, measured at 2^24 rows of Cl(8,0,0) (profiles/r02_k8_v8_*): three groups are capped at 80
@@ -542,22 +545,45 @@ cudaError_t launch_rep_t(int nb, const void *x, int64_t ldx, void *out, int64_t 
 template <typename T, bool AOS> constexpr int default_groups() { return sizeof(T) == 8 && AOS ? 3 : 2; }
 
 template <typename T, bool AOS>
-cudaError_t launch_rep_p(int nb, int mode, const RepParams<T> &P, const ViewArg &x, const ViewArg &out, cudaStream_t s) {
+cudaError_t launch_rep_p(int nb, int mode, const RepParams<T> &P, const T *factor_dev, const ViewArg &x, const ViewArg &out, cudaStream_t s) {
     const int ng = rep_groups() ? rep_groups() : default_groups<T, AOS>();
     if (mode == 2)
-        return ng == 2 ? launch_rep_t<T, 2, 2, AOS>(nb, x.data, x.ld, out.data, out.ld, x.n, P, s) : launch_rep_t<T, 2, 3, AOS>(nb, x.data, x.ld, out.data, out.ld, x.n, P, s);
+        return ng == 2 ? launch_rep_t<T, 2, 2, AOS>(nb, x.data, x.ld, out.data, out.ld, x.n, P, factor_dev, s)
+                       : launch_rep_t<T, 2, 3, AOS>(nb, x.data, x.ld, out.data, out.ld, x.n, P, factor_dev, s);
     if (mode == 0 || mode == 1)
-        return ng == 2 ? launch_rep_t<T, 1, 2, AOS>(nb, x.data, x.ld, out.data, out.ld, x.n, P, s) : launch_rep_t<T, 1, 3, AOS>(nb, x.data, x.ld, out.data, out.ld, x.n, P, s);
+        return ng == 2 ? launch_rep_t<T, 1, 2, AOS>(nb, x.data, x.ld, out.data, out.ld, x.n, P, factor_dev, s)
+                       : launch_rep_t<T, 1, 3, AOS>(nb, x.data, x.ld, out.data, out.ld, x.n, P, factor_dev, s);
     return cudaErrorInvalidValue;
 }
 
+// rho(M) / 16 (or its transpose) of a DEVICE-resident operand M, written in the MMA's physical m / k order:
+// rho(M)[j ^ a][j] = sum_b (-1)^popcount(b & j) sign(a, b) M[blade(a, b)]   (csrc/matrix_rep.hpp).  One thread per entry.
+struct RepTables { uint8_t blade_at[256]; int8_t sign_at[256]; uint8_t omap[16], kmap[16]; };
 template <typename T>
-cudaError_t launch_rep(int nb, int mode, const double *p1, const double *p2, const uint8_t *blade_at, const int8_t *sign_at,
-                       const ViewArg &x, const ViewArg &out, cudaStream_t s) {
+__global__ void build_rep_factor_kernel(const T *__restrict__ m, int64_t m_stride, const __grid_constant__ RepTables tb, int transpose, T *__restrict__ factor) {
+    const int mi = threadIdx.x >> 4, ki = threadIdx.x & 15;
+    const int o = tb.omap[mi], k = tb.kmap[ki];
+    const int i = transpose ? k : o, j = transpose ? o : k;
+    const int a = i ^ j;
+    double acc = 0.0;
+    for (int b = 0; b < 16; ++b) {
+        const int str = (a << 4) | b, sg = tb.sign_at[str];
+        if (sg == 0) continue;
+        const double v = (double)m[(int64_t)tb.blade_at[str] * m_stride];
+        acc += ((__popc(b & j) & 1) != 0) == (sg > 0) ? -v : v;
+    }
+    factor[mi * 16 + ki] = (T)(acc * (1.0 / 16.0));
+}
+
+template <typename T>
+cudaError_t launch_rep(int nb, int mode, const double *p1, const double *p2, const void *m_dev, int64_t m_stride, const uint8_t *blade_at,
+                       const int8_t *sign_at, const ViewArg &x, const ViewArg &out, cudaStream_t s) {
     const RepLayout L = make_rep_layout(blade_at, sign_at);
     const bool aos = x.layout == kAoS;
     RepParams<T> P;
     const double *fac[2] = {p1, p2};
+    RepTables tb;
+    for (int i = 0; i < 256; ++i) { tb.blade_at[i] = blade_at[i]; tb.sign_at[i] = sign_at[i]; }
     // mode 0: column pass with p1; mode 1: row pass with p1; mode 2: column pass with p1, row pass with p2
     if (aos) {
         const RepLayoutAos A = make_rep_layout_aos(L, (int)sizeof(T));
@@ -570,7 +596,7 @@ cudaError_t launch_rep(int nb, int mode, const double *p1, const double *p2, con
                 P.fo[p][i] = pass[p]->fo[i];
                 for (int k = 0; k < 16; ++k) P.factor[p][i * 16 + k] = fac[p] ? (T)fac[p][pass[p]->omap[i] * 16 + pass[p]->kmap[k]] : T(0);
             }
-        for (int i = 0; i < 16; ++i) { P.f_lo[i] = A.g_lo[i]; P.f_hi[i] = A.g_hi[i]; P.amap[i] = A.amap[i]; }
+        for (int i = 0; i < 16; ++i) { P.f_lo[i] = A.g_lo[i]; P.f_hi[i] = A.g_hi[i]; P.amap[i] = A.amap[i]; tb.omap[i] = pass[0]->omap[i]; tb.kmap[i] = pass[0]->kmap[i]; }
     } else {
         if (!L.ok) return cudaErrorNotSupported;
         const RepPass *pass[2] = {mode == 1 ? &L.row : &L.column, &L.row};
@@ -580,29 +606,40 @@ cudaError_t launch_rep(int nb, int mode, const double *p1, const double *p2, con
                 P.cw[p][i] = pass[p]->cw[i];
                 for (int k = 0; k < 16; ++k) P.factor[p][i * 16 + k] = fac[p] ? (T)fac[p][pass[p]->kmap[i] * 16 + pass[p]->kmap[k]] : T(0);
             }
-        for (int i = 0; i < 16; ++i) { P.f_lo[i] = L.f_lo[i]; P.f_hi[i] = L.f_hi[i]; P.amap[i] = (uint32_t)i; }
+        for (int i = 0; i < 16; ++i) { P.f_lo[i] = L.f_lo[i]; P.f_hi[i] = L.f_hi[i]; P.amap[i] = (uint32_t)i; tb.omap[i] = tb.kmap[i] = pass[0]->kmap[i]; }
     }
     for (int i = 0; i < 8; ++i) P.neg[i] = P.valid[i] = 0;
     for (int str = 0; str < 256; ++str) {
         if (sign_at[str] != 0) P.valid[str >> 5] |= 1u << (str & 31);
         if (sign_at[str] < 0) P.neg[str >> 5] |= 1u << (str & 31);
     }
-    return aos ? launch_rep_p<T, true>(nb, mode, P, x, out, s) : launch_rep_p<T, false>(nb, mode, P, x, out, s);
+    T *factor_dev = nullptr;
+    if (m_dev) {  // device-resident operand (mode 0: fixed * x, mode 1: x * fixed): the factor is built on the device
+        if (mode != 0 && mode != 1) return cudaErrorInvalidValue;
+        cudaError_t e = cudaMallocAsync((void **)&factor_dev, 256 * sizeof(T), s);
+        if (e != cudaSuccess) return e;
+        build_rep_factor_kernel<T><<<1, 256, 0, s>>>((const T *)m_dev, m_stride, tb, mode == 1 ? 1 : 0, factor_dev);
+        note_kernel_launch();
+    }
+    const cudaError_t e = aos ? launch_rep_p<T, true>(nb, mode, P, factor_dev, x, out, s) : launch_rep_p<T, false>(nb, mode, P, factor_dev, x, out, s);
+    if (factor_dev) cudaFreeAsync(factor_dev, s);
+    return e;
 }
 
 }  // namespace
 
 // K8 launcher.  mode 0 / 1 / 2 = left product, right product, sandwich; p1 (and p2 for the sandwich) are row-major 16 x 16
 // f64 factors in the orientation the MMA contracts ([o][k]: mode 0 rho(M) / 16, mode 1 rho(M)^T / 16, mode 2 rho(R) / 16 and
-// rho(~R)^T); blade_at / sign_at map a string to its blade and sign.  x and out are views of nb = 128 or 256 blades in ONE
+// rho(~R)^T) -- or, for modes 0 / 1, m_dev: the fixed operand itself as a device row of the batch dtype (element k at
+// m_dev[k * m_stride]), from which a one-block kernel builds the factor; blade_at / sign_at map a string to its blade and sign.  x and out are views of nb = 128 or 256 blades in ONE
 // layout: blade-major (SoA) with a row count that is a multiple of 16 bytes (TMA stores clip at that granularity), or the
 // reference's row-major (AoS) layout with any row count -- whole rows are contiguous there, and a unit is one 16-32 KB span.
 cudaError_t launch_matrix_rep_product(int nb, int mode, const double *p1, const double *p2, const uint8_t *blade_at, const int8_t *sign_at,
-                                      const ViewArg &x, const ViewArg &out, cudaStream_t s) {
+                                      const ViewArg &x, const ViewArg &out, cudaStream_t s, const void *m_dev, int64_t m_stride) {
     if (x.n <= 0) return cudaSuccess;
     if (x.layout != out.layout || (nb != 128 && nb != 256)) return cudaErrorNotSupported;
-    return x.dtype == kF32 ? launch_rep<float>(nb, mode, p1, p2, blade_at, sign_at, x, out, s)
-                           : launch_rep<double>(nb, mode, p1, p2, blade_at, sign_at, x, out, s);
+    return x.dtype == kF32 ? launch_rep<float>(nb, mode, p1, p2, m_dev, m_stride, blade_at, sign_at, x, out, s)
+                           : launch_rep<double>(nb, mode, p1, p2, m_dev, m_stride, blade_at, sign_at, x, out, s);
 }
 
 }  // namespace lcc

@@ -55,7 +55,7 @@ cudaError_t launch_matrix_product_f64_dmma(int nb, const double *wt64, const Vie
 // 128 / 256-blade algebras in their 16 x 16 matrix representation: two Walsh-Hadamard passes + 16^3 FMAs per row instead
 // of the nb^2 GEMM, HBM-bound.  p1 / p2: 16 x 16 f64 factors as the kernel indexes them; SoA views, n * sizeof(T) % 16 == 0.
 cudaError_t launch_matrix_rep_product(int nb, int mode, const double *p1, const double *p2, const uint8_t *blade_at, const int8_t *sign_at,
-                                      const ViewArg &x, const ViewArg &out, cudaStream_t s);
+                                      const ViewArg &x, const ViewArg &out, cudaStream_t s, const void *m_dev = nullptr, int64_t m_stride = 1);
 // PGA3D / CGA3D point embeddings and extractors (src/pga.rs:131-134,579-599; src/cga.rs:189-206,492-508);
 // which 2 / 3: STA bivectors from (E,B) and boost rotors from velocities (src/sta.rs:202-212,253-296)
 cudaError_t launch_points_embed(int which, const void *xyz, const ViewArg &dst, cudaStream_t s);

@@ -572,9 +572,12 @@ static bool matrix_rep_usable(const lcc_algebra *alg, const lcc_view *x, bool st
 // through pool temporaries; for blade-major views the rows up to the last multiple of 16 bytes (TMA stores clip there) --
 // *rows_done tells the caller where its exact kernels have to pick up the 1-3 that remain.
 static lcc_status matrix_rep_apply(const lcc_algebra *alg, int mode, const double *p1, const double *p2, const lcc_view *x,
-                                   const lcc_view *out, cudaStream_t s, int64_t *rows_done) {
+                                   const lcc_view *out, cudaStream_t s, int64_t *rows_done, const lcc_view *fixed_dev = nullptr) {
     *rows_done = 0;
     const int nb = alg->nb;
+    // fixed_dev: the fixed operand as a one-row DEVICE view (modes 0 / 1) -- K8 builds its factor on the device, no read-back
+    const void *m_dev = fixed_dev ? fixed_dev->data : nullptr;
+    const int64_t m_stride = fixed_dev && fixed_dev->layout == LCC_SOA ? fixed_dev->ld : 1;
     const int64_t w = 16 / (int64_t)elem_size(x->dtype);
     PoolBuffer tin, tout;
     lcc_view sx = *x, so = *out;
@@ -582,7 +585,7 @@ static lcc_status matrix_rep_apply(const lcc_algebra *alg, int mode, const doubl
     // traffic against 4.6 for the 128-byte pieces of a blade-major unit, profiles/r02_tma_passthrough_probe.jsonl)
     static const bool aos_direct = [] { const char *e = getenv("LCC_K8_AOS"); return !(e && e[0] == '0'); }();
     if (aos_direct && x->layout == LCC_AOS && out->layout == LCC_AOS) {
-        const cudaError_t e = launch_matrix_rep_product(nb, mode, p1, p2, alg->rep_blade_at.data(), alg->rep_sign_at.data(), arg_of(x), arg_of(out), s);
+        const cudaError_t e = launch_matrix_rep_product(nb, mode, p1, p2, alg->rep_blade_at.data(), alg->rep_sign_at.data(), arg_of(x), arg_of(out), s, m_dev, m_stride);
         if (e != cudaErrorNotSupported) {
             LCC_CUDA(e);
             *rows_done = x->n;
@@ -598,7 +601,7 @@ static lcc_status matrix_rep_apply(const lcc_algebra *alg, int mode, const doubl
         sx.n = so.n = x->n - x->n % w;
     }
     if (sx.n > 0) {
-        const cudaError_t e = launch_matrix_rep_product(nb, mode, p1, p2, alg->rep_blade_at.data(), alg->rep_sign_at.data(), arg_of(&sx), arg_of(&so), s);
+        const cudaError_t e = launch_matrix_rep_product(nb, mode, p1, p2, alg->rep_blade_at.data(), alg->rep_sign_at.data(), arg_of(&sx), arg_of(&so), s, m_dev, m_stride);
         if (e == cudaErrorNotSupported) return LCC_OK;
         LCC_CUDA(e);
     }
@@ -654,6 +657,20 @@ static lcc_status run_product(const lcc_algebra *alg, int op, const lcc_view *a,
     // cores -- K6 (tcgen05, 3xTF32) for f32, K6d (FP64 tensor pipe) for f64; AoS views are transposed through pool
     // temporaries.  Strict mode, and views the kernels cannot take, keep the exact-order table kernel below.
     const bool fixed_operand = (a_bc != b_bc) && (alg->nb == 64 || alg->nb == 128 || alg->nb == 256);
+    // geometric product against ONE device-resident operand in an algebra with a real 16 x 16 matrix representation: K8,
+    // its 16 x 16 factor built from the device row by a one-block kernel (what lcc.torch passes: no host copy of the operand)
+    if (op == kOpGP && fixed_operand && !tensor_path_off() && a->layout == out->layout && b->layout == out->layout) {
+        const lcc_view *fixed = a_bc ? a : b, *batch = a_bc ? b : a;
+        if (matrix_rep_usable(alg, batch, strict)) {
+            int64_t rows_done = 0;
+            LCC_TRY(matrix_rep_apply(alg, a_bc ? 0 : 1, nullptr, nullptr, batch, out, s, &rows_done, fixed));
+            if (rows_done == n) return LCC_OK;
+            if (rows_done > 0) {  // blade-major views: the last 1-3 rows (TMA stores clip at 16 bytes) take the exact kernels
+                const lcc_view bt = tail_view(batch, rows_done), ot = tail_view(out, rows_done);
+                return run_product(alg, op, a_bc ? a : &bt, a_bc ? &bt : b, &ot, nullptr, flags, stream);
+            }
+        }
+    }
     auto tensor_one = [&](int single_op, const lcc_view *dst, bool *handled) -> lcc_status {
         *handled = false;
         if (tensor_path_off() || strict || !fixed_operand) return LCC_OK;

@@ -646,6 +646,40 @@ def test_block_diagonalised_product_on_reference_layout_units(L, sig, dt):
             cabi.check(lib.lcc_batch_fixed_product(alg.h, cabi.LCC_OP_GP, 1, fptr, C.byref(vx), C.byref(vo), 0, None))
             ref = o.geometric_product(x64, m64)
             assert np.all(np.abs(fetch() - ref).max(axis=1) <= tol * np.abs(ref).max(axis=1)), f"right n={n}"
+            # the same two products with the fixed operand resident on the DEVICE (what lcc.torch passes): K8 builds its
+            # 16 x 16 factor from the device row with a one-block kernel -- two launches, no host copy of the operand
+            pm = C.c_void_p()
+            cabi.check(lib.lcc_device_alloc(C.byref(pm), m.nbytes, None))
+            cabi.check(lib.lcc_memcpy_h2d(pm, m.ctypes.data, m.nbytes, None))
+            vm = cabi.view(pm.value, 1, nb, code, cabi.LCC_AOS)
+            before = lib.lcc_kernel_launch_count()
+            cabi.check(lib.lcc_batch_product(alg.h, cabi.LCC_OP_GP, C.byref(vm), C.byref(vx), C.byref(vo), 0, None))
+            assert lib.lcc_kernel_launch_count() - before == 2
+            ref = o.geometric_product(m64, x64)
+            assert np.all(np.abs(fetch() - ref).max(axis=1) <= tol * np.abs(ref).max(axis=1)), f"device operand, left n={n}"
+            cabi.check(lib.lcc_batch_product(alg.h, cabi.LCC_OP_GP, C.byref(vx), C.byref(vm), C.byref(vo), 0, None))
+            ref = o.geometric_product(x64, m64)
+            assert np.all(np.abs(fetch() - ref).max(axis=1) <= tol * np.abs(ref).max(axis=1)), f"device operand, right n={n}"
+            if n == 4099:  # blade-major views of the same data: 128-byte pieces per blade, the last 4099 % (16 / itemsize) rows on the exact kernels
+                ps, pso, pms = C.c_void_p(), C.c_void_p(), C.c_void_p()
+                lds = n + (-n) % 4
+                soa = np.zeros((nb, lds), dt)
+                soa[:, :n] = x.T
+                msoa = np.zeros((nb, 4), dt)
+                msoa[:, 0] = m[0]
+                for ptr, arr in ((ps, soa), (pso, soa), (pms, msoa)):
+                    cabi.check(lib.lcc_device_alloc(C.byref(ptr), arr.nbytes, None))
+                    cabi.check(lib.lcc_memcpy_h2d(ptr, arr.ctypes.data, arr.nbytes, None))
+                vs, vso, vms = cabi.view(ps.value, n, lds, code, cabi.LCC_SOA), cabi.view(pso.value, n, lds, code, cabi.LCC_SOA), cabi.view(pms.value, 1, 4, code, cabi.LCC_SOA)
+                cabi.check(lib.lcc_batch_product(alg.h, cabi.LCC_OP_GP, C.byref(vms), C.byref(vs), C.byref(vso), 0, None))
+                got = np.empty_like(soa)
+                cabi.check(lib.lcc_memcpy_d2h(got.ctypes.data, pso, got.nbytes, None))
+                cabi.check(lib.lcc_stream_sync(None))
+                ref = o.geometric_product(m64, x64)
+                assert np.all(np.abs(got[:, :n].T - ref).max(axis=1) <= tol * np.abs(ref).max(axis=1)), "device operand, blade-major"
+                for ptr in (ps, pso, pms):
+                    cabi.check(lib.lcc_device_free(ptr, None))
+            cabi.check(lib.lcc_device_free(pm, None))
             r = rng.standard_normal(nb) / np.sqrt(nb)
             cabi.check(lib.lcc_batch_sandwich(alg.h, r.ctypes.data_as(C.POINTER(C.c_double)), C.byref(vx), C.byref(vx), 0, None))  # in place
             ref = o.sandwich(r, x64)
