@@ -65,6 +65,23 @@ def main():
     with torch.no_grad():
         ms = timeit(lambda: X.sandwich(R))
     print(json.dumps({"case": "PGA sandwich AoS f32 (lcc.torch)", "rows": n, "ms": ms, "GBps": 128 * n / ms / 1e6}), flush=True)
+    # Cl(8,0,0): one DEVICE-resident operand times a batch of (N, 256) rows -- K8 on units of whole rows, the 16 x 16 factor
+    # built on the device (no host copy of the operand); the dense-GEMM form of the same call beside it (matrix_rep = 0)
+    from largecrimsoncanine_b200 import cabi
+    alg = TorchAlgebra._from_signature(8, 0, 0, device="cuda")
+    for dt, log2n in ((torch.float64, 22), (torch.float32, 23)):
+        n = 1 << log2n
+        x = torch.randn(n, 256, device="cuda", dtype=dt)
+        m = torch.randn(1, 256, device="cuda", dtype=dt)
+        X, M = TorchMultivector(alg, x), TorchMultivector(alg, m)
+        with torch.no_grad():
+            ms = timeit(lambda: M.geometric_product(X))
+            cabi.check(cabi.lib().lcc_set_option(b"matrix_rep", 0))
+            ms_gemm = timeit(lambda: M.geometric_product(X), iters=3)
+            cabi.check(cabi.lib().lcc_set_option(b"matrix_rep", 2))
+        es = x.element_size()
+        print(json.dumps({"case": "Cl(8,0,0) device operand * batch (lcc.torch)", "rows": n, "dtype": str(dt), "ms": ms, "GBps": 2 * 256 * es * n / ms / 1e6,
+                          "dense_gemm_ms": ms_gemm}), flush=True)
 
 
 if __name__ == "__main__":
