@@ -234,7 +234,8 @@ def test_cfg4_sta_grade_inner_sum_on_2p27_multivectors(env):
 
 # ----------------------------------------------------------------------------------------------- cfg5
 def test_cfg5_cl8_fixed_operand_on_2p24_rows(env):
-    """BASELINE configs[4] at full size: one fixed left operand times 2^24 multivectors of Cl(8,0,0), f32, tensor cores."""
+    """BASELINE configs[4] at full size: one fixed left operand (device-resident) times 2^24 multivectors of Cl(8,0,0), f32:
+    K8, block-diagonalised in the 16 x 16 matrix representation, stage 2 on the tensor cores."""
     need_gb(env, 45)
     torch, cabi, lib = env.torch, env.cabi, env.lib
     n, nb = 1 << 24, 256
@@ -251,9 +252,12 @@ def test_cfg5_cl8_fixed_operand_on_2p24_rows(env):
     m[i, 0] = 1.0
     vm = cabi.view(m.data_ptr(), 1, 4, cabi.LCC_F32, cabi.LCC_SOA)
     cabi.check(lib.lcc_batch_product(alg.h, cabi.LCC_OP_GP, C.byref(vm), C.byref(vx), C.byref(vo), 0, env.sptr))
+    # (K8 transforms each row through two Walsh-Hadamard passes, so the permutation is exact to 1e-5 of the ROW's magnitude --
+    # the path's stated tolerance -- not of every single coefficient)
+    row_mag = x.abs().amax(dim=0)
     for k in range(nb):
         ref = x[k] if signs[i, k] > 0 else -x[k]
-        assert bool(((out[i ^ k] - ref).abs() <= 1e-5 * ref.abs()).all()), k
+        assert bool(((out[i ^ k] - ref).abs() <= 1e-5 * row_mag).all()), k
     # (b) a dense fixed operand on sampled rows against the oracle (1e-5 of the row magnitude: tensor-core summation order)
     dense = torch.randn((nb, 4), device=env.dev, dtype=torch.float32, generator=gen)
     vd = cabi.view(dense.data_ptr(), 1, 4, cabi.LCC_F32, cabi.LCC_SOA)
