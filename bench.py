@@ -877,6 +877,38 @@ def measure_e2e(args, lib, alg, code, motor, n, nb, world, rank, dev, dist, flag
             variants[name] = timed(fn, xh if kind == "pinned" else xp, k)
         except Exception as exc:  # a variant that cannot run (host memory) must not take the bench line down
             variants[name] = {"error": f"{type(exc).__name__}: {exc}"}
+    try:
+        # the same points and motor in compact form: (N, 3) xyz in and out, embed + sandwich + extract fused on the device
+        # (24 bytes per point over PCIe instead of 256) -- a different data format from the metric's 16-blade rows, listed
+        # for what the 75 % structural zeros of a PGA point cost end to end
+        ch, co = L.pinned_empty((n_e2e, 3), ndt), L.pinned_empty((n_e2e, 3), ndt)
+        for s in range(0, n_e2e, blk):
+            e = min(n_e2e, s + blk)
+            ch[s:e, 0], ch[s:e, 1], ch[s:e, 2] = -xh[s:e, 14], xh[s:e, 13], -xh[s:e, 11]
+
+        def compact_call():
+            cabi.check(lib.lcc_host_pga_points_sandwich(alg.h, code, mptr, C.c_void_p(ch.ctypes.data), C.c_void_p(co.ctypes.data), n_e2e, flags))
+
+        compact_call()
+        sample = np.r_[0:2048, n_e2e - 2048:n_e2e]
+        ok = bool(np.abs(co[sample] - oracle.pga_transform_points(motor, ch[sample])).max() <= 1e-4)
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            compact_call()
+        torch.cuda.synchronize()
+        dt_s = time.perf_counter() - t0
+        if dist:
+            t = torch.tensor([dt_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_s = float(t.item())
+        variants["compact_xyz_c_abi_pinned"] = {"value": world * n_e2e * steps / dt_s, "s_per_step": dt_s / steps, "steps": steps, "checked_against_oracle": ok,
+                                                "h2d_bytes_per_step": n_e2e * 3 * es, "d2h_bytes_per_step": n_e2e * 3 * es}
+        del ch, co
+    except Exception as exc:
+        variants["compact_xyz_c_abi_pinned"] = {"error": f"{type(exc).__name__}: {exc}"}
     if flags:
         L.set_strict_fp(False)
     head = variants.get("three_call_pinned", {})
@@ -891,7 +923,9 @@ def measure_e2e(args, lib, alg, code, motor, n, nb, world, rank, dev, dist, flag
             "variants": variants,
             "variants_note": "three_call_*: from_numpy -> sandwich -> to_numpy (upload and download are serial by the API's "
                              "semantics); fused_*: MultivectorBatch.sandwich_numpy (one call, both PCIe directions at once); "
-                             "c_abi_pinned: lcc_host_sandwich, the C-ABI entry point behind sandwich_numpy"}
+                             "c_abi_pinned: lcc_host_sandwich, the C-ABI entry point behind sandwich_numpy; compact_xyz_c_abi_pinned: "
+                             "lcc_host_pga_points_sandwich on the same points as (N, 3) xyz rows (24 B per point each way "
+                             "instead of 128: not the metric's data format, listed for comparison)"}
 
 
 def measure_e2e_compact(args, lib, alg, code, motor, n, es, world, rank, dev, dist, flags, numa_bound):

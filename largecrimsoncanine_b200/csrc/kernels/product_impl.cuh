@@ -968,13 +968,18 @@ static __device__ __forceinline__ void sandwich_rows_body(const Tile<real, NB, V
 #undef LCC_TERM
 #undef LCC_OUT_END
 }
-// one DEVICE rotor for the whole batch: is it even?  (every thread holds the same row, so the branch is uniform)
-template <int V> static __device__ __forceinline__ bool bcast_rotor_is_even(const Tile<real, NB, V> &R) {
+// Are the rotors this WARP holds all even (odd-grade coefficients zero)?  One device rotor for the whole batch: every
+// thread holds the same row; one rotor per row: rotor fields are even versors in practice, and the vote keeps the branch
+// warp-uniform when a batch mixes both kinds.
+template <int V> static __device__ __forceinline__ bool warp_rotors_are_even(const Tile<real, NB, V> &R) {
     bool even = true;
 #pragma unroll
     for (int i = 0; i < NB; ++i)
-        if (!even_grade(i)) even = even && (R.v[i][0] == real(0));
-    return even;
+        if (!even_grade(i)) {
+#pragma unroll
+            for (int l = 0; l < V; ++l) even = even && (R.v[i][l] == real(0));
+        }
+    return __all_sync(__activemask(), even) != 0;
 }
 
 template <int LAYOUT, bool STRICT>
@@ -988,7 +993,17 @@ sandwich_rows_kernel(const real *__restrict__ r, int64_t ldr, int r_bcast, const
     if constexpr (LAYOUT == kSoA) { load_soa(R, r, ldr, r0, r_bcast != 0); load_soa(X, x, ldx, r0, false); }
     else { load_aos(R, r, ldr, r0, r_bcast != 0, vec_ok != 0); load_aos(X, x, ldx, r0, false, vec_ok != 0); }
     Sink<LAYOUT, V> sink{out, ldo, r0, vec_ok != 0, {}};
-    if (r_bcast && bcast_rotor_is_even(R)) sandwich_rows_body<STRICT, true, V>(R, X, sink, mu);
+    // (blade-major threads hold V rows: the vote over per-row rotors costs them registers and occupancy -- measured
+    // 6.4 -> 4.8 TB/s on PGA f32 -- so there only the one-device-rotor case is tested)
+    bool even = false;
+    if constexpr (V == 1) even = warp_rotors_are_even(R);
+    else if (r_bcast) {
+        even = true;
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+            if (!even_grade(i)) even = even && (R.v[i][0] == real(0));
+    }
+    if (even) sandwich_rows_body<STRICT, true, V>(R, X, sink, mu);
     else sandwich_rows_body<STRICT, false, V>(R, X, sink, mu);
 }
 
@@ -998,7 +1013,9 @@ __global__ void __launch_bounds__(TmaTile::kRows)
 sandwich_rows_kernel_aos_tma(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_x,
                              const __grid_constant__ CUtensorMap map_out, const real *__restrict__ r_row, const Coeffs mu) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *tile_r = tma_smem_base(smem_raw), *tile_x = tile_r + TmaTile::kBytes;
+    // one device rotor for the batch: no rotor tile, the block is launched with one tile of shared memory (twice the
+    // blocks, and bytes in flight, per SM)
+    uint8_t *tile_r = tma_smem_base(smem_raw), *tile_x = r_row ? tile_r : tile_r + TmaTile::kBytes;
     uint64_t *bar = reinterpret_cast<uint64_t *>(tile_x + TmaTile::kBytes);
     const int t = threadIdx.x, row0 = blockIdx.x * TmaTile::kRows;
     if (t == 0) {
@@ -1014,7 +1031,7 @@ sandwich_rows_kernel_aos_tma(const __grid_constant__ CUtensorMap map_r, const __
     if (!r_row) load_tile_row(R, tile_r, t);
     load_tile_row(X, tile_x, t);
     TileSink sink{tile_x, t, {}};
-    if (r_row && bcast_rotor_is_even(R)) sandwich_rows_body<STRICT, true, 1>(R, X, sink, mu);
+    if (warp_rotors_are_even(R)) sandwich_rows_body<STRICT, true, 1>(R, X, sink, mu);
     else sandwich_rows_body<STRICT, false, 1>(R, X, sink, mu);
     tma::fence_proxy_async();
     __syncthreads();
@@ -1205,7 +1222,7 @@ template <int LAYOUT, bool STRICT> static cudaError_t launch_sandwich_rows_t(con
                     const cudaError_t attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
                     if (attr != cudaSuccess) return attr;
                     const unsigned grid = (unsigned)((g.n + TmaTile::kRows - 1) / TmaTile::kRows);
-                    kernel<<<grid, TmaTile::kRows, smem, g.stream>>>(mr, mx, mo, g.r_bcast ? r : nullptr, to_coeffs(g.mu, 1.0));
+                    kernel<<<grid, TmaTile::kRows, g.r_bcast ? smem - TmaTile::kBytes : smem, g.stream>>>(mr, mx, mo, g.r_bcast ? r : nullptr, to_coeffs(g.mu, 1.0));
                     note_kernel_launch();
                     return cudaGetLastError();
                 }

@@ -67,6 +67,15 @@ def run(sig, dt, log2n):
             rot[[k for k in range(nb) if bin(k).count("1") % 2]] = 0
             keep_rot = rot.reshape(nb, 1).repeat(1, 4).contiguous() if layout == cabi.LCC_SOA else rot.reshape(1, nb).contiguous()
             r2 = cabi.view(keep_rot.data_ptr(), 1, 4 if layout == cabi.LCC_SOA else nb, code, layout)
+            # one EVEN rotor per row (a rotor / motor field): the warps vote and run the pruned term lists
+            rows_even = b.clone()
+            odd = [k for k in range(nb) if bin(k).count("1") % 2]
+            if layout == cabi.LCC_SOA:
+                rows_even[odd, :] = 0
+            else:
+                rows_even[:, odd] = 0
+            vre = v(rows_even)
+            cases["sandwich_rows_even"] = (3 * nb * es, lambda: cabi.check(lib.lcc_batch_sandwich_rows(alg.h, C.byref(vre), C.byref(va), C.byref(vo), 0, sptr)))
             cases["sandwich_rows_bcast_even"] = (2 * nb * es, lambda: cabi.check(lib.lcc_batch_sandwich_rows(alg.h, C.byref(r2), C.byref(va), C.byref(vo), 0, sptr)))
         if alg.r == 0:
             cases["dual"] = (2 * nb * es, lambda: cabi.check(lib.lcc_batch_unary(alg.h, cabi.LCC_UN_DUAL, 0, C.byref(va), C.byref(vo), sptr)))
