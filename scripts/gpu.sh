@@ -118,6 +118,10 @@ stage_k8_mem() {         # K8 memory pipeline experiments: L2 promotion x unit o
     NOPAR= run1 full_default_g2 $wl LCC_K8_GROUPS=2
   done
 }
+stage_tma_probe() {      # which tile shape / unit scheduling lets a persistent TMA ring stream a 256-blade batch at the HBM rate
+  mkdir -p build && nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o build/tma_probe scripts/tma_passthrough_probe.cu \
+    && timeout 300 build/tma_probe | tee gpurun_out/tma_probe.jsonl
+}
 stage_info() { nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit,memory.total --format=csv; nproc; free -g | head -2; nvidia-smi topo -m 2>/dev/null | head -12; }
 
 for st in "$@"; do

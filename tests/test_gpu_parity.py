@@ -453,7 +453,15 @@ def test_per_row_sandwich_through_the_c_abi(sig, dt):
     big = 131072 + 37 if nb * np.dtype(dt).itemsize <= 64 else 4096 + 37  # past the AoS TMA threshold of this row size
     for n in (1, 63, 1000, big):
         x, r = rand(rng, n, nb, dt), rand(rng, n, nb, dt)
-        for rr in (r, r[:1]):
+        # even versors (rotors / motors: odd-grade coefficients zero) take the pruned term lists -- per row when the whole
+        # warp agrees (row-per-thread kernels vote), for the one device rotor always; a batch that mixes both kinds must
+        # come out the same as well
+        odd = [k for k in range(nb) if bin(k).count("1") % 2]
+        r_even, r_mixed = r.copy(), r.copy()
+        r_even[:, odd] = 0
+        r_mixed[::3, odd] = 0
+        r_mixed[n // 2:, odd] = 0
+        for rr in (r, r[:1], r_even, r_even[:1], r_mixed):
             want = o.geometric_product(o.geometric_product(rr, x), rr * rev)
             for layout in (cabi.LCC_AOS, cabi.LCC_SOA):
                 def put(a):
