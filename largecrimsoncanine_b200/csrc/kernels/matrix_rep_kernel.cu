@@ -32,7 +32,11 @@
 
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
 #include <type_traits>
+#include <vector>
 
 #include "../matrix_rep.hpp"
 #include "launch_args.h"
@@ -575,10 +579,31 @@ __global__ void build_rep_factor_kernel(const T *__restrict__ m, int64_t m_strid
     factor[mi * 16 + ki] = (T)(acc * (1.0 / 16.0));
 }
 
+// The shared-memory layouts of a representation (index bases found by search: 6-25 us of host time) are computed once and
+// kept, keyed by the representation's tables.
+struct LayoutSet { uint8_t blade_at[256]; int8_t sign_at[256]; RepLayout L; RepLayoutAos A4, A8; };
+LayoutSet layouts_of(const uint8_t *blade_at, const int8_t *sign_at) {
+    static std::mutex mu;
+    static std::vector<std::unique_ptr<LayoutSet>> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    for (const auto &e : cache)
+        if (!memcmp(e->blade_at, blade_at, 256) && !memcmp(e->sign_at, sign_at, 256)) return *e;
+    if (cache.size() >= 64) cache.erase(cache.begin());
+    auto e = std::make_unique<LayoutSet>();
+    memcpy(e->blade_at, blade_at, 256);
+    memcpy(e->sign_at, sign_at, 256);
+    e->L = make_rep_layout(blade_at, sign_at);
+    e->A4 = make_rep_layout_aos(e->L, 4);
+    e->A8 = make_rep_layout_aos(e->L, 8);
+    cache.push_back(std::move(e));
+    return *cache.back();
+}
+
 template <typename T>
 cudaError_t launch_rep(int nb, int mode, const double *p1, const double *p2, const void *m_dev, int64_t m_stride, const uint8_t *blade_at,
                        const int8_t *sign_at, const ViewArg &x, const ViewArg &out, cudaStream_t s) {
-    const RepLayout L = make_rep_layout(blade_at, sign_at);
+    const LayoutSet layouts = layouts_of(blade_at, sign_at);  // (a copy: 3 KB, and no lifetime question)
+    const RepLayout &L = layouts.L;
     const bool aos = x.layout == kAoS;
     RepParams<T> P;
     const double *fac[2] = {p1, p2};
@@ -586,7 +611,7 @@ cudaError_t launch_rep(int nb, int mode, const double *p1, const double *p2, con
     for (int i = 0; i < 256; ++i) { tb.blade_at[i] = blade_at[i]; tb.sign_at[i] = sign_at[i]; }
     // mode 0: column pass with p1; mode 1: row pass with p1; mode 2: column pass with p1, row pass with p2
     if (aos) {
-        const RepLayoutAos A = make_rep_layout_aos(L, (int)sizeof(T));
+        const RepLayoutAos &A = sizeof(T) == 4 ? layouts.A4 : layouts.A8;
         if (!A.ok) return cudaErrorNotSupported;
         const RepPassAos *pass[2] = {mode == 1 ? &A.row : &A.column, &A.row};
         for (int p = 0; p < 2; ++p)

@@ -67,7 +67,9 @@ def distribute_unique_id(make_id, rank: int, world: int) -> bytes:
 
     host = os.environ.get("MASTER_ADDR", "127.0.0.1")
     port = int(os.environ.get("MASTER_PORT", "29500")) + 17
-    store = TCPStore(host, port, world, is_master=(rank == 0))
+    import datetime
+
+    store = TCPStore(host, port, world, is_master=(rank == 0), timeout=datetime.timedelta(seconds=120))
     if rank == 0:
         store.set("lcc_shard_unique_id", make_id())
     return bytes(store.get("lcc_shard_unique_id"))

@@ -46,11 +46,15 @@ def test_shard_entry_points_validate_and_refuse_without_a_gpu():
 
 def _worker(rank, world, port, out):
     sys.path.insert(0, ROOT)
+    import datetime
+
     import torch.distributed as dist
 
     from largecrimsoncanine_b200 import sharded
 
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    # loopback only: gloo otherwise resolves the container's hostname to pick an interface, which may not resolve (or hang)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      GLOO_SOCKET_IFNAME="lo")
     token = bytes(range(128))
     calls = []
 
@@ -60,29 +64,68 @@ def _worker(rank, world, port, out):
 
     try:
         via_store = sharded.distribute_unique_id(make_id, rank, world)  # no process group yet: TCPStore on MASTER_PORT+17
-        dist.init_process_group("gloo", rank=rank, world_size=world)
+        dist.init_process_group("gloo", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=90))
         via_group = sharded.distribute_unique_id(make_id, rank, world)  # process group present: one broadcast
         info = sharded.shard_rows(1001, rank, world)
         out.put((rank, via_store == token and via_group == token, calls == ([0, 0] if rank == 0 else []), info.rows))
+    except BaseException as exc:  # a worker that dies silently would leave the parent waiting for its timeout
+        import traceback
+
+        out.put((rank, "error", f"{type(exc).__name__}: {exc}\n{traceback.format_exc()}", 0))
+        raise
     finally:
         if dist.is_initialized():
             dist.destroy_process_group()
 
 
-def test_two_ranks_share_the_unique_id_over_gloo():
+def _run_two_ranks():
+    import queue
+
     import torch.multiprocessing as mp
 
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        port = s.getsockname()[1]
+    port = None
+    for _ in range(64):  # a free port whose +17 neighbour (the TCPStore of distribute_unique_id) is free as well
+        with socket.socket() as s, socket.socket() as s17:
+            s.bind(("127.0.0.1", 0))
+            cand = s.getsockname()[1]
+            try:
+                s17.bind(("127.0.0.1", cand + 17))
+            except OSError:
+                continue
+            port = cand
+            break
+    assert port is not None
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=900) for _ in procs]  # a cold `import torch` in a spawned worker can take minutes right after a build
+    results, problem = [], None
+    try:
+        for _ in procs:
+            results.append(q.get(timeout=240))  # (a cold `import torch` in a spawned worker can take a minute right after a build)
+    except queue.Empty:
+        problem = "a rank did not answer within 240 s"
+    errors = [r[2] for r in results if r[1] == "error"]
+    if errors:
+        problem = "; ".join(errors)
     for p in procs:
-        p.join(timeout=300)
-        assert p.exitcode == 0
+        p.join(timeout=5 if problem else 120)
+        if p.is_alive():
+            p.terminate()
+            p.join(timeout=10)
+        elif not problem and p.exitcode != 0:
+            problem = f"rank exited with code {p.exitcode}"
+    return results, problem
+
+
+def test_two_ranks_share_the_unique_id_over_gloo():
+    # the rendezvous (two TCP stores on loopback ports picked here) is retried on a fresh pair of ports: a port can be taken
+    # between the probe and the bind
+    for attempt in range(3):
+        results, problem = _run_two_ranks()
+        if problem is None:
+            break
+    assert problem is None, problem
     assert all(same and only_rank0 for _, same, only_rank0, _ in results)
     assert sum(rows for _, _, _, rows in results) == 1001
