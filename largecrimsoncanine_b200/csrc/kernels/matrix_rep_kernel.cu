@@ -562,21 +562,26 @@ cudaError_t launch_rep_p(int nb, int mode, const RepParams<T> &P, const T *facto
 
 // rho(M) / 16 (or its transpose) of a DEVICE-resident operand M, written in the MMA's physical m / k order:
 // rho(M)[j ^ a][j] = sum_b (-1)^popcount(b & j) sign(a, b) M[blade(a, b)]   (csrc/matrix_rep.hpp).  One thread per entry.
-struct RepTables { uint8_t blade_at[256]; int8_t sign_at[256]; uint8_t omap[16], kmap[16]; };
+// `pass` selects the index maps (sandwich: 0 = column pass with rho(R) / 16, 1 = row pass with rho(~R)^T); `reverse`
+// multiplies every coefficient by its reverse sign (blades.rs:128-135): ~R without materialising it.
+struct RepTables { uint8_t blade_at[256]; int8_t sign_at[256]; uint8_t omap[2][16], kmap[2][16]; };
 template <typename T>
-__global__ void build_rep_factor_kernel(const T *__restrict__ m, int64_t m_stride, const __grid_constant__ RepTables tb, int transpose, T *__restrict__ factor) {
+__global__ void build_rep_factor_kernel(const T *__restrict__ m, int64_t m_stride, const __grid_constant__ RepTables tb, int pass, int transpose,
+                                        int reverse, double scale, T *__restrict__ factor) {
     const int mi = threadIdx.x >> 4, ki = threadIdx.x & 15;
-    const int o = tb.omap[mi], k = tb.kmap[ki];
+    const int o = tb.omap[pass][mi], k = tb.kmap[pass][ki];
     const int i = transpose ? k : o, j = transpose ? o : k;
     const int a = i ^ j;
     double acc = 0.0;
     for (int b = 0; b < 16; ++b) {
         const int str = (a << 4) | b, sg = tb.sign_at[str];
         if (sg == 0) continue;
-        const double v = (double)m[(int64_t)tb.blade_at[str] * m_stride];
+        const int blade = tb.blade_at[str];
+        double v = (double)m[(int64_t)blade * m_stride];
+        if (reverse && (__popc(blade) & 3) >= 2) v = -v;
         acc += ((__popc(b & j) & 1) != 0) == (sg > 0) ? -v : v;
     }
-    factor[mi * 16 + ki] = (T)(acc * (1.0 / 16.0));
+    factor[mi * 16 + ki] = (T)(acc * scale);
 }
 
 // The shared-memory layouts of a representation (index bases found by search: 6-25 us of host time) are computed once and
@@ -621,7 +626,7 @@ cudaError_t launch_rep(int nb, int mode, const double *p1, const double *p2, con
                 P.fo[p][i] = pass[p]->fo[i];
                 for (int k = 0; k < 16; ++k) P.factor[p][i * 16 + k] = fac[p] ? (T)fac[p][pass[p]->omap[i] * 16 + pass[p]->kmap[k]] : T(0);
             }
-        for (int i = 0; i < 16; ++i) { P.f_lo[i] = A.g_lo[i]; P.f_hi[i] = A.g_hi[i]; P.amap[i] = A.amap[i]; tb.omap[i] = pass[0]->omap[i]; tb.kmap[i] = pass[0]->kmap[i]; }
+        for (int i = 0; i < 16; ++i) { P.f_lo[i] = A.g_lo[i]; P.f_hi[i] = A.g_hi[i]; P.amap[i] = A.amap[i]; for (int p = 0; p < 2; ++p) { tb.omap[p][i] = pass[p]->omap[i]; tb.kmap[p][i] = pass[p]->kmap[i]; } }
     } else {
         if (!L.ok) return cudaErrorNotSupported;
         const RepPass *pass[2] = {mode == 1 ? &L.row : &L.column, &L.row};
@@ -631,7 +636,7 @@ cudaError_t launch_rep(int nb, int mode, const double *p1, const double *p2, con
                 P.cw[p][i] = pass[p]->cw[i];
                 for (int k = 0; k < 16; ++k) P.factor[p][i * 16 + k] = fac[p] ? (T)fac[p][pass[p]->kmap[i] * 16 + pass[p]->kmap[k]] : T(0);
             }
-        for (int i = 0; i < 16; ++i) { P.f_lo[i] = L.f_lo[i]; P.f_hi[i] = L.f_hi[i]; P.amap[i] = (uint32_t)i; tb.omap[i] = tb.kmap[i] = pass[0]->kmap[i]; }
+        for (int i = 0; i < 16; ++i) { P.f_lo[i] = L.f_lo[i]; P.f_hi[i] = L.f_hi[i]; P.amap[i] = (uint32_t)i; for (int p = 0; p < 2; ++p) tb.omap[p][i] = tb.kmap[p][i] = pass[p]->kmap[i]; }
     }
     for (int i = 0; i < 8; ++i) P.neg[i] = P.valid[i] = 0;
     for (int str = 0; str < 256; ++str) {
@@ -639,12 +644,15 @@ cudaError_t launch_rep(int nb, int mode, const double *p1, const double *p2, con
         if (sign_at[str] < 0) P.neg[str >> 5] |= 1u << (str & 31);
     }
     T *factor_dev = nullptr;
-    if (m_dev) {  // device-resident operand (mode 0: fixed * x, mode 1: x * fixed): the factor is built on the device
-        if (mode != 0 && mode != 1) return cudaErrorInvalidValue;
-        cudaError_t e = cudaMallocAsync((void **)&factor_dev, 256 * sizeof(T), s);
+    if (m_dev) {  // device-resident operand (mode 0: fixed * x, mode 1: x * fixed, mode 2: R x ~R): the factors are built on the device
+        cudaError_t e = cudaMallocAsync((void **)&factor_dev, 512 * sizeof(T), s);
         if (e != cudaSuccess) return e;
-        build_rep_factor_kernel<T><<<1, 256, 0, s>>>((const T *)m_dev, m_stride, tb, mode == 1 ? 1 : 0, factor_dev);
+        build_rep_factor_kernel<T><<<1, 256, 0, s>>>((const T *)m_dev, m_stride, tb, 0, mode == 1 ? 1 : 0, 0, 1.0 / 16.0, factor_dev);
         note_kernel_launch();
+        if (mode == 2) {
+            build_rep_factor_kernel<T><<<1, 256, 0, s>>>((const T *)m_dev, m_stride, tb, 1, 1, 1, 1.0, factor_dev + 256);
+            note_kernel_launch();
+        }
     }
     const cudaError_t e = aos ? launch_rep_p<T, true>(nb, mode, P, factor_dev, x, out, s) : launch_rep_p<T, false>(nb, mode, P, factor_dev, x, out, s);
     if (factor_dev) cudaFreeAsync(factor_dev, s);
@@ -655,7 +663,7 @@ cudaError_t launch_rep(int nb, int mode, const double *p1, const double *p2, con
 
 // K8 launcher.  mode 0 / 1 / 2 = left product, right product, sandwich; p1 (and p2 for the sandwich) are row-major 16 x 16
 // f64 factors in the orientation the MMA contracts ([o][k]: mode 0 rho(M) / 16, mode 1 rho(M)^T / 16, mode 2 rho(R) / 16 and
-// rho(~R)^T) -- or, for modes 0 / 1, m_dev: the fixed operand itself as a device row of the batch dtype (element k at
+// rho(~R)^T) -- or m_dev: the fixed operand / rotor itself as a device row of the batch dtype (element k at
 // m_dev[k * m_stride]), from which a one-block kernel builds the factor; blade_at / sign_at map a string to its blade and sign.  x and out are views of nb = 128 or 256 blades in ONE
 // layout: blade-major (SoA) with a row count that is a multiple of 16 bytes (TMA stores clip at that granularity), or the
 // reference's row-major (AoS) layout with any row count -- whole rows are contiguous there, and a unit is one 16-32 KB span.

@@ -1025,6 +1025,20 @@ lcc_status lcc_batch_sandwich_rows(const lcc_algebra *alg, const lcc_view *rotor
         const cudaError_t e = alg->sandwich[x->dtype](g);
         if (e != cudaErrorNotSupported) { LCC_CUDA(e); return LCC_OK; }
     }
+    // 128 / 256 blades, ONE device rotor for the batch, an algebra with a real 16 x 16 representation: K8's two-pass form,
+    // both factors (rho(R) / 16, rho(~R)^T) built from the device row by two one-block kernels -- one pass over x instead
+    // of reverse + two products through a full-size temporary
+    lcc_view x_tail, out_tail;
+    if (rotors->n == 1 && x->n > 1 && x->layout == out->layout && rotors->layout == x->layout &&
+        matrix_rep_usable(alg, x, (flags & LCC_FLAG_STRICT_FP) != 0)) {
+        int64_t rows_done = 0;
+        LCC_TRY(matrix_rep_apply(alg, 2, nullptr, nullptr, x, out, s, &rows_done, rotors));
+        if (rows_done == x->n) return LCC_OK;
+        if (rows_done > 0) {  // blade-major views: the last 1-3 rows take the composition below
+            x_tail = tail_view(x, rows_done); out_tail = tail_view(out, rows_done);
+            x = &x_tail; out = &out_tail;
+        }
+    }
     // rx = R * x ; out = rx * ~R   (lcc/torch/multivector.py:1006-1017), composed from K1 and K3
     PoolBuffer brev, brx;
     lcc_view rev = *rotors, rx = *x;

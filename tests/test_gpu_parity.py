@@ -689,6 +689,19 @@ def test_block_diagonalised_product_on_reference_layout_units(L, sig, dt):
                     cabi.check(lib.lcc_device_free(ptr, None))
             cabi.check(lib.lcc_device_free(pm, None))
             r = rng.standard_normal(nb) / np.sqrt(nb)
+            # one DEVICE rotor for the batch (lcc_batch_sandwich_rows, one-row rotors view): K8's two-pass form, both factors
+            # built on the device -- three launches instead of reverse + two products
+            rdev = r.astype(dt)[None, :].copy()
+            pr = C.c_void_p()
+            cabi.check(lib.lcc_device_alloc(C.byref(pr), rdev.nbytes, None))
+            cabi.check(lib.lcc_memcpy_h2d(pr, rdev.ctypes.data, rdev.nbytes, None))
+            vr = cabi.view(pr.value, 1, nb, code, cabi.LCC_AOS)
+            before = lib.lcc_kernel_launch_count()
+            cabi.check(lib.lcc_batch_sandwich_rows(alg.h, C.byref(vr), C.byref(vx), C.byref(vo), 0, None))
+            assert lib.lcc_kernel_launch_count() - before == 3
+            ref = o.sandwich(rdev[0].astype(np.float64), x64)
+            assert np.all(np.abs(fetch() - ref).max(axis=1) <= tol * np.abs(ref).max(axis=1)), f"device rotor n={n}"
+            cabi.check(lib.lcc_device_free(pr, None))
             cabi.check(lib.lcc_batch_sandwich(alg.h, r.ctypes.data_as(C.POINTER(C.c_double)), C.byref(vx), C.byref(vx), 0, None))  # in place
             ref = o.sandwich(r, x64)
             assert np.all(np.abs(fetch(px) - ref).max(axis=1) <= tol * np.abs(ref).max(axis=1)), f"sandwich n={n}"
