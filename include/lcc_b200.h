@@ -223,7 +223,10 @@ LCC_API lcc_status lcc_batch_product_vjp(const lcc_algebra *alg, int op, int wrt
  * batch, two rounded stages as in batch.rs:434-503. */
 LCC_API lcc_status lcc_batch_sandwich(const lcc_algebra *alg, const double *rotor, const lcc_view *x,
                                       const lcc_view *out, unsigned flags, void *stream);
-/* Per-row rotors (rotors.n == x.n): lcc/torch/multivector.py:988-1019. */
+/* Per-row rotors (rotors.n == x.n), or ONE device-resident rotor row for the whole batch (rotors.n == 1: no host copy
+ * of the rotor is needed): lcc/torch/multivector.py:988-1019.  Up to 16 blades one fused kernel (even rotors take pruned
+ * term lists); 128 / 256-blade algebras with a real 16 x 16 matrix representation and one rotor: the block-diagonalised
+ * two-pass form (K8) with both factors built on the device; otherwise reverse + two products. */
 LCC_API lcc_status lcc_batch_sandwich_rows(const lcc_algebra *alg, const lcc_view *rotors, const lcc_view *x,
                                            const lcc_view *out, unsigned flags, void *stream);
 /* Cotangents of lcc_batch_sandwich_rows (autograd of lcc.torch; the reference's backward pass is torch autograd through

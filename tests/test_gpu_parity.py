@@ -685,6 +685,20 @@ def test_block_diagonalised_product_on_reference_layout_units(L, sig, dt):
                 cabi.check(lib.lcc_stream_sync(None))
                 ref = o.geometric_product(m64, x64)
                 assert np.all(np.abs(got[:, :n].T - ref).max(axis=1) <= tol * np.abs(ref).max(axis=1)), "device operand, blade-major"
+                # and one device rotor for the blade-major batch (two-pass K8 + the exact composition on the last rows)
+                rs = rng.standard_normal(nb).astype(dt) / np.sqrt(nb).astype(dt)
+                rsoa = np.zeros((nb, 4), dt)
+                rsoa[:, 0] = rs
+                prs = C.c_void_p()
+                cabi.check(lib.lcc_device_alloc(C.byref(prs), rsoa.nbytes, None))
+                cabi.check(lib.lcc_memcpy_h2d(prs, rsoa.ctypes.data, rsoa.nbytes, None))
+                vrs = cabi.view(prs.value, 1, 4, code, cabi.LCC_SOA)
+                cabi.check(lib.lcc_batch_sandwich_rows(alg.h, C.byref(vrs), C.byref(vs), C.byref(vso), 0, None))
+                cabi.check(lib.lcc_memcpy_d2h(got.ctypes.data, pso, got.nbytes, None))
+                cabi.check(lib.lcc_stream_sync(None))
+                ref = o.sandwich(rs.astype(np.float64), x64)
+                assert np.all(np.abs(got[:, :n].T - ref).max(axis=1) <= tol * np.abs(ref).max(axis=1)), "device rotor, blade-major"
+                cabi.check(lib.lcc_device_free(prs, None))
                 for ptr in (ps, pso, pms):
                     cabi.check(lib.lcc_device_free(ptr, None))
             cabi.check(lib.lcc_device_free(pm, None))
