@@ -15,7 +15,8 @@ One JSON line on stdout (rank 0):
   e2e         the same metric from HOST arrays through the drop-in Python API -- value = the reference's own call
               sequence MultivectorBatch.from_numpy(alg, x).sandwich(M).to_numpy() on a pinned NumPy array, H2D and D2H
               inside the timed region; `variants` adds the pageable-array run, the one-call MultivectorBatch.sandwich_numpy
-              and the C-ABI entry point lcc_host_sandwich behind it
+              and the C-ABI entry point lcc_host_sandwich behind it, plus the same points as compact (N, 3) xyz rows
+              (lcc_host_pga_points_sandwich: 24 bytes per point each way; a different data format, listed for comparison)
   roofline    algorithmic bytes / kernel time against the measured HBM peak (MEASURED_PEAKS.json); tensor-bound
               workloads against profiles/peaks_local.json (cuBLAS TF32 / FP64 measured with scripts/measure_peaks.py)
   cpu_baseline  the oracle port of the reference's Rust loop timed on this box's host cores (N = 1 only)
@@ -23,7 +24,8 @@ One JSON line on stdout (rank 0):
               its NCCL all-reduce every step, through lcc_shard_product_sum_async; at N > 1 also the same kernel without the
               collective and on one GPU of the job alone
   strong      BASELINE config 2 with 2^28 points IN TOTAL (2^28 / N per GPU)
-  secondary   the other BASELINE configs at full size on this rank's GPU (ms_per_step, roofline, parity, clocks each)
+  secondary   the other BASELINE configs at full size on this rank's GPU (ms_per_step, roofline, parity, clocks each);
+              config 5 (Cl(8,0,0) fixed-operand product) as K8 in both layouts and as the dense tensor-core GEMMs
 `--impl reference` times only the CPU implementation (bounded sample per step) and prints the same
 line shape with "impl": "reference" and the same `config` block.
 """
