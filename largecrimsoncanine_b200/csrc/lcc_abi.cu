@@ -202,10 +202,12 @@ lcc_status device_state(DeviceState **out) {
 }
 
 lcc_status resolve_stream(void *stream, cudaStream_t *out) {
-    if (stream) { *out = (cudaStream_t)stream; return LCC_OK; }
+    // the device state is set up on EVERY path, also when the caller brings its own stream: it configures the stream-ordered
+    // pool to keep freed blocks (release threshold), without which the scratch buffers of the entry points (batch sums,
+    // K8's unit counter, matrix builders) go back to the driver at every synchronisation and are re-mapped on the next call
     DeviceState *st = nullptr;
     LCC_TRY(device_state(&st));
-    *out = st->stream;
+    *out = stream ? (cudaStream_t)stream : st->stream;
     return LCC_OK;
 }
 
